@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: mLSTM chunkwise fwd+bwd (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = one forward + one backward of the chunkwise mLSTM over one batch of synthetic
+input: bf16, B=32 NH=4 S=1600 DH=64 chunk=64 per GPU (weak scaling: every rank runs the same
+per-GPU workload on its own data; the op has no cross-sample term, so there is no data-path
+collective -- SURVEY.md §8e).  Prints ONE JSON line (rank 0).
+
+Metric: algorithmic TFLOP/s = 14*L*d*(L+d) FLOP per chunk x chunks / time.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CFG = dict(B=32, NH=4, S=1600, DK=64, DV=64, L=64)
+WORKLOAD = "mlstm_chunkwise_fwbw bf16 B=32 NH=4 S=1600 DH=64 chunk=64 (BASELINE configs[1])"
+METRIC = "mLSTM chunkwise fwd+bwd TFLOP/s (algorithmic, 14*L*d*(L+d) per chunk)"
+N_SETS = 4  # rotating input sets: ~105 MB of inputs + ~105 MB of outputs per step >> 126 MB L2 over a rotation
+
+
+def flops_and_bytes(c, itemsize=2):
+    """Algorithmic FLOPs / bytes per step per GPU."""
+    nc = c["S"] // c["L"]
+    bh = c["B"] * c["NH"]
+    fwd = 4 * c["L"] * c["DK"] * c["DV"] + 2 * c["L"] ** 2 * (c["DK"] + c["DV"])
+    bwd = 10 * c["L"] * c["DK"] * c["DV"] + 2 * c["L"] ** 2 * (3 * c["DK"] + 2 * c["DV"])
+    tok = bh * c["S"]
+    qk, v = tok * c["DK"] * itemsize, tok * c["DV"] * itemsize
+    gate, vec32 = tok * itemsize, tok * 4
+    fw_bytes = 2 * qk + v + 2 * gate + v + 2 * vec32  # read q,k,v,i,f; write h,n_out,m_out
+    bw_bytes = 2 * qk + v + v + 2 * gate + 2 * vec32 + 2 * qk + v + 2 * gate  # read q,k,v,dh,i,f,n,m; write dq,dk,dv,di,df
+    return bh * nc * fwd, bh * nc * bwd, fw_bytes, bw_bytes
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops", 1590.0), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_baseline(sample_b=4, reps=3):
+    """Oracle port (native-torch formulation) in fp32 on the host cores, on a bounded sample."""
+    from oracle import mlstm_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    c = dict(CFG, B=sample_b)
+    inp = O.make_inputs(c["B"], c["NH"], c["S"], c["DK"], c["DV"], seed=0, dtype=torch.float32)
+    best = float("inf")
+    with torch.no_grad():
+        for r in range(reps + 1):
+            t0 = time.perf_counter()
+            O.fwbw(inp["q"], inp["k"], inp["v"], inp["i"], inp["f"], inp["dh"], chunk_size=c["L"])
+            dt = time.perf_counter() - t0
+            if r:
+                best = min(best, dt)
+    ff, fb, _, _ = flops_and_bytes(c, 4)
+    return {"value": (ff + fb) / best / 1e12, "unit": "TFLOP/s", "cores": cores, "kind": "port",
+            "sample": f"fp32 fwd+bwd of B={sample_b} (of 32) NH=4 S=1600 DH=64 chunk=64, best of {reps}, {best * 1e3:.1f} ms",
+            "seconds": best}
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU formulation (oracle port; the Python reference cannot
+    travel to the GPU box) on the host cores, same config / metric."""
+    if rank != 0:
+        return
+    from oracle import mlstm_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_b = 4
+    c = dict(CFG, B=sample_b)
+    inp = O.make_inputs(c["B"], c["NH"], c["S"], c["DK"], c["DV"], seed=0, dtype=torch.float32)
+    times = []
+    with torch.no_grad():
+        for s in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            O.fwbw(inp["q"], inp["k"], inp["v"], inp["i"], inp["f"], inp["dh"], chunk_size=c["L"])
+            if s >= args.warmup:
+                times.append(time.perf_counter() - t0)
+    ff, fb, _, _ = flops_and_bytes(c, 4)
+    dt = sum(times) / len(times)
+    val = (ff + fb) / dt / 1e12
+    sample = f"each step = fp32 fwd+bwd of B={sample_b} (of 32) NH=4 S=1600 DH=64 chunk=64 on host cores"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--kernel-impl", default="auto", choices=["auto", "exact", "tensor"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+
+    import __graft_entry__ as G
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 backend has no CPU fallback")
+    if local_rank == 0 and not os.path.exists(os.path.join(ROOT, "xlstm_yolo_clean_b200", "lib", "libmlstm_b200.so")):
+        G.build()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+    import xlstm_yolo_clean_b200 as pkg
+    from oracle import mlstm_oracle as O
+
+    pkg.set_default_impl(args.kernel_impl)
+    c = CFG
+    dt = torch.bfloat16
+    sets = []
+    for r in range(N_SETS):
+        inp = O.make_inputs(c["B"], c["NH"], c["S"], c["DK"], c["DV"], seed=1000 * rank + r, dtype=torch.float32)
+        sets.append({k: v.to(dt).to(dev) for k, v in inp.items()})
+    ff, fb, fw_bytes, bw_bytes = flops_and_bytes(c)
+
+    def step_device(s):
+        h, n_out, m_out, _ = pkg.mlstm_chunkwise_fw(s["q"], s["k"], s["v"], s["i"], s["f"], chunk_size=c["L"])
+        nfw = pkg.last_launch_count()
+        out = pkg.mlstm_chunkwise_bw(s["q"], s["k"], s["v"], s["i"], s["f"], n_out, m_out, s["dh"], chunk_size=c["L"])
+        return h, out, nfw + pkg.last_launch_count()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") -------------------------------------------------
+    for w in range(args.warmup):
+        step_device(sets[w % N_SETS])
+    sampler = ClockSampler(local_rank)
+    sync_all()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    e0.record()
+    for k in range(args.steps):
+        _, _, n = step_device(sets[k % N_SETS])
+        launches += n
+    e1.record()
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    value = world * (ff + fb) / (ms_step * 1e-3) / 1e12
+
+    # ---- per-phase kernel timing for the roofline (events on the launching stream) ------------
+    fw_ms, bw_ms = [], []
+    for k in range(min(args.steps, 20)):
+        s = sets[k % N_SETS]
+        a, b_, c_ = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record()
+        h, n_out, m_out, _ = pkg.mlstm_chunkwise_fw(s["q"], s["k"], s["v"], s["i"], s["f"], chunk_size=c["L"])
+        b_.record()
+        pkg.mlstm_chunkwise_bw(s["q"], s["k"], s["v"], s["i"], s["f"], n_out, m_out, s["dh"], chunk_size=c["L"])
+        c_.record()
+        torch.cuda.synchronize()
+        fw_ms.append(a.elapsed_time(b_))
+        bw_ms.append(b_.elapsed_time(c_))
+    fw_t, bw_t = statistics.median(fw_ms), statistics.median(bw_ms)
+    hbm_peak, tf_peak, peak_kind = peaks()
+    dom = ("bw", bw_bytes, bw_t) if bw_t >= fw_t else ("fw", fw_bytes, fw_t)
+    roof = {"bound": "hbm", "kernel": f"mlstm_b200_chunkwise_{dom[0]} (C-ABI call; host launch gaps included)",
+            "achieved": dom[1] / (dom[2] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            "frac": dom[1] / (dom[2] * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+            "algorithmic_bytes": dom[1], "fw_ms": fw_t, "bw_ms": bw_t,
+            "fw_gbs": fw_bytes / (fw_t * 1e-3) / 1e9, "bw_gbs": bw_bytes / (bw_t * 1e-3) / 1e9,
+            "tflops_frac_of_bf16_peak": (ff + fb) / ((fw_t + bw_t) * 1e-3) / 1e12 / tf_peak}
+
+    # ---- end to end through the public API with HOST buffers ----------------------------------
+    host = {k: v.cpu().pin_memory() for k, v in sets[0].items()}
+    names_in = ("q", "k", "v", "i", "f", "dh")
+    h2d = sum(host[k].numel() * host[k].element_size() for k in names_in)
+    out_host = None
+
+    def step_e2e():
+        nonlocal out_host
+        d = {k: host[k].to(dev, non_blocking=True) for k in names_in}
+        leaves = {k: d[k].requires_grad_(True) for k in ("q", "k", "v", "i", "f")}
+        h = pkg.mlstm_chunkwise__b200(**leaves, chunk_size=c["L"], eps=1e-6)
+        h.backward(d["dh"])
+        outs = [h.detach()] + [leaves[k].grad for k in ("q", "k", "v", "i", "f")]
+        if out_host is None:
+            out_host = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
+        for dst, src in zip(out_host, outs):
+            dst.copy_(src, non_blocking=True)
+        return sum(o.numel() * o.element_size() for o in outs)
+
+    for _ in range(3):
+        d2h = step_e2e()
+    sync_all()
+    e_steps = max(3, min(args.steps, 10))
+    e0.record()
+    for _ in range(e_steps):
+        step_e2e()
+    e1.record()
+    sync_all()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = world * (ff + fb) / (t.item() / e_steps * 1e-3) / 1e12
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "per_gpu": True, "kernel_impl": args.kernel_impl,
+                       "l2": f"{N_SETS} rotating input sets, >126 MB touched between reuses (no explicit flush)",
+                       "frac_of_bf16_peak": value / world / tf_peak},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": e2e_val, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e_steps},
+            "roofline": roof,
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,141 @@
+/*
+ * mlstm_b200.h -- C-ABI of the B200 (sm_100a) mLSTM chunkwise forward/backward.
+ *
+ * This is the drop-in boundary of the hot path.  The reference has no FFI of its
+ * own (it is pure Python); the entry points below are what a binding for this
+ * path replaces, one to one (paths relative to the reference root):
+ *
+ *   mlstm_b200_chunkwise_fw   <->  mlstm_chunkwise_fw
+ *                                  mlstm_kernels/torch/chunkwise/native/fw.py:224-318
+ *                                  (called from _mlstm_chunkwise_fwbw.forward,
+ *                                   mlstm_kernels/torch/chunkwise/native/fwbw.py:36-102)
+ *   mlstm_b200_chunkwise_bw   <->  mlstm_chunkwise_bw
+ *                                  mlstm_kernels/torch/chunkwise/native/bw.py:206-348
+ *                                  (called from _mlstm_chunkwise_fwbw.backward, fwbw.py:104-171)
+ *
+ * Conventions
+ *   - plain C: device pointers, element strides, sizes; no torch types.
+ *   - every call is asynchronous on the cudaStream_t passed in (as void*), holds no
+ *     global mutable state besides a per-thread error string, and allocates no
+ *     device memory: scratch is a caller-owned workspace whose size is returned by
+ *     mlstm_b200_workspace_bytes().
+ *   - return value: 0 on success, a negative MLSTM_B200_E* code for invalid
+ *     arguments, a positive cudaError_t for CUDA failures.  Never exits / throws.
+ *   - there is NO CPU fallback: on a machine without an sm_100 device every compute
+ *     entry point returns an error.
+ *
+ * Tensor layout (same as the reference API, native/fwbw.py:228-243):
+ *   q, k  (B, NH, S, DHQK)   v, h, dh (B, NH, S, DHHV)   i, f (B, NH, S)
+ *   given as a base pointer plus ELEMENT strides in that index order; the innermost
+ *   stride of q/k/v/dh must be 1 (the BSHD-strided views MatrixLSTMCell.forward
+ *   creates, vision_lstm2.py:718-727, are consumed without a copy).
+ *   States C (B, NH, DHQK, DHHV), n (B, NH, DHQK), m (B, NH) are contiguous fp32.
+ */
+#ifndef MLSTM_B200_H_
+#define MLSTM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLSTM_B200_ABI_VERSION 1
+
+/* element types of q/k/v/i/f/h and of the gradients */
+enum { MLSTM_B200_F32 = 0, MLSTM_B200_BF16 = 1, MLSTM_B200_F16 = 2 };
+
+/* error codes (negative); positive return values are cudaError_t */
+enum {
+  MLSTM_B200_OK = 0,
+  MLSTM_B200_EINVAL = -1,      /* bad shape / stride / null pointer */
+  MLSTM_B200_EUNSUPPORTED = -2,/* shape or dtype outside what the kernels cover */
+  MLSTM_B200_EWORKSPACE = -3,  /* workspace too small */
+  MLSTM_B200_ENODEVICE = -4    /* no sm_100 device / driver entry point missing */
+};
+
+/* kernel families; AUTO picks tensor-core (tcgen05) kernels for 16-bit inputs with
+ * supported head dims and the exact fp32 FFMA kernels otherwise.  This selects between
+ * precision modes of the SAME sm_100a path, not between backends. */
+enum { MLSTM_B200_IMPL_AUTO = 0, MLSTM_B200_IMPL_EXACT = 1, MLSTM_B200_IMPL_TENSOR = 2 };
+
+typedef struct mlstm_b200_tensor {
+  void* ptr;         /* device pointer (may be NULL for optional tensors) */
+  int64_t stride[4]; /* element strides, index order as documented above; unused = 0 */
+} mlstm_b200_tensor;
+
+typedef struct mlstm_b200_shape {
+  int32_t B, NH, S, DHQK, DHHV;
+  int32_t chunk_size; /* S % chunk_size == 0 is required (native/fw.py:252-254) */
+  int32_t dtype;      /* MLSTM_B200_F32 / BF16 / F16 */
+  int32_t impl;       /* MLSTM_B200_IMPL_* */
+  float eps;
+  float qk_scale;     /* <= 0 selects DHQK^-0.5 (native/fw.py:263-264) */
+} mlstm_b200_shape;
+
+typedef struct mlstm_b200_fw_args {
+  mlstm_b200_shape shape;
+  /* inputs */
+  mlstm_b200_tensor q, k, v, i, f;
+  const float* c_initial; /* optional, all three or none */
+  const float* n_initial;
+  const float* m_initial;
+  /* outputs */
+  mlstm_b200_tensor h;    /* dtype, strides given (contiguous BHSD is the usual case) */
+  float* n_out;           /* (B, NH, S) fp32: max(|den|, exp(-m)) saved for backward */
+  float* m_out;           /* (B, NH, S) fp32: per-token stabiliser saved for backward */
+  float* c_last;          /* optional last states, all three or none */
+  float* n_last;
+  float* m_last;
+  void* workspace;
+  size_t workspace_bytes;
+} mlstm_b200_fw_args;
+
+typedef struct mlstm_b200_bw_args {
+  mlstm_b200_shape shape;
+  /* forward inputs and saved vectors */
+  mlstm_b200_tensor q, k, v, i, f;
+  const float* c_initial;
+  const float* n_initial;
+  const float* m_initial;
+  const float* n_out;
+  const float* m_out;
+  /* incoming gradients */
+  mlstm_b200_tensor dh;
+  const float* dc_last;   /* optional (B, NH, DHQK, DHHV) */
+  /* outputs */
+  mlstm_b200_tensor dq, dk, dv; /* dtype */
+  mlstm_b200_tensor di, df;     /* dtype, (B, NH, S) */
+  float* dc_initial;            /* optional; written iff non-NULL */
+  void* workspace;
+  size_t workspace_bytes;
+} mlstm_b200_bw_args;
+
+/* ABI version of the loaded library (== MLSTM_B200_ABI_VERSION it was built with). */
+int mlstm_b200_abi_version(void);
+
+/* Human-readable description of the last error on the calling thread ("" if none). */
+const char* mlstm_b200_last_error(void);
+
+/* Bytes of scratch the forward (backward = 0) or backward (backward = 1) needs. */
+size_t mlstm_b200_workspace_bytes(const mlstm_b200_shape* shape, int backward);
+
+/* 1 if the tensor-core (tcgen05) kernels cover this shape/dtype, else 0. */
+int mlstm_b200_tensor_path_supported(const mlstm_b200_shape* shape);
+
+/* Forward: h, n_out, m_out and optionally the last (C, n, m) states. */
+int mlstm_b200_chunkwise_fw(const mlstm_b200_fw_args* args, void* cuda_stream);
+
+/* Backward (n_out and all max states are constants, native/bw.py:44-47):
+ * dq, dk, dv, di, df and optionally dC_initial. */
+int mlstm_b200_chunkwise_bw(const mlstm_b200_bw_args* args, void* cuda_stream);
+
+/* Number of kernels the last fw / bw call on this thread launched (for bench.py's
+ * gpu_launches claim). */
+int mlstm_b200_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MLSTM_B200_H_ */

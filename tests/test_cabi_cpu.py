@@ -1,0 +1,129 @@
+"""CPU-only checks of the boundary: the C-ABI library loads, exports every symbol the header
+declares, and the host shim refuses to run without a GPU (no fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import __graft_entry__ as G
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    G.build()
+    import xlstm_yolo_clean_b200 as pkg
+
+    return pkg.load_library()
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "mlstm_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mlstm_b200_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_exports_match_header(lib):
+    from xlstm_yolo_clean_b200 import _cabi
+
+    names = _header_functions()
+    assert set(names) == set(_cabi.EXPORTS)
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_abi_version_and_error_string(lib):
+    assert lib.mlstm_b200_abi_version() == 1
+    assert isinstance(lib.mlstm_b200_last_error(), bytes)
+
+
+def test_struct_sizes_match_header(lib):
+    """Compile a tiny C program against the header and compare sizeof with the ctypes mirror."""
+    import subprocess
+    import tempfile
+
+    from xlstm_yolo_clean_b200 import _cabi
+
+    code = '#include <stdio.h>\n#include "mlstm_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n",' \
+           "sizeof(mlstm_b200_tensor),sizeof(mlstm_b200_shape),sizeof(mlstm_b200_fw_args),sizeof(mlstm_b200_bw_args));}"
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "s.c")
+        open(c, "w").write(code)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", os.path.join(d, "s")])
+        out = subprocess.check_output([os.path.join(d, "s")]).split()
+    sizes = [int(x) for x in out]
+    assert sizes == [ctypes.sizeof(_cabi.Tensor), ctypes.sizeof(_cabi.Shape), ctypes.sizeof(_cabi.FwArgs),
+                     ctypes.sizeof(_cabi.BwArgs)]
+
+
+def test_workspace_query_needs_no_gpu(lib):
+    from xlstm_yolo_clean_b200 import _cabi
+
+    s = _cabi.Shape()
+    s.B, s.NH, s.S, s.DHQK, s.DHHV, s.chunk_size, s.dtype, s.impl = 2, 4, 256, 64, 64, 64, _cabi.F32, _cabi.IMPL_EXACT
+    fw = lib.mlstm_b200_workspace_bytes(ctypes.byref(s), 0)
+    bw = lib.mlstm_b200_workspace_bytes(ctypes.byref(s), 1)
+    assert 0 < fw < bw
+
+
+def test_cpu_tensors_are_refused():
+    import xlstm_yolo_clean_b200 as pkg
+
+    q = torch.randn(1, 1, 64, 16)
+    g = torch.randn(1, 1, 64)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        pkg.mlstm_chunkwise__b200(q=q, k=q, v=q, i=g, f=g)
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    from xlstm_yolo_clean_b200 import _cabi
+
+    with pytest.raises(_cabi.LibraryMissing):
+        _cabi.load_library(str(tmp_path / "nope.so"))
+
+
+def test_compute_call_without_device_returns_error(lib):
+    """On a box without a GPU the compute entry points must return an error, never compute."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from xlstm_yolo_clean_b200 import _cabi
+
+    a = _cabi.FwArgs()
+    a.shape.B, a.shape.NH, a.shape.S, a.shape.DHQK, a.shape.DHHV, a.shape.chunk_size = 1, 1, 64, 16, 16, 64
+    dummy = ctypes.create_string_buffer(64)
+    p = ctypes.addressof(dummy)
+    for t in (a.q, a.k, a.v, a.h, a.i, a.f):
+        t.ptr = p
+        t.stride[3] = 1
+    a.n_out = a.m_out = p
+    st = lib.mlstm_b200_chunkwise_fw(ctypes.byref(a), None)
+    assert st != 0
+    assert lib.mlstm_b200_last_error() != b""
+
+
+def test_registry_drop_in():
+    """register() makes 'chunkwise--b200' resolvable through the reference's get_mlstm_kernel
+    (only where the reference package is importable, i.e. the build container)."""
+    import sys
+
+    if not os.path.isdir("/root/reference/mlstm_kernels"):
+        pytest.skip("reference package not present on this box")
+    sys.path.insert(0, "/root/reference")
+    sys.dont_write_bytecode = True
+    try:
+        import xlstm_yolo_clean_b200 as pkg
+        from mlstm_kernels.torch import get_mlstm_kernel
+        from mlstm_kernels.torch.backend_module import mLSTMBackend, mLSTMBackendConfig
+
+        full = pkg.register()
+        assert get_mlstm_kernel(full) is pkg.mlstm_chunkwise__b200
+        be = mLSTMBackend(mLSTMBackendConfig(chunkwise_kernel=full, mode="train_with_padding", return_last_states=False))
+        q = torch.randn(1, 2, 100, 16)
+        g = torch.randn(1, 2, 100)
+        with pytest.raises(RuntimeError, match="no CPU path"):  # routed to our kernel, which refuses CPU
+            be(q=q, k=q, v=q, i=g, f=g)
+    finally:
+        sys.path.remove("/root/reference")

@@ -1,0 +1,279 @@
+"""Host side of the B200 mLSTM chunkwise backend (Python/PyTorch above the C-ABI).
+
+Mirrors the reference's operator interface for this path so it is a drop-in:
+
+  * ``mlstm_chunkwise__b200`` has the signature, return convention, dtype rule and error
+    behaviour of ``mlstm_chunkwise__native_custbw`` (mlstm_kernels/torch/chunkwise/native/fwbw.py:228-263);
+  * ``mlstm_chunkwise_fw`` / ``mlstm_chunkwise_bw`` correspond to native/fw.py:224-318 and
+    native/bw.py:206-348 and are thin wrappers over the two C-ABI calls;
+  * ``register`` / ``patch_model`` hook it into mlstm_kernels.torch.chunkwise.registry and
+    ``MatrixLSTMCell`` (ultralytics/nn/modules/vision_lstm/vision_lstm2.py:623-770).
+
+PyTorch is used for device memory, streams and autograd plumbing only.  There is no CPU or
+eager fallback: CPU tensors or a missing library raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import torch
+from torch.amp import custom_bwd, custom_fwd
+
+from . import _cabi
+
+KERNEL_NAME = "b200"  # registry key -> "chunkwise--b200"
+
+_DTYPES = {torch.float32: _cabi.F32, torch.bfloat16: _cabi.BF16, torch.float16: _cabi.F16}
+_default_impl = _cabi.IMPL_AUTO
+_last_launches = 0
+
+
+def set_default_impl(name: str) -> None:
+    """'auto' | 'exact' (fp32 FFMA kernels) | 'tensor' (tcgen05 kernels, error if unsupported)."""
+    global _default_impl
+    _default_impl = {"auto": _cabi.IMPL_AUTO, "exact": _cabi.IMPL_EXACT, "tensor": _cabi.IMPL_TENSOR}[name]
+
+
+def last_launch_count() -> int:
+    """Kernels launched by the most recent forward or backward call on this thread."""
+    return _cabi.load_library().mlstm_b200_last_launch_count()
+
+
+def _tensor(t: Optional[torch.Tensor]) -> _cabi.Tensor:
+    out = _cabi.Tensor()
+    if t is None:
+        out.ptr = None
+        return out
+    out.ptr = t.data_ptr()
+    for d, s in enumerate(t.stride()):
+        out.stride[d] = s
+    return out
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _shape(q, v, chunk_size, eps, impl, qk_scale=None) -> _cabi.Shape:
+    B, NH, S, DK = q.shape
+    s = _cabi.Shape()
+    s.B, s.NH, s.S, s.DHQK, s.DHHV = B, NH, S, DK, v.shape[-1]
+    s.chunk_size = int(chunk_size)
+    s.dtype = _DTYPES[q.dtype]
+    s.impl = _default_impl if impl is None else impl
+    s.eps = float(eps)
+    s.qk_scale = -1.0 if qk_scale is None else float(qk_scale)
+    return s
+
+
+def tensor_path_supported(B, NH, S, DK, DV, dtype=torch.bfloat16, chunk_size=64) -> bool:
+    s = _cabi.Shape()
+    s.B, s.NH, s.S, s.DHQK, s.DHHV, s.chunk_size, s.dtype = B, NH, S, DK, DV, chunk_size, _DTYPES[dtype]
+    return bool(_cabi.load_library().mlstm_b200_tensor_path_supported(C.byref(s)))
+
+
+def _rowmajor_last(t: torch.Tensor) -> torch.Tensor:
+    """The kernels take any batch/head/token strides but need a unit innermost stride."""
+    return t if t.stride(-1) == 1 else t.contiguous()
+
+
+def _check_inputs(q, k, v, i, f):
+    for name, t in (("q", q), ("k", k), ("v", v), ("i", i), ("f", f)):
+        if not t.is_cuda:
+            raise RuntimeError(f"mlstm_chunkwise__b200: {name} is on {t.device}; this backend has no CPU path")
+    if q.dtype not in _DTYPES:
+        raise RuntimeError(f"unsupported dtype {q.dtype}")
+    B, NH, S, DK = q.shape
+    assert k.shape == (B, NH, S, DK), f"k has wrong shape {tuple(k.shape)}"
+    assert v.shape[:3] == (B, NH, S), f"v has wrong shape {tuple(v.shape)}"
+    assert i.shape == (B, NH, S) and f.shape == (B, NH, S), "i / f must be (B, NH, S)"
+
+
+def _state_f32(t, shape):
+    if t is None:
+        return None
+    return t.detach().to(torch.float32).reshape(shape).contiguous()
+
+
+def mlstm_chunkwise_fw(q, k, v, i, f, c_initial=None, n_initial=None, m_initial=None, qk_scale=None,
+                       return_last_states=False, chunk_size=64, eps=1e-6, impl=None):
+    """C-ABI forward.  Returns h, n_out, m_out, last_states-or-None (states are fp32)."""
+    global _last_launches
+    lib = _cabi.load_library()
+    _check_inputs(q, k, v, i, f)
+    B, NH, S, DK = q.shape
+    DV = v.shape[-1]
+    assert S % chunk_size == 0, f"Sequence length {S} is not divisible by chunk size {chunk_size}."
+    q, k, v = (_rowmajor_last(t) for t in (q, k, v))
+    i = i if i.dtype == q.dtype else i.to(q.dtype)
+    f = f if f.dtype == q.dtype else f.to(q.dtype)
+    k = k if k.dtype == q.dtype else k.to(q.dtype)
+    v = v if v.dtype == q.dtype else v.to(q.dtype)
+    dev = q.device
+    c0, n0, m0 = _state_f32(c_initial, (B, NH, DK, DV)), _state_f32(n_initial, (B, NH, DK)), _state_f32(m_initial, (B, NH))
+    if c0 is not None or n0 is not None or m0 is not None:
+        c0 = torch.zeros(B, NH, DK, DV, device=dev) if c0 is None else c0
+        n0 = torch.zeros(B, NH, DK, device=dev) if n0 is None else n0
+        m0 = torch.zeros(B, NH, device=dev) if m0 is None else m0
+    with torch.cuda.device(dev):
+        h = torch.empty(B, NH, S, DV, dtype=q.dtype, device=dev)
+        n_out = torch.empty(B, NH, S, dtype=torch.float32, device=dev)
+        m_out = torch.empty(B, NH, S, dtype=torch.float32, device=dev)
+        last = None
+        if return_last_states:
+            last = (torch.empty(B, NH, DK, DV, dtype=torch.float32, device=dev),
+                    torch.empty(B, NH, DK, dtype=torch.float32, device=dev),
+                    torch.empty(B, NH, 1, dtype=torch.float32, device=dev))
+        a = _cabi.FwArgs()
+        a.shape = _shape(q, v, chunk_size, eps, impl, qk_scale)
+        ws_bytes = lib.mlstm_b200_workspace_bytes(C.byref(a.shape), 0)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        a.q, a.k, a.v, a.i, a.f, a.h = (_tensor(t) for t in (q, k, v, i, f, h))
+        a.c_initial, a.n_initial, a.m_initial = _ptr(c0), _ptr(n0), _ptr(m0)
+        a.n_out, a.m_out = n_out.data_ptr(), m_out.data_ptr()
+        if last is not None:
+            a.c_last, a.n_last, a.m_last = (t.data_ptr() for t in last)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws_bytes
+        st = lib.mlstm_b200_chunkwise_fw(C.byref(a), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _cabi.check(st, "mlstm_b200_chunkwise_fw")
+    return h, n_out, m_out, last
+
+
+def mlstm_chunkwise_bw(q, k, v, i, f, n_out, m_out, dh, c_initial=None, n_initial=None, m_initial=None,
+                       dc_last=None, qk_scale=None, chunk_size=64, eps=1e-6, impl=None, want_dc_initial=False):
+    """C-ABI backward.  Returns dq, dk, dv, di, df, dc_initial-or-None (fp32)."""
+    lib = _cabi.load_library()
+    _check_inputs(q, k, v, i, f)
+    B, NH, S, DK = q.shape
+    DV = v.shape[-1]
+    q, k, v = (_rowmajor_last(t) for t in (q, k, v))
+    dh = _rowmajor_last(dh if dh.dtype == q.dtype else dh.to(q.dtype))
+    i = i if i.dtype == q.dtype else i.to(q.dtype)
+    f = f if f.dtype == q.dtype else f.to(q.dtype)
+    dev = q.device
+    c0, n0, m0 = _state_f32(c_initial, (B, NH, DK, DV)), _state_f32(n_initial, (B, NH, DK)), _state_f32(m_initial, (B, NH))
+    if c0 is not None or n0 is not None or m0 is not None:
+        c0 = torch.zeros(B, NH, DK, DV, device=dev) if c0 is None else c0
+        n0 = torch.zeros(B, NH, DK, device=dev) if n0 is None else n0
+        m0 = torch.zeros(B, NH, device=dev) if m0 is None else m0
+    dcl = _state_f32(dc_last, (B, NH, DK, DV))
+    with torch.cuda.device(dev):
+        dq = torch.empty(B, NH, S, DK, dtype=q.dtype, device=dev)
+        dk = torch.empty(B, NH, S, DK, dtype=q.dtype, device=dev)
+        dv = torch.empty(B, NH, S, DV, dtype=q.dtype, device=dev)
+        di = torch.empty(B, NH, S, dtype=q.dtype, device=dev)
+        df = torch.empty(B, NH, S, dtype=q.dtype, device=dev)
+        dc0 = torch.empty(B, NH, DK, DV, dtype=torch.float32, device=dev) if want_dc_initial else None
+        a = _cabi.BwArgs()
+        a.shape = _shape(q, v, chunk_size, eps, impl, qk_scale)
+        ws_bytes = lib.mlstm_b200_workspace_bytes(C.byref(a.shape), 1)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        a.q, a.k, a.v, a.i, a.f, a.dh = (_tensor(t) for t in (q, k, v, i, f, dh))
+        a.c_initial, a.n_initial, a.m_initial = _ptr(c0), _ptr(n0), _ptr(m0)
+        a.n_out, a.m_out = n_out.data_ptr(), m_out.data_ptr()
+        a.dc_last = _ptr(dcl)
+        a.dq, a.dk, a.dv, a.di, a.df = (_tensor(t) for t in (dq, dk, dv, di, df))
+        a.dc_initial = _ptr(dc0)
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws_bytes
+        st = lib.mlstm_b200_chunkwise_bw(C.byref(a), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _cabi.check(st, "mlstm_b200_chunkwise_bw")
+    return dq, dk, dv, di, df, dc0
+
+
+def _make_function(autocast_kernel_dtype: torch.dtype):
+    class _MlstmChunkwiseB200(torch.autograd.Function):
+        """autograd.Function with the contract of _mlstm_chunkwise_fwbw (native/fwbw.py:35-171)."""
+
+        @staticmethod
+        @custom_fwd(device_type="cuda", cast_inputs=autocast_kernel_dtype)
+        def forward(ctx, q, k, v, i, f, c_initial, n_initial, m_initial, return_last_states, chunk_size, eps):
+            h, n_out, m_out, last = mlstm_chunkwise_fw(
+                q, k, v, i, f, c_initial, n_initial, m_initial, return_last_states=return_last_states,
+                chunk_size=chunk_size, eps=eps)
+            ctx.save_for_backward(q, k, v, i, f, c_initial, n_initial, m_initial, n_out, m_out)
+            ctx.chunk_size, ctx.eps = chunk_size, eps
+            if last is None:
+                return h, None, None, None
+            # native kernels hand states back in the input dtype (native/fw.py:53-62)
+            return h, last[0].to(q.dtype), last[1].to(q.dtype), last[2].to(q.dtype)
+
+        @staticmethod
+        @custom_bwd(device_type="cuda")
+        def backward(ctx, dh, dc_last, dn_last, dm_last):
+            q, k, v, i, f, c0, n0, m0, n_out, m_out = ctx.saved_tensors
+            dq, dk, dv, di, df, dc0 = mlstm_chunkwise_bw(
+                q, k, v, i, f, n_out, m_out, dh, c0, n0, m0, dc_last=dc_last, chunk_size=ctx.chunk_size, eps=ctx.eps,
+                want_dc_initial=c0 is not None)
+            # dn_last / dm_last are ignored and dN/dM_initial are zeros, as in native/bw.py:329-337
+            return (dq, dk, dv, di, df,
+                    None if c0 is None else dc0.to(c0.dtype),
+                    None if n0 is None else torch.zeros_like(n0),
+                    None if m0 is None else torch.zeros_like(m0),
+                    None, None, None)
+
+    return _MlstmChunkwiseB200
+
+
+_FUNCTIONS = {dt: _make_function(dt) for dt in (torch.float32, torch.float16, torch.bfloat16)}
+
+
+def mlstm_chunkwise__b200(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    i: torch.Tensor,
+    f: torch.Tensor,
+    c_initial: torch.Tensor = None,
+    n_initial: torch.Tensor = None,
+    m_initial: torch.Tensor = None,
+    return_last_states: bool = False,
+    eps: float = 1e-6,
+    chunk_size: int = 64,
+    autocast_kernel_dtype: torch.dtype = torch.bfloat16,
+    **kwargs,
+):
+    """Drop-in for ``mlstm_chunkwise__native_custbw`` (native/fwbw.py:228-263).
+
+    Returns h (B, NH, S, DHHV) or (h, (C_last, n_last, m_last)) when ``return_last_states``.
+    Extra keyword arguments are ignored like ``native_autograd`` does (fwbw.py:204).
+    """
+    if autocast_kernel_dtype not in _FUNCTIONS:
+        raise ValueError(f"Unsupported kernel dtype {autocast_kernel_dtype}.")
+    fn = _FUNCTIONS[autocast_kernel_dtype]
+    h, c_last, n_last, m_last = fn.apply(q, k, v, i, f, c_initial, n_initial, m_initial, bool(return_last_states),
+                                         int(chunk_size), float(eps))
+    if return_last_states:
+        return h, (c_last, n_last, m_last)
+    return h
+
+
+def register(name: str = KERNEL_NAME) -> str:
+    """Insert the kernel into the reference registry (mlstm_kernels/torch/chunkwise/__init__.py:9-15).
+
+    Returns the full kernel name usable as ``mLSTMBackendConfig(chunkwise_kernel=...)``.
+    ``mlstm_kernels`` must be importable (it is the reference's package, not part of this repo).
+    """
+    from mlstm_kernels.torch.chunkwise import registry  # noqa: WPS433 (reference package)
+
+    registry[name] = mlstm_chunkwise__b200
+    return f"chunkwise--{name}"
+
+
+def patch_model(model: torch.nn.Module, name: str = KERNEL_NAME, mode: str = "train_with_padding") -> int:
+    """Point ``gpu_backend`` of every MatrixLSTMCell (vision_lstm2.py:685-697) at the B200 kernel.
+
+    Returns the number of cells patched.
+    """
+    from mlstm_kernels.torch.backend_module import mLSTMBackend, mLSTMBackendConfig
+
+    full = register(name)
+    n = 0
+    for mod in model.modules():
+        if hasattr(mod, "gpu_backend") and hasattr(mod, "cpu_backend"):
+            mod.gpu_backend = mLSTMBackend(mLSTMBackendConfig(
+                chunkwise_kernel=full, sequence_kernel="native_sequence__native", step_kernel="native", mode=mode,
+                return_last_states=False, chunk_size=64, eps=1e-6, autocast_kernel_dtype="bfloat16"))
+            n += 1
+    return n
