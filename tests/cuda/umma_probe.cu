@@ -1,0 +1,167 @@
+// Descriptor probe for the tcgen05 building blocks the mLSTM kernels rely on (run on a B200):
+// TMA 128B-swizzled loads, K-/MN-major UMMA operands, M=64 and M=128 TMEM layouts, manual
+// swizzled operand writes and a TMA store.  Prints one PASS/FAIL line per variant.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -o umma_probe umma_probe.cu
+#include <cuda_bf16.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <math.h>
+#include <vector>
+
+#include "../../xlstm_yolo_clean_b200/csrc/sm100.cuh"
+
+using namespace sm100;
+typedef __nv_bfloat16 bf16;
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); return 1; } } while (0)
+
+// A: K-major -> global [M][K]; MN-major -> global [K][M].  Same for B with N.
+template <int M, int N, int K, bool A_MN, bool B_MN, bool MANUAL_A, bool TMA_OUT>
+__global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap mapA,
+                                             const __grid_constant__ CUtensorMap mapB,
+                                             const __grid_constant__ CUtensorMap mapO, const bf16* __restrict__ gA,
+                                             float* __restrict__ out, bf16* __restrict__ out16) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                      // M*K*2 bytes
+  uint8_t* sB = sA + M * K * 2;            // N*K*2 bytes
+  uint8_t* sO = sB + N * K * 2;            // 128 x 64 bf16 staging for the TMA store
+  __shared__ uint64_t bar_full, bar_mma;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    mbar_init(&bar_full, 1);
+    mbar_init(&bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc<128>(&tmem_base_s);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+
+  if (tid == 0) {
+    uint32_t bytes = N * K * 2 + (MANUAL_A ? 0 : M * K * 2);
+    mbar_expect_tx(&bar_full, bytes);
+    if (!MANUAL_A) {
+      if (A_MN) { for (int mb = 0; mb < M / 64; ++mb) tma_load_4d(sA + mb * K * 128, &mapA, &bar_full, mb * 64, 0, 0, 0); }
+      else      { for (int kb = 0; kb < K / 64; ++kb) tma_load_4d(sA + kb * M * 128, &mapA, &bar_full, kb * 64, 0, 0, 0); }
+    }
+    if (B_MN) { for (int nb = 0; nb < N / 64; ++nb) tma_load_4d(sB + nb * K * 128, &mapB, &bar_full, nb * 64, 0, 0, 0); }
+    else      { for (int kb = 0; kb < K / 64; ++kb) tma_load_4d(sB + kb * N * 128, &mapB, &bar_full, kb * 64, 0, 0, 0); }
+  }
+  if (MANUAL_A) {  // K-major A written by threads with the swizzle formula (row = thread)
+    static_assert(!MANUAL_A || (!A_MN && M == 128), "manual A: K-major, M=128");
+    for (int c = 0; c < K; ++c) {
+      *(bf16*)(sA + (c / 64) * M * 128 + swz128(tid, c % 64)) = gA[tid * K + c];
+    }
+    fence_proxy_async_smem();
+  }
+  __syncthreads();
+  mbar_wait(&bar_full, 0, 101);
+  tc_fence_after_sync();
+
+  if (warp == 0 && elect_one()) {
+    constexpr uint32_t idesc = umma_idesc(M, N, A_MN, B_MN, true);
+    for (int kk = 0; kk < K / 16; ++kk) {
+      uint64_t ad, bd;
+      if (A_MN) ad = umma_smem_desc(smem_u32(sA) + kk * 2048, K * 128, 1024);
+      else      ad = umma_smem_desc(smem_u32(sA) + (kk / 4) * M * 128 + (kk % 4) * 32, 0, 1024);
+      if (B_MN) bd = umma_smem_desc(smem_u32(sB) + kk * 2048, K * 128, 1024);
+      else      bd = umma_smem_desc(smem_u32(sB) + (kk / 4) * N * 128 + (kk % 4) * 32, 0, 1024);
+      umma_f16(tmem, ad, bd, idesc, kk > 0);
+    }
+    umma_commit(&bar_mma);
+  }
+  __syncwarp();
+  mbar_wait(&bar_mma, 0, 102);
+  tc_fence_after_sync();
+
+  // read back: M=128 -> lane = row; M=64 -> row r lives in lane (r%16) + 32*(r/16)
+  int row = (M == 128) ? tid : (lane < 16 ? warp * 16 + lane : -1);
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    float v[32];
+    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    if (row >= 0) {
+      for (int j = 0; j < 32; ++j) {
+        out[row * N + c0 + j] = v[j];
+        if (TMA_OUT && c0 + j < 64) *(bf16*)(sO + swz128(row, c0 + j)) = __float2bfloat16_rn(v[j]);
+      }
+    }
+  }
+  if (TMA_OUT) {
+    fence_proxy_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      tma_store_4d(&mapO, sO, 0, 0, 0, 0);
+      tma_store_commit();
+      tma_store_wait_all<0>();
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<128>(tmem);
+}
+
+static float frand() { return (float)(rand() % 2001 - 1000) / 1000.f; }
+
+template <int M, int N, int K, bool A_MN, bool B_MN, bool MANUAL_A, bool TMA_OUT>
+int run(const char* name) {
+  std::vector<bf16> hA(M * K), hB(N * K);
+  std::vector<float> fA(M * K), fB(N * K);  // logical A[m][k], B[n][k]
+  for (int m = 0; m < M; ++m) for (int k = 0; k < K; ++k) { bf16 x = __float2bfloat16(frand()); fA[m * K + k] = __bfloat162float(x); hA[A_MN ? k * M + m : m * K + k] = x; }
+  for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) { bf16 x = __float2bfloat16(frand()); fB[n * K + k] = __bfloat162float(x); hB[B_MN ? k * N + n : n * K + k] = x; }
+  bf16 *dA, *dB, *dO16; float* dO;
+  CK(cudaMalloc(&dA, M * K * 2)); CK(cudaMalloc(&dB, N * K * 2)); CK(cudaMalloc(&dO, M * N * 4)); CK(cudaMalloc(&dO16, 128 * 64 * 2));
+  CK(cudaMemcpy(dA, hA.data(), M * K * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, hB.data(), N * K * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dO, 0xff, M * N * 4)); CK(cudaMemset(dO16, 0, 128 * 64 * 2));
+  CUtensorMap mA, mB, mO;
+  int rA = A_MN ? sm100_host::make_map_bhsd(&mA, dA, true, 1, 1, K, M, (int64_t)K * M, (int64_t)K * M, M, K)
+                : sm100_host::make_map_bhsd(&mA, dA, true, 1, 1, M, K, (int64_t)K * M, (int64_t)K * M, K, M);
+  int rB = B_MN ? sm100_host::make_map_bhsd(&mB, dB, true, 1, 1, K, N, (int64_t)K * N, (int64_t)K * N, N, K)
+                : sm100_host::make_map_bhsd(&mB, dB, true, 1, 1, N, K, (int64_t)K * N, (int64_t)K * N, K, N);
+  int rO = sm100_host::make_map_bhsd(&mO, dO16, true, 1, 1, 128, 64, 128 * 64, 128 * 64, 64, 128);
+  if (rA || rB || rO) { printf("%s: tensor map encode failed %d %d %d\n", name, rA, rB, rO); return 1; }
+  size_t smem = (size_t)M * K * 2 + (size_t)N * K * 2 + 128 * 128 + 2048;
+  auto kern = probe<M, N, K, A_MN, B_MN, MANUAL_A, TMA_OUT>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int* hdbg = nullptr; int* ddbg = nullptr;
+  CK(cudaHostAlloc(&hdbg, 64, cudaHostAllocMapped)); hdbg[0] = 0; hdbg[1] = 0;
+  CK(cudaHostGetDevicePointer(&ddbg, hdbg, 0));
+  CK(cudaMemcpyToSymbol(g_dbg, &ddbg, sizeof(ddbg)));
+  kern<<<1, 128, smem>>>(mA, mB, mO, dA, dO, dO16);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("%s: FAIL kernel error %s (wait tag %d, thread %d)\n", name, cudaGetErrorString(e), hdbg[0], hdbg[1]); return 2; }
+  std::vector<float> hO(M * N); std::vector<bf16> hO16(128 * 64);
+  CK(cudaMemcpy(hO.data(), dO, M * N * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(hO16.data(), dO16, 128 * 64 * 2, cudaMemcpyDeviceToHost));
+  double maxerr = 0, maxerr16 = 0;
+  for (int m = 0; m < M; ++m) for (int n = 0; n < N; ++n) {
+    double ref = 0; for (int k = 0; k < K; ++k) ref += (double)fA[m * K + k] * fB[n * K + k];
+    double d = fabs(ref - hO[m * N + n]); if (!(d <= maxerr)) maxerr = d;  // NaN-propagating
+    if (TMA_OUT && n < 64) { double d16 = fabs(ref - __bfloat162float(hO16[m * 64 + n])); if (!(d16 <= maxerr16)) maxerr16 = d16; }
+  }
+  bool ok = maxerr < 1e-2 && (!TMA_OUT || maxerr16 < 0.3);
+  printf("%s: %s  max|err|=%.3e%s\n", name, ok ? "PASS" : "FAIL", maxerr, TMA_OUT ? (maxerr16 < 0.3 ? "  tma_store PASS" : "  tma_store FAIL") : "");
+  cudaFree(dA); cudaFree(dB); cudaFree(dO); cudaFree(dO16);
+  return ok ? 0 : 3;
+}
+
+int main() {
+  setvbuf(stdout, NULL, _IONBF, 0);
+  int bad = 0;
+  bad += run<128, 128, 64, false, false, false, false>("S=QK^T      M128 N128 K64  A:K  B:K ") != 0;
+  bad += run<128, 64, 128, false, true, false, true>("PV          M128 N64  K128 A:K  B:MN +tma_store") != 0;
+  bad += run<128, 64, 128, false, true, true, false>("PV manualA  M128 N64  K128 A:K* B:MN") != 0;
+  bad += run<128, 64, 64, false, true, false, false>("QC          M128 N64  K64  A:K  B:MN") != 0;
+  bad += run<64, 64, 128, true, true, false, false>("dC=K^TV     M64  N64  K128 A:MN B:MN") != 0;
+  bad += run<128, 64, 128, true, true, false, false>("dS^T Q      M128 N64  K128 A:MN B:MN") != 0;
+  bad += run<128, 64, 64, false, false, false, false>("dH C^T      M128 N64  K64  A:K  B:K ") != 0;
+  bad += run<128, 128, 128, false, false, false, false>("S d128      M128 N128 K128 A:K  B:K ") != 0;
+  bad += run<128, 128, 128, true, true, false, false>("d128 MN     M128 N128 K128 A:MN B:MN") != 0;
+  bad += run<64, 128, 64, true, true, false, false>("M64 N128    M64  N128 K64  A:MN B:MN") != 0;
+  printf("%d variant(s) failed\n", bad);
+  return bad ? 1 : 0;
+}
