@@ -187,9 +187,10 @@ def main():
     ff, fb, fw_bytes, bw_bytes = flops_and_bytes(c)
 
     def step_device(s):
-        h, n_out, m_out, _ = pkg.mlstm_chunkwise_fw(s["q"], s["k"], s["v"], s["i"], s["f"], chunk_size=c["L"])
+        h, n_out, m_out, _, cst = pkg.mlstm_chunkwise_fw(s["q"], s["k"], s["v"], s["i"], s["f"], chunk_size=c["L"])
         nfw = pkg.last_launch_count()
-        out = pkg.mlstm_chunkwise_bw(s["q"], s["k"], s["v"], s["i"], s["f"], n_out, m_out, s["dh"], chunk_size=c["L"])
+        out = pkg.mlstm_chunkwise_bw(s["q"], s["k"], s["v"], s["i"], s["f"], n_out, m_out, s["dh"], chunk_size=c["L"],
+                                     c_states=cst)
         return h, out, nfw + pkg.last_launch_count()
 
     def sync_all():
@@ -227,9 +228,10 @@ def main():
         s = sets[k % N_SETS]
         a, b_, c_ = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         a.record()
-        h, n_out, m_out, _ = pkg.mlstm_chunkwise_fw(s["q"], s["k"], s["v"], s["i"], s["f"], chunk_size=c["L"])
+        h, n_out, m_out, _, cst = pkg.mlstm_chunkwise_fw(s["q"], s["k"], s["v"], s["i"], s["f"], chunk_size=c["L"])
         b_.record()
-        pkg.mlstm_chunkwise_bw(s["q"], s["k"], s["v"], s["i"], s["f"], n_out, m_out, s["dh"], chunk_size=c["L"])
+        pkg.mlstm_chunkwise_bw(s["q"], s["k"], s["v"], s["i"], s["f"], n_out, m_out, s["dh"], chunk_size=c["L"],
+                               c_states=cst)
         c_.record()
         torch.cuda.synchronize()
         fw_ms.append(a.elapsed_time(b_))

@@ -88,6 +88,8 @@ typedef struct mlstm_b200_fw_args {
   float* c_last;          /* optional last states, all three or none */
   float* n_last;
   float* m_last;
+  void* c_states;         /* optional: per-tile C states for the backward, mlstm_b200_states_bytes()
+                             bytes (the reference's return_all_states mode, native/fwbw.py:73-101) */
   void* workspace;
   size_t workspace_bytes;
 } mlstm_b200_fw_args;
@@ -101,6 +103,7 @@ typedef struct mlstm_b200_bw_args {
   const float* m_initial;
   const float* n_out;
   const float* m_out;
+  const void* c_states;   /* optional: what the forward wrote; NULL = recompute (native/bw.py:251-266) */
   /* incoming gradients */
   mlstm_b200_tensor dh;
   const float* dc_last;   /* optional (B, NH, DHQK, DHHV) */
@@ -120,6 +123,9 @@ const char* mlstm_b200_last_error(void);
 
 /* Bytes of scratch the forward (backward = 0) or backward (backward = 1) needs. */
 size_t mlstm_b200_workspace_bytes(const mlstm_b200_shape* shape, int backward);
+
+/* Bytes of the optional c_states buffer (0 when the selected kernels recompute the states). */
+size_t mlstm_b200_states_bytes(const mlstm_b200_shape* shape);
 
 /* 1 if the tensor-core (tcgen05) kernels cover this shape/dtype, else 0. */
 int mlstm_b200_tensor_path_supported(const mlstm_b200_shape* shape);

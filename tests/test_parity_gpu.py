@@ -155,6 +155,30 @@ def test_extreme_gates_stay_finite(pkg, impl):
         _assert_close(got, _oracle(inp, dtype), 3e-4 if dtype == torch.float32 else 3e-2, f"extreme {dtype} {impl}")
 
 
+def test_tensor_path_is_one_launch_each_way(pkg):
+    """bf16 d=64 must run the tcgen05 kernels: exactly one launch for forward and one for backward
+    (the exact family needs 2 and 4), with and without the saved c_states."""
+    inp = O.make_inputs(2, 4, 320, 64, 64, seed=31, dtype=torch.float32)
+    t = {k: v.to(torch.bfloat16).cuda() for k, v in inp.items()}
+    assert pkg.tensor_path_supported(2, 4, 320, 64, 64, torch.bfloat16)
+    pkg.set_default_impl("tensor")
+    try:
+        h, n_out, m_out, _, cst = pkg.mlstm_chunkwise_fw(t["q"], t["k"], t["v"], t["i"], t["f"])
+        assert pkg.last_launch_count() == 1 and cst is not None
+        g1 = pkg.mlstm_chunkwise_bw(t["q"], t["k"], t["v"], t["i"], t["f"], n_out, m_out, t["dh"], c_states=cst)
+        assert pkg.last_launch_count() == 1
+        g2 = pkg.mlstm_chunkwise_bw(t["q"], t["k"], t["v"], t["i"], t["f"], n_out, m_out, t["dh"], c_states=None)
+        assert pkg.last_launch_count() == 2  # recompute pass + backward
+        torch.cuda.synchronize()
+        for a, b in zip(g1[:5], g2[:5]):
+            assert torch.equal(a, b)
+    finally:
+        pkg.set_default_impl("auto")
+    want = _oracle(inp, torch.bfloat16)
+    got = dict(h=h, dq=g1[0], dk=g1[1], dv=g1[2], di=g1[3], df=g1[4])
+    _assert_close({k: v.double().cpu() for k, v in got.items()}, want, 2e-2, "tensor path S=320 (ragged 128-tile)")
+
+
 def test_chunk_size_error(pkg):
     q = torch.randn(1, 1, 100, 64, device="cuda")
     g = torch.randn(1, 1, 100, device="cuda")

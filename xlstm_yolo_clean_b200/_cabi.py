@@ -18,6 +18,7 @@ EXPORTS = (
     "mlstm_b200_abi_version",
     "mlstm_b200_last_error",
     "mlstm_b200_workspace_bytes",
+    "mlstm_b200_states_bytes",
     "mlstm_b200_tensor_path_supported",
     "mlstm_b200_chunkwise_fw",
     "mlstm_b200_chunkwise_bw",
@@ -45,6 +46,7 @@ class FwArgs(C.Structure):
         ("h", Tensor),
         ("n_out", C.c_void_p), ("m_out", C.c_void_p),
         ("c_last", C.c_void_p), ("n_last", C.c_void_p), ("m_last", C.c_void_p),
+        ("c_states", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]
 
@@ -55,6 +57,7 @@ class BwArgs(C.Structure):
         ("q", Tensor), ("k", Tensor), ("v", Tensor), ("i", Tensor), ("f", Tensor),
         ("c_initial", C.c_void_p), ("n_initial", C.c_void_p), ("m_initial", C.c_void_p),
         ("n_out", C.c_void_p), ("m_out", C.c_void_p),
+        ("c_states", C.c_void_p),
         ("dh", Tensor),
         ("dc_last", C.c_void_p),
         ("dq", Tensor), ("dk", Tensor), ("dv", Tensor), ("di", Tensor), ("df", Tensor),
@@ -85,6 +88,8 @@ def load_library(path: str | None = None):
     lib.mlstm_b200_last_error.restype = C.c_char_p
     lib.mlstm_b200_workspace_bytes.restype = C.c_size_t
     lib.mlstm_b200_workspace_bytes.argtypes = [C.POINTER(Shape), C.c_int]
+    lib.mlstm_b200_states_bytes.restype = C.c_size_t
+    lib.mlstm_b200_states_bytes.argtypes = [C.POINTER(Shape)]
     lib.mlstm_b200_tensor_path_supported.restype = C.c_int
     lib.mlstm_b200_tensor_path_supported.argtypes = [C.POINTER(Shape)]
     lib.mlstm_b200_chunkwise_fw.restype = C.c_int

@@ -98,8 +98,11 @@ def _state_f32(t, shape):
 
 
 def mlstm_chunkwise_fw(q, k, v, i, f, c_initial=None, n_initial=None, m_initial=None, qk_scale=None,
-                       return_last_states=False, chunk_size=64, eps=1e-6, impl=None):
-    """C-ABI forward.  Returns h, n_out, m_out, last_states-or-None (states are fp32)."""
+                       return_last_states=False, chunk_size=64, eps=1e-6, impl=None, save_states=True):
+    """C-ABI forward.  Returns h, n_out, m_out, last_states-or-None (fp32), c_states-or-None.
+
+    ``c_states`` is the opaque per-tile state buffer the tensor-core backward consumes (the
+    reference's return_all_states mode, native/fwbw.py:73-101); None when the kernels recompute."""
     global _last_launches
     lib = _cabi.load_library()
     _check_inputs(q, k, v, i, f)
@@ -130,6 +133,9 @@ def mlstm_chunkwise_fw(q, k, v, i, f, c_initial=None, n_initial=None, m_initial=
         a.shape = _shape(q, v, chunk_size, eps, impl, qk_scale)
         ws_bytes = lib.mlstm_b200_workspace_bytes(C.byref(a.shape), 0)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        st_bytes = lib.mlstm_b200_states_bytes(C.byref(a.shape)) if save_states else 0
+        c_states = torch.empty(st_bytes, dtype=torch.uint8, device=dev) if st_bytes else None
+        a.c_states = _ptr(c_states)
         a.q, a.k, a.v, a.i, a.f, a.h = (_tensor(t) for t in (q, k, v, i, f, h))
         a.c_initial, a.n_initial, a.m_initial = _ptr(c0), _ptr(n0), _ptr(m0)
         a.n_out, a.m_out = n_out.data_ptr(), m_out.data_ptr()
@@ -138,11 +144,12 @@ def mlstm_chunkwise_fw(q, k, v, i, f, c_initial=None, n_initial=None, m_initial=
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws_bytes
         st = lib.mlstm_b200_chunkwise_fw(C.byref(a), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
         _cabi.check(st, "mlstm_b200_chunkwise_fw")
-    return h, n_out, m_out, last
+    return h, n_out, m_out, last, c_states
 
 
 def mlstm_chunkwise_bw(q, k, v, i, f, n_out, m_out, dh, c_initial=None, n_initial=None, m_initial=None,
-                       dc_last=None, qk_scale=None, chunk_size=64, eps=1e-6, impl=None, want_dc_initial=False):
+                       dc_last=None, qk_scale=None, chunk_size=64, eps=1e-6, impl=None, want_dc_initial=False,
+                       c_states=None):
     """C-ABI backward.  Returns dq, dk, dv, di, df, dc_initial-or-None (fp32)."""
     lib = _cabi.load_library()
     _check_inputs(q, k, v, i, f)
@@ -173,6 +180,7 @@ def mlstm_chunkwise_bw(q, k, v, i, f, n_out, m_out, dh, c_initial=None, n_initia
         a.q, a.k, a.v, a.i, a.f, a.dh = (_tensor(t) for t in (q, k, v, i, f, dh))
         a.c_initial, a.n_initial, a.m_initial = _ptr(c0), _ptr(n0), _ptr(m0)
         a.n_out, a.m_out = n_out.data_ptr(), m_out.data_ptr()
+        a.c_states = _ptr(c_states)
         a.dc_last = _ptr(dcl)
         a.dq, a.dk, a.dv, a.di, a.df = (_tensor(t) for t in (dq, dk, dv, di, df))
         a.dc_initial = _ptr(dc0)
@@ -189,10 +197,11 @@ def _make_function(autocast_kernel_dtype: torch.dtype):
         @staticmethod
         @custom_fwd(device_type="cuda", cast_inputs=autocast_kernel_dtype)
         def forward(ctx, q, k, v, i, f, c_initial, n_initial, m_initial, return_last_states, chunk_size, eps):
-            h, n_out, m_out, last = mlstm_chunkwise_fw(
+            need_bw = any(ctx.needs_input_grad[:6])
+            h, n_out, m_out, last, c_states = mlstm_chunkwise_fw(
                 q, k, v, i, f, c_initial, n_initial, m_initial, return_last_states=return_last_states,
-                chunk_size=chunk_size, eps=eps)
-            ctx.save_for_backward(q, k, v, i, f, c_initial, n_initial, m_initial, n_out, m_out)
+                chunk_size=chunk_size, eps=eps, save_states=need_bw)
+            ctx.save_for_backward(q, k, v, i, f, c_initial, n_initial, m_initial, n_out, m_out, c_states)
             ctx.chunk_size, ctx.eps = chunk_size, eps
             if last is None:
                 return h, None, None, None
@@ -202,10 +211,10 @@ def _make_function(autocast_kernel_dtype: torch.dtype):
         @staticmethod
         @custom_bwd(device_type="cuda")
         def backward(ctx, dh, dc_last, dn_last, dm_last):
-            q, k, v, i, f, c0, n0, m0, n_out, m_out = ctx.saved_tensors
+            q, k, v, i, f, c0, n0, m0, n_out, m_out, c_states = ctx.saved_tensors
             dq, dk, dv, di, df, dc0 = mlstm_chunkwise_bw(
                 q, k, v, i, f, n_out, m_out, dh, c0, n0, m0, dc_last=dc_last, chunk_size=ctx.chunk_size, eps=ctx.eps,
-                want_dc_initial=c0 is not None)
+                want_dc_initial=c0 is not None, c_states=c_states)
             # dn_last / dm_last are ignored and dN/dM_initial are zeros, as in native/bw.py:329-337
             return (dq, dk, dv, di, df,
                     None if c0 is None else dc0.to(c0.dtype),

@@ -86,6 +86,12 @@ int mlstm_b200_tensor_path_supported(const mlstm_b200_shape* shape) {
   return tensor_supported(*shape) ? 1 : 0;
 }
 
+size_t mlstm_b200_states_bytes(const mlstm_b200_shape* shape) {
+  if (!shape) return 0;
+  int err = 0;
+  return use_tensor(*shape, &err) ? tensor_states_bytes(*shape) : 0;
+}
+
 size_t mlstm_b200_workspace_bytes(const mlstm_b200_shape* shape, int backward) {
   if (!shape) return 0;
   int err = 0;

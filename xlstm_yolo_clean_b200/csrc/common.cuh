@@ -85,9 +85,9 @@ __device__ __forceinline__ float warp_all_sum(float v) {
 // Tokens t >= n_valid (ragged tail) behave like i = -inf, logsigmoid(f) = 0.
 constexpr int kMaxChunk = 128;
 template <typename T>
-__device__ __forceinline__ float chunk_gate_scan(const T* __restrict__ ig, const T* __restrict__ fg, int64_t gstride,
-                                                 int L, int n_valid, float* sb, float* si, float* spm,
-                                                 float* amax_rel) {
+__device__ __forceinline__ float chunk_gate_scan(const T* __restrict__ ig, int64_t istride, const T* __restrict__ fg,
+                                                 int64_t fstride, int L, int n_valid, float* sb, float* si,
+                                                 float* spm, float* amax_rel) {
   const int lane = threadIdx.x & 31;
   const int E = (L + 31) >> 5;  // consecutive tokens per lane (<= 4)
   float lf[kMaxChunk / 32], iv[kMaxChunk / 32];
@@ -99,8 +99,8 @@ __device__ __forceinline__ float chunk_gate_scan(const T* __restrict__ ig, const
     if (e < E) {
       int t = lane * E + e;
       if (t < L && t < n_valid) {
-        lf[e] = logsigmoid_f32(to_f32<T>(fg[(int64_t)t * gstride]));
-        iv[e] = to_f32<T>(ig[(int64_t)t * gstride]);
+        lf[e] = logsigmoid_f32(to_f32<T>(fg[(int64_t)t * fstride]));
+        iv[e] = to_f32<T>(ig[(int64_t)t * istride]);
       }
       run += lf[e];
       lf[e] = run;  // lane-local inclusive prefix
@@ -155,6 +155,7 @@ int exact_bw(const mlstm_b200_bw_args& a, cudaStream_t st);
 
 bool tensor_supported(const mlstm_b200_shape& s);
 size_t tensor_workspace_bytes(const mlstm_b200_shape& s, int backward);
+size_t tensor_states_bytes(const mlstm_b200_shape& s);
 int tensor_fw(const mlstm_b200_fw_args& a, cudaStream_t st);
 int tensor_bw(const mlstm_b200_bw_args& a, cudaStream_t st);
 

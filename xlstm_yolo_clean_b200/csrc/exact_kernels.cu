@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(kThreads) k_states(ExactParams p) {
     load_tile<T>(sV, ldv, vp + (int64_t)j * L * p.v.ss, p.v.ss, L, DVT);
     if (threadIdx.x < 32) {
       float amax;
-      float g = chunk_gate_scan<T>(ip + (int64_t)j * L * p.ig.ss, fp + (int64_t)j * L * p.fg.ss, p.ig.ss, L, L, sb, si,
+      float g = chunk_gate_scan<T>(ip + (int64_t)j * L * p.ig.ss, p.ig.ss, fp + (int64_t)j * L * p.fg.ss, p.fg.ss, L, L, sb, si,
                                    spm, &amax);
       if (threadIdx.x == 0) { s_g = g; s_amax = amax; }
     }
@@ -219,8 +219,8 @@ __global__ void __launch_bounds__(kThreads) k_fw_h(ExactParams p) {
   const float m_prev = p.Mst[(int64_t)bh * (p.NC + 1) + c];
   if (threadIdx.x < 32) {
     float amax;
-    chunk_gate_scan<T>((const T*)p.ig.ptr + b * p.ig.sb + hh * p.ig.sh + t0 * p.ig.ss,
-                       (const T*)p.fg.ptr + b * p.fg.sb + hh * p.fg.sh + t0 * p.fg.ss, p.ig.ss, L, L, sb, si, spm, &amax);
+    chunk_gate_scan<T>((const T*)p.ig.ptr + b * p.ig.sb + hh * p.ig.sh + t0 * p.ig.ss, p.ig.ss,
+                       (const T*)p.fg.ptr + b * p.fg.sb + hh * p.fg.sh + t0 * p.fg.ss, p.fg.ss, L, L, sb, si, spm, &amax);
   }
   __syncthreads();
   for (int t = threadIdx.x; t < L; t += blockDim.x) smt[t] = sb[t] + fmaxf(m_prev, spm[t]);  // fw.py:178-184
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(kThreads) k_bw_dc(ExactParams p) {
     load_tile<T>(sH, ldv, hp + t0 * p.dh.ss, p.dh.ss, L, DVT);
     if (threadIdx.x < 32) {
       float amax;
-      float g = chunk_gate_scan<T>(ip + t0 * p.ig.ss, fp + t0 * p.fg.ss, p.ig.ss, L, L, sb, si, spm, &amax);
+      float g = chunk_gate_scan<T>(ip + t0 * p.ig.ss, p.ig.ss, fp + t0 * p.fg.ss, p.fg.ss, L, L, sb, si, spm, &amax);
       if (threadIdx.x == 0) s_g = g;
     }
     __syncthreads();
@@ -401,8 +401,8 @@ __global__ void __launch_bounds__(kThreads) k_bw_dqkv(ExactParams p) {
   }
   if (threadIdx.x < 32) {
     float amax;
-    float g = chunk_gate_scan<T>((const T*)p.ig.ptr + b * p.ig.sb + hh * p.ig.sh + t0 * p.ig.ss,
-                                 (const T*)p.fg.ptr + b * p.fg.sb + hh * p.fg.sh + t0 * p.fg.ss, p.ig.ss, L, L, sb, si,
+    float g = chunk_gate_scan<T>((const T*)p.ig.ptr + b * p.ig.sb + hh * p.ig.sh + t0 * p.ig.ss, p.ig.ss,
+                                 (const T*)p.fg.ptr + b * p.fg.sb + hh * p.fg.sh + t0 * p.fg.ss, p.fg.ss, L, L, sb, si,
                                  spm, &amax);
     if (threadIdx.x == 0) s_g = g;
   }

@@ -35,6 +35,7 @@ struct TcFwParams {
   const float *c0, *n0, *m0;
   float *n_out, *m_out;
   float *c_last, *n_last, *m_last;
+  int store_states;  // 1: TMA-store the bf16 copy of C entering every tile (consumed by the backward)
 };
 
 template <int D, int NSTAGE>
@@ -95,7 +96,8 @@ __device__ __forceinline__ void store_row32(uint8_t* base, int row, int col0, co
 template <typename T, int NSTAGE>
 __global__ void __launch_bounds__(kTcThreads, NSTAGE == 1 ? 2 : 1)
 tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
-          const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapH, TcFwParams p) {
+          const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapH,
+          const __grid_constant__ CUtensorMap mapCs, TcFwParams p) {
   constexpr int D = 64;
   constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
   using SM = FwSmem<D, NSTAGE>;
@@ -184,7 +186,7 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
     // ---- A. gates of this tile (one warp, warp-shuffle scans) -------------------------------
     if (warp == 2) {
       float amax;
-      float g = chunk_gate_scan<T>(ip + (int64_t)t0 * p.ig_ss, fp + (int64_t)t0 * p.fg_ss, p.ig_ss, LT, n_valid, sb, sy,
+      float g = chunk_gate_scan<T>(ip + (int64_t)t0 * p.ig_ss, p.ig_ss, fp + (int64_t)t0 * p.fg_ss, p.fg_ss, LT, n_valid, sb, sy,
                                    spm, &amax);
       if (lane == 0) {
         sscal[0] = g;
@@ -204,6 +206,10 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
         umma_commit(&bar_s);
       }
       __syncwarp();
+    }
+    if (tid == 0 && p.store_states) {  // C_{k-1} (bf16 operand copy) -> c_states[b, h, tile]
+      tma_store_4d(&mapCs, sCc, 0, c * D, hh, b);
+      tma_store_commit();
     }
     __syncthreads();  // gates visible
     // ---- C. per-token factors; Kbar = abar . K ----------------------------------------------
@@ -283,6 +289,7 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       }
       srs[ch * LT + row] = rs;
     }
+    if (tid == 0) tma_store_wait_read<0>();  // the c_states store has read sC (rewritten in H)
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
@@ -385,15 +392,397 @@ int num_sms() {
 }
 
 template <typename T, int NSTAGE>
-int launch_fw_d64(const mlstm_b200_fw_args& a, const TcFwParams& p, const CUtensorMap& mq, const CUtensorMap& mk,
-                  const CUtensorMap& mv, const CUtensorMap& mh, cudaStream_t st) {
+int launch_fw_d64(const TcFwParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
+                  const CUtensorMap& mh, const CUtensorMap& mcs, cudaStream_t st) {
   using SM = FwSmem<64, NSTAGE>;
   auto kern = tc_fw_d64<T, NSTAGE>;
   MLSTM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
-  kern<<<p.B * p.NH, kTcThreads, SM::kBytes, st>>>(mq, mk, mv, mh, p);
+  kern<<<p.B * p.NH, kTcThreads, SM::kBytes, st>>>(mq, mk, mv, mh, mcs, p);
   count_launch();
   MLSTM_CUDA_CHECK(cudaGetLastError());
   return 0;
+}
+
+
+// =============================================================================================
+// Backward: one reverse sweep per (batch, head) over 128-token tiles (reference native/bw.py).
+// dC lives on chip (fp32 registers + bf16 operand copy); C_{k-1} comes from the forward's
+// c_states.  n_out and every max state are constants (bw.py:44-47).  Per tile:
+//   S = Q K^T, dSb = dH V^T                      tcgen05 M128 N128 K64 (x2)
+//   W = exp(b_t - b_s + i_s - m_t) / (n_t + eps) (s <= t);  Sb' = S.scale.W ; dS = dSb.W
+//   ddC = (wq.Q)^T dH        M64 N64 K128        dQb = dH C_{k-1}^T     M128 N64 K64
+//   dQa = dS K               M128 N64 K128       dV1 = Sb'^T dH         M128 N64 K128
+//   dV2 = K dC_k             M128 N64 K64        dK1 = dS^T Q           M128 N64 K128
+//   dK2 = V dC_k^T           M128 N64 K64
+//   dq = scale (dQa + bbar/(n+eps) dQb);  dv = dV1 + abar dV2;  dk = scale dK1 + abar dK2
+//   dC_{k-1} = gbar dC_k + ddC;  dI = v.dv;  dF = sigmoid(-f) . suffix-sum(q.dq - k.dk)
+// =============================================================================================
+struct TcBwParams {
+  int B, NH, S, NT;
+  float eps, scale;
+  const void *ig, *fg;
+  int64_t ig_sb, ig_sh, ig_ss, fg_sb, fg_sh, fg_ss;
+  const float* m0;
+  const float *n_out, *m_out, *dc_last;
+  void *di, *df;
+  int64_t di_sb, di_sh, di_ss, df_sb, df_sh, df_ss;
+  float* dc0;
+};
+
+struct BwSmem {
+  static constexpr int kTile = LT * 128;
+  static constexpr int oQ = 0, oK = kTile, oV = 2 * kTile, odH = 3 * kTile;
+  static constexpr int oQt = 4 * kTile;       // wq . Q   (dq staging after its MMA)
+  static constexpr int oSb = 5 * kTile;       // Sb' two halves (dv staging in half 0)
+  static constexpr int odS = 7 * kTile;       // dS  two halves (dk staging in half 0)
+  static constexpr int oCs = 9 * kTile;       // C_{k-1}, 64 x 64 bf16 (TMA)
+  static constexpr int odC = oCs + 64 * 128;  // dC_k bf16 operand copy
+  static constexpr int oSmall = odC + 64 * 128;
+  static constexpr int kSmallFloats = 3 * LT + 6 * LT + 8;
+  static constexpr int kBytes = oSmall + kSmallFloats * 4 + 1024;
+  static constexpr uint32_t kLoadBytes = 4 * kTile + 64 * 128;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+          const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdH,
+          const __grid_constant__ CUtensorMap mapCs, const __grid_constant__ CUtensorMap mapdQ,
+          const __grid_constant__ CUtensorMap mapdK, const __grid_constant__ CUtensorMap mapdV, TcBwParams p) {
+  constexpr int D = 64;
+  constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
+  using SM = BwSmem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem + SM::oQ;
+  uint8_t* sK = smem + SM::oK;
+  uint8_t* sV = smem + SM::oV;
+  uint8_t* sdH = smem + SM::odH;
+  uint8_t* sQt = smem + SM::oQt;
+  uint8_t* sSb = smem + SM::oSb;
+  uint8_t* sdS = smem + SM::odS;
+  uint8_t* sCs = smem + SM::oCs;
+  uint8_t* sdC = smem + SM::odC;
+  float* sb = (float*)(smem + SM::oSmall);
+  float* sy = sb + LT;
+  float* spm = sy + LT;
+  float* spart = spm + LT;  // [3][2][LT]: q.dq, k.dk, v.dv partials per column half
+  float* sscal = spart + 6 * LT;
+  __shared__ uint64_t bar_full, bar_s, bar_d, bar_main;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rb = warp & 3, ch = warp >> 2;
+  const int row = rb * 32 + lane;
+  const int bh = blockIdx.x, b = bh / p.NH, hh = bh % p.NH;
+  const uint32_t lane_base = (uint32_t)(rb * 32) << 16;
+
+  if (tid == 0) {
+    mbar_init(&bar_full, 1);
+    mbar_init(&bar_s, 1);
+    mbar_init(&bar_d, 1);
+    mbar_init(&bar_main, 1);
+    fence_mbar_init();
+    prefetch_tmap(&mapQ); prefetch_tmap(&mapK); prefetch_tmap(&mapV); prefetch_tmap(&mapdH);
+    prefetch_tmap(&mapCs); prefetch_tmap(&mapdQ); prefetch_tmap(&mapdK); prefetch_tmap(&mapdV);
+  }
+  if (warp == 1) tmem_alloc<512>(&tmem_base_s);
+
+  float dCreg[32];
+  const int drow = rb * 16 + (lane & 15);
+  const bool owns_c = lane < 16;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) dCreg[j] = 0.f;
+  if (p.dc_last && owns_c) {
+    const float* src = p.dc_last + ((int64_t)bh * D + drow) * D + ch * 32;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) dCreg[j] = src[j];
+  }
+  if (owns_c) store_row32<T>(sdC, drow, ch * 32, dCreg);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t tS = tmem, tdSb = tmem + 128;
+  const uint32_t tdV1 = tmem, tdV2 = tmem + 64, tdK1 = tmem + 128, tdK2 = tmem + 192;
+  const uint32_t tdQa = tmem + 256, tdQb = tmem + 320, tddC = tmem + 384;
+
+  auto issue_loads = [&](int c) {
+    mbar_expect_tx(&bar_full, SM::kLoadBytes);
+    tma_load_4d(sQ, &mapQ, &bar_full, 0, c * LT, hh, b);
+    tma_load_4d(sK, &mapK, &bar_full, 0, c * LT, hh, b);
+    tma_load_4d(sV, &mapV, &bar_full, 0, c * LT, hh, b);
+    tma_load_4d(sdH, &mapdH, &bar_full, 0, c * LT, hh, b);
+    tma_load_4d(sCs, &mapCs, &bar_full, 0, c * D, hh, b);
+  };
+  if (tid == 0) issue_loads(p.NT - 1);
+
+  const T* ip = (const T*)p.ig + b * p.ig_sb + hh * p.ig_sh;
+  const T* fp = (const T*)p.fg + b * p.fg_sb + hh * p.fg_sh;
+  const float* mo = p.m_out + (int64_t)bh * p.S;
+  const float* no = p.n_out + (int64_t)bh * p.S;
+  float carry = 0.f;  // running suffix sum of (q.dq - k.dk), kept by warp 3
+
+  for (int it = 0; it < p.NT; ++it) {
+    const int c = p.NT - 1 - it;
+    const uint32_t par = it & 1;
+    const int t0 = c * LT;
+    const int n_valid = min(LT, p.S - t0);
+    const bool valid = row < n_valid;
+    const float m_t = valid ? mo[t0 + row] : 0.f;
+    const float n_t = valid ? no[t0 + row] : 1.f;
+    const float m_prev = c > 0 ? mo[t0 - 1] : (p.m0 ? p.m0[bh] : 0.f);  // m of the state entering the tile
+    const float m_next = mo[t0 + n_valid - 1];                            // m of the state leaving it
+
+    // ---- A. gates ---------------------------------------------------------------------------
+    if (warp == 2) {
+      float amax;
+      float g = chunk_gate_scan<T>(ip + (int64_t)t0 * p.ig_ss, p.ig_ss, fp + (int64_t)t0 * p.fg_ss, p.fg_ss, LT, n_valid, sb, sy,
+                                   spm, &amax);
+      if (lane == 0) sscal[0] = g;
+    }
+    // ---- B. S = Q K^T, dSb = dH V^T ---------------------------------------------------------
+    if (warp == 0) {
+      mbar_wait(&bar_full, par, 11);
+      tc_fence_after_sync();
+      if (elect_one()) {
+        constexpr uint32_t idesc = umma_idesc(128, 128, false, false, kBf16);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)
+          umma_f16(tS, umma_smem_desc(smem_u32(sQ) + kk * 32, 0, 1024), umma_smem_desc(smem_u32(sK) + kk * 32, 0, 1024),
+                   idesc, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)
+          umma_f16(tdSb, umma_smem_desc(smem_u32(sdH) + kk * 32, 0, 1024),
+                   umma_smem_desc(smem_u32(sV) + kk * 32, 0, 1024), idesc, kk > 0);
+        umma_commit(&bar_s);
+      }
+      __syncwarp();
+    }
+    if (tid == 0) tma_store_wait_read<0>();  // previous tile's dq/dk/dv staging buffers are free again
+    __syncthreads();                         // #1 gates visible
+    const float g = sscal[0];
+    const float b_t = sb[row], i_t = sy[row];
+    const float rinv = valid ? 1.f / (n_t + p.eps) : 0.f;                 // bw.py:135
+    const float bbar = valid ? __expf(b_t + m_prev - m_t) : 0.f;          // bw.py:186
+    const float abar = __expf(g - b_t + i_t - m_next);                    // bw.py:187 (0 for tail tokens)
+    const float gbar = __expf(g + m_prev - m_next);                       // bw.py:76
+    __syncthreads();                                                      // #2 raw i consumed
+    if (ch == 0) sy[row] = (i_t - b_t) * kLog2e;
+    mbar_wait(&bar_full, par, 12);
+    // ---- C. Qt = wq . Q; keep this thread's q / k / v row slices for the gate gradients -------
+    uint32_t qs[16], ks[16], vs[16];
+    {
+      const float wq = p.scale * bbar * rinv;  // bw.py:83-90
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t off = swz128(row, ch * 32 + 8 * j);
+        uint4 u = *reinterpret_cast<const uint4*>(sQ + off);
+        qs[4 * j] = u.x; qs[4 * j + 1] = u.y; qs[4 * j + 2] = u.z; qs[4 * j + 3] = u.w;
+        float2 a0 = unpack2<T>(u.x), a1 = unpack2<T>(u.y), a2 = unpack2<T>(u.z), a3 = unpack2<T>(u.w);
+        u.x = pack2<T>(a0.x * wq, a0.y * wq);
+        u.y = pack2<T>(a1.x * wq, a1.y * wq);
+        u.z = pack2<T>(a2.x * wq, a2.y * wq);
+        u.w = pack2<T>(a3.x * wq, a3.y * wq);
+        *reinterpret_cast<uint4*>(sQt + off) = u;
+        uint4 uk = *reinterpret_cast<const uint4*>(sK + off);
+        ks[4 * j] = uk.x; ks[4 * j + 1] = uk.y; ks[4 * j + 2] = uk.z; ks[4 * j + 3] = uk.w;
+        uint4 uv = *reinterpret_cast<const uint4*>(sV + off);
+        vs[4 * j] = uv.x; vs[4 * j + 1] = uv.y; vs[4 * j + 2] = uv.z; vs[4 * j + 3] = uv.w;
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();  // #3
+    // ---- D. ddC = Qt^T dH ; dQb = dH C_{k-1}^T -------------------------------------------------
+    if (warp == 0) {
+      if (elect_one()) {
+        constexpr uint32_t idesc_c = umma_idesc(64, 64, true, true, kBf16);
+#pragma unroll
+        for (int kk = 0; kk < LT / 16; ++kk)
+          umma_f16(tddC, umma_smem_desc(smem_u32(sQt) + kk * 2048, SM::kTile, 1024),
+                   umma_smem_desc(smem_u32(sdH) + kk * 2048, SM::kTile, 1024), idesc_c, kk > 0);
+        constexpr uint32_t idesc_q = umma_idesc(128, 64, false, false, kBf16);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)
+          umma_f16(tdQb, umma_smem_desc(smem_u32(sdH) + kk * 32, 0, 1024),
+                   umma_smem_desc(smem_u32(sCs) + kk * 32, 0, 1024), idesc_q, kk > 0);
+        umma_commit(&bar_d);
+      }
+      __syncwarp();
+    }
+    // ---- E. W; Sb' = S.scale.W, dS = dSb.W ------------------------------------------------------
+    mbar_wait(&bar_s, par, 13);
+    tc_fence_after_sync();
+    {
+      const float x_t = (b_t - m_t) * kLog2e;
+      for (int u = 0; u < 4; ++u) {
+        if ((u & 1) != ch) continue;
+        float v[32], w[32];
+        if (u <= rb) {
+          tmem_ld32(tS + lane_base + u * 32, v);
+          tmem_ld32(tdSb + lane_base + u * 32, w);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float wg = exp2f(x_t + sy[u * 32 + j]) * rinv;
+            const bool keep = valid && (u < rb || j <= lane);
+            v[j] = keep ? v[j] * p.scale * wg : 0.f;
+            w[j] = keep ? w[j] * wg : 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { v[j] = 0.f; w[j] = 0.f; }
+        }
+        store_row32<T>(sSb, row, u * 32, v);
+        store_row32<T>(sdS, row, u * 32, w);
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();  // #4
+    // ---- F. the five output MMAs ---------------------------------------------------------------
+    if (warp == 0) {
+      tc_fence_after_sync();
+      if (elect_one()) {
+        constexpr uint32_t id_k_mn = umma_idesc(128, 64, false, true, kBf16);   // A K-major, B MN-major
+        constexpr uint32_t id_mn_mn = umma_idesc(128, 64, true, true, kBf16);   // A MN-major, B MN-major
+        constexpr uint32_t id_k_k = umma_idesc(128, 64, false, false, kBf16);   // A K-major, B K-major
+#pragma unroll
+        for (int kk = 0; kk < LT / 16; ++kk)  // dQa = dS K
+          umma_f16(tdQa, umma_smem_desc(smem_u32(sdS) + (kk / 4) * SM::kTile + (kk % 4) * 32, 0, 1024),
+                   umma_smem_desc(smem_u32(sK) + kk * 2048, SM::kTile, 1024), id_k_mn, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < LT / 16; ++kk)  // dV1 = Sb'^T dH
+          umma_f16(tdV1, umma_smem_desc(smem_u32(sSb) + kk * 2048, SM::kTile, 1024),
+                   umma_smem_desc(smem_u32(sdH) + kk * 2048, SM::kTile, 1024), id_mn_mn, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)  // dV2 = K dC_k
+          umma_f16(tdV2, umma_smem_desc(smem_u32(sK) + kk * 32, 0, 1024),
+                   umma_smem_desc(smem_u32(sdC) + kk * 2048, D * 128, 1024), id_k_mn, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < LT / 16; ++kk)  // dK1 = dS^T Q
+          umma_f16(tdK1, umma_smem_desc(smem_u32(sdS) + kk * 2048, SM::kTile, 1024),
+                   umma_smem_desc(smem_u32(sQ) + kk * 2048, SM::kTile, 1024), id_mn_mn, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)  // dK2 = V dC_k^T
+          umma_f16(tdK2, umma_smem_desc(smem_u32(sV) + kk * 32, 0, 1024),
+                   umma_smem_desc(smem_u32(sdC) + kk * 32, 0, 1024), id_k_k, kk > 0);
+        umma_commit(&bar_main);
+      }
+      __syncwarp();
+    }
+    // ---- G. dC_{k-1} = gbar dC_k + ddC (registers) -----------------------------------------------
+    mbar_wait(&bar_d, par, 14);
+    tc_fence_after_sync();
+    {
+      float v[32];
+      tmem_ld32(tddC + lane_base + ch * 32, v);
+      if (owns_c) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) dCreg[j] = gbar * dCreg[j] + v[j];  // bw.py:93-95
+      }
+    }
+    // ---- H. epilogue --------------------------------------------------------------------------------
+    mbar_wait(&bar_main, par, 15);
+    tc_fence_after_sync();
+    if (tid == 0 && c > 0) issue_loads(c - 1);  // every MMA / thread is done with this tile's inputs
+    if (owns_c) store_row32<T>(sdC, drow, ch * 32, dCreg);
+    {
+      float a[32], bq[32];
+      float dot;
+      // dq
+      tmem_ld32(tdQa + lane_base + ch * 32, a);
+      tmem_ld32(tdQb + lane_base + ch * 32, bq);
+      const float wb = bbar * rinv;
+      dot = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        a[2 * j] = p.scale * (a[2 * j] + wb * bq[2 * j]);              // bw.py:169,193
+        a[2 * j + 1] = p.scale * (a[2 * j + 1] + wb * bq[2 * j + 1]);
+        float2 qv = unpack2<T>(qs[j]);
+        dot += qv.x * a[2 * j] + qv.y * a[2 * j + 1];
+      }
+      store_row32<T>(sQt, row, ch * 32, a);
+      spart[(0 * 2 + ch) * LT + row] = dot;
+      // dv
+      tmem_ld32(tdV1 + lane_base + ch * 32, a);
+      tmem_ld32(tdV2 + lane_base + ch * 32, bq);
+      dot = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        a[2 * j] = a[2 * j] + abar * bq[2 * j];                        // bw.py:164,190
+        a[2 * j + 1] = a[2 * j + 1] + abar * bq[2 * j + 1];
+        float2 vv = unpack2<T>(vs[j]);
+        dot += vv.x * a[2 * j] + vv.y * a[2 * j + 1];
+      }
+      store_row32<T>(sSb, row, ch * 32, a);
+      spart[(2 * 2 + ch) * LT + row] = dot;
+      // dk
+      tmem_ld32(tdK1 + lane_base + ch * 32, a);
+      tmem_ld32(tdK2 + lane_base + ch * 32, bq);
+      dot = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        a[2 * j] = p.scale * a[2 * j] + abar * bq[2 * j];              // bw.py:170,192
+        a[2 * j + 1] = p.scale * a[2 * j + 1] + abar * bq[2 * j + 1];
+        float2 kv = unpack2<T>(ks[j]);
+        dot += kv.x * a[2 * j] + kv.y * a[2 * j + 1];
+      }
+      store_row32<T>(sdS, row, ch * 32, a);
+      spart[(1 * 2 + ch) * LT + row] = dot;
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();  // #5
+    if (tid == 0) {
+      tma_store_4d(&mapdQ, sQt, 0, t0, hh, b);
+      tma_store_4d(&mapdV, sSb, 0, t0, hh, b);
+      tma_store_4d(&mapdK, sdS, 0, t0, hh, b);
+      tma_store_commit();
+    }
+    // ---- gate gradients: warp 3 runs the reverse (suffix) scan over the tile, carrying across tiles
+    if (warp == 3) {
+      float acc[4], di[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int t = lane * 4 + e;
+        acc[e] = (spart[0 * LT + t] + spart[1 * LT + t]) - (spart[2 * LT + t] + spart[3 * LT + t]);  // bw.py:321
+        di[e] = spart[4 * LT + t] + spart[5 * LT + t];                                               // bw.py:326
+      }
+      acc[2] += acc[3];
+      acc[1] += acc[2];
+      acc[0] += acc[1];
+      float incl = acc[0];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        float u = __shfl_down_sync(0xffffffffu, incl, o);
+        if (lane + o < 32) incl += u;
+      }
+      const float excl = incl - acc[0] + carry;
+      T* dip = (T*)p.di + b * p.di_sb + hh * p.di_sh;
+      T* dfp = (T*)p.df + b * p.df_sb + hh * p.df_sh;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int t = lane * 4 + e;
+        if (t < n_valid) {
+          const float fraw = to_f32<T>(fp[(int64_t)(t0 + t) * p.fg_ss]);
+          dip[(int64_t)(t0 + t) * p.di_ss] = from_f32<T>(di[e]);
+          dfp[(int64_t)(t0 + t) * p.df_ss] = from_f32<T>((acc[e] + excl) * sigmoid_neg_f32(fraw));  // bw.py:322-323
+        }
+      }
+      carry += __shfl_sync(0xffffffffu, incl, 0);
+    }
+  }
+
+  if (p.dc0 && owns_c) {  // dC_initial = dC_0 (bw.py:329-331)
+    float* dst = p.dc0 + ((int64_t)bh * D + drow) * D + ch * 32;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) dst[j] = dCreg[j];
+  }
+  if (tid == 0) tma_store_wait_all<0>();
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem);
 }
 
 bool tma_ok(const mlstm_b200_tensor& t) {
@@ -401,32 +790,27 @@ bool tma_ok(const mlstm_b200_tensor& t) {
          (t.stride[2] % 8) == 0;
 }
 
-}  // namespace
-
-bool tensor_supported(const mlstm_b200_shape& s) {
-  if (s.dtype != MLSTM_B200_BF16 && s.dtype != MLSTM_B200_F16) return false;
-  if (s.DHQK != 64 || s.DHHV != 64) return false;
-  if (s.chunk_size % 64 != 0 || s.S % 64 != 0) return false;
-  return true;
+int make_map(CUtensorMap* m, const mlstm_b200_tensor& t, const mlstm_b200_shape& s, int D) {
+  return sm100_host::make_map_bhsd(m, t.ptr, s.dtype == MLSTM_B200_BF16, s.B, s.NH, s.S, D, t.stride[0], t.stride[1],
+                                   t.stride[2], LT);
+}
+int make_states_map(CUtensorMap* m, const void* ptr, const mlstm_b200_shape& s) {
+  const int NT = (s.S + LT - 1) / LT;
+  return sm100_host::make_map_bhsd(m, ptr, s.dtype == MLSTM_B200_BF16, s.B, s.NH, NT * 64, 64, (int64_t)s.NH * NT * 4096,
+                                   (int64_t)NT * 4096, 64, 64);
 }
 
-size_t tensor_workspace_bytes(const mlstm_b200_shape& s, int backward) {
-  return backward ? exact_workspace_bytes(s, 1) : 256;
-}
-
-int tensor_fw(const mlstm_b200_fw_args& a, cudaStream_t st) {
+int run_fw(const mlstm_b200_fw_args& a, void* c_states, cudaStream_t st) {
   const mlstm_b200_shape& s = a.shape;
   if (!tma_ok(a.q) || !tma_ok(a.k) || !tma_ok(a.v) || !tma_ok(a.h)) {
     set_error("tensor path needs 16-byte aligned q/k/v/h with strides that are multiples of 8 elements");
     return MLSTM_B200_EUNSUPPORTED;
   }
-  const bool bf = s.dtype == MLSTM_B200_BF16;
-  CUtensorMap mq, mk, mv, mh;
-  int r = 0;
-  r |= sm100_host::make_map_bhsd(&mq, a.q.ptr, bf, s.B, s.NH, s.S, s.DHQK, a.q.stride[0], a.q.stride[1], a.q.stride[2], LT);
-  r |= sm100_host::make_map_bhsd(&mk, a.k.ptr, bf, s.B, s.NH, s.S, s.DHQK, a.k.stride[0], a.k.stride[1], a.k.stride[2], LT);
-  r |= sm100_host::make_map_bhsd(&mv, a.v.ptr, bf, s.B, s.NH, s.S, s.DHHV, a.v.stride[0], a.v.stride[1], a.v.stride[2], LT);
-  r |= sm100_host::make_map_bhsd(&mh, a.h.ptr, bf, s.B, s.NH, s.S, s.DHHV, a.h.stride[0], a.h.stride[1], a.h.stride[2], LT);
+  CUtensorMap mq, mk, mv, mh, mcs;
+  int r = make_map(&mq, a.q, s, s.DHQK) | make_map(&mk, a.k, s, s.DHQK) | make_map(&mv, a.v, s, s.DHHV) |
+          make_map(&mh, a.h, s, s.DHHV);
+  // without a c_states buffer the map is never used by the kernel; point it at h to keep it valid
+  r |= c_states ? make_states_map(&mcs, c_states, s) : make_map(&mcs, a.h, s, s.DHHV);
   if (r) {
     set_error("cuTensorMapEncodeTiled failed (%d)", r);
     return MLSTM_B200_ENODEVICE;
@@ -440,15 +824,105 @@ int tensor_fw(const mlstm_b200_fw_args& a, cudaStream_t st) {
   p.c0 = a.c_initial; p.n0 = a.n_initial; p.m0 = a.m_initial;
   p.n_out = a.n_out; p.m_out = a.m_out;
   p.c_last = a.c_last; p.n_last = a.n_last; p.m_last = a.m_last;
+  p.store_states = c_states != nullptr;
   const bool two_per_sm = (long)s.B * s.NH > num_sms();
-  if (bf) {
-    return two_per_sm ? launch_fw_d64<__nv_bfloat16, 1>(a, p, mq, mk, mv, mh, st)
-                      : launch_fw_d64<__nv_bfloat16, 2>(a, p, mq, mk, mv, mh, st);
+  if (s.dtype == MLSTM_B200_BF16) {
+    return two_per_sm ? launch_fw_d64<__nv_bfloat16, 1>(p, mq, mk, mv, mh, mcs, st)
+                      : launch_fw_d64<__nv_bfloat16, 2>(p, mq, mk, mv, mh, mcs, st);
   }
-  return two_per_sm ? launch_fw_d64<__half, 1>(a, p, mq, mk, mv, mh, st)
-                    : launch_fw_d64<__half, 2>(a, p, mq, mk, mv, mh, st);
+  return two_per_sm ? launch_fw_d64<__half, 1>(p, mq, mk, mv, mh, mcs, st)
+                    : launch_fw_d64<__half, 2>(p, mq, mk, mv, mh, mcs, st);
 }
 
-int tensor_bw(const mlstm_b200_bw_args& a, cudaStream_t st) { return exact_bw(a, st); }
+struct BwWs {
+  size_t off_states, off_h, off_n, off_m, total;
+};
+BwWs bw_ws(const mlstm_b200_shape& s) {
+  BwWs w{};
+  size_t tok = (size_t)s.B * s.NH * s.S, o = 0;
+  w.off_states = o; o += align_up(tensor_states_bytes(s), 256);
+  w.off_h = o; o += align_up(tok * s.DHHV * 2, 256);
+  w.off_n = o; o += align_up(tok * 4, 256);
+  w.off_m = o; o += align_up(tok * 4, 256);
+  w.total = o;
+  return w;
+}
+
+}  // namespace
+
+bool tensor_supported(const mlstm_b200_shape& s) {
+  if (s.dtype != MLSTM_B200_BF16 && s.dtype != MLSTM_B200_F16) return false;
+  if (s.DHQK != 64 || s.DHHV != 64) return false;
+  if (s.chunk_size % 64 != 0 || s.S % 64 != 0) return false;
+  return true;
+}
+
+size_t tensor_states_bytes(const mlstm_b200_shape& s) {
+  const size_t NT = (s.S + LT - 1) / LT;
+  return (size_t)s.B * s.NH * NT * 64 * 64 * 2;
+}
+
+// forward needs no scratch; backward needs room to recompute the states when c_states is absent
+size_t tensor_workspace_bytes(const mlstm_b200_shape& s, int backward) { return backward ? bw_ws(s).total : 256; }
+
+int tensor_fw(const mlstm_b200_fw_args& a, cudaStream_t st) { return run_fw(a, a.c_states, st); }
+
+int tensor_bw(const mlstm_b200_bw_args& a, cudaStream_t st) {
+  const mlstm_b200_shape& s = a.shape;
+  if (!tma_ok(a.q) || !tma_ok(a.k) || !tma_ok(a.v) || !tma_ok(a.dh) || !tma_ok(a.dq) || !tma_ok(a.dk) || !tma_ok(a.dv)) {
+    set_error("tensor path needs 16-byte aligned q/k/v/dh/dq/dk/dv with strides that are multiples of 8 elements");
+    return MLSTM_B200_EUNSUPPORTED;
+  }
+  const void* c_states = a.c_states;
+  if (!c_states) {  // recompute the states with a forward pass into the workspace (bw.py:251-266)
+    BwWs w = bw_ws(s);
+    if (!a.workspace || a.workspace_bytes < w.total) {
+      set_error("workspace too small: need %zu bytes, got %zu", w.total, a.workspace_bytes);
+      return MLSTM_B200_EWORKSPACE;
+    }
+    char* ws = (char*)a.workspace;
+    mlstm_b200_fw_args f{};
+    f.shape = s;
+    f.q = a.q; f.k = a.k; f.v = a.v; f.i = a.i; f.f = a.f;
+    f.c_initial = a.c_initial; f.n_initial = a.n_initial; f.m_initial = a.m_initial;
+    f.h.ptr = ws + w.off_h;
+    f.h.stride[0] = (int64_t)s.NH * s.S * s.DHHV; f.h.stride[1] = (int64_t)s.S * s.DHHV; f.h.stride[2] = s.DHHV;
+    f.h.stride[3] = 1;
+    f.n_out = (float*)(ws + w.off_n); f.m_out = (float*)(ws + w.off_m);
+    if (int e = run_fw(f, ws + w.off_states, st)) return e;
+    c_states = ws + w.off_states;
+  }
+  CUtensorMap mq, mk, mv, mdh, mcs, mdq, mdk, mdv;
+  int r = make_map(&mq, a.q, s, 64) | make_map(&mk, a.k, s, 64) | make_map(&mv, a.v, s, 64) | make_map(&mdh, a.dh, s, 64) |
+          make_states_map(&mcs, c_states, s) | make_map(&mdq, a.dq, s, 64) | make_map(&mdk, a.dk, s, 64) |
+          make_map(&mdv, a.dv, s, 64);
+  if (r) {
+    set_error("cuTensorMapEncodeTiled failed (%d)", r);
+    return MLSTM_B200_ENODEVICE;
+  }
+  TcBwParams p{};
+  p.B = s.B; p.NH = s.NH; p.S = s.S; p.NT = (s.S + LT - 1) / LT;
+  p.eps = s.eps;
+  p.scale = s.qk_scale > 0.f ? s.qk_scale : 1.f / sqrtf((float)s.DHQK);
+  p.ig = a.i.ptr; p.ig_sb = a.i.stride[0]; p.ig_sh = a.i.stride[1]; p.ig_ss = a.i.stride[2];
+  p.fg = a.f.ptr; p.fg_sb = a.f.stride[0]; p.fg_sh = a.f.stride[1]; p.fg_ss = a.f.stride[2];
+  p.m0 = a.m_initial;
+  p.n_out = a.n_out; p.m_out = a.m_out; p.dc_last = a.dc_last;
+  p.di = a.di.ptr; p.di_sb = a.di.stride[0]; p.di_sh = a.di.stride[1]; p.di_ss = a.di.stride[2];
+  p.df = a.df.ptr; p.df_sb = a.df.stride[0]; p.df_sh = a.df.stride[1]; p.df_ss = a.df.stride[2];
+  p.dc0 = a.dc_initial;
+  if (s.dtype == MLSTM_B200_BF16) {
+    auto kern = tc_bw_d64<__nv_bfloat16>;
+    MLSTM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwSmem::kBytes));
+    kern<<<s.B * s.NH, kTcThreads, BwSmem::kBytes, st>>>(mq, mk, mv, mdh, mcs, mdq, mdk, mdv, p);
+  } else {
+    auto kern = tc_bw_d64<__half>;
+    MLSTM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwSmem::kBytes));
+    kern<<<s.B * s.NH, kTcThreads, BwSmem::kBytes, st>>>(mq, mk, mv, mdh, mcs, mdq, mdk, mdv, p);
+  }
+  count_launch();
+  MLSTM_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
 
 }  // namespace mlstm
