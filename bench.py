@@ -53,38 +53,55 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled through NVML DURING the timed region (the nvidia-smi
+    subprocess of the profiling recipe stalls kernel launches of a sub-millisecond step, so the
+    same counters are read in-process)."""
 
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.bits, self.max_mhz = index, [], 0, None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # pragma: no cover
+            self.nv, self.err = None, repr(e)
+
+    def _sample(self):
+        self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+        try:
+            self.bits |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            self.bits |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+
+    def _loop(self):
+        while not self._stop.is_set():
+            self._sample()
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        if self.nv is None:
+            return
+        self._thr = threading.Thread(target=self._loop, daemon=True)
+        self._thr.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "?")]}
+        self._sample()
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+        reasons = sorted(n for b, n in self.REASONS.items() if self.bits & b)
+        return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(self.sm)}
 
 
 def cpu_baseline(sample_b=4, reps=3):
@@ -145,8 +162,8 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--kernel-impl", default="auto", choices=["auto", "exact", "tensor"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -186,12 +203,13 @@ def main():
         sets.append({k: v.to(dt).to(dev) for k, v in inp.items()})
     ff, fb, fw_bytes, bw_bytes = flops_and_bytes(c)
 
-    def step_device(s):
-        h, n_out, m_out, _, cst = pkg.mlstm_chunkwise_fw(s["q"], s["k"], s["v"], s["i"], s["f"], chunk_size=c["L"])
-        nfw = pkg.last_launch_count()
-        out = pkg.mlstm_chunkwise_bw(s["q"], s["k"], s["v"], s["i"], s["f"], n_out, m_out, s["dh"], chunk_size=c["L"],
-                                     c_states=cst)
-        return h, out, nfw + pkg.last_launch_count()
+    def fw_only(s):
+        return pkg.mlstm_chunkwise_fw(s["q"], s["k"], s["v"], s["i"], s["f"], chunk_size=c["L"])
+
+    def bw_only(s, saved):
+        h, n_out, m_out, _, cst = saved
+        return pkg.mlstm_chunkwise_bw(s["q"], s["k"], s["v"], s["i"], s["f"], n_out, m_out, s["dh"], chunk_size=c["L"],
+                                      c_states=cst)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -199,22 +217,53 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    # eager warm-up (also counts the kernels one step launches)
+    launches_per_step = 0
+    for w in range(max(args.warmup, 3)):
+        saved = fw_only(sets[w % N_SETS])
+        n1 = pkg.last_launch_count()
+        bw_only(sets[w % N_SETS], saved)
+        launches_per_step = n1 + pkg.last_launch_count()
+    torch.cuda.synchronize()
+
+    # One CUDA graph per rotating input set: the step is two ~100 us kernels, so eager Python/ctypes
+    # launch gaps would dominate.  Outputs live in the graphs' private pools.
+    graphs, fw_graphs, bw_graphs, keep = [], [], [], []
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for r in range(N_SETS):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                saved = fw_only(sets[r])
+                out = bw_only(sets[r], saved)
+            graphs.append(g)
+            keep.append((saved, out))
+            gf = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gf, stream=side):
+                saved_f = fw_only(sets[r])
+            gb = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gb, stream=side):
+                out_b = bw_only(sets[r], saved_f)
+            fw_graphs.append(gf)
+            bw_graphs.append(gb)
+            keep.append((saved_f, out_b))
+    torch.cuda.synchronize()
+
     # ---- device-resident throughput ("value") -------------------------------------------------
     for w in range(args.warmup):
-        step_device(sets[w % N_SETS])
+        graphs[w % N_SETS].replay()
     sampler = ClockSampler(local_rank)
     sync_all()
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches = 0
     e0.record()
     for k in range(args.steps):
-        _, _, n = step_device(sets[k % N_SETS])
-        launches += n
+        graphs[k % N_SETS].replay()
     e1.record()
     sync_all()
     clocks = sampler.stop() if rank == 0 else None
+    launches = launches_per_step * args.steps
     ms_total = e0.elapsed_time(e1)
     t = torch.tensor([ms_total], device=dev)
     if world > 1:
@@ -222,28 +271,28 @@ def main():
     ms_step = t.item() / args.steps
     value = world * (ff + fb) / (ms_step * 1e-3) / 1e12
 
-    # ---- per-phase kernel timing for the roofline (events on the launching stream) ------------
+    # ---- per-kernel timing for the roofline: CUDA events on the launching stream, one kernel per graph
     fw_ms, bw_ms = [], []
-    for k in range(min(args.steps, 20)):
-        s = sets[k % N_SETS]
+    for k in range(max(8, min(args.steps, 40))):
+        r = k % N_SETS
         a, b_, c_ = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         a.record()
-        h, n_out, m_out, _, cst = pkg.mlstm_chunkwise_fw(s["q"], s["k"], s["v"], s["i"], s["f"], chunk_size=c["L"])
+        fw_graphs[r].replay()
         b_.record()
-        pkg.mlstm_chunkwise_bw(s["q"], s["k"], s["v"], s["i"], s["f"], n_out, m_out, s["dh"], chunk_size=c["L"],
-                               c_states=cst)
+        bw_graphs[r].replay()
         c_.record()
         torch.cuda.synchronize()
         fw_ms.append(a.elapsed_time(b_))
         bw_ms.append(b_.elapsed_time(c_))
     fw_t, bw_t = statistics.median(fw_ms), statistics.median(bw_ms)
     hbm_peak, tf_peak, peak_kind = peaks()
-    dom = ("bw", bw_bytes, bw_t) if bw_t >= fw_t else ("fw", fw_bytes, fw_t)
-    roof = {"bound": "hbm", "kernel": f"mlstm_b200_chunkwise_{dom[0]} (C-ABI call; host launch gaps included)",
+    dom = ("bw", bw_bytes, bw_t, "tc_bw_d64") if bw_t >= fw_t else ("fw", fw_bytes, fw_t, "tc_fw_d64")
+    roof = {"bound": "hbm", "kernel": f"{dom[3]} (mlstm_b200_chunkwise_{dom[0]}, one launch per call)",
             "achieved": dom[1] / (dom[2] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": dom[1] / (dom[2] * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_kind": peak_kind,
             "algorithmic_bytes": dom[1], "fw_ms": fw_t, "bw_ms": bw_t,
             "fw_gbs": fw_bytes / (fw_t * 1e-3) / 1e9, "bw_gbs": bw_bytes / (bw_t * 1e-3) / 1e9,
+            "fw_frac": fw_bytes / (fw_t * 1e-3) / 1e9 / hbm_peak, "bw_frac": bw_bytes / (bw_t * 1e-3) / 1e9 / hbm_peak,
             "tflops_frac_of_bf16_peak": (ff + fb) / ((fw_t + bw_t) * 1e-3) / 1e12 / tf_peak}
 
     # ---- end to end through the public API with HOST buffers ----------------------------------
@@ -286,6 +335,7 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_gpu": True, "kernel_impl": args.kernel_impl,
                        "l2": f"{N_SETS} rotating input sets, >126 MB touched between reuses (no explicit flush)",
+                       "launch": "CUDA graph replay per step (fw + bw kernels)",
                        "frac_of_bf16_peak": value / world / tf_peak},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_val, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

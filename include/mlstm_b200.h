@@ -141,6 +141,11 @@ int mlstm_b200_chunkwise_bw(const mlstm_b200_bw_args* args, void* cuda_stream);
  * gpu_launches claim). */
 int mlstm_b200_last_launch_count(void);
 
+/* Debug / profiling hook (not thread-safe): when set to a device buffer of at least 8192
+ * int64, CTA 0 of the tensor-core kernels records clock64() at its phase boundaries
+ * (forward at [tile*16 + slot], backward at [4096 + tile*16 + slot]).  NULL disables it. */
+void mlstm_b200_debug_set_clock_buffer(void* dev_ptr);
+
 #ifdef __cplusplus
 }
 #endif

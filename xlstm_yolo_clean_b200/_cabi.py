@@ -23,6 +23,7 @@ EXPORTS = (
     "mlstm_b200_chunkwise_fw",
     "mlstm_b200_chunkwise_bw",
     "mlstm_b200_last_launch_count",
+    "mlstm_b200_debug_set_clock_buffer",
 )
 
 
@@ -97,6 +98,8 @@ def load_library(path: str | None = None):
     lib.mlstm_b200_chunkwise_bw.restype = C.c_int
     lib.mlstm_b200_chunkwise_bw.argtypes = [C.POINTER(BwArgs), C.c_void_p]
     lib.mlstm_b200_last_launch_count.restype = C.c_int
+    lib.mlstm_b200_debug_set_clock_buffer.restype = None
+    lib.mlstm_b200_debug_set_clock_buffer.argtypes = [C.c_void_p]
     v = lib.mlstm_b200_abi_version()
     if v != ABI_VERSION:
         raise RuntimeError(f"ABI mismatch: library {v}, binding {ABI_VERSION}")

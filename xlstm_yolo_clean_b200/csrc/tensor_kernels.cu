@@ -36,7 +36,10 @@ struct TcFwParams {
   float *n_out, *m_out;
   float *c_last, *n_last, *m_last;
   int store_states;  // 1: TMA-store the bf16 copy of C entering every tile (consumed by the backward)
+  long long* prof;   // debug: per-tile phase clocks of CTA 0 (mlstm_b200_debug_set_clock_buffer)
 };
+#define TC_PROF(tile, slot) \
+  if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) p.prof[(tile) * 16 + (slot)] = clock64()
 
 template <int D, int NSTAGE>
 struct FwSmem {
@@ -102,7 +105,7 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
   constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
   using SM = FwSmem<D, NSTAGE>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   float* sb = (float*)(smem + SM::oSmall);  // chunk-local cumsum of logsigmoid(f)
   float* sy = sb + LT;                      // (i_s - b_s) * log2e
   float* spm = sy + LT;                     // prefix max of (i_s - b_s)
@@ -183,6 +186,7 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
     const int t0 = c * LT;
     const int n_valid = min(LT, p.S - t0);
 
+    TC_PROF(c, 0);
     // ---- A. gates of this tile (one warp, warp-shuffle scans) -------------------------------
     if (warp == 2) {
       float amax;
@@ -212,6 +216,7 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       tma_store_commit();
     }
     __syncthreads();  // gates visible
+    TC_PROF(c, 1);
     // ---- C. per-token factors; Kbar = abar . K ----------------------------------------------
     const float g = sscal[0];
     const float m_next = fmaxf(g + m_run, g + sscal[1]);  // fw.py:96-98
@@ -251,6 +256,7 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
     if (tid == 0) tma_store_wait_read<0>();  // previous tile's h store has left sP
     fence_proxy_async_smem();
     __syncthreads();
+    TC_PROF(c, 2);
     // ---- D. dC = Kbar^T V --------------------------------------------------------------------
     if (warp == 0) {
       if (elect_one()) {
@@ -266,6 +272,7 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
     // ---- E. P = S . D (causal), row sums ------------------------------------------------------
     mbar_wait(&bar_s, par, 3);
     tc_fence_after_sync();
+    TC_PROF(c, 3);
     {
       const float x_t = (b_t - m_t) * kLog2e + log2f(p.scale);
       float rs = 0.f;
@@ -276,7 +283,7 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
           tmem_ld32(tS + lane_base + u * 32, v);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float pv = v[j] * exp2f(x_t + sy[u * 32 + j]);
+            float pv = v[j] * ex2_approx(x_t + sy[u * 32 + j]);
             pv = (u < rb || j <= lane) ? pv : 0.f;
             rs += pv;
             v[j] = pv;
@@ -293,6 +300,7 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
+    TC_PROF(c, 4);
     // ---- F. Hintra = P V ; Hinter = Q C_{k-1} -------------------------------------------------
     if (warp == 0) {
       tc_fence_after_sync();
@@ -313,6 +321,7 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
     // ---- G. state update C_k = gbar C_{k-1} + dC (overlaps the H MMAs) ------------------------
     mbar_wait(&bar_dc, par, 4);
     tc_fence_after_sync();
+    TC_PROF(c, 5);
     {
       float v[32];
       tmem_ld32(tDC + lane_base + ch * 32, v);  // M=64 layout: lanes 0-15 of each quadrant hold rows
@@ -327,8 +336,10 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       }
     }
     // ---- H. epilogue -----------------------------------------------------------------------
+    TC_PROF(c, 6);
     mbar_wait(&bar_h, par, 5);
     tc_fence_after_sync();
+    TC_PROF(c, 7);
     if (owns_c) store_row32<T>(sCc, drow, ch * 32, Creg);  // the Q C_{k-1} MMA has finished reading the old copy
     {
       float hi[32], hx[32];
@@ -349,6 +360,7 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
+    TC_PROF(c, 8);
     if (tid == 0) {
       tma_store_4d(&mapH, sP, 0, t0, hh, b);
       tma_store_commit();
@@ -380,6 +392,8 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
   __syncthreads();
   if (warp == 1) tmem_dealloc<256>(tmem);
 }
+
+long long* g_prof = nullptr;  // debug hook, see tensor_set_clock_buffer
 
 int num_sms() {
   static int n = 0;
@@ -427,6 +441,7 @@ struct TcBwParams {
   void *di, *df;
   int64_t di_sb, di_sh, di_ss, df_sb, df_sh, df_ss;
   float* dc0;
+  long long* prof;
 };
 
 struct BwSmem {
@@ -453,7 +468,7 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
   constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
   using SM = BwSmem;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   uint8_t* sQ = smem + SM::oQ;
   uint8_t* sK = smem + SM::oK;
   uint8_t* sV = smem + SM::oV;
@@ -535,6 +550,7 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
     const float m_prev = c > 0 ? mo[t0 - 1] : (p.m0 ? p.m0[bh] : 0.f);  // m of the state entering the tile
     const float m_next = mo[t0 + n_valid - 1];                            // m of the state leaving it
 
+    TC_PROF(it, 0);
     // ---- A. gates ---------------------------------------------------------------------------
     if (warp == 2) {
       float amax;
@@ -562,6 +578,7 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
     }
     if (tid == 0) tma_store_wait_read<0>();  // previous tile's dq/dk/dv staging buffers are free again
     __syncthreads();                         // #1 gates visible
+    TC_PROF(it, 1);
     const float g = sscal[0];
     const float b_t = sb[row], i_t = sy[row];
     const float rinv = valid ? 1.f / (n_t + p.eps) : 0.f;                 // bw.py:135
@@ -594,6 +611,7 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
     }
     fence_proxy_async_smem();
     __syncthreads();  // #3
+    TC_PROF(it, 2);
     // ---- D. ddC = Qt^T dH ; dQb = dH C_{k-1}^T -------------------------------------------------
     if (warp == 0) {
       if (elect_one()) {
@@ -614,6 +632,7 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
     // ---- E. W; Sb' = S.scale.W, dS = dSb.W ------------------------------------------------------
     mbar_wait(&bar_s, par, 13);
     tc_fence_after_sync();
+    TC_PROF(it, 3);
     {
       const float x_t = (b_t - m_t) * kLog2e;
       for (int u = 0; u < 4; ++u) {
@@ -624,7 +643,7 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
           tmem_ld32(tdSb + lane_base + u * 32, w);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float wg = exp2f(x_t + sy[u * 32 + j]) * rinv;
+            const float wg = ex2_approx(x_t + sy[u * 32 + j]) * rinv;
             const bool keep = valid && (u < rb || j <= lane);
             v[j] = keep ? v[j] * p.scale * wg : 0.f;
             w[j] = keep ? w[j] * wg : 0.f;
@@ -640,6 +659,7 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();  // #4
+    TC_PROF(it, 4);
     // ---- F. the five output MMAs ---------------------------------------------------------------
     if (warp == 0) {
       tc_fence_after_sync();
@@ -674,6 +694,7 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
     // ---- G. dC_{k-1} = gbar dC_k + ddC (registers) -----------------------------------------------
     mbar_wait(&bar_d, par, 14);
     tc_fence_after_sync();
+    TC_PROF(it, 5);
     {
       float v[32];
       tmem_ld32(tddC + lane_base + ch * 32, v);
@@ -683,8 +704,10 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       }
     }
     // ---- H. epilogue --------------------------------------------------------------------------------
+    TC_PROF(it, 6);
     mbar_wait(&bar_main, par, 15);
     tc_fence_after_sync();
+    TC_PROF(it, 7);
     if (tid == 0 && c > 0) issue_loads(c - 1);  // every MMA / thread is done with this tile's inputs
     if (owns_c) store_row32<T>(sdC, drow, ch * 32, dCreg);
     {
@@ -734,6 +757,7 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();  // #5
+    TC_PROF(it, 8);
     if (tid == 0) {
       tma_store_4d(&mapdQ, sQt, 0, t0, hh, b);
       tma_store_4d(&mapdV, sSb, 0, t0, hh, b);
@@ -825,6 +849,7 @@ int run_fw(const mlstm_b200_fw_args& a, void* c_states, cudaStream_t st) {
   p.n_out = a.n_out; p.m_out = a.m_out;
   p.c_last = a.c_last; p.n_last = a.n_last; p.m_last = a.m_last;
   p.store_states = c_states != nullptr;
+  p.prof = g_prof;
   const bool two_per_sm = (long)s.B * s.NH > num_sms();
   if (s.dtype == MLSTM_B200_BF16) {
     return two_per_sm ? launch_fw_d64<__nv_bfloat16, 1>(p, mq, mk, mv, mh, mcs, st)
@@ -849,6 +874,8 @@ BwWs bw_ws(const mlstm_b200_shape& s) {
 }
 
 }  // namespace
+
+void tensor_set_clock_buffer(void* dev_ptr) { g_prof = (long long*)dev_ptr; }
 
 bool tensor_supported(const mlstm_b200_shape& s) {
   if (s.dtype != MLSTM_B200_BF16 && s.dtype != MLSTM_B200_F16) return false;
@@ -911,6 +938,7 @@ int tensor_bw(const mlstm_b200_bw_args& a, cudaStream_t st) {
   p.di = a.di.ptr; p.di_sb = a.di.stride[0]; p.di_sh = a.di.stride[1]; p.di_ss = a.di.stride[2];
   p.df = a.df.ptr; p.df_sb = a.df.stride[0]; p.df_sh = a.df.stride[1]; p.df_ss = a.df.stride[2];
   p.dc0 = a.dc_initial;
+  p.prof = g_prof ? g_prof + 4096 : nullptr;
   if (s.dtype == MLSTM_B200_BF16) {
     auto kern = tc_bw_d64<__nv_bfloat16>;
     MLSTM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwSmem::kBytes));
