@@ -3,6 +3,12 @@
 // that walks the sequence in 128-token tiles and keeps the C / n / m state on chip
 // (C: fp32 master copy in registers + bf16 MMA operand copy in shared memory).
 //
+// CTA = 8 worker warps + 1 control warp.  Worker warp w owns tile rows 32*(w%4).. (== its TMEM
+// lane quadrant) and column half w/4.  The control warp issues every TMA copy and every
+// tcgen05.mma (one lane), and runs the gate scans (log-sigmoid cumsum, running max) one tile
+// ahead of the workers.  Hand-offs: workers -> control through named barriers (bar.arrive /
+// bar.sync), control -> workers through mbarriers (tcgen05.commit, TMA complete_tx).
+//
 // Forward, per 128-token tile k (math: SURVEY.md Appendix A; reference native/fw.py:29-221):
 //   S      = Q K^T                      tcgen05  M128 N128 K64   (A, B K-major from TMA)
 //   dC     = (abar.K)^T V               tcgen05  M64  N64  K128  (A, B MN-major)
@@ -23,38 +29,21 @@ namespace {
 
 using namespace sm100;
 
-constexpr int LT = 128;          // tokens per tile
-constexpr int kTcThreads = 256;  // 8 warps: warp w owns rows 32*(w%4).., column half w/4
+constexpr int LT = 128;           // tokens per tile
+constexpr int kWorkers = 256;     // 8 worker warps
+constexpr int kTcThreads = 288;   // + 1 control warp
+constexpr int kCtlWarp = 8;
 constexpr float kLog2e = 1.4426950408889634f;
+enum { NB_A = 1, NB_B = 2, NB_C = 3 };  // named barriers: operand ready / P ready / epilogue done
 
-struct TcFwParams {
-  int B, NH, S, NT;  // NT = number of 128-token tiles
-  float eps, scale;
-  const void *ig, *fg;
-  int64_t ig_sb, ig_sh, ig_ss, fg_sb, fg_sh, fg_ss;
-  const float *c0, *n0, *m0;
-  float *n_out, *m_out;
-  float *c_last, *n_last, *m_last;
-  int store_states;  // 1: TMA-store the bf16 copy of C entering every tile (consumed by the backward)
-  long long* prof;   // debug: per-tile phase clocks of CTA 0 (mlstm_b200_debug_set_clock_buffer)
+// per-tile gate vectors produced by the control warp (floats)
+struct GateBuf {
+  static constexpr int oB = 0, oI = LT, oPm = 2 * LT, oY = 3 * LT, oF = 4 * LT, oMt = 5 * LT, oNt = 6 * LT,
+                       oScal = 7 * LT, kFloats = 7 * LT + 8;
 };
+
 #define TC_PROF(tile, slot) \
-  if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) p.prof[(tile) * 16 + (slot)] = clock64()
-
-template <int D, int NSTAGE>
-struct FwSmem {
-  static constexpr int kTile = LT * 128;                 // one [128][64] 16-bit tile
-  static constexpr int oQ = 0;                           // [NSTAGE] Q tiles
-  static constexpr int oK = oQ + NSTAGE * kTile;
-  static constexpr int oV = oK + NSTAGE * kTile;
-  static constexpr int oKb = oV + NSTAGE * kTile;        // abar . K
-  static constexpr int oP = oKb + kTile;                 // P: two K-halves; h staging aliases half 0
-  static constexpr int oC = oP + 2 * kTile;              // bf16 copy of C (64 x 64), MMA B operand
-  static constexpr int oSmall = oC + D * 128;
-  // small region (floats): sb, sy, spm, sabar [LT each]; srs[2][LT]; sqn[2][LT]; sN[2][D]; scalars
-  static constexpr int kSmallFloats = 4 * LT + 2 * LT + 2 * LT + 2 * D + 8;
-  static constexpr int kBytes = oSmall + kSmallFloats * 4 + 1024 /*alignment slack*/;
-};
+  if (p.prof && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == kWorkers)) p.prof[(tile) * 16 + (slot)] = clock64()
 
 template <typename T>
 __device__ __forceinline__ uint32_t pack2(float a, float b);
@@ -80,7 +69,7 @@ __device__ __forceinline__ float2 unpack2<__half>(uint32_t u) {
 }
 
 // store 32 consecutive columns (col0 multiple of 32) of row `row` of a [128][64]-subtiled,
-// 128B-swizzled 16-bit matrix; `base` points at the first subtile, subtiles are kTile apart.
+// 128B-swizzled 16-bit matrix; `base` points at the first subtile, subtiles are LT*128 B apart.
 template <typename T>
 __device__ __forceinline__ void store_row32(uint8_t* base, int row, int col0, const float (&v)[32]) {
   uint8_t* tile = base + (col0 >> 6) * (LT * 128);
@@ -96,6 +85,82 @@ __device__ __forceinline__ void store_row32(uint8_t* base, int row, int col0, co
   }
 }
 
+// Column sums over the 32 rows held by a warp: lane L ends up with sum_rows v[.][L]
+// (butterfly transpose-reduce, 31 shuffles).  v is destroyed.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < off; ++j) {
+      const float keep = hi ? v[j + off] : v[j];
+      const float send = hi ? v[j] : v[j + off];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+// Control warp: gate vectors of one tile into `gb` (forward direction inside the tile).
+//   b (inclusive cumsum of logsigmoid f), raw i, prefix max of (i - b), y = (i - b) log2e, raw f
+template <typename T>
+__device__ __forceinline__ void control_gate_scan(float* gb, const T* ip, int64_t is, const T* fp, int64_t fs, int n_valid) {
+  const int lane = threadIdx.x & 31;
+  float fraw[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int t = lane * 4 + e;
+    fraw[e] = t < n_valid ? to_f32<T>(fp[(int64_t)t * fs]) : 0.f;
+  }
+  float amax;
+  const float g = chunk_gate_scan<T>(ip, is, fp, fs, LT, n_valid, gb + GateBuf::oB, gb + GateBuf::oI, gb + GateBuf::oPm, &amax);
+  __syncwarp();
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int t = lane * 4 + e;
+    gb[GateBuf::oY + t] = (gb[GateBuf::oI + t] - gb[GateBuf::oB + t]) * kLog2e;
+    gb[GateBuf::oF + t] = fraw[e];
+  }
+  if (lane == 0) {
+    gb[GateBuf::oScal + 0] = g;
+    gb[GateBuf::oScal + 1] = amax;
+  }
+}
+
+// =============================================================================================
+// Forward
+// =============================================================================================
+struct TcFwParams {
+  int B, NH, S, NT;  // NT = number of 128-token tiles
+  float eps, scale;
+  const void *ig, *fg;
+  int64_t ig_sb, ig_sh, ig_ss, fg_sb, fg_sh, fg_ss;
+  const float *c0, *n0, *m0;
+  float *n_out, *m_out;
+  float *c_last, *n_last, *m_last;
+  int store_states;  // 1: TMA-store the bf16 copy of C entering every tile (consumed by the backward)
+  long long* prof;   // debug: per-tile phase clocks of CTA 0 (mlstm_b200_debug_set_clock_buffer)
+};
+
+template <int NSTAGE>
+struct FwSmem {
+  static constexpr int D = 64;
+  static constexpr int kTile = LT * 128;  // one [128][64] 16-bit tile
+  static constexpr int oQ = 0;            // [NSTAGE] Q tiles
+  static constexpr int oK = oQ + NSTAGE * kTile;
+  static constexpr int oV = oK + NSTAGE * kTile;
+  static constexpr int oKb = oV + NSTAGE * kTile;          // abar . K
+  static constexpr int oP = oKb + kTile;                   // P: two K-halves
+  static constexpr int oH = NSTAGE == 2 ? oP + 2 * kTile : oP;  // h staging (aliases P half 0 when smem is tight)
+  static constexpr int oC = oH + (NSTAGE == 2 ? kTile : 2 * kTile);  // bf16 copy of C (64 x 64), MMA B operand
+  static constexpr int oSmall = oC + D * 128;
+  // floats: gates[2], srs[2][2][LT], sqn[2][2][LT], npart[2][4][D], sN[2][D]
+  static constexpr int fGates = 0, fRs = 2 * GateBuf::kFloats, fQn = fRs + 4 * LT, fNp = fQn + 4 * LT,
+                       fN = fNp + 8 * D, kSmallFloats = fN + 2 * D;
+  static constexpr int kBytes = oSmall + kSmallFloats * 4 + 1024 /*alignment slack*/;
+  static constexpr int kTmemCols = NSTAGE == 2 ? 512 : 256;
+};
+
 template <typename T, int NSTAGE>
 __global__ void __launch_bounds__(kTcThreads, NSTAGE == 1 ? 2 : 1)
 tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
@@ -103,320 +168,315 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
           const __grid_constant__ CUtensorMap mapCs, TcFwParams p) {
   constexpr int D = 64;
   constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
-  using SM = FwSmem<D, NSTAGE>;
+  using SM = FwSmem<NSTAGE>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
-  float* sb = (float*)(smem + SM::oSmall);  // chunk-local cumsum of logsigmoid(f)
-  float* sy = sb + LT;                      // (i_s - b_s) * log2e
-  float* spm = sy + LT;                     // prefix max of (i_s - b_s)
-  float* sabar = spm + LT;                  // exp(a_t - m_next)
-  float* srs = sabar + LT;                  // [2][LT] partial row sums of P
-  float* sqn = srs + 2 * LT;                // [2][LT] partial q . n
-  float* sN = sqn + 2 * LT;                 // [2][D]
-  float* sscal = sN + 2 * D;                // g, amax
-  __shared__ uint64_t bar_full[NSTAGE], bar_s, bar_dc, bar_h;
+  float* fsm = (float*)(smem + SM::oSmall);
+  uint8_t* sKb = smem + SM::oKb;
+  uint8_t* sP = smem + SM::oP;
+  uint8_t* sH = smem + SM::oH;
+  uint8_t* sC = smem + SM::oC;
+  __shared__ uint64_t bar_full[NSTAGE], bar_s, bar_dc, bar_h, bar_g[2], bar_n;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int rb = warp & 3, ch = warp >> 2;
-  const int row = rb * 32 + lane;  // tile row == TMEM lane of this thread
   const int bh = blockIdx.x, b = bh / p.NH, hh = bh % p.NH;
-  const uint32_t lane_base = (uint32_t)(rb * 32) << 16;
 
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) mbar_init(&bar_full[s], 1);
     mbar_init(&bar_s, 1);
     mbar_init(&bar_dc, 1);
     mbar_init(&bar_h, 1);
+    mbar_init(&bar_g[0], 1);
+    mbar_init(&bar_g[1], 1);
+    mbar_init(&bar_n, D);
     fence_mbar_init();
-    prefetch_tmap(&mapQ);
-    prefetch_tmap(&mapK);
-    prefetch_tmap(&mapV);
-    prefetch_tmap(&mapH);
   }
-  if (warp == 1) tmem_alloc<256>(&tmem_base_s);
-
-  // state: fp32 master copy of C in registers of the threads with lane < 16:
+  if (warp == kCtlWarp) {
+    tmem_alloc<SM::kTmemCols>(&tmem_base_s);
+    if (lane == 0) {
+      prefetch_tmap(&mapQ); prefetch_tmap(&mapK); prefetch_tmap(&mapV); prefetch_tmap(&mapH); prefetch_tmap(&mapCs);
+    }
+  }
+  // worker-side state: fp32 master copy of C in the registers of lanes < 16 of every worker warp:
   // row d = 16*rb + lane (M=64 TMEM layout), columns 32*ch .. 32*ch+31
-  float Creg[32];
+  const int rb = warp & 3, ch = (warp >> 2) & 1;
+  const int row = rb * 32 + lane;  // tile row == TMEM lane of this thread
+  const uint32_t lane_base = (uint32_t)(rb * 32) << 16;
   const int drow = rb * 16 + (lane & 15);
-  const bool owns_c = lane < 16;
+  const bool owns_c = warp < kCtlWarp && lane < 16;
+  float Creg[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) Creg[j] = 0.f;
-  if (p.c0 && owns_c) {
-    const float* src = p.c0 + ((int64_t)bh * D + drow) * D + ch * 32;
+  if (warp < kCtlWarp) {
+    if (p.c0 && owns_c) {
+      const float* src = p.c0 + ((int64_t)bh * D + drow) * D + ch * 32;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) Creg[j] = src[j];
+      for (int j = 0; j < 32; ++j) Creg[j] = src[j];
+    }
+    if (owns_c) store_row32<T>(sC, drow, ch * 32, Creg);
+    if (tid < D) fsm[SM::fN + tid] = p.n0 ? p.n0[(int64_t)bh * D + tid] : 0.f;
+    fence_proxy_async_smem();
   }
-  if (owns_c) store_row32<T>(smem + SM::oC, drow, ch * 32, Creg);  // [64][64] tile: rows < 64 of subtile 0
-  if (tid < D) sN[tid] = p.n0 ? p.n0[(int64_t)bh * D + tid] : 0.f;
-  float m_run = p.m0 ? p.m0[bh] : 0.f;
-  fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t tS = tmem, tHi = tmem, tHx = tmem + 64, tDC = tmem + 128;
-
-  constexpr uint32_t kStageBytes = 3 * SM::kTile;
-  if (tid == 0) {
-    for (int s = 0; s < NSTAGE && s < p.NT; ++s) {
-      mbar_expect_tx(&bar_full[s], kStageBytes);
-      tma_load_4d(smem + SM::oQ + s * SM::kTile, &mapQ, &bar_full[s], 0, s * LT, hh, b);
-      tma_load_4d(smem + SM::oK + s * SM::kTile, &mapK, &bar_full[s], 0, s * LT, hh, b);
-      tma_load_4d(smem + SM::oV + s * SM::kTile, &mapV, &bar_full[s], 0, s * LT, hh, b);
-    }
-  }
+  // TMEM columns: with 512 columns S is double-buffered by tile parity and nothing aliases
+  const uint32_t tS0 = tmem, tS1 = NSTAGE == 2 ? tmem + 128 : tmem;
+  const uint32_t tHi = NSTAGE == 2 ? tmem + 256 : tmem, tHx = tHi + 64, tDC = NSTAGE == 2 ? tmem + 384 : tmem + 128;
 
   const T* ip = (const T*)p.ig + b * p.ig_sb + hh * p.ig_sh;
   const T* fp = (const T*)p.fg + b * p.fg_sb + hh * p.fg_sh;
-  int cur = 0;
+  constexpr uint32_t kStageBytes = 3 * SM::kTile;
 
-  for (int c = 0; c < p.NT; ++c) {
-    const int s = c % NSTAGE;
-    const uint32_t par_full = (c / NSTAGE) & 1, par = c & 1;
-    uint8_t* sQ = smem + SM::oQ + s * SM::kTile;
-    uint8_t* sK = smem + SM::oK + s * SM::kTile;
-    uint8_t* sV = smem + SM::oV + s * SM::kTile;
-    uint8_t* sKb = smem + SM::oKb;
-    uint8_t* sP = smem + SM::oP;
-    uint8_t* sCc = smem + SM::oC;
-    const float* sNc = sN + cur * D;
-    float* sNn = sN + (cur ^ 1) * D;
-    const int t0 = c * LT;
-    const int n_valid = min(LT, p.S - t0);
+  if (warp == kCtlWarp) {
+    // =========================== control warp ===================================================
+    auto load_stage = [&](int s, int c) {
+      mbar_expect_tx(&bar_full[s], kStageBytes);
+      tma_load_4d(smem + SM::oQ + s * SM::kTile, &mapQ, &bar_full[s], 0, c * LT, hh, b);
+      tma_load_4d(smem + SM::oK + s * SM::kTile, &mapK, &bar_full[s], 0, c * LT, hh, b);
+      tma_load_4d(smem + SM::oV + s * SM::kTile, &mapV, &bar_full[s], 0, c * LT, hh, b);
+    };
+    if (lane == 0)
+      for (int s = 0; s < NSTAGE && s < p.NT; ++s) load_stage(s, s);
+    control_gate_scan<T>(fsm + SM::fGates, ip, p.ig_ss, fp, p.fg_ss, min(LT, p.S));
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bar_g[0]);
 
-    TC_PROF(c, 0);
-    // ---- A. gates of this tile (one warp, warp-shuffle scans) -------------------------------
-    if (warp == 2) {
-      float amax;
-      float g = chunk_gate_scan<T>(ip + (int64_t)t0 * p.ig_ss, p.ig_ss, fp + (int64_t)t0 * p.fg_ss, p.fg_ss, LT, n_valid, sb, sy,
-                                   spm, &amax);
-      if (lane == 0) {
-        sscal[0] = g;
-        sscal[1] = amax;
-      }
-    }
-    // ---- B. S = Q K^T -----------------------------------------------------------------------
-    if (warp == 0) {
-      mbar_wait(&bar_full[s], par_full, 1);
+    constexpr uint32_t id_s = umma_idesc(128, 128, false, false, kBf16);
+    constexpr uint32_t id_dc = umma_idesc(64, 64, true, true, kBf16);
+    constexpr uint32_t id_h = umma_idesc(128, 64, false, true, kBf16);
+    const uint64_t dKb = umma_smem_desc(smem_u32(sKb), SM::kTile, 1024);
+    const uint64_t dP = umma_smem_desc(smem_u32(sP), 0, 1024);
+    const uint64_t dC = umma_smem_desc(smem_u32(sC), D * 128, 1024);
+    auto issue_s = [&](int c) {  // S(c) = Q K^T into the parity buffer
+      const int s = c % NSTAGE;
+      mbar_wait(&bar_full[s], (c / NSTAGE) & 1, 1);
       tc_fence_after_sync();
-      if (elect_one()) {
-        constexpr uint32_t idesc = umma_idesc(128, 128, false, false, kBf16);
+      const uint64_t dQ = umma_smem_desc(smem_u32(smem + SM::oQ + s * SM::kTile), 0, 1024);
+      const uint64_t dK = umma_smem_desc(smem_u32(smem + SM::oK + s * SM::kTile), 0, 1024);
+      const uint32_t tS = (c & 1) ? tS1 : tS0;
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk)
-          umma_f16(tS, umma_smem_desc(smem_u32(sQ) + kk * 32, 0, 1024), umma_smem_desc(smem_u32(sK) + kk * 32, 0, 1024),
-                   idesc, kk > 0);
-        umma_commit(&bar_s);
+      for (int kk = 0; kk < D / 16; ++kk)
+        umma_f16(tS, umma_desc_advance(dQ, kk * 32), umma_desc_advance(dK, kk * 32), id_s, kk > 0);
+      umma_commit(&bar_s);
+    };
+
+    for (int c = 0; c < p.NT; ++c) {
+      const int s = c % NSTAGE;
+      const uint64_t dQ = umma_smem_desc(smem_u32(smem + SM::oQ + s * SM::kTile), 0, 1024);
+      const uint64_t dV = umma_smem_desc(smem_u32(smem + SM::oV + s * SM::kTile), SM::kTile, 1024);
+      TC_PROF(c, 9);
+      if (lane == 0) {
+        tma_store_wait_read<0>();  // h staging / sC of the previous tile have been read
+        if (p.store_states) {      // C_{k-1} (bf16 operand copy) -> c_states[b, h, tile]
+          tma_store_4d(&mapCs, sC, 0, c * D, hh, b);
+          tma_store_commit();
+        }
+        if (NSTAGE == 1 || c == 0) issue_s(c);
       }
       __syncwarp();
-    }
-    if (tid == 0 && p.store_states) {  // C_{k-1} (bf16 operand copy) -> c_states[b, h, tile]
-      tma_store_4d(&mapCs, sCc, 0, c * D, hh, b);
-      tma_store_commit();
-    }
-    __syncthreads();  // gates visible
-    TC_PROF(c, 1);
-    // ---- C. per-token factors; Kbar = abar . K ----------------------------------------------
-    const float g = sscal[0];
-    const float m_next = fmaxf(g + m_run, g + sscal[1]);  // fw.py:96-98
-    const float gbar = __expf(g + m_run - m_next);        // fw.py:106
-    const float b_t = sb[row], i_t = sy[row];             // sy holds raw i at this point
-    const float m_t = b_t + fmaxf(m_run, spm[row]);       // fw.py:178-184
-    __syncthreads();                                      // everyone has read raw i from sy
-    if (ch == 0) sy[row] = (i_t - b_t) * kLog2e;
-    mbar_wait(&bar_full[s], par_full, 2);  // K tile landed (generic-proxy read below)
-    {
-      const float ab = __expf(g - b_t + i_t - m_next);  // fw.py:102 (exp(-inf) = 0 for tail tokens)
+      named_sync(NB_A, kTcThreads);  // Kbar written
+      TC_PROF(c, 10);
+      if (lane == 0) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t off = swz128(row, ch * 32 + 8 * j);
-        uint4 u = *reinterpret_cast<const uint4*>(sK + off);
-        float2 a0 = unpack2<T>(u.x), a1 = unpack2<T>(u.y), a2 = unpack2<T>(u.z), a3 = unpack2<T>(u.w);
-        u.x = pack2<T>(a0.x * ab, a0.y * ab);
-        u.y = pack2<T>(a1.x * ab, a1.y * ab);
-        u.z = pack2<T>(a2.x * ab, a2.y * ab);
-        u.w = pack2<T>(a3.x * ab, a3.y * ab);
-        *reinterpret_cast<uint4*>(sKb + off) = u;
-      }
-    }
-    // partial q . n_{k-1} over this thread's 32 columns
-    {
-      float qn = 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 u = *reinterpret_cast<const uint4*>(sQ + swz128(row, ch * 32 + 8 * j));
-        float2 a0 = unpack2<T>(u.x), a1 = unpack2<T>(u.y), a2 = unpack2<T>(u.z), a3 = unpack2<T>(u.w);
-        const float* nn = sNc + ch * 32 + 8 * j;
-        qn += a0.x * nn[0] + a0.y * nn[1] + a1.x * nn[2] + a1.y * nn[3] + a2.x * nn[4] + a2.y * nn[5] + a3.x * nn[6] +
-              a3.y * nn[7];
-      }
-      sqn[ch * LT + row] = qn;
-    }
-    if (tid == 0) tma_store_wait_read<0>();  // previous tile's h store has left sP
-    fence_proxy_async_smem();
-    __syncthreads();
-    TC_PROF(c, 2);
-    // ---- D. dC = Kbar^T V --------------------------------------------------------------------
-    if (warp == 0) {
-      if (elect_one()) {
-        constexpr uint32_t idesc = umma_idesc(64, 64, true, true, kBf16);
-#pragma unroll
-        for (int kk = 0; kk < LT / 16; ++kk)
-          umma_f16(tDC, umma_smem_desc(smem_u32(sKb) + kk * 2048, LT * 128, 1024),
-                   umma_smem_desc(smem_u32(sV) + kk * 2048, LT * 128, 1024), idesc, kk > 0);
+        for (int kk = 0; kk < LT / 16; ++kk)  // dC = Kbar^T V
+          umma_f16(tDC, umma_desc_advance(dKb, kk * 2048), umma_desc_advance(dV, kk * 2048), id_dc, kk > 0);
         umma_commit(&bar_dc);
       }
       __syncwarp();
-    }
-    // ---- E. P = S . D (causal), row sums ------------------------------------------------------
-    mbar_wait(&bar_s, par, 3);
-    tc_fence_after_sync();
-    TC_PROF(c, 3);
-    {
-      const float x_t = (b_t - m_t) * kLog2e + log2f(p.scale);
-      float rs = 0.f;
-      for (int u = 0; u < 4; ++u) {
-        if ((u & 1) != ch) continue;  // warp-uniform
-        float v[32];
-        if (u <= rb) {
-          tmem_ld32(tS + lane_base + u * 32, v);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float pv = v[j] * ex2_approx(x_t + sy[u * 32 + j]);
-            pv = (u < rb || j <= lane) ? pv : 0.f;
-            rs += pv;
-            v[j] = pv;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
-        }
-        store_row32<T>(sP, row, u * 32, v);
+      if (c + 1 < p.NT) {  // gates of the next tile, one tile ahead of the workers
+        const int t1 = (c + 1) * LT;
+        control_gate_scan<T>(fsm + SM::fGates + ((c + 1) & 1) * GateBuf::kFloats, ip + (int64_t)t1 * p.ig_ss, p.ig_ss,
+                             fp + (int64_t)t1 * p.fg_ss, p.fg_ss, min(LT, p.S - t1));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_g[(c + 1) & 1]);
       }
-      srs[ch * LT + row] = rs;
-    }
-    if (tid == 0) tma_store_wait_read<0>();  // the c_states store has read sC (rewritten in H)
-    fence_proxy_async_smem();
-    tc_fence_before_sync();
-    __syncthreads();
-    TC_PROF(c, 4);
-    // ---- F. Hintra = P V ; Hinter = Q C_{k-1} -------------------------------------------------
-    if (warp == 0) {
-      tc_fence_after_sync();
-      if (elect_one()) {
-        constexpr uint32_t idesc = umma_idesc(128, 64, false, true, kBf16);
+      TC_PROF(c, 11);
+      named_sync(NB_B, kTcThreads);  // P written
+      TC_PROF(c, 12);
+      if (lane == 0) {
+        tc_fence_after_sync();
+        tma_store_wait_read<0>();  // the c_states store has read sC (workers rewrite it after bar_h)
 #pragma unroll
-        for (int kk = 0; kk < LT / 16; ++kk)
-          umma_f16(tHi, umma_smem_desc(smem_u32(sP) + (kk / 4) * SM::kTile + (kk % 4) * 32, 0, 1024),
-                   umma_smem_desc(smem_u32(sV) + kk * 2048, LT * 128, 1024), idesc, kk > 0);
+        for (int kk = 0; kk < LT / 16; ++kk)  // Hintra = P V
+          umma_f16(tHi, umma_desc_advance(dP, (kk / 4) * SM::kTile + (kk % 4) * 32), umma_desc_advance(dV, kk * 2048), id_h,
+                   kk > 0);
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk)
-          umma_f16(tHx, umma_smem_desc(smem_u32(sQ) + kk * 32, 0, 1024),
-                   umma_smem_desc(smem_u32(sCc) + kk * 2048, D * 128, 1024), idesc, kk > 0);
+        for (int kk = 0; kk < D / 16; ++kk)  // Hinter = Q C_{k-1}
+          umma_f16(tHx, umma_desc_advance(dQ, kk * 32), umma_desc_advance(dC, kk * 2048), id_h, kk > 0);
         umma_commit(&bar_h);
+        if (NSTAGE == 2 && c + 1 < p.NT) issue_s(c + 1);  // S of the next tile into the other TMEM buffer
+      }
+      __syncwarp();
+      TC_PROF(c, 13);
+      named_sync(NB_C, kTcThreads);  // h staged, every worker is done with this tile
+      TC_PROF(c, 14);
+      if (lane == 0) {
+        tma_store_4d(&mapH, sH, 0, c * LT, hh, b);
+        tma_store_commit();
+        if (c + NSTAGE < p.NT) load_stage(s, c + NSTAGE);
       }
       __syncwarp();
     }
-    // ---- G. state update C_k = gbar C_{k-1} + dC (overlaps the H MMAs) ------------------------
-    mbar_wait(&bar_dc, par, 4);
-    tc_fence_after_sync();
-    TC_PROF(c, 5);
-    {
-      float v[32];
-      tmem_ld32(tDC + lane_base + ch * 32, v);  // M=64 layout: lanes 0-15 of each quadrant hold rows
-      if (owns_c) {
+    if (lane == 0) tma_store_wait_all<0>();
+  } else {
+    // =========================== worker warps ===================================================
+    float m_run = p.m0 ? p.m0[bh] : 0.f;
+    int cur = 0;
+    for (int c = 0; c < p.NT; ++c) {
+      const int s = c % NSTAGE, pb = c & 1;
+      const uint32_t par_full = (c / NSTAGE) & 1, par = c & 1;
+      const uint8_t* sQ = smem + SM::oQ + s * SM::kTile;
+      const uint8_t* sK = smem + SM::oK + s * SM::kTile;
+      const float* gb = fsm + SM::fGates + pb * GateBuf::kFloats;
+      float* srs = fsm + SM::fRs + pb * 2 * LT;
+      float* sqn = fsm + SM::fQn + pb * 2 * LT;
+      float* snp = fsm + SM::fNp + pb * 4 * D;
+      const float* sNc = fsm + SM::fN + cur * D;
+      float* sNn = fsm + SM::fN + (cur ^ 1) * D;
+      const int t0 = c * LT;
+      const int n_valid = min(LT, p.S - t0);
+      const uint32_t tS = (c & 1) ? tS1 : tS0;
+
+      TC_PROF(c, 0);
+      mbar_wait(&bar_g[pb], (c >> 1) & 1, 2);
+      const float g = gb[GateBuf::oScal], amax = gb[GateBuf::oScal + 1];
+      const float m_next = fmaxf(g + m_run, g + amax);                  // fw.py:96-98
+      const float gbar = __expf(g + m_run - m_next);                    // fw.py:106
+      const float b_t = gb[GateBuf::oB + row], i_t = gb[GateBuf::oI + row];
+      const float m_t = b_t + fmaxf(m_run, gb[GateBuf::oPm + row]);     // fw.py:178-184
+      mbar_wait(&bar_full[s], par_full, 3);
+      if (c > 0) mbar_wait(&bar_n, (c - 1) & 1, 4);  // n_{k-1} finalised
+      TC_PROF(c, 1);
+      // ---- Kbar = abar . K (this thread: row, 32 columns); column sums for n; partial q . n ------
+      {
+        const float ab = __expf(g - b_t + i_t - m_next);  // fw.py:102 (exp(-inf) = 0 for tail tokens)
+        float kb[32];
+        float qn = 0.f;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) Creg[j] = gbar * Creg[j] + v[j];
-        if (ch == 0) {  // n_k = gbar n_{k-1} + column sums of Kbar (fw.py:116)
-          float acc = 0.f;
-          for (int t = 0; t < LT; ++t) acc += to_f32<T>(*reinterpret_cast<const T*>(sKb + swz128(t, drow)));
-          sNn[drow] = gbar * sNc[drow] + acc;
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t off = swz128(row, ch * 32 + 8 * j);
+          uint4 u = *reinterpret_cast<const uint4*>(sK + off);
+          float2 a0 = unpack2<T>(u.x), a1 = unpack2<T>(u.y), a2 = unpack2<T>(u.z), a3 = unpack2<T>(u.w);
+          kb[8 * j + 0] = a0.x * ab; kb[8 * j + 1] = a0.y * ab; kb[8 * j + 2] = a1.x * ab; kb[8 * j + 3] = a1.y * ab;
+          kb[8 * j + 4] = a2.x * ab; kb[8 * j + 5] = a2.y * ab; kb[8 * j + 6] = a3.x * ab; kb[8 * j + 7] = a3.y * ab;
+          uint4 q = *reinterpret_cast<const uint4*>(sQ + off);
+          float2 q0 = unpack2<T>(q.x), q1 = unpack2<T>(q.y), q2 = unpack2<T>(q.z), q3 = unpack2<T>(q.w);
+          const float4 n0 = *reinterpret_cast<const float4*>(sNc + ch * 32 + 8 * j);
+          const float4 n1 = *reinterpret_cast<const float4*>(sNc + ch * 32 + 8 * j + 4);
+          qn += q0.x * n0.x + q0.y * n0.y + q1.x * n0.z + q1.y * n0.w + q2.x * n1.x + q2.y * n1.y + q3.x * n1.z + q3.y * n1.w;
+        }
+        store_row32<T>(sKb, row, ch * 32, kb);
+        sqn[ch * LT + row] = qn;
+        const float cs = warp_colsum32(kb, lane);  // sum over this warp's 32 rows of column ch*32 + lane
+        snp[rb * D + ch * 32 + lane] = cs;
+      }
+      fence_proxy_async_smem();
+      named_arrive(NB_A, kTcThreads);
+      TC_PROF(c, 2);
+      // ---- P = S . D (causal), row sums ----------------------------------------------------------
+      mbar_wait(&bar_s, par, 5);
+      tc_fence_after_sync();
+      TC_PROF(c, 3);
+      {
+        const float x_t = (b_t - m_t) * kLog2e + log2f(p.scale);
+        const float* sy = gb + GateBuf::oY;
+        float rs = 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if ((u & 1) != ch) continue;  // warp-uniform
+          float v[32];
+          if (u <= rb) {
+            tmem_ld32(tS + lane_base + u * 32, v);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 y = *reinterpret_cast<const float4*>(sy + u * 32 + 4 * j4);
+              const float yy[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = 4 * j4 + e;
+                float pv = v[j] * ex2_approx(x_t + yy[e]);
+                pv = (u < rb || j <= lane) ? pv : 0.f;
+                rs += pv;
+                v[j] = pv;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+          store_row32<T>(sP, row, u * 32, v);
+        }
+        srs[ch * LT + row] = rs;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      named_arrive(NB_B, kTcThreads);
+      TC_PROF(c, 4);
+      // ---- state update C_k = gbar C_{k-1} + dC; n_k -------------------------------------------------
+      mbar_wait(&bar_dc, par, 6);
+      tc_fence_after_sync();
+      TC_PROF(c, 5);
+      {
+        float v[32];
+        tmem_ld32(tDC + lane_base + ch * 32, v);  // M=64 layout: lanes 0-15 of each quadrant hold rows
+        if (owns_c) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) Creg[j] = gbar * Creg[j] + v[j];
+        }
+        if (tid < D) {  // n_k = gbar n_{k-1} + column sums of Kbar (fw.py:116)
+          sNn[tid] = gbar * sNc[tid] + ((snp[tid] + snp[D + tid]) + (snp[2 * D + tid] + snp[3 * D + tid]));
+          mbar_arrive(&bar_n);
         }
       }
-    }
-    // ---- H. epilogue -----------------------------------------------------------------------
-    TC_PROF(c, 6);
-    mbar_wait(&bar_h, par, 5);
-    tc_fence_after_sync();
-    TC_PROF(c, 7);
-    if (owns_c) store_row32<T>(sCc, drow, ch * 32, Creg);  // the Q C_{k-1} MMA has finished reading the old copy
-    {
-      float hi[32], hx[32];
-      tmem_ld32(tHi + lane_base + ch * 32, hi);
-      tmem_ld32(tHx + lane_base + ch * 32, hx);
-      const float bq = __expf(b_t + m_run - m_t) * p.scale;                       // fw.py:197-198
-      const float den = bq * (sqn[row] + sqn[LT + row]) + srs[row] + srs[LT + row];  // fw.py:204-206
-      const float nmax = fmaxf(fabsf(den), __expf(-m_t));                          // fw.py:208-210
-      const float inv = 1.f / (nmax + p.eps);
+      TC_PROF(c, 6);
+      // ---- epilogue -----------------------------------------------------------------------------------
+      mbar_wait(&bar_h, par, 7);
+      tc_fence_after_sync();
+      TC_PROF(c, 7);
+      if (owns_c) store_row32<T>(sC, drow, ch * 32, Creg);  // the Q C_{k-1} MMA has finished reading the old copy
+      {
+        uint32_t hi[32], hx[32];
+        tmem_ld32_nowait(tHi + lane_base + ch * 32, hi);
+        tmem_ld32_nowait(tHx + lane_base + ch * 32, hx);
+        const float bq = __expf(b_t + m_run - m_t) * p.scale;                          // fw.py:197-198
+        const float den = bq * (sqn[row] + sqn[LT + row]) + srs[row] + srs[LT + row];  // fw.py:204-206
+        const float nmax = fmaxf(fabsf(den), __expf(-m_t));                            // fw.py:208-210
+        const float inv = 1.f / (nmax + p.eps);
+        tmem_ld_wait();
+        float o[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) hi[j] = (hi[j] + bq * hx[j]) * inv;  // fw.py:200-212
-      store_row32<T>(sP, row, ch * 32, hi);  // h staging aliases P half 0 (PV MMA has completed)
-      if (ch == 0 && row < n_valid) {
-        p.n_out[(int64_t)bh * p.S + t0 + row] = nmax;
-        p.m_out[(int64_t)bh * p.S + t0 + row] = m_t;
+        for (int j = 0; j < 32; ++j) o[j] = (__uint_as_float(hi[j]) + bq * __uint_as_float(hx[j])) * inv;  // fw.py:200-212
+        store_row32<T>(sH, row, ch * 32, o);
+        if (ch == 0 && row < n_valid) {
+          p.n_out[(int64_t)bh * p.S + t0 + row] = nmax;
+          p.m_out[(int64_t)bh * p.S + t0 + row] = m_t;
+        }
       }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      named_arrive(NB_C, kTcThreads);
+      TC_PROF(c, 8);
+      m_run = m_next;
+      cur ^= 1;
     }
-    fence_proxy_async_smem();
-    tc_fence_before_sync();
-    __syncthreads();
-    TC_PROF(c, 8);
-    if (tid == 0) {
-      tma_store_4d(&mapH, sP, 0, t0, hh, b);
-      tma_store_commit();
-      // ---- I. refill this stage with tile c + NSTAGE ------------------------------------------
-      const int cn = c + NSTAGE;
-      if (cn < p.NT) {
-        mbar_expect_tx(&bar_full[s], kStageBytes);
-        tma_load_4d(sQ, &mapQ, &bar_full[s], 0, cn * LT, hh, b);
-        tma_load_4d(sK, &mapK, &bar_full[s], 0, cn * LT, hh, b);
-        tma_load_4d(sV, &mapV, &bar_full[s], 0, cn * LT, hh, b);
-      }
-    }
-    m_run = m_next;
-    cur ^= 1;
-  }
-
-  // final states (fw.py:302-309)
-  if (p.c_last) {
-    if (owns_c) {
-      float* dst = p.c_last + ((int64_t)bh * D + drow) * D + ch * 32;
+    // final states (fw.py:302-309)
+    if (p.c_last) {
+      if (owns_c) {
+        float* dst = p.c_last + ((int64_t)bh * D + drow) * D + ch * 32;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) dst[j] = Creg[j];
+        for (int j = 0; j < 32; ++j) dst[j] = Creg[j];
+      }
+      if (tid < D) p.n_last[(int64_t)bh * D + tid] = fsm[SM::fN + cur * D + tid];  // own write (tid < D finalises n)
+      if (tid == 0) p.m_last[bh] = m_run;
     }
-    if (tid < D) p.n_last[(int64_t)bh * D + tid] = sN[cur * D + tid];
-    if (tid == 0) p.m_last[bh] = m_run;
   }
-  if (tid == 0) tma_store_wait_all<0>();
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<256>(tmem);
+  if (warp == kCtlWarp) tmem_dealloc<SM::kTmemCols>(tmem);
 }
-
-long long* g_prof = nullptr;  // debug hook, see tensor_set_clock_buffer
-
-int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return n;
-}
-
-template <typename T, int NSTAGE>
-int launch_fw_d64(const TcFwParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
-                  const CUtensorMap& mh, const CUtensorMap& mcs, cudaStream_t st) {
-  using SM = FwSmem<64, NSTAGE>;
-  auto kern = tc_fw_d64<T, NSTAGE>;
-  MLSTM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
-  kern<<<p.B * p.NH, kTcThreads, SM::kBytes, st>>>(mq, mk, mv, mh, mcs, p);
-  count_launch();
-  MLSTM_CUDA_CHECK(cudaGetLastError());
-  return 0;
-}
-
 
 // =============================================================================================
 // Backward: one reverse sweep per (batch, head) over 128-token tiles (reference native/bw.py).
@@ -445,15 +505,18 @@ struct TcBwParams {
 };
 
 struct BwSmem {
+  static constexpr int D = 64;
   static constexpr int kTile = LT * 128;
   static constexpr int oQ = 0, oK = kTile, oV = 2 * kTile, odH = 3 * kTile;
-  static constexpr int oQt = 4 * kTile;       // wq . Q   (dq staging after its MMA)
+  static constexpr int oQt = 4 * kTile;       // wq . Q
   static constexpr int oSb = 5 * kTile;       // Sb' two halves (dv staging in half 0)
   static constexpr int odS = 7 * kTile;       // dS  two halves (dk staging in half 0)
-  static constexpr int oCs = 9 * kTile;       // C_{k-1}, 64 x 64 bf16 (TMA)
+  static constexpr int odQ = 9 * kTile;       // dq staging
+  static constexpr int oCs = 10 * kTile;      // C_{k-1}, 64 x 64 bf16 (TMA)
   static constexpr int odC = oCs + 64 * 128;  // dC_k bf16 operand copy
   static constexpr int oSmall = odC + 64 * 128;
-  static constexpr int kSmallFloats = 3 * LT + 6 * LT + 8;
+  // floats: gates[2], spart[2][6][LT]
+  static constexpr int fGates = 0, fPart = 2 * GateBuf::kFloats, kSmallFloats = fPart + 12 * LT;
   static constexpr int kBytes = oSmall + kSmallFloats * 4 + 1024;
   static constexpr uint32_t kLoadBytes = 4 * kTile + 64 * 128;
 };
@@ -468,7 +531,7 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
   constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
   using SM = BwSmem;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem + SM::oQ;
   uint8_t* sK = smem + SM::oK;
   uint8_t* sV = smem + SM::oV;
@@ -476,45 +539,49 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
   uint8_t* sQt = smem + SM::oQt;
   uint8_t* sSb = smem + SM::oSb;
   uint8_t* sdS = smem + SM::odS;
+  uint8_t* sdQ = smem + SM::odQ;
   uint8_t* sCs = smem + SM::oCs;
   uint8_t* sdC = smem + SM::odC;
-  float* sb = (float*)(smem + SM::oSmall);
-  float* sy = sb + LT;
-  float* spm = sy + LT;
-  float* spart = spm + LT;  // [3][2][LT]: q.dq, k.dk, v.dv partials per column half
-  float* sscal = spart + 6 * LT;
-  __shared__ uint64_t bar_full, bar_s, bar_d, bar_main;
+  float* fsm = (float*)(smem + SM::oSmall);
+  __shared__ uint64_t bar_full, bar_s, bar_d, bar_main, bar_g[2];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int rb = warp & 3, ch = warp >> 2;
-  const int row = rb * 32 + lane;
   const int bh = blockIdx.x, b = bh / p.NH, hh = bh % p.NH;
-  const uint32_t lane_base = (uint32_t)(rb * 32) << 16;
 
   if (tid == 0) {
     mbar_init(&bar_full, 1);
     mbar_init(&bar_s, 1);
     mbar_init(&bar_d, 1);
     mbar_init(&bar_main, 1);
+    mbar_init(&bar_g[0], 1);
+    mbar_init(&bar_g[1], 1);
     fence_mbar_init();
-    prefetch_tmap(&mapQ); prefetch_tmap(&mapK); prefetch_tmap(&mapV); prefetch_tmap(&mapdH);
-    prefetch_tmap(&mapCs); prefetch_tmap(&mapdQ); prefetch_tmap(&mapdK); prefetch_tmap(&mapdV);
   }
-  if (warp == 1) tmem_alloc<512>(&tmem_base_s);
-
-  float dCreg[32];
+  if (warp == kCtlWarp) {
+    tmem_alloc<512>(&tmem_base_s);
+    if (lane == 0) {
+      prefetch_tmap(&mapQ); prefetch_tmap(&mapK); prefetch_tmap(&mapV); prefetch_tmap(&mapdH);
+      prefetch_tmap(&mapCs); prefetch_tmap(&mapdQ); prefetch_tmap(&mapdK); prefetch_tmap(&mapdV);
+    }
+  }
+  const int rb = warp & 3, ch = (warp >> 2) & 1;
+  const int row = rb * 32 + lane;
+  const uint32_t lane_base = (uint32_t)(rb * 32) << 16;
   const int drow = rb * 16 + (lane & 15);
-  const bool owns_c = lane < 16;
+  const bool owns_c = warp < kCtlWarp && lane < 16;
+  float dCreg[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) dCreg[j] = 0.f;
-  if (p.dc_last && owns_c) {
-    const float* src = p.dc_last + ((int64_t)bh * D + drow) * D + ch * 32;
+  if (warp < kCtlWarp) {
+    if (p.dc_last && owns_c) {
+      const float* src = p.dc_last + ((int64_t)bh * D + drow) * D + ch * 32;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) dCreg[j] = src[j];
+      for (int j = 0; j < 32; ++j) dCreg[j] = src[j];
+    }
+    if (owns_c) store_row32<T>(sdC, drow, ch * 32, dCreg);
+    fence_proxy_async_smem();
   }
-  if (owns_c) store_row32<T>(sdC, drow, ch * 32, dCreg);
-  fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -523,290 +590,354 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
   const uint32_t tdV1 = tmem, tdV2 = tmem + 64, tdK1 = tmem + 128, tdK2 = tmem + 192;
   const uint32_t tdQa = tmem + 256, tdQb = tmem + 320, tddC = tmem + 384;
 
-  auto issue_loads = [&](int c) {
-    mbar_expect_tx(&bar_full, SM::kLoadBytes);
-    tma_load_4d(sQ, &mapQ, &bar_full, 0, c * LT, hh, b);
-    tma_load_4d(sK, &mapK, &bar_full, 0, c * LT, hh, b);
-    tma_load_4d(sV, &mapV, &bar_full, 0, c * LT, hh, b);
-    tma_load_4d(sdH, &mapdH, &bar_full, 0, c * LT, hh, b);
-    tma_load_4d(sCs, &mapCs, &bar_full, 0, c * D, hh, b);
-  };
-  if (tid == 0) issue_loads(p.NT - 1);
-
   const T* ip = (const T*)p.ig + b * p.ig_sb + hh * p.ig_sh;
   const T* fp = (const T*)p.fg + b * p.fg_sb + hh * p.fg_sh;
   const float* mo = p.m_out + (int64_t)bh * p.S;
   const float* no = p.n_out + (int64_t)bh * p.S;
-  float carry = 0.f;  // running suffix sum of (q.dq - k.dk), kept by warp 3
 
-  for (int it = 0; it < p.NT; ++it) {
-    const int c = p.NT - 1 - it;
-    const uint32_t par = it & 1;
-    const int t0 = c * LT;
-    const int n_valid = min(LT, p.S - t0);
-    const bool valid = row < n_valid;
-    const float m_t = valid ? mo[t0 + row] : 0.f;
-    const float n_t = valid ? no[t0 + row] : 1.f;
-    const float m_prev = c > 0 ? mo[t0 - 1] : (p.m0 ? p.m0[bh] : 0.f);  // m of the state entering the tile
-    const float m_next = mo[t0 + n_valid - 1];                            // m of the state leaving it
+  if (warp == kCtlWarp) {
+    // =========================== control warp ===================================================
+    auto issue_loads = [&](int c) {
+      mbar_expect_tx(&bar_full, SM::kLoadBytes);
+      tma_load_4d(sQ, &mapQ, &bar_full, 0, c * LT, hh, b);
+      tma_load_4d(sK, &mapK, &bar_full, 0, c * LT, hh, b);
+      tma_load_4d(sV, &mapV, &bar_full, 0, c * LT, hh, b);
+      tma_load_4d(sdH, &mapdH, &bar_full, 0, c * LT, hh, b);
+      tma_load_4d(sCs, &mapCs, &bar_full, 0, c * D, hh, b);
+    };
+    // gate vectors + saved per-token m / n of tile c into buffer `gb`
+    auto tile_vectors = [&](float* gb, int c) {
+      const int t0 = c * LT, n_valid = min(LT, p.S - t0);
+      control_gate_scan<T>(gb, ip + (int64_t)t0 * p.ig_ss, p.ig_ss, fp + (int64_t)t0 * p.fg_ss, p.fg_ss, n_valid);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int t = lane + 32 * e;
+        gb[GateBuf::oMt + t] = t < n_valid ? mo[t0 + t] : 0.f;
+        gb[GateBuf::oNt + t] = t < n_valid ? no[t0 + t] : 1.f;
+      }
+      if (lane == 0) {
+        gb[GateBuf::oScal + 2] = c > 0 ? mo[t0 - 1] : (p.m0 ? p.m0[bh] : 0.f);  // m of the state entering the tile
+        gb[GateBuf::oScal + 3] = mo[t0 + n_valid - 1];                          // m of the state leaving it
+      }
+    };
+    if (lane == 0) issue_loads(p.NT - 1);
+    tile_vectors(fsm + SM::fGates, p.NT - 1);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&bar_g[0]);
 
-    TC_PROF(it, 0);
-    // ---- A. gates ---------------------------------------------------------------------------
-    if (warp == 2) {
-      float amax;
-      float g = chunk_gate_scan<T>(ip + (int64_t)t0 * p.ig_ss, p.ig_ss, fp + (int64_t)t0 * p.fg_ss, p.fg_ss, LT, n_valid, sb, sy,
-                                   spm, &amax);
-      if (lane == 0) sscal[0] = g;
-    }
-    // ---- B. S = Q K^T, dSb = dH V^T ---------------------------------------------------------
-    if (warp == 0) {
-      mbar_wait(&bar_full, par, 11);
-      tc_fence_after_sync();
-      if (elect_one()) {
-        constexpr uint32_t idesc = umma_idesc(128, 128, false, false, kBf16);
+    constexpr uint32_t id_s = umma_idesc(128, 128, false, false, kBf16);
+    constexpr uint32_t id_c = umma_idesc(64, 64, true, true, kBf16);
+    constexpr uint32_t id_k_mn = umma_idesc(128, 64, false, true, kBf16);   // A K-major, B MN-major
+    constexpr uint32_t id_mn_mn = umma_idesc(128, 64, true, true, kBf16);   // A MN-major, B MN-major
+    constexpr uint32_t id_k_k = umma_idesc(128, 64, false, false, kBf16);   // A K-major, B K-major
+    const uint64_t kQ = umma_smem_desc(smem_u32(sQ), 0, 1024), mQ = umma_smem_desc(smem_u32(sQ), SM::kTile, 1024);
+    const uint64_t kK = umma_smem_desc(smem_u32(sK), 0, 1024), mK = umma_smem_desc(smem_u32(sK), SM::kTile, 1024);
+    const uint64_t kV = umma_smem_desc(smem_u32(sV), 0, 1024);
+    const uint64_t kH = umma_smem_desc(smem_u32(sdH), 0, 1024), mH = umma_smem_desc(smem_u32(sdH), SM::kTile, 1024);
+    const uint64_t mQt = umma_smem_desc(smem_u32(sQt), SM::kTile, 1024);
+    const uint64_t mSb = umma_smem_desc(smem_u32(sSb), SM::kTile, 1024);
+    const uint64_t kdS = umma_smem_desc(smem_u32(sdS), 0, 1024), mdS = umma_smem_desc(smem_u32(sdS), SM::kTile, 1024);
+    const uint64_t kCs = umma_smem_desc(smem_u32(sCs), 0, 1024);
+    const uint64_t kdC = umma_smem_desc(smem_u32(sdC), 0, 1024), mdC = umma_smem_desc(smem_u32(sdC), D * 128, 1024);
+    float carry = 0.f;  // running suffix sum of (q.dq - k.dk)
+
+    for (int it = 0; it < p.NT; ++it) {
+      const int c = p.NT - 1 - it, pb = it & 1;
+      const uint32_t par = it & 1;
+      const int t0 = c * LT, n_valid = min(LT, p.S - t0);
+      TC_PROF(it, 9);
+      if (lane == 0) {
+        tma_store_wait_read<0>();  // previous tile's dq / dk / dv staging buffers are free again
+        mbar_wait(&bar_full, par, 11);
+        tc_fence_after_sync();
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk)
-          umma_f16(tS, umma_smem_desc(smem_u32(sQ) + kk * 32, 0, 1024), umma_smem_desc(smem_u32(sK) + kk * 32, 0, 1024),
-                   idesc, kk > 0);
+        for (int kk = 0; kk < D / 16; ++kk)  // S = Q K^T
+          umma_f16(tS, umma_desc_advance(kQ, kk * 32), umma_desc_advance(kK, kk * 32), id_s, kk > 0);
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk)
-          umma_f16(tdSb, umma_smem_desc(smem_u32(sdH) + kk * 32, 0, 1024),
-                   umma_smem_desc(smem_u32(sV) + kk * 32, 0, 1024), idesc, kk > 0);
+        for (int kk = 0; kk < D / 16; ++kk)  // dSb = dH V^T
+          umma_f16(tdSb, umma_desc_advance(kH, kk * 32), umma_desc_advance(kV, kk * 32), id_s, kk > 0);
         umma_commit(&bar_s);
       }
       __syncwarp();
-    }
-    if (tid == 0) tma_store_wait_read<0>();  // previous tile's dq/dk/dv staging buffers are free again
-    __syncthreads();                         // #1 gates visible
-    TC_PROF(it, 1);
-    const float g = sscal[0];
-    const float b_t = sb[row], i_t = sy[row];
-    const float rinv = valid ? 1.f / (n_t + p.eps) : 0.f;                 // bw.py:135
-    const float bbar = valid ? __expf(b_t + m_prev - m_t) : 0.f;          // bw.py:186
-    const float abar = __expf(g - b_t + i_t - m_next);                    // bw.py:187 (0 for tail tokens)
-    const float gbar = __expf(g + m_prev - m_next);                       // bw.py:76
-    __syncthreads();                                                      // #2 raw i consumed
-    if (ch == 0) sy[row] = (i_t - b_t) * kLog2e;
-    mbar_wait(&bar_full, par, 12);
-    // ---- C. Qt = wq . Q; keep this thread's q / k / v row slices for the gate gradients -------
-    uint32_t qs[16], ks[16], vs[16];
-    {
-      const float wq = p.scale * bbar * rinv;  // bw.py:83-90
+      named_sync(NB_A, kTcThreads);  // Qt written
+      TC_PROF(it, 10);
+      if (lane == 0) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t off = swz128(row, ch * 32 + 8 * j);
-        uint4 u = *reinterpret_cast<const uint4*>(sQ + off);
-        qs[4 * j] = u.x; qs[4 * j + 1] = u.y; qs[4 * j + 2] = u.z; qs[4 * j + 3] = u.w;
-        float2 a0 = unpack2<T>(u.x), a1 = unpack2<T>(u.y), a2 = unpack2<T>(u.z), a3 = unpack2<T>(u.w);
-        u.x = pack2<T>(a0.x * wq, a0.y * wq);
-        u.y = pack2<T>(a1.x * wq, a1.y * wq);
-        u.z = pack2<T>(a2.x * wq, a2.y * wq);
-        u.w = pack2<T>(a3.x * wq, a3.y * wq);
-        *reinterpret_cast<uint4*>(sQt + off) = u;
-        uint4 uk = *reinterpret_cast<const uint4*>(sK + off);
-        ks[4 * j] = uk.x; ks[4 * j + 1] = uk.y; ks[4 * j + 2] = uk.z; ks[4 * j + 3] = uk.w;
-        uint4 uv = *reinterpret_cast<const uint4*>(sV + off);
-        vs[4 * j] = uv.x; vs[4 * j + 1] = uv.y; vs[4 * j + 2] = uv.z; vs[4 * j + 3] = uv.w;
-      }
-    }
-    fence_proxy_async_smem();
-    __syncthreads();  // #3
-    TC_PROF(it, 2);
-    // ---- D. ddC = Qt^T dH ; dQb = dH C_{k-1}^T -------------------------------------------------
-    if (warp == 0) {
-      if (elect_one()) {
-        constexpr uint32_t idesc_c = umma_idesc(64, 64, true, true, kBf16);
+        for (int kk = 0; kk < LT / 16; ++kk)  // ddC = Qt^T dH
+          umma_f16(tddC, umma_desc_advance(mQt, kk * 2048), umma_desc_advance(mH, kk * 2048), id_c, kk > 0);
 #pragma unroll
-        for (int kk = 0; kk < LT / 16; ++kk)
-          umma_f16(tddC, umma_smem_desc(smem_u32(sQt) + kk * 2048, SM::kTile, 1024),
-                   umma_smem_desc(smem_u32(sdH) + kk * 2048, SM::kTile, 1024), idesc_c, kk > 0);
-        constexpr uint32_t idesc_q = umma_idesc(128, 64, false, false, kBf16);
-#pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk)
-          umma_f16(tdQb, umma_smem_desc(smem_u32(sdH) + kk * 32, 0, 1024),
-                   umma_smem_desc(smem_u32(sCs) + kk * 32, 0, 1024), idesc_q, kk > 0);
+        for (int kk = 0; kk < D / 16; ++kk)  // dQb = dH C_{k-1}^T
+          umma_f16(tdQb, umma_desc_advance(kH, kk * 32), umma_desc_advance(kCs, kk * 32), id_k_k, kk > 0);
         umma_commit(&bar_d);
       }
       __syncwarp();
-    }
-    // ---- E. W; Sb' = S.scale.W, dS = dSb.W ------------------------------------------------------
-    mbar_wait(&bar_s, par, 13);
-    tc_fence_after_sync();
-    TC_PROF(it, 3);
-    {
-      const float x_t = (b_t - m_t) * kLog2e;
-      for (int u = 0; u < 4; ++u) {
-        if ((u & 1) != ch) continue;
-        float v[32], w[32];
-        if (u <= rb) {
-          tmem_ld32(tS + lane_base + u * 32, v);
-          tmem_ld32(tdSb + lane_base + u * 32, w);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float wg = ex2_approx(x_t + sy[u * 32 + j]) * rinv;
-            const bool keep = valid && (u < rb || j <= lane);
-            v[j] = keep ? v[j] * p.scale * wg : 0.f;
-            w[j] = keep ? w[j] * wg : 0.f;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) { v[j] = 0.f; w[j] = 0.f; }
-        }
-        store_row32<T>(sSb, row, u * 32, v);
-        store_row32<T>(sdS, row, u * 32, w);
+      if (it + 1 < p.NT) {  // vectors of the next tile, one tile ahead of the workers
+        tile_vectors(fsm + SM::fGates + ((it + 1) & 1) * GateBuf::kFloats, c - 1);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_g[(it + 1) & 1]);
       }
-    }
-    fence_proxy_async_smem();
-    tc_fence_before_sync();
-    __syncthreads();  // #4
-    TC_PROF(it, 4);
-    // ---- F. the five output MMAs ---------------------------------------------------------------
-    if (warp == 0) {
-      tc_fence_after_sync();
-      if (elect_one()) {
-        constexpr uint32_t id_k_mn = umma_idesc(128, 64, false, true, kBf16);   // A K-major, B MN-major
-        constexpr uint32_t id_mn_mn = umma_idesc(128, 64, true, true, kBf16);   // A MN-major, B MN-major
-        constexpr uint32_t id_k_k = umma_idesc(128, 64, false, false, kBf16);   // A K-major, B K-major
+      TC_PROF(it, 11);
+      named_sync(NB_B, kTcThreads);  // Sb', dS written
+      TC_PROF(it, 12);
+      if (lane == 0) {
+        tc_fence_after_sync();
 #pragma unroll
         for (int kk = 0; kk < LT / 16; ++kk)  // dQa = dS K
-          umma_f16(tdQa, umma_smem_desc(smem_u32(sdS) + (kk / 4) * SM::kTile + (kk % 4) * 32, 0, 1024),
-                   umma_smem_desc(smem_u32(sK) + kk * 2048, SM::kTile, 1024), id_k_mn, kk > 0);
+          umma_f16(tdQa, umma_desc_advance(kdS, (kk / 4) * SM::kTile + (kk % 4) * 32), umma_desc_advance(mK, kk * 2048),
+                   id_k_mn, kk > 0);
 #pragma unroll
         for (int kk = 0; kk < LT / 16; ++kk)  // dV1 = Sb'^T dH
-          umma_f16(tdV1, umma_smem_desc(smem_u32(sSb) + kk * 2048, SM::kTile, 1024),
-                   umma_smem_desc(smem_u32(sdH) + kk * 2048, SM::kTile, 1024), id_mn_mn, kk > 0);
+          umma_f16(tdV1, umma_desc_advance(mSb, kk * 2048), umma_desc_advance(mH, kk * 2048), id_mn_mn, kk > 0);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk)  // dV2 = K dC_k
-          umma_f16(tdV2, umma_smem_desc(smem_u32(sK) + kk * 32, 0, 1024),
-                   umma_smem_desc(smem_u32(sdC) + kk * 2048, D * 128, 1024), id_k_mn, kk > 0);
+          umma_f16(tdV2, umma_desc_advance(kK, kk * 32), umma_desc_advance(mdC, kk * 2048), id_k_mn, kk > 0);
 #pragma unroll
         for (int kk = 0; kk < LT / 16; ++kk)  // dK1 = dS^T Q
-          umma_f16(tdK1, umma_smem_desc(smem_u32(sdS) + kk * 2048, SM::kTile, 1024),
-                   umma_smem_desc(smem_u32(sQ) + kk * 2048, SM::kTile, 1024), id_mn_mn, kk > 0);
+          umma_f16(tdK1, umma_desc_advance(mdS, kk * 2048), umma_desc_advance(mQ, kk * 2048), id_mn_mn, kk > 0);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk)  // dK2 = V dC_k^T
-          umma_f16(tdK2, umma_smem_desc(smem_u32(sV) + kk * 32, 0, 1024),
-                   umma_smem_desc(smem_u32(sdC) + kk * 32, 0, 1024), id_k_k, kk > 0);
+          umma_f16(tdK2, umma_desc_advance(kV, kk * 32), umma_desc_advance(kdC, kk * 32), id_k_k, kk > 0);
         umma_commit(&bar_main);
+        TC_PROF(it, 13);
+        mbar_wait(&bar_main, par, 15);  // every MMA is done with this tile's inputs: refill them
+        if (c > 0) issue_loads(c - 1);
+      }
+      __syncwarp();
+      named_sync(NB_C, kTcThreads);  // dq / dk / dv staged
+      TC_PROF(it, 14);
+      if (lane == 0) {
+        tma_store_4d(&mapdQ, sdQ, 0, t0, hh, b);
+        tma_store_4d(&mapdV, sSb, 0, t0, hh, b);
+        tma_store_4d(&mapdK, sdS, 0, t0, hh, b);
+        tma_store_commit();
+      }
+      // ---- gate gradients: reverse (suffix) scan over the tile, carried across tiles -------------
+      {
+        const float* sp = fsm + SM::fPart + pb * 6 * LT;
+        const float* gb = fsm + SM::fGates + pb * GateBuf::kFloats;
+        float acc[4], di[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int t = lane * 4 + e;
+          acc[e] = (sp[0 * LT + t] + sp[1 * LT + t]) - (sp[2 * LT + t] + sp[3 * LT + t]);  // bw.py:321
+          di[e] = sp[4 * LT + t] + sp[5 * LT + t];                                         // bw.py:326
+        }
+        acc[2] += acc[3];
+        acc[1] += acc[2];
+        acc[0] += acc[1];
+        float incl = acc[0];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          float u = __shfl_down_sync(0xffffffffu, incl, o);
+          if (lane + o < 32) incl += u;
+        }
+        const float excl = incl - acc[0] + carry;
+        T* dip = (T*)p.di + b * p.di_sb + hh * p.di_sh;
+        T* dfp = (T*)p.df + b * p.df_sb + hh * p.df_sh;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int t = lane * 4 + e;
+          if (t < n_valid) {
+            dip[(int64_t)(t0 + t) * p.di_ss] = from_f32<T>(di[e]);
+            dfp[(int64_t)(t0 + t) * p.df_ss] =
+                from_f32<T>((acc[e] + excl) * sigmoid_neg_f32(gb[GateBuf::oF + t]));  // bw.py:322-323
+          }
+        }
+        carry += __shfl_sync(0xffffffffu, incl, 0);
       }
       __syncwarp();
     }
-    // ---- G. dC_{k-1} = gbar dC_k + ddC (registers) -----------------------------------------------
-    mbar_wait(&bar_d, par, 14);
-    tc_fence_after_sync();
-    TC_PROF(it, 5);
-    {
-      float v[32];
-      tmem_ld32(tddC + lane_base + ch * 32, v);
-      if (owns_c) {
+    if (lane == 0) tma_store_wait_all<0>();
+  } else {
+    // =========================== worker warps ===================================================
+    for (int it = 0; it < p.NT; ++it) {
+      const int pb = it & 1;
+      const uint32_t par = it & 1;
+      const float* gb = fsm + SM::fGates + pb * GateBuf::kFloats;
+      float* spart = fsm + SM::fPart + pb * 6 * LT;
+      const int n_valid = min(LT, p.S - (p.NT - 1 - it) * LT);
+      const bool valid = row < n_valid;
+
+      TC_PROF(it, 0);
+      mbar_wait(&bar_g[pb], (it >> 1) & 1, 12);
+      const float g = gb[GateBuf::oScal], m_prev = gb[GateBuf::oScal + 2], m_next = gb[GateBuf::oScal + 3];
+      const float b_t = gb[GateBuf::oB + row], i_t = gb[GateBuf::oI + row];
+      const float m_t = gb[GateBuf::oMt + row], n_t = gb[GateBuf::oNt + row];
+      const float rinv = valid ? 1.f / (n_t + p.eps) : 0.f;         // bw.py:135
+      const float bbar = valid ? __expf(b_t + m_prev - m_t) : 0.f;  // bw.py:186
+      const float abar = __expf(g - b_t + i_t - m_next);            // bw.py:187 (0 for tail tokens)
+      const float gbar = __expf(g + m_prev - m_next);               // bw.py:76
+      mbar_wait(&bar_full, par, 13);
+      TC_PROF(it, 1);
+      // ---- Qt = wq . Q; keep this thread's q / k / v row slices for the gate gradients ------------
+      uint32_t qs[16], ks[16], vs[16];
+      {
+        const float wq = p.scale * bbar * rinv;  // bw.py:83-90
 #pragma unroll
-        for (int j = 0; j < 32; ++j) dCreg[j] = gbar * dCreg[j] + v[j];  // bw.py:93-95
-      }
-    }
-    // ---- H. epilogue --------------------------------------------------------------------------------
-    TC_PROF(it, 6);
-    mbar_wait(&bar_main, par, 15);
-    tc_fence_after_sync();
-    TC_PROF(it, 7);
-    if (tid == 0 && c > 0) issue_loads(c - 1);  // every MMA / thread is done with this tile's inputs
-    if (owns_c) store_row32<T>(sdC, drow, ch * 32, dCreg);
-    {
-      float a[32], bq[32];
-      float dot;
-      // dq
-      tmem_ld32(tdQa + lane_base + ch * 32, a);
-      tmem_ld32(tdQb + lane_base + ch * 32, bq);
-      const float wb = bbar * rinv;
-      dot = 0.f;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        a[2 * j] = p.scale * (a[2 * j] + wb * bq[2 * j]);              // bw.py:169,193
-        a[2 * j + 1] = p.scale * (a[2 * j + 1] + wb * bq[2 * j + 1]);
-        float2 qv = unpack2<T>(qs[j]);
-        dot += qv.x * a[2 * j] + qv.y * a[2 * j + 1];
-      }
-      store_row32<T>(sQt, row, ch * 32, a);
-      spart[(0 * 2 + ch) * LT + row] = dot;
-      // dv
-      tmem_ld32(tdV1 + lane_base + ch * 32, a);
-      tmem_ld32(tdV2 + lane_base + ch * 32, bq);
-      dot = 0.f;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        a[2 * j] = a[2 * j] + abar * bq[2 * j];                        // bw.py:164,190
-        a[2 * j + 1] = a[2 * j + 1] + abar * bq[2 * j + 1];
-        float2 vv = unpack2<T>(vs[j]);
-        dot += vv.x * a[2 * j] + vv.y * a[2 * j + 1];
-      }
-      store_row32<T>(sSb, row, ch * 32, a);
-      spart[(2 * 2 + ch) * LT + row] = dot;
-      // dk
-      tmem_ld32(tdK1 + lane_base + ch * 32, a);
-      tmem_ld32(tdK2 + lane_base + ch * 32, bq);
-      dot = 0.f;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        a[2 * j] = p.scale * a[2 * j] + abar * bq[2 * j];              // bw.py:170,192
-        a[2 * j + 1] = p.scale * a[2 * j + 1] + abar * bq[2 * j + 1];
-        float2 kv = unpack2<T>(ks[j]);
-        dot += kv.x * a[2 * j] + kv.y * a[2 * j + 1];
-      }
-      store_row32<T>(sdS, row, ch * 32, a);
-      spart[(1 * 2 + ch) * LT + row] = dot;
-    }
-    fence_proxy_async_smem();
-    tc_fence_before_sync();
-    __syncthreads();  // #5
-    TC_PROF(it, 8);
-    if (tid == 0) {
-      tma_store_4d(&mapdQ, sQt, 0, t0, hh, b);
-      tma_store_4d(&mapdV, sSb, 0, t0, hh, b);
-      tma_store_4d(&mapdK, sdS, 0, t0, hh, b);
-      tma_store_commit();
-    }
-    // ---- gate gradients: warp 3 runs the reverse (suffix) scan over the tile, carrying across tiles
-    if (warp == 3) {
-      float acc[4], di[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int t = lane * 4 + e;
-        acc[e] = (spart[0 * LT + t] + spart[1 * LT + t]) - (spart[2 * LT + t] + spart[3 * LT + t]);  // bw.py:321
-        di[e] = spart[4 * LT + t] + spart[5 * LT + t];                                               // bw.py:326
-      }
-      acc[2] += acc[3];
-      acc[1] += acc[2];
-      acc[0] += acc[1];
-      float incl = acc[0];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        float u = __shfl_down_sync(0xffffffffu, incl, o);
-        if (lane + o < 32) incl += u;
-      }
-      const float excl = incl - acc[0] + carry;
-      T* dip = (T*)p.di + b * p.di_sb + hh * p.di_sh;
-      T* dfp = (T*)p.df + b * p.df_sb + hh * p.df_sh;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int t = lane * 4 + e;
-        if (t < n_valid) {
-          const float fraw = to_f32<T>(fp[(int64_t)(t0 + t) * p.fg_ss]);
-          dip[(int64_t)(t0 + t) * p.di_ss] = from_f32<T>(di[e]);
-          dfp[(int64_t)(t0 + t) * p.df_ss] = from_f32<T>((acc[e] + excl) * sigmoid_neg_f32(fraw));  // bw.py:322-323
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t off = swz128(row, ch * 32 + 8 * j);
+          uint4 u = *reinterpret_cast<const uint4*>(sQ + off);
+          qs[4 * j] = u.x; qs[4 * j + 1] = u.y; qs[4 * j + 2] = u.z; qs[4 * j + 3] = u.w;
+          float2 a0 = unpack2<T>(u.x), a1 = unpack2<T>(u.y), a2 = unpack2<T>(u.z), a3 = unpack2<T>(u.w);
+          u.x = pack2<T>(a0.x * wq, a0.y * wq);
+          u.y = pack2<T>(a1.x * wq, a1.y * wq);
+          u.z = pack2<T>(a2.x * wq, a2.y * wq);
+          u.w = pack2<T>(a3.x * wq, a3.y * wq);
+          *reinterpret_cast<uint4*>(sQt + off) = u;
+          uint4 uk = *reinterpret_cast<const uint4*>(sK + off);
+          ks[4 * j] = uk.x; ks[4 * j + 1] = uk.y; ks[4 * j + 2] = uk.z; ks[4 * j + 3] = uk.w;
+          uint4 uv = *reinterpret_cast<const uint4*>(sV + off);
+          vs[4 * j] = uv.x; vs[4 * j + 1] = uv.y; vs[4 * j + 2] = uv.z; vs[4 * j + 3] = uv.w;
         }
       }
-      carry += __shfl_sync(0xffffffffu, incl, 0);
+      fence_proxy_async_smem();
+      named_arrive(NB_A, kTcThreads);
+      TC_PROF(it, 2);
+      // ---- W; Sb' = S.scale.W, dS = dSb.W ------------------------------------------------------------
+      mbar_wait(&bar_s, par, 14);
+      tc_fence_after_sync();
+      TC_PROF(it, 3);
+      {
+        const float x_t = (b_t - m_t) * kLog2e;
+        const float* sy = gb + GateBuf::oY;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if ((u & 1) != ch) continue;
+          float v[32], w[32];
+          if (u <= rb) {
+            uint32_t rv[32], rw[32];
+            tmem_ld32_nowait(tS + lane_base + u * 32, rv);
+            tmem_ld32_nowait(tdSb + lane_base + u * 32, rw);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 y = *reinterpret_cast<const float4*>(sy + u * 32 + 4 * j4);
+              const float yy[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = 4 * j4 + e;
+                const float wg = ex2_approx(x_t + yy[e]) * rinv;
+                const bool keep = valid && (u < rb || j <= lane);
+                v[j] = keep ? __uint_as_float(rv[j]) * p.scale * wg : 0.f;
+                w[j] = keep ? __uint_as_float(rw[j]) * wg : 0.f;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { v[j] = 0.f; w[j] = 0.f; }
+          }
+          store_row32<T>(sSb, row, u * 32, v);
+          store_row32<T>(sdS, row, u * 32, w);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      named_arrive(NB_B, kTcThreads);
+      TC_PROF(it, 4);
+      // ---- dC_{k-1} = gbar dC_k + ddC (registers) --------------------------------------------------
+      mbar_wait(&bar_d, par, 15);
+      tc_fence_after_sync();
+      TC_PROF(it, 5);
+      {
+        float v[32];
+        tmem_ld32(tddC + lane_base + ch * 32, v);
+        if (owns_c) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dCreg[j] = gbar * dCreg[j] + v[j];  // bw.py:93-95
+        }
+      }
+      TC_PROF(it, 6);
+      // ---- epilogue ------------------------------------------------------------------------------------
+      mbar_wait(&bar_main, par, 16);
+      tc_fence_after_sync();
+      TC_PROF(it, 7);
+      if (owns_c) store_row32<T>(sdC, drow, ch * 32, dCreg);
+      {
+        uint32_t ra[32], rq[32];
+        float o[32];
+        float dot;
+        // dq
+        tmem_ld32_nowait(tdQa + lane_base + ch * 32, ra);
+        tmem_ld32_nowait(tdQb + lane_base + ch * 32, rq);
+        tmem_ld_wait();
+        const float wb = bbar * rinv;
+        dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          o[2 * j] = p.scale * (__uint_as_float(ra[2 * j]) + wb * __uint_as_float(rq[2 * j]));  // bw.py:169,193
+          o[2 * j + 1] = p.scale * (__uint_as_float(ra[2 * j + 1]) + wb * __uint_as_float(rq[2 * j + 1]));
+          float2 qv = unpack2<T>(qs[j]);
+          dot += qv.x * o[2 * j] + qv.y * o[2 * j + 1];
+        }
+        store_row32<T>(sdQ, row, ch * 32, o);
+        spart[(0 * 2 + ch) * LT + row] = dot;
+        // dv
+        tmem_ld32_nowait(tdV1 + lane_base + ch * 32, ra);
+        tmem_ld32_nowait(tdV2 + lane_base + ch * 32, rq);
+        tmem_ld_wait();
+        dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          o[2 * j] = __uint_as_float(ra[2 * j]) + abar * __uint_as_float(rq[2 * j]);  // bw.py:164,190
+          o[2 * j + 1] = __uint_as_float(ra[2 * j + 1]) + abar * __uint_as_float(rq[2 * j + 1]);
+          float2 vv = unpack2<T>(vs[j]);
+          dot += vv.x * o[2 * j] + vv.y * o[2 * j + 1];
+        }
+        store_row32<T>(sSb, row, ch * 32, o);
+        spart[(2 * 2 + ch) * LT + row] = dot;
+        // dk
+        tmem_ld32_nowait(tdK1 + lane_base + ch * 32, ra);
+        tmem_ld32_nowait(tdK2 + lane_base + ch * 32, rq);
+        tmem_ld_wait();
+        dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          o[2 * j] = p.scale * __uint_as_float(ra[2 * j]) + abar * __uint_as_float(rq[2 * j]);  // bw.py:170,192
+          o[2 * j + 1] = p.scale * __uint_as_float(ra[2 * j + 1]) + abar * __uint_as_float(rq[2 * j + 1]);
+          float2 kv = unpack2<T>(ks[j]);
+          dot += kv.x * o[2 * j] + kv.y * o[2 * j + 1];
+        }
+        store_row32<T>(sdS, row, ch * 32, o);
+        spart[(1 * 2 + ch) * LT + row] = dot;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      named_arrive(NB_C, kTcThreads);
+      TC_PROF(it, 8);
+    }
+    if (p.dc0 && owns_c) {  // dC_initial = dC_0 (bw.py:329-331)
+      float* dst = p.dc0 + ((int64_t)bh * D + drow) * D + ch * 32;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) dst[j] = dCreg[j];
     }
   }
-
-  if (p.dc0 && owns_c) {  // dC_initial = dC_0 (bw.py:329-331)
-    float* dst = p.dc0 + ((int64_t)bh * D + drow) * D + ch * 32;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) dst[j] = dCreg[j];
-  }
-  if (tid == 0) tma_store_wait_all<0>();
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem);
+  if (warp == kCtlWarp) tmem_dealloc<512>(tmem);
+}
+
+long long* g_prof = nullptr;  // debug hook, see tensor_set_clock_buffer
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <typename T>
+int launch_fw_d64(const TcFwParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
+                  const CUtensorMap& mh, const CUtensorMap& mcs, cudaStream_t st) {
+  using SM = FwSmem<2>;
+  auto kern = tc_fw_d64<T, 2>;
+  MLSTM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
+  kern<<<p.B * p.NH, kTcThreads, SM::kBytes, st>>>(mq, mk, mv, mh, mcs, p);
+  count_launch();
+  MLSTM_CUDA_CHECK(cudaGetLastError());
+  return 0;
 }
 
 bool tma_ok(const mlstm_b200_tensor& t) {
@@ -850,13 +981,8 @@ int run_fw(const mlstm_b200_fw_args& a, void* c_states, cudaStream_t st) {
   p.c_last = a.c_last; p.n_last = a.n_last; p.m_last = a.m_last;
   p.store_states = c_states != nullptr;
   p.prof = g_prof;
-  const bool two_per_sm = (long)s.B * s.NH > num_sms();
-  if (s.dtype == MLSTM_B200_BF16) {
-    return two_per_sm ? launch_fw_d64<__nv_bfloat16, 1>(p, mq, mk, mv, mh, mcs, st)
-                      : launch_fw_d64<__nv_bfloat16, 2>(p, mq, mk, mv, mh, mcs, st);
-  }
-  return two_per_sm ? launch_fw_d64<__half, 1>(p, mq, mk, mv, mh, mcs, st)
-                    : launch_fw_d64<__half, 2>(p, mq, mk, mv, mh, mcs, st);
+  if (s.dtype == MLSTM_B200_BF16) return launch_fw_d64<__nv_bfloat16>(p, mq, mk, mv, mh, mcs, st);
+  return launch_fw_d64<__half>(p, mq, mk, mv, mh, mcs, st);
 }
 
 struct BwWs {
