@@ -26,5 +26,6 @@ for name, k in (("fw", 0), ("bw", 1)):
     for tile in range(NT):
         r = v[k, tile]
         base = r[0].item()
-        print(f"  tile {tile:2d}: " + " ".join(f"{(r[i].item() - base):6d}" for i in range(9)) +
-              (f"   | to next top {(v[k, tile + 1, 0].item() - base):6d}" if tile + 1 < NT else ""))
+        print(f"  tile {tile:2d}: " + " ".join(f"{(r[i].item() - base):6d}" for i in range(9)) + "  || ctl " +
+              " ".join(f"{(r[i].item() - base):6d}" for i in range(9, 16)) +
+              (f"   | next top {(v[k, tile + 1, 0].item() - base):6d}" if tile + 1 < NT else ""))

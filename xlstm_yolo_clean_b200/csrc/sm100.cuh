@@ -45,8 +45,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 #define SM100_WAIT_CYCLES (1ll << 31)
 #endif
 static __device__ volatile int* g_dbg = nullptr;
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
-  if (mbar_try_wait(bar, parity)) return;
+// slow path kept out of line: the kernels are instruction-cache sensitive
+__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, int tag) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > SM100_WAIT_CYCLES) {
@@ -58,6 +58,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
+  if (mbar_try_wait(bar, parity)) return;
+  if (mbar_try_wait(bar, parity)) return;  // try_wait suspends for a while by itself; retry once inline
+  mbar_wait_slow(bar, parity, tag);
 }
 
 // ---------------------------------------------------------------- named barriers (sub-CTA handoff)
@@ -90,6 +95,11 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(smem_u32(smem_dst)), "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"((uint64_t)m), "r"(c0), "r"(c1),
+               "r"(c2), "r"(c3)
+               : "memory");
 }
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"((uint64_t)m),

@@ -31,15 +31,18 @@ using namespace sm100;
 
 constexpr int LT = 128;           // tokens per tile
 constexpr int kWorkers = 256;     // 8 worker warps
-constexpr int kTcThreads = 288;   // + 1 control warp
-constexpr int kCtlWarp = 8;
+constexpr int kTcThreads = 320;   // + control warp (TMA / MMA issue) + scan warp (gate vectors, dF scan)
+constexpr int kCtlWarp = 8, kScanWarp = 9;
+constexpr int kNbAB = kWorkers + 32;  // workers + control
+constexpr int kNbC = kWorkers + 64;   // workers + control + scan
 constexpr float kLog2e = 1.4426950408889634f;
 enum { NB_A = 1, NB_B = 2, NB_C = 3 };  // named barriers: operand ready / P ready / epilogue done
 
 // per-tile gate vectors produced by the control warp (floats)
 struct GateBuf {
   static constexpr int oB = 0, oI = LT, oPm = 2 * LT, oY = 3 * LT, oF = 4 * LT, oMt = 5 * LT, oNt = 6 * LT,
-                       oScal = 7 * LT, kFloats = 7 * LT + 8;
+                       oCf = 7 * LT, oScal = 8 * LT, kFloats = 8 * LT + 8;
+  // oScal: 0 g, 1 amax, 2 m_prev, 3 m_next (backward), 4..7 max of y over each 32-column unit
 };
 
 #define TC_PROF(tile, slot) \
@@ -101,30 +104,85 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
-// Control warp: gate vectors of one tile into `gb` (forward direction inside the tile).
-//   b (inclusive cumsum of logsigmoid f), raw i, prefix max of (i - b), y = (i - b) log2e, raw f
+// Raw gate inputs of one tile held in registers by the control warp (lane owns tokens 4*lane..+3),
+// loaded one tile ahead of their use so the scans never wait on global memory.
 template <typename T>
-__device__ __forceinline__ void control_gate_scan(float* gb, const T* ip, int64_t is, const T* fp, int64_t fs, int n_valid) {
+struct GateRaw {
+  T f[4], i[4];  // kept as loaded (no arithmetic) so the loads stay in flight until the scan
+  int n_valid;
+};
+template <typename T>
+__device__ __forceinline__ GateRaw<T> load_gate_raw(const T* ip, int64_t is, const T* fp, int64_t fs, int n_valid) {
+  GateRaw<T> r;
   const int lane = threadIdx.x & 31;
-  float fraw[4];
+  r.n_valid = n_valid;
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    const int t = lane * 4 + e;
-    fraw[e] = t < n_valid ? to_f32<T>(fp[(int64_t)t * fs]) : 0.f;
+    const int t = min(lane * 4 + e, n_valid - 1);  // clamp: tail tokens are masked at scan time
+    r.f[e] = fp[(int64_t)t * fs];
+    r.i[e] = ip[(int64_t)t * is];
   }
-  float amax;
-  const float g = chunk_gate_scan<T>(ip, is, fp, fs, LT, n_valid, gb + GateBuf::oB, gb + GateBuf::oI, gb + GateBuf::oPm, &amax);
-  __syncwarp();
+  return r;
+}
+// Control warp: gate vectors of one tile into `gb` (warp-shuffle scans, north_star item 1):
+//   b = inclusive cumsum of logsigmoid(f) (fw.py:261-262), raw i, prefix max of (i - b) so that
+//   m_t = b_t + max(m_prev, pm_t) (fw.py:171-184), y = (i - b) log2e, raw f, g = b_L, amax = max(i - b),
+//   and the factorisation of the decay matrix used for 32x32 blocks strictly below the diagonal:
+//   exp2(x_t + y_s) = exp2(x_t + ymax_u) * cf_s with cf_s = exp2(y_s - ymax_u) <= 1 (no overflow
+//   because x_t + y_s <= 0 for every s <= t).  Ragged tail tokens act as logsigmoid(f) = 0, i = -inf.
+// logsigmoid with the fast exp / log units (the 16-bit path tolerates 1e-6 relative error here)
+__device__ __forceinline__ float logsigmoid_fast(float x) { return fminf(x, 0.f) - __logf(1.f + __expf(-fabsf(x))); }
+
+template <typename T>
+__device__ __noinline__ void gate_scan_regs(float* gb, const GateRaw<T>& r) {
+  const int lane = threadIdx.x & 31;
+  float lf[4], iv[4], fv[4];
+  float run = 0.f;
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    const int t = lane * 4 + e;
-    gb[GateBuf::oY + t] = (gb[GateBuf::oI + t] - gb[GateBuf::oB + t]) * kLog2e;
-    gb[GateBuf::oF + t] = fraw[e];
+    const bool ok = lane * 4 + e < r.n_valid;
+    fv[e] = ok ? to_f32<T>(r.f[e]) : INFINITY;
+    iv[e] = ok ? to_f32<T>(r.i[e]) : -INFINITY;
+    run += logsigmoid_fast(fv[e]);
+    lf[e] = run;
   }
+  const float incl = warp_incl_sum(run, lane);
+  const float base = incl - run;
+  float pmax = -INFINITY;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    lf[e] += base;
+    pmax = fmaxf(pmax, iv[e] - lf[e]);
+  }
+  const float incl_max = warp_incl_max(pmax, lane);
+  float runmax = __shfl_up_sync(0xffffffffu, incl_max, 1);
+  if (lane == 0) runmax = -INFINITY;
+  // maximum of y over this lane's 32-column unit (8 lanes per unit)
+  float umax = pmax;
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) umax = fmaxf(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+  umax = fmaxf(umax * kLog2e, -1e30f);
+  float pm[4], y[4], cf[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    runmax = fmaxf(runmax, iv[e] - lf[e]);
+    pm[e] = runmax;
+    y[e] = (iv[e] - lf[e]) * kLog2e;
+    cf[e] = ex2_approx(y[e] - umax);
+  }
+  reinterpret_cast<float4*>(gb + GateBuf::oB)[lane] = make_float4(lf[0], lf[1], lf[2], lf[3]);
+  reinterpret_cast<float4*>(gb + GateBuf::oI)[lane] = make_float4(iv[0], iv[1], iv[2], iv[3]);
+  reinterpret_cast<float4*>(gb + GateBuf::oPm)[lane] = make_float4(pm[0], pm[1], pm[2], pm[3]);
+  reinterpret_cast<float4*>(gb + GateBuf::oY)[lane] = make_float4(y[0], y[1], y[2], y[3]);
+  reinterpret_cast<float4*>(gb + GateBuf::oF)[lane] = make_float4(fv[0], fv[1], fv[2], fv[3]);
+  reinterpret_cast<float4*>(gb + GateBuf::oCf)[lane] = make_float4(cf[0], cf[1], cf[2], cf[3]);
+  const float g = __shfl_sync(0xffffffffu, incl, 31);
+  const float amax = warp_all_max(pmax);
   if (lane == 0) {
     gb[GateBuf::oScal + 0] = g;
     gb[GateBuf::oScal + 1] = amax;
   }
+  if ((lane & 7) == 0) gb[GateBuf::oScal + 4 + (lane >> 3)] = umax;
 }
 
 // =============================================================================================
@@ -179,7 +237,8 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
   __shared__ uint64_t bar_full[NSTAGE], bar_s, bar_dc, bar_h, bar_g[2], bar_n;
   __shared__ uint32_t tmem_base_s;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: role branches stay uniform
   const int bh = blockIdx.x, b = bh / p.NH, hh = bh % p.NH;
 
   if (tid == 0) {
@@ -240,9 +299,6 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
     };
     if (lane == 0)
       for (int s = 0; s < NSTAGE && s < p.NT; ++s) load_stage(s, s);
-    control_gate_scan<T>(fsm + SM::fGates, ip, p.ig_ss, fp, p.fg_ss, min(LT, p.S));
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&bar_g[0]);
 
     constexpr uint32_t id_s = umma_idesc(128, 128, false, false, kBf16);
     constexpr uint32_t id_dc = umma_idesc(64, 64, true, true, kBf16);
@@ -250,55 +306,46 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
     const uint64_t dKb = umma_smem_desc(smem_u32(sKb), SM::kTile, 1024);
     const uint64_t dP = umma_smem_desc(smem_u32(sP), 0, 1024);
     const uint64_t dC = umma_smem_desc(smem_u32(sC), D * 128, 1024);
-    auto issue_s = [&](int c) {  // S(c) = Q K^T into the parity buffer
-      const int s = c % NSTAGE;
+    // Every shared-memory descriptor is loop invariant and provably warp-uniform (the stage / TMEM
+    // parity is a compile-time constant of the two-tile unrolled body), so the tcgen05.mma operands
+    // live in uniform registers instead of going through a per-instruction R2UR waterfall.
+    const uint64_t dQ0 = umma_smem_desc(smem_u32(smem + SM::oQ), 0, 1024);
+    const uint64_t dK0 = umma_smem_desc(smem_u32(smem + SM::oK), 0, 1024);
+    const uint64_t dV0 = umma_smem_desc(smem_u32(smem + SM::oV), SM::kTile, 1024);
+    const uint64_t dQ1 = umma_desc_advance(dQ0, (NSTAGE - 1) * SM::kTile);
+    const uint64_t dK1 = umma_desc_advance(dK0, (NSTAGE - 1) * SM::kTile);
+    const uint64_t dV1 = umma_desc_advance(dV0, (NSTAGE - 1) * SM::kTile);
+    auto issue_s = [&](int c, auto PAR) {  // S(c) = Q K^T into the TMEM buffer of the tile's parity
+      constexpr int par = decltype(PAR)::value;
+      constexpr int s = par % NSTAGE;
       mbar_wait(&bar_full[s], (c / NSTAGE) & 1, 1);
       tc_fence_after_sync();
-      const uint64_t dQ = umma_smem_desc(smem_u32(smem + SM::oQ + s * SM::kTile), 0, 1024);
-      const uint64_t dK = umma_smem_desc(smem_u32(smem + SM::oK + s * SM::kTile), 0, 1024);
-      const uint32_t tS = (c & 1) ? tS1 : tS0;
+      const uint64_t dQ = par ? dQ1 : dQ0, dK = par ? dK1 : dK0;
+      const uint32_t tS = par ? tS1 : tS0;
 #pragma unroll
       for (int kk = 0; kk < D / 16; ++kk)
         umma_f16(tS, umma_desc_advance(dQ, kk * 32), umma_desc_advance(dK, kk * 32), id_s, kk > 0);
       umma_commit(&bar_s);
     };
+    if (lane == 0) {
+      if (p.store_states) {  // state entering tile 0 (bf16 operand copy) -> c_states[b, h, 0]
+        tma_store_4d(&mapCs, sC, 0, 0, hh, b);
+        tma_store_commit();
+      }
+      issue_s(0, std::integral_constant<int, 0>{});
+    }
+    __syncwarp();
 
-    for (int c = 0; c < p.NT; ++c) {
-      const int s = c % NSTAGE;
-      const uint64_t dQ = umma_smem_desc(smem_u32(smem + SM::oQ + s * SM::kTile), 0, 1024);
-      const uint64_t dV = umma_smem_desc(smem_u32(smem + SM::oV + s * SM::kTile), SM::kTile, 1024);
+    auto tile_body = [&](int c, auto PAR) {
+      constexpr int par = decltype(PAR)::value;
+      constexpr int s = par % NSTAGE;
+      const uint64_t dQ = par ? dQ1 : dQ0, dV = par ? dV1 : dV0;
       TC_PROF(c, 9);
-      if (lane == 0) {
-        tma_store_wait_read<0>();  // h staging / sC of the previous tile have been read
-        if (p.store_states) {      // C_{k-1} (bf16 operand copy) -> c_states[b, h, tile]
-          tma_store_4d(&mapCs, sC, 0, c * D, hh, b);
-          tma_store_commit();
-        }
-        if (NSTAGE == 1 || c == 0) issue_s(c);
-      }
-      __syncwarp();
-      named_sync(NB_A, kTcThreads);  // Kbar written
-      TC_PROF(c, 10);
-      if (lane == 0) {
-#pragma unroll
-        for (int kk = 0; kk < LT / 16; ++kk)  // dC = Kbar^T V
-          umma_f16(tDC, umma_desc_advance(dKb, kk * 2048), umma_desc_advance(dV, kk * 2048), id_dc, kk > 0);
-        umma_commit(&bar_dc);
-      }
-      __syncwarp();
-      if (c + 1 < p.NT) {  // gates of the next tile, one tile ahead of the workers
-        const int t1 = (c + 1) * LT;
-        control_gate_scan<T>(fsm + SM::fGates + ((c + 1) & 1) * GateBuf::kFloats, ip + (int64_t)t1 * p.ig_ss, p.ig_ss,
-                             fp + (int64_t)t1 * p.fg_ss, p.fg_ss, min(LT, p.S - t1));
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_g[(c + 1) & 1]);
-      }
-      TC_PROF(c, 11);
-      named_sync(NB_B, kTcThreads);  // P written
-      TC_PROF(c, 12);
+      named_sync(NB_B, kNbAB);  // P(c) written
       if (lane == 0) {
         tc_fence_after_sync();
-        tma_store_wait_read<0>();  // the c_states store has read sC (workers rewrite it after bar_h)
+        tma_store_wait_read<0>();  // earlier h / c_states stores have read sH and sC (rewritten after bar_h)
+        TC_PROF(c, 10);
 #pragma unroll
         for (int kk = 0; kk < LT / 16; ++kk)  // Hintra = P V
           umma_f16(tHi, umma_desc_advance(dP, (kk / 4) * SM::kTile + (kk % 4) * 32), umma_desc_advance(dV, kk * 2048), id_h,
@@ -307,20 +354,51 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
         for (int kk = 0; kk < D / 16; ++kk)  // Hinter = Q C_{k-1}
           umma_f16(tHx, umma_desc_advance(dQ, kk * 32), umma_desc_advance(dC, kk * 2048), id_h, kk > 0);
         umma_commit(&bar_h);
-        if (NSTAGE == 2 && c + 1 < p.NT) issue_s(c + 1);  // S of the next tile into the other TMEM buffer
+        TC_PROF(c, 11);
       }
       __syncwarp();
-      TC_PROF(c, 13);
-      named_sync(NB_C, kTcThreads);  // h staged, every worker is done with this tile
-      TC_PROF(c, 14);
+      named_sync(NB_A, kNbAB);  // Kbar(c) written
       if (lane == 0) {
+        TC_PROF(c, 12);
+#pragma unroll
+        for (int kk = 0; kk < LT / 16; ++kk)  // dC = Kbar^T V
+          umma_f16(tDC, umma_desc_advance(dKb, kk * 2048), umma_desc_advance(dV, kk * 2048), id_dc, kk > 0);
+        umma_commit(&bar_dc);
+        if (c + 1 < p.NT) issue_s(c + 1, std::integral_constant<int, par ^ 1>{});  // next tile's S, other TMEM buffer
+        TC_PROF(c, 13);
+      }
+      __syncwarp();
+      named_sync(NB_C, kNbC);  // h staged, C_k written: every worker is done with this tile
+      if (lane == 0) {
+        TC_PROF(c, 14);
         tma_store_4d(&mapH, sH, 0, c * LT, hh, b);
+        if (p.store_states && c + 1 < p.NT) tma_store_4d(&mapCs, sC, 0, (c + 1) * D, hh, b);  // state entering tile c+1
         tma_store_commit();
         if (c + NSTAGE < p.NT) load_stage(s, c + NSTAGE);
+        TC_PROF(c, 15);
       }
       __syncwarp();
+    };
+    for (int c = 0; c < p.NT; c += 2) {
+      tile_body(c, std::integral_constant<int, 0>{});
+      if (c + 1 < p.NT) tile_body(c + 1, std::integral_constant<int, 1>{});
     }
     if (lane == 0) tma_store_wait_all<0>();
+  } else if (warp == kScanWarp) {
+    // =========================== scan warp: gate vectors two tiles ahead ===========================
+    auto raw_of = [&](int c) {
+      const int t1 = c * LT;
+      return load_gate_raw<T>(ip + (int64_t)t1 * p.ig_ss, p.ig_ss, fp + (int64_t)t1 * p.fg_ss, p.fg_ss, min(LT, p.S - t1));
+    };
+    GateRaw<T> raw = raw_of(0);
+    for (int n = 0; n < p.NT; ++n) {  // vectors of tile n; tiles 0 and 1 need no buffer hand-back
+      if (n >= 2) named_sync(NB_C, kNbC);  // every worker is done with tile n-2: its gate buffer can be reused
+      gate_scan_regs(fsm + SM::fGates + (n & 1) * GateBuf::kFloats, raw);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_g[n & 1]);
+      if (n + 1 < p.NT) raw = raw_of(n + 1);  // stays in flight until the next hand-back
+    }
+    for (int n = max(p.NT - 2, 0); n < p.NT; ++n) named_sync(NB_C, kNbC);  // match the workers' remaining arrivals
   } else {
     // =========================== worker warps ===================================================
     float m_run = p.m0 ? p.m0[bh] : 0.f;
@@ -349,46 +427,45 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       const float m_t = b_t + fmaxf(m_run, gb[GateBuf::oPm + row]);     // fw.py:178-184
       mbar_wait(&bar_full[s], par_full, 3);
       if (c > 0) mbar_wait(&bar_n, (c - 1) & 1, 4);  // n_{k-1} finalised
-      TC_PROF(c, 1);
-      // ---- Kbar = abar . K (this thread: row, 32 columns); column sums for n; partial q . n ------
+      // ---- partial q . n_{k-1} over this thread's 32 columns ---------------------------------------
       {
-        const float ab = __expf(g - b_t + i_t - m_next);  // fw.py:102 (exp(-inf) = 0 for tail tokens)
-        float kb[32];
         float qn = 0.f;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint32_t off = swz128(row, ch * 32 + 8 * j);
-          uint4 u = *reinterpret_cast<const uint4*>(sK + off);
-          float2 a0 = unpack2<T>(u.x), a1 = unpack2<T>(u.y), a2 = unpack2<T>(u.z), a3 = unpack2<T>(u.w);
-          kb[8 * j + 0] = a0.x * ab; kb[8 * j + 1] = a0.y * ab; kb[8 * j + 2] = a1.x * ab; kb[8 * j + 3] = a1.y * ab;
-          kb[8 * j + 4] = a2.x * ab; kb[8 * j + 5] = a2.y * ab; kb[8 * j + 6] = a3.x * ab; kb[8 * j + 7] = a3.y * ab;
-          uint4 q = *reinterpret_cast<const uint4*>(sQ + off);
+          uint4 q = *reinterpret_cast<const uint4*>(sQ + swz128(row, ch * 32 + 8 * j));
           float2 q0 = unpack2<T>(q.x), q1 = unpack2<T>(q.y), q2 = unpack2<T>(q.z), q3 = unpack2<T>(q.w);
           const float4 n0 = *reinterpret_cast<const float4*>(sNc + ch * 32 + 8 * j);
           const float4 n1 = *reinterpret_cast<const float4*>(sNc + ch * 32 + 8 * j + 4);
           qn += q0.x * n0.x + q0.y * n0.y + q1.x * n0.z + q1.y * n0.w + q2.x * n1.x + q2.y * n1.y + q3.x * n1.z + q3.y * n1.w;
         }
-        store_row32<T>(sKb, row, ch * 32, kb);
         sqn[ch * LT + row] = qn;
-        const float cs = warp_colsum32(kb, lane);  // sum over this warp's 32 rows of column ch*32 + lane
-        snp[rb * D + ch * 32 + lane] = cs;
       }
-      fence_proxy_async_smem();
-      named_arrive(NB_A, kTcThreads);
-      TC_PROF(c, 2);
+      TC_PROF(c, 1);
       // ---- P = S . D (causal), row sums ----------------------------------------------------------
       mbar_wait(&bar_s, par, 5);
       tc_fence_after_sync();
-      TC_PROF(c, 3);
+      TC_PROF(c, 2);
       {
         const float x_t = (b_t - m_t) * kLog2e + log2f(p.scale);
         const float* sy = gb + GateBuf::oY;
+        const float* scf = gb + GateBuf::oCf;
         float rs = 0.f;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if ((u & 1) != ch) continue;  // warp-uniform
+#pragma unroll 1
+        for (int u = ch; u < 4; u += 2) {  // this thread's two 32-column units (warp-uniform branches)
           float v[32];
-          if (u <= rb) {
+          if (u < rb) {  // block strictly below the diagonal: rank-1 decay, one exp per row
+            tmem_ld32(tS + lane_base + u * 32, v);
+            const float r_t = ex2_approx(x_t + gb[GateBuf::oScal + 4 + u]);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 cf = *reinterpret_cast<const float4*>(scf + u * 32 + 4 * j4);
+              v[4 * j4 + 0] *= cf.x * r_t;
+              v[4 * j4 + 1] *= cf.y * r_t;
+              v[4 * j4 + 2] *= cf.z * r_t;
+              v[4 * j4 + 3] *= cf.w * r_t;
+              rs += (v[4 * j4 + 0] + v[4 * j4 + 1]) + (v[4 * j4 + 2] + v[4 * j4 + 3]);
+            }
+          } else if (u == rb) {  // diagonal block: causal mask, one exp per entry
             tmem_ld32(tS + lane_base + u * 32, v);
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
@@ -398,7 +475,7 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
               for (int e = 0; e < 4; ++e) {
                 const int j = 4 * j4 + e;
                 float pv = v[j] * ex2_approx(x_t + yy[e]);
-                pv = (u < rb || j <= lane) ? pv : 0.f;
+                pv = j <= lane ? pv : 0.f;
                 rs += pv;
                 v[j] = pv;
               }
@@ -411,32 +488,34 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
         }
         srs[ch * LT + row] = rs;
       }
+      TC_PROF(c, 3);
       fence_proxy_async_smem();
-      tc_fence_before_sync();
-      named_arrive(NB_B, kTcThreads);
       TC_PROF(c, 4);
-      // ---- state update C_k = gbar C_{k-1} + dC; n_k -------------------------------------------------
-      mbar_wait(&bar_dc, par, 6);
-      tc_fence_after_sync();
+      tc_fence_before_sync();
+      named_arrive(NB_B, kNbAB);
       TC_PROF(c, 5);
+      // ---- Kbar = abar . K (this thread: row, 32 columns); column sums for n (overlaps the H MMAs) --
       {
-        float v[32];
-        tmem_ld32(tDC + lane_base + ch * 32, v);  // M=64 layout: lanes 0-15 of each quadrant hold rows
-        if (owns_c) {
+        const float ab = __expf(g - b_t + i_t - m_next);  // fw.py:102 (exp(-inf) = 0 for tail tokens)
+        float kb[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) Creg[j] = gbar * Creg[j] + v[j];
+        for (int j = 0; j < 4; ++j) {
+          uint4 u = *reinterpret_cast<const uint4*>(sK + swz128(row, ch * 32 + 8 * j));
+          float2 a0 = unpack2<T>(u.x), a1 = unpack2<T>(u.y), a2 = unpack2<T>(u.z), a3 = unpack2<T>(u.w);
+          kb[8 * j + 0] = a0.x * ab; kb[8 * j + 1] = a0.y * ab; kb[8 * j + 2] = a1.x * ab; kb[8 * j + 3] = a1.y * ab;
+          kb[8 * j + 4] = a2.x * ab; kb[8 * j + 5] = a2.y * ab; kb[8 * j + 6] = a3.x * ab; kb[8 * j + 7] = a3.y * ab;
         }
-        if (tid < D) {  // n_k = gbar n_{k-1} + column sums of Kbar (fw.py:116)
-          sNn[tid] = gbar * sNc[tid] + ((snp[tid] + snp[D + tid]) + (snp[2 * D + tid] + snp[3 * D + tid]));
-          mbar_arrive(&bar_n);
-        }
+        store_row32<T>(sKb, row, ch * 32, kb);
+        const float cs = warp_colsum32(kb, lane);  // sum over this warp's 32 rows of column ch*32 + lane
+        snp[rb * D + ch * 32 + lane] = cs;
+        fence_proxy_async_smem();
+        named_arrive(NB_A, kNbAB);
       }
       TC_PROF(c, 6);
       // ---- epilogue -----------------------------------------------------------------------------------
       mbar_wait(&bar_h, par, 7);
       tc_fence_after_sync();
       TC_PROF(c, 7);
-      if (owns_c) store_row32<T>(sC, drow, ch * 32, Creg);  // the Q C_{k-1} MMA has finished reading the old copy
       {
         uint32_t hi[32], hx[32];
         tmem_ld32_nowait(tHi + lane_base + ch * 32, hi);
@@ -455,9 +534,25 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
           p.m_out[(int64_t)bh * p.S + t0 + row] = m_t;
         }
       }
+      // ---- state update C_k = gbar C_{k-1} + dC; n_k ---------------------------------------------------
+      mbar_wait(&bar_dc, par, 6);
+      tc_fence_after_sync();
+      {
+        float v[32];
+        tmem_ld32(tDC + lane_base + ch * 32, v);  // M=64 layout: lanes 0-15 of each quadrant hold rows
+        if (owns_c) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) Creg[j] = gbar * Creg[j] + v[j];
+          store_row32<T>(sC, drow, ch * 32, Creg);  // Q C_{k-1} (bar_h) has finished reading the old copy
+        }
+        if (tid < D) {  // n_k = gbar n_{k-1} + column sums of Kbar (fw.py:116)
+          sNn[tid] = gbar * sNc[tid] + ((snp[tid] + snp[D + tid]) + (snp[2 * D + tid] + snp[3 * D + tid]));
+          mbar_arrive(&bar_n);
+        }
+      }
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      named_arrive(NB_C, kTcThreads);
+      named_arrive(NB_C, kNbC);
       TC_PROF(c, 8);
       m_run = m_next;
       cur ^= 1;
@@ -543,17 +638,20 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
   uint8_t* sCs = smem + SM::oCs;
   uint8_t* sdC = smem + SM::odC;
   float* fsm = (float*)(smem + SM::oSmall);
-  __shared__ uint64_t bar_full, bar_s, bar_d, bar_main, bar_g[2];
+  __shared__ uint64_t bar_full, bar_s, bar_q, bar_v, bar_k, bar_d, bar_g[2];
   __shared__ uint32_t tmem_base_s;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: role branches stay uniform
   const int bh = blockIdx.x, b = bh / p.NH, hh = bh % p.NH;
 
   if (tid == 0) {
     mbar_init(&bar_full, 1);
     mbar_init(&bar_s, 1);
+    mbar_init(&bar_q, 1);
+    mbar_init(&bar_v, 1);
+    mbar_init(&bar_k, 1);
     mbar_init(&bar_d, 1);
-    mbar_init(&bar_main, 1);
     mbar_init(&bar_g[0], 1);
     mbar_init(&bar_g[1], 1);
     fence_mbar_init();
@@ -605,26 +703,13 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       tma_load_4d(sdH, &mapdH, &bar_full, 0, c * LT, hh, b);
       tma_load_4d(sCs, &mapCs, &bar_full, 0, c * D, hh, b);
     };
-    // gate vectors + saved per-token m / n of tile c into buffer `gb`
-    auto tile_vectors = [&](float* gb, int c) {
-      const int t0 = c * LT, n_valid = min(LT, p.S - t0);
-      control_gate_scan<T>(gb, ip + (int64_t)t0 * p.ig_ss, p.ig_ss, fp + (int64_t)t0 * p.fg_ss, p.fg_ss, n_valid);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int t = lane + 32 * e;
-        gb[GateBuf::oMt + t] = t < n_valid ? mo[t0 + t] : 0.f;
-        gb[GateBuf::oNt + t] = t < n_valid ? no[t0 + t] : 1.f;
-      }
-      if (lane == 0) {
-        gb[GateBuf::oScal + 2] = c > 0 ? mo[t0 - 1] : (p.m0 ? p.m0[bh] : 0.f);  // m of the state entering the tile
-        gb[GateBuf::oScal + 3] = mo[t0 + n_valid - 1];                          // m of the state leaving it
-      }
+    auto prefetch_l2 = [&](int c) {
+      tma_prefetch_4d(&mapQ, 0, c * LT, hh, b);
+      tma_prefetch_4d(&mapK, 0, c * LT, hh, b);
+      tma_prefetch_4d(&mapV, 0, c * LT, hh, b);
+      tma_prefetch_4d(&mapdH, 0, c * LT, hh, b);
+      tma_prefetch_4d(&mapCs, 0, c * D, hh, b);
     };
-    if (lane == 0) issue_loads(p.NT - 1);
-    tile_vectors(fsm + SM::fGates, p.NT - 1);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&bar_g[0]);
-
     constexpr uint32_t id_s = umma_idesc(128, 128, false, false, kBf16);
     constexpr uint32_t id_c = umma_idesc(64, 64, true, true, kBf16);
     constexpr uint32_t id_k_mn = umma_idesc(128, 64, false, true, kBf16);   // A K-major, B MN-major
@@ -639,46 +724,33 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
     const uint64_t kdS = umma_smem_desc(smem_u32(sdS), 0, 1024), mdS = umma_smem_desc(smem_u32(sdS), SM::kTile, 1024);
     const uint64_t kCs = umma_smem_desc(smem_u32(sCs), 0, 1024);
     const uint64_t kdC = umma_smem_desc(smem_u32(sdC), 0, 1024), mdC = umma_smem_desc(smem_u32(sdC), D * 128, 1024);
-    float carry = 0.f;  // running suffix sum of (q.dq - k.dk)
+    auto issue_s = [&](uint32_t par) {  // S = Q K^T, dSb = dH V^T of the tile whose loads are in flight
+      mbar_wait(&bar_full, par, 11);
+      tc_fence_after_sync();
+#pragma unroll
+      for (int kk = 0; kk < D / 16; ++kk)
+        umma_f16(tS, umma_desc_advance(kQ, kk * 32), umma_desc_advance(kK, kk * 32), id_s, kk > 0);
+#pragma unroll
+      for (int kk = 0; kk < D / 16; ++kk)
+        umma_f16(tdSb, umma_desc_advance(kH, kk * 32), umma_desc_advance(kV, kk * 32), id_s, kk > 0);
+      tma_store_wait_read<0>();  // the previous tile's dq / dk / dv staging buffers are free again ...
+      umma_commit(&bar_s);       // ... which the workers learn from the same barrier
+    };
+
+    if (lane == 0) {
+      issue_loads(p.NT - 1);
+      if (p.NT > 1) prefetch_l2(p.NT - 2);
+    }
+    if (lane == 0) issue_s(0);
+    __syncwarp();
 
     for (int it = 0; it < p.NT; ++it) {
       const int c = p.NT - 1 - it, pb = it & 1;
       const uint32_t par = it & 1;
       const int t0 = c * LT, n_valid = min(LT, p.S - t0);
       TC_PROF(it, 9);
-      if (lane == 0) {
-        tma_store_wait_read<0>();  // previous tile's dq / dk / dv staging buffers are free again
-        mbar_wait(&bar_full, par, 11);
-        tc_fence_after_sync();
-#pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk)  // S = Q K^T
-          umma_f16(tS, umma_desc_advance(kQ, kk * 32), umma_desc_advance(kK, kk * 32), id_s, kk > 0);
-#pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk)  // dSb = dH V^T
-          umma_f16(tdSb, umma_desc_advance(kH, kk * 32), umma_desc_advance(kV, kk * 32), id_s, kk > 0);
-        umma_commit(&bar_s);
-      }
-      __syncwarp();
-      named_sync(NB_A, kTcThreads);  // Qt written
+      named_sync(NB_B, kNbAB);  // Sb', dS written
       TC_PROF(it, 10);
-      if (lane == 0) {
-#pragma unroll
-        for (int kk = 0; kk < LT / 16; ++kk)  // ddC = Qt^T dH
-          umma_f16(tddC, umma_desc_advance(mQt, kk * 2048), umma_desc_advance(mH, kk * 2048), id_c, kk > 0);
-#pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk)  // dQb = dH C_{k-1}^T
-          umma_f16(tdQb, umma_desc_advance(kH, kk * 32), umma_desc_advance(kCs, kk * 32), id_k_k, kk > 0);
-        umma_commit(&bar_d);
-      }
-      __syncwarp();
-      if (it + 1 < p.NT) {  // vectors of the next tile, one tile ahead of the workers
-        tile_vectors(fsm + SM::fGates + ((it + 1) & 1) * GateBuf::kFloats, c - 1);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_g[(it + 1) & 1]);
-      }
-      TC_PROF(it, 11);
-      named_sync(NB_B, kTcThreads);  // Sb', dS written
-      TC_PROF(it, 12);
       if (lane == 0) {
         tc_fence_after_sync();
 #pragma unroll
@@ -686,31 +758,93 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
           umma_f16(tdQa, umma_desc_advance(kdS, (kk / 4) * SM::kTile + (kk % 4) * 32), umma_desc_advance(mK, kk * 2048),
                    id_k_mn, kk > 0);
 #pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)  // dQb = dH C_{k-1}^T
+          umma_f16(tdQb, umma_desc_advance(kH, kk * 32), umma_desc_advance(kCs, kk * 32), id_k_k, kk > 0);
+        umma_commit(&bar_q);
+#pragma unroll
         for (int kk = 0; kk < LT / 16; ++kk)  // dV1 = Sb'^T dH
           umma_f16(tdV1, umma_desc_advance(mSb, kk * 2048), umma_desc_advance(mH, kk * 2048), id_mn_mn, kk > 0);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk)  // dV2 = K dC_k
           umma_f16(tdV2, umma_desc_advance(kK, kk * 32), umma_desc_advance(mdC, kk * 2048), id_k_mn, kk > 0);
+        umma_commit(&bar_v);
 #pragma unroll
         for (int kk = 0; kk < LT / 16; ++kk)  // dK1 = dS^T Q
           umma_f16(tdK1, umma_desc_advance(mdS, kk * 2048), umma_desc_advance(mQ, kk * 2048), id_mn_mn, kk > 0);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk)  // dK2 = V dC_k^T
           umma_f16(tdK2, umma_desc_advance(kV, kk * 32), umma_desc_advance(kdC, kk * 32), id_k_k, kk > 0);
-        umma_commit(&bar_main);
-        TC_PROF(it, 13);
-        mbar_wait(&bar_main, par, 15);  // every MMA is done with this tile's inputs: refill them
+        umma_commit(&bar_k);
+        if (c > 1) prefetch_l2(c - 2);  // pull the tile after next into L2 (its smem stage is single-buffered)
+      }
+      __syncwarp();
+      TC_PROF(it, 11);
+      named_sync(NB_A, kNbAB);  // Qt written
+      TC_PROF(it, 12);
+      if (lane == 0) {
+#pragma unroll
+        for (int kk = 0; kk < LT / 16; ++kk)  // ddC = Qt^T dH
+          umma_f16(tddC, umma_desc_advance(mQt, kk * 2048), umma_desc_advance(mH, kk * 2048), id_c, kk > 0);
+        umma_commit(&bar_d);
+        mbar_wait(&bar_d, par, 15);  // last MMA of the tile: its inputs can be refilled
         if (c > 0) issue_loads(c - 1);
       }
       __syncwarp();
-      named_sync(NB_C, kTcThreads);  // dq / dk / dv staged
+      TC_PROF(it, 13);
+      named_sync(NB_C, kNbC);  // dq / dk / dv staged, dC_{k-1} written
       TC_PROF(it, 14);
       if (lane == 0) {
         tma_store_4d(&mapdQ, sdQ, 0, t0, hh, b);
         tma_store_4d(&mapdV, sSb, 0, t0, hh, b);
         tma_store_4d(&mapdK, sdS, 0, t0, hh, b);
         tma_store_commit();
+        if (c > 0) issue_s(par ^ 1);  // S / dSb of the next tile (their TMEM columns were read by this epilogue)
       }
+      __syncwarp();
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  } else if (warp == kScanWarp) {
+    // =========================== scan warp: tile vectors two tiles ahead + dI / dF ==================
+    // raw per-tile vectors (gate inputs, saved m / n) are loaded one tile before they are scanned
+    struct TileRaw {
+      GateRaw<T> g;
+      float4 mt, nt;
+      float m_prev, m_next;
+    };
+    auto raw_of = [&](int c) {
+      TileRaw r;
+      const int t0 = c * LT, n_valid = min(LT, p.S - t0);
+      r.g = load_gate_raw<T>(ip + (int64_t)t0 * p.ig_ss, p.ig_ss, fp + (int64_t)t0 * p.fg_ss, p.fg_ss, n_valid);
+      if (lane * 4 < n_valid) {  // n_valid is a multiple of 64
+        r.mt = *reinterpret_cast<const float4*>(mo + t0 + lane * 4);
+        r.nt = *reinterpret_cast<const float4*>(no + t0 + lane * 4);
+      } else {
+        r.mt = make_float4(0.f, 0.f, 0.f, 0.f);
+        r.nt = make_float4(1.f, 1.f, 1.f, 1.f);
+      }
+      r.m_prev = c > 0 ? mo[t0 - 1] : (p.m0 ? p.m0[bh] : 0.f);  // m of the state entering the tile
+      r.m_next = mo[t0 + n_valid - 1];                          // m of the state leaving it
+      return r;
+    };
+    auto publish = [&](float* gb, const TileRaw& r) {
+      gate_scan_regs(gb, r.g);
+      reinterpret_cast<float4*>(gb + GateBuf::oMt)[lane] = r.mt;
+      reinterpret_cast<float4*>(gb + GateBuf::oNt)[lane] = r.nt;
+      if (lane == 0) {
+        gb[GateBuf::oScal + 2] = r.m_prev;
+        gb[GateBuf::oScal + 3] = r.m_next;
+      }
+    };
+
+    TileRaw raw = raw_of(p.NT - 1);
+    float carry = 0.f;  // running suffix sum of (q.dq - k.dk)
+    // n = processing index of the tile whose vectors are published; the dI / dF scan lags two tiles
+    for (int n = 0; n < p.NT + 2; ++n) {
+      if (n >= 2) {
+      const int it = n - 2;
+      const int c = p.NT - 1 - it, pb = it & 1;
+      const int t0 = c * LT, n_valid = min(LT, p.S - t0);
+      named_sync(NB_C, kNbC);  // row dots of tile `it` are in shared memory; its buffers can be reused afterwards
       // ---- gate gradients: reverse (suffix) scan over the tile, carried across tiles -------------
       {
         const float* sp = fsm + SM::fPart + pb * 6 * LT;
@@ -746,8 +880,14 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
         carry += __shfl_sync(0xffffffffu, incl, 0);
       }
       __syncwarp();
+      }
+      if (n < p.NT) {
+        publish(fsm + SM::fGates + (n & 1) * GateBuf::kFloats, raw);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_g[n & 1]);
+        if (n + 1 < p.NT) raw = raw_of(p.NT - 2 - n);
+      }
     }
-    if (lane == 0) tma_store_wait_all<0>();
   } else {
     // =========================== worker warps ===================================================
     for (int it = 0; it < p.NT; ++it) {
@@ -767,9 +907,67 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       const float bbar = valid ? __expf(b_t + m_prev - m_t) : 0.f;  // bw.py:186
       const float abar = __expf(g - b_t + i_t - m_next);            // bw.py:187 (0 for tail tokens)
       const float gbar = __expf(g + m_prev - m_next);               // bw.py:76
-      mbar_wait(&bar_full, par, 13);
       TC_PROF(it, 1);
-      // ---- Qt = wq . Q; keep this thread's q / k / v row slices for the gate gradients ------------
+      // ---- W = D / (n + eps); Sb' = S.scale.W, dS = dSb.W ------------------------------------------
+      mbar_wait(&bar_s, par, 14);
+      tc_fence_after_sync();
+      TC_PROF(it, 2);
+      {
+        // the 1/(n+eps) and scale factors ride in the exponent: W = 2^(x_t + y_s)
+        const float x_t = valid ? (b_t - m_t) * kLog2e + log2f(rinv) : -INFINITY;
+        const float* sy = gb + GateBuf::oY;
+        const float* scf = gb + GateBuf::oCf;
+#pragma unroll 1
+        for (int u = ch; u < 4; u += 2) {  // this thread's two 32-column units (warp-uniform branches)
+          float v[32], w[32];
+          if (u <= rb) {
+            uint32_t rv[32], rw[32];
+            tmem_ld32_nowait(tS + lane_base + u * 32, rv);
+            tmem_ld32_nowait(tdSb + lane_base + u * 32, rw);
+            tmem_ld_wait();
+            if (u < rb) {  // block strictly below the diagonal: rank-1 decay, one exp per row
+              const float r_t = ex2_approx(x_t + gb[GateBuf::oScal + 4 + u]);
+              const float r_s = r_t * p.scale;
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 cf = *reinterpret_cast<const float4*>(scf + u * 32 + 4 * j4);
+                const float cc[4] = {cf.x, cf.y, cf.z, cf.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int j = 4 * j4 + e;
+                  v[j] = __uint_as_float(rv[j]) * (cc[e] * r_s);
+                  w[j] = __uint_as_float(rw[j]) * (cc[e] * r_t);
+                }
+              }
+            } else {  // diagonal block: causal mask, one exp per entry
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 y = *reinterpret_cast<const float4*>(sy + u * 32 + 4 * j4);
+                const float yy[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int j = 4 * j4 + e;
+                  float wg = ex2_approx(x_t + yy[e]);
+                  wg = j <= lane ? wg : 0.f;
+                  v[j] = __uint_as_float(rv[j]) * (wg * p.scale);
+                  w[j] = __uint_as_float(rw[j]) * wg;
+                }
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { v[j] = 0.f; w[j] = 0.f; }
+          }
+          store_row32<T>(sSb, row, u * 32, v);
+          store_row32<T>(sdS, row, u * 32, w);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      named_arrive(NB_B, kNbAB);
+      TC_PROF(it, 3);
+      // ---- Qt = wq . Q; keep this thread's q / k / v row slices for the gate gradients (overlaps MMAs)
+      mbar_wait(&bar_full, par, 13);
       uint32_t qs[16], ks[16], vs[16];
       {
         const float wq = p.scale * bbar * rinv;  // bw.py:83-90
@@ -791,72 +989,17 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
         }
       }
       fence_proxy_async_smem();
-      named_arrive(NB_A, kTcThreads);
-      TC_PROF(it, 2);
-      // ---- W; Sb' = S.scale.W, dS = dSb.W ------------------------------------------------------------
-      mbar_wait(&bar_s, par, 14);
-      tc_fence_after_sync();
-      TC_PROF(it, 3);
-      {
-        const float x_t = (b_t - m_t) * kLog2e;
-        const float* sy = gb + GateBuf::oY;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if ((u & 1) != ch) continue;
-          float v[32], w[32];
-          if (u <= rb) {
-            uint32_t rv[32], rw[32];
-            tmem_ld32_nowait(tS + lane_base + u * 32, rv);
-            tmem_ld32_nowait(tdSb + lane_base + u * 32, rw);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 y = *reinterpret_cast<const float4*>(sy + u * 32 + 4 * j4);
-              const float yy[4] = {y.x, y.y, y.z, y.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int j = 4 * j4 + e;
-                const float wg = ex2_approx(x_t + yy[e]) * rinv;
-                const bool keep = valid && (u < rb || j <= lane);
-                v[j] = keep ? __uint_as_float(rv[j]) * p.scale * wg : 0.f;
-                w[j] = keep ? __uint_as_float(rw[j]) * wg : 0.f;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { v[j] = 0.f; w[j] = 0.f; }
-          }
-          store_row32<T>(sSb, row, u * 32, v);
-          store_row32<T>(sdS, row, u * 32, w);
-        }
-      }
-      fence_proxy_async_smem();
-      tc_fence_before_sync();
-      named_arrive(NB_B, kTcThreads);
+      named_arrive(NB_A, kNbAB);
       TC_PROF(it, 4);
-      // ---- dC_{k-1} = gbar dC_k + ddC (registers) --------------------------------------------------
-      mbar_wait(&bar_d, par, 15);
-      tc_fence_after_sync();
-      TC_PROF(it, 5);
-      {
-        float v[32];
-        tmem_ld32(tddC + lane_base + ch * 32, v);
-        if (owns_c) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) dCreg[j] = gbar * dCreg[j] + v[j];  // bw.py:93-95
-        }
-      }
-      TC_PROF(it, 6);
-      // ---- epilogue ------------------------------------------------------------------------------------
-      mbar_wait(&bar_main, par, 16);
-      tc_fence_after_sync();
-      TC_PROF(it, 7);
-      if (owns_c) store_row32<T>(sdC, drow, ch * 32, dCreg);
+      // ---- epilogues, pipelined with the MMA batch through three commits ------------------------------
       {
         uint32_t ra[32], rq[32];
         float o[32];
         float dot;
         // dq
+        mbar_wait(&bar_q, par, 16);
+        tc_fence_after_sync();
+        TC_PROF(it, 5);
         tmem_ld32_nowait(tdQa + lane_base + ch * 32, ra);
         tmem_ld32_nowait(tdQb + lane_base + ch * 32, rq);
         tmem_ld_wait();
@@ -872,6 +1015,8 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
         store_row32<T>(sdQ, row, ch * 32, o);
         spart[(0 * 2 + ch) * LT + row] = dot;
         // dv
+        mbar_wait(&bar_v, par, 17);
+        tc_fence_after_sync();
         tmem_ld32_nowait(tdV1 + lane_base + ch * 32, ra);
         tmem_ld32_nowait(tdV2 + lane_base + ch * 32, rq);
         tmem_ld_wait();
@@ -883,9 +1028,12 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
           float2 vv = unpack2<T>(vs[j]);
           dot += vv.x * o[2 * j] + vv.y * o[2 * j + 1];
         }
-        store_row32<T>(sSb, row, ch * 32, o);
+        store_row32<T>(sSb, row, ch * 32, o);  // dV1 (the only reader of Sb') has completed
         spart[(2 * 2 + ch) * LT + row] = dot;
         // dk
+        mbar_wait(&bar_k, par, 18);
+        tc_fence_after_sync();
+        TC_PROF(it, 6);
         tmem_ld32_nowait(tdK1 + lane_base + ch * 32, ra);
         tmem_ld32_nowait(tdK2 + lane_base + ch * 32, rq);
         tmem_ld_wait();
@@ -897,12 +1045,25 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
           float2 kv = unpack2<T>(ks[j]);
           dot += kv.x * o[2 * j] + kv.y * o[2 * j + 1];
         }
-        store_row32<T>(sdS, row, ch * 32, o);
+        store_row32<T>(sdS, row, ch * 32, o);  // dQa and dK1 (the readers of dS) have completed
         spart[(1 * 2 + ch) * LT + row] = dot;
+      }
+      // ---- dC_{k-1} = gbar dC_k + ddC ----------------------------------------------------------------
+      mbar_wait(&bar_d, par, 15);
+      tc_fence_after_sync();
+      TC_PROF(it, 7);
+      {
+        float v[32];
+        tmem_ld32(tddC + lane_base + ch * 32, v);
+        if (owns_c) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dCreg[j] = gbar * dCreg[j] + v[j];  // bw.py:93-95
+          store_row32<T>(sdC, drow, ch * 32, dCreg);                       // dV2 / dK2 have completed (bar_k)
+        }
       }
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      named_arrive(NB_C, kTcThreads);
+      named_arrive(NB_C, kNbC);
       TC_PROF(it, 8);
     }
     if (p.dc0 && owns_c) {  // dC_initial = dC_0 (bw.py:329-331)
