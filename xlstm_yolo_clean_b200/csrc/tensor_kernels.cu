@@ -327,13 +327,12 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
         umma_f16(tS, umma_desc_advance(dQ, kk * 32), umma_desc_advance(dK, kk * 32), id_s, kk > 0);
       umma_commit(&bar_s);
     };
-    if (lane == 0) {
-      if (p.store_states) {  // state entering tile 0 (bf16 operand copy) -> c_states[b, h, 0]
-        tma_store_4d(&mapCs, sC, 0, 0, hh, b);
-        tma_store_commit();
-      }
-      issue_s(0, std::integral_constant<int, 0>{});
+    if (lane == 0 && p.store_states) {  // state entering tile 0 (bf16 operand copy) -> c_states[b, h, 0]
+      tma_store_4d(&mapCs, sC, 0, 0, hh, b);
+      tma_store_commit();
     }
+    __syncwarp();
+    if (elect_one()) issue_s(0, std::integral_constant<int, 0>{});
     __syncwarp();
 
     auto tile_body = [&](int c, auto PAR) {
@@ -343,9 +342,12 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       TC_PROF(c, 9);
       named_sync(NB_B, kNbAB);  // P(c) written
       if (lane == 0) {
-        tc_fence_after_sync();
         tma_store_wait_read<0>();  // earlier h / c_states stores have read sH and sC (rewritten after bar_h)
         TC_PROF(c, 10);
+      }
+      __syncwarp();
+      if (elect_one()) {  // elect.sync lets ptxas emit straight-line UTCHMMA (no per-instruction thread loop)
+        tc_fence_after_sync();
 #pragma unroll
         for (int kk = 0; kk < LT / 16; ++kk)  // Hintra = P V
           umma_f16(tHi, umma_desc_advance(dP, (kk / 4) * SM::kTile + (kk % 4) * 32), umma_desc_advance(dV, kk * 2048), id_h,
@@ -354,20 +356,19 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
         for (int kk = 0; kk < D / 16; ++kk)  // Hinter = Q C_{k-1}
           umma_f16(tHx, umma_desc_advance(dQ, kk * 32), umma_desc_advance(dC, kk * 2048), id_h, kk > 0);
         umma_commit(&bar_h);
-        TC_PROF(c, 11);
       }
       __syncwarp();
+      TC_PROF(c, 11);
       named_sync(NB_A, kNbAB);  // Kbar(c) written
-      if (lane == 0) {
-        TC_PROF(c, 12);
+      if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < LT / 16; ++kk)  // dC = Kbar^T V
           umma_f16(tDC, umma_desc_advance(dKb, kk * 2048), umma_desc_advance(dV, kk * 2048), id_dc, kk > 0);
         umma_commit(&bar_dc);
         if (c + 1 < p.NT) issue_s(c + 1, std::integral_constant<int, par ^ 1>{});  // next tile's S, other TMEM buffer
-        TC_PROF(c, 13);
       }
       __syncwarp();
+      TC_PROF(c, 13);
       named_sync(NB_C, kNbC);  // h staged, C_k written: every worker is done with this tile
       if (lane == 0) {
         TC_PROF(c, 14);
@@ -604,10 +605,12 @@ struct BwSmem {
   static constexpr int kTile = LT * 128;
   static constexpr int oQ = 0, oK = kTile, oV = 2 * kTile, odH = 3 * kTile;
   static constexpr int oQt = 4 * kTile;       // wq . Q
-  static constexpr int oSb = 5 * kTile;       // Sb' two halves (dv staging in half 0)
-  static constexpr int odS = 7 * kTile;       // dS  two halves (dk staging in half 0)
-  static constexpr int odQ = 9 * kTile;       // dq staging
-  static constexpr int oCs = 10 * kTile;      // C_{k-1}, 64 x 64 bf16 (TMA)
+  static constexpr int oSb = 5 * kTile;       // Sb' two halves
+  static constexpr int odS = 7 * kTile;       // dS  two halves
+  static constexpr int odQ = 9 * kTile;       // dq / dv / dk staging (their stores overlap the next tile's W phase)
+  static constexpr int odV = 10 * kTile;
+  static constexpr int odK = 11 * kTile;
+  static constexpr int oCs = 12 * kTile;      // C_{k-1}, 64 x 64 bf16 (TMA)
   static constexpr int odC = oCs + 64 * 128;  // dC_k bf16 operand copy
   static constexpr int oSmall = odC + 64 * 128;
   // floats: gates[2], spart[2][6][LT]
@@ -635,6 +638,8 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
   uint8_t* sSb = smem + SM::oSb;
   uint8_t* sdS = smem + SM::odS;
   uint8_t* sdQ = smem + SM::odQ;
+  uint8_t* sdV = smem + SM::odV;
+  uint8_t* sdK = smem + SM::odK;
   uint8_t* sCs = smem + SM::oCs;
   uint8_t* sdC = smem + SM::odC;
   float* fsm = (float*)(smem + SM::oSmall);
@@ -733,15 +738,15 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
 #pragma unroll
       for (int kk = 0; kk < D / 16; ++kk)
         umma_f16(tdSb, umma_desc_advance(kH, kk * 32), umma_desc_advance(kV, kk * 32), id_s, kk > 0);
-      tma_store_wait_read<0>();  // the previous tile's dq / dk / dv staging buffers are free again ...
-      umma_commit(&bar_s);       // ... which the workers learn from the same barrier
+      umma_commit(&bar_s);
     };
 
     if (lane == 0) {
       issue_loads(p.NT - 1);
       if (p.NT > 1) prefetch_l2(p.NT - 2);
     }
-    if (lane == 0) issue_s(0);
+    __syncwarp();
+    if (elect_one()) issue_s(0);
     __syncwarp();
 
     for (int it = 0; it < p.NT; ++it) {
@@ -751,7 +756,9 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       TC_PROF(it, 9);
       named_sync(NB_B, kNbAB);  // Sb', dS written
       TC_PROF(it, 10);
-      if (lane == 0) {
+      if (lane == 0) tma_store_wait_read<0>();  // the previous tile's dq / dk / dv stores have left their staging buffers
+      __syncwarp();
+      if (elect_one()) {
         tc_fence_after_sync();
 #pragma unroll
         for (int kk = 0; kk < LT / 16; ++kk)  // dQa = dS K
@@ -775,13 +782,13 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
         for (int kk = 0; kk < D / 16; ++kk)  // dK2 = V dC_k^T
           umma_f16(tdK2, umma_desc_advance(kV, kk * 32), umma_desc_advance(kdC, kk * 32), id_k_k, kk > 0);
         umma_commit(&bar_k);
-        if (c > 1) prefetch_l2(c - 2);  // pull the tile after next into L2 (its smem stage is single-buffered)
       }
       __syncwarp();
+      if (lane == 0 && c > 1) prefetch_l2(c - 2);  // pull the tile after next into L2 (single-buffered smem stage)
       TC_PROF(it, 11);
       named_sync(NB_A, kNbAB);  // Qt written
       TC_PROF(it, 12);
-      if (lane == 0) {
+      if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < LT / 16; ++kk)  // ddC = Qt^T dH
           umma_f16(tddC, umma_desc_advance(mQt, kk * 2048), umma_desc_advance(mH, kk * 2048), id_c, kk > 0);
@@ -795,11 +802,12 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       TC_PROF(it, 14);
       if (lane == 0) {
         tma_store_4d(&mapdQ, sdQ, 0, t0, hh, b);
-        tma_store_4d(&mapdV, sSb, 0, t0, hh, b);
-        tma_store_4d(&mapdK, sdS, 0, t0, hh, b);
+        tma_store_4d(&mapdV, sdV, 0, t0, hh, b);
+        tma_store_4d(&mapdK, sdK, 0, t0, hh, b);
         tma_store_commit();
-        if (c > 0) issue_s(par ^ 1);  // S / dSb of the next tile (their TMEM columns were read by this epilogue)
       }
+      __syncwarp();
+      if (c > 0 && elect_one()) issue_s(par ^ 1);  // S / dSb of the next tile (their TMEM columns were read by this epilogue)
       __syncwarp();
     }
     if (lane == 0) tma_store_wait_all<0>();
@@ -1028,7 +1036,7 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
           float2 vv = unpack2<T>(vs[j]);
           dot += vv.x * o[2 * j] + vv.y * o[2 * j + 1];
         }
-        store_row32<T>(sSb, row, ch * 32, o);  // dV1 (the only reader of Sb') has completed
+        store_row32<T>(sdV, row, ch * 32, o);
         spart[(2 * 2 + ch) * LT + row] = dot;
         // dk
         mbar_wait(&bar_k, par, 18);
@@ -1045,7 +1053,7 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
           float2 kv = unpack2<T>(ks[j]);
           dot += kv.x * o[2 * j] + kv.y * o[2 * j + 1];
         }
-        store_row32<T>(sdS, row, ch * 32, o);  // dQa and dK1 (the readers of dS) have completed
+        store_row32<T>(sdK, row, ch * 32, o);
         spart[(1 * 2 + ch) * LT + row] = dot;
       }
       // ---- dC_{k-1} = gbar dC_k + ddC ----------------------------------------------------------------
