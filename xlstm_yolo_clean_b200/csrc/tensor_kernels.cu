@@ -88,6 +88,33 @@ __device__ __forceinline__ void store_row32(uint8_t* base, int row, int col0, co
   }
 }
 
+// the same 32 columns written straight to global memory (row pointer `dst` = &out[row][col0])
+template <typename T>
+__device__ __forceinline__ void store_row32_global(T* dst, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 u;
+    u.x = pack2<T>(v[8 * j + 0], v[8 * j + 1]);
+    u.y = pack2<T>(v[8 * j + 2], v[8 * j + 3]);
+    u.z = pack2<T>(v[8 * j + 4], v[8 * j + 5]);
+    u.w = pack2<T>(v[8 * j + 6], v[8 * j + 7]);
+    reinterpret_cast<uint4*>(dst)[j] = u;
+  }
+}
+
+// Coalesced copy-out of 16 rows (row0 .. row0+15) of a swizzled [128][64] staging tile: every
+// instruction moves four complete 128-byte rows (lane -> row lane/8, 16-byte chunk lane%8).
+template <typename T>
+__device__ __forceinline__ void copy_out_rows16(const uint8_t* stage, T* gbase, int64_t gstride, int row0, int n_valid,
+                                                int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = row0 + 4 * i + (lane >> 3), c = (lane & 7) * 8;
+    const uint4 u = *reinterpret_cast<const uint4*>(stage + swz128(r, c));
+    if (r < n_valid) *reinterpret_cast<uint4*>(gbase + (int64_t)r * gstride + c) = u;
+  }
+}
+
 // Column sums over the 32 rows held by a warp: lane L ends up with sum_rows v[.][L]
 // (butterfly transpose-reduce, 31 shuffles).  v is destroyed.
 __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
@@ -596,6 +623,8 @@ struct TcBwParams {
   const float *n_out, *m_out, *dc_last;
   void *di, *df;
   int64_t di_sb, di_sh, di_ss, df_sb, df_sh, df_ss;
+  void *dq, *dk, *dv;  // written straight from registers (64 contiguous bytes per thread and row)
+  int64_t dq_sb, dq_sh, dq_ss, dk_sb, dk_sh, dk_ss, dv_sb, dv_sh, dv_ss;
   float* dc0;
   long long* prof;
 };
@@ -607,7 +636,7 @@ struct BwSmem {
   static constexpr int oQt = 4 * kTile;       // wq . Q
   static constexpr int oSb = 5 * kTile;       // Sb' two halves
   static constexpr int odS = 7 * kTile;       // dS  two halves
-  static constexpr int odQ = 9 * kTile;       // dq / dv / dk staging (their stores overlap the next tile's W phase)
+  static constexpr int odQ = 9 * kTile;       // dq / dv / dk staging for the coalesced copy-out
   static constexpr int odV = 10 * kTile;
   static constexpr int odK = 11 * kTile;
   static constexpr int oCs = 12 * kTile;      // C_{k-1}, 64 x 64 bf16 (TMA)
@@ -623,8 +652,7 @@ template <typename T>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
           const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdH,
-          const __grid_constant__ CUtensorMap mapCs, const __grid_constant__ CUtensorMap mapdQ,
-          const __grid_constant__ CUtensorMap mapdK, const __grid_constant__ CUtensorMap mapdV, TcBwParams p) {
+          const __grid_constant__ CUtensorMap mapCs, TcBwParams p) {
   constexpr int D = 64;
   constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
   using SM = BwSmem;
@@ -665,7 +693,7 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
     tmem_alloc<512>(&tmem_base_s);
     if (lane == 0) {
       prefetch_tmap(&mapQ); prefetch_tmap(&mapK); prefetch_tmap(&mapV); prefetch_tmap(&mapdH);
-      prefetch_tmap(&mapCs); prefetch_tmap(&mapdQ); prefetch_tmap(&mapdK); prefetch_tmap(&mapdV);
+      prefetch_tmap(&mapCs);
     }
   }
   const int rb = warp & 3, ch = (warp >> 2) & 1;
@@ -708,13 +736,6 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       tma_load_4d(sdH, &mapdH, &bar_full, 0, c * LT, hh, b);
       tma_load_4d(sCs, &mapCs, &bar_full, 0, c * D, hh, b);
     };
-    auto prefetch_l2 = [&](int c) {
-      tma_prefetch_4d(&mapQ, 0, c * LT, hh, b);
-      tma_prefetch_4d(&mapK, 0, c * LT, hh, b);
-      tma_prefetch_4d(&mapV, 0, c * LT, hh, b);
-      tma_prefetch_4d(&mapdH, 0, c * LT, hh, b);
-      tma_prefetch_4d(&mapCs, 0, c * D, hh, b);
-    };
     constexpr uint32_t id_s = umma_idesc(128, 128, false, false, kBf16);
     constexpr uint32_t id_c = umma_idesc(64, 64, true, true, kBf16);
     constexpr uint32_t id_k_mn = umma_idesc(128, 64, false, true, kBf16);   // A K-major, B MN-major
@@ -741,10 +762,7 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       umma_commit(&bar_s);
     };
 
-    if (lane == 0) {
-      issue_loads(p.NT - 1);
-      if (p.NT > 1) prefetch_l2(p.NT - 2);
-    }
+    if (lane == 0) issue_loads(p.NT - 1);
     __syncwarp();
     if (elect_one()) issue_s(0);
     __syncwarp();
@@ -756,8 +774,6 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       TC_PROF(it, 9);
       named_sync(NB_B, kNbAB);  // Sb', dS written
       TC_PROF(it, 10);
-      if (lane == 0) tma_store_wait_read<0>();  // the previous tile's dq / dk / dv stores have left their staging buffers
-      __syncwarp();
       if (elect_one()) {
         tc_fence_after_sync();
 #pragma unroll
@@ -784,7 +800,6 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
         umma_commit(&bar_k);
       }
       __syncwarp();
-      if (lane == 0 && c > 1) prefetch_l2(c - 2);  // pull the tile after next into L2 (single-buffered smem stage)
       TC_PROF(it, 11);
       named_sync(NB_A, kNbAB);  // Qt written
       TC_PROF(it, 12);
@@ -800,17 +815,9 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       TC_PROF(it, 13);
       named_sync(NB_C, kNbC);  // dq / dk / dv staged, dC_{k-1} written
       TC_PROF(it, 14);
-      if (lane == 0) {
-        tma_store_4d(&mapdQ, sdQ, 0, t0, hh, b);
-        tma_store_4d(&mapdV, sdV, 0, t0, hh, b);
-        tma_store_4d(&mapdK, sdK, 0, t0, hh, b);
-        tma_store_commit();
-      }
-      __syncwarp();
       if (c > 0 && elect_one()) issue_s(par ^ 1);  // S / dSb of the next tile (their TMEM columns were read by this epilogue)
       __syncwarp();
     }
-    if (lane == 0) tma_store_wait_all<0>();
   } else if (warp == kScanWarp) {
     // =========================== scan warp: tile vectors two tiles ahead + dI / dF ==================
     // raw per-tile vectors (gate inputs, saved m / n) are loaded one tile before they are scanned
@@ -903,7 +910,8 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       const uint32_t par = it & 1;
       const float* gb = fsm + SM::fGates + pb * GateBuf::kFloats;
       float* spart = fsm + SM::fPart + pb * 6 * LT;
-      const int n_valid = min(LT, p.S - (p.NT - 1 - it) * LT);
+      const int t0 = (p.NT - 1 - it) * LT;
+      const int n_valid = min(LT, p.S - t0);
       const bool valid = row < n_valid;
 
       TC_PROF(it, 0);
@@ -1021,6 +1029,9 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
           dot += qv.x * o[2 * j] + qv.y * o[2 * j + 1];
         }
         store_row32<T>(sdQ, row, ch * 32, o);
+        named_sync(4 + rb, 64);  // the two warps of this row block have staged their halves
+        copy_out_rows16<T>(sdQ, (T*)p.dq + b * p.dq_sb + hh * p.dq_sh + (int64_t)t0 * p.dq_ss, p.dq_ss, rb * 32 + ch * 16,
+                           n_valid, lane);
         spart[(0 * 2 + ch) * LT + row] = dot;
         // dv
         mbar_wait(&bar_v, par, 17);
@@ -1037,6 +1048,9 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
           dot += vv.x * o[2 * j] + vv.y * o[2 * j + 1];
         }
         store_row32<T>(sdV, row, ch * 32, o);
+        named_sync(4 + rb, 64);
+        copy_out_rows16<T>(sdV, (T*)p.dv + b * p.dv_sb + hh * p.dv_sh + (int64_t)t0 * p.dv_ss, p.dv_ss, rb * 32 + ch * 16,
+                           n_valid, lane);
         spart[(2 * 2 + ch) * LT + row] = dot;
         // dk
         mbar_wait(&bar_k, par, 18);
@@ -1054,6 +1068,9 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
           dot += kv.x * o[2 * j] + kv.y * o[2 * j + 1];
         }
         store_row32<T>(sdK, row, ch * 32, o);
+        named_sync(4 + rb, 64);
+        copy_out_rows16<T>(sdK, (T*)p.dk + b * p.dk_sb + hh * p.dk_sh + (int64_t)t0 * p.dk_ss, p.dk_ss, rb * 32 + ch * 16,
+                           n_valid, lane);
         spart[(1 * 2 + ch) * LT + row] = dot;
       }
       // ---- dC_{k-1} = gbar dC_k + ddC ----------------------------------------------------------------
@@ -1214,10 +1231,9 @@ int tensor_bw(const mlstm_b200_bw_args& a, cudaStream_t st) {
     if (int e = run_fw(f, ws + w.off_states, st)) return e;
     c_states = ws + w.off_states;
   }
-  CUtensorMap mq, mk, mv, mdh, mcs, mdq, mdk, mdv;
+  CUtensorMap mq, mk, mv, mdh, mcs;
   int r = make_map(&mq, a.q, s, 64) | make_map(&mk, a.k, s, 64) | make_map(&mv, a.v, s, 64) | make_map(&mdh, a.dh, s, 64) |
-          make_states_map(&mcs, c_states, s) | make_map(&mdq, a.dq, s, 64) | make_map(&mdk, a.dk, s, 64) |
-          make_map(&mdv, a.dv, s, 64);
+          make_states_map(&mcs, c_states, s);
   if (r) {
     set_error("cuTensorMapEncodeTiled failed (%d)", r);
     return MLSTM_B200_ENODEVICE;
@@ -1232,16 +1248,19 @@ int tensor_bw(const mlstm_b200_bw_args& a, cudaStream_t st) {
   p.n_out = a.n_out; p.m_out = a.m_out; p.dc_last = a.dc_last;
   p.di = a.di.ptr; p.di_sb = a.di.stride[0]; p.di_sh = a.di.stride[1]; p.di_ss = a.di.stride[2];
   p.df = a.df.ptr; p.df_sb = a.df.stride[0]; p.df_sh = a.df.stride[1]; p.df_ss = a.df.stride[2];
+  p.dq = a.dq.ptr; p.dq_sb = a.dq.stride[0]; p.dq_sh = a.dq.stride[1]; p.dq_ss = a.dq.stride[2];
+  p.dk = a.dk.ptr; p.dk_sb = a.dk.stride[0]; p.dk_sh = a.dk.stride[1]; p.dk_ss = a.dk.stride[2];
+  p.dv = a.dv.ptr; p.dv_sb = a.dv.stride[0]; p.dv_sh = a.dv.stride[1]; p.dv_ss = a.dv.stride[2];
   p.dc0 = a.dc_initial;
   p.prof = g_prof ? g_prof + 4096 : nullptr;
   if (s.dtype == MLSTM_B200_BF16) {
     auto kern = tc_bw_d64<__nv_bfloat16>;
     MLSTM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwSmem::kBytes));
-    kern<<<s.B * s.NH, kTcThreads, BwSmem::kBytes, st>>>(mq, mk, mv, mdh, mcs, mdq, mdk, mdv, p);
+    kern<<<s.B * s.NH, kTcThreads, BwSmem::kBytes, st>>>(mq, mk, mv, mdh, mcs, p);
   } else {
     auto kern = tc_bw_d64<__half>;
     MLSTM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwSmem::kBytes));
-    kern<<<s.B * s.NH, kTcThreads, BwSmem::kBytes, st>>>(mq, mk, mv, mdh, mcs, mdq, mdk, mdv, p);
+    kern<<<s.B * s.NH, kTcThreads, BwSmem::kBytes, st>>>(mq, mk, mv, mdh, mcs, p);
   }
   count_launch();
   MLSTM_CUDA_CHECK(cudaGetLastError());
