@@ -1,6 +1,8 @@
 """Debug: per-tile phase clocks of CTA 0 for the tensor-core kernels (config 2 shape)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+os.environ["MLSTM_B200_LIB"] = os.path.join(ROOT, "xlstm_yolo_clean_b200", "lib", "libmlstm_b200_prof.so")  # built by `python __graft_entry__.py --profile`
 import torch
 import xlstm_yolo_clean_b200 as pkg
 from xlstm_yolo_clean_b200 import _cabi
