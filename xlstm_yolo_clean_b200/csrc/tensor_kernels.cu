@@ -30,11 +30,9 @@ namespace {
 using namespace sm100;
 
 constexpr int LT = 128;           // tokens per tile
-constexpr int kWorkerWarps = 16;  // warp w: TMEM lane quadrant / row block w%4, column quarter w/4
-constexpr int kWorkers = kWorkerWarps * 32;
-constexpr int kTcThreads = kWorkers + 64;  // + control warp (TMA / MMA issue) + scan warp (gate vectors, dF scan)
-constexpr int kCtlWarp = kWorkerWarps, kScanWarp = kWorkerWarps + 1;
-constexpr int CW = 16;            // columns of Q/K/V/H-shaped tiles owned by one worker thread
+constexpr int kWorkers = 256;     // 8 worker warps
+constexpr int kTcThreads = 320;   // + control warp (TMA / MMA issue) + scan warp (gate vectors, dF scan)
+constexpr int kCtlWarp = 8, kScanWarp = 9;
 constexpr int kNbAB = kWorkers + 32;  // workers + control
 constexpr int kNbC = kWorkers + 64;   // workers + control + scan
 constexpr float kLog2e = 1.4426950408889634f;
@@ -91,75 +89,6 @@ __device__ __forceinline__ void store_row32(uint8_t* base, int row, int col0, co
     u.z = pack2<T>(v[8 * j + 4], v[8 * j + 5]);
     u.w = pack2<T>(v[8 * j + 6], v[8 * j + 7]);
     *reinterpret_cast<uint4*>(tile + swz128(row, c + 8 * j)) = u;
-  }
-}
-
-// 16 consecutive columns (col0 multiple of 16): two 16-byte chunks
-template <typename T>
-__device__ __forceinline__ void store_row16(uint8_t* base, int row, int col0, const float (&v)[16]) {
-  uint8_t* tile = base + (col0 >> 6) * (LT * 128);
-  const int c = col0 & 63;
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    uint4 u;
-    u.x = pack2<T>(v[8 * j + 0], v[8 * j + 1]);
-    u.y = pack2<T>(v[8 * j + 2], v[8 * j + 3]);
-    u.z = pack2<T>(v[8 * j + 4], v[8 * j + 5]);
-    u.w = pack2<T>(v[8 * j + 6], v[8 * j + 7]);
-    *reinterpret_cast<uint4*>(tile + swz128(row, c + 8 * j)) = u;
-  }
-}
-
-// the same 32 columns written straight to global memory (row pointer `dst` = &out[row][col0])
-template <typename T>
-__device__ __forceinline__ void store_row32_global(T* dst, const float (&v)[32]) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    uint4 u;
-    u.x = pack2<T>(v[8 * j + 0], v[8 * j + 1]);
-    u.y = pack2<T>(v[8 * j + 2], v[8 * j + 3]);
-    u.z = pack2<T>(v[8 * j + 4], v[8 * j + 5]);
-    u.w = pack2<T>(v[8 * j + 6], v[8 * j + 7]);
-    reinterpret_cast<uint4*>(dst)[j] = u;
-  }
-}
-
-// Coalesced copy-out of 16 rows (row0 .. row0+15) of a swizzled [128][64] staging tile: every
-// instruction moves four complete 128-byte rows (lane -> row lane/8, 16-byte chunk lane%8).
-template <typename T>
-__device__ __forceinline__ void copy_out_rows16(const uint8_t* stage, T* gbase, int64_t gstride, int row0, int n_valid,
-                                                int lane) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = row0 + 4 * i + (lane >> 3), c = (lane & 7) * 8;
-    const uint4 u = *reinterpret_cast<const uint4*>(stage + swz128(r, c));
-    if (r < n_valid) *reinterpret_cast<uint4*>(gbase + (int64_t)r * gstride + c) = u;
-  }
-}
-
-// 16-column variant: lanes L and L^16 both end up with sum_rows v[.][L & 15] (15 + 1 shuffles).
-__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
-#pragma unroll
-  for (int off = 8; off >= 1; off >>= 1) {
-    const bool hi = (lane & off) != 0;
-#pragma unroll
-    for (int j = 0; j < off; ++j) {
-      const float keep = hi ? v[j + off] : v[j];
-      const float send = hi ? v[j] : v[j + off];
-      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
-}
-// Coalesced copy-out of 8 rows (row0 .. row0+7) of a swizzled [128][64] staging tile.
-template <typename T>
-__device__ __forceinline__ void copy_out_rows8(const uint8_t* stage, T* gbase, int64_t gstride, int row0, int n_valid,
-                                               int lane) {
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int r = row0 + 4 * i + (lane >> 3), c = (lane & 7) * 8;
-    const uint4 u = *reinterpret_cast<const uint4*>(stage + swz128(r, c));
-    if (r < n_valid) *reinterpret_cast<uint4*>(gbase + (int64_t)r * gstride + c) = u;
   }
 }
 
@@ -287,8 +216,8 @@ struct FwSmem {
   static constexpr int oH = NSTAGE == 2 ? oP + 2 * kTile : oP;  // h staging (aliases P half 0 when smem is tight)
   static constexpr int oC = oH + (NSTAGE == 2 ? kTile : 2 * kTile);  // bf16 copy of C (64 x 64), MMA B operand
   static constexpr int oSmall = oC + D * 128;
-  // floats: gates[2], srs[2][4][LT], sqn[2][4][LT], npart[2][4][D], sN[2][D]
-  static constexpr int fGates = 0, fRs = 2 * GateBuf::kFloats, fQn = fRs + 8 * LT, fNp = fQn + 8 * LT,
+  // floats: gates[2], srs[2][2][LT], sqn[2][2][LT], npart[2][4][D], sN[2][D]
+  static constexpr int fGates = 0, fRs = 2 * GateBuf::kFloats, fQn = fRs + 4 * LT, fNp = fQn + 4 * LT,
                        fN = fNp + 8 * D, kSmallFloats = fN + 2 * D;
   static constexpr int kBytes = oSmall + kSmallFloats * 4 + 1024 /*alignment slack*/;
   static constexpr int kTmemCols = NSTAGE == 2 ? 512 : 256;
@@ -334,22 +263,21 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
   }
   // worker-side state: fp32 master copy of C in the registers of lanes < 16 of every worker warp:
   // row d = 16*rb + lane (M=64 TMEM layout), columns 32*ch .. 32*ch+31
-  const int rb = warp & 3, cq = (warp >> 2) & 3;
+  const int rb = warp & 3, ch = (warp >> 2) & 1;
   const int row = rb * 32 + lane;  // tile row == TMEM lane of this thread
-  const int col0 = cq * CW;        // this thread's 16-column slice of Q/K/V/H-shaped tiles
   const uint32_t lane_base = (uint32_t)(rb * 32) << 16;
   const int drow = rb * 16 + (lane & 15);
   const bool owns_c = warp < kCtlWarp && lane < 16;
-  float Creg[CW];
+  float Creg[32];
 #pragma unroll
-  for (int j = 0; j < CW; ++j) Creg[j] = 0.f;
+  for (int j = 0; j < 32; ++j) Creg[j] = 0.f;
   if (warp < kCtlWarp) {
     if (p.c0 && owns_c) {
-      const float* src = p.c0 + ((int64_t)bh * D + drow) * D + col0;
+      const float* src = p.c0 + ((int64_t)bh * D + drow) * D + ch * 32;
 #pragma unroll
-      for (int j = 0; j < CW; ++j) Creg[j] = src[j];
+      for (int j = 0; j < 32; ++j) Creg[j] = src[j];
     }
-    if (owns_c) store_row16<T>(sC, drow, col0, Creg);
+    if (owns_c) store_row32<T>(sC, drow, ch * 32, Creg);
     if (tid < D) fsm[SM::fN + tid] = p.n0 ? p.n0[(int64_t)bh * D + tid] : 0.f;
     fence_proxy_async_smem();
   }
@@ -486,8 +414,8 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       const uint8_t* sQ = smem + SM::oQ + s * SM::kTile;
       const uint8_t* sK = smem + SM::oK + s * SM::kTile;
       const float* gb = fsm + SM::fGates + pb * GateBuf::kFloats;
-      float* srs = fsm + SM::fRs + pb * 4 * LT;
-      float* sqn = fsm + SM::fQn + pb * 4 * LT;
+      float* srs = fsm + SM::fRs + pb * 2 * LT;
+      float* sqn = fsm + SM::fQn + pb * 2 * LT;
       float* snp = fsm + SM::fNp + pb * 4 * D;
       const float* sNc = fsm + SM::fN + cur * D;
       float* sNn = fsm + SM::fN + (cur ^ 1) * D;
@@ -504,120 +432,123 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       const float m_t = b_t + fmaxf(m_run, gb[GateBuf::oPm + row]);     // fw.py:178-184
       mbar_wait(&bar_full[s], par_full, 3);
       if (c > 0) mbar_wait(&bar_n, (c - 1) & 1, 4);  // n_{k-1} finalised
-      // ---- partial q . n_{k-1} over this thread's 16 columns ---------------------------------------
+      // ---- partial q . n_{k-1} over this thread's 32 columns ---------------------------------------
       {
         float qn = 0.f;
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          uint4 q = *reinterpret_cast<const uint4*>(sQ + swz128(row, col0 + 8 * j));
+        for (int j = 0; j < 4; ++j) {
+          uint4 q = *reinterpret_cast<const uint4*>(sQ + swz128(row, ch * 32 + 8 * j));
           float2 q0 = unpack2<T>(q.x), q1 = unpack2<T>(q.y), q2 = unpack2<T>(q.z), q3 = unpack2<T>(q.w);
-          const float4 n0 = *reinterpret_cast<const float4*>(sNc + col0 + 8 * j);
-          const float4 n1 = *reinterpret_cast<const float4*>(sNc + col0 + 8 * j + 4);
+          const float4 n0 = *reinterpret_cast<const float4*>(sNc + ch * 32 + 8 * j);
+          const float4 n1 = *reinterpret_cast<const float4*>(sNc + ch * 32 + 8 * j + 4);
           qn += q0.x * n0.x + q0.y * n0.y + q1.x * n0.z + q1.y * n0.w + q2.x * n1.x + q2.y * n1.y + q3.x * n1.z + q3.y * n1.w;
         }
-        sqn[cq * LT + row] = qn;
+        sqn[ch * LT + row] = qn;
       }
       TC_PROF(c, 1);
-      // ---- P = S . D (causal), row sums: this thread owns the 32-column unit u = cq of its row -----
+      // ---- P = S . D (causal), row sums ----------------------------------------------------------
       mbar_wait(&bar_s, par, 5);
       tc_fence_after_sync();
       TC_PROF(c, 2);
       {
         const float x_t = (b_t - m_t) * kLog2e + log2f(p.scale);
-        const int u = cq;
+        const float* sy = gb + GateBuf::oY;
+        const float* scf = gb + GateBuf::oCf;
         float rs = 0.f;
-        float v[32];
-        if (u < rb) {  // block strictly below the diagonal: rank-1 decay, one exp per row
-          tmem_ld32(tS + lane_base + u * 32, v);
-          const float r_t = ex2_approx(x_t + gb[GateBuf::oScal + 4 + u]);
-          const float* scf = gb + GateBuf::oCf + u * 32;
+#pragma unroll 1
+        for (int u = ch; u < 4; u += 2) {  // this thread's two 32-column units (warp-uniform branches)
+          float v[32];
+          if (u < rb) {  // block strictly below the diagonal: rank-1 decay, one exp per row
+            tmem_ld32(tS + lane_base + u * 32, v);
+            const float r_t = ex2_approx(x_t + gb[GateBuf::oScal + 4 + u]);
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 cf = *reinterpret_cast<const float4*>(scf + 4 * j4);
-            v[4 * j4 + 0] *= cf.x * r_t;
-            v[4 * j4 + 1] *= cf.y * r_t;
-            v[4 * j4 + 2] *= cf.z * r_t;
-            v[4 * j4 + 3] *= cf.w * r_t;
-            rs += (v[4 * j4 + 0] + v[4 * j4 + 1]) + (v[4 * j4 + 2] + v[4 * j4 + 3]);
-          }
-        } else if (u == rb) {  // diagonal block: causal mask, one exp per entry
-          tmem_ld32(tS + lane_base + u * 32, v);
-          const float* sy = gb + GateBuf::oY + u * 32;
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 y = *reinterpret_cast<const float4*>(sy + 4 * j4);
-            const float yy[4] = {y.x, y.y, y.z, y.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = 4 * j4 + e;
-              float pv = v[j] * ex2_approx(x_t + yy[e]);
-              pv = j <= lane ? pv : 0.f;
-              rs += pv;
-              v[j] = pv;
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 cf = *reinterpret_cast<const float4*>(scf + u * 32 + 4 * j4);
+              v[4 * j4 + 0] *= cf.x * r_t;
+              v[4 * j4 + 1] *= cf.y * r_t;
+              v[4 * j4 + 2] *= cf.z * r_t;
+              v[4 * j4 + 3] *= cf.w * r_t;
+              rs += (v[4 * j4 + 0] + v[4 * j4 + 1]) + (v[4 * j4 + 2] + v[4 * j4 + 3]);
             }
-          }
-        } else {
+          } else if (u == rb) {  // diagonal block: causal mask, one exp per entry
+            tmem_ld32(tS + lane_base + u * 32, v);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 y = *reinterpret_cast<const float4*>(sy + u * 32 + 4 * j4);
+              const float yy[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = 4 * j4 + e;
+                float pv = v[j] * ex2_approx(x_t + yy[e]);
+                pv = j <= lane ? pv : 0.f;
+                rs += pv;
+                v[j] = pv;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+          store_row32<T>(sP, row, u * 32, v);
         }
-        store_row32<T>(sP, row, u * 32, v);
-        srs[cq * LT + row] = rs;
+        srs[ch * LT + row] = rs;
       }
+      TC_PROF(c, 3);
       fence_proxy_async_smem();
+      TC_PROF(c, 4);
       tc_fence_before_sync();
       named_arrive(NB_B, kNbAB);
-      TC_PROF(c, 3);
-      // ---- Kbar = abar . K (row, 16 columns); column sums for n (overlaps the H MMAs) -----------------
+      TC_PROF(c, 5);
+      // ---- Kbar = abar . K (this thread: row, 32 columns); column sums for n (overlaps the H MMAs) --
       {
         const float ab = __expf(g - b_t + i_t - m_next);  // fw.py:102 (exp(-inf) = 0 for tail tokens)
-        float kb[CW];
+        float kb[32];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          uint4 u = *reinterpret_cast<const uint4*>(sK + swz128(row, col0 + 8 * j));
+        for (int j = 0; j < 4; ++j) {
+          uint4 u = *reinterpret_cast<const uint4*>(sK + swz128(row, ch * 32 + 8 * j));
           float2 a0 = unpack2<T>(u.x), a1 = unpack2<T>(u.y), a2 = unpack2<T>(u.z), a3 = unpack2<T>(u.w);
           kb[8 * j + 0] = a0.x * ab; kb[8 * j + 1] = a0.y * ab; kb[8 * j + 2] = a1.x * ab; kb[8 * j + 3] = a1.y * ab;
           kb[8 * j + 4] = a2.x * ab; kb[8 * j + 5] = a2.y * ab; kb[8 * j + 6] = a3.x * ab; kb[8 * j + 7] = a3.y * ab;
         }
-        store_row16<T>(sKb, row, col0, kb);
-        const float cs = warp_colsum16(kb, lane);  // sum over this warp's 32 rows of column col0 + (lane & 15)
-        if (lane < 16) snp[rb * D + col0 + lane] = cs;
+        store_row32<T>(sKb, row, ch * 32, kb);
+        const float cs = warp_colsum32(kb, lane);  // sum over this warp's 32 rows of column ch*32 + lane
+        snp[rb * D + ch * 32 + lane] = cs;
         fence_proxy_async_smem();
         named_arrive(NB_A, kNbAB);
       }
-      TC_PROF(c, 4);
+      TC_PROF(c, 6);
       // ---- epilogue -----------------------------------------------------------------------------------
       mbar_wait(&bar_h, par, 7);
       tc_fence_after_sync();
-      TC_PROF(c, 5);
+      TC_PROF(c, 7);
       {
-        float hi[CW], hx[CW];
-        tmem_ld16(tHi + lane_base + col0, hi);
-        tmem_ld16(tHx + lane_base + col0, hx);
-        const float bq = __expf(b_t + m_run - m_t) * p.scale;  // fw.py:197-198
-        const float den = bq * ((sqn[row] + sqn[LT + row]) + (sqn[2 * LT + row] + sqn[3 * LT + row])) +
-                          ((srs[row] + srs[LT + row]) + (srs[2 * LT + row] + srs[3 * LT + row]));  // fw.py:204-206
-        const float nmax = fmaxf(fabsf(den), __expf(-m_t));                                         // fw.py:208-210
+        uint32_t hi[32], hx[32];
+        tmem_ld32_nowait(tHi + lane_base + ch * 32, hi);
+        tmem_ld32_nowait(tHx + lane_base + ch * 32, hx);
+        const float bq = __expf(b_t + m_run - m_t) * p.scale;                          // fw.py:197-198
+        const float den = bq * (sqn[row] + sqn[LT + row]) + srs[row] + srs[LT + row];  // fw.py:204-206
+        const float nmax = fmaxf(fabsf(den), __expf(-m_t));                            // fw.py:208-210
         const float inv = 1.f / (nmax + p.eps);
+        tmem_ld_wait();
+        float o[32];
 #pragma unroll
-        for (int j = 0; j < CW; ++j) hi[j] = (hi[j] + bq * hx[j]) * inv;  // fw.py:200-212
-        store_row16<T>(sH, row, col0, hi);
-        if (cq == 0 && row < n_valid) {
+        for (int j = 0; j < 32; ++j) o[j] = (__uint_as_float(hi[j]) + bq * __uint_as_float(hx[j])) * inv;  // fw.py:200-212
+        store_row32<T>(sH, row, ch * 32, o);
+        if (ch == 0 && row < n_valid) {
           p.n_out[(int64_t)bh * p.S + t0 + row] = nmax;
           p.m_out[(int64_t)bh * p.S + t0 + row] = m_t;
         }
       }
-      TC_PROF(c, 6);
       // ---- state update C_k = gbar C_{k-1} + dC; n_k ---------------------------------------------------
       mbar_wait(&bar_dc, par, 6);
       tc_fence_after_sync();
-      TC_PROF(c, 7);
       {
-        float v[CW];
-        tmem_ld16(tDC + lane_base + col0, v);  // M=64 layout: lanes 0-15 of each quadrant hold rows
+        float v[32];
+        tmem_ld32(tDC + lane_base + ch * 32, v);  // M=64 layout: lanes 0-15 of each quadrant hold rows
         if (owns_c) {
 #pragma unroll
-          for (int j = 0; j < CW; ++j) Creg[j] = gbar * Creg[j] + v[j];
-          store_row16<T>(sC, drow, col0, Creg);  // Q C_{k-1} (bar_h) has finished reading the old copy
+          for (int j = 0; j < 32; ++j) Creg[j] = gbar * Creg[j] + v[j];
+          store_row32<T>(sC, drow, ch * 32, Creg);  // Q C_{k-1} (bar_h) has finished reading the old copy
         }
         if (tid < D) {  // n_k = gbar n_{k-1} + column sums of Kbar (fw.py:116)
           sNn[tid] = gbar * sNc[tid] + ((snp[tid] + snp[D + tid]) + (snp[2 * D + tid] + snp[3 * D + tid]));
@@ -634,9 +565,9 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
     // final states (fw.py:302-309)
     if (p.c_last) {
       if (owns_c) {
-        float* dst = p.c_last + ((int64_t)bh * D + drow) * D + col0;
+        float* dst = p.c_last + ((int64_t)bh * D + drow) * D + ch * 32;
 #pragma unroll
-        for (int j = 0; j < CW; ++j) dst[j] = Creg[j];
+        for (int j = 0; j < 32; ++j) dst[j] = Creg[j];
       }
       if (tid < D) p.n_last[(int64_t)bh * D + tid] = fsm[SM::fN + cur * D + tid];  // own write (tid < D finalises n)
       if (tid == 0) p.m_last[bh] = m_run;
@@ -669,8 +600,6 @@ struct TcBwParams {
   const float *n_out, *m_out, *dc_last;
   void *di, *df;
   int64_t di_sb, di_sh, di_ss, df_sb, df_sh, df_ss;
-  void *dq, *dk, *dv;  // written straight from registers (64 contiguous bytes per thread and row)
-  int64_t dq_sb, dq_sh, dq_ss, dk_sb, dk_sh, dk_ss, dv_sb, dv_sh, dv_ss;
   float* dc0;
   long long* prof;
 };
@@ -682,12 +611,14 @@ struct BwSmem {
   static constexpr int oQt = 4 * kTile;       // wq . Q
   static constexpr int oSb = 5 * kTile;       // Sb' two halves
   static constexpr int odS = 7 * kTile;       // dS  two halves
-  static constexpr int oStg = 9 * kTile;      // staging tile of the coalesced dq / dv / dk copy-out
-  static constexpr int oCs = 10 * kTile;      // C_{k-1}, 64 x 64 bf16 (TMA)
+  static constexpr int odQ = 9 * kTile;       // dq / dv / dk staging (their stores overlap the next tile's W phase)
+  static constexpr int odV = 10 * kTile;
+  static constexpr int odK = 11 * kTile;
+  static constexpr int oCs = 12 * kTile;      // C_{k-1}, 64 x 64 bf16 (TMA)
   static constexpr int odC = oCs + 64 * 128;  // dC_k bf16 operand copy
   static constexpr int oSmall = odC + 64 * 128;
-  // floats: gates[2], spart[2][3][4][LT] (q.dq, k.dk, v.dv partials per column quarter)
-  static constexpr int fGates = 0, fPart = 2 * GateBuf::kFloats, kSmallFloats = fPart + 24 * LT;
+  // floats: gates[2], spart[2][6][LT]
+  static constexpr int fGates = 0, fPart = 2 * GateBuf::kFloats, kSmallFloats = fPart + 12 * LT;
   static constexpr int kBytes = oSmall + kSmallFloats * 4 + 1024;
   static constexpr uint32_t kLoadBytes = 4 * kTile + 64 * 128;
 };
@@ -696,7 +627,8 @@ template <typename T>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
           const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdH,
-          const __grid_constant__ CUtensorMap mapCs, TcBwParams p) {
+          const __grid_constant__ CUtensorMap mapCs, const __grid_constant__ CUtensorMap mapdQ,
+          const __grid_constant__ CUtensorMap mapdK, const __grid_constant__ CUtensorMap mapdV, TcBwParams p) {
   constexpr int D = 64;
   constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
   using SM = BwSmem;
@@ -709,7 +641,9 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
   uint8_t* sQt = smem + SM::oQt;
   uint8_t* sSb = smem + SM::oSb;
   uint8_t* sdS = smem + SM::odS;
-  uint8_t* sStg = smem + SM::oStg;
+  uint8_t* sdQ = smem + SM::odQ;
+  uint8_t* sdV = smem + SM::odV;
+  uint8_t* sdK = smem + SM::odK;
   uint8_t* sCs = smem + SM::oCs;
   uint8_t* sdC = smem + SM::odC;
   float* fsm = (float*)(smem + SM::oSmall);
@@ -735,25 +669,24 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
     tmem_alloc<512>(&tmem_base_s);
     if (lane == 0) {
       prefetch_tmap(&mapQ); prefetch_tmap(&mapK); prefetch_tmap(&mapV); prefetch_tmap(&mapdH);
-      prefetch_tmap(&mapCs);
+      prefetch_tmap(&mapCs); prefetch_tmap(&mapdQ); prefetch_tmap(&mapdK); prefetch_tmap(&mapdV);
     }
   }
-  const int rb = warp & 3, cq = (warp >> 2) & 3;
+  const int rb = warp & 3, ch = (warp >> 2) & 1;
   const int row = rb * 32 + lane;
-  const int col0 = cq * CW;
   const uint32_t lane_base = (uint32_t)(rb * 32) << 16;
   const int drow = rb * 16 + (lane & 15);
   const bool owns_c = warp < kCtlWarp && lane < 16;
-  float dCreg[CW];
+  float dCreg[32];
 #pragma unroll
-  for (int j = 0; j < CW; ++j) dCreg[j] = 0.f;
+  for (int j = 0; j < 32; ++j) dCreg[j] = 0.f;
   if (warp < kCtlWarp) {
     if (p.dc_last && owns_c) {
-      const float* src = p.dc_last + ((int64_t)bh * D + drow) * D + col0;
+      const float* src = p.dc_last + ((int64_t)bh * D + drow) * D + ch * 32;
 #pragma unroll
-      for (int j = 0; j < CW; ++j) dCreg[j] = src[j];
+      for (int j = 0; j < 32; ++j) dCreg[j] = src[j];
     }
-    if (owns_c) store_row16<T>(sdC, drow, col0, dCreg);
+    if (owns_c) store_row32<T>(sdC, drow, ch * 32, dCreg);
     fence_proxy_async_smem();
   }
   tc_fence_before_sync();
@@ -817,6 +750,8 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       TC_PROF(it, 9);
       named_sync(NB_B, kNbAB);  // Sb', dS written
       TC_PROF(it, 10);
+      if (lane == 0) tma_store_wait_read<0>();  // the previous tile's dq / dk / dv stores have left their staging buffers
+      __syncwarp();
       if (elect_one()) {
         tc_fence_after_sync();
 #pragma unroll
@@ -858,9 +793,17 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       TC_PROF(it, 13);
       named_sync(NB_C, kNbC);  // dq / dk / dv staged, dC_{k-1} written
       TC_PROF(it, 14);
+      if (lane == 0) {
+        tma_store_4d(&mapdQ, sdQ, 0, t0, hh, b);
+        tma_store_4d(&mapdV, sdV, 0, t0, hh, b);
+        tma_store_4d(&mapdK, sdK, 0, t0, hh, b);
+        tma_store_commit();
+      }
+      __syncwarp();
       if (c > 0 && elect_one()) issue_s(par ^ 1);  // S / dSb of the next tile (their TMEM columns were read by this epilogue)
       __syncwarp();
     }
+    if (lane == 0) tma_store_wait_all<0>();
   } else if (warp == kScanWarp) {
     // =========================== scan warp: tile vectors two tiles ahead + dI / dF ==================
     // raw per-tile vectors (gate inputs, saved m / n) are loaded one tile before they are scanned
@@ -905,16 +848,14 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       named_sync(NB_C, kNbC);  // row dots of tile `it` are in shared memory; its buffers can be reused afterwards
       // ---- gate gradients: reverse (suffix) scan over the tile, carried across tiles -------------
       {
-        const float* sp = fsm + SM::fPart + pb * 12 * LT;
+        const float* sp = fsm + SM::fPart + pb * 6 * LT;
         const float* gb = fsm + SM::fGates + pb * GateBuf::kFloats;
         float acc[4], di[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int t = lane * 4 + e;
-          const float qdq = (sp[0 * LT + t] + sp[1 * LT + t]) + (sp[2 * LT + t] + sp[3 * LT + t]);
-          const float kdk = (sp[4 * LT + t] + sp[5 * LT + t]) + (sp[6 * LT + t] + sp[7 * LT + t]);
-          acc[e] = qdq - kdk;                                                                    // bw.py:321
-          di[e] = (sp[8 * LT + t] + sp[9 * LT + t]) + (sp[10 * LT + t] + sp[11 * LT + t]);       // bw.py:326
+          acc[e] = (sp[0 * LT + t] + sp[1 * LT + t]) - (sp[2 * LT + t] + sp[3 * LT + t]);  // bw.py:321
+          di[e] = sp[4 * LT + t] + sp[5 * LT + t];                                         // bw.py:326
         }
         acc[2] += acc[3];
         acc[1] += acc[2];
@@ -954,9 +895,8 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       const int pb = it & 1;
       const uint32_t par = it & 1;
       const float* gb = fsm + SM::fGates + pb * GateBuf::kFloats;
-      float* spart = fsm + SM::fPart + pb * 12 * LT;
-      const int t0 = (p.NT - 1 - it) * LT;
-      const int n_valid = min(LT, p.S - t0);
+      float* spart = fsm + SM::fPart + pb * 6 * LT;
+      const int n_valid = min(LT, p.S - (p.NT - 1 - it) * LT);
       const bool valid = row < n_valid;
 
       TC_PROF(it, 0);
@@ -969,59 +909,58 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       const float abar = __expf(g - b_t + i_t - m_next);            // bw.py:187 (0 for tail tokens)
       const float gbar = __expf(g + m_prev - m_next);               // bw.py:76
       TC_PROF(it, 1);
-      // ---- W = D / (n + eps); Sb' = S.scale.W, dS = dSb.W: this thread owns unit u = cq of its row ----
+      // ---- W = D / (n + eps); Sb' = S.scale.W, dS = dSb.W ------------------------------------------
       mbar_wait(&bar_s, par, 14);
       tc_fence_after_sync();
       TC_PROF(it, 2);
       {
-        // the 1/(n+eps) factor rides in the exponent: W = 2^(x_t + y_s)
+        // the 1/(n+eps) and scale factors ride in the exponent: W = 2^(x_t + y_s)
         const float x_t = valid ? (b_t - m_t) * kLog2e + log2f(rinv) : -INFINITY;
-        const int u = cq;
-        if (u <= rb) {
-          const float r_t = ex2_approx(x_t + gb[GateBuf::oScal + 4 + u]);  // used by the rank-1 (u < rb) blocks
+        const float* sy = gb + GateBuf::oY;
+        const float* scf = gb + GateBuf::oCf;
 #pragma unroll 1
-          for (int hf = 0; hf < 2; ++hf) {  // two 16-column halves keep the register footprint small
-            const int cb = u * 32 + hf * 16;
-            float v[16], w[16];
-            tmem_ld16(tS + lane_base + cb, v);
-            tmem_ld16(tdSb + lane_base + cb, w);
+        for (int u = ch; u < 4; u += 2) {  // this thread's two 32-column units (warp-uniform branches)
+          float v[32], w[32];
+          if (u <= rb) {
+            uint32_t rv[32], rw[32];
+            tmem_ld32_nowait(tS + lane_base + u * 32, rv);
+            tmem_ld32_nowait(tdSb + lane_base + u * 32, rw);
+            tmem_ld_wait();
             if (u < rb) {  // block strictly below the diagonal: rank-1 decay, one exp per row
-              const float* scf = gb + GateBuf::oCf + cb;
+              const float r_t = ex2_approx(x_t + gb[GateBuf::oScal + 4 + u]);
+              const float r_s = r_t * p.scale;
 #pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 cf = *reinterpret_cast<const float4*>(scf + 4 * j4);
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 cf = *reinterpret_cast<const float4*>(scf + u * 32 + 4 * j4);
                 const float cc[4] = {cf.x, cf.y, cf.z, cf.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                  const float wg = cc[e] * r_t;
-                  v[4 * j4 + e] *= wg * p.scale;
-                  w[4 * j4 + e] *= wg;
+                  const int j = 4 * j4 + e;
+                  v[j] = __uint_as_float(rv[j]) * (cc[e] * r_s);
+                  w[j] = __uint_as_float(rw[j]) * (cc[e] * r_t);
                 }
               }
             } else {  // diagonal block: causal mask, one exp per entry
-              const float* sy = gb + GateBuf::oY + cb;
 #pragma unroll
-              for (int j4 = 0; j4 < 4; ++j4) {
-                const float4 y = *reinterpret_cast<const float4*>(sy + 4 * j4);
+              for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 y = *reinterpret_cast<const float4*>(sy + u * 32 + 4 * j4);
                 const float yy[4] = {y.x, y.y, y.z, y.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
+                  const int j = 4 * j4 + e;
                   float wg = ex2_approx(x_t + yy[e]);
-                  wg = (hf * 16 + 4 * j4 + e) <= lane ? wg : 0.f;
-                  v[4 * j4 + e] *= wg * p.scale;
-                  w[4 * j4 + e] *= wg;
+                  wg = j <= lane ? wg : 0.f;
+                  v[j] = __uint_as_float(rv[j]) * (wg * p.scale);
+                  w[j] = __uint_as_float(rw[j]) * wg;
                 }
               }
             }
-            store_row16<T>(sSb, row, cb, v);
-            store_row16<T>(sdS, row, cb, w);
-          }
-        } else {
-          float z[32];
+          } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) z[j] = 0.f;
-          store_row32<T>(sSb, row, u * 32, z);
-          store_row32<T>(sdS, row, u * 32, z);
+            for (int j = 0; j < 32; ++j) { v[j] = 0.f; w[j] = 0.f; }
+          }
+          store_row32<T>(sSb, row, u * 32, v);
+          store_row32<T>(sdS, row, u * 32, w);
         }
       }
       fence_proxy_async_smem();
@@ -1030,12 +969,12 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       TC_PROF(it, 3);
       // ---- Qt = wq . Q; keep this thread's q / k / v row slices for the gate gradients (overlaps MMAs)
       mbar_wait(&bar_full, par, 13);
-      uint32_t qs[8], ks[8], vs[8];
+      uint32_t qs[16], ks[16], vs[16];
       {
         const float wq = p.scale * bbar * rinv;  // bw.py:83-90
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const uint32_t off = swz128(row, col0 + 8 * j);
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t off = swz128(row, ch * 32 + 8 * j);
           uint4 u = *reinterpret_cast<const uint4*>(sQ + off);
           qs[4 * j] = u.x; qs[4 * j + 1] = u.y; qs[4 * j + 2] = u.z; qs[4 * j + 3] = u.w;
           float2 a0 = unpack2<T>(u.x), a1 = unpack2<T>(u.y), a2 = unpack2<T>(u.z), a3 = unpack2<T>(u.w);
@@ -1053,80 +992,74 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       fence_proxy_async_smem();
       named_arrive(NB_A, kNbAB);
       TC_PROF(it, 4);
-      // ---- epilogues, pipelined with the MMA batch through three commits.  Each output goes through one
-      //      shared staging tile: stage -> row-block barrier -> coalesced copy-out -> row-block barrier.
+      // ---- epilogues, pipelined with the MMA batch through three commits ------------------------------
       {
-        float a[CW], bq[CW];
+        uint32_t ra[32], rq[32];
+        float o[32];
         float dot;
-        const int row0 = rb * 32 + cq * 8;  // the 8 rows this warp copies out
         // dq
         mbar_wait(&bar_q, par, 16);
         tc_fence_after_sync();
         TC_PROF(it, 5);
-        tmem_ld16(tdQa + lane_base + col0, a);
-        tmem_ld16(tdQb + lane_base + col0, bq);
+        tmem_ld32_nowait(tdQa + lane_base + ch * 32, ra);
+        tmem_ld32_nowait(tdQb + lane_base + ch * 32, rq);
+        tmem_ld_wait();
         const float wb = bbar * rinv;
         dot = 0.f;
 #pragma unroll
-        for (int j = 0; j < CW / 2; ++j) {
-          a[2 * j] = p.scale * (a[2 * j] + wb * bq[2 * j]);  // bw.py:169,193
-          a[2 * j + 1] = p.scale * (a[2 * j + 1] + wb * bq[2 * j + 1]);
+        for (int j = 0; j < 16; ++j) {
+          o[2 * j] = p.scale * (__uint_as_float(ra[2 * j]) + wb * __uint_as_float(rq[2 * j]));  // bw.py:169,193
+          o[2 * j + 1] = p.scale * (__uint_as_float(ra[2 * j + 1]) + wb * __uint_as_float(rq[2 * j + 1]));
           float2 qv = unpack2<T>(qs[j]);
-          dot += qv.x * a[2 * j] + qv.y * a[2 * j + 1];
+          dot += qv.x * o[2 * j] + qv.y * o[2 * j + 1];
         }
-        store_row16<T>(sStg, row, col0, a);
-        spart[(0 * 4 + cq) * LT + row] = dot;
-        named_sync(4 + rb, 128);  // the four warps of this row block have staged their quarters
-        copy_out_rows8<T>(sStg, (T*)p.dq + b * p.dq_sb + hh * p.dq_sh + (int64_t)t0 * p.dq_ss, p.dq_ss, row0, n_valid, lane);
+        store_row32<T>(sdQ, row, ch * 32, o);
+        spart[(0 * 2 + ch) * LT + row] = dot;
         // dv
         mbar_wait(&bar_v, par, 17);
         tc_fence_after_sync();
-        tmem_ld16(tdV1 + lane_base + col0, a);
-        tmem_ld16(tdV2 + lane_base + col0, bq);
+        tmem_ld32_nowait(tdV1 + lane_base + ch * 32, ra);
+        tmem_ld32_nowait(tdV2 + lane_base + ch * 32, rq);
+        tmem_ld_wait();
         dot = 0.f;
 #pragma unroll
-        for (int j = 0; j < CW / 2; ++j) {
-          a[2 * j] = a[2 * j] + abar * bq[2 * j];  // bw.py:164,190
-          a[2 * j + 1] = a[2 * j + 1] + abar * bq[2 * j + 1];
+        for (int j = 0; j < 16; ++j) {
+          o[2 * j] = __uint_as_float(ra[2 * j]) + abar * __uint_as_float(rq[2 * j]);  // bw.py:164,190
+          o[2 * j + 1] = __uint_as_float(ra[2 * j + 1]) + abar * __uint_as_float(rq[2 * j + 1]);
           float2 vv = unpack2<T>(vs[j]);
-          dot += vv.x * a[2 * j] + vv.y * a[2 * j + 1];
+          dot += vv.x * o[2 * j] + vv.y * o[2 * j + 1];
         }
-        named_sync(4 + rb, 128);  // the dq copy-out has left the staging rows of this row block
-        store_row16<T>(sStg, row, col0, a);
-        spart[(2 * 4 + cq) * LT + row] = dot;
-        named_sync(4 + rb, 128);
-        copy_out_rows8<T>(sStg, (T*)p.dv + b * p.dv_sb + hh * p.dv_sh + (int64_t)t0 * p.dv_ss, p.dv_ss, row0, n_valid, lane);
+        store_row32<T>(sdV, row, ch * 32, o);
+        spart[(2 * 2 + ch) * LT + row] = dot;
         // dk
         mbar_wait(&bar_k, par, 18);
         tc_fence_after_sync();
         TC_PROF(it, 6);
-        tmem_ld16(tdK1 + lane_base + col0, a);
-        tmem_ld16(tdK2 + lane_base + col0, bq);
+        tmem_ld32_nowait(tdK1 + lane_base + ch * 32, ra);
+        tmem_ld32_nowait(tdK2 + lane_base + ch * 32, rq);
+        tmem_ld_wait();
         dot = 0.f;
 #pragma unroll
-        for (int j = 0; j < CW / 2; ++j) {
-          a[2 * j] = p.scale * a[2 * j] + abar * bq[2 * j];  // bw.py:170,192
-          a[2 * j + 1] = p.scale * a[2 * j + 1] + abar * bq[2 * j + 1];
+        for (int j = 0; j < 16; ++j) {
+          o[2 * j] = p.scale * __uint_as_float(ra[2 * j]) + abar * __uint_as_float(rq[2 * j]);  // bw.py:170,192
+          o[2 * j + 1] = p.scale * __uint_as_float(ra[2 * j + 1]) + abar * __uint_as_float(rq[2 * j + 1]);
           float2 kv = unpack2<T>(ks[j]);
-          dot += kv.x * a[2 * j] + kv.y * a[2 * j + 1];
+          dot += kv.x * o[2 * j] + kv.y * o[2 * j + 1];
         }
-        named_sync(4 + rb, 128);
-        store_row16<T>(sStg, row, col0, a);
-        spart[(1 * 4 + cq) * LT + row] = dot;
-        named_sync(4 + rb, 128);
-        copy_out_rows8<T>(sStg, (T*)p.dk + b * p.dk_sb + hh * p.dk_sh + (int64_t)t0 * p.dk_ss, p.dk_ss, row0, n_valid, lane);
+        store_row32<T>(sdK, row, ch * 32, o);
+        spart[(1 * 2 + ch) * LT + row] = dot;
       }
       // ---- dC_{k-1} = gbar dC_k + ddC ----------------------------------------------------------------
       mbar_wait(&bar_d, par, 15);
       tc_fence_after_sync();
       TC_PROF(it, 7);
       {
-        float v[CW];
-        tmem_ld16(tddC + lane_base + col0, v);
+        float v[32];
+        tmem_ld32(tddC + lane_base + ch * 32, v);
         if (owns_c) {
 #pragma unroll
-          for (int j = 0; j < CW; ++j) dCreg[j] = gbar * dCreg[j] + v[j];  // bw.py:93-95
-          store_row16<T>(sdC, drow, col0, dCreg);                          // dV2 / dK2 have completed (bar_k)
+          for (int j = 0; j < 32; ++j) dCreg[j] = gbar * dCreg[j] + v[j];  // bw.py:93-95
+          store_row32<T>(sdC, drow, ch * 32, dCreg);                       // dV2 / dK2 have completed (bar_k)
         }
       }
       fence_proxy_async_smem();
@@ -1135,9 +1068,9 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       TC_PROF(it, 8);
     }
     if (p.dc0 && owns_c) {  // dC_initial = dC_0 (bw.py:329-331)
-      float* dst = p.dc0 + ((int64_t)bh * D + drow) * D + col0;
+      float* dst = p.dc0 + ((int64_t)bh * D + drow) * D + ch * 32;
 #pragma unroll
-      for (int j = 0; j < CW; ++j) dst[j] = dCreg[j];
+      for (int j = 0; j < 32; ++j) dst[j] = dCreg[j];
     }
   }
   tc_fence_before_sync();
@@ -1274,9 +1207,10 @@ int tensor_bw(const mlstm_b200_bw_args& a, cudaStream_t st) {
     if (int e = run_fw(f, ws + w.off_states, st)) return e;
     c_states = ws + w.off_states;
   }
-  CUtensorMap mq, mk, mv, mdh, mcs;
+  CUtensorMap mq, mk, mv, mdh, mcs, mdq, mdk, mdv;
   int r = make_map(&mq, a.q, s, 64) | make_map(&mk, a.k, s, 64) | make_map(&mv, a.v, s, 64) | make_map(&mdh, a.dh, s, 64) |
-          make_states_map(&mcs, c_states, s);
+          make_states_map(&mcs, c_states, s) | make_map(&mdq, a.dq, s, 64) | make_map(&mdk, a.dk, s, 64) |
+          make_map(&mdv, a.dv, s, 64);
   if (r) {
     set_error("cuTensorMapEncodeTiled failed (%d)", r);
     return MLSTM_B200_ENODEVICE;
@@ -1291,19 +1225,16 @@ int tensor_bw(const mlstm_b200_bw_args& a, cudaStream_t st) {
   p.n_out = a.n_out; p.m_out = a.m_out; p.dc_last = a.dc_last;
   p.di = a.di.ptr; p.di_sb = a.di.stride[0]; p.di_sh = a.di.stride[1]; p.di_ss = a.di.stride[2];
   p.df = a.df.ptr; p.df_sb = a.df.stride[0]; p.df_sh = a.df.stride[1]; p.df_ss = a.df.stride[2];
-  p.dq = a.dq.ptr; p.dq_sb = a.dq.stride[0]; p.dq_sh = a.dq.stride[1]; p.dq_ss = a.dq.stride[2];
-  p.dk = a.dk.ptr; p.dk_sb = a.dk.stride[0]; p.dk_sh = a.dk.stride[1]; p.dk_ss = a.dk.stride[2];
-  p.dv = a.dv.ptr; p.dv_sb = a.dv.stride[0]; p.dv_sh = a.dv.stride[1]; p.dv_ss = a.dv.stride[2];
   p.dc0 = a.dc_initial;
   p.prof = g_prof ? g_prof + 4096 : nullptr;
   if (s.dtype == MLSTM_B200_BF16) {
     auto kern = tc_bw_d64<__nv_bfloat16>;
     MLSTM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwSmem::kBytes));
-    kern<<<s.B * s.NH, kTcThreads, BwSmem::kBytes, st>>>(mq, mk, mv, mdh, mcs, p);
+    kern<<<s.B * s.NH, kTcThreads, BwSmem::kBytes, st>>>(mq, mk, mv, mdh, mcs, mdq, mdk, mdv, p);
   } else {
     auto kern = tc_bw_d64<__half>;
     MLSTM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwSmem::kBytes));
-    kern<<<s.B * s.NH, kTcThreads, BwSmem::kBytes, st>>>(mq, mk, mv, mdh, mcs, p);
+    kern<<<s.B * s.NH, kTcThreads, BwSmem::kBytes, st>>>(mq, mk, mv, mdh, mcs, mdq, mdk, mdv, p);
   }
   count_launch();
   MLSTM_CUDA_CHECK(cudaGetLastError());
