@@ -264,12 +264,10 @@ def main():
     sync_all()
     clocks = sampler.stop() if rank == 0 else None
     launches = launches_per_step * args.steps
-    ms_total = e0.elapsed_time(e1)
-    t = torch.tensor([ms_total], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = t.item() / args.steps
-    value = world * (ff + fb) / (ms_step * 1e-3) / 1e12
+    from xlstm_yolo_clean_b200 import replicas
+
+    ms_step = replicas.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps  # slowest rank
+    value = replicas.sum_over_ranks(ff + fb, dev) / (ms_step * 1e-3) / 1e12    # all ranks' work over that time
 
     # ---- per-kernel timing for the roofline: CUDA events on the launching stream, one kernel per graph
     fw_ms, bw_ms = [], []
@@ -287,46 +285,40 @@ def main():
     fw_t, bw_t = statistics.median(fw_ms), statistics.median(bw_ms)
     hbm_peak, tf_peak, peak_kind = peaks()
     dom = ("bw", bw_bytes, bw_t, "tc_bw_d64") if bw_t >= fw_t else ("fw", fw_bytes, fw_t, "tc_fw_d64")
+    traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu capture (same workload)
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[dom[3]]
+        traffic = tj["dram_read_bytes"] + tj["dram_write_bytes"] if args.kernel_impl == "auto" else None
+    except Exception:
+        pass
     roof = {"bound": "hbm", "kernel": f"{dom[3]} (mlstm_b200_chunkwise_{dom[0]}, one launch per call)",
             "achieved": dom[1] / (dom[2] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-            "frac": dom[1] / (dom[2] * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_kind": peak_kind,
+            "frac": dom[1] / (dom[2] * 1e-3) / 1e9 / hbm_peak, "traffic": traffic,
+            "traffic_source": "profiles/r01_traffic.json (ncu --set full, same command)" if traffic else None,
+            "peak_kind": peak_kind,
             "algorithmic_bytes": dom[1], "fw_ms": fw_t, "bw_ms": bw_t,
             "fw_gbs": fw_bytes / (fw_t * 1e-3) / 1e9, "bw_gbs": bw_bytes / (bw_t * 1e-3) / 1e9,
             "fw_frac": fw_bytes / (fw_t * 1e-3) / 1e9 / hbm_peak, "bw_frac": bw_bytes / (bw_t * 1e-3) / 1e9 / hbm_peak,
             "tflops_frac_of_bf16_peak": (ff + fb) / ((fw_t + bw_t) * 1e-3) / 1e12 / tf_peak}
 
-    # ---- end to end through the public API with HOST buffers ----------------------------------
+    # ---- end to end through the public host-buffer API: pinned host tensors in, pinned host tensors out,
+    #      H2D / kernels / D2H pipelined over batch slices (xlstm_yolo_clean_b200.HostFwBw) -----------
     host = {k: v.cpu().pin_memory() for k, v in sets[0].items()}
-    names_in = ("q", "k", "v", "i", "f", "dh")
-    h2d = sum(host[k].numel() * host[k].element_size() for k in names_in)
-    out_host = None
-
-    def step_e2e():
-        nonlocal out_host
-        d = {k: host[k].to(dev, non_blocking=True) for k in names_in}
-        leaves = {k: d[k].requires_grad_(True) for k in ("q", "k", "v", "i", "f")}
-        h = pkg.mlstm_chunkwise__b200(**leaves, chunk_size=c["L"], eps=1e-6)
-        h.backward(d["dh"])
-        outs = [h.detach()] + [leaves[k].grad for k in ("q", "k", "v", "i", "f")]
-        if out_host is None:
-            out_host = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs]
-        for dst, src in zip(out_host, outs):
-            dst.copy_(src, non_blocking=True)
-        return sum(o.numel() * o.element_size() for o in outs)
-
+    pipe = pkg.HostFwBw(c["B"], c["NH"], c["S"], c["DK"], c["DV"], dtype=dt, device=dev, n_slices=8, chunk_size=c["L"])
+    host_out = pkg.HostFwBw.alloc_host(c["B"], c["NH"], c["S"], c["DK"], c["DV"], dtype=dt)
+    h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
     for _ in range(3):
-        d2h = step_e2e()
+        pipe.run(host, host_out)
     sync_all()
-    e_steps = max(3, min(args.steps, 10))
+    e_steps = max(3, min(args.steps, 20))
     e0.record()
     for _ in range(e_steps):
-        step_e2e()
+        pipe.run(host, host_out)
     e1.record()
     sync_all()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_val = world * (ff + fb) / (t.item() / e_steps * 1e-3) / 1e12
+    e2e_ms = replicas.max_over_ranks(e0.elapsed_time(e1), dev) / e_steps
+    e2e_val = replicas.sum_over_ranks(ff + fb, dev) / (e2e_ms * 1e-3) / 1e12
+    e2e_check = float((host_out["h"].float() - keep[0][0][0].float().cpu()).abs().max())  # same inputs as set 0
 
     if rank == 0:
         line = {
@@ -339,7 +331,8 @@ def main():
                        "frac_of_bf16_peak": value / world / tf_peak},
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_val, "unit": "TFLOP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e_steps},
+                    "steps": e_steps, "ms_per_step": e2e_ms, "api": "HostFwBw.run (pinned host in/out, 8 batch slices, 3 streams)",
+                    "max_abs_diff_vs_device_path": e2e_check},
             "roofline": roof,
         }
         if not args.no_cpu_baseline:

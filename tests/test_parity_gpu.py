@@ -197,6 +197,33 @@ def test_autocast_casts_to_kernel_dtype(pkg):
     assert O.rel_err(h, _oracle(inp, torch.bfloat16)["h"]) < 2e-2
 
 
+@pytest.mark.parametrize("S", [128, 448, 1600, 6400])
+@pytest.mark.parametrize("D", [32, 64, 128])
+def test_model_call_shapes(pkg, S, D):
+    """The four sequence lengths (after x64 padding) and three head dims the YAML models produce
+    (SURVEY.md §3.1): 640-base192 (d=32), base256 (d=64), base384 (d=128); bf16, small batch."""
+    inp = O.make_inputs(1, 2, S, D, D, seed=40 + D, dtype=torch.float32, dist="model" if S == 6400 else "normal")
+    got = _run(pkg, inp, torch.bfloat16)
+    _assert_close(got, _oracle(inp, torch.bfloat16), 2e-2, f"S={S} D={D}")
+
+
+def test_host_pipeline_matches_device_path(pkg):
+    """HostFwBw (pinned host buffers, batch-sliced 3-stream pipeline) == one device-resident call."""
+    B, NH, S, D = 6, 4, 320, 64
+    inp = O.make_inputs(B, NH, S, D, D, seed=50, dtype=torch.float32)
+    host = {k: v.to(torch.bfloat16).pin_memory() for k, v in inp.items()}
+    pipe = pkg.HostFwBw(B, NH, S, D, D, n_slices=4)
+    out = pkg.HostFwBw.alloc_host(B, NH, S, D, D)
+    pipe.run(host, out)
+    torch.cuda.synchronize()
+    d = {k: v.cuda() for k, v in host.items()}
+    h, n_out, m_out, _, cst = pkg.mlstm_chunkwise_fw(d["q"], d["k"], d["v"], d["i"], d["f"])
+    g = pkg.mlstm_chunkwise_bw(d["q"], d["k"], d["v"], d["i"], d["f"], n_out, m_out, d["dh"], c_states=cst)
+    torch.cuda.synchronize()
+    for name, ref in zip(("h", "dq", "dk", "dv", "di", "df"), (h,) + tuple(g[:5])):
+        assert torch.equal(out[name], ref.cpu()), name
+
+
 # ---- full-size (BASELINE config 2) checks through size-independent properties -----------------
 
 CFG2 = (32, 4, 1600, 64, 64)

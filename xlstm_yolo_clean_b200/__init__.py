@@ -10,6 +10,7 @@ mlstm_kernels/torch/chunkwise/__init__.py:9-15 of the reference):
     patch_model(model)    point every MatrixLSTMCell.gpu_backend at the new kernel
 """
 from ._cabi import LIB_PATH, LibraryMissing, load_library  # noqa: F401
+from .host_pipeline import HostFwBw  # noqa: F401
 from .backend import (  # noqa: F401
     KERNEL_NAME,
     last_launch_count,

@@ -1,0 +1,68 @@
+"""Host-buffer entry point: fwd+bwd of the chunkwise mLSTM for tensors that live in (pinned) host
+memory, pipelined over batch slices so that the H2D copy of slice j+1, the kernels of slice j and
+the D2H copy of slice j-1 overlap (three CUDA streams, full-duplex PCIe).  The op has no
+cross-sample term, so slicing the batch axis is exact.
+"""
+from __future__ import annotations
+
+import torch
+
+from .backend import mlstm_chunkwise_bw, mlstm_chunkwise_fw
+
+_IN = ("q", "k", "v", "i", "f", "dh")
+_OUT = ("h", "dq", "dk", "dv", "di", "df")
+
+
+class HostFwBw:
+    def __init__(self, B, NH, S, DK, DV, dtype=torch.bfloat16, device="cuda:0", n_slices=8, chunk_size=64, eps=1e-6):
+        self.dev = torch.device(device)
+        self.n_slices = max(1, min(n_slices, B))
+        self.chunk_size, self.eps = chunk_size, eps
+        shp = dict(q=(B, NH, S, DK), k=(B, NH, S, DK), v=(B, NH, S, DV), i=(B, NH, S), f=(B, NH, S), dh=(B, NH, S, DV),
+                   h=(B, NH, S, DV), dq=(B, NH, S, DK), dk=(B, NH, S, DK), dv=(B, NH, S, DV), di=(B, NH, S), df=(B, NH, S))
+        self.d_in = {k: torch.empty(shp[k], dtype=dtype, device=self.dev) for k in _IN}
+        self.s_h2d, self.s_cmp, self.s_d2h = (torch.cuda.Stream(self.dev) for _ in range(3))
+        bounds = torch.linspace(0, B, self.n_slices + 1).round().long().tolist()
+        self.slices = [slice(a, b) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.d_in.values())
+        self.d2h_bytes = sum(torch.Size(shp[k]).numel() for k in _OUT) * torch.empty((), dtype=dtype).element_size()
+
+    @staticmethod
+    def alloc_host(B, NH, S, DK, DV, dtype=torch.bfloat16):
+        shp = dict(h=(B, NH, S, DV), dq=(B, NH, S, DK), dk=(B, NH, S, DK), dv=(B, NH, S, DV), di=(B, NH, S), df=(B, NH, S))
+        return {k: torch.empty(v, dtype=dtype).pin_memory() for k, v in shp.items()}
+
+    def run(self, host_in: dict, host_out: dict):
+        """host_in: pinned q,k,v,i,f,dh; host_out: pinned h,dq,dk,dv,di,df (filled asynchronously;
+        synchronise the device or `self.s_d2h` before reading them)."""
+        cur = torch.cuda.current_stream(self.dev)
+        for s in (self.s_h2d, self.s_cmp, self.s_d2h):
+            s.wait_stream(cur)
+        keep = []
+        for sl in self.slices:
+            with torch.cuda.stream(self.s_h2d):
+                for k in _IN:
+                    self.d_in[k][sl].copy_(host_in[k][sl], non_blocking=True)
+                e_in = torch.cuda.Event()
+                e_in.record(self.s_h2d)
+            with torch.cuda.stream(self.s_cmp):
+                self.s_cmp.wait_event(e_in)
+                d = {k: self.d_in[k][sl] for k in _IN}
+                h, n_out, m_out, _, cst = mlstm_chunkwise_fw(d["q"], d["k"], d["v"], d["i"], d["f"],
+                                                             chunk_size=self.chunk_size, eps=self.eps)
+                dq, dk, dv, di, df, _ = mlstm_chunkwise_bw(d["q"], d["k"], d["v"], d["i"], d["f"], n_out, m_out, d["dh"],
+                                                           chunk_size=self.chunk_size, eps=self.eps, c_states=cst)
+                e_c = torch.cuda.Event()
+                e_c.record(self.s_cmp)
+            outs = dict(h=h, dq=dq, dk=dk, dv=dv, di=di, df=df)
+            with torch.cuda.stream(self.s_d2h):
+                self.s_d2h.wait_event(e_c)
+                for k in _OUT:
+                    host_out[k][sl].copy_(outs[k], non_blocking=True)
+                    outs[k].record_stream(self.s_d2h)
+            keep.append((n_out, m_out, cst))
+            for t in (n_out, m_out, cst):
+                if t is not None:
+                    t.record_stream(self.s_cmp)
+        cur.wait_stream(self.s_d2h)
+        return host_out
