@@ -70,6 +70,9 @@ typedef struct mlstm_b200_shape {
   int32_t chunk_size; /* S % chunk_size == 0 is required (native/fw.py:252-254) */
   int32_t dtype;      /* MLSTM_B200_F32 / BF16 / F16 */
   int32_t impl;       /* MLSTM_B200_IMPL_* */
+  int32_t reverse;    /* 1: anti-causal scan, h = flip(mLSTM(flip(inputs))) along S without any copy
+                         (the ROWWISE_FROM_BOT_RIGHT direction of ViLLayer, vision_lstm2.py:292-312);
+                         initial / last states then refer to the END / START of the sequence in memory */
   float eps;
   float qk_scale;     /* <= 0 selects DHQK^-0.5 (native/fw.py:263-264) */
 } mlstm_b200_shape;

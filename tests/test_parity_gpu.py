@@ -207,6 +207,39 @@ def test_model_call_shapes(pkg, S, D):
     _assert_close(got, _oracle(inp, torch.bfloat16), 2e-2, f"S={S} D={D}")
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+@pytest.mark.parametrize("states", [False, True], ids=["plain", "states"])
+def test_reverse_direction_equals_flipped_oracle(pkg, dtype, states):
+    """reverse=True == flip(mLSTM(flip(inputs))) -- the bottom-right ViL direction (vision_lstm2.py:292-312)
+    -- for outputs, every gradient and the boundary states, with no data movement."""
+    inp = O.make_inputs(2, 3, 320, 64, 64, seed=60, dtype=torch.float32, with_states=states)
+    dev = torch.device("cuda:0")
+    t = {k: v.to(dtype).to(dev) for k, v in inp.items()}
+    leaves = {k: t[k].detach().requires_grad_(True) for k in ("q", "k", "v", "i", "f")}
+    kw = {}
+    if states:
+        c0 = t["c0"].detach().requires_grad_(True)
+        kw = dict(c_initial=c0, n_initial=t["n0"], m_initial=t["m0"], return_last_states=True)
+    out = pkg.mlstm_chunkwise__b200(**leaves, reverse=True, autocast_kernel_dtype=torch.float32, **kw)
+    if states:
+        h, (c_last, n_last, m_last) = out
+        torch.autograd.backward([h, c_last], [t["dh"], t["dc_last"].to(c_last.dtype)])
+    else:
+        h = out
+        h.backward(t["dh"])
+    torch.cuda.synchronize()
+    seq = ("q", "k", "v", "i", "f", "dh")
+    flipped = {k: (v.flip(2) if k in seq else v) for k, v in inp.items()}
+    want = _oracle(flipped, dtype, states=states)
+    got = dict(h=h, dq=leaves["q"].grad, dk=leaves["k"].grad, dv=leaves["v"].grad, di=leaves["i"].grad, df=leaves["f"].grad)
+    tol = TOL[dtype]
+    for name in got:
+        assert O.rel_err(got[name].double().cpu(), want[name].flip(2)) < tol, name
+    if states:
+        assert O.rel_err(c_last.double().cpu(), want["c_last"]) < tol
+        assert O.rel_err(c0.grad.double().cpu(), want["dc0"]) < tol
+
+
 def test_host_pipeline_matches_device_path(pkg):
     """HostFwBw (pinned host buffers, batch-sliced 3-stream pipeline) == one device-resident call."""
     B, NH, S, D = 6, 4, 320, 64

@@ -56,13 +56,14 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
-def _shape(q, v, chunk_size, eps, impl, qk_scale=None) -> _cabi.Shape:
+def _shape(q, v, chunk_size, eps, impl, qk_scale=None, reverse=False) -> _cabi.Shape:
     B, NH, S, DK = q.shape
     s = _cabi.Shape()
     s.B, s.NH, s.S, s.DHQK, s.DHHV = B, NH, S, DK, v.shape[-1]
     s.chunk_size = int(chunk_size)
     s.dtype = _DTYPES[q.dtype]
     s.impl = _default_impl if impl is None else impl
+    s.reverse = 1 if reverse else 0
     s.eps = float(eps)
     s.qk_scale = -1.0 if qk_scale is None else float(qk_scale)
     return s
@@ -98,7 +99,7 @@ def _state_f32(t, shape):
 
 
 def mlstm_chunkwise_fw(q, k, v, i, f, c_initial=None, n_initial=None, m_initial=None, qk_scale=None,
-                       return_last_states=False, chunk_size=64, eps=1e-6, impl=None, save_states=True):
+                       return_last_states=False, chunk_size=64, eps=1e-6, impl=None, save_states=True, reverse=False):
     """C-ABI forward.  Returns h, n_out, m_out, last_states-or-None (fp32), c_states-or-None.
 
     ``c_states`` is the opaque per-tile state buffer the tensor-core backward consumes (the
@@ -130,7 +131,7 @@ def mlstm_chunkwise_fw(q, k, v, i, f, c_initial=None, n_initial=None, m_initial=
                     torch.empty(B, NH, DK, dtype=torch.float32, device=dev),
                     torch.empty(B, NH, 1, dtype=torch.float32, device=dev))
         a = _cabi.FwArgs()
-        a.shape = _shape(q, v, chunk_size, eps, impl, qk_scale)
+        a.shape = _shape(q, v, chunk_size, eps, impl, qk_scale, reverse)
         ws_bytes = lib.mlstm_b200_workspace_bytes(C.byref(a.shape), 0)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         st_bytes = lib.mlstm_b200_states_bytes(C.byref(a.shape)) if save_states else 0
@@ -149,7 +150,7 @@ def mlstm_chunkwise_fw(q, k, v, i, f, c_initial=None, n_initial=None, m_initial=
 
 def mlstm_chunkwise_bw(q, k, v, i, f, n_out, m_out, dh, c_initial=None, n_initial=None, m_initial=None,
                        dc_last=None, qk_scale=None, chunk_size=64, eps=1e-6, impl=None, want_dc_initial=False,
-                       c_states=None):
+                       c_states=None, reverse=False):
     """C-ABI backward.  Returns dq, dk, dv, di, df, dc_initial-or-None (fp32)."""
     lib = _cabi.load_library()
     _check_inputs(q, k, v, i, f)
@@ -174,7 +175,7 @@ def mlstm_chunkwise_bw(q, k, v, i, f, n_out, m_out, dh, c_initial=None, n_initia
         df = torch.empty(B, NH, S, dtype=q.dtype, device=dev)
         dc0 = torch.empty(B, NH, DK, DV, dtype=torch.float32, device=dev) if want_dc_initial else None
         a = _cabi.BwArgs()
-        a.shape = _shape(q, v, chunk_size, eps, impl, qk_scale)
+        a.shape = _shape(q, v, chunk_size, eps, impl, qk_scale, reverse)
         ws_bytes = lib.mlstm_b200_workspace_bytes(C.byref(a.shape), 1)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         a.q, a.k, a.v, a.i, a.f, a.dh = (_tensor(t) for t in (q, k, v, i, f, dh))
@@ -196,13 +197,13 @@ def _make_function(autocast_kernel_dtype: torch.dtype):
 
         @staticmethod
         @custom_fwd(device_type="cuda", cast_inputs=autocast_kernel_dtype)
-        def forward(ctx, q, k, v, i, f, c_initial, n_initial, m_initial, return_last_states, chunk_size, eps):
+        def forward(ctx, q, k, v, i, f, c_initial, n_initial, m_initial, return_last_states, chunk_size, eps, reverse):
             need_bw = any(ctx.needs_input_grad[:6])
             h, n_out, m_out, last, c_states = mlstm_chunkwise_fw(
                 q, k, v, i, f, c_initial, n_initial, m_initial, return_last_states=return_last_states,
-                chunk_size=chunk_size, eps=eps, save_states=need_bw)
+                chunk_size=chunk_size, eps=eps, save_states=need_bw, reverse=reverse)
             ctx.save_for_backward(q, k, v, i, f, c_initial, n_initial, m_initial, n_out, m_out, c_states)
-            ctx.chunk_size, ctx.eps = chunk_size, eps
+            ctx.chunk_size, ctx.eps, ctx.reverse = chunk_size, eps, reverse
             if last is None:
                 return h, None, None, None
             # native kernels hand states back in the input dtype (native/fw.py:53-62)
@@ -214,13 +215,13 @@ def _make_function(autocast_kernel_dtype: torch.dtype):
             q, k, v, i, f, c0, n0, m0, n_out, m_out, c_states = ctx.saved_tensors
             dq, dk, dv, di, df, dc0 = mlstm_chunkwise_bw(
                 q, k, v, i, f, n_out, m_out, dh, c0, n0, m0, dc_last=dc_last, chunk_size=ctx.chunk_size, eps=ctx.eps,
-                want_dc_initial=c0 is not None, c_states=c_states)
+                want_dc_initial=c0 is not None, c_states=c_states, reverse=ctx.reverse)
             # dn_last / dm_last are ignored and dN/dM_initial are zeros, as in native/bw.py:329-337
             return (dq, dk, dv, di, df,
                     None if c0 is None else dc0.to(c0.dtype),
                     None if n0 is None else torch.zeros_like(n0),
                     None if m0 is None else torch.zeros_like(m0),
-                    None, None, None)
+                    None, None, None, None)
 
     return _MlstmChunkwiseB200
 
@@ -241,9 +242,14 @@ def mlstm_chunkwise__b200(
     eps: float = 1e-6,
     chunk_size: int = 64,
     autocast_kernel_dtype: torch.dtype = torch.bfloat16,
+    reverse: bool = False,
     **kwargs,
 ):
     """Drop-in for ``mlstm_chunkwise__native_custbw`` (native/fwbw.py:228-263).
+
+    ``reverse=True`` (extension) runs the anti-causal scan: the result equals
+    ``flip(f(flip(q), flip(k), ...))`` along S -- what ViLLayer obtains with two ``x.flip`` copies for
+    its bottom-right direction (vision_lstm2.py:292-312) -- without moving any data.
 
     Returns h (B, NH, S, DHHV) or (h, (C_last, n_last, m_last)) when ``return_last_states``.
     Extra keyword arguments are ignored like ``native_autograd`` does (fwbw.py:204).
@@ -252,7 +258,7 @@ def mlstm_chunkwise__b200(
         raise ValueError(f"Unsupported kernel dtype {autocast_kernel_dtype}.")
     fn = _FUNCTIONS[autocast_kernel_dtype]
     h, c_last, n_last, m_last = fn.apply(q, k, v, i, f, c_initial, n_initial, m_initial, bool(return_last_states),
-                                         int(chunk_size), float(eps))
+                                         int(chunk_size), float(eps), bool(reverse))
     if return_last_states:
         return h, (c_last, n_last, m_last)
     return h

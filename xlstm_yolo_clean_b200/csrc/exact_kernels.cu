@@ -48,7 +48,11 @@ struct ExactParams {
   int64_t dq_s[3], dk_s[3], dv_s[3], di_s[3], df_s[3];
   float* dc0;
   int DVT;  // dv slice width of the recurrent kernels
+  int rev;  // 1: anti-causal scan -- processing index t lives at memory token S-1-t (no data is moved)
 };
+// memory token of processing index t, and the signed token step
+__device__ __forceinline__ int64_t tok(const ExactParams& p, int64_t t) { return p.rev ? (int64_t)p.S - 1 - t : t; }
+__device__ __forceinline__ int64_t sgn(const ExactParams& p) { return p.rev ? -1 : 1; }
 
 // acc[a][j] += sum_k A(m_a, k) * B(k, n_j) with m_a = tm + a*MS, n_j = tn + j*NS.
 // TA: A stored [k][m]; TB: B stored [n][k].  All leading dimensions are odd -> conflict-free.
@@ -131,11 +135,12 @@ __global__ void __launch_bounds__(kThreads) k_states(ExactParams p) {
     }
     if (j == p.NC) break;
 
-    load_tile<T>(sK, ldk, kp + (int64_t)j * L * p.k.ss, p.k.ss, L, DK);
-    load_tile<T>(sV, ldv, vp + (int64_t)j * L * p.v.ss, p.v.ss, L, DVT);
+    const int64_t m0 = tok(p, (int64_t)j * L), sg = sgn(p);
+    load_tile<T>(sK, ldk, kp + m0 * p.k.ss, sg * p.k.ss, L, DK);
+    load_tile<T>(sV, ldv, vp + m0 * p.v.ss, sg * p.v.ss, L, DVT);
     if (threadIdx.x < 32) {
       float amax;
-      float g = chunk_gate_scan<T>(ip + (int64_t)j * L * p.ig.ss, p.ig.ss, fp + (int64_t)j * L * p.fg.ss, p.fg.ss, L, L, sb, si,
+      float g = chunk_gate_scan<T>(ip + m0 * p.ig.ss, sg * p.ig.ss, fp + m0 * p.fg.ss, sg * p.fg.ss, L, L, sb, si,
                                    spm, &amax);
       if (threadIdx.x == 0) { s_g = g; s_amax = amax; }
     }
@@ -206,10 +211,10 @@ __global__ void __launch_bounds__(kThreads) k_fw_h(ExactParams p) {
   float* sden = sbq + L;  // n_out + eps
   float* smt = sden + L;  // m_t
 
-  const int64_t t0 = (int64_t)c * L;
-  load_tile<T>(sQ, ldk, (const T*)p.q.ptr + b * p.q.sb + hh * p.q.sh + t0 * p.q.ss, p.q.ss, L, DK);
-  load_tile<T>(sK, ldk, (const T*)p.k.ptr + b * p.k.sb + hh * p.k.sh + t0 * p.k.ss, p.k.ss, L, DK);
-  load_tile<T>(sV, ldv, (const T*)p.v.ptr + b * p.v.sb + hh * p.v.sh + t0 * p.v.ss, p.v.ss, L, DV);
+  const int64_t t0 = tok(p, (int64_t)c * L), sg = sgn(p);  // memory token of the chunk's first processed row
+  load_tile<T>(sQ, ldk, (const T*)p.q.ptr + b * p.q.sb + hh * p.q.sh + t0 * p.q.ss, sg * p.q.ss, L, DK);
+  load_tile<T>(sK, ldk, (const T*)p.k.ptr + b * p.k.sb + hh * p.k.sh + t0 * p.k.ss, sg * p.k.ss, L, DK);
+  load_tile<T>(sV, ldv, (const T*)p.v.ptr + b * p.v.sb + hh * p.v.sh + t0 * p.v.ss, sg * p.v.ss, L, DV);
   const float* Cs = p.Cst + ((int64_t)bh * (p.NC + 1) + c) * DK * DV;
   for (int e = threadIdx.x; e < DK * DV; e += blockDim.x) {
     int d = e / DV, x = e - d * DV;
@@ -219,8 +224,8 @@ __global__ void __launch_bounds__(kThreads) k_fw_h(ExactParams p) {
   const float m_prev = p.Mst[(int64_t)bh * (p.NC + 1) + c];
   if (threadIdx.x < 32) {
     float amax;
-    chunk_gate_scan<T>((const T*)p.ig.ptr + b * p.ig.sb + hh * p.ig.sh + t0 * p.ig.ss, p.ig.ss,
-                       (const T*)p.fg.ptr + b * p.fg.sb + hh * p.fg.sh + t0 * p.fg.ss, p.fg.ss, L, L, sb, si, spm, &amax);
+    chunk_gate_scan<T>((const T*)p.ig.ptr + b * p.ig.sb + hh * p.ig.sh + t0 * p.ig.ss, sg * p.ig.ss,
+                       (const T*)p.fg.ptr + b * p.fg.sb + hh * p.fg.sh + t0 * p.fg.ss, sg * p.fg.ss, L, L, sb, si, spm, &amax);
   }
   __syncthreads();
   for (int t = threadIdx.x; t < L; t += blockDim.x) smt[t] = sb[t] + fmaxf(m_prev, spm[t]);  // fw.py:178-184
@@ -253,8 +258,8 @@ __global__ void __launch_bounds__(kThreads) k_fw_h(ExactParams p) {
     float nmax = fmaxf(fabsf(den), expf(-smt[t]));        // fw.py:208-210
     sbq[t] = bq;
     sden[t] = nmax + p.eps;
-    p.n_out[(int64_t)bh * p.S + t0 + t] = nmax;
-    p.m_out[(int64_t)bh * p.S + t0 + t] = smt[t];
+    p.n_out[(int64_t)bh * p.S + t0 + sg * t] = nmax;  // saved vectors are indexed by memory token
+    p.m_out[(int64_t)bh * p.S + t0 + sg * t] = smt[t];
   }
   __syncthreads();
   {  // h = (qbar C + P V) / (n + eps), fw.py:200-212
@@ -272,7 +277,7 @@ __global__ void __launch_bounds__(kThreads) k_fw_h(ExactParams p) {
 #pragma unroll
         for (int y = 0; y < 4; ++y) {
           int t = tm + x * MS, e = tn + y * NS;
-          hp[(int64_t)t * p.h_ss + e] = from_f32<T>((sbq[t] * a1[x][y] + a2[x][y]) / sden[t]);
+          hp[(int64_t)t * sg * p.h_ss + e] = from_f32<T>((sbq[t] * a1[x][y] + a2[x][y]) / sden[t]);
         }
     }
   }
@@ -316,12 +321,12 @@ __global__ void __launch_bounds__(kThreads) k_bw_dc(ExactParams p) {
     }
     if (j == 0) break;
     const int c = j - 1;
-    const int64_t t0 = (int64_t)c * L;
-    load_tile<T>(sQ, ldk, qp + t0 * p.q.ss, p.q.ss, L, DK);
-    load_tile<T>(sH, ldv, hp + t0 * p.dh.ss, p.dh.ss, L, DVT);
+    const int64_t t0 = tok(p, (int64_t)c * L), sg = sgn(p);
+    load_tile<T>(sQ, ldk, qp + t0 * p.q.ss, sg * p.q.ss, L, DK);
+    load_tile<T>(sH, ldv, hp + t0 * p.dh.ss, sg * p.dh.ss, L, DVT);
     if (threadIdx.x < 32) {
       float amax;
-      float g = chunk_gate_scan<T>(ip + t0 * p.ig.ss, p.ig.ss, fp + t0 * p.fg.ss, p.fg.ss, L, L, sb, si, spm, &amax);
+      float g = chunk_gate_scan<T>(ip + t0 * p.ig.ss, sg * p.ig.ss, fp + t0 * p.fg.ss, sg * p.fg.ss, L, L, sb, si, spm, &amax);
       if (threadIdx.x == 0) s_g = g;
     }
     __syncthreads();
@@ -329,12 +334,12 @@ __global__ void __launch_bounds__(kThreads) k_bw_dc(ExactParams p) {
     const float decay = expf(s_g + m_prev - m_next);  // bw.py:76
     for (int e = threadIdx.x; e < L * DK; e += blockDim.x) {
       int t = e / DK, d = e - t * DK;
-      float bq = expf(sb[t] + m_prev - p.m_out_in[(int64_t)bh * p.S + t0 + t]) * p.scale;  // bw.py:79-86
+      float bq = expf(sb[t] + m_prev - p.m_out_in[(int64_t)bh * p.S + t0 + sg * t]) * p.scale;  // bw.py:79-86
       sQ[t * ldk + d] *= bq;
     }
     for (int e = threadIdx.x; e < L * DVT; e += blockDim.x) {
       int t = e / DVT, x = e - t * DVT;
-      sH[t * ldv + x] /= (p.n_out_in[(int64_t)bh * p.S + t0 + t] + p.eps);  // bw.py:88-90
+      sH[t * ldv + x] /= (p.n_out_in[(int64_t)bh * p.S + t0 + sg * t] + p.eps);  // bw.py:88-90
     }
     __syncthreads();
     for (int idx = threadIdx.x; idx < MS * NS; idx += blockDim.x) {
@@ -387,11 +392,11 @@ __global__ void __launch_bounds__(kThreads) k_bw_dqkv(ExactParams p) {
   float* sacc = smt + L;  // q.dq - k.dk
   __shared__ float s_g;
 
-  const int64_t t0 = (int64_t)c * L;
-  load_tile<T>(sQ, ldk, (const T*)p.q.ptr + b * p.q.sb + hh * p.q.sh + t0 * p.q.ss, p.q.ss, L, DK);
-  load_tile<T>(sK, ldk, (const T*)p.k.ptr + b * p.k.sb + hh * p.k.sh + t0 * p.k.ss, p.k.ss, L, DK);
-  load_tile<T>(sV, ldv, (const T*)p.v.ptr + b * p.v.sb + hh * p.v.sh + t0 * p.v.ss, p.v.ss, L, DV);
-  load_tile<T>(sH, ldv, (const T*)p.dh.ptr + b * p.dh.sb + hh * p.dh.sh + t0 * p.dh.ss, p.dh.ss, L, DV);
+  const int64_t t0 = tok(p, (int64_t)c * L), sg = sgn(p);
+  load_tile<T>(sQ, ldk, (const T*)p.q.ptr + b * p.q.sb + hh * p.q.sh + t0 * p.q.ss, sg * p.q.ss, L, DK);
+  load_tile<T>(sK, ldk, (const T*)p.k.ptr + b * p.k.sb + hh * p.k.sh + t0 * p.k.ss, sg * p.k.ss, L, DK);
+  load_tile<T>(sV, ldv, (const T*)p.v.ptr + b * p.v.sb + hh * p.v.sh + t0 * p.v.ss, sg * p.v.ss, L, DV);
+  load_tile<T>(sH, ldv, (const T*)p.dh.ptr + b * p.dh.sb + hh * p.dh.sh + t0 * p.dh.ss, sg * p.dh.ss, L, DV);
   const float* Cs = p.Cst + ((int64_t)bh * (p.NC + 1) + c) * DK * DV;
   const float* dCs = p.dCst + ((int64_t)bh * (p.NC + 1) + c + 1) * DK * DV;
   for (int e = threadIdx.x; e < DK * DV; e += blockDim.x) {
@@ -401,22 +406,22 @@ __global__ void __launch_bounds__(kThreads) k_bw_dqkv(ExactParams p) {
   }
   if (threadIdx.x < 32) {
     float amax;
-    float g = chunk_gate_scan<T>((const T*)p.ig.ptr + b * p.ig.sb + hh * p.ig.sh + t0 * p.ig.ss, p.ig.ss,
-                                 (const T*)p.fg.ptr + b * p.fg.sb + hh * p.fg.sh + t0 * p.fg.ss, p.fg.ss, L, L, sb, si,
+    float g = chunk_gate_scan<T>((const T*)p.ig.ptr + b * p.ig.sb + hh * p.ig.sh + t0 * p.ig.ss, sg * p.ig.ss,
+                                 (const T*)p.fg.ptr + b * p.fg.sb + hh * p.fg.sh + t0 * p.fg.ss, sg * p.fg.ss, L, L, sb, si,
                                  spm, &amax);
     if (threadIdx.x == 0) s_g = g;
   }
   __syncthreads();
   const float m_prev = p.Mst[(int64_t)bh * (p.NC + 1) + c], m_next = p.Mst[(int64_t)bh * (p.NC + 1) + c + 1];
   for (int t = threadIdx.x; t < L; t += blockDim.x) {
-    float mt = p.m_out_in[(int64_t)bh * p.S + t0 + t];
+    float mt = p.m_out_in[(int64_t)bh * p.S + t0 + sg * t];
     smt[t] = mt;
     sab[t] = expf(s_g - sb[t] + si[t] - m_next);  // bw.py:181,187
     sbb[t] = expf(sb[t] + m_prev - mt);           // bw.py:186
   }
   for (int e = threadIdx.x; e < L * DV; e += blockDim.x) {
     int t = e / DV, x = e - t * DV;
-    sH[t * ldv + x] /= (p.n_out_in[(int64_t)bh * p.S + t0 + t] + p.eps);  // bw.py:135
+    sH[t * ldv + x] /= (p.n_out_in[(int64_t)bh * p.S + t0 + sg * t] + p.eps);  // bw.py:135
   }
   __syncthreads();
 
@@ -442,7 +447,7 @@ __global__ void __launch_bounds__(kThreads) k_bw_dqkv(ExactParams p) {
   }
   __syncthreads();
 
-  const int64_t tok0 = (int64_t)bh * p.S + t0;
+  const int64_t tok0 = (int64_t)bh * p.S + (int64_t)c * L;  // the q.dq - k.dk workspace is in processing order
   {  // dV = Sbar^T dHt + abar (K dC_k); dI = v . dv   (bw.py:164,190,326)
     const int MS = L / 4, NS = DV / 4;
     T* op = (T*)p.dv + b * p.dv_s[0] + hh * p.dv_s[1] + t0 * p.dv_s[2];
@@ -463,7 +468,7 @@ __global__ void __launch_bounds__(kThreads) k_bw_dqkv(ExactParams p) {
           for (int y = 0; y < 4; ++y) {
             int e = tn + y * NS;
             float val = a1[x][y] + sab[s] * a2[x][y];
-            op[(int64_t)s * p.dv_s[2] + e] = from_f32<T>(val);
+            op[(int64_t)s * sg * p.dv_s[2] + e] = from_f32<T>(val);
             part = fmaf(sV[s * ldv + e], val, part);
           }
           spart[s * 32 + tn] = part;
@@ -475,7 +480,7 @@ __global__ void __launch_bounds__(kThreads) k_bw_dqkv(ExactParams p) {
     for (int s = threadIdx.x; s < L; s += blockDim.x) {
       float r = 0.f;
       for (int x = 0; x < NS; ++x) r += spart[s * 32 + x];
-      dip[(int64_t)s * p.di_s[2]] = from_f32<T>(r);
+      dip[(int64_t)s * sg * p.di_s[2]] = from_f32<T>(r);
     }
     __syncthreads();
   }
@@ -499,7 +504,7 @@ __global__ void __launch_bounds__(kThreads) k_bw_dqkv(ExactParams p) {
           for (int y = 0; y < 4; ++y) {
             int d = tn + y * NS;
             float val = p.scale * a1[x][y] + sab[s] * a2[x][y];
-            op[(int64_t)s * p.dk_s[2] + d] = from_f32<T>(val);
+            op[(int64_t)s * sg * p.dk_s[2] + d] = from_f32<T>(val);
             part = fmaf(sK[s * ldk + d], val, part);
           }
           spart[s * 32 + tn] = part;
@@ -534,7 +539,7 @@ __global__ void __launch_bounds__(kThreads) k_bw_dqkv(ExactParams p) {
           for (int y = 0; y < 4; ++y) {
             int d = tn + y * NS;
             float val = p.scale * (a1[x][y] + sbb[t] * a2[x][y]);
-            op[(int64_t)t * p.dq_s[2] + d] = from_f32<T>(val);
+            op[(int64_t)t * sg * p.dq_s[2] + d] = from_f32<T>(val);
             part = fmaf(sQ[t * ldk + d], val, part);
           }
           spart[t * 32 + tn] = part;
@@ -570,7 +575,10 @@ __global__ void k_bw_df(ExactParams p) {
       if (lane + o < 32) v += u;
     }
     v += carry;
-    if (t >= 0) dfp[(int64_t)t * p.df_s[2]] = from_f32<T>(v * sigmoid_neg_f32(to_f32<T>(fp[(int64_t)t * p.fg.ss])));
+    if (t >= 0) {
+      const int64_t mt = tok(p, t);
+      dfp[mt * p.df_s[2]] = from_f32<T>(v * sigmoid_neg_f32(to_f32<T>(fp[mt * p.fg.ss])));
+    }
     carry = __shfl_sync(0xffffffffu, v, 0);
   }
 }
@@ -705,6 +713,7 @@ int exact_fw(const mlstm_b200_fw_args& a, cudaStream_t st) {
   p.n_out = a.n_out; p.m_out = a.m_out;
   p.c_last = a.c_last; p.n_last = a.n_last; p.m_last = a.m_last;
   p.DVT = pick_dvt(s);
+  p.rev = s.reverse ? 1 : 0;
   MLSTM_DISPATCH_DTYPE(s.dtype, T, {
     if (int e = launch_states<T>(p, st)) return e;
     size_t sm = smem_fw_h(L, p.DK, p.DV);
@@ -743,6 +752,7 @@ int exact_bw(const mlstm_b200_bw_args& a, cudaStream_t st) {
   }
   p.dc0 = a.dc_initial;
   p.DVT = pick_dvt(s);
+  p.rev = s.reverse ? 1 : 0;
   MLSTM_DISPATCH_DTYPE(s.dtype, T, {
     if (int e = launch_states<T>(p, st)) return e;  // recompute C/n/m states (bw.py:251-266)
     size_t sm = smem_bw_dc(L, p.DK, p.DVT);

@@ -1168,6 +1168,7 @@ void tensor_set_clock_buffer(void* dev_ptr) { g_prof = (long long*)dev_ptr; }
 bool tensor_supported(const mlstm_b200_shape& s) {
   if (s.dtype != MLSTM_B200_BF16 && s.dtype != MLSTM_B200_F16) return false;
   if (s.DHQK != 64 || s.DHHV != 64) return false;
+  if (s.reverse) return false;  // the anti-causal variant runs on the exact family for now
   if (s.chunk_size % 64 != 0 || s.S % 64 != 0) return false;
   return true;
 }
