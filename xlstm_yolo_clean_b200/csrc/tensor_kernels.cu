@@ -137,20 +137,41 @@ __device__ __forceinline__ GateRaw<T> load_gate_raw(const T* ip, int64_t is, con
 // logsigmoid with the fast exp / log units (the 16-bit path tolerates 1e-6 relative error here)
 __device__ __forceinline__ float logsigmoid_fast(float x) { return fminf(x, 0.f) - __logf(1.f + __expf(-fabsf(x))); }
 
+// suffix (reverse-direction) variants of the warp scans
+__device__ __forceinline__ float warp_incl_sum_dir(float v, int lane, bool rev) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float up = __shfl_up_sync(0xffffffffu, v, o), dn = __shfl_down_sync(0xffffffffu, v, o);
+    if (rev ? (lane + o < 32) : (lane >= o)) v += rev ? dn : up;
+  }
+  return v;
+}
+__device__ __forceinline__ float warp_incl_max_dir(float v, int lane, bool rev) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float up = __shfl_up_sync(0xffffffffu, v, o), dn = __shfl_down_sync(0xffffffffu, v, o);
+    if (rev ? (lane + o < 32) : (lane >= o)) v = fmaxf(v, rev ? dn : up);
+  }
+  return v;
+}
+
+// `rev`: anti-causal direction -- the cumulative sums / maxima run from the END of the tile
+// (suffix scans over the memory rows), everything else is unchanged.
 template <typename T>
-__device__ __noinline__ void gate_scan_regs(float* gb, const GateRaw<T>& r) {
+__device__ __noinline__ void gate_scan_regs(float* gb, const GateRaw<T>& r, bool rev) {
   const int lane = threadIdx.x & 31;
   float lf[4], iv[4], fv[4];
   float run = 0.f;
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
+  for (int k = 0; k < 4; ++k) {
+    const int e = rev ? 3 - k : k;  // scan order inside the lane
     const bool ok = lane * 4 + e < r.n_valid;
     fv[e] = ok ? to_f32<T>(r.f[e]) : INFINITY;
     iv[e] = ok ? to_f32<T>(r.i[e]) : -INFINITY;
     run += logsigmoid_fast(fv[e]);
     lf[e] = run;
   }
-  const float incl = warp_incl_sum(run, lane);
+  const float incl = warp_incl_sum_dir(run, lane, rev);
   const float base = incl - run;
   float pmax = -INFINITY;
 #pragma unroll
@@ -158,9 +179,9 @@ __device__ __noinline__ void gate_scan_regs(float* gb, const GateRaw<T>& r) {
     lf[e] += base;
     pmax = fmaxf(pmax, iv[e] - lf[e]);
   }
-  const float incl_max = warp_incl_max(pmax, lane);
-  float runmax = __shfl_up_sync(0xffffffffu, incl_max, 1);
-  if (lane == 0) runmax = -INFINITY;
+  const float incl_max = warp_incl_max_dir(pmax, lane, rev);
+  float runmax = rev ? __shfl_down_sync(0xffffffffu, incl_max, 1) : __shfl_up_sync(0xffffffffu, incl_max, 1);
+  if (lane == (rev ? 31 : 0)) runmax = -INFINITY;
   // maximum of y over this lane's 32-column unit (8 lanes per unit)
   float umax = pmax;
 #pragma unroll
@@ -168,7 +189,8 @@ __device__ __noinline__ void gate_scan_regs(float* gb, const GateRaw<T>& r) {
   umax = fmaxf(umax * kLog2e, -1e30f);
   float pm[4], y[4], cf[4];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
+  for (int k = 0; k < 4; ++k) {
+    const int e = rev ? 3 - k : k;
     runmax = fmaxf(runmax, iv[e] - lf[e]);
     pm[e] = runmax;
     y[e] = (iv[e] - lf[e]) * kLog2e;
@@ -180,7 +202,7 @@ __device__ __noinline__ void gate_scan_regs(float* gb, const GateRaw<T>& r) {
   reinterpret_cast<float4*>(gb + GateBuf::oY)[lane] = make_float4(y[0], y[1], y[2], y[3]);
   reinterpret_cast<float4*>(gb + GateBuf::oF)[lane] = make_float4(fv[0], fv[1], fv[2], fv[3]);
   reinterpret_cast<float4*>(gb + GateBuf::oCf)[lane] = make_float4(cf[0], cf[1], cf[2], cf[3]);
-  const float g = __shfl_sync(0xffffffffu, incl, 31);
+  const float g = __shfl_sync(0xffffffffu, incl, rev ? 0 : 31);
   const float amax = warp_all_max(pmax);
   if (lane == 0) {
     gb[GateBuf::oScal + 0] = g;
@@ -200,6 +222,7 @@ struct TcFwParams {
   const float *c0, *n0, *m0;
   float *n_out, *m_out;
   float *c_last, *n_last, *m_last;
+  int rev;           // 1: anti-causal direction (tiles walked from the end, mirrored in-tile mask)
   int store_states;  // 1: TMA-store the bf16 copy of C entering every tile (consumed by the backward)
   long long* prof;   // debug: per-tile phase clocks of CTA 0 (mlstm_b200_debug_set_clock_buffer)
 };
@@ -223,7 +246,7 @@ struct FwSmem {
   static constexpr int kTmemCols = NSTAGE == 2 ? 512 : 256;
 };
 
-template <typename T, int NSTAGE>
+template <typename T, int NSTAGE, bool REV>
 __global__ void __launch_bounds__(kTcThreads, NSTAGE == 1 ? 2 : 1)
 tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
           const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapH,
@@ -292,14 +315,17 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
   const T* ip = (const T*)p.ig + b * p.ig_sb + hh * p.ig_sh;
   const T* fp = (const T*)p.fg + b * p.fg_sb + hh * p.fg_sh;
   constexpr uint32_t kStageBytes = 3 * SM::kTile;
+  // memory tile of processing tile c: the anti-causal direction walks the tiles from the end and
+  // mirrors the in-tile mask / scans; no data is ever reversed (north_star item 4)
+  auto mt = [&](int c) { return REV ? p.NT - 1 - c : c; };
 
   if (warp == kCtlWarp) {
     // =========================== control warp ===================================================
     auto load_stage = [&](int s, int c) {
       mbar_expect_tx(&bar_full[s], kStageBytes);
-      tma_load_4d(smem + SM::oQ + s * SM::kTile, &mapQ, &bar_full[s], 0, c * LT, hh, b);
-      tma_load_4d(smem + SM::oK + s * SM::kTile, &mapK, &bar_full[s], 0, c * LT, hh, b);
-      tma_load_4d(smem + SM::oV + s * SM::kTile, &mapV, &bar_full[s], 0, c * LT, hh, b);
+      tma_load_4d(smem + SM::oQ + s * SM::kTile, &mapQ, &bar_full[s], 0, mt(c) * LT, hh, b);
+      tma_load_4d(smem + SM::oK + s * SM::kTile, &mapK, &bar_full[s], 0, mt(c) * LT, hh, b);
+      tma_load_4d(smem + SM::oV + s * SM::kTile, &mapV, &bar_full[s], 0, mt(c) * LT, hh, b);
     };
     if (lane == 0)
       for (int s = 0; s < NSTAGE && s < p.NT; ++s) load_stage(s, s);
@@ -332,7 +358,7 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       umma_commit(&bar_s);
     };
     if (lane == 0 && p.store_states) {  // state entering tile 0 (bf16 operand copy) -> c_states[b, h, 0]
-      tma_store_4d(&mapCs, sC, 0, 0, hh, b);
+      tma_store_4d(&mapCs, sC, 0, mt(0) * D, hh, b);
       tma_store_commit();
     }
     __syncwarp();
@@ -376,8 +402,8 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       named_sync(NB_C, kNbC);  // h staged, C_k written: every worker is done with this tile
       if (lane == 0) {
         TC_PROF(c, 14);
-        tma_store_4d(&mapH, sH, 0, c * LT, hh, b);
-        if (p.store_states && c + 1 < p.NT) tma_store_4d(&mapCs, sC, 0, (c + 1) * D, hh, b);  // state entering tile c+1
+        tma_store_4d(&mapH, sH, 0, mt(c) * LT, hh, b);
+        if (p.store_states && c + 1 < p.NT) tma_store_4d(&mapCs, sC, 0, mt(c + 1) * D, hh, b);  // state entering tile c+1
         tma_store_commit();
         if (c + NSTAGE < p.NT) load_stage(s, c + NSTAGE);
         TC_PROF(c, 15);
@@ -392,13 +418,13 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
   } else if (warp == kScanWarp) {
     // =========================== scan warp: gate vectors two tiles ahead ===========================
     auto raw_of = [&](int c) {
-      const int t1 = c * LT;
+      const int t1 = mt(c) * LT;
       return load_gate_raw<T>(ip + (int64_t)t1 * p.ig_ss, p.ig_ss, fp + (int64_t)t1 * p.fg_ss, p.fg_ss, min(LT, p.S - t1));
     };
     GateRaw<T> raw = raw_of(0);
     for (int n = 0; n < p.NT; ++n) {  // vectors of tile n; tiles 0 and 1 need no buffer hand-back
       if (n >= 2) named_sync(NB_C, kNbC);  // every worker is done with tile n-2: its gate buffer can be reused
-      gate_scan_regs(fsm + SM::fGates + (n & 1) * GateBuf::kFloats, raw);
+      gate_scan_regs(fsm + SM::fGates + (n & 1) * GateBuf::kFloats, raw, REV);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_g[n & 1]);
       if (n + 1 < p.NT) raw = raw_of(n + 1);  // stays in flight until the next hand-back
@@ -419,7 +445,7 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       float* snp = fsm + SM::fNp + pb * 4 * D;
       const float* sNc = fsm + SM::fN + cur * D;
       float* sNn = fsm + SM::fN + (cur ^ 1) * D;
-      const int t0 = c * LT;
+      const int t0 = mt(c) * LT;
       const int n_valid = min(LT, p.S - t0);
       const uint32_t tS = (c & 1) ? tS1 : tS0;
 
@@ -458,7 +484,8 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
 #pragma unroll 1
         for (int u = ch; u < 4; u += 2) {  // this thread's two 32-column units (warp-uniform branches)
           float v[32];
-          if (u < rb) {  // block strictly below the diagonal: rank-1 decay, one exp per row
+          const bool off_diag = REV ? u > rb : u < rb;  // fully unmasked 32x32 block
+          if (off_diag) {  // rank-1 decay, one exp per row
             tmem_ld32(tS + lane_base + u * 32, v);
             const float r_t = ex2_approx(x_t + gb[GateBuf::oScal + 4 + u]);
 #pragma unroll
@@ -480,7 +507,7 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
               for (int e = 0; e < 4; ++e) {
                 const int j = 4 * j4 + e;
                 float pv = v[j] * ex2_approx(x_t + yy[e]);
-                pv = j <= lane ? pv : 0.f;
+                pv = (REV ? j >= lane : j <= lane) ? pv : 0.f;
                 rs += pv;
                 v[j] = pv;
               }
@@ -601,6 +628,7 @@ struct TcBwParams {
   void *di, *df;
   int64_t di_sb, di_sh, di_ss, df_sb, df_sh, df_ss;
   float* dc0;
+  int rev;  // 1: the forward ran anti-causally; this sweep then walks the memory tiles in ascending order
   long long* prof;
 };
 
@@ -623,7 +651,7 @@ struct BwSmem {
   static constexpr uint32_t kLoadBytes = 4 * kTile + 64 * 128;
 };
 
-template <typename T>
+template <typename T, bool REV>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
           const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdH,
@@ -701,16 +729,18 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
   const T* fp = (const T*)p.fg + b * p.fg_sb + hh * p.fg_sh;
   const float* mo = p.m_out + (int64_t)bh * p.S;
   const float* no = p.n_out + (int64_t)bh * p.S;
+  // memory tile of processing tile c (see the forward kernel); the sweep visits c = NT-1 .. 0
+  auto mt = [&](int c) { return REV ? p.NT - 1 - c : c; };
 
   if (warp == kCtlWarp) {
     // =========================== control warp ===================================================
     auto issue_loads = [&](int c) {
       mbar_expect_tx(&bar_full, SM::kLoadBytes);
-      tma_load_4d(sQ, &mapQ, &bar_full, 0, c * LT, hh, b);
-      tma_load_4d(sK, &mapK, &bar_full, 0, c * LT, hh, b);
-      tma_load_4d(sV, &mapV, &bar_full, 0, c * LT, hh, b);
-      tma_load_4d(sdH, &mapdH, &bar_full, 0, c * LT, hh, b);
-      tma_load_4d(sCs, &mapCs, &bar_full, 0, c * D, hh, b);
+      tma_load_4d(sQ, &mapQ, &bar_full, 0, mt(c) * LT, hh, b);
+      tma_load_4d(sK, &mapK, &bar_full, 0, mt(c) * LT, hh, b);
+      tma_load_4d(sV, &mapV, &bar_full, 0, mt(c) * LT, hh, b);
+      tma_load_4d(sdH, &mapdH, &bar_full, 0, mt(c) * LT, hh, b);
+      tma_load_4d(sCs, &mapCs, &bar_full, 0, mt(c) * D, hh, b);
     };
     constexpr uint32_t id_s = umma_idesc(128, 128, false, false, kBf16);
     constexpr uint32_t id_c = umma_idesc(64, 64, true, true, kBf16);
@@ -746,7 +776,7 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
     for (int it = 0; it < p.NT; ++it) {
       const int c = p.NT - 1 - it, pb = it & 1;
       const uint32_t par = it & 1;
-      const int t0 = c * LT, n_valid = min(LT, p.S - t0);
+      const int t0 = mt(c) * LT, n_valid = min(LT, p.S - t0);
       TC_PROF(it, 9);
       named_sync(NB_B, kNbAB);  // Sb', dS written
       TC_PROF(it, 10);
@@ -814,7 +844,7 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
     };
     auto raw_of = [&](int c) {
       TileRaw r;
-      const int t0 = c * LT, n_valid = min(LT, p.S - t0);
+      const int t0 = mt(c) * LT, n_valid = min(LT, p.S - t0);
       r.g = load_gate_raw<T>(ip + (int64_t)t0 * p.ig_ss, p.ig_ss, fp + (int64_t)t0 * p.fg_ss, p.fg_ss, n_valid);
       if (lane * 4 < n_valid) {  // n_valid is a multiple of 64
         r.mt = *reinterpret_cast<const float4*>(mo + t0 + lane * 4);
@@ -823,12 +853,19 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
         r.mt = make_float4(0.f, 0.f, 0.f, 0.f);
         r.nt = make_float4(1.f, 1.f, 1.f, 1.f);
       }
-      r.m_prev = c > 0 ? mo[t0 - 1] : (p.m0 ? p.m0[bh] : 0.f);  // m of the state entering the tile
-      r.m_next = mo[t0 + n_valid - 1];                          // m of the state leaving it
+      // m of the state entering the tile = m_out of the previously processed token; m of the state leaving it
+      // = m_out of the tile's last processed token (its first memory row in the anti-causal direction)
+      if (!REV) {
+        r.m_prev = c > 0 ? mo[t0 - 1] : (p.m0 ? p.m0[bh] : 0.f);
+        r.m_next = mo[t0 + n_valid - 1];
+      } else {
+        r.m_prev = c > 0 ? mo[t0 + LT] : (p.m0 ? p.m0[bh] : 0.f);
+        r.m_next = mo[t0];
+      }
       return r;
     };
     auto publish = [&](float* gb, const TileRaw& r) {
-      gate_scan_regs(gb, r.g);
+      gate_scan_regs(gb, r.g, REV);
       reinterpret_cast<float4*>(gb + GateBuf::oMt)[lane] = r.mt;
       reinterpret_cast<float4*>(gb + GateBuf::oNt)[lane] = r.nt;
       if (lane == 0) {
@@ -844,7 +881,7 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       if (n >= 2) {
       const int it = n - 2;
       const int c = p.NT - 1 - it, pb = it & 1;
-      const int t0 = c * LT, n_valid = min(LT, p.S - t0);
+      const int t0 = mt(c) * LT, n_valid = min(LT, p.S - t0);
       named_sync(NB_C, kNbC);  // row dots of tile `it` are in shared memory; its buffers can be reused afterwards
       // ---- gate gradients: reverse (suffix) scan over the tile, carried across tiles -------------
       {
@@ -857,16 +894,31 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
           acc[e] = (sp[0 * LT + t] + sp[1 * LT + t]) - (sp[2 * LT + t] + sp[3 * LT + t]);  // bw.py:321
           di[e] = sp[4 * LT + t] + sp[5 * LT + t];                                         // bw.py:326
         }
-        acc[2] += acc[3];
-        acc[1] += acc[2];
-        acc[0] += acc[1];
-        float incl = acc[0];
+        // sum over all tokens processed AFTER t: a suffix sum over memory rows, or a prefix sum when the
+        // forward ran anti-causally (this sweep then visits the memory tiles in ascending order)
+        float incl, own;
+        if (!REV) {
+          acc[2] += acc[3];
+          acc[1] += acc[2];
+          acc[0] += acc[1];
+          incl = own = acc[0];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          float u = __shfl_down_sync(0xffffffffu, incl, o);
-          if (lane + o < 32) incl += u;
+          for (int o = 1; o < 32; o <<= 1) {
+            float u = __shfl_down_sync(0xffffffffu, incl, o);
+            if (lane + o < 32) incl += u;
+          }
+        } else {
+          acc[1] += acc[0];
+          acc[2] += acc[1];
+          acc[3] += acc[2];
+          incl = own = acc[3];
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            float u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+          }
         }
-        const float excl = incl - acc[0] + carry;
+        const float excl = incl - own + carry;
         T* dip = (T*)p.di + b * p.di_sb + hh * p.di_sh;
         T* dfp = (T*)p.df + b * p.df_sb + hh * p.df_sh;
 #pragma unroll
@@ -878,7 +930,7 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
                 from_f32<T>((acc[e] + excl) * sigmoid_neg_f32(gb[GateBuf::oF + t]));  // bw.py:322-323
           }
         }
-        carry += __shfl_sync(0xffffffffu, incl, 0);
+        carry += __shfl_sync(0xffffffffu, incl, REV ? 31 : 0);
       }
       __syncwarp();
       }
@@ -896,7 +948,7 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       const uint32_t par = it & 1;
       const float* gb = fsm + SM::fGates + pb * GateBuf::kFloats;
       float* spart = fsm + SM::fPart + pb * 6 * LT;
-      const int n_valid = min(LT, p.S - (p.NT - 1 - it) * LT);
+      const int n_valid = min(LT, p.S - mt(p.NT - 1 - it) * LT);
       const bool valid = row < n_valid;
 
       TC_PROF(it, 0);
@@ -921,12 +973,12 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
 #pragma unroll 1
         for (int u = ch; u < 4; u += 2) {  // this thread's two 32-column units (warp-uniform branches)
           float v[32], w[32];
-          if (u <= rb) {
+          if (REV ? u >= rb : u <= rb) {
             uint32_t rv[32], rw[32];
             tmem_ld32_nowait(tS + lane_base + u * 32, rv);
             tmem_ld32_nowait(tdSb + lane_base + u * 32, rw);
             tmem_ld_wait();
-            if (u < rb) {  // block strictly below the diagonal: rank-1 decay, one exp per row
+            if (u != rb) {  // fully unmasked 32x32 block: rank-1 decay, one exp per row
               const float r_t = ex2_approx(x_t + gb[GateBuf::oScal + 4 + u]);
               const float r_s = r_t * p.scale;
 #pragma unroll
@@ -949,7 +1001,7 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
                 for (int e = 0; e < 4; ++e) {
                   const int j = 4 * j4 + e;
                   float wg = ex2_approx(x_t + yy[e]);
-                  wg = j <= lane ? wg : 0.f;
+                  wg = (REV ? j >= lane : j <= lane) ? wg : 0.f;
                   v[j] = __uint_as_float(rv[j]) * (wg * p.scale);
                   w[j] = __uint_as_float(rw[j]) * wg;
                 }
@@ -1094,7 +1146,7 @@ template <typename T>
 int launch_fw_d64(const TcFwParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
                   const CUtensorMap& mh, const CUtensorMap& mcs, cudaStream_t st) {
   using SM = FwSmem<2>;
-  auto kern = tc_fw_d64<T, 2>;
+  auto kern = p.rev ? tc_fw_d64<T, 2, true> : tc_fw_d64<T, 2, false>;
   MLSTM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
   kern<<<p.B * p.NH, kTcThreads, SM::kBytes, st>>>(mq, mk, mv, mh, mcs, p);
   count_launch();
@@ -1141,6 +1193,7 @@ int run_fw(const mlstm_b200_fw_args& a, void* c_states, cudaStream_t st) {
   p.c0 = a.c_initial; p.n0 = a.n_initial; p.m0 = a.m_initial;
   p.n_out = a.n_out; p.m_out = a.m_out;
   p.c_last = a.c_last; p.n_last = a.n_last; p.m_last = a.m_last;
+  p.rev = s.reverse ? 1 : 0;
   p.store_states = c_states != nullptr;
   p.prof = g_prof;
   if (s.dtype == MLSTM_B200_BF16) return launch_fw_d64<__nv_bfloat16>(p, mq, mk, mv, mh, mcs, st);
@@ -1168,7 +1221,6 @@ void tensor_set_clock_buffer(void* dev_ptr) { g_prof = (long long*)dev_ptr; }
 bool tensor_supported(const mlstm_b200_shape& s) {
   if (s.dtype != MLSTM_B200_BF16 && s.dtype != MLSTM_B200_F16) return false;
   if (s.DHQK != 64 || s.DHHV != 64) return false;
-  if (s.reverse) return false;  // the anti-causal variant runs on the exact family for now
   if (s.chunk_size % 64 != 0 || s.S % 64 != 0) return false;
   return true;
 }
@@ -1227,13 +1279,14 @@ int tensor_bw(const mlstm_b200_bw_args& a, cudaStream_t st) {
   p.di = a.di.ptr; p.di_sb = a.di.stride[0]; p.di_sh = a.di.stride[1]; p.di_ss = a.di.stride[2];
   p.df = a.df.ptr; p.df_sb = a.df.stride[0]; p.df_sh = a.df.stride[1]; p.df_ss = a.df.stride[2];
   p.dc0 = a.dc_initial;
+  p.rev = s.reverse ? 1 : 0;
   p.prof = g_prof ? g_prof + 4096 : nullptr;
   if (s.dtype == MLSTM_B200_BF16) {
-    auto kern = tc_bw_d64<__nv_bfloat16>;
+    auto kern = p.rev ? tc_bw_d64<__nv_bfloat16, true> : tc_bw_d64<__nv_bfloat16, false>;
     MLSTM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwSmem::kBytes));
     kern<<<s.B * s.NH, kTcThreads, BwSmem::kBytes, st>>>(mq, mk, mv, mdh, mcs, mdq, mdk, mdv, p);
   } else {
-    auto kern = tc_bw_d64<__half>;
+    auto kern = p.rev ? tc_bw_d64<__half, true> : tc_bw_d64<__half, false>;
     MLSTM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwSmem::kBytes));
     kern<<<s.B * s.NH, kTcThreads, BwSmem::kBytes, st>>>(mq, mk, mv, mdh, mcs, mdq, mdk, mdv, p);
   }
