@@ -73,6 +73,9 @@ typedef struct mlstm_b200_shape {
   int32_t reverse;    /* 1: anti-causal scan, h = flip(mLSTM(flip(inputs))) along S without any copy
                          (the ROWWISE_FROM_BOT_RIGHT direction of ViLLayer, vision_lstm2.py:292-312);
                          initial / last states then refer to the END / START of the sequence in memory */
+  int32_t siging;     /* 1: sigmoid input gate, no max state, denominator max(|n|, 1) -- the variant the
+                         reference's CUDA model path uses (triton_xl_chunk_siging/fwbw.py:211-268,
+                         parallel/native_siging/fw.py:15-74); m_initial / m_last are then ignored / zero */
   float eps;
   float qk_scale;     /* <= 0 selects DHQK^-0.5 (native/fw.py:263-264) */
 } mlstm_b200_shape;

@@ -46,8 +46,11 @@ class ChunkGates:
     i: torch.Tensor
 
 
-def chunk_gates(i: torch.Tensor, f: torch.Tensor, L: int) -> ChunkGates:
-    """fw.py:257-262 (b) and fw.py:81-83 (a, g)."""
+def chunk_gates(i: torch.Tensor, f: torch.Tensor, L: int, siging: bool = False) -> ChunkGates:
+    """fw.py:257-262 (b) and fw.py:81-83 (a, g).  ``siging``: the input gate is logsigmoid(i)
+    (triton_xl_chunk_siging/chunkwise_gates.py:15-47, parallel/native_siging/fw.py:50-52)."""
+    if siging:
+        i = F.logsigmoid(i)
     B, NH, S = f.shape
     assert S % L == 0, f"Sequence length {S} is not divisible by chunk size {L}."
     lf = F.logsigmoid(f).reshape(B, NH, S // L, L)
@@ -58,7 +61,7 @@ def chunk_gates(i: torch.Tensor, f: torch.Tensor, L: int) -> ChunkGates:
     return ChunkGates(b=b, a=a, g=g, i=ic)
 
 
-def inter_chunk_states(k, v, gates: ChunkGates, c0=None, n0=None, m0=None):
+def inter_chunk_states(k, v, gates: ChunkGates, c0=None, n0=None, m0=None, siging=False):
     """State recurrence over chunk boundaries, fw.py:29-128.
 
     Returns C (B,NH,NC+1,DK,DV), n (B,NH,NC+1,DK), m (B,NH,NC+1); index j holds
@@ -82,6 +85,8 @@ def inter_chunk_states(k, v, gates: ChunkGates, c0=None, n0=None, m0=None):
     a_max = gates.a.amax(dim=-1)
     for j in range(NC):
         m_next = torch.maximum(gates.g[:, :, j] + m[:, :, j], a_max[:, :, j])  # fw.py:96-98
+        if siging:  # no max state: every gate factor is <= 1 already
+            m_next = torch.zeros_like(m_next)
         decay = torch.exp(gates.g[:, :, j] + m[:, :, j] - m_next)  # fw.py:106
         w = torch.exp(gates.a[:, :, j] - m_next[..., None])  # fw.py:102
         kw = kc[:, :, j] * w[..., None]  # K is not scaled, fw.py:100
@@ -99,7 +104,7 @@ def _log_decay_matrix(gates: ChunkGates):
     return logd.masked_fill(~keep, float("-inf"))
 
 
-def intra_chunk_outputs(q, k, v, gates: ChunkGates, C, n, m, scale: float, eps: float):
+def intra_chunk_outputs(q, k, v, gates: ChunkGates, C, n, m, scale: float, eps: float, siging=False):
     """fw.py:131-221.  C/n/m are the states entering each chunk (first NC entries)."""
     B, NH, S, DK = q.shape
     DV = v.shape[-1]
@@ -111,6 +116,8 @@ def intra_chunk_outputs(q, k, v, gates: ChunkGates, C, n, m, scale: float, eps: 
     m_intra = logd.amax(dim=-1)  # fw.py:178-180
     m_inter = gates.b + m[:, :, :NC, None]  # fw.py:183
     m_tok = torch.maximum(m_inter, m_intra)  # fw.py:184
+    if siging:  # denominator becomes max(|n|, 1): parallel/native_siging/fw.py:62-66
+        m_tok = torch.zeros_like(m_tok)
     d = torch.exp(logd - m_tok[..., None])  # fw.py:189-190
     s = torch.einsum("bhctd,bhcsd->bhcts", qc, kc) * scale  # fw.py:192
     p = s * d  # fw.py:194
@@ -122,22 +129,22 @@ def intra_chunk_outputs(q, k, v, gates: ChunkGates, C, n, m, scale: float, eps: 
     return h.reshape(B, NH, S, DV), n_tok.reshape(B, NH, S), m_tok.reshape(B, NH, S)
 
 
-def chunkwise_fw(q, k, v, i, f, c0=None, n0=None, m0=None, chunk_size=64, eps=1e-6, scale=None):
+def chunkwise_fw(q, k, v, i, f, c0=None, n0=None, m0=None, chunk_size=64, eps=1e-6, scale=None, siging=False):
     """mlstm_chunkwise_fw, fw.py:224-318.
 
     Returns h, n_out, m_out, (C_last, n_last, m_last), (C_all, n_all, m_all).
     """
     B, NH, S, DK = q.shape
     scale = DK ** -0.5 if scale is None else scale
-    gates = chunk_gates(i, f, chunk_size)
-    C, n, m = inter_chunk_states(k, v, gates, c0, n0, m0)
-    h, n_tok, m_tok = intra_chunk_outputs(q, k, v, gates, C, n, m, scale, eps)
+    gates = chunk_gates(i, f, chunk_size, siging)
+    C, n, m = inter_chunk_states(k, v, gates, c0, n0, m0, siging)
+    h, n_tok, m_tok = intra_chunk_outputs(q, k, v, gates, C, n, m, scale, eps, siging)
     last = (C[:, :, -1], n[:, :, -1], m[:, :, -1:])
     return h, n_tok, m_tok, last, (C, n, m)
 
 
 def chunkwise_bw(q, k, v, i, f, dh, n_tok, m_tok, c0=None, n0=None, m0=None, dc_last=None,
-                 chunk_size=64, eps=1e-6, scale=None):
+                 chunk_size=64, eps=1e-6, scale=None, siging=False):
     """mlstm_chunkwise_bw, bw.py:206-348 (n_tok and every m are constants).
 
     Returns dq, dk, dv, di, df, dc0 (dc0 only meaningful when c0 was given).
@@ -147,8 +154,8 @@ def chunkwise_bw(q, k, v, i, f, dh, n_tok, m_tok, c0=None, n0=None, m0=None, dc_
     L = chunk_size
     NC = S // L
     scale = DK ** -0.5 if scale is None else scale
-    gates = chunk_gates(i, f, L)
-    C, _, m = inter_chunk_states(k, v, gates, c0, n0, m0)  # bw.py:251-266 (recompute)
+    gates = chunk_gates(i, f, L, siging)
+    C, _, m = inter_chunk_states(k, v, gates, c0, n0, m0, siging)  # bw.py:251-266 (recompute)
 
     qc = q.reshape(B, NH, NC, L, DK)
     kc = k.reshape(B, NH, NC, L, DK)
@@ -189,6 +196,8 @@ def chunkwise_bw(q, k, v, i, f, dh, n_tok, m_tok, c0=None, n0=None, m0=None, dc_
     dfbar = acc.flip(-1).cumsum(-1).flip(-1)
     df = dfbar * torch.sigmoid(-f)
     di = (v * dv_).sum(dim=-1)
+    if siging:  # chain rule through logsigmoid(i): chunkwise_gates.py:97-98, parallel/native_siging/bw.py
+        di = di * torch.sigmoid(-i)
     return dq_, dk_, dv_, di, df, dC[:, :, 0]
 
 
@@ -217,10 +226,10 @@ def step_recurrence(q, k, v, i, f, c0=None, n0=None, m0=None, eps=1e-6):
     return torch.stack(hs, dim=2), (C, n, m[..., None])
 
 
-def fwbw(q, k, v, i, f, dh, c0=None, n0=None, m0=None, dc_last=None, chunk_size=64, eps=1e-6):
+def fwbw(q, k, v, i, f, dh, c0=None, n0=None, m0=None, dc_last=None, chunk_size=64, eps=1e-6, siging=False):
     """Forward followed by the hand-written backward: what one bench 'step' computes."""
-    h, n_tok, m_tok, last, _ = chunkwise_fw(q, k, v, i, f, c0, n0, m0, chunk_size, eps)
-    grads = chunkwise_bw(q, k, v, i, f, dh, n_tok, m_tok, c0, n0, m0, dc_last, chunk_size, eps)
+    h, n_tok, m_tok, last, _ = chunkwise_fw(q, k, v, i, f, c0, n0, m0, chunk_size, eps, siging=siging)
+    grads = chunkwise_bw(q, k, v, i, f, dh, n_tok, m_tok, c0, n0, m0, dc_last, chunk_size, eps, siging=siging)
     return h, last, grads
 
 

@@ -149,8 +149,10 @@ int run(const char* name) {
   return ok ? 0 : 3;
 }
 
-int main() {
+int time_main();
+int main(int argc, char** argv) {
   setvbuf(stdout, NULL, _IONBF, 0);
+  if (argc > 1 && argv[1][0] == 't') return time_main();
   int bad = 0;
   bad += run<128, 128, 64, false, false, false, false>("S=QK^T      M128 N128 K64  A:K  B:K ") != 0;
   bad += run<128, 64, 128, false, true, false, true>("PV          M128 N64  K128 A:K  B:MN +tma_store") != 0;
@@ -164,4 +166,82 @@ int main() {
   bad += run<64, 128, 64, true, true, false, false>("M64 N128    M64  N128 K64  A:MN B:MN") != 0;
   printf("%d variant(s) failed\n", bad);
   return bad ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// timing mode: `umma_probe time` -- cycles per tcgen05.mma for the operand layouts the kernels use
+// (a batch of REP x (K/16) MMAs issued back to back, clock64 from first issue to commit arrival).
+// ------------------------------------------------------------------------------------------
+template <int M, int N, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(128) time_mma(long long* out, int rep) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;                 // 128 x 128 bf16 (two [128][64] subtiles)
+  uint8_t* sB = smem + 2 * 128 * 128;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < 2 * 2 * 128 * 128 / 4; i += 128) ((uint32_t*)smem)[i] = 0x3c003c00u;
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc<256>(&tmem_base_s);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  constexpr int K = 128;
+  if (warp == 0 && elect_one()) {
+    constexpr uint32_t idesc = umma_idesc(M, N, A_MN, B_MN, true);
+    const uint64_t dA = umma_smem_desc(smem_u32(sA), A_MN ? 128 * 128 : 0, 1024);
+    const uint64_t dB = umma_smem_desc(smem_u32(sB), B_MN ? 128 * 128 : 0, 1024);
+    long long t0 = clock64();
+    for (int r = 0; r < rep; ++r) {
+#pragma unroll
+      for (int kk = 0; kk < K / 16; ++kk) {
+        const uint64_t a = umma_desc_advance(dA, A_MN ? kk * 2048 : (kk / 4) * 128 * 128 + (kk % 4) * 32);
+        const uint64_t b = umma_desc_advance(dB, B_MN ? kk * 2048 : (kk / 4) * 128 * 128 + (kk % 4) * 32);
+        umma_f16(tmem, a, b, idesc, true);
+      }
+    }
+    long long t1 = clock64();
+    umma_commit(&bar);
+    mbar_wait(&bar, 0, 7);
+    long long t2 = clock64();
+    out[0] = t1 - t0;
+    out[1] = t2 - t0;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
+template <int M, int N, bool A_MN, bool B_MN>
+void run_time(const char* name) {
+  long long *d, h[2];
+  cudaMalloc(&d, 16);
+  auto kern = time_mma<M, N, A_MN, B_MN>;
+  size_t smem = 4 * 128 * 128 + 2048;
+  cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int rep = 8;
+  for (int it = 0; it < 2; ++it) {
+    kern<<<1, 128, smem>>>(d, rep);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("%s: error %s\n", name, cudaGetErrorString(e)); return; }
+  }
+  cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+  printf("%s: %d MMAs  issue %.1f cyc/MMA   complete %.1f cyc/MMA\n", name, rep * 8, h[0] / (rep * 8.0), h[1] / (rep * 8.0));
+  cudaFree(d);
+}
+
+int time_main() {
+  run_time<128, 128, false, false>("M128 N128 A:K  B:K ");
+  run_time<128, 64, false, false>("M128 N64  A:K  B:K ");
+  run_time<128, 64, false, true>("M128 N64  A:K  B:MN");
+  run_time<128, 64, true, true>("M128 N64  A:MN B:MN");
+  run_time<128, 64, true, false>("M128 N64  A:MN B:K ");
+  run_time<64, 64, true, true>("M64  N64  A:MN B:MN");
+  run_time<64, 64, false, false>("M64  N64  A:K  B:K ");
+  run_time<128, 128, true, true>("M128 N128 A:MN B:MN");
+  run_time<128, 256, false, false>("M128 N256 A:K  B:K ");
+  return 0;
 }

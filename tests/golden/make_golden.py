@@ -90,8 +90,27 @@ def run_padded():
     print("padded_S100", tuple(h.shape))
 
 
+def run_siging():
+    """Sigmoid-input-gate variant (what the reference's CUDA model path computes, vision_lstm2.py:685-697):
+    quadratic native formulation ``parallel--native_siging_custbw`` (n treated as a constant in the backward,
+    parallel/native_siging/bw.py), float64."""
+    B, NH, S, DK, DV = 1, 2, 192, 16, 32
+    inp = make_inputs(B, NH, S, DK, DV, seed=6, dtype=torch.float64)
+    leaf = {k: inp[k].clone().requires_grad_(True) for k in ("q", "k", "v", "i", "f")}
+    fn = get_mlstm_kernel("parallel--native_siging_custbw")
+    h = fn(q=leaf["q"], k=leaf["k"], v=leaf["v"], i=leaf["i"], f=leaf["f"], eps=1e-6)
+    (h * inp["dh"]).sum().backward()
+    blob = {f"in_{k}": v.numpy() for k, v in inp.items()}
+    blob.update(h=h.detach().numpy(), dq=leaf["q"].grad.numpy(), dk=leaf["k"].grad.numpy(),
+                dv=leaf["v"].grad.numpy(), di=leaf["i"].grad.numpy(), df=leaf["f"].grad.numpy(),
+                meta=np.array([B, NH, S, DK, DV, 64, 0, 6]))
+    np.savez_compressed(os.path.join(HERE, "siging_S192.npz"), **blob)
+    print("siging_S192", tuple(h.shape))
+
+
 if __name__ == "__main__":
     torch.set_default_dtype(torch.float64)  # reference allocates its state buffers in the input dtype anyway
     for name, cfg in CASES.items():
         run_case(name, *cfg)
     run_padded()
+    run_siging()

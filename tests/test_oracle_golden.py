@@ -21,10 +21,10 @@ def _load(path):
 
 
 def test_golden_files_present():
-    assert len(GOLD) >= 6
+    assert len(GOLD) >= 7
 
 
-@pytest.mark.parametrize("path", [p for p in GOLD if "padded" not in p], ids=os.path.basename)
+@pytest.mark.parametrize("path", [p for p in GOLD if "padded" not in p and "siging" not in p], ids=os.path.basename)
 def test_oracle_matches_reference(path):
     d, meta = _load(path)
     st = meta["with_states"]
@@ -64,6 +64,20 @@ def test_oracle_matches_reference_padded():
     grads = O.chunkwise_bw(q, k, v, i, f, dh, n_tok, m_tok)
     for name, g in zip(("dq", "dk", "dv", "di", "df"), grads):
         assert O.rel_err(g[:, :, :S], d[name]) < TOL, name
+
+
+@pytest.mark.parametrize("L", [32, 64])
+def test_oracle_matches_reference_siging(L):
+    """Sigmoid-input-gate variant vs the reference's quadratic native_siging_custbw (any chunk size)."""
+    (path,) = [p for p in GOLD if "siging" in p]
+    d, meta = _load(path)
+    h, n_tok, m_tok, _, _ = O.chunkwise_fw(d["in_q"], d["in_k"], d["in_v"], d["in_i"], d["in_f"], chunk_size=L, siging=True)
+    assert O.rel_err(h, d["h"]) < TOL
+    assert float(m_tok.abs().max()) == 0.0
+    grads = O.chunkwise_bw(d["in_q"], d["in_k"], d["in_v"], d["in_i"], d["in_f"], d["in_dh"], n_tok, m_tok, chunk_size=L,
+                           siging=True)
+    for name, g in zip(("dq", "dk", "dv", "di", "df"), grads):
+        assert O.rel_err(g, d[name]) < TOL, name
 
 
 @pytest.mark.parametrize("L", [16, 32, 64])

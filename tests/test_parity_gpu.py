@@ -14,7 +14,7 @@ from oracle import mlstm_oracle as O
 pytestmark = pytest.mark.gpu
 
 TOL = {torch.float32: 1e-5, torch.bfloat16: 2e-2, torch.float16: 2e-2}
-GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if "siging" not in p)
 IMPLS = ["exact", "auto"]
 
 
@@ -238,6 +238,40 @@ def test_reverse_direction_equals_flipped_oracle(pkg, dtype, states):
     if states:
         assert O.rel_err(c_last.double().cpu(), want["c_last"]) < tol
         assert O.rel_err(c0.grad.double().cpu(), want["dc0"]) < tol
+
+
+@pytest.mark.parametrize("dtype,shape", [(torch.float32, (1, 2, 192, 16, 32)), (torch.float32, (2, 2, 256, 64, 64)),
+                                         (torch.bfloat16, (2, 4, 320, 64, 64)), (torch.bfloat16, (1, 2, 256, 128, 128))],
+                         ids=["fp32-rect", "fp32-d64", "bf16-d64-tensor", "bf16-d128"])
+def test_siging_variant(pkg, dtype, shape):
+    """Sigmoid-input-gate variant (the reference's CUDA model default) vs the oracle, which is pinned
+    against parallel--native_siging_custbw (tests/golden/siging_S192.npz)."""
+    inp = O.make_inputs(*shape, seed=70, dtype=torch.float32)
+    t = {k: v.to(dtype).cuda() for k, v in inp.items()}
+    leaves = {k: t[k].detach().requires_grad_(True) for k in ("q", "k", "v", "i", "f")}
+    h, (c_last, n_last) = pkg.mlstm_siging_chunkwise__b200(**leaves, return_last_states=True,
+                                                          autocast_kernel_dtype=torch.float32)
+    h.backward(t["dh"])
+    torch.cuda.synchronize()
+    r = {k: v.to(dtype).double() for k, v in inp.items()}
+    hw, last, grads = O.fwbw(r["q"], r["k"], r["v"], r["i"], r["f"], r["dh"], siging=True)
+    got = dict(h=h, dq=leaves["q"].grad, dk=leaves["k"].grad, dv=leaves["v"].grad, di=leaves["i"].grad, df=leaves["f"].grad,
+               c_last=c_last, n_last=n_last)
+    want = dict(h=hw, dq=grads[0], dk=grads[1], dv=grads[2], di=grads[3], df=grads[4], c_last=last[0], n_last=last[1])
+    _assert_close({k: v.detach().double().cpu() for k, v in got.items()}, want, TOL[dtype], f"siging {dtype} {shape}")
+
+
+def test_siging_golden_fp32(pkg):
+    """CUDA fp32 siging path vs the vector produced by the reference itself."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "siging_S192.npz"))
+    t = {k[3:]: torch.from_numpy(z[k]).float().cuda() for k in z.files if k.startswith("in_")}
+    leaves = {k: t[k].detach().requires_grad_(True) for k in ("q", "k", "v", "i", "f")}
+    h = pkg.mlstm_siging_chunkwise__b200(**leaves, autocast_kernel_dtype=torch.float32)
+    h.backward(t["dh"])
+    torch.cuda.synchronize()
+    got = dict(h=h, dq=leaves["q"].grad, dk=leaves["k"].grad, dv=leaves["v"].grad, di=leaves["i"].grad, df=leaves["f"].grad)
+    _assert_close({k: v.detach().double().cpu() for k, v in got.items()}, {k: torch.from_numpy(z[k]) for k in got}, 1e-5,
+                  "siging golden")
 
 
 def test_host_pipeline_matches_device_path(pkg):

@@ -17,6 +17,7 @@ from .backend import (  # noqa: F401
     mlstm_chunkwise__b200,
     mlstm_chunkwise_bw,
     mlstm_chunkwise_fw,
+    mlstm_siging_chunkwise__b200,
     patch_model,
     register,
     set_default_impl,

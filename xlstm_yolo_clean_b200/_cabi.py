@@ -34,7 +34,7 @@ class Tensor(C.Structure):
 class Shape(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("NH", C.c_int32), ("S", C.c_int32), ("DHQK", C.c_int32), ("DHHV", C.c_int32),
-        ("chunk_size", C.c_int32), ("dtype", C.c_int32), ("impl", C.c_int32), ("reverse", C.c_int32),
+        ("chunk_size", C.c_int32), ("dtype", C.c_int32), ("impl", C.c_int32), ("reverse", C.c_int32), ("siging", C.c_int32),
         ("eps", C.c_float), ("qk_scale", C.c_float),
     ]
 

@@ -56,7 +56,7 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
-def _shape(q, v, chunk_size, eps, impl, qk_scale=None, reverse=False) -> _cabi.Shape:
+def _shape(q, v, chunk_size, eps, impl, qk_scale=None, reverse=False, siging=False) -> _cabi.Shape:
     B, NH, S, DK = q.shape
     s = _cabi.Shape()
     s.B, s.NH, s.S, s.DHQK, s.DHHV = B, NH, S, DK, v.shape[-1]
@@ -64,6 +64,7 @@ def _shape(q, v, chunk_size, eps, impl, qk_scale=None, reverse=False) -> _cabi.S
     s.dtype = _DTYPES[q.dtype]
     s.impl = _default_impl if impl is None else impl
     s.reverse = 1 if reverse else 0
+    s.siging = 1 if siging else 0
     s.eps = float(eps)
     s.qk_scale = -1.0 if qk_scale is None else float(qk_scale)
     return s
@@ -99,7 +100,7 @@ def _state_f32(t, shape):
 
 
 def mlstm_chunkwise_fw(q, k, v, i, f, c_initial=None, n_initial=None, m_initial=None, qk_scale=None,
-                       return_last_states=False, chunk_size=64, eps=1e-6, impl=None, save_states=True, reverse=False):
+                       return_last_states=False, chunk_size=64, eps=1e-6, impl=None, save_states=True, reverse=False, siging=False):
     """C-ABI forward.  Returns h, n_out, m_out, last_states-or-None (fp32), c_states-or-None.
 
     ``c_states`` is the opaque per-tile state buffer the tensor-core backward consumes (the
@@ -131,7 +132,7 @@ def mlstm_chunkwise_fw(q, k, v, i, f, c_initial=None, n_initial=None, m_initial=
                     torch.empty(B, NH, DK, dtype=torch.float32, device=dev),
                     torch.empty(B, NH, 1, dtype=torch.float32, device=dev))
         a = _cabi.FwArgs()
-        a.shape = _shape(q, v, chunk_size, eps, impl, qk_scale, reverse)
+        a.shape = _shape(q, v, chunk_size, eps, impl, qk_scale, reverse, siging)
         ws_bytes = lib.mlstm_b200_workspace_bytes(C.byref(a.shape), 0)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         st_bytes = lib.mlstm_b200_states_bytes(C.byref(a.shape)) if save_states else 0
@@ -150,7 +151,7 @@ def mlstm_chunkwise_fw(q, k, v, i, f, c_initial=None, n_initial=None, m_initial=
 
 def mlstm_chunkwise_bw(q, k, v, i, f, n_out, m_out, dh, c_initial=None, n_initial=None, m_initial=None,
                        dc_last=None, qk_scale=None, chunk_size=64, eps=1e-6, impl=None, want_dc_initial=False,
-                       c_states=None, reverse=False):
+                       c_states=None, reverse=False, siging=False):
     """C-ABI backward.  Returns dq, dk, dv, di, df, dc_initial-or-None (fp32)."""
     lib = _cabi.load_library()
     _check_inputs(q, k, v, i, f)
@@ -175,7 +176,7 @@ def mlstm_chunkwise_bw(q, k, v, i, f, n_out, m_out, dh, c_initial=None, n_initia
         df = torch.empty(B, NH, S, dtype=q.dtype, device=dev)
         dc0 = torch.empty(B, NH, DK, DV, dtype=torch.float32, device=dev) if want_dc_initial else None
         a = _cabi.BwArgs()
-        a.shape = _shape(q, v, chunk_size, eps, impl, qk_scale, reverse)
+        a.shape = _shape(q, v, chunk_size, eps, impl, qk_scale, reverse, siging)
         ws_bytes = lib.mlstm_b200_workspace_bytes(C.byref(a.shape), 1)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         a.q, a.k, a.v, a.i, a.f, a.dh = (_tensor(t) for t in (q, k, v, i, f, dh))
@@ -197,13 +198,14 @@ def _make_function(autocast_kernel_dtype: torch.dtype):
 
         @staticmethod
         @custom_fwd(device_type="cuda", cast_inputs=autocast_kernel_dtype)
-        def forward(ctx, q, k, v, i, f, c_initial, n_initial, m_initial, return_last_states, chunk_size, eps, reverse):
+        def forward(ctx, q, k, v, i, f, c_initial, n_initial, m_initial, return_last_states, chunk_size, eps, reverse,
+                    siging):
             need_bw = any(ctx.needs_input_grad[:6])
             h, n_out, m_out, last, c_states = mlstm_chunkwise_fw(
                 q, k, v, i, f, c_initial, n_initial, m_initial, return_last_states=return_last_states,
-                chunk_size=chunk_size, eps=eps, save_states=need_bw, reverse=reverse)
+                chunk_size=chunk_size, eps=eps, save_states=need_bw, reverse=reverse, siging=siging)
             ctx.save_for_backward(q, k, v, i, f, c_initial, n_initial, m_initial, n_out, m_out, c_states)
-            ctx.chunk_size, ctx.eps, ctx.reverse = chunk_size, eps, reverse
+            ctx.chunk_size, ctx.eps, ctx.reverse, ctx.siging = chunk_size, eps, reverse, siging
             if last is None:
                 return h, None, None, None
             # native kernels hand states back in the input dtype (native/fw.py:53-62)
@@ -215,13 +217,13 @@ def _make_function(autocast_kernel_dtype: torch.dtype):
             q, k, v, i, f, c0, n0, m0, n_out, m_out, c_states = ctx.saved_tensors
             dq, dk, dv, di, df, dc0 = mlstm_chunkwise_bw(
                 q, k, v, i, f, n_out, m_out, dh, c0, n0, m0, dc_last=dc_last, chunk_size=ctx.chunk_size, eps=ctx.eps,
-                want_dc_initial=c0 is not None, c_states=c_states, reverse=ctx.reverse)
+                want_dc_initial=c0 is not None, c_states=c_states, reverse=ctx.reverse, siging=ctx.siging)
             # dn_last / dm_last are ignored and dN/dM_initial are zeros, as in native/bw.py:329-337
             return (dq, dk, dv, di, df,
                     None if c0 is None else dc0.to(c0.dtype),
                     None if n0 is None else torch.zeros_like(n0),
                     None if m0 is None else torch.zeros_like(m0),
-                    None, None, None, None)
+                    None, None, None, None, None)
 
     return _MlstmChunkwiseB200
 
@@ -258,14 +260,57 @@ def mlstm_chunkwise__b200(
         raise ValueError(f"Unsupported kernel dtype {autocast_kernel_dtype}.")
     fn = _FUNCTIONS[autocast_kernel_dtype]
     h, c_last, n_last, m_last = fn.apply(q, k, v, i, f, c_initial, n_initial, m_initial, bool(return_last_states),
-                                         int(chunk_size), float(eps), bool(reverse))
+                                         int(chunk_size), float(eps), bool(reverse), False)
     if return_last_states:
         return h, (c_last, n_last, m_last)
     return h
 
 
+def mlstm_siging_chunkwise__b200(
+    q: torch.Tensor,
+    k: torch.Tensor,
+    v: torch.Tensor,
+    i: torch.Tensor,
+    f: torch.Tensor,
+    c_initial: torch.Tensor = None,
+    n_initial: torch.Tensor = None,
+    return_last_states: bool = False,
+    eps: float = 1e-6,
+    normalize: bool = True,
+    chunk_size: int = 64,
+    autocast_kernel_dtype: torch.dtype = torch.bfloat16,
+    reverse: bool = False,
+    **kwargs,
+):
+    """Sigmoid-input-gate variant: drop-in for ``mlstm_siging_chunkwise__xl_chunk``
+    (mlstm_kernels/torch/chunkwise/triton_xl_chunk_siging/fwbw.py:211-268), the kernel the reference's
+    CUDA model path selects (vision_lstm2.py:685-697).  No max state: last states are (C, n).
+    The Triton tile-size kwargs are accepted and ignored.
+    """
+    if not normalize:
+        raise NotImplementedError("normalize=False is not supported by the B200 siging kernel")
+    if autocast_kernel_dtype not in _FUNCTIONS:
+        raise ValueError(f"Unsupported kernel dtype {autocast_kernel_dtype}.")
+    fn = _FUNCTIONS[autocast_kernel_dtype]
+    need_states = c_initial is not None or n_initial is not None
+    m_initial = None
+    if need_states:
+        B, NH = q.shape[:2]
+        m_initial = torch.zeros(B, NH, 1, dtype=q.dtype, device=q.device)
+        if c_initial is None:
+            c_initial = torch.zeros(B, NH, q.shape[-1], v.shape[-1], dtype=q.dtype, device=q.device)
+        if n_initial is None:
+            n_initial = torch.zeros(B, NH, q.shape[-1], dtype=q.dtype, device=q.device)
+    h, c_last, n_last, _ = fn.apply(q, k, v, i, f, c_initial, n_initial, m_initial, bool(return_last_states),
+                                    int(chunk_size), float(eps), bool(reverse), True)
+    if return_last_states:
+        return h, (c_last, n_last)
+    return h
+
+
 def register(name: str = KERNEL_NAME) -> str:
-    """Insert the kernel into the reference registry (mlstm_kernels/torch/chunkwise/__init__.py:9-15).
+    """Insert the kernels into the reference registry (mlstm_kernels/torch/chunkwise/__init__.py:9-15):
+    ``<name>`` (exp input gate, max-state stabilised) and ``<name>_siging`` (sigmoid input gate).
 
     Returns the full kernel name usable as ``mLSTMBackendConfig(chunkwise_kernel=...)``.
     ``mlstm_kernels`` must be importable (it is the reference's package, not part of this repo).
@@ -273,17 +318,22 @@ def register(name: str = KERNEL_NAME) -> str:
     from mlstm_kernels.torch.chunkwise import registry  # noqa: WPS433 (reference package)
 
     registry[name] = mlstm_chunkwise__b200
+    registry[name + "_siging"] = mlstm_siging_chunkwise__b200
     return f"chunkwise--{name}"
 
 
-def patch_model(model: torch.nn.Module, name: str = KERNEL_NAME, mode: str = "train_with_padding") -> int:
+def patch_model(model: torch.nn.Module, name: str = KERNEL_NAME, mode: str = "train_with_padding",
+                siging: bool = False) -> int:
     """Point ``gpu_backend`` of every MatrixLSTMCell (vision_lstm2.py:685-697) at the B200 kernel.
 
+    ``siging=True`` selects the sigmoid-input-gate variant, i.e. the same function the reference's
+    CUDA default (``chunkwise--triton_xl_chunk_siging``) computes, so released weights keep their meaning;
+    the default is the exp-gate / max-state path the reference runs on CPU (SURVEY.md finding 6).
     Returns the number of cells patched.
     """
     from mlstm_kernels.torch.backend_module import mLSTMBackend, mLSTMBackendConfig
 
-    full = register(name)
+    full = register(name) + ("_siging" if siging else "")
     n = 0
     for mod in model.modules():
         if hasattr(mod, "gpu_backend") and hasattr(mod, "cpu_backend"):

@@ -87,7 +87,7 @@ constexpr int kMaxChunk = 128;
 template <typename T>
 __device__ __forceinline__ float chunk_gate_scan(const T* __restrict__ ig, int64_t istride, const T* __restrict__ fg,
                                                  int64_t fstride, int L, int n_valid, float* sb, float* si,
-                                                 float* spm, float* amax_rel) {
+                                                 float* spm, float* amax_rel, bool siging = false) {
   const int lane = threadIdx.x & 31;
   const int E = (L + 31) >> 5;  // consecutive tokens per lane (<= 4)
   float lf[kMaxChunk / 32], iv[kMaxChunk / 32];
@@ -101,6 +101,7 @@ __device__ __forceinline__ float chunk_gate_scan(const T* __restrict__ ig, int64
       if (t < L && t < n_valid) {
         lf[e] = logsigmoid_f32(to_f32<T>(fg[(int64_t)t * fstride]));
         iv[e] = to_f32<T>(ig[(int64_t)t * istride]);
+        if (siging) iv[e] = logsigmoid_f32(iv[e]);  // sigmoid input gate (chunkwise_gates.py:34)
       }
       run += lf[e];
       lf[e] = run;  // lane-local inclusive prefix

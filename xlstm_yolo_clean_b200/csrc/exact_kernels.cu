@@ -49,6 +49,7 @@ struct ExactParams {
   float* dc0;
   int DVT;  // dv slice width of the recurrent kernels
   int rev;  // 1: anti-causal scan -- processing index t lives at memory token S-1-t (no data is moved)
+  int sig;  // 1: sigmoid input gate, every max state is 0 (siging variant)
 };
 // memory token of processing index t, and the signed token step
 __device__ __forceinline__ int64_t tok(const ExactParams& p, int64_t t) { return p.rev ? (int64_t)p.S - 1 - t : t; }
@@ -141,12 +142,12 @@ __global__ void __launch_bounds__(kThreads) k_states(ExactParams p) {
     if (threadIdx.x < 32) {
       float amax;
       float g = chunk_gate_scan<T>(ip + m0 * p.ig.ss, sg * p.ig.ss, fp + m0 * p.fg.ss, sg * p.fg.ss, L, L, sb, si,
-                                   spm, &amax);
+                                   spm, &amax, p.sig != 0);
       if (threadIdx.x == 0) { s_g = g; s_amax = amax; }
     }
     __syncthreads();
     const float g = s_g;
-    const float m_next = fmaxf(g + m, g + s_amax);        // fw.py:96-98
+    const float m_next = p.sig ? 0.f : fmaxf(g + m, g + s_amax);  // fw.py:96-98
     const float decay = expf(g + m - m_next);             // fw.py:106
     for (int t = threadIdx.x; t < L; t += blockDim.x) sw[t] = expf(g - sb[t] + si[t] - m_next);  // fw.py:102
     __syncthreads();
@@ -225,10 +226,11 @@ __global__ void __launch_bounds__(kThreads) k_fw_h(ExactParams p) {
   if (threadIdx.x < 32) {
     float amax;
     chunk_gate_scan<T>((const T*)p.ig.ptr + b * p.ig.sb + hh * p.ig.sh + t0 * p.ig.ss, sg * p.ig.ss,
-                       (const T*)p.fg.ptr + b * p.fg.sb + hh * p.fg.sh + t0 * p.fg.ss, sg * p.fg.ss, L, L, sb, si, spm, &amax);
+                       (const T*)p.fg.ptr + b * p.fg.sb + hh * p.fg.sh + t0 * p.fg.ss, sg * p.fg.ss, L, L, sb, si, spm, &amax, p.sig != 0);
   }
   __syncthreads();
-  for (int t = threadIdx.x; t < L; t += blockDim.x) smt[t] = sb[t] + fmaxf(m_prev, spm[t]);  // fw.py:178-184
+  for (int t = threadIdx.x; t < L; t += blockDim.x)
+    smt[t] = p.sig ? 0.f : sb[t] + fmaxf(m_prev, spm[t]);  // fw.py:178-184
   __syncthreads();
 
   {  // P = (Q K^T * scale) . D, fw.py:171-194
@@ -326,7 +328,7 @@ __global__ void __launch_bounds__(kThreads) k_bw_dc(ExactParams p) {
     load_tile<T>(sH, ldv, hp + t0 * p.dh.ss, sg * p.dh.ss, L, DVT);
     if (threadIdx.x < 32) {
       float amax;
-      float g = chunk_gate_scan<T>(ip + t0 * p.ig.ss, sg * p.ig.ss, fp + t0 * p.fg.ss, sg * p.fg.ss, L, L, sb, si, spm, &amax);
+      float g = chunk_gate_scan<T>(ip + t0 * p.ig.ss, sg * p.ig.ss, fp + t0 * p.fg.ss, sg * p.fg.ss, L, L, sb, si, spm, &amax, p.sig != 0);
       if (threadIdx.x == 0) s_g = g;
     }
     __syncthreads();
@@ -408,7 +410,7 @@ __global__ void __launch_bounds__(kThreads) k_bw_dqkv(ExactParams p) {
     float amax;
     float g = chunk_gate_scan<T>((const T*)p.ig.ptr + b * p.ig.sb + hh * p.ig.sh + t0 * p.ig.ss, sg * p.ig.ss,
                                  (const T*)p.fg.ptr + b * p.fg.sb + hh * p.fg.sh + t0 * p.fg.ss, sg * p.fg.ss, L, L, sb, si,
-                                 spm, &amax);
+                                 spm, &amax, p.sig != 0);
     if (threadIdx.x == 0) s_g = g;
   }
   __syncthreads();
@@ -480,6 +482,7 @@ __global__ void __launch_bounds__(kThreads) k_bw_dqkv(ExactParams p) {
     for (int s = threadIdx.x; s < L; s += blockDim.x) {
       float r = 0.f;
       for (int x = 0; x < NS; ++x) r += spart[s * 32 + x];
+      if (p.sig) r *= 1.f - expf(si[s]);  // d logsigmoid(i)/di = sigmoid(-i) = 1 - exp(logsigmoid(i))
       dip[(int64_t)s * sg * p.di_s[2]] = from_f32<T>(r);
     }
     __syncthreads();
@@ -714,6 +717,7 @@ int exact_fw(const mlstm_b200_fw_args& a, cudaStream_t st) {
   p.c_last = a.c_last; p.n_last = a.n_last; p.m_last = a.m_last;
   p.DVT = pick_dvt(s);
   p.rev = s.reverse ? 1 : 0;
+  p.sig = s.siging ? 1 : 0;
   MLSTM_DISPATCH_DTYPE(s.dtype, T, {
     if (int e = launch_states<T>(p, st)) return e;
     size_t sm = smem_fw_h(L, p.DK, p.DV);
@@ -753,6 +757,7 @@ int exact_bw(const mlstm_b200_bw_args& a, cudaStream_t st) {
   p.dc0 = a.dc_initial;
   p.DVT = pick_dvt(s);
   p.rev = s.reverse ? 1 : 0;
+  p.sig = s.siging ? 1 : 0;
   MLSTM_DISPATCH_DTYPE(s.dtype, T, {
     if (int e = launch_states<T>(p, st)) return e;  // recompute C/n/m states (bw.py:251-266)
     size_t sm = smem_bw_dc(L, p.DK, p.DVT);

@@ -158,7 +158,7 @@ __device__ __forceinline__ float warp_incl_max_dir(float v, int lane, bool rev) 
 // `rev`: anti-causal direction -- the cumulative sums / maxima run from the END of the tile
 // (suffix scans over the memory rows), everything else is unchanged.
 template <typename T>
-__device__ __noinline__ void gate_scan_regs(float* gb, const GateRaw<T>& r, bool rev) {
+__device__ __noinline__ void gate_scan_regs(float* gb, const GateRaw<T>& r, bool rev, bool siging) {
   const int lane = threadIdx.x & 31;
   float lf[4], iv[4], fv[4];
   float run = 0.f;
@@ -168,6 +168,7 @@ __device__ __noinline__ void gate_scan_regs(float* gb, const GateRaw<T>& r, bool
     const bool ok = lane * 4 + e < r.n_valid;
     fv[e] = ok ? to_f32<T>(r.f[e]) : INFINITY;
     iv[e] = ok ? to_f32<T>(r.i[e]) : -INFINITY;
+    if (siging) iv[e] = ok ? logsigmoid_fast(iv[e]) : -INFINITY;  // sigmoid input gate
     run += logsigmoid_fast(fv[e]);
     lf[e] = run;
   }
@@ -223,6 +224,7 @@ struct TcFwParams {
   float *n_out, *m_out;
   float *c_last, *n_last, *m_last;
   int rev;           // 1: anti-causal direction (tiles walked from the end, mirrored in-tile mask)
+  int sig;           // 1: sigmoid input gate, all max states are 0 (siging variant)
   int store_states;  // 1: TMA-store the bf16 copy of C entering every tile (consumed by the backward)
   long long* prof;   // debug: per-tile phase clocks of CTA 0 (mlstm_b200_debug_set_clock_buffer)
 };
@@ -424,7 +426,7 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
     GateRaw<T> raw = raw_of(0);
     for (int n = 0; n < p.NT; ++n) {  // vectors of tile n; tiles 0 and 1 need no buffer hand-back
       if (n >= 2) named_sync(NB_C, kNbC);  // every worker is done with tile n-2: its gate buffer can be reused
-      gate_scan_regs(fsm + SM::fGates + (n & 1) * GateBuf::kFloats, raw, REV);
+      gate_scan_regs(fsm + SM::fGates + (n & 1) * GateBuf::kFloats, raw, REV, p.sig != 0);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_g[n & 1]);
       if (n + 1 < p.NT) raw = raw_of(n + 1);  // stays in flight until the next hand-back
@@ -452,10 +454,10 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       TC_PROF(c, 0);
       mbar_wait(&bar_g[pb], (c >> 1) & 1, 2);
       const float g = gb[GateBuf::oScal], amax = gb[GateBuf::oScal + 1];
-      const float m_next = fmaxf(g + m_run, g + amax);                  // fw.py:96-98
+      const float m_next = p.sig ? 0.f : fmaxf(g + m_run, g + amax);    // fw.py:96-98
       const float gbar = __expf(g + m_run - m_next);                    // fw.py:106
       const float b_t = gb[GateBuf::oB + row], i_t = gb[GateBuf::oI + row];
-      const float m_t = b_t + fmaxf(m_run, gb[GateBuf::oPm + row]);     // fw.py:178-184
+      const float m_t = p.sig ? 0.f : b_t + fmaxf(m_run, gb[GateBuf::oPm + row]);  // fw.py:178-184
       mbar_wait(&bar_full[s], par_full, 3);
       if (c > 0) mbar_wait(&bar_n, (c - 1) & 1, 4);  // n_{k-1} finalised
       // ---- partial q . n_{k-1} over this thread's 32 columns ---------------------------------------
@@ -629,6 +631,7 @@ struct TcBwParams {
   int64_t di_sb, di_sh, di_ss, df_sb, df_sh, df_ss;
   float* dc0;
   int rev;  // 1: the forward ran anti-causally; this sweep then walks the memory tiles in ascending order
+  int sig;  // 1: sigmoid input gate (m_out is all zeros, dI picks up sigmoid(-i))
   long long* prof;
 };
 
@@ -865,7 +868,7 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       return r;
     };
     auto publish = [&](float* gb, const TileRaw& r) {
-      gate_scan_regs(gb, r.g, REV);
+      gate_scan_regs(gb, r.g, REV, p.sig != 0);
       reinterpret_cast<float4*>(gb + GateBuf::oMt)[lane] = r.mt;
       reinterpret_cast<float4*>(gb + GateBuf::oNt)[lane] = r.nt;
       if (lane == 0) {
@@ -925,7 +928,8 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
         for (int e = 0; e < 4; ++e) {
           const int t = lane * 4 + e;
           if (t < n_valid) {
-            dip[(int64_t)(t0 + t) * p.di_ss] = from_f32<T>(di[e]);
+            const float dsig = p.sig ? 1.f - __expf(gb[GateBuf::oI + t]) : 1.f;  // sigmoid(-i) = 1 - exp(logsigmoid(i))
+            dip[(int64_t)(t0 + t) * p.di_ss] = from_f32<T>(di[e] * dsig);
             dfp[(int64_t)(t0 + t) * p.df_ss] =
                 from_f32<T>((acc[e] + excl) * sigmoid_neg_f32(gb[GateBuf::oF + t]));  // bw.py:322-323
           }
@@ -1194,6 +1198,7 @@ int run_fw(const mlstm_b200_fw_args& a, void* c_states, cudaStream_t st) {
   p.n_out = a.n_out; p.m_out = a.m_out;
   p.c_last = a.c_last; p.n_last = a.n_last; p.m_last = a.m_last;
   p.rev = s.reverse ? 1 : 0;
+  p.sig = s.siging ? 1 : 0;
   p.store_states = c_states != nullptr;
   p.prof = g_prof;
   if (s.dtype == MLSTM_B200_BF16) return launch_fw_d64<__nv_bfloat16>(p, mq, mk, mv, mh, mcs, st);
@@ -1280,6 +1285,7 @@ int tensor_bw(const mlstm_b200_bw_args& a, cudaStream_t st) {
   p.df = a.df.ptr; p.df_sb = a.df.stride[0]; p.df_sh = a.df.stride[1]; p.df_ss = a.df.stride[2];
   p.dc0 = a.dc_initial;
   p.rev = s.reverse ? 1 : 0;
+  p.sig = s.siging ? 1 : 0;
   p.prof = g_prof ? g_prof + 4096 : nullptr;
   if (s.dtype == MLSTM_B200_BF16) {
     auto kern = p.rev ? tc_bw_d64<__nv_bfloat16, true> : tc_bw_d64<__nv_bfloat16, false>;
