@@ -56,10 +56,10 @@ int require_device() {
   return 0;
 }
 
-bool use_tensor(const mlstm_b200_shape& s, int* err) {
+bool use_tensor(const mlstm_b200_shape& s, int backward, int* err) {
   *err = 0;
   if (s.impl == MLSTM_B200_IMPL_EXACT) return false;
-  bool ok = tensor_supported(s);
+  bool ok = tensor_supported(s, backward);
   if (s.impl == MLSTM_B200_IMPL_TENSOR && !ok) {
     set_error("tensor-core path does not cover dtype=%d DHQK=%d DHHV=%d chunk=%d", s.dtype, s.DHQK, s.DHHV,
               s.chunk_size);
@@ -85,19 +85,19 @@ void mlstm_b200_debug_set_clock_buffer(void* dev_ptr) { tensor_set_clock_buffer(
 
 int mlstm_b200_tensor_path_supported(const mlstm_b200_shape* shape) {
   if (!shape) return 0;
-  return tensor_supported(*shape) ? 1 : 0;
+  return (tensor_supported(*shape, 0) && tensor_supported(*shape, 1)) ? 1 : 0;
 }
 
 size_t mlstm_b200_states_bytes(const mlstm_b200_shape* shape) {
   if (!shape) return 0;
   int err = 0;
-  return use_tensor(*shape, &err) ? tensor_states_bytes(*shape) : 0;
+  return use_tensor(*shape, 1, &err) ? tensor_states_bytes(*shape) : 0;
 }
 
 size_t mlstm_b200_workspace_bytes(const mlstm_b200_shape* shape, int backward) {
   if (!shape) return 0;
   int err = 0;
-  size_t n = use_tensor(*shape, &err) ? tensor_workspace_bytes(*shape, backward)
+  size_t n = use_tensor(*shape, backward, &err) ? tensor_workspace_bytes(*shape, backward)
                                       : exact_workspace_bytes(*shape, backward);
   return n < 256 ? 256 : n;
 }
@@ -131,7 +131,7 @@ int mlstm_b200_chunkwise_fw(const mlstm_b200_fw_args* a, void* stream) {
   }
   if (int e = require_device()) return e;
   int err = 0;
-  bool tc = use_tensor(a->shape, &err);
+  bool tc = use_tensor(a->shape, 0, &err);
   if (err) return err;
   return tc ? tensor_fw(*a, (cudaStream_t)stream) : exact_fw(*a, (cudaStream_t)stream);
 }
@@ -169,7 +169,7 @@ int mlstm_b200_chunkwise_bw(const mlstm_b200_bw_args* a, void* stream) {
   }
   if (int e = require_device()) return e;
   int err = 0;
-  bool tc = use_tensor(a->shape, &err);
+  bool tc = use_tensor(a->shape, 1, &err);
   if (err) return err;
   return tc ? tensor_bw(*a, (cudaStream_t)stream) : exact_bw(*a, (cudaStream_t)stream);
 }

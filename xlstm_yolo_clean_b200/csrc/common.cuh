@@ -154,7 +154,7 @@ size_t exact_workspace_bytes(const mlstm_b200_shape& s, int backward);
 int exact_fw(const mlstm_b200_fw_args& a, cudaStream_t st);
 int exact_bw(const mlstm_b200_bw_args& a, cudaStream_t st);
 
-bool tensor_supported(const mlstm_b200_shape& s);
+bool tensor_supported(const mlstm_b200_shape& s, int backward);
 size_t tensor_workspace_bytes(const mlstm_b200_shape& s, int backward);
 size_t tensor_states_bytes(const mlstm_b200_shape& s);
 void tensor_set_clock_buffer(void* dev_ptr);

@@ -608,6 +608,354 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
 }
 
 // =============================================================================================
+// Forward, head dim 128 (640-base384.yaml: NH=6, DH=128; the inference config of BASELINE.json).
+// Same algorithm and warp roles as tc_fw_d64; differences: every Q/K/V/H/C tile is two [128][64]
+// swizzled sub-tiles (column halves), dC = Kbar^T V is M128 N128 so C lives in the plain TMEM
+// lane == row layout (every worker thread owns C[row][64 columns] in 64 registers), shared memory
+// (192 KB of tiles) leaves room for ONE Q/K/V stage and S is single-buffered in TMEM (4 x 128 columns).
+// =============================================================================================
+struct FwSmem128 {
+  static constexpr int D = 128;
+  static constexpr int kTile = LT * 128;      // one [128][64] sub-tile
+  static constexpr int oQ = 0, oK = 2 * kTile, oV = 4 * kTile;
+  static constexpr int oKb = 6 * kTile;       // abar . K
+  static constexpr int oP = 8 * kTile;        // P (two K-halves); the h staging tile aliases it
+  static constexpr int oC = 10 * kTile;       // bf16 copy of C: [128 dqk rows][128 dv cols]
+  static constexpr int oSmall = 12 * kTile;
+  // floats: gates[2], srs[2][2][LT], sqn[2][2][LT], npart[2][4][D], sN[2][D]
+  static constexpr int fGates = 0, fRs = 2 * GateBuf::kFloats, fQn = fRs + 4 * LT, fNp = fQn + 4 * LT,
+                       fN = fNp + 8 * D, kSmallFloats = fN + 2 * D;
+  static constexpr int kBytes = oSmall + kSmallFloats * 4 + 1024;
+  static constexpr uint32_t kLoadBytes = 6 * kTile;
+};
+
+template <typename T, bool REV>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_fw_d128(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+           const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapH, TcFwParams p) {
+  constexpr int D = 128;
+  constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
+  using SM = FwSmem128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* fsm = (float*)(smem + SM::oSmall);
+  uint8_t* sQ = smem + SM::oQ;
+  uint8_t* sK = smem + SM::oK;
+  uint8_t* sV = smem + SM::oV;
+  uint8_t* sKb = smem + SM::oKb;
+  uint8_t* sP = smem + SM::oP;
+  uint8_t* sH = sP;
+  uint8_t* sC = smem + SM::oC;
+  __shared__ uint64_t bar_full, bar_s, bar_dc, bar_h, bar_g[2], bar_n;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int bh = blockIdx.x, b = bh / p.NH, hh = bh % p.NH;
+
+  if (tid == 0) {
+    mbar_init(&bar_full, 1);
+    mbar_init(&bar_s, 1);
+    mbar_init(&bar_dc, 1);
+    mbar_init(&bar_h, 1);
+    mbar_init(&bar_g[0], 1);
+    mbar_init(&bar_g[1], 1);
+    mbar_init(&bar_n, D);
+    fence_mbar_init();
+  }
+  if (warp == kCtlWarp) {
+    tmem_alloc<512>(&tmem_base_s);
+    if (lane == 0) {
+      prefetch_tmap(&mapQ); prefetch_tmap(&mapK); prefetch_tmap(&mapV); prefetch_tmap(&mapH);
+    }
+  }
+  const int rb = warp & 3, ch = (warp >> 2) & 1;
+  const int row = rb * 32 + lane;  // tile row == TMEM lane; also the dqk row of C this thread owns
+  const uint32_t lane_base = (uint32_t)(rb * 32) << 16;
+  float Creg[64];                  // C[row][64*ch .. 64*ch+63], fp32 master copy
+#pragma unroll
+  for (int j = 0; j < 64; ++j) Creg[j] = 0.f;
+  if (warp < kCtlWarp) {
+    if (p.c0) {
+      const float* src = p.c0 + ((int64_t)bh * D + row) * D + ch * 64;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) Creg[j] = src[j];
+    }
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      float t32[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) t32[j] = Creg[hf * 32 + j];
+      store_row32<T>(sC, row, ch * 64 + hf * 32, t32);
+    }
+    if (tid < D) fsm[SM::fN + tid] = p.n0 ? p.n0[(int64_t)bh * D + tid] : 0.f;
+    fence_proxy_async_smem();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t tS = tmem, tHi = tmem + 128, tHx = tmem + 256, tDC = tmem + 384;
+
+  const T* ip = (const T*)p.ig + b * p.ig_sb + hh * p.ig_sh;
+  const T* fp = (const T*)p.fg + b * p.fg_sb + hh * p.fg_sh;
+  auto mt = [&](int c) { return REV ? p.NT - 1 - c : c; };
+
+  if (warp == kCtlWarp) {
+    // =========================== control warp ===================================================
+    auto load_tile = [&](int c) {
+      mbar_expect_tx(&bar_full, SM::kLoadBytes);
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        tma_load_4d(sQ + hf * SM::kTile, &mapQ, &bar_full, hf * 64, mt(c) * LT, hh, b);
+        tma_load_4d(sK + hf * SM::kTile, &mapK, &bar_full, hf * 64, mt(c) * LT, hh, b);
+        tma_load_4d(sV + hf * SM::kTile, &mapV, &bar_full, hf * 64, mt(c) * LT, hh, b);
+      }
+    };
+    constexpr uint32_t id_kk = umma_idesc(128, 128, false, false, kBf16);  // A K-major, B K-major
+    constexpr uint32_t id_mm = umma_idesc(128, 128, true, true, kBf16);    // A MN-major, B MN-major
+    constexpr uint32_t id_km = umma_idesc(128, 128, false, true, kBf16);   // A K-major, B MN-major
+    const uint64_t dQ = umma_smem_desc(smem_u32(sQ), 0, 1024), dK = umma_smem_desc(smem_u32(sK), 0, 1024);
+    const uint64_t dV = umma_smem_desc(smem_u32(sV), SM::kTile, 1024);
+    const uint64_t dKb = umma_smem_desc(smem_u32(sKb), SM::kTile, 1024);
+    const uint64_t dP = umma_smem_desc(smem_u32(sP), 0, 1024);
+    const uint64_t dC = umma_smem_desc(smem_u32(sC), SM::kTile, 1024);
+    auto issue_s = [&](int c) {  // S(c) = Q K^T
+      mbar_wait(&bar_full, c & 1, 1);
+      tc_fence_after_sync();
+#pragma unroll
+      for (int kk = 0; kk < D / 16; ++kk)
+        umma_f16(tS, umma_desc_advance(dQ, (kk / 4) * SM::kTile + (kk % 4) * 32),
+                 umma_desc_advance(dK, (kk / 4) * SM::kTile + (kk % 4) * 32), id_kk, kk > 0);
+      umma_commit(&bar_s);
+    };
+    if (lane == 0) load_tile(0);
+    __syncwarp();
+    if (elect_one()) issue_s(0);
+    __syncwarp();
+    for (int c = 0; c < p.NT; ++c) {
+      const uint32_t par = c & 1;
+      named_sync(NB_B, kNbAB);  // P(c) written
+      if (elect_one()) {
+        tc_fence_after_sync();
+#pragma unroll
+        for (int kk = 0; kk < LT / 16; ++kk)  // Hintra = P V
+          umma_f16(tHi, umma_desc_advance(dP, (kk / 4) * SM::kTile + (kk % 4) * 32), umma_desc_advance(dV, kk * 2048), id_km,
+                   kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)  // Hinter = Q C_{k-1}
+          umma_f16(tHx, umma_desc_advance(dQ, (kk / 4) * SM::kTile + (kk % 4) * 32), umma_desc_advance(dC, kk * 2048), id_km,
+                   kk > 0);
+        umma_commit(&bar_h);
+      }
+      __syncwarp();
+      named_sync(NB_A, kNbAB);  // Kbar(c) written
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < LT / 16; ++kk)  // dC = Kbar^T V
+          umma_f16(tDC, umma_desc_advance(dKb, kk * 2048), umma_desc_advance(dV, kk * 2048), id_mm, kk > 0);
+        umma_commit(&bar_dc);
+        mbar_wait(&bar_h, par, 8);   // every MMA of this tile has read Q/K/V: refill the single stage
+        mbar_wait(&bar_dc, par, 9);
+        if (c + 1 < p.NT) load_tile(c + 1);
+      }
+      __syncwarp();
+      named_sync(NB_C, kNbC);  // h staged, C_k written
+      if (lane == 0) {
+        tma_store_4d(&mapH, sH, 0, mt(c) * LT, hh, b);
+        tma_store_4d(&mapH, sH + SM::kTile, 64, mt(c) * LT, hh, b);
+        tma_store_commit();
+        tma_store_wait_read<0>();  // the staging tile aliases P: it must be drained before bar_s(c+1) completes
+      }
+      __syncwarp();
+      if (c + 1 < p.NT && elect_one()) issue_s(c + 1);
+      __syncwarp();
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  } else if (warp == kScanWarp) {
+    // =========================== scan warp: gate vectors two tiles ahead ===========================
+    auto raw_of = [&](int c) {
+      const int t1 = mt(c) * LT;
+      return load_gate_raw<T>(ip + (int64_t)t1 * p.ig_ss, p.ig_ss, fp + (int64_t)t1 * p.fg_ss, p.fg_ss, min(LT, p.S - t1));
+    };
+    GateRaw<T> raw = raw_of(0);
+    for (int n = 0; n < p.NT; ++n) {
+      if (n >= 2) named_sync(NB_C, kNbC);
+      gate_scan_regs(fsm + SM::fGates + (n & 1) * GateBuf::kFloats, raw, REV, p.sig != 0);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_g[n & 1]);
+      if (n + 1 < p.NT) raw = raw_of(n + 1);
+    }
+    for (int n = max(p.NT - 2, 0); n < p.NT; ++n) named_sync(NB_C, kNbC);
+  } else {
+    // =========================== worker warps ===================================================
+    float m_run = p.m0 ? p.m0[bh] : 0.f;
+    int cur = 0;
+    for (int c = 0; c < p.NT; ++c) {
+      const int pb = c & 1;
+      const uint32_t par = c & 1;
+      const float* gb = fsm + SM::fGates + pb * GateBuf::kFloats;
+      float* srs = fsm + SM::fRs + pb * 2 * LT;
+      float* sqn = fsm + SM::fQn + pb * 2 * LT;
+      float* snp = fsm + SM::fNp + pb * 4 * D;
+      const float* sNc = fsm + SM::fN + cur * D;
+      float* sNn = fsm + SM::fN + (cur ^ 1) * D;
+      const int t0 = mt(c) * LT;
+      const int n_valid = min(LT, p.S - t0);
+
+      mbar_wait(&bar_g[pb], (c >> 1) & 1, 2);
+      const float g = gb[GateBuf::oScal], amax = gb[GateBuf::oScal + 1];
+      const float m_next = p.sig ? 0.f : fmaxf(g + m_run, g + amax);    // fw.py:96-98
+      const float gbar = __expf(g + m_run - m_next);                    // fw.py:106
+      const float b_t = gb[GateBuf::oB + row], i_t = gb[GateBuf::oI + row];
+      const float m_t = p.sig ? 0.f : b_t + fmaxf(m_run, gb[GateBuf::oPm + row]);  // fw.py:178-184
+      mbar_wait(&bar_full, par, 3);
+      if (c > 0) mbar_wait(&bar_n, (c - 1) & 1, 4);
+      {  // partial q . n_{k-1} over this thread's 64 columns
+        float qn = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 q = *reinterpret_cast<const uint4*>(sQ + ch * SM::kTile + swz128(row, 8 * j));
+          float2 q0 = unpack2<T>(q.x), q1 = unpack2<T>(q.y), q2 = unpack2<T>(q.z), q3 = unpack2<T>(q.w);
+          const float4 n0 = *reinterpret_cast<const float4*>(sNc + ch * 64 + 8 * j);
+          const float4 n1 = *reinterpret_cast<const float4*>(sNc + ch * 64 + 8 * j + 4);
+          qn += q0.x * n0.x + q0.y * n0.y + q1.x * n0.z + q1.y * n0.w + q2.x * n1.x + q2.y * n1.y + q3.x * n1.z + q3.y * n1.w;
+        }
+        sqn[ch * LT + row] = qn;
+      }
+      // ---- P = S . D (causal), row sums -- identical to the d=64 kernel (S is 128 x 128 either way) ----
+      mbar_wait(&bar_s, par, 5);
+      tc_fence_after_sync();
+      {
+        const float x_t = (b_t - m_t) * kLog2e + log2f(p.scale);
+        const float* sy = gb + GateBuf::oY;
+        const float* scf = gb + GateBuf::oCf;
+        float rs = 0.f;
+#pragma unroll 1
+        for (int u = ch; u < 4; u += 2) {
+          float v[32];
+          const bool off_diag = REV ? u > rb : u < rb;
+          if (off_diag) {
+            tmem_ld32(tS + lane_base + u * 32, v);
+            const float r_t = ex2_approx(x_t + gb[GateBuf::oScal + 4 + u]);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 cf = *reinterpret_cast<const float4*>(scf + u * 32 + 4 * j4);
+              v[4 * j4 + 0] *= cf.x * r_t;
+              v[4 * j4 + 1] *= cf.y * r_t;
+              v[4 * j4 + 2] *= cf.z * r_t;
+              v[4 * j4 + 3] *= cf.w * r_t;
+              rs += (v[4 * j4 + 0] + v[4 * j4 + 1]) + (v[4 * j4 + 2] + v[4 * j4 + 3]);
+            }
+          } else if (u == rb) {
+            tmem_ld32(tS + lane_base + u * 32, v);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 y = *reinterpret_cast<const float4*>(sy + u * 32 + 4 * j4);
+              const float yy[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = 4 * j4 + e;
+                float pv = v[j] * ex2_approx(x_t + yy[e]);
+                pv = (REV ? j >= lane : j <= lane) ? pv : 0.f;
+                rs += pv;
+                v[j] = pv;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          }
+          store_row32<T>(sP, row, u * 32, v);
+        }
+        srs[ch * LT + row] = rs;
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      named_arrive(NB_B, kNbAB);
+      {  // Kbar = abar . K (row, 64 columns in two halves); column sums for n
+        const float ab = __expf(g - b_t + i_t - m_next);  // fw.py:102
+#pragma unroll 1
+        for (int hf = 0; hf < 2; ++hf) {
+          float kb[32];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 u = *reinterpret_cast<const uint4*>(sK + ch * SM::kTile + swz128(row, hf * 32 + 8 * j));
+            float2 a0 = unpack2<T>(u.x), a1 = unpack2<T>(u.y), a2 = unpack2<T>(u.z), a3 = unpack2<T>(u.w);
+            kb[8 * j + 0] = a0.x * ab; kb[8 * j + 1] = a0.y * ab; kb[8 * j + 2] = a1.x * ab; kb[8 * j + 3] = a1.y * ab;
+            kb[8 * j + 4] = a2.x * ab; kb[8 * j + 5] = a2.y * ab; kb[8 * j + 6] = a3.x * ab; kb[8 * j + 7] = a3.y * ab;
+          }
+          store_row32<T>(sKb, row, ch * 64 + hf * 32, kb);
+          const float cs = warp_colsum32(kb, lane);
+          snp[rb * D + ch * 64 + hf * 32 + lane] = cs;
+        }
+        fence_proxy_async_smem();
+        named_arrive(NB_A, kNbAB);
+      }
+      // ---- epilogue: h (row, 64 columns in two halves) -----------------------------------------------------
+      mbar_wait(&bar_h, par, 7);
+      tc_fence_after_sync();
+      {
+        const float bq = __expf(b_t + m_run - m_t) * p.scale;                          // fw.py:197-198
+        const float den = bq * (sqn[row] + sqn[LT + row]) + srs[row] + srs[LT + row];  // fw.py:204-206
+        const float nmax = fmaxf(fabsf(den), __expf(-m_t));                            // fw.py:208-210
+        const float inv = 1.f / (nmax + p.eps);
+#pragma unroll 1
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t hi[32], hx[32];
+          tmem_ld32_nowait(tHi + lane_base + ch * 64 + hf * 32, hi);
+          tmem_ld32_nowait(tHx + lane_base + ch * 64 + hf * 32, hx);
+          tmem_ld_wait();
+          float o[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = (__uint_as_float(hi[j]) + bq * __uint_as_float(hx[j])) * inv;  // fw.py:200-212
+          store_row32<T>(sH, row, ch * 64 + hf * 32, o);
+        }
+        if (ch == 0 && row < n_valid) {
+          p.n_out[(int64_t)bh * p.S + t0 + row] = nmax;
+          p.m_out[(int64_t)bh * p.S + t0 + row] = m_t;
+        }
+      }
+      // ---- state update C_k = gbar C_{k-1} + dC (M128 layout: lane == dqk row); n_k -----------------------
+      mbar_wait(&bar_dc, par, 6);
+      tc_fence_after_sync();
+      {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          float v[32], t32[32];
+          tmem_ld32(tDC + lane_base + ch * 64 + hf * 32, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            Creg[hf * 32 + j] = gbar * Creg[hf * 32 + j] + v[j];
+            t32[j] = Creg[hf * 32 + j];
+          }
+          store_row32<T>(sC, row, ch * 64 + hf * 32, t32);  // Q C_{k-1} (bar_h) has finished reading the old copy
+        }
+        if (tid < D) {  // n_k = gbar n_{k-1} + column sums of Kbar (fw.py:116)
+          sNn[tid] = gbar * sNc[tid] + ((snp[tid] + snp[D + tid]) + (snp[2 * D + tid] + snp[3 * D + tid]));
+          mbar_arrive(&bar_n);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      named_arrive(NB_C, kNbC);
+      m_run = m_next;
+      cur ^= 1;
+    }
+    if (p.c_last) {  // final states (fw.py:302-309)
+      float* dst = p.c_last + ((int64_t)bh * D + row) * D + ch * 64;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) dst[j] = Creg[j];
+      if (tid < D) p.n_last[(int64_t)bh * D + tid] = fsm[SM::fN + cur * D + tid];
+      if (tid == 0) p.m_last[bh] = m_run;
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kCtlWarp) tmem_dealloc<512>(tmem);
+}
+
+// =============================================================================================
 // Backward: one reverse sweep per (batch, head) over 128-token tiles (reference native/bw.py).
 // dC lives on chip (fp32 registers + bf16 operand copy); C_{k-1} comes from the forward's
 // c_states.  n_out and every max state are constants (bw.py:44-47).  Per tile:
@@ -1158,6 +1506,17 @@ int launch_fw_d64(const TcFwParams& p, const CUtensorMap& mq, const CUtensorMap&
   return 0;
 }
 
+template <typename T>
+int launch_fw_d128(const TcFwParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
+                   const CUtensorMap& mh, cudaStream_t st) {
+  auto kern = p.rev ? tc_fw_d128<T, true> : tc_fw_d128<T, false>;
+  MLSTM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FwSmem128::kBytes));
+  kern<<<p.B * p.NH, kTcThreads, FwSmem128::kBytes, st>>>(mq, mk, mv, mh, p);
+  count_launch();
+  MLSTM_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 bool tma_ok(const mlstm_b200_tensor& t) {
   return ((uintptr_t)t.ptr & 15) == 0 && t.stride[3] == 1 && (t.stride[0] % 8) == 0 && (t.stride[1] % 8) == 0 &&
          (t.stride[2] % 8) == 0;
@@ -1183,7 +1542,7 @@ int run_fw(const mlstm_b200_fw_args& a, void* c_states, cudaStream_t st) {
   int r = make_map(&mq, a.q, s, s.DHQK) | make_map(&mk, a.k, s, s.DHQK) | make_map(&mv, a.v, s, s.DHHV) |
           make_map(&mh, a.h, s, s.DHHV);
   // without a c_states buffer the map is never used by the kernel; point it at h to keep it valid
-  r |= c_states ? make_states_map(&mcs, c_states, s) : make_map(&mcs, a.h, s, s.DHHV);
+  r |= (c_states && s.DHQK == 64) ? make_states_map(&mcs, c_states, s) : make_map(&mcs, a.h, s, s.DHHV);
   if (r) {
     set_error("cuTensorMapEncodeTiled failed (%d)", r);
     return MLSTM_B200_ENODEVICE;
@@ -1201,6 +1560,11 @@ int run_fw(const mlstm_b200_fw_args& a, void* c_states, cudaStream_t st) {
   p.sig = s.siging ? 1 : 0;
   p.store_states = c_states != nullptr;
   p.prof = g_prof;
+  if (s.DHQK == 128) {
+    p.store_states = 0;  // the d=128 backward runs on the exact family, which recomputes its states
+    if (s.dtype == MLSTM_B200_BF16) return launch_fw_d128<__nv_bfloat16>(p, mq, mk, mv, mh, st);
+    return launch_fw_d128<__half>(p, mq, mk, mv, mh, st);
+  }
   if (s.dtype == MLSTM_B200_BF16) return launch_fw_d64<__nv_bfloat16>(p, mq, mk, mv, mh, mcs, st);
   return launch_fw_d64<__half>(p, mq, mk, mv, mh, mcs, st);
 }
@@ -1223,14 +1587,17 @@ BwWs bw_ws(const mlstm_b200_shape& s) {
 
 void tensor_set_clock_buffer(void* dev_ptr) { g_prof = (long long*)dev_ptr; }
 
-bool tensor_supported(const mlstm_b200_shape& s) {
+// forward: d = 64 and d = 128; backward: d = 64 (d = 128 backward does not fit shared memory with 128-token tiles)
+bool tensor_supported(const mlstm_b200_shape& s, int backward) {
   if (s.dtype != MLSTM_B200_BF16 && s.dtype != MLSTM_B200_F16) return false;
-  if (s.DHQK != 64 || s.DHHV != 64) return false;
+  if (s.DHQK != s.DHHV) return false;
+  if (s.DHQK != 64 && !(s.DHQK == 128 && !backward)) return false;
   if (s.chunk_size % 64 != 0 || s.S % 64 != 0) return false;
   return true;
 }
 
 size_t tensor_states_bytes(const mlstm_b200_shape& s) {
+  if (!tensor_supported(s, 1)) return 0;
   const size_t NT = (s.S + LT - 1) / LT;
   return (size_t)s.B * s.NH * NT * 64 * 64 * 2;
 }
