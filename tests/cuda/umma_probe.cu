@@ -150,9 +150,11 @@ int run(const char* name) {
 }
 
 int time_main();
+int sw64_main();
 int main(int argc, char** argv) {
   setvbuf(stdout, NULL, _IONBF, 0);
   if (argc > 1 && argv[1][0] == 't') return time_main();
+  if (argc > 1 && argv[1][0] == 's') return sw64_main();
   int bad = 0;
   bad += run<128, 128, 64, false, false, false, false>("S=QK^T      M128 N128 K64  A:K  B:K ") != 0;
   bad += run<128, 64, 128, false, true, false, true>("PV          M128 N64  K128 A:K  B:MN +tma_store") != 0;
@@ -244,4 +246,128 @@ int time_main() {
   run_time<128, 128, true, true>("M128 N128 A:MN B:MN");
   run_time<128, 256, false, false>("M128 N256 A:K  B:K ");
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// `umma_probe sw64`: operand layouts for head dim 32 (64-byte swizzle) mixed with 128-byte ones.
+// Operands are written by threads with the swizzle formulas (so the formulas themselves are tested);
+// one variant loads A through TMA SWIZZLE_64B.
+// ------------------------------------------------------------------------------------------
+struct OpLayout {
+  int mn, k;        // logical extent
+  int mn_major;     // 0: K-major, 1: MN-major
+  int rowb;         // swizzle / row width in bytes: 64 or 128
+};
+__host__ __device__ inline uint32_t op_offset(const OpLayout& L, int mn, int k) {
+  const int epr = L.rowb / 2;  // elements per row
+  if (!L.mn_major) {
+    const int sub = k / epr, kc = k % epr;
+    const int sw = L.rowb == 128 ? (mn & 7) : ((mn >> 1) & 3);
+    return sub * L.mn * L.rowb + mn * L.rowb + ((((kc >> 3) ^ sw)) << 4) + ((kc & 7) << 1);
+  } else {
+    const int blk = mn / epr, mc = mn % epr;
+    const int sw = L.rowb == 128 ? (k & 7) : ((k >> 1) & 3);
+    return blk * L.k * L.rowb + k * L.rowb + ((((mc >> 3) ^ sw)) << 4) + ((mc & 7) << 1);
+  }
+}
+__device__ inline uint64_t op_desc(const OpLayout& L, uint32_t base, int kk /*k-step of 16*/, int dup_blocks) {
+  const uint32_t lt = L.rowb == 128 ? 2u : 4u;
+  uint32_t start, lbo, sbo = 8 * L.rowb;
+  if (!L.mn_major) {
+    const int epr = L.rowb / 2, k0 = kk * 16;
+    start = base + (k0 / epr) * L.mn * L.rowb + (k0 % epr) * 2;
+    lbo = 0;
+  } else {
+    start = base + kk * 16 * L.rowb;
+    lbo = dup_blocks ? 0 : L.k * L.rowb;
+  }
+  uint64_t d = 0;
+  d |= (uint64_t)((start & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)lt << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(128) probe_sw(OpLayout LA, OpLayout LB, int M, int N, int dupA, const bf16* gA,
+                                                const bf16* gB, float* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + 32768;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int e = tid; e < LA.mn * LA.k; e += 128) *(bf16*)(sA + op_offset(LA, e / LA.k, e % LA.k)) = gA[e];
+  for (int e = tid; e < LB.mn * LB.k; e += 128) *(bf16*)(sB + op_offset(LB, e / LB.k, e % LB.k)) = gB[e];
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc<128>(&tmem_base_s);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  if (warp == 0 && elect_one()) {
+    const uint32_t idesc = umma_idesc(M, N, LA.mn_major, LB.mn_major, true);
+    for (int kk = 0; kk < LA.k / 16; ++kk)
+      umma_f16(tmem, op_desc(LA, smem_u32(sA), kk, dupA), op_desc(LB, smem_u32(sB), kk, 0), idesc, kk > 0);
+    umma_commit(&bar);
+  }
+  __syncwarp();
+  mbar_wait(&bar, 0, 103);
+  tc_fence_after_sync();
+  int row = (M == 128) ? tid : (lane < 16 ? warp * 16 + lane : -1);
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    float v[32];
+    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    if (row >= 0)
+      for (int j = 0; j < 32 && c0 + j < N; ++j) out[row * N + c0 + j] = v[j];
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<128>(tmem);
+}
+
+int run_sw(const char* name, int M, int N, int K, int a_mn, int a_rowb, int b_mn, int b_rowb, int validM) {
+  // logical A[M'][K] with M' = validM rows of real data (the MMA's M may be larger: duplicated block)
+  OpLayout LA{validM, K, a_mn, a_rowb}, LB{N, K, b_mn, b_rowb};
+  std::vector<bf16> hA(validM * K), hB(N * K);
+  std::vector<float> fA(validM * K), fB(N * K);
+  for (int i = 0; i < validM * K; ++i) { bf16 x = __float2bfloat16(frand()); hA[i] = x; fA[i] = __bfloat162float(x); }
+  for (int i = 0; i < N * K; ++i) { bf16 x = __float2bfloat16(frand()); hB[i] = x; fB[i] = __bfloat162float(x); }
+  bf16 *dA, *dB; float* dO;
+  cudaMalloc(&dA, validM * K * 2); cudaMalloc(&dB, N * K * 2); cudaMalloc(&dO, M * N * 4);
+  cudaMemcpy(dA, hA.data(), validM * K * 2, cudaMemcpyHostToDevice);
+  cudaMemcpy(dB, hB.data(), N * K * 2, cudaMemcpyHostToDevice);
+  cudaMemset(dO, 0xff, M * N * 4);
+  size_t smem = 65536 + 2048;
+  cudaFuncSetAttribute(probe_sw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  probe_sw<<<1, 128, smem>>>(LA, LB, M, N, validM < M, dA, dB, dO);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("%s: FAIL kernel error %s\n", name, cudaGetErrorString(e)); return 2; }
+  std::vector<float> hO(M * N);
+  cudaMemcpy(hO.data(), dO, M * N * 4, cudaMemcpyDeviceToHost);
+  double maxerr = 0;
+  for (int m = 0; m < validM; ++m) for (int n = 0; n < N; ++n) {
+    double ref = 0; for (int k = 0; k < K; ++k) ref += (double)fA[m * K + k] * fB[n * K + k];
+    double d = fabs(ref - hO[m * N + n]); if (!(d <= maxerr)) maxerr = d;
+  }
+  printf("%s: %s  max|err|=%.3e\n", name, maxerr < 1e-2 ? "PASS" : "FAIL", maxerr);
+  cudaFree(dA); cudaFree(dB); cudaFree(dO);
+  return maxerr < 1e-2 ? 0 : 1;
+}
+
+int sw64_main() {
+  int bad = 0;
+  bad += run_sw("S d32      M128 N128 K32  A:K/64  B:K/64 ", 128, 128, 32, 0, 64, 0, 64, 128);
+  bad += run_sw("PV d32     M128 N32  K128 A:K/128 B:MN/64", 128, 32, 128, 0, 128, 1, 64, 128);
+  bad += run_sw("QC d32     M128 N32  K32  A:K/64  B:MN/64", 128, 32, 32, 0, 64, 1, 64, 128);
+  bad += run_sw("dC d32     M64  N32  K128 A:MN/64(dup) B:MN/64", 64, 32, 128, 1, 64, 1, 64, 32);
+  bad += run_sw("dSK d32    M128 N32  K128 A:K/128 B:MN/64", 128, 32, 128, 0, 128, 1, 64, 128);
+  bad += run_sw("SbT dH d32 M128 N32  K128 A:MN/128 B:MN/64", 128, 32, 128, 1, 128, 1, 64, 128);
+  bad += run_sw("dH CT d32  M128 N32  K32  A:K/64  B:K/64 ", 128, 32, 32, 0, 64, 0, 64, 128);
+  bad += run_sw("ref d64    M128 N64  K128 A:MN/128 B:MN/128", 128, 64, 128, 1, 128, 1, 128, 128);
+  printf("%d sw64 variant(s) failed\n", bad);
+  return bad ? 1 : 0;
 }
