@@ -183,6 +183,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 // K-major  (rows = M/N index, 128B row = 64 K elements): SBO = 1024 (next 8 rows), LBO unused.
 // MN-major (rows = K index,  128B row = 64 M/N elements): SBO = 1024 (next 8 K rows),
 //           LBO = byte distance to the next 64-wide M/N block.
+// general form: layout type 2 = SWIZZLE_128B, 4 = SWIZZLE_64B (rows of 64 bytes, 512-byte swizzle atoms)
+__device__ __forceinline__ uint64_t umma_smem_desc_lt(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                      uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
@@ -224,6 +235,11 @@ __device__ __forceinline__ uint32_t swz128(int row, int col) {
   return (uint32_t)(row * 128 + ((((col >> 3) ^ row) & 7) << 4) + ((col & 7) << 1));
 }
 
+// Same for a dense 64B-swizzled [rows][32] 16-bit tile (TMA SWIZZLE_64B): chunk index XOR ((row >> 1) & 3).
+__device__ __forceinline__ uint32_t swz64(int row, int col) {
+  return (uint32_t)(row * 64 + ((((col >> 3) ^ (row >> 1)) & 3) << 4) + ((col & 7) << 1));
+}
+
 }  // namespace sm100
 
 // ------------------------------------------------------------------- host: tensor maps
@@ -247,17 +263,19 @@ inline EncodeTiledFn get_encode_fn() {
 
 // 4-D map over a (B, NH, S, D) 16-bit tensor with element strides (sb, sh, ss, 1);
 // box = (64 cols, box_rows, 1, 1), 128B swizzle, out-of-bounds rows read as zero / are not written.
+// box_cols = 64 -> 128B swizzle (default); box_cols = 32 -> 64B swizzle (head dim 32).
 inline int make_map_bhsd(CUtensorMap* map, const void* ptr, bool bf16, int B, int NH, int S, int D, int64_t sb,
-                         int64_t sh, int64_t ss, int box_rows) {
+                         int64_t sh, int64_t ss, int box_rows, int box_cols = 64) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return -1;
   cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)S, (cuuint64_t)NH, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)ss * 2, (cuuint64_t)sh * 2, (cuuint64_t)sb * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 1, 1};
+  cuuint32_t box[4] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   if (((uintptr_t)ptr & 15) || (strides[0] & 15) || (strides[1] & 15) || (strides[2] & 15)) return -2;
   CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, (void*)ptr, dims,
-                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
