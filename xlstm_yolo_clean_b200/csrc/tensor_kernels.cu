@@ -515,6 +515,7 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
               }
             }
           } else {
+            if (NSTAGE == 2 && c > 0) continue;  // blocks above the diagonal stay zero (P has its own buffer)
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
@@ -1026,7 +1027,7 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
   uint8_t* sCs = smem + SM::oCs;
   uint8_t* sdC = smem + SM::odC;
   float* fsm = (float*)(smem + SM::oSmall);
-  __shared__ uint64_t bar_full, bar_s, bar_q, bar_v, bar_k, bar_d, bar_g[2];
+  __shared__ uint64_t bar_full, bar_s, bar_q, bar_v, bar_k, bar_d, bar_a, bar_b, bar_g[2];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -1036,6 +1037,8 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
   if (tid == 0) {
     mbar_init(&bar_full, 1);
     mbar_init(&bar_s, 1);
+    mbar_init(&bar_a, 1);
+    mbar_init(&bar_b, 1);
     mbar_init(&bar_q, 1);
     mbar_init(&bar_v, 1);
     mbar_init(&bar_k, 1);
@@ -1133,42 +1136,59 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       TC_PROF(it, 10);
       if (lane == 0) tma_store_wait_read<0>();  // the previous tile's dq / dk / dv stores have left their staging buffers
       __syncwarp();
+      // MMA batch, ordered so that the input tiles die one after the other (Q, K, V, C_{k-1}, dH): every
+      // tile is re-filled with the next tile's rows as soon as its last reader has completed, so the loads
+      // of tile k-1 overlap the rest of the batch and the epilogues instead of idling the whole CTA.
       if (elect_one()) {
         tc_fence_after_sync();
+#pragma unroll
+        for (int kk = 0; kk < LT / 16; ++kk)  // dK1 = dS^T Q
+          umma_f16(tdK1, umma_desc_advance(mdS, kk * 2048), umma_desc_advance(mQ, kk * 2048), id_mn_mn, kk > 0);
+        umma_commit(&bar_a);  // Q consumed
 #pragma unroll
         for (int kk = 0; kk < LT / 16; ++kk)  // dQa = dS K
           umma_f16(tdQa, umma_desc_advance(kdS, (kk / 4) * SM::kTile + (kk % 4) * 32), umma_desc_advance(mK, kk * 2048),
                    id_k_mn, kk > 0);
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk)  // dQb = dH C_{k-1}^T
-          umma_f16(tdQb, umma_desc_advance(kH, kk * 32), umma_desc_advance(kCs, kk * 32), id_k_k, kk > 0);
-        umma_commit(&bar_q);
-#pragma unroll
-        for (int kk = 0; kk < LT / 16; ++kk)  // dV1 = Sb'^T dH
-          umma_f16(tdV1, umma_desc_advance(mSb, kk * 2048), umma_desc_advance(mH, kk * 2048), id_mn_mn, kk > 0);
-#pragma unroll
         for (int kk = 0; kk < D / 16; ++kk)  // dV2 = K dC_k
           umma_f16(tdV2, umma_desc_advance(kK, kk * 32), umma_desc_advance(mdC, kk * 2048), id_k_mn, kk > 0);
-        umma_commit(&bar_v);
-#pragma unroll
-        for (int kk = 0; kk < LT / 16; ++kk)  // dK1 = dS^T Q
-          umma_f16(tdK1, umma_desc_advance(mdS, kk * 2048), umma_desc_advance(mQ, kk * 2048), id_mn_mn, kk > 0);
+        umma_commit(&bar_b);  // K consumed
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk)  // dK2 = V dC_k^T
           umma_f16(tdK2, umma_desc_advance(kV, kk * 32), umma_desc_advance(kdC, kk * 32), id_k_k, kk > 0);
-        umma_commit(&bar_k);
+        umma_commit(&bar_k);  // V consumed; dk complete
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)  // dQb = dH C_{k-1}^T
+          umma_f16(tdQb, umma_desc_advance(kH, kk * 32), umma_desc_advance(kCs, kk * 32), id_k_k, kk > 0);
+        umma_commit(&bar_q);  // C_{k-1} consumed; dq complete
       }
       __syncwarp();
       TC_PROF(it, 11);
-      named_sync(NB_A, kNbAB);  // Qt written
+      named_sync(NB_A, kNbAB);  // Qt written; the workers hold their q / k / v row slices in registers
       TC_PROF(it, 12);
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < LT / 16; ++kk)  // ddC = Qt^T dH
           umma_f16(tddC, umma_desc_advance(mQt, kk * 2048), umma_desc_advance(mH, kk * 2048), id_c, kk > 0);
         umma_commit(&bar_d);
-        mbar_wait(&bar_d, par, 15);  // last MMA of the tile: its inputs can be refilled
-        if (c > 0) issue_loads(c - 1);
+#pragma unroll
+        for (int kk = 0; kk < LT / 16; ++kk)  // dV1 = Sb'^T dH
+          umma_f16(tdV1, umma_desc_advance(mSb, kk * 2048), umma_desc_advance(mH, kk * 2048), id_mn_mn, kk > 0);
+        umma_commit(&bar_v);  // dH consumed; dv complete
+        if (c > 0) {
+          const int r = mt(c - 1) * LT;
+          mbar_expect_tx(&bar_full, SM::kLoadBytes);
+          mbar_wait(&bar_a, par, 21);
+          tma_load_4d(sQ, &mapQ, &bar_full, 0, r, hh, b);
+          mbar_wait(&bar_b, par, 22);
+          tma_load_4d(sK, &mapK, &bar_full, 0, r, hh, b);
+          mbar_wait(&bar_k, par, 23);
+          tma_load_4d(sV, &mapV, &bar_full, 0, r, hh, b);
+          mbar_wait(&bar_q, par, 24);
+          tma_load_4d(sCs, &mapCs, &bar_full, 0, mt(c - 1) * D, hh, b);
+          mbar_wait(&bar_v, par, 25);
+          tma_load_4d(sdH, &mapdH, &bar_full, 0, r, hh, b);
+        }
       }
       __syncwarp();
       TC_PROF(it, 13);
@@ -1360,6 +1380,7 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
               }
             }
           } else {
+            if (it > 0) continue;  // blocks above the diagonal stay zero: written once, by the first tile
 #pragma unroll
             for (int j = 0; j < 32; ++j) { v[j] = 0.f; w[j] = 0.f; }
           }
@@ -1401,10 +1422,27 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
         uint32_t ra[32], rq[32];
         float o[32];
         float dot;
+        // dk
+        mbar_wait(&bar_k, par, 18);
+        tc_fence_after_sync();
+        TC_PROF(it, 5);
+        tmem_ld32_nowait(tdK1 + lane_base + ch * 32, ra);
+        tmem_ld32_nowait(tdK2 + lane_base + ch * 32, rq);
+        tmem_ld_wait();
+        dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          o[2 * j] = p.scale * __uint_as_float(ra[2 * j]) + abar * __uint_as_float(rq[2 * j]);  // bw.py:170,192
+          o[2 * j + 1] = p.scale * __uint_as_float(ra[2 * j + 1]) + abar * __uint_as_float(rq[2 * j + 1]);
+          float2 kv = unpack2<T>(ks[j]);
+          dot += kv.x * o[2 * j] + kv.y * o[2 * j + 1];
+        }
+        store_row32<T>(sdK, row, ch * 32, o);
+        spart[(1 * 2 + ch) * LT + row] = dot;
         // dq
         mbar_wait(&bar_q, par, 16);
         tc_fence_after_sync();
-        TC_PROF(it, 5);
+        TC_PROF(it, 6);
         tmem_ld32_nowait(tdQa + lane_base + ch * 32, ra);
         tmem_ld32_nowait(tdQb + lane_base + ch * 32, rq);
         tmem_ld_wait();
@@ -1419,6 +1457,25 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
         }
         store_row32<T>(sdQ, row, ch * 32, o);
         spart[(0 * 2 + ch) * LT + row] = dot;
+      }
+      // ---- dC_{k-1} = gbar dC_k + ddC ----------------------------------------------------------------
+      mbar_wait(&bar_d, par, 15);
+      tc_fence_after_sync();
+      TC_PROF(it, 7);
+      {
+        float v[32];
+        tmem_ld32(tddC + lane_base + ch * 32, v);
+        if (owns_c) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) dCreg[j] = gbar * dCreg[j] + v[j];  // bw.py:93-95
+          store_row32<T>(sdC, drow, ch * 32, dCreg);                       // dV2 / dK2 have completed (bar_k)
+        }
+      }
+      // ---- dv last: dV1 = Sb'^T dH is the final MMA group of the batch ---------------------------------
+      {
+        uint32_t ra[32], rq[32];
+        float o[32];
+        float dot;
         // dv
         mbar_wait(&bar_v, par, 17);
         tc_fence_after_sync();
@@ -1435,36 +1492,6 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
         }
         store_row32<T>(sdV, row, ch * 32, o);
         spart[(2 * 2 + ch) * LT + row] = dot;
-        // dk
-        mbar_wait(&bar_k, par, 18);
-        tc_fence_after_sync();
-        TC_PROF(it, 6);
-        tmem_ld32_nowait(tdK1 + lane_base + ch * 32, ra);
-        tmem_ld32_nowait(tdK2 + lane_base + ch * 32, rq);
-        tmem_ld_wait();
-        dot = 0.f;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          o[2 * j] = p.scale * __uint_as_float(ra[2 * j]) + abar * __uint_as_float(rq[2 * j]);  // bw.py:170,192
-          o[2 * j + 1] = p.scale * __uint_as_float(ra[2 * j + 1]) + abar * __uint_as_float(rq[2 * j + 1]);
-          float2 kv = unpack2<T>(ks[j]);
-          dot += kv.x * o[2 * j] + kv.y * o[2 * j + 1];
-        }
-        store_row32<T>(sdK, row, ch * 32, o);
-        spart[(1 * 2 + ch) * LT + row] = dot;
-      }
-      // ---- dC_{k-1} = gbar dC_k + ddC ----------------------------------------------------------------
-      mbar_wait(&bar_d, par, 15);
-      tc_fence_after_sync();
-      TC_PROF(it, 7);
-      {
-        float v[32];
-        tmem_ld32(tddC + lane_base + ch * 32, v);
-        if (owns_c) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) dCreg[j] = gbar * dCreg[j] + v[j];  // bw.py:93-95
-          store_row32<T>(sdC, drow, ch * 32, dCreg);                       // dV2 / dK2 have completed (bar_k)
-        }
       }
       fence_proxy_async_smem();
       tc_fence_before_sync();
