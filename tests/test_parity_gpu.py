@@ -328,3 +328,96 @@ def test_split_sequence_continuation_gpu(pkg):
                                        autocast_kernel_dtype=torch.float32)
     assert O.rel_err(torch.cat([h1, h2], 2), full) < 1e-5
     assert O.rel_err(l2[0], last[0]) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------------
+# Head dim 32 (640-base192.yaml: NH=12, DH=32) on the tcgen05 kernels: 64-byte-swizzle operand tiles.
+# ---------------------------------------------------------------------------------------------------
+def test_d32_tensor_path_one_launch_and_states(pkg):
+    """bf16 d=32 runs the tensor kernels (one launch each way), with initial states, dC_last and last states."""
+    assert pkg.tensor_path_supported(2, 12, 320, 32, 32, torch.bfloat16)
+    inp = O.make_inputs(2, 3, 320, 32, 32, seed=81, dtype=torch.float32, with_states=True)
+    pkg.set_default_impl("tensor")
+    try:
+        got = _run(pkg, inp, torch.bfloat16, states=True, impl="tensor")
+        t = {k: v.to(torch.bfloat16).cuda() for k, v in inp.items()}
+        h, n_out, m_out, _, cst = pkg.mlstm_chunkwise_fw(t["q"], t["k"], t["v"], t["i"], t["f"])
+        assert pkg.last_launch_count() == 1 and cst is not None
+        pkg.mlstm_chunkwise_bw(t["q"], t["k"], t["v"], t["i"], t["f"], n_out, m_out, t["dh"], c_states=cst)
+        assert pkg.last_launch_count() == 1
+    finally:
+        pkg.set_default_impl("auto")
+    _assert_close(got, _oracle(inp, torch.bfloat16, states=True), 2e-2, "d32 states")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+def test_d32_strided_bshd_inputs(pkg, dtype):
+    """The BSHD-strided views MatrixLSTMCell.forward creates (vision_lstm2.py:718-727), base192 geometry."""
+    inp = O.make_inputs(2, 12, 448, 32, 32, seed=82, dtype=torch.float32, dist="model")
+    got = _run(pkg, inp, dtype, strided=True, impl="tensor")
+    _assert_close(got, _oracle(inp, dtype), 2e-2, f"d32 strided {dtype}")
+
+
+def test_d32_extreme_gates(pkg):
+    inp = O.make_inputs(1, 2, 256, 32, 32, seed=83, dtype=torch.float32)
+    inp["i"] = (inp["i"] * 8.0).clamp_(-15, 15)
+    inp["f"] = ((inp["f"] - 3.0) * 8.0).clamp_(-15, 15)
+    got = _run(pkg, inp, torch.bfloat16, impl="tensor")
+    assert all(torch.isfinite(v).all() for v in got.values())
+    _assert_close(got, _oracle(inp, torch.bfloat16), 3e-2, "d32 extreme")
+
+
+@pytest.mark.parametrize("states", [False, True], ids=["plain", "states"])
+def test_d32_reverse_direction(pkg, states):
+    inp = O.make_inputs(2, 3, 320, 32, 32, seed=84, dtype=torch.float32, with_states=states)
+    dtype = torch.bfloat16
+    t = {k: v.to(dtype).cuda() for k, v in inp.items()}
+    leaves = {k: t[k].detach().requires_grad_(True) for k in ("q", "k", "v", "i", "f")}
+    kw = {}
+    if states:
+        c0 = t["c0"].detach().requires_grad_(True)
+        kw = dict(c_initial=c0, n_initial=t["n0"], m_initial=t["m0"], return_last_states=True)
+    out = pkg.mlstm_chunkwise__b200(**leaves, reverse=True, autocast_kernel_dtype=torch.float32, **kw)
+    if states:
+        h, (c_last, n_last, m_last) = out
+        torch.autograd.backward([h, c_last], [t["dh"], t["dc_last"].to(c_last.dtype)])
+    else:
+        h = out
+        h.backward(t["dh"])
+    torch.cuda.synchronize()
+    seq = ("q", "k", "v", "i", "f", "dh")
+    flipped = {k: (v.flip(2) if k in seq else v) for k, v in inp.items()}
+    want = _oracle(flipped, dtype, states=states)
+    got = dict(h=h, dq=leaves["q"].grad, dk=leaves["k"].grad, dv=leaves["v"].grad, di=leaves["i"].grad, df=leaves["f"].grad)
+    for name in got:
+        assert O.rel_err(got[name].double().cpu(), want[name].flip(2)) < 2e-2, name
+    if states:
+        assert O.rel_err(c_last.double().cpu(), want["c_last"]) < 2e-2
+        assert O.rel_err(c0.grad.double().cpu(), want["dc0"]) < 2e-2
+
+
+def test_d32_siging_variant(pkg):
+    inp = O.make_inputs(2, 4, 320, 32, 32, seed=85, dtype=torch.float32)
+    dtype = torch.bfloat16
+    t = {k: v.to(dtype).cuda() for k, v in inp.items()}
+    leaves = {k: t[k].detach().requires_grad_(True) for k in ("q", "k", "v", "i", "f")}
+    h, (c_last, n_last) = pkg.mlstm_siging_chunkwise__b200(**leaves, return_last_states=True,
+                                                          autocast_kernel_dtype=torch.float32)
+    h.backward(t["dh"])
+    torch.cuda.synchronize()
+    r = {k: v.to(dtype).double() for k, v in inp.items()}
+    hw, last, grads = O.fwbw(r["q"], r["k"], r["v"], r["i"], r["f"], r["dh"], siging=True)
+    got = dict(h=h, dq=leaves["q"].grad, dk=leaves["k"].grad, dv=leaves["v"].grad, di=leaves["i"].grad, df=leaves["f"].grad,
+               c_last=c_last, n_last=n_last)
+    want = dict(h=hw, dq=grads[0], dk=grads[1], dv=grads[2], di=grads[3], df=grads[4], c_last=last[0], n_last=last[1])
+    for name in got:
+        assert O.rel_err(got[name].double().cpu(), want[name]) < 2e-2, name
+
+
+def test_d32_base192_call_exact_vs_tensor(pkg):
+    """A base192-sized call (B=4 of 64, NH=12, S=1600): tensor path agrees with the exact fp32-accumulate route."""
+    inp = O.make_inputs(4, 12, 1600, 32, 32, seed=86, dtype=torch.float32, dist="model")
+    a = _run(pkg, inp, torch.bfloat16, impl="tensor")
+    b = _run(pkg, inp, torch.bfloat16, impl="exact")
+    for name in a:
+        assert O.rel_err(a[name], b[name]) < 2e-2, name

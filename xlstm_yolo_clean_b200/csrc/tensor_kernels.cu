@@ -108,6 +108,69 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Head-dim dependent layout of the [rows][D] 16-bit tiles (Q, K, V, H, C, ...): D = 64 -> 128-byte
+// rows, TMA / UMMA SWIZZLE_128B; D = 32 -> 64-byte rows, SWIZZLE_64B (descriptor forms validated by
+// tests/cuda/umma_probe.cu sw64).  The 128 x 128 tiles (P, Sb', dS) always use 128-byte rows.
+// ---------------------------------------------------------------------------------------------
+template <int D>
+struct Lay {
+  static_assert(D == 64 || D == 32, "head dim 64 or 32");
+  static constexpr int kRowB = 2 * D;                  // bytes per tile row
+  static constexpr int kTile = LT * kRowB;             // one [128][D] tile
+  static constexpr int kState = D * kRowB;             // one [D][D] state tile
+  static constexpr uint32_t kSbo = 8 * kRowB;          // 8-row swizzle atom
+  static constexpr uint32_t kLt = D == 64 ? 2u : 4u;   // UMMA layout type
+  static constexpr int CW = D / 2;                     // columns per worker thread
+  static constexpr uint32_t kAdvMN = 16 * kRowB;       // descriptor advance per 16 K-rows of an MN-major operand
+  __device__ static __forceinline__ uint32_t swz(int row, int col) { return D == 64 ? swz128(row, col) : swz64(row, col); }
+  // K-major operand: lbo = 0; MN-major operand: lbo = byte distance to the next D-wide block (0 re-reads the
+  // same block: the M = 64 MMA of the D = 32 state update duplicates its 32 real rows)
+  __device__ static __forceinline__ uint64_t desc(uint32_t saddr, uint32_t lbo) { return umma_smem_desc_lt(saddr, lbo, kSbo, kLt); }
+};
+
+// store N consecutive columns (col0 multiple of 8) of row `row` of a swizzled [rows][D] 16-bit tile
+template <typename T, int D, int N>
+__device__ __forceinline__ void store_cols(uint8_t* tile, int row, int col0, const float (&v)[N]) {
+#pragma unroll
+  for (int j = 0; j < N / 8; ++j) {
+    uint4 u;
+    u.x = pack2<T>(v[8 * j + 0], v[8 * j + 1]);
+    u.y = pack2<T>(v[8 * j + 2], v[8 * j + 3]);
+    u.z = pack2<T>(v[8 * j + 4], v[8 * j + 5]);
+    u.w = pack2<T>(v[8 * j + 6], v[8 * j + 7]);
+    *reinterpret_cast<uint4*>(tile + Lay<D>::swz(row, col0 + 8 * j)) = u;
+  }
+}
+
+// Column sums over the 32 rows held by a warp for N = 16 columns: every lane ends up with the sum of
+// column (lane & 15).
+__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int off = 8; off >= 1; off >>= 1) {
+    const bool hi = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < off; ++j) {
+      const float keep = hi ? v[j + off] : v[j];
+      const float send = hi ? v[j] : v[j + off];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+template <int N>
+__device__ __forceinline__ float warp_colsum(float (&v)[N], int lane);
+template <>
+__device__ __forceinline__ float warp_colsum<32>(float (&v)[32], int lane) { return warp_colsum32(v, lane); }
+template <>
+__device__ __forceinline__ float warp_colsum<16>(float (&v)[16], int lane) { return warp_colsum16(v, lane); }
+
+// TMEM -> registers, N = 32 or 16 consecutive fp32 columns of this thread's lane
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[32]) { tmem_ld32(taddr, v); }
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float (&v)[16]) { tmem_ld16(taddr, v); }
+__device__ __forceinline__ void tmem_ld_nowait(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32_nowait(taddr, r); }
+__device__ __forceinline__ void tmem_ld_nowait(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld16_nowait(taddr, r); }
+
 // Raw gate inputs of one tile held in registers by the control warp (lane owns tokens 4*lane..+3),
 // loaded one tile ahead of their use so the scans never wait on global memory.
 template <typename T>
@@ -229,33 +292,40 @@ struct TcFwParams {
   long long* prof;   // debug: per-tile phase clocks of CTA 0 (mlstm_b200_debug_set_clock_buffer)
 };
 
-template <int NSTAGE>
+template <int D_>
 struct FwSmem {
-  static constexpr int D = 64;
-  static constexpr int kTile = LT * 128;  // one [128][64] 16-bit tile
-  static constexpr int oQ = 0;            // [NSTAGE] Q tiles
+  static constexpr int D = D_;
+  static constexpr int NSTAGE = 2;                   // Q / K / V ring
+  static constexpr int kTile = Lay<D>::kTile;        // one [128][D] 16-bit tile
+  static constexpr int kPTile = LT * 128;            // one [128][64] half of P
+  static constexpr int oQ = 0;                       // [NSTAGE] Q tiles
   static constexpr int oK = oQ + NSTAGE * kTile;
   static constexpr int oV = oK + NSTAGE * kTile;
-  static constexpr int oKb = oV + NSTAGE * kTile;          // abar . K
-  static constexpr int oP = oKb + kTile;                   // P: two K-halves
-  static constexpr int oH = NSTAGE == 2 ? oP + 2 * kTile : oP;  // h staging (aliases P half 0 when smem is tight)
-  static constexpr int oC = oH + (NSTAGE == 2 ? kTile : 2 * kTile);  // bf16 copy of C (64 x 64), MMA B operand
-  static constexpr int oSmall = oC + D * 128;
+  static constexpr int oKb = oV + NSTAGE * kTile;    // abar . K
+  static constexpr int oP = oKb + kTile;             // P: two K-halves
+  static constexpr int oH = oP + 2 * kPTile;         // h staging
+  static constexpr int oC = oH + kTile;              // bf16 copy of C (D x D), MMA B operand
+  static constexpr int oSmall = oC + Lay<D>::kState;
   // floats: gates[2], srs[2][2][LT], sqn[2][2][LT], npart[2][4][D], sN[2][D]
   static constexpr int fGates = 0, fRs = 2 * GateBuf::kFloats, fQn = fRs + 4 * LT, fNp = fQn + 4 * LT,
                        fN = fNp + 8 * D, kSmallFloats = fN + 2 * D;
   static constexpr int kBytes = oSmall + kSmallFloats * 4 + 1024 /*alignment slack*/;
-  static constexpr int kTmemCols = NSTAGE == 2 ? 512 : 256;
+  // TMEM columns.  D = 64: S double-buffered by tile parity (512 columns, one CTA per SM).  D = 32: one S
+  // buffer, 256 columns, so that two CTAs share an SM (S(k+1) is issued after P(k) has been read).
+  static constexpr int kTmemCols = D == 64 ? 512 : 256;
+  static constexpr uint32_t cS0 = 0, cS1 = D == 64 ? 128 : 0, cHi = D == 64 ? 256 : 128, cHx = cHi + D,
+                            cDC = D == 64 ? 384 : 192;
 };
 
-template <typename T, int NSTAGE, bool REV>
-__global__ void __launch_bounds__(kTcThreads, NSTAGE == 1 ? 2 : 1)
-tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+template <typename T, int D, bool REV>
+__global__ void __launch_bounds__(kTcThreads, D == 32 ? 2 : 1)
+tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
           const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapH,
           const __grid_constant__ CUtensorMap mapCs, TcFwParams p) {
-  constexpr int D = 64;
   constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
-  using SM = FwSmem<NSTAGE>;
+  using SM = FwSmem<D>;
+  using L = Lay<D>;
+  constexpr int NSTAGE = SM::NSTAGE, CW = L::CW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   float* fsm = (float*)(smem + SM::oSmall);
@@ -286,23 +356,23 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       prefetch_tmap(&mapQ); prefetch_tmap(&mapK); prefetch_tmap(&mapV); prefetch_tmap(&mapH); prefetch_tmap(&mapCs);
     }
   }
-  // worker-side state: fp32 master copy of C in the registers of lanes < 16 of every worker warp:
-  // row d = 16*rb + lane (M=64 TMEM layout), columns 32*ch .. 32*ch+31
+  // worker-side state: fp32 master copy of C in the registers of lanes < 16 of the worker warps:
+  // row d = 16*rb + lane (M=64 TMEM layout; D = 32 has 32 real rows, warps rb < 2), columns CW*ch .. CW*ch+CW-1
   const int rb = warp & 3, ch = (warp >> 2) & 1;
   const int row = rb * 32 + lane;  // tile row == TMEM lane of this thread
   const uint32_t lane_base = (uint32_t)(rb * 32) << 16;
   const int drow = rb * 16 + (lane & 15);
-  const bool owns_c = warp < kCtlWarp && lane < 16;
-  float Creg[32];
+  const bool owns_c = warp < kCtlWarp && lane < 16 && rb * 16 < D;
+  float Creg[CW];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) Creg[j] = 0.f;
+  for (int j = 0; j < CW; ++j) Creg[j] = 0.f;
   if (warp < kCtlWarp) {
     if (p.c0 && owns_c) {
-      const float* src = p.c0 + ((int64_t)bh * D + drow) * D + ch * 32;
+      const float* src = p.c0 + ((int64_t)bh * D + drow) * D + ch * CW;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) Creg[j] = src[j];
+      for (int j = 0; j < CW; ++j) Creg[j] = src[j];
     }
-    if (owns_c) store_row32<T>(sC, drow, ch * 32, Creg);
+    if (owns_c) store_cols<T, D>(sC, drow, ch * CW, Creg);
     if (tid < D) fsm[SM::fN + tid] = p.n0 ? p.n0[(int64_t)bh * D + tid] : 0.f;
     fence_proxy_async_smem();
   }
@@ -310,9 +380,7 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = tmem_base_s;
-  // TMEM columns: with 512 columns S is double-buffered by tile parity and nothing aliases
-  const uint32_t tS0 = tmem, tS1 = NSTAGE == 2 ? tmem + 128 : tmem;
-  const uint32_t tHi = NSTAGE == 2 ? tmem + 256 : tmem, tHx = tHi + 64, tDC = NSTAGE == 2 ? tmem + 384 : tmem + 128;
+  const uint32_t tS0 = tmem + SM::cS0, tS1 = tmem + SM::cS1, tHi = tmem + SM::cHi, tHx = tmem + SM::cHx, tDC = tmem + SM::cDC;
 
   const T* ip = (const T*)p.ig + b * p.ig_sb + hh * p.ig_sh;
   const T* fp = (const T*)p.fg + b * p.fg_sb + hh * p.fg_sh;
@@ -333,17 +401,17 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       for (int s = 0; s < NSTAGE && s < p.NT; ++s) load_stage(s, s);
 
     constexpr uint32_t id_s = umma_idesc(128, 128, false, false, kBf16);
-    constexpr uint32_t id_dc = umma_idesc(64, 64, true, true, kBf16);
-    constexpr uint32_t id_h = umma_idesc(128, 64, false, true, kBf16);
-    const uint64_t dKb = umma_smem_desc(smem_u32(sKb), SM::kTile, 1024);
+    constexpr uint32_t id_dc = umma_idesc(64, D, true, true, kBf16);
+    constexpr uint32_t id_h = umma_idesc(128, D, false, true, kBf16);
+    const uint64_t dKb = L::desc(smem_u32(sKb), D == 64 ? SM::kTile : 0);  // D = 32: rows 32-63 of the M = 64 MMA re-read the block
     const uint64_t dP = umma_smem_desc(smem_u32(sP), 0, 1024);
-    const uint64_t dC = umma_smem_desc(smem_u32(sC), D * 128, 1024);
+    const uint64_t dC = L::desc(smem_u32(sC), L::kState);
     // Every shared-memory descriptor is loop invariant and provably warp-uniform (the stage / TMEM
     // parity is a compile-time constant of the two-tile unrolled body), so the tcgen05.mma operands
     // live in uniform registers instead of going through a per-instruction R2UR waterfall.
-    const uint64_t dQ0 = umma_smem_desc(smem_u32(smem + SM::oQ), 0, 1024);
-    const uint64_t dK0 = umma_smem_desc(smem_u32(smem + SM::oK), 0, 1024);
-    const uint64_t dV0 = umma_smem_desc(smem_u32(smem + SM::oV), SM::kTile, 1024);
+    const uint64_t dQ0 = L::desc(smem_u32(smem + SM::oQ), 0);
+    const uint64_t dK0 = L::desc(smem_u32(smem + SM::oK), 0);
+    const uint64_t dV0 = L::desc(smem_u32(smem + SM::oV), SM::kTile);
     const uint64_t dQ1 = umma_desc_advance(dQ0, (NSTAGE - 1) * SM::kTile);
     const uint64_t dK1 = umma_desc_advance(dK0, (NSTAGE - 1) * SM::kTile);
     const uint64_t dV1 = umma_desc_advance(dV0, (NSTAGE - 1) * SM::kTile);
@@ -382,11 +450,11 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
         tc_fence_after_sync();
 #pragma unroll
         for (int kk = 0; kk < LT / 16; ++kk)  // Hintra = P V
-          umma_f16(tHi, umma_desc_advance(dP, (kk / 4) * SM::kTile + (kk % 4) * 32), umma_desc_advance(dV, kk * 2048), id_h,
+          umma_f16(tHi, umma_desc_advance(dP, (kk / 4) * SM::kPTile + (kk % 4) * 32), umma_desc_advance(dV, kk * L::kAdvMN), id_h,
                    kk > 0);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk)  // Hinter = Q C_{k-1}
-          umma_f16(tHx, umma_desc_advance(dQ, kk * 32), umma_desc_advance(dC, kk * 2048), id_h, kk > 0);
+          umma_f16(tHx, umma_desc_advance(dQ, kk * 32), umma_desc_advance(dC, kk * L::kAdvMN), id_h, kk > 0);
         umma_commit(&bar_h);
       }
       __syncwarp();
@@ -395,7 +463,7 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < LT / 16; ++kk)  // dC = Kbar^T V
-          umma_f16(tDC, umma_desc_advance(dKb, kk * 2048), umma_desc_advance(dV, kk * 2048), id_dc, kk > 0);
+          umma_f16(tDC, umma_desc_advance(dKb, kk * L::kAdvMN), umma_desc_advance(dV, kk * L::kAdvMN), id_dc, kk > 0);
         umma_commit(&bar_dc);
         if (c + 1 < p.NT) issue_s(c + 1, std::integral_constant<int, par ^ 1>{});  // next tile's S, other TMEM buffer
       }
@@ -464,11 +532,11 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       {
         float qn = 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 q = *reinterpret_cast<const uint4*>(sQ + swz128(row, ch * 32 + 8 * j));
+        for (int j = 0; j < CW / 8; ++j) {
+          uint4 q = *reinterpret_cast<const uint4*>(sQ + L::swz(row, ch * CW + 8 * j));
           float2 q0 = unpack2<T>(q.x), q1 = unpack2<T>(q.y), q2 = unpack2<T>(q.z), q3 = unpack2<T>(q.w);
-          const float4 n0 = *reinterpret_cast<const float4*>(sNc + ch * 32 + 8 * j);
-          const float4 n1 = *reinterpret_cast<const float4*>(sNc + ch * 32 + 8 * j + 4);
+          const float4 n0 = *reinterpret_cast<const float4*>(sNc + ch * CW + 8 * j);
+          const float4 n1 = *reinterpret_cast<const float4*>(sNc + ch * CW + 8 * j + 4);
           qn += q0.x * n0.x + q0.y * n0.y + q1.x * n0.z + q1.y * n0.w + q2.x * n1.x + q2.y * n1.y + q3.x * n1.z + q3.y * n1.w;
         }
         sqn[ch * LT + row] = qn;
@@ -515,7 +583,7 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
               }
             }
           } else {
-            if (NSTAGE == 2 && c > 0) continue;  // blocks above the diagonal stay zero (P has its own buffer)
+            if (c > 0) continue;  // blocks above the diagonal stay zero (P has its own buffer)
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
@@ -532,17 +600,17 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       // ---- Kbar = abar . K (this thread: row, 32 columns); column sums for n (overlaps the H MMAs) --
       {
         const float ab = __expf(g - b_t + i_t - m_next);  // fw.py:102 (exp(-inf) = 0 for tail tokens)
-        float kb[32];
+        float kb[CW];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 u = *reinterpret_cast<const uint4*>(sK + swz128(row, ch * 32 + 8 * j));
+        for (int j = 0; j < CW / 8; ++j) {
+          uint4 u = *reinterpret_cast<const uint4*>(sK + L::swz(row, ch * CW + 8 * j));
           float2 a0 = unpack2<T>(u.x), a1 = unpack2<T>(u.y), a2 = unpack2<T>(u.z), a3 = unpack2<T>(u.w);
           kb[8 * j + 0] = a0.x * ab; kb[8 * j + 1] = a0.y * ab; kb[8 * j + 2] = a1.x * ab; kb[8 * j + 3] = a1.y * ab;
           kb[8 * j + 4] = a2.x * ab; kb[8 * j + 5] = a2.y * ab; kb[8 * j + 6] = a3.x * ab; kb[8 * j + 7] = a3.y * ab;
         }
-        store_row32<T>(sKb, row, ch * 32, kb);
-        const float cs = warp_colsum32(kb, lane);  // sum over this warp's 32 rows of column ch*32 + lane
-        snp[rb * D + ch * 32 + lane] = cs;
+        store_cols<T, D>(sKb, row, ch * CW, kb);
+        const float cs = warp_colsum<CW>(kb, lane);  // sum over this warp's 32 rows of column ch*CW + (lane % CW)
+        if (lane < CW) snp[rb * D + ch * CW + lane] = cs;
         fence_proxy_async_smem();
         named_arrive(NB_A, kNbAB);
       }
@@ -552,18 +620,18 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       tc_fence_after_sync();
       TC_PROF(c, 7);
       {
-        uint32_t hi[32], hx[32];
-        tmem_ld32_nowait(tHi + lane_base + ch * 32, hi);
-        tmem_ld32_nowait(tHx + lane_base + ch * 32, hx);
+        uint32_t hi[CW], hx[CW];
+        tmem_ld_nowait(tHi + lane_base + ch * CW, hi);
+        tmem_ld_nowait(tHx + lane_base + ch * CW, hx);
         const float bq = __expf(b_t + m_run - m_t) * p.scale;                          // fw.py:197-198
         const float den = bq * (sqn[row] + sqn[LT + row]) + srs[row] + srs[LT + row];  // fw.py:204-206
         const float nmax = fmaxf(fabsf(den), __expf(-m_t));                            // fw.py:208-210
         const float inv = 1.f / (nmax + p.eps);
         tmem_ld_wait();
-        float o[32];
+        float o[CW];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) o[j] = (__uint_as_float(hi[j]) + bq * __uint_as_float(hx[j])) * inv;  // fw.py:200-212
-        store_row32<T>(sH, row, ch * 32, o);
+        for (int j = 0; j < CW; ++j) o[j] = (__uint_as_float(hi[j]) + bq * __uint_as_float(hx[j])) * inv;  // fw.py:200-212
+        store_cols<T, D>(sH, row, ch * CW, o);
         if (ch == 0 && row < n_valid) {
           p.n_out[(int64_t)bh * p.S + t0 + row] = nmax;
           p.m_out[(int64_t)bh * p.S + t0 + row] = m_t;
@@ -573,12 +641,12 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       mbar_wait(&bar_dc, par, 6);
       tc_fence_after_sync();
       {
-        float v[32];
-        tmem_ld32(tDC + lane_base + ch * 32, v);  // M=64 layout: lanes 0-15 of each quadrant hold rows
+        float v[CW];
+        tmem_ld(tDC + lane_base + ch * CW, v);  // M=64 layout: lanes 0-15 of each quadrant hold rows
         if (owns_c) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) Creg[j] = gbar * Creg[j] + v[j];
-          store_row32<T>(sC, drow, ch * 32, Creg);  // Q C_{k-1} (bar_h) has finished reading the old copy
+          for (int j = 0; j < CW; ++j) Creg[j] = gbar * Creg[j] + v[j];
+          store_cols<T, D>(sC, drow, ch * CW, Creg);  // Q C_{k-1} (bar_h) has finished reading the old copy
         }
         if (tid < D) {  // n_k = gbar n_{k-1} + column sums of Kbar (fw.py:116)
           sNn[tid] = gbar * sNc[tid] + ((snp[tid] + snp[D + tid]) + (snp[2 * D + tid] + snp[3 * D + tid]));
@@ -595,9 +663,9 @@ tc_fw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
     // final states (fw.py:302-309)
     if (p.c_last) {
       if (owns_c) {
-        float* dst = p.c_last + ((int64_t)bh * D + drow) * D + ch * 32;
+        float* dst = p.c_last + ((int64_t)bh * D + drow) * D + ch * CW;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) dst[j] = Creg[j];
+        for (int j = 0; j < CW; ++j) dst[j] = Creg[j];
       }
       if (tid < D) p.n_last[(int64_t)bh * D + tid] = fsm[SM::fN + cur * D + tid];  // own write (tid < D finalises n)
       if (tid == 0) p.m_last[bh] = m_run;
@@ -984,34 +1052,42 @@ struct TcBwParams {
   long long* prof;
 };
 
+template <int D_>
 struct BwSmem {
-  static constexpr int D = 64;
-  static constexpr int kTile = LT * 128;
+  static constexpr int D = D_;
+  static constexpr int kTile = Lay<D>::kTile;   // one [128][D] tile
+  static constexpr int kPTile = LT * 128;       // one [128][64] half of Sb' / dS
+  static constexpr int kState = Lay<D>::kState;
   static constexpr int oQ = 0, oK = kTile, oV = 2 * kTile, odH = 3 * kTile;
-  static constexpr int oQt = 4 * kTile;       // wq . Q
-  static constexpr int oSb = 5 * kTile;       // Sb' two halves
-  static constexpr int odS = 7 * kTile;       // dS  two halves
-  static constexpr int odQ = 9 * kTile;       // dq / dv / dk staging (their stores overlap the next tile's W phase)
-  static constexpr int odV = 10 * kTile;
-  static constexpr int odK = 11 * kTile;
-  static constexpr int oCs = 12 * kTile;      // C_{k-1}, 64 x 64 bf16 (TMA)
-  static constexpr int odC = oCs + 64 * 128;  // dC_k bf16 operand copy
-  static constexpr int oSmall = odC + 64 * 128;
+  static constexpr int oQt = 4 * kTile;         // wq . Q
+  static constexpr int oSb = 5 * kTile;         // Sb' two halves
+  static constexpr int odS = oSb + 2 * kPTile;  // dS  two halves
+  static constexpr int odQ = odS + 2 * kPTile;  // dq / dv / dk staging (their stores overlap the next tile's W phase)
+  static constexpr int odV = odQ + kTile;
+  static constexpr int odK = odV + kTile;
+  static constexpr int oCs = odK + kTile;       // C_{k-1}, D x D bf16 (TMA)
+  static constexpr int odC = oCs + kState;      // dC_k bf16 operand copy
+  static constexpr int oSmall = odC + kState;
   // floats: gates[2], spart[2][6][LT]
   static constexpr int fGates = 0, fPart = 2 * GateBuf::kFloats, kSmallFloats = fPart + 12 * LT;
   static constexpr int kBytes = oSmall + kSmallFloats * 4 + 1024;
-  static constexpr uint32_t kLoadBytes = 4 * kTile + 64 * 128;
+  static constexpr uint32_t kLoadBytes = 4 * kTile + kState;
+  // TMEM columns.  D = 64: the S / dSb columns are re-used by the dV / dK accumulators.  D = 32: nothing aliases.
+  static constexpr uint32_t cS = 0, cdSb = 128;
+  static constexpr uint32_t cdV1 = D == 64 ? 0 : 256, cdV2 = cdV1 + D, cdK1 = D == 64 ? 128 : 320, cdK2 = cdK1 + D,
+                            cdQa = D == 64 ? 256 : 384, cdQb = cdQa + D, cddC = D == 64 ? 384 : 448;
 };
 
-template <typename T, bool REV>
+template <typename T, int D, bool REV>
 __global__ void __launch_bounds__(kTcThreads, 1)
-tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
           const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdH,
           const __grid_constant__ CUtensorMap mapCs, const __grid_constant__ CUtensorMap mapdQ,
           const __grid_constant__ CUtensorMap mapdK, const __grid_constant__ CUtensorMap mapdV, TcBwParams p) {
-  constexpr int D = 64;
   constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
-  using SM = BwSmem;
+  using SM = BwSmem<D>;
+  using L = Lay<D>;
+  constexpr int CW = L::CW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem + SM::oQ;
@@ -1058,26 +1134,26 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
   const int row = rb * 32 + lane;
   const uint32_t lane_base = (uint32_t)(rb * 32) << 16;
   const int drow = rb * 16 + (lane & 15);
-  const bool owns_c = warp < kCtlWarp && lane < 16;
-  float dCreg[32];
+  const bool owns_c = warp < kCtlWarp && lane < 16 && rb * 16 < D;
+  float dCreg[CW];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) dCreg[j] = 0.f;
+  for (int j = 0; j < CW; ++j) dCreg[j] = 0.f;
   if (warp < kCtlWarp) {
     if (p.dc_last && owns_c) {
-      const float* src = p.dc_last + ((int64_t)bh * D + drow) * D + ch * 32;
+      const float* src = p.dc_last + ((int64_t)bh * D + drow) * D + ch * CW;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) dCreg[j] = src[j];
+      for (int j = 0; j < CW; ++j) dCreg[j] = src[j];
     }
-    if (owns_c) store_row32<T>(sdC, drow, ch * 32, dCreg);
+    if (owns_c) store_cols<T, D>(sdC, drow, ch * CW, dCreg);
     fence_proxy_async_smem();
   }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t tS = tmem, tdSb = tmem + 128;
-  const uint32_t tdV1 = tmem, tdV2 = tmem + 64, tdK1 = tmem + 128, tdK2 = tmem + 192;
-  const uint32_t tdQa = tmem + 256, tdQb = tmem + 320, tddC = tmem + 384;
+  const uint32_t tS = tmem + SM::cS, tdSb = tmem + SM::cdSb;
+  const uint32_t tdV1 = tmem + SM::cdV1, tdV2 = tmem + SM::cdV2, tdK1 = tmem + SM::cdK1, tdK2 = tmem + SM::cdK2;
+  const uint32_t tdQa = tmem + SM::cdQa, tdQb = tmem + SM::cdQb, tddC = tmem + SM::cddC;
 
   const T* ip = (const T*)p.ig + b * p.ig_sb + hh * p.ig_sh;
   const T* fp = (const T*)p.fg + b * p.fg_sb + hh * p.fg_sh;
@@ -1097,19 +1173,19 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       tma_load_4d(sCs, &mapCs, &bar_full, 0, mt(c) * D, hh, b);
     };
     constexpr uint32_t id_s = umma_idesc(128, 128, false, false, kBf16);
-    constexpr uint32_t id_c = umma_idesc(64, 64, true, true, kBf16);
-    constexpr uint32_t id_k_mn = umma_idesc(128, 64, false, true, kBf16);   // A K-major, B MN-major
-    constexpr uint32_t id_mn_mn = umma_idesc(128, 64, true, true, kBf16);   // A MN-major, B MN-major
-    constexpr uint32_t id_k_k = umma_idesc(128, 64, false, false, kBf16);   // A K-major, B K-major
-    const uint64_t kQ = umma_smem_desc(smem_u32(sQ), 0, 1024), mQ = umma_smem_desc(smem_u32(sQ), SM::kTile, 1024);
-    const uint64_t kK = umma_smem_desc(smem_u32(sK), 0, 1024), mK = umma_smem_desc(smem_u32(sK), SM::kTile, 1024);
-    const uint64_t kV = umma_smem_desc(smem_u32(sV), 0, 1024);
-    const uint64_t kH = umma_smem_desc(smem_u32(sdH), 0, 1024), mH = umma_smem_desc(smem_u32(sdH), SM::kTile, 1024);
-    const uint64_t mQt = umma_smem_desc(smem_u32(sQt), SM::kTile, 1024);
-    const uint64_t mSb = umma_smem_desc(smem_u32(sSb), SM::kTile, 1024);
-    const uint64_t kdS = umma_smem_desc(smem_u32(sdS), 0, 1024), mdS = umma_smem_desc(smem_u32(sdS), SM::kTile, 1024);
-    const uint64_t kCs = umma_smem_desc(smem_u32(sCs), 0, 1024);
-    const uint64_t kdC = umma_smem_desc(smem_u32(sdC), 0, 1024), mdC = umma_smem_desc(smem_u32(sdC), D * 128, 1024);
+    constexpr uint32_t id_c = umma_idesc(64, D, true, true, kBf16);
+    constexpr uint32_t id_k_mn = umma_idesc(128, D, false, true, kBf16);   // A K-major, B MN-major
+    constexpr uint32_t id_mn_mn = umma_idesc(128, D, true, true, kBf16);   // A MN-major, B MN-major
+    constexpr uint32_t id_k_k = umma_idesc(128, D, false, false, kBf16);   // A K-major, B K-major
+    const uint64_t kQ = L::desc(smem_u32(sQ), 0), mQ = L::desc(smem_u32(sQ), SM::kTile);
+    const uint64_t kK = L::desc(smem_u32(sK), 0), mK = L::desc(smem_u32(sK), SM::kTile);
+    const uint64_t kV = L::desc(smem_u32(sV), 0);
+    const uint64_t kH = L::desc(smem_u32(sdH), 0), mH = L::desc(smem_u32(sdH), SM::kTile);
+    const uint64_t mQt = L::desc(smem_u32(sQt), D == 64 ? SM::kTile : 0);  // D = 32: rows 32-63 of the M = 64 MMA re-read the block
+    const uint64_t mSb = umma_smem_desc(smem_u32(sSb), SM::kPTile, 1024);
+    const uint64_t kdS = umma_smem_desc(smem_u32(sdS), 0, 1024), mdS = umma_smem_desc(smem_u32(sdS), SM::kPTile, 1024);
+    const uint64_t kCs = L::desc(smem_u32(sCs), 0);
+    const uint64_t kdC = L::desc(smem_u32(sdC), 0), mdC = L::desc(smem_u32(sdC), SM::kState);
     auto issue_s = [&](uint32_t par) {  // S = Q K^T, dSb = dH V^T of the tile whose loads are in flight
       mbar_wait(&bar_full, par, 11);
       tc_fence_after_sync();
@@ -1143,15 +1219,15 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
         tc_fence_after_sync();
 #pragma unroll
         for (int kk = 0; kk < LT / 16; ++kk)  // dK1 = dS^T Q
-          umma_f16(tdK1, umma_desc_advance(mdS, kk * 2048), umma_desc_advance(mQ, kk * 2048), id_mn_mn, kk > 0);
+          umma_f16(tdK1, umma_desc_advance(mdS, kk * 2048), umma_desc_advance(mQ, kk * L::kAdvMN), id_mn_mn, kk > 0);
         umma_commit(&bar_a);  // Q consumed
 #pragma unroll
         for (int kk = 0; kk < LT / 16; ++kk)  // dQa = dS K
-          umma_f16(tdQa, umma_desc_advance(kdS, (kk / 4) * SM::kTile + (kk % 4) * 32), umma_desc_advance(mK, kk * 2048),
+          umma_f16(tdQa, umma_desc_advance(kdS, (kk / 4) * SM::kPTile + (kk % 4) * 32), umma_desc_advance(mK, kk * L::kAdvMN),
                    id_k_mn, kk > 0);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk)  // dV2 = K dC_k
-          umma_f16(tdV2, umma_desc_advance(kK, kk * 32), umma_desc_advance(mdC, kk * 2048), id_k_mn, kk > 0);
+          umma_f16(tdV2, umma_desc_advance(kK, kk * 32), umma_desc_advance(mdC, kk * L::kAdvMN), id_k_mn, kk > 0);
         umma_commit(&bar_b);  // K consumed
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk)  // dK2 = V dC_k^T
@@ -1169,11 +1245,11 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < LT / 16; ++kk)  // ddC = Qt^T dH
-          umma_f16(tddC, umma_desc_advance(mQt, kk * 2048), umma_desc_advance(mH, kk * 2048), id_c, kk > 0);
+          umma_f16(tddC, umma_desc_advance(mQt, kk * L::kAdvMN), umma_desc_advance(mH, kk * L::kAdvMN), id_c, kk > 0);
         umma_commit(&bar_d);
 #pragma unroll
         for (int kk = 0; kk < LT / 16; ++kk)  // dV1 = Sb'^T dH
-          umma_f16(tdV1, umma_desc_advance(mSb, kk * 2048), umma_desc_advance(mH, kk * 2048), id_mn_mn, kk > 0);
+          umma_f16(tdV1, umma_desc_advance(mSb, kk * 2048), umma_desc_advance(mH, kk * L::kAdvMN), id_mn_mn, kk > 0);
         umma_commit(&bar_v);  // dH consumed; dv complete
         if (c > 0) {
           const int r = mt(c - 1) * LT;
@@ -1394,12 +1470,12 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       TC_PROF(it, 3);
       // ---- Qt = wq . Q; keep this thread's q / k / v row slices for the gate gradients (overlaps MMAs)
       mbar_wait(&bar_full, par, 13);
-      uint32_t qs[16], ks[16], vs[16];
+      uint32_t qs[CW / 2], ks[CW / 2], vs[CW / 2];
       {
         const float wq = p.scale * bbar * rinv;  // bw.py:83-90
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t off = swz128(row, ch * 32 + 8 * j);
+        for (int j = 0; j < CW / 8; ++j) {
+          const uint32_t off = L::swz(row, ch * CW + 8 * j);
           uint4 u = *reinterpret_cast<const uint4*>(sQ + off);
           qs[4 * j] = u.x; qs[4 * j + 1] = u.y; qs[4 * j + 2] = u.z; qs[4 * j + 3] = u.w;
           float2 a0 = unpack2<T>(u.x), a1 = unpack2<T>(u.y), a2 = unpack2<T>(u.z), a3 = unpack2<T>(u.w);
@@ -1419,43 +1495,43 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       TC_PROF(it, 4);
       // ---- epilogues, pipelined with the MMA batch through three commits ------------------------------
       {
-        uint32_t ra[32], rq[32];
-        float o[32];
+        uint32_t ra[CW], rq[CW];
+        float o[CW];
         float dot;
         // dk
         mbar_wait(&bar_k, par, 18);
         tc_fence_after_sync();
         TC_PROF(it, 5);
-        tmem_ld32_nowait(tdK1 + lane_base + ch * 32, ra);
-        tmem_ld32_nowait(tdK2 + lane_base + ch * 32, rq);
+        tmem_ld_nowait(tdK1 + lane_base + ch * CW, ra);
+        tmem_ld_nowait(tdK2 + lane_base + ch * CW, rq);
         tmem_ld_wait();
         dot = 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < CW / 2; ++j) {
           o[2 * j] = p.scale * __uint_as_float(ra[2 * j]) + abar * __uint_as_float(rq[2 * j]);  // bw.py:170,192
           o[2 * j + 1] = p.scale * __uint_as_float(ra[2 * j + 1]) + abar * __uint_as_float(rq[2 * j + 1]);
           float2 kv = unpack2<T>(ks[j]);
           dot += kv.x * o[2 * j] + kv.y * o[2 * j + 1];
         }
-        store_row32<T>(sdK, row, ch * 32, o);
+        store_cols<T, D>(sdK, row, ch * CW, o);
         spart[(1 * 2 + ch) * LT + row] = dot;
         // dq
         mbar_wait(&bar_q, par, 16);
         tc_fence_after_sync();
         TC_PROF(it, 6);
-        tmem_ld32_nowait(tdQa + lane_base + ch * 32, ra);
-        tmem_ld32_nowait(tdQb + lane_base + ch * 32, rq);
+        tmem_ld_nowait(tdQa + lane_base + ch * CW, ra);
+        tmem_ld_nowait(tdQb + lane_base + ch * CW, rq);
         tmem_ld_wait();
         const float wb = bbar * rinv;
         dot = 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < CW / 2; ++j) {
           o[2 * j] = p.scale * (__uint_as_float(ra[2 * j]) + wb * __uint_as_float(rq[2 * j]));  // bw.py:169,193
           o[2 * j + 1] = p.scale * (__uint_as_float(ra[2 * j + 1]) + wb * __uint_as_float(rq[2 * j + 1]));
           float2 qv = unpack2<T>(qs[j]);
           dot += qv.x * o[2 * j] + qv.y * o[2 * j + 1];
         }
-        store_row32<T>(sdQ, row, ch * 32, o);
+        store_cols<T, D>(sdQ, row, ch * CW, o);
         spart[(0 * 2 + ch) * LT + row] = dot;
       }
       // ---- dC_{k-1} = gbar dC_k + ddC ----------------------------------------------------------------
@@ -1463,34 +1539,34 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       tc_fence_after_sync();
       TC_PROF(it, 7);
       {
-        float v[32];
-        tmem_ld32(tddC + lane_base + ch * 32, v);
+        float v[CW];
+        tmem_ld(tddC + lane_base + ch * CW, v);
         if (owns_c) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) dCreg[j] = gbar * dCreg[j] + v[j];  // bw.py:93-95
-          store_row32<T>(sdC, drow, ch * 32, dCreg);                       // dV2 / dK2 have completed (bar_k)
+          for (int j = 0; j < CW; ++j) dCreg[j] = gbar * dCreg[j] + v[j];  // bw.py:93-95
+          store_cols<T, D>(sdC, drow, ch * CW, dCreg);                     // dV2 / dK2 have completed (bar_k)
         }
       }
       // ---- dv last: dV1 = Sb'^T dH is the final MMA group of the batch ---------------------------------
       {
-        uint32_t ra[32], rq[32];
-        float o[32];
+        uint32_t ra[CW], rq[CW];
+        float o[CW];
         float dot;
         // dv
         mbar_wait(&bar_v, par, 17);
         tc_fence_after_sync();
-        tmem_ld32_nowait(tdV1 + lane_base + ch * 32, ra);
-        tmem_ld32_nowait(tdV2 + lane_base + ch * 32, rq);
+        tmem_ld_nowait(tdV1 + lane_base + ch * CW, ra);
+        tmem_ld_nowait(tdV2 + lane_base + ch * CW, rq);
         tmem_ld_wait();
         dot = 0.f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < CW / 2; ++j) {
           o[2 * j] = __uint_as_float(ra[2 * j]) + abar * __uint_as_float(rq[2 * j]);  // bw.py:164,190
           o[2 * j + 1] = __uint_as_float(ra[2 * j + 1]) + abar * __uint_as_float(rq[2 * j + 1]);
           float2 vv = unpack2<T>(vs[j]);
           dot += vv.x * o[2 * j] + vv.y * o[2 * j + 1];
         }
-        store_row32<T>(sdV, row, ch * 32, o);
+        store_cols<T, D>(sdV, row, ch * CW, o);
         spart[(2 * 2 + ch) * LT + row] = dot;
       }
       fence_proxy_async_smem();
@@ -1499,9 +1575,9 @@ tc_bw_d64(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUte
       TC_PROF(it, 8);
     }
     if (p.dc0 && owns_c) {  // dC_initial = dC_0 (bw.py:329-331)
-      float* dst = p.dc0 + ((int64_t)bh * D + drow) * D + ch * 32;
+      float* dst = p.dc0 + ((int64_t)bh * D + drow) * D + ch * CW;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) dst[j] = dCreg[j];
+      for (int j = 0; j < CW; ++j) dst[j] = dCreg[j];
     }
   }
   tc_fence_before_sync();
@@ -1521,11 +1597,11 @@ int num_sms() {
   return n;
 }
 
-template <typename T>
-int launch_fw_d64(const TcFwParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
-                  const CUtensorMap& mh, const CUtensorMap& mcs, cudaStream_t st) {
-  using SM = FwSmem<2>;
-  auto kern = p.rev ? tc_fw_d64<T, 2, true> : tc_fw_d64<T, 2, false>;
+template <typename T, int D>
+int launch_fw(const TcFwParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
+              const CUtensorMap& mh, const CUtensorMap& mcs, cudaStream_t st) {
+  using SM = FwSmem<D>;
+  auto kern = p.rev ? tc_fw<T, D, true> : tc_fw<T, D, false>;
   MLSTM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
   kern<<<p.B * p.NH, kTcThreads, SM::kBytes, st>>>(mq, mk, mv, mh, mcs, p);
   count_launch();
@@ -1544,19 +1620,33 @@ int launch_fw_d128(const TcFwParams& p, const CUtensorMap& mq, const CUtensorMap
   return 0;
 }
 
+template <typename T, int D>
+int launch_bw(const TcBwParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
+              const CUtensorMap& mdh, const CUtensorMap& mcs, const CUtensorMap& mdq, const CUtensorMap& mdk,
+              const CUtensorMap& mdv, cudaStream_t st) {
+  using SM = BwSmem<D>;
+  auto kern = p.rev ? tc_bw<T, D, true> : tc_bw<T, D, false>;
+  MLSTM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
+  kern<<<p.B * p.NH, kTcThreads, SM::kBytes, st>>>(mq, mk, mv, mdh, mcs, mdq, mdk, mdv, p);
+  MLSTM_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 bool tma_ok(const mlstm_b200_tensor& t) {
   return ((uintptr_t)t.ptr & 15) == 0 && t.stride[3] == 1 && (t.stride[0] % 8) == 0 && (t.stride[1] % 8) == 0 &&
          (t.stride[2] % 8) == 0;
 }
 
+// [128 tokens][min(D, 64)] boxes: D = 32 -> 64-byte rows / SWIZZLE_64B, otherwise 128-byte rows / SWIZZLE_128B
 int make_map(CUtensorMap* m, const mlstm_b200_tensor& t, const mlstm_b200_shape& s, int D) {
   return sm100_host::make_map_bhsd(m, t.ptr, s.dtype == MLSTM_B200_BF16, s.B, s.NH, s.S, D, t.stride[0], t.stride[1],
-                                   t.stride[2], LT);
+                                   t.stride[2], LT, D == 32 ? 32 : 64);
 }
+// c_states: (B, NH, NT, D, D) 16-bit, one [D][D] box per tile
 int make_states_map(CUtensorMap* m, const void* ptr, const mlstm_b200_shape& s) {
-  const int NT = (s.S + LT - 1) / LT;
-  return sm100_host::make_map_bhsd(m, ptr, s.dtype == MLSTM_B200_BF16, s.B, s.NH, NT * 64, 64, (int64_t)s.NH * NT * 4096,
-                                   (int64_t)NT * 4096, 64, 64);
+  const int NT = (s.S + LT - 1) / LT, D = s.DHQK;
+  return sm100_host::make_map_bhsd(m, ptr, s.dtype == MLSTM_B200_BF16, s.B, s.NH, NT * D, D, (int64_t)s.NH * NT * D * D,
+                                   (int64_t)NT * D * D, D, D, D);
 }
 
 int run_fw(const mlstm_b200_fw_args& a, void* c_states, cudaStream_t st) {
@@ -1569,7 +1659,7 @@ int run_fw(const mlstm_b200_fw_args& a, void* c_states, cudaStream_t st) {
   int r = make_map(&mq, a.q, s, s.DHQK) | make_map(&mk, a.k, s, s.DHQK) | make_map(&mv, a.v, s, s.DHHV) |
           make_map(&mh, a.h, s, s.DHHV);
   // without a c_states buffer the map is never used by the kernel; point it at h to keep it valid
-  r |= (c_states && s.DHQK == 64) ? make_states_map(&mcs, c_states, s) : make_map(&mcs, a.h, s, s.DHHV);
+  r |= (c_states && s.DHQK <= 64) ? make_states_map(&mcs, c_states, s) : make_map(&mcs, a.h, s, s.DHHV);
   if (r) {
     set_error("cuTensorMapEncodeTiled failed (%d)", r);
     return MLSTM_B200_ENODEVICE;
@@ -1592,8 +1682,12 @@ int run_fw(const mlstm_b200_fw_args& a, void* c_states, cudaStream_t st) {
     if (s.dtype == MLSTM_B200_BF16) return launch_fw_d128<__nv_bfloat16>(p, mq, mk, mv, mh, st);
     return launch_fw_d128<__half>(p, mq, mk, mv, mh, st);
   }
-  if (s.dtype == MLSTM_B200_BF16) return launch_fw_d64<__nv_bfloat16>(p, mq, mk, mv, mh, mcs, st);
-  return launch_fw_d64<__half>(p, mq, mk, mv, mh, mcs, st);
+  if (s.DHQK == 32) {
+    if (s.dtype == MLSTM_B200_BF16) return launch_fw<__nv_bfloat16, 32>(p, mq, mk, mv, mh, mcs, st);
+    return launch_fw<__half, 32>(p, mq, mk, mv, mh, mcs, st);
+  }
+  if (s.dtype == MLSTM_B200_BF16) return launch_fw<__nv_bfloat16, 64>(p, mq, mk, mv, mh, mcs, st);
+  return launch_fw<__half, 64>(p, mq, mk, mv, mh, mcs, st);
 }
 
 struct BwWs {
@@ -1614,11 +1708,11 @@ BwWs bw_ws(const mlstm_b200_shape& s) {
 
 void tensor_set_clock_buffer(void* dev_ptr) { g_prof = (long long*)dev_ptr; }
 
-// forward: d = 64 and d = 128; backward: d = 64 (d = 128 backward does not fit shared memory with 128-token tiles)
+// forward: d = 32, 64 and 128; backward: d = 32 and 64 (d = 128 backward does not fit shared memory with 128-token tiles)
 bool tensor_supported(const mlstm_b200_shape& s, int backward) {
   if (s.dtype != MLSTM_B200_BF16 && s.dtype != MLSTM_B200_F16) return false;
   if (s.DHQK != s.DHHV) return false;
-  if (s.DHQK != 64 && !(s.DHQK == 128 && !backward)) return false;
+  if (s.DHQK != 64 && s.DHQK != 32 && !(s.DHQK == 128 && !backward)) return false;
   if (s.chunk_size % 64 != 0 || s.S % 64 != 0) return false;
   return true;
 }
@@ -1626,7 +1720,7 @@ bool tensor_supported(const mlstm_b200_shape& s, int backward) {
 size_t tensor_states_bytes(const mlstm_b200_shape& s) {
   if (!tensor_supported(s, 1)) return 0;
   const size_t NT = (s.S + LT - 1) / LT;
-  return (size_t)s.B * s.NH * NT * 64 * 64 * 2;
+  return (size_t)s.B * s.NH * NT * s.DHQK * s.DHQK * 2;
 }
 
 // forward needs no scratch; backward needs room to recompute the states when c_states is absent
@@ -1660,9 +1754,10 @@ int tensor_bw(const mlstm_b200_bw_args& a, cudaStream_t st) {
     c_states = ws + w.off_states;
   }
   CUtensorMap mq, mk, mv, mdh, mcs, mdq, mdk, mdv;
-  int r = make_map(&mq, a.q, s, 64) | make_map(&mk, a.k, s, 64) | make_map(&mv, a.v, s, 64) | make_map(&mdh, a.dh, s, 64) |
-          make_states_map(&mcs, c_states, s) | make_map(&mdq, a.dq, s, 64) | make_map(&mdk, a.dk, s, 64) |
-          make_map(&mdv, a.dv, s, 64);
+  const int D = s.DHQK;
+  int r = make_map(&mq, a.q, s, D) | make_map(&mk, a.k, s, D) | make_map(&mv, a.v, s, D) | make_map(&mdh, a.dh, s, D) |
+          make_states_map(&mcs, c_states, s) | make_map(&mdq, a.dq, s, D) | make_map(&mdk, a.dk, s, D) |
+          make_map(&mdv, a.dv, s, D);
   if (r) {
     set_error("cuTensorMapEncodeTiled failed (%d)", r);
     return MLSTM_B200_ENODEVICE;
@@ -1681,15 +1776,14 @@ int tensor_bw(const mlstm_b200_bw_args& a, cudaStream_t st) {
   p.rev = s.reverse ? 1 : 0;
   p.sig = s.siging ? 1 : 0;
   p.prof = g_prof ? g_prof + 4096 : nullptr;
-  if (s.dtype == MLSTM_B200_BF16) {
-    auto kern = p.rev ? tc_bw_d64<__nv_bfloat16, true> : tc_bw_d64<__nv_bfloat16, false>;
-    MLSTM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwSmem::kBytes));
-    kern<<<s.B * s.NH, kTcThreads, BwSmem::kBytes, st>>>(mq, mk, mv, mdh, mcs, mdq, mdk, mdv, p);
-  } else {
-    auto kern = p.rev ? tc_bw_d64<__half, true> : tc_bw_d64<__half, false>;
-    MLSTM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BwSmem::kBytes));
-    kern<<<s.B * s.NH, kTcThreads, BwSmem::kBytes, st>>>(mq, mk, mv, mdh, mcs, mdq, mdk, mdv, p);
-  }
+  int e;
+  if (s.DHQK == 32)
+    e = s.dtype == MLSTM_B200_BF16 ? launch_bw<__nv_bfloat16, 32>(p, mq, mk, mv, mdh, mcs, mdq, mdk, mdv, st)
+                                   : launch_bw<__half, 32>(p, mq, mk, mv, mdh, mcs, mdq, mdk, mdv, st);
+  else
+    e = s.dtype == MLSTM_B200_BF16 ? launch_bw<__nv_bfloat16, 64>(p, mq, mk, mv, mdh, mcs, mdq, mdk, mdv, st)
+                                   : launch_bw<__half, 64>(p, mq, mk, mv, mdh, mcs, mdq, mdk, mdv, st);
+  if (e) return e;
   count_launch();
   MLSTM_CUDA_CHECK(cudaGetLastError());
   return 0;
