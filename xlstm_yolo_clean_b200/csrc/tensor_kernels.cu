@@ -1058,21 +1058,26 @@ struct BwSmem {
   static constexpr int kTile = Lay<D>::kTile;   // one [128][D] tile
   static constexpr int kPTile = LT * 128;       // one [128][64] half of Sb' / dS
   static constexpr int kState = Lay<D>::kState;
-  static constexpr int oQ = 0, oK = kTile, oV = 2 * kTile, odH = 3 * kTile;
-  static constexpr int oQt = 4 * kTile;         // wq . Q
-  static constexpr int oSb = 5 * kTile;         // Sb' two halves
+  // input ring: kNST stages of [Q | K | V | dH | C_{k-1}].  D = 64 has room for one stage (its tiles are
+  // re-filled one by one as the MMA batch releases them); D = 32 prefetches a whole tile ahead.
+  static constexpr int kNST = D == 64 ? 1 : 2;
+  static constexpr int kStage = 4 * kTile + kState;
+  static constexpr int oQ = 0, oK = kTile, oV = 2 * kTile, odH = 3 * kTile, oCs = 4 * kTile;  // inside a stage
+  static constexpr int oQt = kNST * kStage;     // wq . Q
+  static constexpr int oSb = oQt + kTile;       // Sb' two halves
   static constexpr int odS = oSb + 2 * kPTile;  // dS  two halves
   static constexpr int odQ = odS + 2 * kPTile;  // dq / dv / dk staging (their stores overlap the next tile's W phase)
   static constexpr int odV = odQ + kTile;
   static constexpr int odK = odV + kTile;
-  static constexpr int oCs = odK + kTile;       // C_{k-1}, D x D bf16 (TMA)
-  static constexpr int odC = oCs + kState;      // dC_k bf16 operand copy
+  static constexpr int odC = odK + kTile;       // dC_k bf16 operand copy
   static constexpr int oSmall = odC + kState;
   // floats: gates[2], spart[2][6][LT]
   static constexpr int fGates = 0, fPart = 2 * GateBuf::kFloats, kSmallFloats = fPart + 12 * LT;
   static constexpr int kBytes = oSmall + kSmallFloats * 4 + 1024;
   static constexpr uint32_t kLoadBytes = 4 * kTile + kState;
-  // TMEM columns.  D = 64: the S / dSb columns are re-used by the dV / dK accumulators.  D = 32: nothing aliases.
+  // TMEM columns.  D = 64: the S / dSb columns are re-used by the dV / dK accumulators.  D = 32: nothing aliases,
+  // so S / dSb of the next tile are issued right behind the MMA batch and overlap the epilogues.
+  static constexpr bool kAlias = D == 64;
   static constexpr uint32_t cS = 0, cdSb = 128;
   static constexpr uint32_t cdV1 = D == 64 ? 0 : 256, cdV2 = cdV1 + D, cdK1 = D == 64 ? 128 : 320, cdK2 = cdK1 + D,
                             cdQa = D == 64 ? 256 : 384, cdQb = cdQa + D, cddC = D == 64 ? 384 : 448;
@@ -1090,7 +1095,7 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
   constexpr int CW = L::CW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sQ = smem + SM::oQ;
+  uint8_t* sQ = smem + SM::oQ;  // stage 0; stage s is SM::kStage bytes further
   uint8_t* sK = smem + SM::oK;
   uint8_t* sV = smem + SM::oV;
   uint8_t* sdH = smem + SM::odH;
@@ -1103,7 +1108,7 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
   uint8_t* sCs = smem + SM::oCs;
   uint8_t* sdC = smem + SM::odC;
   float* fsm = (float*)(smem + SM::oSmall);
-  __shared__ uint64_t bar_full, bar_s, bar_q, bar_v, bar_k, bar_d, bar_a, bar_b, bar_g[2];
+  __shared__ uint64_t bar_full[SM::kNST], bar_s, bar_q, bar_v, bar_k, bar_d, bar_a, bar_b, bar_g[2];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -1111,7 +1116,7 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
   const int bh = blockIdx.x, b = bh / p.NH, hh = bh % p.NH;
 
   if (tid == 0) {
-    mbar_init(&bar_full, 1);
+    for (int s = 0; s < SM::kNST; ++s) mbar_init(&bar_full[s], 1);
     mbar_init(&bar_s, 1);
     mbar_init(&bar_a, 1);
     mbar_init(&bar_b, 1);
@@ -1164,30 +1169,36 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
 
   if (warp == kCtlWarp) {
     // =========================== control warp ===================================================
-    auto issue_loads = [&](int c) {
-      mbar_expect_tx(&bar_full, SM::kLoadBytes);
-      tma_load_4d(sQ, &mapQ, &bar_full, 0, mt(c) * LT, hh, b);
-      tma_load_4d(sK, &mapK, &bar_full, 0, mt(c) * LT, hh, b);
-      tma_load_4d(sV, &mapV, &bar_full, 0, mt(c) * LT, hh, b);
-      tma_load_4d(sdH, &mapdH, &bar_full, 0, mt(c) * LT, hh, b);
-      tma_load_4d(sCs, &mapCs, &bar_full, 0, mt(c) * D, hh, b);
+    auto load_stage = [&](int s, int c) {  // every input tile of memory tile mt(c) into stage s
+      uint8_t* base = smem + s * SM::kStage;
+      mbar_expect_tx(&bar_full[s], SM::kLoadBytes);
+      tma_load_4d(base + SM::oQ, &mapQ, &bar_full[s], 0, mt(c) * LT, hh, b);
+      tma_load_4d(base + SM::oK, &mapK, &bar_full[s], 0, mt(c) * LT, hh, b);
+      tma_load_4d(base + SM::oV, &mapV, &bar_full[s], 0, mt(c) * LT, hh, b);
+      tma_load_4d(base + SM::odH, &mapdH, &bar_full[s], 0, mt(c) * LT, hh, b);
+      tma_load_4d(base + SM::oCs, &mapCs, &bar_full[s], 0, mt(c) * D, hh, b);
     };
     constexpr uint32_t id_s = umma_idesc(128, 128, false, false, kBf16);
     constexpr uint32_t id_c = umma_idesc(64, D, true, true, kBf16);
     constexpr uint32_t id_k_mn = umma_idesc(128, D, false, true, kBf16);   // A K-major, B MN-major
     constexpr uint32_t id_mn_mn = umma_idesc(128, D, true, true, kBf16);   // A MN-major, B MN-major
     constexpr uint32_t id_k_k = umma_idesc(128, D, false, false, kBf16);   // A K-major, B K-major
-    const uint64_t kQ = L::desc(smem_u32(sQ), 0), mQ = L::desc(smem_u32(sQ), SM::kTile);
-    const uint64_t kK = L::desc(smem_u32(sK), 0), mK = L::desc(smem_u32(sK), SM::kTile);
-    const uint64_t kV = L::desc(smem_u32(sV), 0);
-    const uint64_t kH = L::desc(smem_u32(sdH), 0), mH = L::desc(smem_u32(sdH), SM::kTile);
+    // stage-0 descriptors; stage s adds s * kStage (warp-uniform)
+    const uint64_t kQ0 = L::desc(smem_u32(sQ), 0), mQ0 = L::desc(smem_u32(sQ), SM::kTile);
+    const uint64_t kK0 = L::desc(smem_u32(sK), 0), mK0 = L::desc(smem_u32(sK), SM::kTile);
+    const uint64_t kV0 = L::desc(smem_u32(sV), 0);
+    const uint64_t kH0 = L::desc(smem_u32(sdH), 0), mH0 = L::desc(smem_u32(sdH), SM::kTile);
+    const uint64_t kCs0 = L::desc(smem_u32(sCs), 0);
     const uint64_t mQt = L::desc(smem_u32(sQt), D == 64 ? SM::kTile : 0);  // D = 32: rows 32-63 of the M = 64 MMA re-read the block
     const uint64_t mSb = umma_smem_desc(smem_u32(sSb), SM::kPTile, 1024);
     const uint64_t kdS = umma_smem_desc(smem_u32(sdS), 0, 1024), mdS = umma_smem_desc(smem_u32(sdS), SM::kPTile, 1024);
-    const uint64_t kCs = L::desc(smem_u32(sCs), 0);
     const uint64_t kdC = L::desc(smem_u32(sdC), 0), mdC = L::desc(smem_u32(sdC), SM::kState);
-    auto issue_s = [&](uint32_t par) {  // S = Q K^T, dSb = dH V^T of the tile whose loads are in flight
-      mbar_wait(&bar_full, par, 11);
+    auto issue_s = [&](int it) {  // S = Q K^T, dSb = dH V^T of processing step `it` (its loads are in flight)
+      const int s = it % SM::kNST;
+      const uint32_t so = (uint32_t)s * SM::kStage;
+      const uint64_t kQ = umma_desc_advance(kQ0, so), kK = umma_desc_advance(kK0, so);
+      const uint64_t kH = umma_desc_advance(kH0, so), kV = umma_desc_advance(kV0, so);
+      mbar_wait(&bar_full[s], (it / SM::kNST) & 1, 11);
       tc_fence_after_sync();
 #pragma unroll
       for (int kk = 0; kk < D / 16; ++kk)
@@ -1198,7 +1209,8 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       umma_commit(&bar_s);
     };
 
-    if (lane == 0) issue_loads(p.NT - 1);
+    if (lane == 0)
+      for (int s = 0; s < SM::kNST && s < p.NT; ++s) load_stage(s, p.NT - 1 - s);
     __syncwarp();
     if (elect_one()) issue_s(0);
     __syncwarp();
@@ -1207,6 +1219,11 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       const int c = p.NT - 1 - it, pb = it & 1;
       const uint32_t par = it & 1;
       const int t0 = mt(c) * LT, n_valid = min(LT, p.S - t0);
+      const uint32_t so = (uint32_t)(it % SM::kNST) * SM::kStage;
+      const uint64_t kQ = umma_desc_advance(kQ0, so), mQ = umma_desc_advance(mQ0, so);
+      const uint64_t kK = umma_desc_advance(kK0, so), mK = umma_desc_advance(mK0, so);
+      const uint64_t kV = umma_desc_advance(kV0, so), kCs = umma_desc_advance(kCs0, so);
+      const uint64_t kH = umma_desc_advance(kH0, so), mH = umma_desc_advance(mH0, so);
       TC_PROF(it, 9);
       named_sync(NB_B, kNbAB);  // Sb', dS written
       TC_PROF(it, 10);
@@ -1251,19 +1268,25 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
         for (int kk = 0; kk < LT / 16; ++kk)  // dV1 = Sb'^T dH
           umma_f16(tdV1, umma_desc_advance(mSb, kk * 2048), umma_desc_advance(mH, kk * L::kAdvMN), id_mn_mn, kk > 0);
         umma_commit(&bar_v);  // dH consumed; dv complete
-        if (c > 0) {
-          const int r = mt(c - 1) * LT;
-          mbar_expect_tx(&bar_full, SM::kLoadBytes);
-          mbar_wait(&bar_a, par, 21);
-          tma_load_4d(sQ, &mapQ, &bar_full, 0, r, hh, b);
-          mbar_wait(&bar_b, par, 22);
-          tma_load_4d(sK, &mapK, &bar_full, 0, r, hh, b);
-          mbar_wait(&bar_k, par, 23);
-          tma_load_4d(sV, &mapV, &bar_full, 0, r, hh, b);
-          mbar_wait(&bar_q, par, 24);
-          tma_load_4d(sCs, &mapCs, &bar_full, 0, mt(c - 1) * D, hh, b);
+        if (!SM::kAlias && c > 0) issue_s(it + 1);  // next tile's S / dSb queue up behind the batch
+        if (SM::kNST == 1) {
+          if (c > 0) {  // re-fill the single stage tile by tile, each as soon as its last reader has completed
+            const int r = mt(c - 1) * LT;
+            mbar_expect_tx(&bar_full[0], SM::kLoadBytes);
+            mbar_wait(&bar_a, par, 21);
+            tma_load_4d(sQ, &mapQ, &bar_full[0], 0, r, hh, b);
+            mbar_wait(&bar_b, par, 22);
+            tma_load_4d(sK, &mapK, &bar_full[0], 0, r, hh, b);
+            mbar_wait(&bar_k, par, 23);
+            tma_load_4d(sV, &mapV, &bar_full[0], 0, r, hh, b);
+            mbar_wait(&bar_q, par, 24);
+            tma_load_4d(sCs, &mapCs, &bar_full[0], 0, mt(c - 1) * D, hh, b);
+            mbar_wait(&bar_v, par, 25);
+            tma_load_4d(sdH, &mapdH, &bar_full[0], 0, r, hh, b);
+          }
+        } else if (c >= SM::kNST) {  // this stage is free once the whole batch has completed
           mbar_wait(&bar_v, par, 25);
-          tma_load_4d(sdH, &mapdH, &bar_full, 0, r, hh, b);
+          load_stage(it % SM::kNST, c - SM::kNST);
         }
       }
       __syncwarp();
@@ -1277,7 +1300,7 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
         tma_store_commit();
       }
       __syncwarp();
-      if (c > 0 && elect_one()) issue_s(par ^ 1);  // S / dSb of the next tile (their TMEM columns were read by this epilogue)
+      if (SM::kAlias && c > 0 && elect_one()) issue_s(it + 1);  // S / dSb of the next tile (their TMEM columns were read by this epilogue)
       __syncwarp();
     }
     if (lane == 0) tma_store_wait_all<0>();
@@ -1398,6 +1421,7 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       float* spart = fsm + SM::fPart + pb * 6 * LT;
       const int n_valid = min(LT, p.S - mt(p.NT - 1 - it) * LT);
       const bool valid = row < n_valid;
+      const uint32_t so = (uint32_t)(it % SM::kNST) * SM::kStage;  // input stage of this tile
 
       TC_PROF(it, 0);
       mbar_wait(&bar_g[pb], (it >> 1) & 1, 12);
@@ -1469,14 +1493,14 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       named_arrive(NB_B, kNbAB);
       TC_PROF(it, 3);
       // ---- Qt = wq . Q; keep this thread's q / k / v row slices for the gate gradients (overlaps MMAs)
-      mbar_wait(&bar_full, par, 13);
+      mbar_wait(&bar_full[it % SM::kNST], (it / SM::kNST) & 1, 13);
       uint32_t qs[CW / 2], ks[CW / 2], vs[CW / 2];
       {
         const float wq = p.scale * bbar * rinv;  // bw.py:83-90
 #pragma unroll
         for (int j = 0; j < CW / 8; ++j) {
           const uint32_t off = L::swz(row, ch * CW + 8 * j);
-          uint4 u = *reinterpret_cast<const uint4*>(sQ + off);
+          uint4 u = *reinterpret_cast<const uint4*>(sQ + so + off);
           qs[4 * j] = u.x; qs[4 * j + 1] = u.y; qs[4 * j + 2] = u.z; qs[4 * j + 3] = u.w;
           float2 a0 = unpack2<T>(u.x), a1 = unpack2<T>(u.y), a2 = unpack2<T>(u.z), a3 = unpack2<T>(u.w);
           u.x = pack2<T>(a0.x * wq, a0.y * wq);
@@ -1484,9 +1508,9 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
           u.z = pack2<T>(a2.x * wq, a2.y * wq);
           u.w = pack2<T>(a3.x * wq, a3.y * wq);
           *reinterpret_cast<uint4*>(sQt + off) = u;
-          uint4 uk = *reinterpret_cast<const uint4*>(sK + off);
+          uint4 uk = *reinterpret_cast<const uint4*>(sK + so + off);
           ks[4 * j] = uk.x; ks[4 * j + 1] = uk.y; ks[4 * j + 2] = uk.z; ks[4 * j + 3] = uk.w;
-          uint4 uv = *reinterpret_cast<const uint4*>(sV + off);
+          uint4 uv = *reinterpret_cast<const uint4*>(sV + so + off);
           vs[4 * j] = uv.x; vs[4 * j + 1] = uv.y; vs[4 * j + 2] = uv.z; vs[4 * j + 3] = uv.w;
         }
       }
