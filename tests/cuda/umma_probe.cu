@@ -358,6 +358,86 @@ int run_sw(const char* name, int M, int N, int K, int a_mn, int a_rowb, int b_mn
   return maxerr < 1e-2 ? 0 : 1;
 }
 
+// A operand in TMEM (TS mode): every thread writes its row of A with tcgen05.st (two bf16 per column),
+// B from shared memory (MN-major, 128- or 64-byte rows).  M = 128, K = 128.
+__global__ void __launch_bounds__(128) probe_ts(OpLayout LB, int N, const bf16* gA, const bf16* gB, float* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sB = smem;
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  constexpr int K = 128;
+  for (int e = tid; e < LB.mn * LB.k; e += 128) *(bf16*)(sB + op_offset(LB, e / LB.k, e % LB.k)) = gB[e];
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc<256>(&tmem_base_s);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t tA = tmem + 128;  // 64 columns of packed A
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  for (int c0 = 0; c0 < K / 2; c0 += 16) {
+    uint32_t r[16];
+    for (int j = 0; j < 16; ++j) {
+      const uint16_t lo = *(const uint16_t*)&gA[tid * K + 2 * (c0 + j)];
+      const uint16_t hi = *(const uint16_t*)&gA[tid * K + 2 * (c0 + j) + 1];
+      r[j] = (uint32_t)lo | ((uint32_t)hi << 16);
+    }
+    tmem_st16(tA + lane_base + c0, r);
+  }
+  tmem_st_wait();
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0 && elect_one()) {
+    tc_fence_after_sync();
+    const uint32_t idesc = umma_idesc(128, N, false, LB.mn_major, true);
+    for (int kk = 0; kk < K / 16; ++kk) umma_f16_ts(tmem, tA + kk * 8, op_desc(LB, smem_u32(sB), kk, 0), idesc, kk > 0);
+    umma_commit(&bar);
+  }
+  __syncwarp();
+  mbar_wait(&bar, 0, 104);
+  tc_fence_after_sync();
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    float v[32];
+    tmem_ld32(tmem + lane_base + c0, v);
+    for (int j = 0; j < 32 && c0 + j < N; ++j) out[tid * N + c0 + j] = v[j];
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
+int run_ts(const char* name, int N, int b_mn, int b_rowb) {
+  const int M = 128, K = 128;
+  OpLayout LB{N, K, b_mn, b_rowb};
+  std::vector<bf16> hA(M * K), hB(N * K);
+  std::vector<float> fA(M * K), fB(N * K);
+  for (int i = 0; i < M * K; ++i) { bf16 x = __float2bfloat16(frand()); hA[i] = x; fA[i] = __bfloat162float(x); }
+  for (int i = 0; i < N * K; ++i) { bf16 x = __float2bfloat16(frand()); hB[i] = x; fB[i] = __bfloat162float(x); }
+  bf16 *dA, *dB; float* dO;
+  cudaMalloc(&dA, M * K * 2); cudaMalloc(&dB, N * K * 2); cudaMalloc(&dO, M * N * 4);
+  cudaMemcpy(dA, hA.data(), M * K * 2, cudaMemcpyHostToDevice);
+  cudaMemcpy(dB, hB.data(), N * K * 2, cudaMemcpyHostToDevice);
+  cudaMemset(dO, 0xff, M * N * 4);
+  size_t smem = 32768 + 2048;
+  cudaFuncSetAttribute(probe_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  probe_ts<<<1, 128, smem>>>(LB, N, dA, dB, dO);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("%s: FAIL kernel error %s\n", name, cudaGetErrorString(e)); return 2; }
+  std::vector<float> hO(M * N);
+  cudaMemcpy(hO.data(), dO, M * N * 4, cudaMemcpyDeviceToHost);
+  double maxerr = 0;
+  for (int m = 0; m < M; ++m) for (int n = 0; n < N; ++n) {
+    double ref = 0; for (int k = 0; k < K; ++k) ref += (double)fA[m * K + k] * fB[n * K + k];
+    double d = fabs(ref - hO[m * N + n]); if (!(d <= maxerr)) maxerr = d;
+  }
+  printf("%s: %s  max|err|=%.3e\n", name, maxerr < 1e-2 ? "PASS" : "FAIL", maxerr);
+  cudaFree(dA); cudaFree(dB); cudaFree(dO);
+  return maxerr < 1e-2 ? 0 : 1;
+}
+
 int sw64_main() {
   int bad = 0;
   bad += run_sw("S d32      M128 N128 K32  A:K/64  B:K/64 ", 128, 128, 32, 0, 64, 0, 64, 128);
@@ -368,6 +448,9 @@ int sw64_main() {
   bad += run_sw("SbT dH d32 M128 N32  K128 A:MN/128 B:MN/64", 128, 32, 128, 1, 128, 1, 64, 128);
   bad += run_sw("dH CT d32  M128 N32  K32  A:K/64  B:K/64 ", 128, 32, 32, 0, 64, 0, 64, 128);
   bad += run_sw("ref d64    M128 N64  K128 A:MN/128 B:MN/128", 128, 64, 128, 1, 128, 1, 128, 128);
+  bad += run_ts("TS PV d64  M128 N64  K128 A:TMEM   B:MN/128", 64, 1, 128);
+  bad += run_ts("TS PV d32  M128 N32  K128 A:TMEM   B:MN/64", 32, 1, 64);
+  bad += run_ts("TS    d64  M128 N64  K128 A:TMEM   B:K/128", 64, 0, 128);
   printf("%d sw64 variant(s) failed\n", bad);
   return bad ? 1 : 0;
 }

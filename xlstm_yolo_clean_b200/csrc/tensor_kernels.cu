@@ -36,7 +36,7 @@ constexpr int kCtlWarp = 8, kScanWarp = 9;
 constexpr int kNbAB = kWorkers + 32;  // workers + control
 constexpr int kNbC = kWorkers + 64;   // workers + control + scan
 constexpr float kLog2e = 1.4426950408889634f;
-enum { NB_A = 1, NB_B = 2, NB_C = 3 };  // named barriers: operand ready / P ready / epilogue done
+enum { NB_A = 1, NB_B = 2, NB_C = 3, NB_PAIR0 = 4 };  // named barriers: operand ready / P ready / epilogue done / warp pairs (4..7)
 
 // per-tile gate vectors produced by the control warp (floats)
 struct GateBuf {
@@ -295,15 +295,13 @@ struct TcFwParams {
 template <int D_>
 struct FwSmem {
   static constexpr int D = D_;
-  static constexpr int NSTAGE = 2;                   // Q / K / V ring
+  static constexpr int NSTAGE = 3;                   // Q / K / V ring: two tiles in flight while one is consumed
   static constexpr int kTile = Lay<D>::kTile;        // one [128][D] 16-bit tile
-  static constexpr int kPTile = LT * 128;            // one [128][64] half of P
   static constexpr int oQ = 0;                       // [NSTAGE] Q tiles
   static constexpr int oK = oQ + NSTAGE * kTile;
   static constexpr int oV = oK + NSTAGE * kTile;
   static constexpr int oKb = oV + NSTAGE * kTile;    // abar . K
-  static constexpr int oP = oKb + kTile;             // P: two K-halves
-  static constexpr int oH = oP + 2 * kPTile;         // h staging
+  static constexpr int oH = oKb + kTile;             // h staging
   static constexpr int oC = oH + kTile;              // bf16 copy of C (D x D), MMA B operand
   static constexpr int oSmall = oC + Lay<D>::kState;
   // floats: gates[2], srs[2][2][LT], sqn[2][2][LT], npart[2][4][D], sN[2][D]
@@ -311,7 +309,10 @@ struct FwSmem {
                        fN = fNp + 8 * D, kSmallFloats = fN + 2 * D;
   static constexpr int kBytes = oSmall + kSmallFloats * 4 + 1024 /*alignment slack*/;
   // TMEM columns.  D = 64: S double-buffered by tile parity (512 columns, one CTA per SM).  D = 32: one S
-  // buffer, 256 columns, so that two CTAs share an SM (S(k+1) is issued after P(k) has been read).
+  // buffer, 256 columns, so that two CTAs share an SM (S(k+1) is issued behind the MMAs that read P(k)).
+  // P (16-bit, the A operand of P V) never goes through shared memory: each thread packs its S row in
+  // place -- the 16 packed columns of 32-column unit u overwrite S columns 32u .. 32u+15, which only the
+  // writing warp has read -- and the MMA takes A from TMEM.
   static constexpr int kTmemCols = D == 64 ? 512 : 256;
   static constexpr uint32_t cS0 = 0, cS1 = D == 64 ? 128 : 0, cHi = D == 64 ? 256 : 128, cHx = cHi + D,
                             cDC = D == 64 ? 384 : 192;
@@ -330,7 +331,6 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   float* fsm = (float*)(smem + SM::oSmall);
   uint8_t* sKb = smem + SM::oKb;
-  uint8_t* sP = smem + SM::oP;
   uint8_t* sH = smem + SM::oH;
   uint8_t* sC = smem + SM::oC;
   __shared__ uint64_t bar_full[NSTAGE], bar_s, bar_dc, bar_h, bar_g[2], bar_n;
@@ -347,7 +347,7 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
     mbar_init(&bar_h, 1);
     mbar_init(&bar_g[0], 1);
     mbar_init(&bar_g[1], 1);
-    mbar_init(&bar_n, D);
+    mbar_init(&bar_n, D / 32);  // one arrival per warp that finalises n
     fence_mbar_init();
   }
   if (warp == kCtlWarp) {
@@ -404,23 +404,19 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
     constexpr uint32_t id_dc = umma_idesc(64, D, true, true, kBf16);
     constexpr uint32_t id_h = umma_idesc(128, D, false, true, kBf16);
     const uint64_t dKb = L::desc(smem_u32(sKb), D == 64 ? SM::kTile : 0);  // D = 32: rows 32-63 of the M = 64 MMA re-read the block
-    const uint64_t dP = umma_smem_desc(smem_u32(sP), 0, 1024);
     const uint64_t dC = L::desc(smem_u32(sC), L::kState);
-    // Every shared-memory descriptor is loop invariant and provably warp-uniform (the stage / TMEM
-    // parity is a compile-time constant of the two-tile unrolled body), so the tcgen05.mma operands
+    // Every shared-memory descriptor is provably warp-uniform (stage-0 descriptor + stage index * tile bytes;
+    // the TMEM parity is a compile-time constant of the two-tile unrolled body), so the tcgen05.mma operands
     // live in uniform registers instead of going through a per-instruction R2UR waterfall.
     const uint64_t dQ0 = L::desc(smem_u32(smem + SM::oQ), 0);
     const uint64_t dK0 = L::desc(smem_u32(smem + SM::oK), 0);
     const uint64_t dV0 = L::desc(smem_u32(smem + SM::oV), SM::kTile);
-    const uint64_t dQ1 = umma_desc_advance(dQ0, (NSTAGE - 1) * SM::kTile);
-    const uint64_t dK1 = umma_desc_advance(dK0, (NSTAGE - 1) * SM::kTile);
-    const uint64_t dV1 = umma_desc_advance(dV0, (NSTAGE - 1) * SM::kTile);
     auto issue_s = [&](int c, auto PAR) {  // S(c) = Q K^T into the TMEM buffer of the tile's parity
       constexpr int par = decltype(PAR)::value;
-      constexpr int s = par % NSTAGE;
+      const int s = c % NSTAGE;
       mbar_wait(&bar_full[s], (c / NSTAGE) & 1, 1);
       tc_fence_after_sync();
-      const uint64_t dQ = par ? dQ1 : dQ0, dK = par ? dK1 : dK0;
+      const uint64_t dQ = umma_desc_advance(dQ0, s * SM::kTile), dK = umma_desc_advance(dK0, s * SM::kTile);
       const uint32_t tS = par ? tS1 : tS0;
 #pragma unroll
       for (int kk = 0; kk < D / 16; ++kk)
@@ -437,8 +433,8 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
 
     auto tile_body = [&](int c, auto PAR) {
       constexpr int par = decltype(PAR)::value;
-      constexpr int s = par % NSTAGE;
-      const uint64_t dQ = par ? dQ1 : dQ0, dV = par ? dV1 : dV0;
+      const int s = c % NSTAGE;
+      const uint64_t dQ = umma_desc_advance(dQ0, s * SM::kTile), dV = umma_desc_advance(dV0, s * SM::kTile);
       TC_PROF(c, 9);
       named_sync(NB_B, kNbAB);  // P(c) written
       if (lane == 0) {
@@ -449,9 +445,8 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       if (elect_one()) {  // elect.sync lets ptxas emit straight-line UTCHMMA (no per-instruction thread loop)
         tc_fence_after_sync();
 #pragma unroll
-        for (int kk = 0; kk < LT / 16; ++kk)  // Hintra = P V
-          umma_f16(tHi, umma_desc_advance(dP, (kk / 4) * SM::kPTile + (kk % 4) * 32), umma_desc_advance(dV, kk * L::kAdvMN), id_h,
-                   kk > 0);
+        for (int kk = 0; kk < LT / 16; ++kk)  // Hintra = P V, A = P from TMEM (packed inside the S columns)
+          umma_f16_ts(tHi, (par ? tS1 : tS0) + 32 * (kk / 2) + 8 * (kk % 2), umma_desc_advance(dV, kk * L::kAdvMN), id_h, kk > 0);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk)  // Hinter = Q C_{k-1}
           umma_f16(tHx, umma_desc_advance(dQ, kk * 32), umma_desc_advance(dC, kk * L::kAdvMN), id_h, kk > 0);
@@ -526,21 +521,6 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       const float gbar = __expf(g + m_run - m_next);                    // fw.py:106
       const float b_t = gb[GateBuf::oB + row], i_t = gb[GateBuf::oI + row];
       const float m_t = p.sig ? 0.f : b_t + fmaxf(m_run, gb[GateBuf::oPm + row]);  // fw.py:178-184
-      mbar_wait(&bar_full[s], par_full, 3);
-      if (c > 0) mbar_wait(&bar_n, (c - 1) & 1, 4);  // n_{k-1} finalised
-      // ---- partial q . n_{k-1} over this thread's 32 columns ---------------------------------------
-      {
-        float qn = 0.f;
-#pragma unroll
-        for (int j = 0; j < CW / 8; ++j) {
-          uint4 q = *reinterpret_cast<const uint4*>(sQ + L::swz(row, ch * CW + 8 * j));
-          float2 q0 = unpack2<T>(q.x), q1 = unpack2<T>(q.y), q2 = unpack2<T>(q.z), q3 = unpack2<T>(q.w);
-          const float4 n0 = *reinterpret_cast<const float4*>(sNc + ch * CW + 8 * j);
-          const float4 n1 = *reinterpret_cast<const float4*>(sNc + ch * CW + 8 * j + 4);
-          qn += q0.x * n0.x + q0.y * n0.y + q1.x * n0.z + q1.y * n0.w + q2.x * n1.x + q2.y * n1.y + q3.x * n1.z + q3.y * n1.w;
-        }
-        sqn[ch * LT + row] = qn;
-      }
       TC_PROF(c, 1);
       // ---- P = S . D (causal), row sums ----------------------------------------------------------
       mbar_wait(&bar_s, par, 5);
@@ -582,21 +562,39 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
                 v[j] = pv;
               }
             }
-          } else {
-            if (c > 0) continue;  // blocks above the diagonal stay zero (P has its own buffer)
+          } else {  // above the diagonal: zeros (the S MMA of every tile overwrites these columns)
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
-          store_row32<T>(sP, row, u * 32, v);
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) pk[j] = pack2<T>(v[2 * j], v[2 * j + 1]);
+          tmem_st16(tS + lane_base + u * 32, pk);
         }
         srs[ch * LT + row] = rs;
       }
       TC_PROF(c, 3);
-      fence_proxy_async_smem();
+      tmem_st_wait();
       TC_PROF(c, 4);
       tc_fence_before_sync();
       named_arrive(NB_B, kNbAB);
       TC_PROF(c, 5);
+      // (the loads and n_{k-1} are only needed from here on: their waits stay off the S -> P -> PV chain)
+      mbar_wait(&bar_full[s], par_full, 3);
+      if (c > 0) mbar_wait(&bar_n, (c - 1) & 1, 4);  // n_{k-1} finalised
+      // ---- partial q . n_{k-1} over this thread's 32 columns ---------------------------------------
+      {
+        float qn = 0.f;
+#pragma unroll
+        for (int j = 0; j < CW / 8; ++j) {
+          uint4 q = *reinterpret_cast<const uint4*>(sQ + L::swz(row, ch * CW + 8 * j));
+          float2 q0 = unpack2<T>(q.x), q1 = unpack2<T>(q.y), q2 = unpack2<T>(q.z), q3 = unpack2<T>(q.w);
+          const float4 n0 = *reinterpret_cast<const float4*>(sNc + ch * CW + 8 * j);
+          const float4 n1 = *reinterpret_cast<const float4*>(sNc + ch * CW + 8 * j + 4);
+          qn += q0.x * n0.x + q0.y * n0.y + q1.x * n0.z + q1.y * n0.w + q2.x * n1.x + q2.y * n1.y + q3.x * n1.z + q3.y * n1.w;
+        }
+        sqn[ch * LT + row] = qn;
+      }
       // ---- Kbar = abar . K (this thread: row, 32 columns); column sums for n (overlaps the H MMAs) --
       {
         const float ab = __expf(g - b_t + i_t - m_next);  // fw.py:102 (exp(-inf) = 0 for tail tokens)
@@ -624,6 +622,7 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
         tmem_ld_nowait(tHi + lane_base + ch * CW, hi);
         tmem_ld_nowait(tHx + lane_base + ch * CW, hx);
         const float bq = __expf(b_t + m_run - m_t) * p.scale;                          // fw.py:197-198
+        named_sync(NB_PAIR0 + rb, 64);  // the partner warp (other column half of these rows) has written its q.n partial
         const float den = bq * (sqn[row] + sqn[LT + row]) + srs[row] + srs[LT + row];  // fw.py:204-206
         const float nmax = fmaxf(fabsf(den), __expf(-m_t));                            // fw.py:208-210
         const float inv = 1.f / (nmax + p.eps);
@@ -648,9 +647,10 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
           for (int j = 0; j < CW; ++j) Creg[j] = gbar * Creg[j] + v[j];
           store_cols<T, D>(sC, drow, ch * CW, Creg);  // Q C_{k-1} (bar_h) has finished reading the old copy
         }
-        if (tid < D) {  // n_k = gbar n_{k-1} + column sums of Kbar (fw.py:116)
+        if (warp < D / 32) {  // n_k = gbar n_{k-1} + column sums of Kbar (fw.py:116)
           sNn[tid] = gbar * sNc[tid] + ((snp[tid] + snp[D + tid]) + (snp[2 * D + tid] + snp[3 * D + tid]));
-          mbar_arrive(&bar_n);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bar_n);
         }
       }
       fence_proxy_async_smem();
