@@ -302,11 +302,12 @@ struct FwSmem {
   static constexpr int oV = oK + NSTAGE * kTile;
   static constexpr int oKb = oV + NSTAGE * kTile;    // abar . K
   static constexpr int oH = oKb + kTile;             // h staging
-  static constexpr int oC = oH + kTile;              // bf16 copy of C (D x D), MMA B operand
-  static constexpr int oSmall = oC + Lay<D>::kState;
-  // floats: gates[2], srs[2][2][LT], sqn[2][2][LT], npart[2][4][D], sN[2][D]
-  static constexpr int fGates = 0, fRs = 2 * GateBuf::kFloats, fQn = fRs + 4 * LT, fNp = fQn + 4 * LT,
-                       fN = fNp + 8 * D, kSmallFloats = fN + 2 * D;
+  static constexpr int oC = oH + kTile;              // bf16 copy of C (D x D), MMA B operand of Q [C | n]
+  static constexpr int oNt = oC + Lay<D>::kState;    // second N block of that operand: column 0 = bf16 copy of n
+  static constexpr int oOnes = oNt + Lay<D>::kState; // [8][128] ones, K-major: B operand of dn = Kbar^T 1
+  static constexpr int oSmall = oOnes + 2048;
+  // floats: gates[2], srs[2][2][LT]
+  static constexpr int fGates = 0, fRs = 2 * GateBuf::kFloats, kSmallFloats = fRs + 4 * LT;
   static constexpr int kBytes = oSmall + kSmallFloats * 4 + 1024 /*alignment slack*/;
   // TMEM columns.  D = 64: S double-buffered by tile parity (512 columns, one CTA per SM).  D = 32: one S
   // buffer, 256 columns, so that two CTAs share an SM (S(k+1) is issued behind the MMAs that read P(k)).
@@ -314,8 +315,10 @@ struct FwSmem {
   // place -- the 16 packed columns of 32-column unit u overwrite S columns 32u .. 32u+15, which only the
   // writing warp has read -- and the MMA takes A from TMEM.
   static constexpr int kTmemCols = D == 64 ? 512 : 256;
+  // Hx = Q [C | n] has D + 16 columns (column D = q . n_{k-1}); dN = Kbar^T 1 has 8 (identical) columns.
   static constexpr uint32_t cS0 = 0, cS1 = D == 64 ? 128 : 0, cHi = D == 64 ? 256 : 128, cHx = cHi + D,
-                            cDC = D == 64 ? 384 : 192;
+                            cDC = cHx + D + 16, cDN = cDC + D;
+  static_assert(cDN + 8 <= kTmemCols, "TMEM budget");
 };
 
 template <typename T, int D, bool REV>
@@ -333,7 +336,9 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
   uint8_t* sKb = smem + SM::oKb;
   uint8_t* sH = smem + SM::oH;
   uint8_t* sC = smem + SM::oC;
-  __shared__ uint64_t bar_full[NSTAGE], bar_s, bar_dc, bar_h, bar_g[2], bar_n;
+  uint8_t* sNt = smem + SM::oNt;
+  uint8_t* sOnes = smem + SM::oOnes;
+  __shared__ uint64_t bar_full[NSTAGE], bar_s, bar_dc, bar_h, bar_g[2];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -347,7 +352,6 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
     mbar_init(&bar_h, 1);
     mbar_init(&bar_g[0], 1);
     mbar_init(&bar_g[1], 1);
-    mbar_init(&bar_n, D / 32);  // one arrival per warp that finalises n
     fence_mbar_init();
   }
   if (warp == kCtlWarp) {
@@ -357,13 +361,15 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
     }
   }
   // worker-side state: fp32 master copy of C in the registers of lanes < 16 of the worker warps:
-  // row d = 16*rb + lane (M=64 TMEM layout; D = 32 has 32 real rows, warps rb < 2), columns CW*ch .. CW*ch+CW-1
+  // row d = 16*rb + lane (M=64 TMEM layout; D = 32 has 32 real rows, warps rb < 2), columns CW*ch .. CW*ch+CW-1;
+  // the ch == 0 owner of a row also keeps n[d] (fp32) and its 16-bit operand copy in sNt(d, 0)
   const int rb = warp & 3, ch = (warp >> 2) & 1;
   const int row = rb * 32 + lane;  // tile row == TMEM lane of this thread
   const uint32_t lane_base = (uint32_t)(rb * 32) << 16;
   const int drow = rb * 16 + (lane & 15);
   const bool owns_c = warp < kCtlWarp && lane < 16 && rb * 16 < D;
   float Creg[CW];
+  float n_reg = 0.f;
 #pragma unroll
   for (int j = 0; j < CW; ++j) Creg[j] = 0.f;
   if (warp < kCtlWarp) {
@@ -373,14 +379,24 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       for (int j = 0; j < CW; ++j) Creg[j] = src[j];
     }
     if (owns_c) store_cols<T, D>(sC, drow, ch * CW, Creg);
-    if (tid < D) fsm[SM::fN + tid] = p.n0 ? p.n0[(int64_t)bh * D + tid] : 0.f;
+    for (int e = tid; e < L::kState / 16; e += kWorkers) reinterpret_cast<uint4*>(sNt)[e] = make_uint4(0, 0, 0, 0);
+    {
+      const uint32_t one2 = pack2<T>(1.f, 1.f);
+      for (int e = tid; e < 2048 / 16; e += kWorkers) reinterpret_cast<uint4*>(sOnes)[e] = make_uint4(one2, one2, one2, one2);
+    }
+    named_sync(NB_PAIR0, kWorkers);  // sNt zeroed before the owners write column 0
+    if (owns_c && ch == 0) {
+      n_reg = p.n0 ? p.n0[(int64_t)bh * D + drow] : 0.f;
+      *reinterpret_cast<T*>(sNt + L::swz(drow, 0)) = from_f32<T>(n_reg);
+    }
     fence_proxy_async_smem();
   }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t tS0 = tmem + SM::cS0, tS1 = tmem + SM::cS1, tHi = tmem + SM::cHi, tHx = tmem + SM::cHx, tDC = tmem + SM::cDC;
+  const uint32_t tS0 = tmem + SM::cS0, tS1 = tmem + SM::cS1, tHi = tmem + SM::cHi, tHx = tmem + SM::cHx, tDC = tmem + SM::cDC,
+                 tDN = tmem + SM::cDN;
 
   const T* ip = (const T*)p.ig + b * p.ig_sb + hh * p.ig_sh;
   const T* fp = (const T*)p.fg + b * p.fg_sb + hh * p.fg_sh;
@@ -403,6 +419,9 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
     constexpr uint32_t id_s = umma_idesc(128, 128, false, false, kBf16);
     constexpr uint32_t id_dc = umma_idesc(64, D, true, true, kBf16);
     constexpr uint32_t id_h = umma_idesc(128, D, false, true, kBf16);
+    constexpr uint32_t id_hx = umma_idesc(128, D + 16, false, true, kBf16);  // Q [C | n]
+    constexpr uint32_t id_dn = umma_idesc(64, 8, true, false, kBf16);        // Kbar^T 1
+    const uint64_t dOnes = umma_smem_desc(smem_u32(sOnes), 0, 1024);
     const uint64_t dKb = L::desc(smem_u32(sKb), D == 64 ? SM::kTile : 0);  // D = 32: rows 32-63 of the M = 64 MMA re-read the block
     const uint64_t dC = L::desc(smem_u32(sC), L::kState);
     // Every shared-memory descriptor is provably warp-uniform (stage-0 descriptor + stage index * tile bytes;
@@ -448,8 +467,8 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
         for (int kk = 0; kk < LT / 16; ++kk)  // Hintra = P V, A = P from TMEM (packed inside the S columns)
           umma_f16_ts(tHi, (par ? tS1 : tS0) + 32 * (kk / 2) + 8 * (kk % 2), umma_desc_advance(dV, kk * L::kAdvMN), id_h, kk > 0);
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk)  // Hinter = Q C_{k-1}
-          umma_f16(tHx, umma_desc_advance(dQ, kk * 32), umma_desc_advance(dC, kk * L::kAdvMN), id_h, kk > 0);
+        for (int kk = 0; kk < D / 16; ++kk)  // Hinter = Q [C_{k-1} | n_{k-1}]: column D is q . n_{k-1}
+          umma_f16(tHx, umma_desc_advance(dQ, kk * 32), umma_desc_advance(dC, kk * L::kAdvMN), id_hx, kk > 0);
         umma_commit(&bar_h);
       }
       __syncwarp();
@@ -459,6 +478,10 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
 #pragma unroll
         for (int kk = 0; kk < LT / 16; ++kk)  // dC = Kbar^T V
           umma_f16(tDC, umma_desc_advance(dKb, kk * L::kAdvMN), umma_desc_advance(dV, kk * L::kAdvMN), id_dc, kk > 0);
+#pragma unroll
+        for (int kk = 0; kk < LT / 16; ++kk)  // dn = Kbar^T 1 (column sums on the tensor pipe)
+          umma_f16(tDN, umma_desc_advance(dKb, kk * L::kAdvMN), umma_desc_advance(dOnes, (kk / 4) * 1024 + (kk % 4) * 32), id_dn,
+                   kk > 0);
         umma_commit(&bar_dc);
         if (c + 1 < p.NT) issue_s(c + 1, std::integral_constant<int, par ^ 1>{});  // next tile's S, other TMEM buffer
       }
@@ -498,7 +521,6 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
   } else {
     // =========================== worker warps ===================================================
     float m_run = p.m0 ? p.m0[bh] : 0.f;
-    int cur = 0;
     for (int c = 0; c < p.NT; ++c) {
       const int s = c % NSTAGE, pb = c & 1;
       const uint32_t par_full = (c / NSTAGE) & 1, par = c & 1;
@@ -506,10 +528,6 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       const uint8_t* sK = smem + SM::oK + s * SM::kTile;
       const float* gb = fsm + SM::fGates + pb * GateBuf::kFloats;
       float* srs = fsm + SM::fRs + pb * 2 * LT;
-      float* sqn = fsm + SM::fQn + pb * 2 * LT;
-      float* snp = fsm + SM::fNp + pb * 4 * D;
-      const float* sNc = fsm + SM::fN + cur * D;
-      float* sNn = fsm + SM::fN + (cur ^ 1) * D;
       const int t0 = mt(c) * LT;
       const int n_valid = min(LT, p.S - t0);
       const uint32_t tS = (c & 1) ? tS1 : tS0;
@@ -581,21 +599,7 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       TC_PROF(c, 5);
       // (the loads and n_{k-1} are only needed from here on: their waits stay off the S -> P -> PV chain)
       mbar_wait(&bar_full[s], par_full, 3);
-      if (c > 0) mbar_wait(&bar_n, (c - 1) & 1, 4);  // n_{k-1} finalised
-      // ---- partial q . n_{k-1} over this thread's 32 columns ---------------------------------------
-      {
-        float qn = 0.f;
-#pragma unroll
-        for (int j = 0; j < CW / 8; ++j) {
-          uint4 q = *reinterpret_cast<const uint4*>(sQ + L::swz(row, ch * CW + 8 * j));
-          float2 q0 = unpack2<T>(q.x), q1 = unpack2<T>(q.y), q2 = unpack2<T>(q.z), q3 = unpack2<T>(q.w);
-          const float4 n0 = *reinterpret_cast<const float4*>(sNc + ch * CW + 8 * j);
-          const float4 n1 = *reinterpret_cast<const float4*>(sNc + ch * CW + 8 * j + 4);
-          qn += q0.x * n0.x + q0.y * n0.y + q1.x * n0.z + q1.y * n0.w + q2.x * n1.x + q2.y * n1.y + q3.x * n1.z + q3.y * n1.w;
-        }
-        sqn[ch * LT + row] = qn;
-      }
-      // ---- Kbar = abar . K (this thread: row, 32 columns); column sums for n (overlaps the H MMAs) --
+      // ---- Kbar = abar . K (this thread: row, CW columns); overlaps the H MMAs ---------------------------
       {
         const float ab = __expf(g - b_t + i_t - m_next);  // fw.py:102 (exp(-inf) = 0 for tail tokens)
         float kb[CW];
@@ -607,8 +611,6 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
           kb[8 * j + 4] = a2.x * ab; kb[8 * j + 5] = a2.y * ab; kb[8 * j + 6] = a3.x * ab; kb[8 * j + 7] = a3.y * ab;
         }
         store_cols<T, D>(sKb, row, ch * CW, kb);
-        const float cs = warp_colsum<CW>(kb, lane);  // sum over this warp's 32 rows of column ch*CW + (lane % CW)
-        if (lane < CW) snp[rb * D + ch * CW + lane] = cs;
         fence_proxy_async_smem();
         named_arrive(NB_A, kNbAB);
       }
@@ -618,15 +620,16 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       tc_fence_after_sync();
       TC_PROF(c, 7);
       {
-        uint32_t hi[CW], hx[CW];
+        uint32_t hi[CW], hx[CW], qn_u;
         tmem_ld_nowait(tHi + lane_base + ch * CW, hi);
         tmem_ld_nowait(tHx + lane_base + ch * CW, hx);
-        const float bq = __expf(b_t + m_run - m_t) * p.scale;                          // fw.py:197-198
-        named_sync(NB_PAIR0 + rb, 64);  // the partner warp (other column half of these rows) has written its q.n partial
-        const float den = bq * (sqn[row] + sqn[LT + row]) + srs[row] + srs[LT + row];  // fw.py:204-206
-        const float nmax = fmaxf(fabsf(den), __expf(-m_t));                            // fw.py:208-210
-        const float inv = 1.f / (nmax + p.eps);
+        tmem_ld1_nowait(tHx + lane_base + D, qn_u);  // q . n_{k-1}
+        const float bq = __expf(b_t + m_run - m_t) * p.scale;  // fw.py:197-198
+        const float rs = srs[row] + srs[LT + row];
         tmem_ld_wait();
+        const float den = bq * __uint_as_float(qn_u) + rs;       // fw.py:204-206
+        const float nmax = fmaxf(fabsf(den), __expf(-m_t));    // fw.py:208-210
+        const float inv = 1.f / (nmax + p.eps);
         float o[CW];
 #pragma unroll
         for (int j = 0; j < CW; ++j) o[j] = (__uint_as_float(hi[j]) + bq * __uint_as_float(hx[j])) * inv;  // fw.py:200-212
@@ -640,17 +643,18 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       mbar_wait(&bar_dc, par, 6);
       tc_fence_after_sync();
       {
-        float v[CW];
-        tmem_ld(tDC + lane_base + ch * CW, v);  // M=64 layout: lanes 0-15 of each quadrant hold rows
+        uint32_t v[CW], dn_u;
+        tmem_ld_nowait(tDC + lane_base + ch * CW, v);  // M=64 layout: lanes 0-15 of each quadrant hold rows
+        tmem_ld1_nowait(tDN + lane_base, dn_u);
+        tmem_ld_wait();
         if (owns_c) {
 #pragma unroll
-          for (int j = 0; j < CW; ++j) Creg[j] = gbar * Creg[j] + v[j];
-          store_cols<T, D>(sC, drow, ch * CW, Creg);  // Q C_{k-1} (bar_h) has finished reading the old copy
-        }
-        if (warp < D / 32) {  // n_k = gbar n_{k-1} + column sums of Kbar (fw.py:116)
-          sNn[tid] = gbar * sNc[tid] + ((snp[tid] + snp[D + tid]) + (snp[2 * D + tid] + snp[3 * D + tid]));
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bar_n);
+          for (int j = 0; j < CW; ++j) Creg[j] = gbar * Creg[j] + __uint_as_float(v[j]);
+          store_cols<T, D>(sC, drow, ch * CW, Creg);  // Q [C | n]_{k-1} (bar_h) has finished reading the old copies
+          if (ch == 0) {  // n_k = gbar n_{k-1} + column sums of Kbar (fw.py:116)
+            n_reg = gbar * n_reg + __uint_as_float(dn_u);
+            *reinterpret_cast<T*>(sNt + L::swz(drow, 0)) = from_f32<T>(n_reg);
+          }
         }
       }
       fence_proxy_async_smem();
@@ -658,7 +662,6 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       named_arrive(NB_C, kNbC);
       TC_PROF(c, 8);
       m_run = m_next;
-      cur ^= 1;
     }
     // final states (fw.py:302-309)
     if (p.c_last) {
@@ -667,7 +670,7 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
 #pragma unroll
         for (int j = 0; j < CW; ++j) dst[j] = Creg[j];
       }
-      if (tid < D) p.n_last[(int64_t)bh * D + tid] = fsm[SM::fN + cur * D + tid];  // own write (tid < D finalises n)
+      if (owns_c && ch == 0) p.n_last[(int64_t)bh * D + drow] = n_reg;
       if (tid == 0) p.m_last[bh] = m_run;
     }
   }
