@@ -25,6 +25,10 @@ v = buf.cpu().view(2, 256, 16)
 NT = (S + 127) // 128
 for name, k in (("fw", 0), ("bw", 1)):
     print(name, "slots: 0 top | 1 after sync(gates) | 2 after prep+sync | 3 S ready | 4 after P/W+sync | 5 dC ready | 6 dC done | 7 H/main ready | 8 epilogue done")
+    e = v[k, 200]
+    t0, tl = v[k, 0, 0].item(), v[k, NT - 1, 0].item()
+    print(f"  kernel entry -> tile 0 top {t0 - e[0].item()} clk; last tile top -> workers done {e[1].item() - tl} clk; "
+          f"-> after final CTA sync {e[2].item() - tl} clk; entry -> exit {e[2].item() - e[0].item()} clk")
     for tile in range(NT):
         r = v[k, tile]
         base = r[0].item()

@@ -330,6 +330,7 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
   using SM = FwSmem<D>;
   using L = Lay<D>;
   constexpr int NSTAGE = SM::NSTAGE, CW = L::CW;
+  TC_PROF(200, 0);  // kernel entry
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   float* fsm = (float*)(smem + SM::oSmall);
@@ -345,8 +346,25 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: role branches stay uniform
   const int bh = blockIdx.x, b = bh / p.NH, hh = bh % p.NH;
 
-  if (tid == 0) {
+  const T* ip = (const T*)p.ig + b * p.ig_sb + hh * p.ig_sh;
+  const T* fp = (const T*)p.fg + b * p.fg_sb + hh * p.fg_sh;
+  constexpr uint32_t kStageBytes = 3 * SM::kTile;
+  // memory tile of processing tile c: the anti-causal direction walks the tiles from the end and
+  // mirrors the in-tile mask / scans; no data is ever reversed (north_star item 4)
+  auto mt = [&](int c) { return REV ? p.NT - 1 - c : c; };
+  auto load_stage = [&](int s, int c) {
+    mbar_expect_tx(&bar_full[s], kStageBytes);
+    tma_load_4d(smem + SM::oQ + s * SM::kTile, &mapQ, &bar_full[s], 0, mt(c) * LT, hh, b);
+    tma_load_4d(smem + SM::oK + s * SM::kTile, &mapK, &bar_full[s], 0, mt(c) * LT, hh, b);
+    tma_load_4d(smem + SM::oV + s * SM::kTile, &mapV, &bar_full[s], 0, mt(c) * LT, hh, b);
+  };
+  // cold start: the first Q / K / V tiles are requested before anything else happens in the CTA
+  if (tid == kCtlWarp * 32) {
     for (int s = 0; s < NSTAGE; ++s) mbar_init(&bar_full[s], 1);
+    fence_mbar_init();
+    for (int s = 0; s < NSTAGE && s < p.NT; ++s) load_stage(s, s);
+  }
+  if (tid == 0) {
     mbar_init(&bar_s, 1);
     mbar_init(&bar_dc, 1);
     mbar_init(&bar_h, 1);
@@ -391,6 +409,13 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
     }
     fence_proxy_async_smem();
   }
+  if (warp == kScanWarp) {  // cold start: pull the first tile's gate rows towards L2 / L1 while the CTA sets up
+    const int t1 = mt(0) * LT, nv = min(LT, p.S - t1);
+    for (int e = lane; e < nv; e += 32) {
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(ip + (int64_t)(t1 + e) * p.ig_ss));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(fp + (int64_t)(t1 + e) * p.fg_ss));
+    }
+  }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -398,24 +423,8 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
   const uint32_t tS0 = tmem + SM::cS0, tS1 = tmem + SM::cS1, tHi = tmem + SM::cHi, tHx = tmem + SM::cHx, tDC = tmem + SM::cDC,
                  tDN = tmem + SM::cDN;
 
-  const T* ip = (const T*)p.ig + b * p.ig_sb + hh * p.ig_sh;
-  const T* fp = (const T*)p.fg + b * p.fg_sb + hh * p.fg_sh;
-  constexpr uint32_t kStageBytes = 3 * SM::kTile;
-  // memory tile of processing tile c: the anti-causal direction walks the tiles from the end and
-  // mirrors the in-tile mask / scans; no data is ever reversed (north_star item 4)
-  auto mt = [&](int c) { return REV ? p.NT - 1 - c : c; };
-
   if (warp == kCtlWarp) {
     // =========================== control warp ===================================================
-    auto load_stage = [&](int s, int c) {
-      mbar_expect_tx(&bar_full[s], kStageBytes);
-      tma_load_4d(smem + SM::oQ + s * SM::kTile, &mapQ, &bar_full[s], 0, mt(c) * LT, hh, b);
-      tma_load_4d(smem + SM::oK + s * SM::kTile, &mapK, &bar_full[s], 0, mt(c) * LT, hh, b);
-      tma_load_4d(smem + SM::oV + s * SM::kTile, &mapV, &bar_full[s], 0, mt(c) * LT, hh, b);
-    };
-    if (lane == 0)
-      for (int s = 0; s < NSTAGE && s < p.NT; ++s) load_stage(s, s);
-
     constexpr uint32_t id_s = umma_idesc(128, 128, false, false, kBf16);
     constexpr uint32_t id_dc = umma_idesc(64, D, true, true, kBf16);
     constexpr uint32_t id_h = umma_idesc(128, D, false, true, kBf16);
@@ -674,8 +683,10 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       if (tid == 0) p.m_last[bh] = m_run;
     }
   }
+  TC_PROF(200, 1);  // this role is done
   tc_fence_before_sync();
   __syncthreads();
+  TC_PROF(200, 2);
   if (warp == kCtlWarp) tmem_dealloc<SM::kTmemCols>(tmem);
 }
 
@@ -1032,7 +1043,7 @@ tc_fw_d128(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUt
 // dC lives on chip (fp32 registers + bf16 operand copy); C_{k-1} comes from the forward's
 // c_states.  n_out and every max state are constants (bw.py:44-47).  Per tile:
 //   S = Q K^T, dSb = dH V^T                      tcgen05 M128 N128 K64 (x2)
-//   W = exp(b_t - b_s + i_s - m_t) / (n_t + eps) (s <= t);  Sb' = S.scale.W ; dS = dSb.W
+//   W = exp(b_t - b_s + i_s - m_t) / (n_t + eps) (s <= t);  Sb' = S.W (scale applied to dV1) ; dS = dSb.W
 //   ddC = (wq.Q)^T dH        M64 N64 K128        dQb = dH C_{k-1}^T     M128 N64 K64
 //   dQa = dS K               M128 N64 K128       dV1 = Sb'^T dH         M128 N64 K128
 //   dV2 = K dC_k             M128 N64 K64        dK1 = dS^T Q           M128 N64 K128
@@ -1096,6 +1107,7 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
   using SM = BwSmem<D>;
   using L = Lay<D>;
   constexpr int CW = L::CW;
+  TC_PROF(200, 0);  // kernel entry
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem + SM::oQ;  // stage 0; stage s is SM::kStage bytes further
@@ -1111,17 +1123,32 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
   uint8_t* sCs = smem + SM::oCs;
   uint8_t* sdC = smem + SM::odC;
   float* fsm = (float*)(smem + SM::oSmall);
-  __shared__ uint64_t bar_full[SM::kNST], bar_s, bar_q, bar_v, bar_k, bar_d, bar_a, bar_b, bar_g[2];
+  __shared__ uint64_t bar_full[SM::kNST], bar_s, bar_q, bar_v, bar_k, bar_d, bar_b, bar_g[2];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: role branches stay uniform
   const int bh = blockIdx.x, b = bh / p.NH, hh = bh % p.NH;
 
-  if (tid == 0) {
+  // memory tile of processing tile c (see the forward kernel); the sweep visits c = NT-1 .. 0
+  auto mt = [&](int c) { return REV ? p.NT - 1 - c : c; };
+  auto load_stage = [&](int s, int c) {  // every input tile of memory tile mt(c) into stage s
+    uint8_t* base = smem + s * SM::kStage;
+    mbar_expect_tx(&bar_full[s], SM::kLoadBytes);
+    tma_load_4d(base + SM::oQ, &mapQ, &bar_full[s], 0, mt(c) * LT, hh, b);
+    tma_load_4d(base + SM::oK, &mapK, &bar_full[s], 0, mt(c) * LT, hh, b);
+    tma_load_4d(base + SM::oV, &mapV, &bar_full[s], 0, mt(c) * LT, hh, b);
+    tma_load_4d(base + SM::odH, &mapdH, &bar_full[s], 0, mt(c) * LT, hh, b);
+    tma_load_4d(base + SM::oCs, &mapCs, &bar_full[s], 0, mt(c) * D, hh, b);
+  };
+  // cold start: the first input tiles are requested before anything else happens in the CTA
+  if (tid == kCtlWarp * 32) {
     for (int s = 0; s < SM::kNST; ++s) mbar_init(&bar_full[s], 1);
+    fence_mbar_init();
+    for (int s = 0; s < SM::kNST && s < p.NT; ++s) load_stage(s, p.NT - 1 - s);
+  }
+  if (tid == 0) {
     mbar_init(&bar_s, 1);
-    mbar_init(&bar_a, 1);
     mbar_init(&bar_b, 1);
     mbar_init(&bar_q, 1);
     mbar_init(&bar_v, 1);
@@ -1167,20 +1194,8 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
   const T* fp = (const T*)p.fg + b * p.fg_sb + hh * p.fg_sh;
   const float* mo = p.m_out + (int64_t)bh * p.S;
   const float* no = p.n_out + (int64_t)bh * p.S;
-  // memory tile of processing tile c (see the forward kernel); the sweep visits c = NT-1 .. 0
-  auto mt = [&](int c) { return REV ? p.NT - 1 - c : c; };
-
   if (warp == kCtlWarp) {
     // =========================== control warp ===================================================
-    auto load_stage = [&](int s, int c) {  // every input tile of memory tile mt(c) into stage s
-      uint8_t* base = smem + s * SM::kStage;
-      mbar_expect_tx(&bar_full[s], SM::kLoadBytes);
-      tma_load_4d(base + SM::oQ, &mapQ, &bar_full[s], 0, mt(c) * LT, hh, b);
-      tma_load_4d(base + SM::oK, &mapK, &bar_full[s], 0, mt(c) * LT, hh, b);
-      tma_load_4d(base + SM::oV, &mapV, &bar_full[s], 0, mt(c) * LT, hh, b);
-      tma_load_4d(base + SM::odH, &mapdH, &bar_full[s], 0, mt(c) * LT, hh, b);
-      tma_load_4d(base + SM::oCs, &mapCs, &bar_full[s], 0, mt(c) * D, hh, b);
-    };
     constexpr uint32_t id_s = umma_idesc(128, 128, false, false, kBf16);
     constexpr uint32_t id_c = umma_idesc(64, D, true, true, kBf16);
     constexpr uint32_t id_k_mn = umma_idesc(128, D, false, true, kBf16);   // A K-major, B MN-major
@@ -1212,9 +1227,6 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       umma_commit(&bar_s);
     };
 
-    if (lane == 0)
-      for (int s = 0; s < SM::kNST && s < p.NT; ++s) load_stage(s, p.NT - 1 - s);
-    __syncwarp();
     if (elect_one()) issue_s(0);
     __syncwarp();
 
@@ -1228,35 +1240,42 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       const uint64_t kV = umma_desc_advance(kV0, so), kCs = umma_desc_advance(kCs0, so);
       const uint64_t kH = umma_desc_advance(kH0, so), mH = umma_desc_advance(mH0, so);
       TC_PROF(it, 9);
+      if (SM::kNST == 1 && c > 0 && lane == 0) {  // single input stage: pull the next tile into L2 a whole tile ahead,
+        const int r = mt(c - 1) * LT;             // so that the re-fills behind the MMA batch are L2 hits
+        tma_prefetch_4d(&mapQ, 0, r, hh, b);
+        tma_prefetch_4d(&mapK, 0, r, hh, b);
+        tma_prefetch_4d(&mapV, 0, r, hh, b);
+        tma_prefetch_4d(&mapdH, 0, r, hh, b);
+        tma_prefetch_4d(&mapCs, 0, mt(c - 1) * D, hh, b);
+      }
       named_sync(NB_B, kNbAB);  // Sb', dS written
       TC_PROF(it, 10);
       if (lane == 0) tma_store_wait_read<0>();  // the previous tile's dq / dk / dv stores have left their staging buffers
       __syncwarp();
-      // MMA batch, ordered so that the input tiles die one after the other (Q, K, V, C_{k-1}, dH): every
-      // tile is re-filled with the next tile's rows as soon as its last reader has completed, so the loads
-      // of tile k-1 overlap the rest of the batch and the epilogues instead of idling the whole CTA.
+      // MMA batch, ordered (a) so that the first epilogue (dk) can start after 12 of the 44 instructions and
+      // (b) so that the input tiles die one after the other: each is re-filled with the next tile's rows as soon
+      // as its last reader has completed (D = 64, single input stage) instead of idling the CTA on the loads.
       if (elect_one()) {
         tc_fence_after_sync();
 #pragma unroll
         for (int kk = 0; kk < LT / 16; ++kk)  // dK1 = dS^T Q
           umma_f16(tdK1, umma_desc_advance(mdS, kk * 2048), umma_desc_advance(mQ, kk * L::kAdvMN), id_mn_mn, kk > 0);
-        umma_commit(&bar_a);  // Q consumed
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)  // dK2 = V dC_k^T
+          umma_f16(tdK2, umma_desc_advance(kV, kk * 32), umma_desc_advance(kdC, kk * 32), id_k_k, kk > 0);
+        umma_commit(&bar_k);  // Q, V consumed; dk complete
 #pragma unroll
         for (int kk = 0; kk < LT / 16; ++kk)  // dQa = dS K
           umma_f16(tdQa, umma_desc_advance(kdS, (kk / 4) * SM::kPTile + (kk % 4) * 32), umma_desc_advance(mK, kk * L::kAdvMN),
                    id_k_mn, kk > 0);
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk)  // dV2 = K dC_k
-          umma_f16(tdV2, umma_desc_advance(kK, kk * 32), umma_desc_advance(mdC, kk * L::kAdvMN), id_k_mn, kk > 0);
-        umma_commit(&bar_b);  // K consumed
-#pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk)  // dK2 = V dC_k^T
-          umma_f16(tdK2, umma_desc_advance(kV, kk * 32), umma_desc_advance(kdC, kk * 32), id_k_k, kk > 0);
-        umma_commit(&bar_k);  // V consumed; dk complete
-#pragma unroll
         for (int kk = 0; kk < D / 16; ++kk)  // dQb = dH C_{k-1}^T
           umma_f16(tdQb, umma_desc_advance(kH, kk * 32), umma_desc_advance(kCs, kk * 32), id_k_k, kk > 0);
         umma_commit(&bar_q);  // C_{k-1} consumed; dq complete
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)  // dV2 = K dC_k
+          umma_f16(tdV2, umma_desc_advance(kK, kk * 32), umma_desc_advance(mdC, kk * L::kAdvMN), id_k_mn, kk > 0);
+        umma_commit(&bar_b);  // K consumed
       }
       __syncwarp();
       TC_PROF(it, 11);
@@ -1276,14 +1295,13 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
           if (c > 0) {  // re-fill the single stage tile by tile, each as soon as its last reader has completed
             const int r = mt(c - 1) * LT;
             mbar_expect_tx(&bar_full[0], SM::kLoadBytes);
-            mbar_wait(&bar_a, par, 21);
+            mbar_wait(&bar_k, par, 21);
             tma_load_4d(sQ, &mapQ, &bar_full[0], 0, r, hh, b);
-            mbar_wait(&bar_b, par, 22);
-            tma_load_4d(sK, &mapK, &bar_full[0], 0, r, hh, b);
-            mbar_wait(&bar_k, par, 23);
             tma_load_4d(sV, &mapV, &bar_full[0], 0, r, hh, b);
             mbar_wait(&bar_q, par, 24);
             tma_load_4d(sCs, &mapCs, &bar_full[0], 0, mt(c - 1) * D, hh, b);
+            mbar_wait(&bar_b, par, 22);
+            tma_load_4d(sK, &mapK, &bar_full[0], 0, r, hh, b);
             mbar_wait(&bar_v, par, 25);
             tma_load_4d(sdH, &mapdH, &bar_full[0], 0, r, hh, b);
           }
@@ -1455,7 +1473,6 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
             tmem_ld_wait();
             if (u != rb) {  // fully unmasked 32x32 block: rank-1 decay, one exp per row
               const float r_t = ex2_approx(x_t + gb[GateBuf::oScal + 4 + u]);
-              const float r_s = r_t * p.scale;
 #pragma unroll
               for (int j4 = 0; j4 < 8; ++j4) {
                 const float4 cf = *reinterpret_cast<const float4*>(scf + u * 32 + 4 * j4);
@@ -1463,8 +1480,9 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const int j = 4 * j4 + e;
-                  v[j] = __uint_as_float(rv[j]) * (cc[e] * r_s);
-                  w[j] = __uint_as_float(rw[j]) * (cc[e] * r_t);
+                  const float wg = cc[e] * r_t;
+                  v[j] = __uint_as_float(rv[j]) * wg;  // the scale factor of Sb' is applied in the dv epilogue
+                  w[j] = __uint_as_float(rw[j]) * wg;
                 }
               }
             } else {  // diagonal block: causal mask, one exp per entry
@@ -1477,7 +1495,7 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
                   const int j = 4 * j4 + e;
                   float wg = ex2_approx(x_t + yy[e]);
                   wg = (REV ? j >= lane : j <= lane) ? wg : 0.f;
-                  v[j] = __uint_as_float(rv[j]) * (wg * p.scale);
+                  v[j] = __uint_as_float(rv[j]) * wg;
                   w[j] = __uint_as_float(rw[j]) * wg;
                 }
               }
@@ -1588,8 +1606,8 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
         dot = 0.f;
 #pragma unroll
         for (int j = 0; j < CW / 2; ++j) {
-          o[2 * j] = __uint_as_float(ra[2 * j]) + abar * __uint_as_float(rq[2 * j]);  // bw.py:164,190
-          o[2 * j + 1] = __uint_as_float(ra[2 * j + 1]) + abar * __uint_as_float(rq[2 * j + 1]);
+          o[2 * j] = p.scale * __uint_as_float(ra[2 * j]) + abar * __uint_as_float(rq[2 * j]);  // bw.py:164,190
+          o[2 * j + 1] = p.scale * __uint_as_float(ra[2 * j + 1]) + abar * __uint_as_float(rq[2 * j + 1]);
           float2 vv = unpack2<T>(vs[j]);
           dot += vv.x * o[2 * j] + vv.y * o[2 * j + 1];
         }
@@ -1607,8 +1625,10 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       for (int j = 0; j < CW; ++j) dst[j] = dCreg[j];
     }
   }
+  TC_PROF(200, 1);  // this role is done
   tc_fence_before_sync();
   __syncthreads();
+  TC_PROF(200, 2);
   if (warp == kCtlWarp) tmem_dealloc<512>(tmem);
 }
 
