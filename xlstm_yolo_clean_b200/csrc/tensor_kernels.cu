@@ -36,7 +36,7 @@ constexpr int kCtlWarp = 8, kScanWarp = 9;
 constexpr int kNbAB = kWorkers + 32;  // workers + control
 constexpr int kNbC = kWorkers + 64;   // workers + control + scan
 constexpr float kLog2e = 1.4426950408889634f;
-enum { NB_A = 1, NB_B = 2, NB_C = 3, NB_PAIR0 = 4, NB_D = 4, NB_E = 5 };  // named barriers: operand ready / P ready / epilogue done / warp pairs (4..7)
+enum { NB_A = 1, NB_B = 2, NB_C = 3, NB_PAIR0 = 4 };  // named barriers: operand ready / P ready / epilogue done / warp pairs (4..7)
 
 // per-tile gate vectors produced by the control warp (floats)
 struct GateBuf {
@@ -1088,16 +1088,13 @@ struct BwSmem {
   // floats: gates[2], spart[2][6][LT]
   static constexpr int fGates = 0, fPart = 2 * GateBuf::kFloats, kSmallFloats = fPart + 12 * LT;
   static constexpr int kBytes = oSmall + kSmallFloats * 4 + 1024;
-  static constexpr uint32_t kLoadBytesA = 2 * kTile;           // Q, K  (operands of S)
-  static constexpr uint32_t kLoadBytesB = 2 * kTile + kState;  // V, dH (operands of dSb), C_{k-1}
-  // TMEM columns.  D = 64: the S columns are re-used by the dK accumulators and the dSb columns by the dQ
-  // accumulators -- the first two epilogues -- so S / dSb of the next tile are issued as soon as the workers
-  // have read dk / dq and overlap the dC update and the dv epilogue.  D = 32: nothing aliases, S / dSb of the
-  // next tile are issued right behind the MMA batch.
+  static constexpr uint32_t kLoadBytes = 4 * kTile + kState;
+  // TMEM columns.  D = 64: the S / dSb columns are re-used by the dV / dK accumulators.  D = 32: nothing aliases,
+  // so S / dSb of the next tile are issued right behind the MMA batch and overlap the epilogues.
   static constexpr bool kAlias = D == 64;
   static constexpr uint32_t cS = 0, cdSb = 128;
-  static constexpr uint32_t cdK1 = D == 64 ? 0 : 320, cdK2 = cdK1 + D, cdQa = D == 64 ? 128 : 384, cdQb = cdQa + D,
-                            cdV1 = 256, cdV2 = cdV1 + D, cddC = D == 64 ? 384 : 448;
+  static constexpr uint32_t cdV1 = D == 64 ? 0 : 256, cdV2 = cdV1 + D, cdK1 = D == 64 ? 128 : 320, cdK2 = cdK1 + D,
+                            cdQa = D == 64 ? 256 : 384, cdQb = cdQa + D, cddC = D == 64 ? 384 : 448;
 };
 
 template <typename T, int D, bool REV>
@@ -1126,7 +1123,7 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
   uint8_t* sCs = smem + SM::oCs;
   uint8_t* sdC = smem + SM::odC;
   float* fsm = (float*)(smem + SM::oSmall);
-  __shared__ uint64_t bar_fa[SM::kNST], bar_fb[SM::kNST], bar_s, bar_q, bar_v, bar_k, bar_d, bar_b, bar_g[2];
+  __shared__ uint64_t bar_full[SM::kNST], bar_s, bar_q, bar_v, bar_k, bar_d, bar_b, bar_st, bar_g[2];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -1137,23 +1134,23 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
   auto mt = [&](int c) { return REV ? p.NT - 1 - c : c; };
   auto load_stage = [&](int s, int c) {  // every input tile of memory tile mt(c) into stage s
     uint8_t* base = smem + s * SM::kStage;
-    mbar_expect_tx(&bar_fa[s], SM::kLoadBytesA);
-    mbar_expect_tx(&bar_fb[s], SM::kLoadBytesB);
-    tma_load_4d(base + SM::oQ, &mapQ, &bar_fa[s], 0, mt(c) * LT, hh, b);
-    tma_load_4d(base + SM::oK, &mapK, &bar_fa[s], 0, mt(c) * LT, hh, b);
-    tma_load_4d(base + SM::oV, &mapV, &bar_fb[s], 0, mt(c) * LT, hh, b);
-    tma_load_4d(base + SM::odH, &mapdH, &bar_fb[s], 0, mt(c) * LT, hh, b);
-    tma_load_4d(base + SM::oCs, &mapCs, &bar_fb[s], 0, mt(c) * D, hh, b);
+    mbar_expect_tx(&bar_full[s], SM::kLoadBytes);
+    tma_load_4d(base + SM::oQ, &mapQ, &bar_full[s], 0, mt(c) * LT, hh, b);
+    tma_load_4d(base + SM::oK, &mapK, &bar_full[s], 0, mt(c) * LT, hh, b);
+    tma_load_4d(base + SM::oV, &mapV, &bar_full[s], 0, mt(c) * LT, hh, b);
+    tma_load_4d(base + SM::odH, &mapdH, &bar_full[s], 0, mt(c) * LT, hh, b);
+    tma_load_4d(base + SM::oCs, &mapCs, &bar_full[s], 0, mt(c) * D, hh, b);
   };
   // cold start: the first input tiles are requested before anything else happens in the CTA
   if (tid == kCtlWarp * 32) {
-    for (int s = 0; s < SM::kNST; ++s) { mbar_init(&bar_fa[s], 1); mbar_init(&bar_fb[s], 1); }
+    for (int s = 0; s < SM::kNST; ++s) mbar_init(&bar_full[s], 1);
     fence_mbar_init();
     for (int s = 0; s < SM::kNST && s < p.NT; ++s) load_stage(s, p.NT - 1 - s);
   }
   if (tid == 0) {
-    mbar_init(&bar_s, 2);  // S and dSb commit separately
+    mbar_init(&bar_s, 1);
     mbar_init(&bar_b, 1);
+    mbar_init(&bar_st, 1);
     mbar_init(&bar_q, 1);
     mbar_init(&bar_v, 1);
     mbar_init(&bar_k, 1);
@@ -1215,33 +1212,23 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
     const uint64_t mSb = umma_smem_desc(smem_u32(sSb), SM::kPTile, 1024);
     const uint64_t kdS = umma_smem_desc(smem_u32(sdS), 0, 1024), mdS = umma_smem_desc(smem_u32(sdS), SM::kPTile, 1024);
     const uint64_t kdC = L::desc(smem_u32(sdC), 0), mdC = L::desc(smem_u32(sdC), SM::kState);
-    auto issue_S = [&](int it) {  // S = Q K^T of processing step `it` (its loads are in flight)
+    auto issue_s = [&](int it) {  // S = Q K^T, dSb = dH V^T of processing step `it` (its loads are in flight)
       const int s = it % SM::kNST;
       const uint32_t so = (uint32_t)s * SM::kStage;
       const uint64_t kQ = umma_desc_advance(kQ0, so), kK = umma_desc_advance(kK0, so);
-      mbar_wait(&bar_fa[s], (it / SM::kNST) & 1, 11);
+      const uint64_t kH = umma_desc_advance(kH0, so), kV = umma_desc_advance(kV0, so);
+      mbar_wait(&bar_full[s], (it / SM::kNST) & 1, 11);
       tc_fence_after_sync();
 #pragma unroll
       for (int kk = 0; kk < D / 16; ++kk)
         umma_f16(tS, umma_desc_advance(kQ, kk * 32), umma_desc_advance(kK, kk * 32), id_s, kk > 0);
-      umma_commit(&bar_s);
-    };
-    auto issue_dSb = [&](int it) {  // dSb = dH V^T
-      const int s = it % SM::kNST;
-      const uint32_t so = (uint32_t)s * SM::kStage;
-      const uint64_t kH = umma_desc_advance(kH0, so), kV = umma_desc_advance(kV0, so);
-      mbar_wait(&bar_fb[s], (it / SM::kNST) & 1, 11);
-      tc_fence_after_sync();
 #pragma unroll
       for (int kk = 0; kk < D / 16; ++kk)
         umma_f16(tdSb, umma_desc_advance(kH, kk * 32), umma_desc_advance(kV, kk * 32), id_s, kk > 0);
       umma_commit(&bar_s);
     };
 
-    if (elect_one()) {
-      issue_S(0);
-      issue_dSb(0);
-    }
+    if (elect_one()) issue_s(0);
     __syncwarp();
 
     for (int it = 0; it < p.NT; ++it) {
@@ -1264,8 +1251,6 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       }
       named_sync(NB_B, kNbAB);  // Sb', dS written
       TC_PROF(it, 10);
-      if (lane == 0) tma_store_wait_read<0>();  // the previous tile's dq / dk / dv stores have left their staging buffers
-      __syncwarp();
       // MMA batch, ordered (a) so that the first epilogue (dk) can start after 12 of the 44 instructions and
       // (b) so that the input tiles die one after the other: each is re-filled with the next tile's rows as soon
       // as its last reader has completed (D = 64, single input stage) instead of idling the CTA on the loads.
@@ -1290,50 +1275,44 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
         for (int kk = 0; kk < D / 16; ++kk)  // dV2 = K dC_k
           umma_f16(tdV2, umma_desc_advance(kK, kk * 32), umma_desc_advance(mdC, kk * L::kAdvMN), id_k_mn, kk > 0);
         umma_commit(&bar_b);  // K consumed
+      }
+      __syncwarp();
+      if (lane == 0) {  // (off the MMA issue path: 128 CTAs store in lockstep, the reads take a while to drain)
+        tma_store_wait_read<0>();  // the previous tile's dq / dk / dv stores have left their staging buffers
+        mbar_arrive(&bar_st);
+      }
+      __syncwarp();
+      TC_PROF(it, 11);
+      named_sync(NB_A, kNbAB);  // Qt written; the workers hold their q / k / v row slices in registers
+      TC_PROF(it, 12);
+      if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < LT / 16; ++kk)  // ddC = Qt^T dH (Qt was written before the W phase)
+        for (int kk = 0; kk < LT / 16; ++kk)  // ddC = Qt^T dH
           umma_f16(tddC, umma_desc_advance(mQt, kk * L::kAdvMN), umma_desc_advance(mH, kk * L::kAdvMN), id_c, kk > 0);
         umma_commit(&bar_d);
 #pragma unroll
         for (int kk = 0; kk < LT / 16; ++kk)  // dV1 = Sb'^T dH
           umma_f16(tdV1, umma_desc_advance(mSb, kk * 2048), umma_desc_advance(mH, kk * L::kAdvMN), id_mn_mn, kk > 0);
         umma_commit(&bar_v);  // dH consumed; dv complete
-        if (!SM::kAlias && c > 0) {  // next tile's S / dSb queue up behind the batch
-          issue_S(it + 1);
-          issue_dSb(it + 1);
-        }
-      }
-      __syncwarp();
-      TC_PROF(it, 11);
-      named_sync(NB_A, kNbAB);  // the workers hold their k / v row slices in registers: the inputs may be re-filled
-      TC_PROF(it, 12);
-      if (SM::kNST == 1) {
-        // re-fill the single stage tile by tile, each as soon as its last reader has completed
-        const int r = c > 0 ? mt(c - 1) * LT : 0;
-        if (c > 0 && elect_one()) {
-          mbar_expect_tx(&bar_fa[0], SM::kLoadBytesA);
-          mbar_expect_tx(&bar_fb[0], SM::kLoadBytesB);
-          mbar_wait(&bar_k, par, 21);
-          tma_load_4d(sQ, &mapQ, &bar_fa[0], 0, r, hh, b);
-          tma_load_4d(sV, &mapV, &bar_fb[0], 0, r, hh, b);
-          mbar_wait(&bar_q, par, 24);
-          tma_load_4d(sCs, &mapCs, &bar_fb[0], 0, mt(c - 1) * D, hh, b);
-          mbar_wait(&bar_b, par, 22);
-          tma_load_4d(sK, &mapK, &bar_fa[0], 0, r, hh, b);
-        }
-        __syncwarp();
-        if (SM::kAlias) named_sync(NB_D, kNbAB);  // every worker has read dK1 / dK2: the S columns are free
-        if (c > 0 && elect_one()) {
+        if (!SM::kAlias && c > 0) issue_s(it + 1);  // next tile's S / dSb queue up behind the batch
+        if (SM::kNST == 1) {
+          if (c > 0) {  // re-fill the single stage tile by tile, each as soon as its last reader has completed
+            const int r = mt(c - 1) * LT;
+            mbar_expect_tx(&bar_full[0], SM::kLoadBytes);
+            mbar_wait(&bar_k, par, 21);
+            tma_load_4d(sQ, &mapQ, &bar_full[0], 0, r, hh, b);
+            tma_load_4d(sV, &mapV, &bar_full[0], 0, r, hh, b);
+            mbar_wait(&bar_q, par, 24);
+            tma_load_4d(sCs, &mapCs, &bar_full[0], 0, mt(c - 1) * D, hh, b);
+            mbar_wait(&bar_b, par, 22);
+            tma_load_4d(sK, &mapK, &bar_full[0], 0, r, hh, b);
+            mbar_wait(&bar_v, par, 25);
+            tma_load_4d(sdH, &mapdH, &bar_full[0], 0, r, hh, b);
+          }
+        } else if (c >= SM::kNST) {  // this stage is free once the whole batch has completed
           mbar_wait(&bar_v, par, 25);
-          tma_load_4d(sdH, &mapdH, &bar_fb[0], 0, r, hh, b);
-          if (SM::kAlias) issue_S(it + 1);
+          load_stage(it % SM::kNST, c - SM::kNST);
         }
-        __syncwarp();
-        if (SM::kAlias) named_sync(NB_E, kNbAB);  // every worker has read dQa / dQb: the dSb columns are free
-        if (SM::kAlias && c > 0 && elect_one()) issue_dSb(it + 1);
-      } else if (c >= SM::kNST && elect_one()) {  // this stage is free once the whole batch has completed
-        mbar_wait(&bar_v, par, 25);
-        load_stage(it % SM::kNST, c - SM::kNST);
       }
       __syncwarp();
       TC_PROF(it, 13);
@@ -1345,6 +1324,8 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
         tma_store_4d(&mapdK, sdK, 0, t0, hh, b);
         tma_store_commit();
       }
+      __syncwarp();
+      if (SM::kAlias && c > 0 && elect_one()) issue_s(it + 1);  // S / dSb of the next tile (their TMEM columns were read by this epilogue)
       __syncwarp();
     }
     if (lane == 0) tma_store_wait_all<0>();
@@ -1479,7 +1460,7 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       TC_PROF(it, 1);
       // ---- Qt = wq . Q, written while the S / dSb MMAs of this tile run (ddC of the previous tile, the last
       // reader of sQt, completed before the previous dC update); q row slice kept for the gate gradients
-      mbar_wait(&bar_fa[it % SM::kNST], (it / SM::kNST) & 1, 13);
+      mbar_wait(&bar_full[it % SM::kNST], (it / SM::kNST) & 1, 13);
       uint32_t qs[CW / 2];
       {
         const float wq = p.scale * bbar * rinv;  // bw.py:83-90
@@ -1556,7 +1537,6 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       named_arrive(NB_B, kNbAB);
       TC_PROF(it, 3);
       // ---- this thread's k / v row slices for the gate gradients (the inputs may be re-filled afterwards) --
-      mbar_wait(&bar_fb[it % SM::kNST], (it / SM::kNST) & 1, 13);
       uint32_t ks[CW / 2], vs[CW / 2];
 #pragma unroll
       for (int j = 0; j < CW / 8; ++j) {
@@ -1581,10 +1561,6 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
         tmem_ld_nowait(tdK1 + lane_base + ch * CW, ra);
         tmem_ld_nowait(tdK2 + lane_base + ch * CW, rq);
         tmem_ld_wait();
-        if (SM::kAlias) {  // the S columns (= dK1 / dK2) may be overwritten by the next tile's S
-          tc_fence_before_sync();
-          named_arrive(NB_D, kNbAB);
-        }
         dot = 0.f;
 #pragma unroll
         for (int j = 0; j < CW / 2; ++j) {
@@ -1593,6 +1569,7 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
           float2 kv = unpack2<T>(ks[j]);
           dot += kv.x * o[2 * j] + kv.y * o[2 * j + 1];
         }
+        mbar_wait(&bar_st, par, 19);  // staging buffers free (the previous tile's stores have read them)
         store_cols<T, D>(sdK, row, ch * CW, o);
         spart[(1 * 2 + ch) * LT + row] = dot;
         // dq
@@ -1602,10 +1579,6 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
         tmem_ld_nowait(tdQa + lane_base + ch * CW, ra);
         tmem_ld_nowait(tdQb + lane_base + ch * CW, rq);
         tmem_ld_wait();
-        if (SM::kAlias) {  // the dSb columns (= dQa / dQb) may be overwritten by the next tile's dSb
-          tc_fence_before_sync();
-          named_arrive(NB_E, kNbAB);
-        }
         const float wb = bbar * rinv;
         dot = 0.f;
 #pragma unroll
