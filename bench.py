@@ -284,7 +284,7 @@ def main():
         bw_ms.append(b_.elapsed_time(c_))
     fw_t, bw_t = statistics.median(fw_ms), statistics.median(bw_ms)
     hbm_peak, tf_peak, peak_kind = peaks()
-    dom = ("bw", bw_bytes, bw_t, "tc_bw_d64") if bw_t >= fw_t else ("fw", fw_bytes, fw_t, "tc_fw_d64")
+    dom = ("bw", bw_bytes, bw_t, "tc_bw") if bw_t >= fw_t else ("fw", fw_bytes, fw_t, "tc_fw")
     traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu capture (same workload)
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[dom[3]]
