@@ -9,8 +9,9 @@ B, NH, S, D = 32, 4, 1600, 64
 inp = O.make_inputs(B, NH, S, D, D, seed=0, dtype=torch.float32)
 host = {k: v.to(torch.bfloat16).pin_memory() for k, v in inp.items()}
 out = pkg.HostFwBw.alloc_host(B, NH, S, D, D)
-for ns in (1, 2, 4, 8, 16):
-    pipe = pkg.HostFwBw(B, NH, S, D, D, n_slices=ns)
+for ns, tp in ((2, False), (3, False), (3, True), (4, True), (5, True), (6, True)):
+    pipe = pkg.HostFwBw(B, NH, S, D, D, n_slices=ns, taper=tp)
+    print([sl.stop - sl.start for sl in pipe.slices], end=' ')
     for _ in range(3):
         pipe.run(host, out)
     torch.cuda.synchronize()

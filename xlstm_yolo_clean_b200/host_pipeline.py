@@ -14,7 +14,7 @@ _OUT = ("h", "dq", "dk", "dv", "di", "df")
 
 
 class HostFwBw:
-    def __init__(self, B, NH, S, DK, DV, dtype=torch.bfloat16, device="cuda:0", n_slices=8, chunk_size=64, eps=1e-6):
+    def __init__(self, B, NH, S, DK, DV, dtype=torch.bfloat16, device="cuda:0", n_slices=8, chunk_size=64, eps=1e-6, taper=True):
         self.dev = torch.device(device)
         self.n_slices = max(1, min(n_slices, B))
         self.chunk_size, self.eps = chunk_size, eps
@@ -22,8 +22,16 @@ class HostFwBw:
                    h=(B, NH, S, DV), dq=(B, NH, S, DK), dk=(B, NH, S, DK), dv=(B, NH, S, DV), di=(B, NH, S), df=(B, NH, S))
         self.d_in = {k: torch.empty(shp[k], dtype=dtype, device=self.dev) for k in _IN}
         self.s_h2d, self.s_cmp, self.s_d2h = (torch.cuda.Stream(self.dev) for _ in range(3))
-        bounds = torch.linspace(0, B, self.n_slices + 1).round().long().tolist()
+        # tapered batch slices: small first and last slices keep the pipeline's fill (first H2D, nothing else
+        # running) and drain (last D2H) short, large middle slices keep the number of copies low
+        n = self.n_slices
+        w = [min(2.0 ** j, 2.0 ** (n - 1 - j), 8.0) for j in range(n)] if taper else [1.0] * n
+        acc, bounds = 0.0, [0]
+        for x in w:
+            acc += x
+            bounds.append(int(round(B * acc / sum(w))))
         self.slices = [slice(a, b) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+        self._graphs, self._keep = {}, {}
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.d_in.values())
         self.d2h_bytes = sum(torch.Size(shp[k]).numel() for k in _OUT) * torch.empty((), dtype=dtype).element_size()
 
@@ -32,9 +40,32 @@ class HostFwBw:
         shp = dict(h=(B, NH, S, DV), dq=(B, NH, S, DK), dk=(B, NH, S, DK), dv=(B, NH, S, DV), di=(B, NH, S), df=(B, NH, S))
         return {k: torch.empty(v, dtype=dtype).pin_memory() for k, v in shp.items()}
 
-    def run(self, host_in: dict, host_out: dict):
+    def run(self, host_in: dict, host_out: dict, use_graph: bool = True):
         """host_in: pinned q,k,v,i,f,dh; host_out: pinned h,dq,dk,dv,di,df (filled asynchronously;
-        synchronise the device or `self.s_d2h` before reading them)."""
+        synchronise the device or the current stream before reading them).
+
+        With ``use_graph`` the whole pipeline (copies and kernels on the three streams) is captured once per set
+        of host buffers and replayed: a step costs one graph launch instead of ~30 Python-level launches per
+        slice, which otherwise bound the step at more than 8 slices."""
+        if not use_graph:
+            return self._run(host_in, host_out, record=True)
+        key = tuple(host_in[k].data_ptr() for k in _IN) + tuple(host_out[k].data_ptr() for k in _OUT)
+        g = self._graphs.get(key)
+        if g is None:
+            self._run(host_in, host_out, record=True)  # warm-up outside capture (lazy module / attribute setup)
+            torch.cuda.current_stream(self.dev).synchronize()
+            g = torch.cuda.CUDAGraph()
+            cap = torch.cuda.Stream(self.dev)
+            cap.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.graph(g, stream=cap):
+                self._run(host_in, host_out, record=False)
+            torch.cuda.current_stream(self.dev).wait_stream(cap)
+            self._graphs[key] = g
+            self._keep[key] = (host_in, host_out)  # the graph holds raw pointers into these buffers
+        g.replay()
+        return host_out
+
+    def _run(self, host_in: dict, host_out: dict, record: bool):
         cur = torch.cuda.current_stream(self.dev)
         for s in (self.s_h2d, self.s_cmp, self.s_d2h):
             s.wait_stream(cur)
@@ -59,10 +90,13 @@ class HostFwBw:
                 self.s_d2h.wait_event(e_c)
                 for k in _OUT:
                     host_out[k][sl].copy_(outs[k], non_blocking=True)
-                    outs[k].record_stream(self.s_d2h)
+                    if record:
+                        outs[k].record_stream(self.s_d2h)
             keep.append((n_out, m_out, cst))
-            for t in (n_out, m_out, cst):
-                if t is not None:
-                    t.record_stream(self.s_cmp)
-        cur.wait_stream(self.s_d2h)
+            if record:
+                for t in (n_out, m_out, cst):
+                    if t is not None:
+                        t.record_stream(self.s_cmp)
+        for s in (self.s_h2d, self.s_cmp, self.s_d2h):
+            cur.wait_stream(s)
         return host_out
