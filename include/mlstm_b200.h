@@ -152,6 +152,12 @@ int mlstm_b200_last_launch_count(void);
  * (forward at [tile*16 + slot], backward at [4096 + tile*16 + slot]).  NULL disables it. */
 void mlstm_b200_debug_set_clock_buffer(void* dev_ptr);
 
+/* Backward formulation of the tensor-core path: 1 = tc_bw (query index on the TMEM lanes; default),
+ * 2 = tc_bw2 (transposed: key / value index on the lanes, TS-mode operands, one accumulator per output).
+ * Both compute the same function (bw.py:206-348); returns the previous value.  Also settable through
+ * the environment variable MLSTM_B200_BW before the first call. */
+int mlstm_b200_debug_set_bw_variant(int variant);
+
 #ifdef __cplusplus
 }
 #endif

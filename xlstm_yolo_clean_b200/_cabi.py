@@ -24,6 +24,7 @@ EXPORTS = (
     "mlstm_b200_chunkwise_bw",
     "mlstm_b200_last_launch_count",
     "mlstm_b200_debug_set_clock_buffer",
+    "mlstm_b200_debug_set_bw_variant",
 )
 
 
@@ -100,6 +101,8 @@ def load_library(path: str | None = None):
     lib.mlstm_b200_last_launch_count.restype = C.c_int
     lib.mlstm_b200_debug_set_clock_buffer.restype = None
     lib.mlstm_b200_debug_set_clock_buffer.argtypes = [C.c_void_p]
+    lib.mlstm_b200_debug_set_bw_variant.restype = C.c_int
+    lib.mlstm_b200_debug_set_bw_variant.argtypes = [C.c_int]
     v = lib.mlstm_b200_abi_version()
     if v != ABI_VERSION:
         raise RuntimeError(f"ABI mismatch: library {v}, binding {ABI_VERSION}")

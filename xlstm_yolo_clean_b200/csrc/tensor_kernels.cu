@@ -1675,10 +1675,11 @@ struct Bw2Smem {
   static constexpr int kTile = Lay<D>::kTile;   // one [128][D] tile
   static constexpr int kPTile = LT * 128;       // one [128][64] half of dS^T
   static constexpr int kState = Lay<D>::kState;
-  static constexpr int kNST = D == 64 ? 1 : 2;  // input stages of [Q | K | V | dH | C_{k-1}]
-  static constexpr int kStage = 4 * kTile + kState;
-  static constexpr int oQ = 0, oK = kTile, oV = 2 * kTile, odH = 3 * kTile, oCs = 4 * kTile;  // inside a stage
-  static constexpr int oQt = kNST * kStage;     // wq . Q
+  // Input buffers.  D = 32: two of each (a whole tile prefetched ahead).  D = 64: two K and two dH tiles (loaded a
+  // tile ahead), one Q, V, C_{k-1}, re-filled behind the MMA batch as soon as their last reader has completed.
+  static constexpr int nQ = D == 64 ? 1 : 2, nK = 2, nV = nQ, nH = 2, nCs = nQ;
+  static constexpr int oQ = 0, oK = oQ + nQ * kTile, oV = oK + nK * kTile, odH = oV + nV * kTile, oCs = odH + nH * kTile;
+  static constexpr int oQt = oCs + nCs * kState;  // wq . Q
   static constexpr int odS = oQt + kTile;       // dS^T rows, two halves (query columns 0-63 / 64-127)
   static constexpr int odQ = odS + 2 * kPTile;  // dq / dv / dk staging
   static constexpr int odV = odQ + kTile;
@@ -1687,7 +1688,6 @@ struct Bw2Smem {
   static constexpr int oSmall = odC + kState;
   static constexpr int fGates = 0, fPart = 2 * GateBuf::kFloats, kSmallFloats = fPart + 12 * LT;
   static constexpr int kBytes = oSmall + kSmallFloats * 4 + 1024;
-  static constexpr uint32_t kLoadBytes = 4 * kTile + kState;
   static constexpr bool kAlias = false;
   // TMEM: S^T and dSb^T (128 columns each; later the packed operands), one accumulator per output
   static constexpr uint32_t cST = 0, cdST = 128, cdV = 256, cdK = cdV + D, cdQ = cdK + D, cddC = cdQ + D;
@@ -1706,7 +1706,7 @@ tc_bw2(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtenso
   TC_PROF(200, 0);  // kernel entry
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sQ = smem + SM::oQ;  // stage 0; stage s is SM::kStage bytes further
+  uint8_t* sQ = smem + SM::oQ;  // buffer 0 of each input; processing step `it` uses buffer it % n
   uint8_t* sK = smem + SM::oK;
   uint8_t* sV = smem + SM::oV;
   uint8_t* sdH = smem + SM::odH;
@@ -1718,7 +1718,7 @@ tc_bw2(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtenso
   uint8_t* sCs = smem + SM::oCs;
   uint8_t* sdC = smem + SM::odC;
   float* fsm = (float*)(smem + SM::oSmall);
-  __shared__ uint64_t bar_full[SM::kNST], bar_s, bar_q, bar_v, bar_k, bar_d, bar_st, bar_g[2];
+  __shared__ uint64_t bar_fa[2], bar_fb[2], bar_fc[2], bar_s, bar_q, bar_v, bar_k, bar_d, bar_st, bar_g[2];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -1727,20 +1727,24 @@ tc_bw2(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtenso
 
   // memory tile of processing tile c (see the forward kernel); the sweep visits c = NT-1 .. 0
   auto mt = [&](int c) { return REV ? p.NT - 1 - c : c; };
-  auto load_stage = [&](int s, int c) {  // every input tile of memory tile mt(c) into stage s
-    uint8_t* base = smem + s * SM::kStage;
-    mbar_expect_tx(&bar_full[s], SM::kLoadBytes);
-    tma_load_4d(base + SM::oQ, &mapQ, &bar_full[s], 0, mt(c) * LT, hh, b);
-    tma_load_4d(base + SM::oK, &mapK, &bar_full[s], 0, mt(c) * LT, hh, b);
-    tma_load_4d(base + SM::oV, &mapV, &bar_full[s], 0, mt(c) * LT, hh, b);
-    tma_load_4d(base + SM::odH, &mapdH, &bar_full[s], 0, mt(c) * LT, hh, b);
-    tma_load_4d(base + SM::oCs, &mapCs, &bar_full[s], 0, mt(c) * D, hh, b);
+  // loads of processing step `it` (memory tile mt(NT-1-it)): Q, K complete on bar_fa[it & 1] (operands of S^T),
+  // V, dH on bar_fb (operands of dSb^T), C_{k-1} on bar_fc
+  auto expect_step = [&](int it) {
+    mbar_expect_tx(&bar_fa[it & 1], 2 * SM::kTile);
+    mbar_expect_tx(&bar_fb[it & 1], 2 * SM::kTile);
+    mbar_expect_tx(&bar_fc[it & 1], SM::kState);
   };
+  auto load_Q = [&](int it) { tma_load_4d(sQ + (it % SM::nQ) * SM::kTile, &mapQ, &bar_fa[it & 1], 0, mt(p.NT - 1 - it) * LT, hh, b); };
+  auto load_K = [&](int it) { tma_load_4d(sK + (it % SM::nK) * SM::kTile, &mapK, &bar_fa[it & 1], 0, mt(p.NT - 1 - it) * LT, hh, b); };
+  auto load_V = [&](int it) { tma_load_4d(sV + (it % SM::nV) * SM::kTile, &mapV, &bar_fb[it & 1], 0, mt(p.NT - 1 - it) * LT, hh, b); };
+  auto load_H = [&](int it) { tma_load_4d(sdH + (it % SM::nH) * SM::kTile, &mapdH, &bar_fb[it & 1], 0, mt(p.NT - 1 - it) * LT, hh, b); };
+  auto load_C = [&](int it) { tma_load_4d(sCs + (it % SM::nCs) * SM::kState, &mapCs, &bar_fc[it & 1], 0, mt(p.NT - 1 - it) * D, hh, b); };
   // cold start: the first input tiles are requested before anything else happens in the CTA
   if (tid == kCtlWarp * 32) {
-    for (int s = 0; s < SM::kNST; ++s) mbar_init(&bar_full[s], 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&bar_fa[s], 1); mbar_init(&bar_fb[s], 1); mbar_init(&bar_fc[s], 1); }
     fence_mbar_init();
-    for (int s = 0; s < SM::kNST && s < p.NT; ++s) load_stage(s, p.NT - 1 - s);
+    expect_step(0);
+    load_Q(0); load_K(0); load_V(0); load_H(0); load_C(0);
   }
   if (tid == 0) {
     mbar_init(&bar_s, 1);
@@ -1810,15 +1814,15 @@ tc_bw2(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtenso
     const uint64_t kdS = umma_smem_desc(smem_u32(sdS), 0, 1024), mdS = umma_smem_desc(smem_u32(sdS), SM::kPTile, 1024);
     const uint64_t kdC = L::desc(smem_u32(sdC), 0), mdC = L::desc(smem_u32(sdC), SM::kState);
     auto issue_s = [&](int it) {  // S^T = K Q^T, dSb^T = V dH^T of processing step `it` (its loads are in flight)
-      const int s = it % SM::kNST;
-      const uint32_t so = (uint32_t)s * SM::kStage;
-      const uint64_t kQ = umma_desc_advance(kQ0, so), kK = umma_desc_advance(kK0, so);
-      const uint64_t kH = umma_desc_advance(kH0, so), kV = umma_desc_advance(kV0, so);
-      mbar_wait(&bar_full[s], (it / SM::kNST) & 1, 11);
+      const uint64_t kQ = umma_desc_advance(kQ0, (it % SM::nQ) * SM::kTile), kK = umma_desc_advance(kK0, (it % SM::nK) * SM::kTile);
+      const uint64_t kH = umma_desc_advance(kH0, (it % SM::nH) * SM::kTile), kV = umma_desc_advance(kV0, (it % SM::nV) * SM::kTile);
+      mbar_wait(&bar_fa[it & 1], (it >> 1) & 1, 11);
       tc_fence_after_sync();
 #pragma unroll
       for (int kk = 0; kk < D / 16; ++kk)
         umma_f16(tST, umma_desc_advance(kK, kk * 32), umma_desc_advance(kQ, kk * 32), id_s, kk > 0);
+      mbar_wait(&bar_fb[it & 1], (it >> 1) & 1, 11);
+      tc_fence_after_sync();
 #pragma unroll
       for (int kk = 0; kk < D / 16; ++kk)
         umma_f16(tdST, umma_desc_advance(kV, kk * 32), umma_desc_advance(kH, kk * 32), id_s, kk > 0);
@@ -1832,22 +1836,30 @@ tc_bw2(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtenso
       const int c = p.NT - 1 - it, pb = it & 1;
       const uint32_t par = it & 1;
       const int t0 = mt(c) * LT, n_valid = min(LT, p.S - t0);
-      const uint32_t so = (uint32_t)(it % SM::kNST) * SM::kStage;
-      const uint64_t kQ = umma_desc_advance(kQ0, so), mQ = umma_desc_advance(mQ0, so);
-      const uint64_t kK = umma_desc_advance(kK0, so), mK = umma_desc_advance(mK0, so);
-      const uint64_t kV = umma_desc_advance(kV0, so), kCs = umma_desc_advance(kCs0, so);
-      const uint64_t kH = umma_desc_advance(kH0, so), mH = umma_desc_advance(mH0, so);
+      const uint64_t mQ = umma_desc_advance(mQ0, (it % SM::nQ) * SM::kTile), mK = umma_desc_advance(mK0, (it % SM::nK) * SM::kTile);
+      const uint64_t mH = umma_desc_advance(mH0, (it % SM::nH) * SM::kTile), kCs = umma_desc_advance(kCs0, (it % SM::nCs) * SM::kState);
       TC_PROF(it, 9);
-      if (SM::kNST == 1 && c > 0 && lane == 0) {  // single input stage: pull the next tile into L2 a whole tile ahead,
-        const int r = mt(c - 1) * LT;             // so that the re-fills behind the MMA batch are L2 hits
-        tma_prefetch_4d(&mapQ, 0, r, hh, b);
-        tma_prefetch_4d(&mapK, 0, r, hh, b);
-        tma_prefetch_4d(&mapV, 0, r, hh, b);
-        tma_prefetch_4d(&mapdH, 0, r, hh, b);
-        tma_prefetch_4d(&mapCs, 0, mt(c - 1) * D, hh, b);
+      if (c > 0 && lane == 0) {  // inputs of the next tile
+        expect_step(it + 1);
+        if (SM::nK == 2) load_K(it + 1);  // double-buffered: the other buffer was released by the previous tile's batch
+        load_H(it + 1);
+        if (SM::nQ == 2) { load_Q(it + 1); load_V(it + 1); load_C(it + 1); }
+        else {  // single buffers: pull the rows into L2 now, so that the re-fills behind the MMA batch are L2 hits
+          const int r = mt(c - 1) * LT;
+          tma_prefetch_4d(&mapQ, 0, r, hh, b);
+          tma_prefetch_4d(&mapV, 0, r, hh, b);
+          tma_prefetch_4d(&mapCs, 0, mt(c - 1) * D, hh, b);
+          if (SM::nK == 1) tma_prefetch_4d(&mapK, 0, r, hh, b);
+        }
       }
-      named_sync(NB_B, kNbAB);  // Sb', dS written
+      named_sync(NB_B, kNbAB);  // operands written, input rows read
       TC_PROF(it, 10);
+      if (lane == 0) {
+        tma_store_wait_read<0>();  // the previous tile's dq / dk / dv stores (issued a W phase ago) have left their
+        mbar_arrive(&bar_st);      // staging buffers
+        mbar_wait(&bar_fc[it & 1], (it >> 1) & 1, 26);  // C_{k-1} has landed
+      }
+      __syncwarp();
       // MMA batch.  Every 128 x 128 A operand that has the tile row on its M axis comes from TMEM (TS mode: no
       // shared-memory read for A), the inter-chunk terms are accumulated into the same TMEM columns through
       // row-scaled operand copies, so each output has ONE accumulator and needs no scaling in its epilogue.
@@ -1863,45 +1875,42 @@ tc_bw2(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtenso
 #pragma unroll
         for (int kk = 0; kk < LT / 16; ++kk)  // dq  = dS K              (A = dS^T rows in shared memory, MN-major)
           umma_f16(tdQ, umma_desc_advance(mdS, kk * 2048), umma_desc_advance(mK, kk * L::kAdvMN), id_mn_mn, kk > 0);
+      }
+      __syncwarp();
+      named_sync(NB_A, kNbAB);  // Kbar / dHbar copies written
+      if (elect_one()) {
+        tc_fence_after_sync();
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk)   //     + (wb dH) C_{k-1}^T (A = dHbar slots of tST)
           umma_f16_ts(tdQ, half_op(tST, 2, kk), umma_desc_advance(kCs, kk * 32), id_ts_k, true);
         umma_commit(&bar_q);  // K, C_{k-1} consumed; dq complete
-#pragma unroll
-        for (int kk = 0; kk < LT / 16; ++kk)  // ddC = Qt^T dH
-          umma_f16(tddC, umma_desc_advance(mQt, kk * L::kAdvMN), umma_desc_advance(mH, kk * L::kAdvMN), id_c, kk > 0);
-        umma_commit(&bar_d);
 #pragma unroll
         for (int kk = 0; kk < LT / 16; ++kk)  // dv  = Sb'^T dH          (A = packed Sb'^T in tST)
           umma_f16_ts(tdV, tST + 32 * (kk / 2) + 8 * (kk % 2), umma_desc_advance(mH, kk * L::kAdvMN), id_ts_mn, kk > 0);
 #pragma unroll
         for (int kk = 0; kk < D / 16; ++kk)   //     + (abar K) dC_k     (A = Kbar slots of tST)
           umma_f16_ts(tdV, half_op(tST, 0, kk), umma_desc_advance(mdC, kk * L::kAdvMN), id_ts_mn, true);
-        umma_commit(&bar_v);  // dH consumed; dv complete
-      }
-      __syncwarp();
-      if (lane == 0) {  // (off the MMA issue path: 128 CTAs store in lockstep, the reads take a while to drain)
-        tma_store_wait_read<0>();  // the previous tile's dq / dk / dv stores have left their staging buffers
-        mbar_arrive(&bar_st);
+        umma_commit(&bar_v);  // dv complete (dC_k consumed)
+#pragma unroll
+        for (int kk = 0; kk < LT / 16; ++kk)  // ddC = Qt^T dH
+          umma_f16(tddC, umma_desc_advance(mQt, kk * L::kAdvMN), umma_desc_advance(mH, kk * L::kAdvMN), id_c, kk > 0);
+        umma_commit(&bar_d);  // dH consumed; last group of the batch
       }
       __syncwarp();
       TC_PROF(it, 11);
-      if (SM::kNST == 1) {
-        if (c > 0 && elect_one()) {  // re-fill the single stage tile by tile, each as soon as its last reader has completed
-          const int r = mt(c - 1) * LT;
-          mbar_expect_tx(&bar_full[0], SM::kLoadBytes);
-          tma_load_4d(sV, &mapV, &bar_full[0], 0, r, hh, b);  // V: only dSb^T (complete) and the workers (NB_B) read it
+      if (c > 0 && elect_one()) {
+        if (SM::nQ == 1) {  // single-buffered inputs: re-fill each as soon as its last reader has completed
+          load_V(it + 1);   // V: only dSb^T (complete) and the workers (before NB_B) read it
           mbar_wait(&bar_k, par, 21);
-          tma_load_4d(sQ, &mapQ, &bar_full[0], 0, r, hh, b);
-          mbar_wait(&bar_q, par, 24);
-          tma_load_4d(sK, &mapK, &bar_full[0], 0, r, hh, b);
-          tma_load_4d(sCs, &mapCs, &bar_full[0], 0, mt(c - 1) * D, hh, b);
-          mbar_wait(&bar_v, par, 25);
-          tma_load_4d(sdH, &mapdH, &bar_full[0], 0, r, hh, b);
+          load_Q(it + 1);
         }
-      } else if (c >= SM::kNST && elect_one()) {  // this stage is free once the whole batch has completed
-        mbar_wait(&bar_v, par, 25);
-        load_stage(it % SM::kNST, c - SM::kNST);
+        mbar_wait(&bar_v, par, 25);  // the TS groups have read their packed TMEM operands (ddC, still queued, has none) (measured: an MMA that writes
+        issue_s(it + 1);             // TMEM columns may overtake the A-operand reads of the instruction before it)
+        if (SM::nQ == 1) {
+          mbar_wait(&bar_q, par, 24);
+          if (SM::nK == 1) load_K(it + 1);
+          load_C(it + 1);
+        }
       }
       __syncwarp();
       TC_PROF(it, 13);
@@ -1913,8 +1922,6 @@ tc_bw2(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtenso
         tma_store_4d(&mapdK, sdK, 0, t0, hh, b);
         tma_store_commit();
       }
-      __syncwarp();
-      if (c > 0 && elect_one()) issue_s(it + 1);  // S^T / dSb^T of the next tile
       __syncwarp();
     }
     if (lane == 0) tma_store_wait_all<0>();
@@ -2055,7 +2062,6 @@ tc_bw2(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtenso
       float* spart = fsm + SM::fPart + pb * 6 * LT;
       const int n_valid = min(LT, p.S - mt(p.NT - 1 - it) * LT);
       const bool valid = row < n_valid;
-      const uint32_t so = (uint32_t)(it % SM::kNST) * SM::kStage;  // input stage of this tile
 
       TC_PROF(it, 0);
       mbar_wait(&bar_g[pb], (it >> 1) & 1, 12);
@@ -2069,14 +2075,14 @@ tc_bw2(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtenso
       TC_PROF(it, 1);
       // ---- Qt = wq . Q, written while the S / dSb MMAs of this tile run (ddC of the previous tile, the last
       // reader of sQt, completed before the previous dC update); q row slice kept for the gate gradients
-      mbar_wait(&bar_full[it % SM::kNST], (it / SM::kNST) & 1, 13);
+      mbar_wait(&bar_fa[it & 1], (it >> 1) & 1, 13);
       uint32_t qs[CW / 2];
       {
         const float wq = p.scale * bbar * rinv;  // bw.py:83-90
 #pragma unroll
         for (int j = 0; j < CW / 8; ++j) {
           const uint32_t off = L::swz(row, ch * CW + 8 * j);
-          uint4 u = *reinterpret_cast<const uint4*>(sQ + so + off);
+          uint4 u = *reinterpret_cast<const uint4*>(sQ + (it % SM::nQ) * SM::kTile + off);
           qs[4 * j] = u.x; qs[4 * j + 1] = u.y; qs[4 * j + 2] = u.z; qs[4 * j + 3] = u.w;
           float2 a0 = unpack2<T>(u.x), a1 = unpack2<T>(u.y), a2 = unpack2<T>(u.z), a3 = unpack2<T>(u.w);
           u.x = pack2<T>(a0.x * wq, a0.y * wq);
@@ -2157,6 +2163,7 @@ tc_bw2(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtenso
         }
       }
       // ---- row-scaled operand copies into the free TMEM slots; k / v row slices kept for the gate gradients ----
+      mbar_wait(&bar_fb[it & 1], (it >> 1) & 1, 13);
       uint32_t ks[CW / 2], vs[CW / 2];
       {
         uint32_t ob[CW / 2];
@@ -2165,30 +2172,35 @@ tc_bw2(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtenso
 #pragma unroll
         for (int j = 0; j < CW / 8; ++j) {
           const uint32_t off = L::swz(row, ch * CW + 8 * j);
-          const uint4 uk = *reinterpret_cast<const uint4*>(sK + so + off);
+          const uint4 uk = *reinterpret_cast<const uint4*>(sK + (it % SM::nK) * SM::kTile + off);
           ks[4 * j] = uk.x; ks[4 * j + 1] = uk.y; ks[4 * j + 2] = uk.z; ks[4 * j + 3] = uk.w;
-          const uint4 uv = *reinterpret_cast<const uint4*>(sV + so + off);
+          const uint4 uv = *reinterpret_cast<const uint4*>(sV + (it % SM::nV) * SM::kTile + off);
           vs[4 * j] = uv.x; vs[4 * j + 1] = uv.y; vs[4 * j + 2] = uv.z; vs[4 * j + 3] = uv.w;
         }
+#pragma unroll
+        for (int j = 0; j < CW / 2; ++j) ob[j] = mul2<T>(vs[j], ab);   // Vbar = abar v  (bw.py:192)
+        tmem_st(slot(tdST, ch) + lane_base, ob);
+        // first hand-off: everything the dk group and the shared-memory half of the dq group need
+        tmem_st_wait();
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        named_arrive(NB_B, kNbAB);
+        TC_PROF(it, 3);
 #pragma unroll
         for (int j = 0; j < CW / 2; ++j) ob[j] = mul2<T>(ks[j], ab);   // Kbar = abar k  (bw.py:190)
         tmem_st(slot(tST, ch) + lane_base, ob);
 #pragma unroll
-        for (int j = 0; j < CW / 2; ++j) ob[j] = mul2<T>(vs[j], ab);   // Vbar = abar v  (bw.py:192)
-        tmem_st(slot(tdST, ch) + lane_base, ob);
-#pragma unroll
         for (int j = 0; j < CW / 8; ++j) {
-          const uint4 uh = *reinterpret_cast<const uint4*>(sdH + so + L::swz(row, ch * CW + 8 * j));
+          const uint4 uh = *reinterpret_cast<const uint4*>(sdH + (it % SM::nH) * SM::kTile + L::swz(row, ch * CW + 8 * j));
           ob[4 * j] = mul2<T>(uh.x, wbs); ob[4 * j + 1] = mul2<T>(uh.y, wbs);
           ob[4 * j + 2] = mul2<T>(uh.z, wbs); ob[4 * j + 3] = mul2<T>(uh.w, wbs);  // dHbar = scale bbar/(n+eps) dh (bw.py:193)
         }
         tmem_st(slot(tST, ch + 2) + lane_base, ob);
       }
+      // second hand-off: the row-scaled copies the remaining TS instructions read (written while the dk group runs)
       tmem_st_wait();
-      fence_proxy_async_smem();
       tc_fence_before_sync();
-      named_arrive(NB_B, kNbAB);
-      TC_PROF(it, 3);
+      named_arrive(NB_A, kNbAB);
       TC_PROF(it, 4);
       // ---- epilogues (one accumulator per output, no scaling), pipelined with the MMA batch ------------------
       {
@@ -2229,20 +2241,7 @@ tc_bw2(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtenso
         store_cols<T, D>(sdQ, row, ch * CW, o);
         spart[(0 * 2 + ch) * LT + row] = dot;
       }
-      // ---- dC_{k-1} = gbar dC_k + ddC ----------------------------------------------------------------
-      mbar_wait(&bar_d, par, 15);
-      tc_fence_after_sync();
-      TC_PROF(it, 7);
-      {
-        float v[CW];
-        tmem_ld(tddC + lane_base + ch * CW, v);
-        if (owns_c) {
-#pragma unroll
-          for (int j = 0; j < CW; ++j) dCreg[j] = gbar * dCreg[j] + v[j];  // bw.py:93-95
-          store_cols<T, D>(sdC, drow, ch * CW, dCreg);                     // its readers (dk, dv) ... see below
-        }
-      }
-      // ---- dv last ---------------------------------------------------------------------------------------
+      // ---- dv ---------------------------------------------------------------------------------------
       {
         uint32_t ra[CW];
         float o[CW];
@@ -2260,6 +2259,19 @@ tc_bw2(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtenso
         }
         store_cols<T, D>(sdV, row, ch * CW, o);
         spart[(2 * 2 + ch) * LT + row] = dot;
+      }
+      // ---- dC_{k-1} = gbar dC_k + ddC ----------------------------------------------------------------
+      mbar_wait(&bar_d, par, 15);
+      tc_fence_after_sync();
+      TC_PROF(it, 7);
+      {
+        float v[CW];
+        tmem_ld(tddC + lane_base + ch * CW, v);
+        if (owns_c) {
+#pragma unroll
+          for (int j = 0; j < CW; ++j) dCreg[j] = gbar * dCreg[j] + v[j];  // bw.py:93-95
+          store_cols<T, D>(sdC, drow, ch * CW, dCreg);                     // its readers (dk, dv groups) have completed
+        }
       }
       fence_proxy_async_smem();
       tc_fence_before_sync();
@@ -2327,14 +2339,15 @@ int launch_bw2(const TcBwParams& p, const CUtensorMap& mq, const CUtensorMap& mk
   return 0;
 }
 
-// which backward formulation: 2 = transposed (tc_bw2, default), 1 = tc_bw (MLSTM_B200_BW=1 in the environment)
+// which backward formulation: 1 = tc_bw (default), 2 = transposed tc_bw2 (MLSTM_B200_BW=2 in the environment or
+// mlstm_b200_debug_set_bw_variant)
+int g_bw_variant = 0;
 int bw_variant() {
-  static int v = 0;
-  if (!v) {
+  if (!g_bw_variant) {
     const char* e = getenv("MLSTM_B200_BW");
-    v = (e && e[0] == '1') ? 1 : 2;
+    g_bw_variant = (e && e[0] == '2') ? 2 : 1;
   }
-  return v;
+  return g_bw_variant;
 }
 
 template <typename T, int D>
@@ -2425,6 +2438,11 @@ BwWs bw_ws(const mlstm_b200_shape& s) {
 }  // namespace
 
 void tensor_set_clock_buffer(void* dev_ptr) { g_prof = (long long*)dev_ptr; }
+int tensor_set_bw_variant(int variant) {
+  const int prev = bw_variant();
+  if (variant == 1 || variant == 2) g_bw_variant = variant;
+  return prev;
+}
 
 // forward: d = 32, 64 and 128; backward: d = 32 and 64 (d = 128 backward does not fit shared memory with 128-token tiles)
 bool tensor_supported(const mlstm_b200_shape& s, int backward) {
