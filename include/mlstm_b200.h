@@ -158,6 +158,52 @@ void mlstm_b200_debug_set_clock_buffer(void* dev_ptr);
  * the environment variable MLSTM_B200_BW before the first call. */
 int mlstm_b200_debug_set_bw_variant(int variant);
 
+/* ---------------------------------------------------------------------------------------------
+ * The cell's output stage (the callers either side of the path).
+ *
+ *   y[b,s,hd*D+d] = (h[b,hd,s,d] - mean) * rstd * weight[c] + bias[c] + skip[c] * x[b,s,c]
+ *
+ * with mean / rstd over the D elements of one (token, head) group (biased variance, rstd = (var+eps)^-1/2).
+ * One pass replaces, in the reference:
+ *   MultiHeadLayerNorm.forward       ultralytics/nn/modules/vision_lstm/vision_lstm2.py:928-944
+ *   MatrixLSTMCell.forward tail      vision_lstm2.py:749-751 (h.to(dtype), transpose + reshape copy)
+ *   ViLLayer.mlstm_branch skip add   vision_lstm2.py:306     (h + learnable_skip * x_qk_conv_act)
+ * and mlstm_b200_cellout_bw replaces their autograd backward.
+ *   h, dh   (B, NH, S, D)  element strides [b, head, s, 1], h_dtype
+ *   x, y, dy, dx (B, S, NH*D)  element strides [b, s, 1];  x and y share one dtype (x_dtype == y_dtype)
+ *   weight (= 1 + MultiHeadLayerNorm.weight, the reference's weight_proxy, vision_lstm2.py:900-907),
+ *   bias, skip: contiguous fp32 (NH*D); weight / bias may be NULL (1 / 0); x.ptr == NULL drops the skip term.
+ * Supported: D in {32, 64, 128}, NH*D a multiple of 128 and <= 2048; pointers 8-byte (16-bit types) or
+ * 16-byte (fp32) aligned, strides multiples of 4 elements.
+ */
+typedef struct mlstm_b200_cellout_args {
+  int32_t B, NH, S, D;
+  int32_t h_dtype, x_dtype, y_dtype; /* MLSTM_B200_F32 / BF16 / F16 */
+  float eps;
+  mlstm_b200_tensor h;
+  mlstm_b200_tensor x; /* optional */
+  mlstm_b200_tensor y; /* out */
+  const float* weight;
+  const float* bias;
+  const float* skip;
+} mlstm_b200_cellout_args;
+
+typedef struct mlstm_b200_cellout_bw_args {
+  mlstm_b200_cellout_args fw; /* h, x, weight, skip as given to the forward (y is ignored) */
+  mlstm_b200_tensor dy;       /* incoming gradient, y_dtype */
+  mlstm_b200_tensor dh;       /* out, h_dtype */
+  mlstm_b200_tensor dx;       /* out, x_dtype: dy * skip; optional */
+  float* dweight;             /* out (NH*D) fp32, each optional */
+  float* dbias;
+  float* dskip;
+  void* workspace;            /* mlstm_b200_cellout_workspace_bytes() bytes (CTA partial sums) */
+  size_t workspace_bytes;
+} mlstm_b200_cellout_bw_args;
+
+size_t mlstm_b200_cellout_workspace_bytes(const mlstm_b200_cellout_args* args);
+int mlstm_b200_cellout_fw(const mlstm_b200_cellout_args* args, void* cuda_stream);
+int mlstm_b200_cellout_bw(const mlstm_b200_cellout_bw_args* args, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

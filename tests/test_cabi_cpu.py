@@ -47,8 +47,9 @@ def test_struct_sizes_match_header(lib):
 
     from xlstm_yolo_clean_b200 import _cabi
 
-    code = '#include <stdio.h>\n#include "mlstm_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n",' \
-           "sizeof(mlstm_b200_tensor),sizeof(mlstm_b200_shape),sizeof(mlstm_b200_fw_args),sizeof(mlstm_b200_bw_args));}"
+    code = '#include <stdio.h>\n#include "mlstm_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",' \
+           "sizeof(mlstm_b200_tensor),sizeof(mlstm_b200_shape),sizeof(mlstm_b200_fw_args),sizeof(mlstm_b200_bw_args)," \
+           "sizeof(mlstm_b200_cellout_args),sizeof(mlstm_b200_cellout_bw_args));}"
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
         open(c, "w").write(code)
@@ -56,7 +57,7 @@ def test_struct_sizes_match_header(lib):
         out = subprocess.check_output([os.path.join(d, "s")]).split()
     sizes = [int(x) for x in out]
     assert sizes == [ctypes.sizeof(_cabi.Tensor), ctypes.sizeof(_cabi.Shape), ctypes.sizeof(_cabi.FwArgs),
-                     ctypes.sizeof(_cabi.BwArgs)]
+                     ctypes.sizeof(_cabi.BwArgs), ctypes.sizeof(_cabi.CellOutArgs), ctypes.sizeof(_cabi.CellOutBwArgs)]
 
 
 def test_workspace_query_needs_no_gpu(lib):
@@ -127,3 +128,36 @@ def test_registry_drop_in():
             be(q=q, k=q, v=q, i=g, f=g)
     finally:
         sys.path.remove("/root/reference")
+
+
+def test_rotated_conv_equals_flip_conv_flip():
+    """The identity the flip-free bottom-right branch rests on (vision_lstm2.py:292-294, 309-310): flipping the
+    row-major token sequence is a 180-degree rotation of the image, so conv(flip(x)) flipped back equals the
+    depthwise conv with its 3x3 kernel rotated.  Pure host logic, CPU."""
+    from xlstm_yolo_clean_b200 import vil
+
+    torch.manual_seed(0)
+    conv = torch.nn.Conv2d(24, 24, 3, padding=1, groups=24).double()
+    conv.seqlens = [6, 6]
+    x = torch.randn(2, 36, 48, dtype=torch.float64)[..., :24]  # a chunk view, like x_qk in mlstm_branch
+    want = vil._seq_conv(conv, x.flip(dims=[1]), rotate=False).flip(dims=[1])
+    got = vil._seq_conv(conv, x, rotate=True)
+    assert torch.allclose(got, want, atol=1e-12)
+
+
+def test_fused_cell_refuses_cpu():
+    import xlstm_yolo_clean_b200 as pkg
+
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        pkg.cell_out(torch.randn(1, 4, 8, 64))
+
+
+def test_cellout_without_device_returns_error(lib):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from xlstm_yolo_clean_b200 import _cabi
+
+    a = _cabi.CellOutArgs()
+    a.B, a.NH, a.S, a.D = 1, 2, 8, 64
+    st = lib.mlstm_b200_cellout_fw(ctypes.byref(a), None)
+    assert st != 0 and lib.mlstm_b200_last_error() != b""

@@ -1,0 +1,209 @@
+"""Parity of the cell's fused output stage and of the flip-free ViLLayer branch.
+
+The checker is a plain PyTorch fp32 restatement of what the reference composes
+(vision_lstm2.py:292-312, 701-753, 928-944): flips, F.group_norm over heads, transposes, skip add.
+Tolerances: 1e-5 relative for fp32 tensors, 2e-2 where a 16-bit rounding is part of the function."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import __graft_entry__ as G
+
+    G.build()
+    import xlstm_yolo_clean_b200 as p
+
+    return p
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def ref_cell_out(h, weight, bias, skip, x, eps):
+    """MultiHeadLayerNorm (vision_lstm2.py:928-944) + skip (vision_lstm2.py:306), float64."""
+    B, NH, S, D = h.shape
+    g = F.group_norm(h.double().transpose(1, 2).reshape(B * S, NH * D), NH,
+                     None if weight is None else weight.double(), None if bias is None else bias.double(), eps)
+    y = g.view(B, S, NH * D)
+    if x is not None:
+        y = y + skip.double() * x.double()
+    return y
+
+
+@pytest.mark.parametrize("NH,D", [(8, 64), (12, 32), (6, 128), (4, 64)])
+@pytest.mark.parametrize("h_dtype,x_dtype", [(torch.bfloat16, torch.float16), (torch.float32, torch.float32),
+                                             (torch.float16, torch.float32), (torch.bfloat16, torch.bfloat16)])
+def test_cell_out_fw_bw(pkg, NH, D, h_dtype, x_dtype):
+    torch.manual_seed(NH * 1000 + D)
+    dev = torch.device("cuda:0")
+    B, S = 3, 333  # rows not a multiple of anything the kernel tiles by
+    H = NH * D
+    h = (torch.randn(B, NH, S, D, device=dev) * 1.7 + 0.3).to(h_dtype).requires_grad_(True)
+    x = torch.randn(B, S, H, device=dev).to(x_dtype).requires_grad_(True)
+    w = (1.0 + 0.2 * torch.randn(H, device=dev)).requires_grad_(True)
+    b = (0.1 * torch.randn(H, device=dev)).requires_grad_(True)
+    sk = (1.0 + 0.1 * torch.randn(H, device=dev)).requires_grad_(True)
+    dy = torch.randn(B, S, H, device=dev).to(x_dtype)
+    y = pkg.cell_out(h, w, b, sk, x, eps=1e-6, out_dtype=x_dtype)
+    assert y.shape == (B, S, H) and y.dtype == x_dtype
+    y.backward(dy)
+    got = dict(y=y, dh=h.grad, dx=x.grad, dw=w.grad, db=b.grad, dsk=sk.grad)
+    leaves = [t.detach().double().requires_grad_(True) for t in (h, x, w, b, sk)]
+    yr = ref_cell_out(leaves[0], leaves[2], leaves[3], leaves[4], leaves[1], 1e-6)
+    yr.backward(dy.double())
+    want = dict(y=yr, dh=leaves[0].grad, dx=leaves[1].grad, dw=leaves[2].grad, db=leaves[3].grad, dsk=leaves[4].grad)
+    # outputs are rounded to their storage dtype once: half an ulp of the largest element
+    tol_of = {torch.float32: 1e-5, torch.float16: 1e-3, torch.bfloat16: 8e-3}
+    for k in got:
+        tol = tol_of[h_dtype] if k == "dh" else tol_of[x_dtype] if k in ("y", "dx") else 1e-5
+        assert rel(got[k], want[k]) < tol, (k, rel(got[k], want[k]), tol)
+
+
+def test_cell_out_no_skip_strided_h(pkg):
+    """h as a slice of a larger buffer (the padded-call case), no skip / bias."""
+    torch.manual_seed(1)
+    dev = torch.device("cuda:0")
+    B, NH, S, D = 2, 8, 100, 64
+    big = torch.randn(B, NH, S + 28, D, device=dev).to(torch.bfloat16)
+    h = big[:, :, 28:]
+    w = 1.0 + 0.2 * torch.randn(NH * D, device=dev)
+    y = pkg.cell_out(h, w, None, None, None, eps=1e-6, out_dtype=torch.float32)
+    assert rel(y, ref_cell_out(h, w, None, None, None, 1e-6)) < 1e-5
+
+
+def test_cell_out_deterministic(pkg):
+    torch.manual_seed(2)
+    dev = torch.device("cuda:0")
+    B, NH, S, D = 4, 8, 1600, 64
+    h = torch.randn(B, NH, S, D, device=dev).to(torch.bfloat16).requires_grad_(True)
+    x = torch.randn(B, S, NH * D, device=dev).to(torch.float16)
+    w, sk = (torch.randn(NH * D, device=dev).requires_grad_(True) for _ in range(2))
+    dy = torch.randn(B, S, NH * D, device=dev).to(torch.float16)
+    outs = []
+    for _ in range(2):
+        h.grad = w.grad = sk.grad = None
+        pkg.cell_out(h, w, None, sk, x, out_dtype=torch.float16).backward(dy)
+        outs.append((h.grad.clone(), w.grad.clone(), sk.grad.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)  # two-stage reduction in a fixed order: bit-identical parameter gradients
+
+
+def test_cell_out_rejects_cpu_and_bad_shape(pkg):
+    with pytest.raises(RuntimeError):
+        pkg.cell_out(torch.randn(1, 4, 8, 64))
+    with pytest.raises(RuntimeError):
+        pkg.cell_out(torch.randn(1, 3, 8, 48, device="cuda:0"))  # D = 48 unsupported
+
+
+# ---------------------------------------------------------------------------------------------
+class _Norm(torch.nn.Module):
+    def __init__(self, H):
+        super().__init__()
+        self.weight = torch.nn.Parameter(0.1 * torch.randn(H))
+        self.bias = torch.nn.Parameter(0.1 * torch.randn(H))
+        self.eps = 1e-6
+
+    @property
+    def weight_proxy(self):
+        return 1.0 + self.weight
+
+
+class _Conv(torch.nn.Conv2d):
+    seqlens = None
+
+
+class _Cell(torch.nn.Module):
+    def __init__(self, H, NH):
+        super().__init__()
+        self.dim, self.num_heads, self.gate_soft_cap = H, NH, 15.0
+        self.use_autocast, self.autocast_dtype = True, torch.float16
+        self.ifgate = torch.nn.Linear(3 * H, 2 * NH)
+        self.outnorm = _Norm(H)
+        with torch.no_grad():
+            self.ifgate.bias[:NH] = -2.0
+            self.ifgate.bias[NH:] = torch.linspace(3.0, 6.0, NH)
+
+
+class _Layer(torch.nn.Module):
+    """Attribute-compatible stand-in for ViLLayer (vision_lstm2.py:218-290), test-local."""
+
+    def __init__(self, dim, NH, direction):
+        super().__init__()
+        inner = 2 * dim
+        self.direction = direction
+        self.proj_up = torch.nn.Linear(dim, 2 * inner)
+        self.conv = _Conv(inner, inner, 3, padding=1, groups=inner)
+        self.qk_proj = torch.nn.Linear(inner, 2 * inner)
+        self.v_proj = torch.nn.Linear(inner, inner)
+        self.mlstm_cell = _Cell(inner, NH)
+        self.learnable_skip = torch.nn.Parameter(1.0 + 0.1 * torch.randn(inner))
+        self.proj_down = torch.nn.Linear(inner, dim)
+
+
+def _reference_branch(pkg, layer, x, reverse):
+    """The composition the reference runs (flip, conv, cell with group_norm, skip, flip back), plain torch +
+    the already parity-tested causal kernel."""
+    if reverse:
+        x = x.flip(dims=[1])
+    B, S, _ = x.shape
+    x_qk, x_v = torch.chunk(layer.proj_up(x), 2, dim=-1)
+    hh = int(S ** 0.5)
+    img = x_qk.reshape(B, hh, hh, -1).permute(0, 3, 1, 2)
+    x_act = F.silu(layer.conv(img).permute(0, 2, 3, 1).reshape(B, S, -1))
+    q, k = torch.chunk(layer.qk_proj(x_act), 2, dim=-1)
+    v = layer.v_proj(x_v)
+    cell = layer.mlstm_cell
+    NH = cell.num_heads
+    pre = cell.ifgate(torch.cat([q, k, v], -1))
+    pre = 15.0 * torch.tanh(pre / 15.0)
+    i, f = (t.transpose(-1, -2) for t in torch.chunk(pre, 2, -1))
+    qh, kh, vh = (t.view(B, S, NH, -1).transpose(1, 2).to(torch.float16) for t in (q, k, v))
+    i, f = i.to(torch.float16), f.to(torch.float16)
+    pad = (-S) % 64
+    if pad:
+        qh, kh, vh = (F.pad(t, (0, 0, 0, pad)) for t in (qh, kh, vh))
+        i, f = F.pad(i, (0, pad)), F.pad(f, (0, pad))
+    h = pkg.mlstm_chunkwise__b200(q=qh, k=kh, v=vh, i=i, f=f, chunk_size=64, eps=1e-6)[:, :, :S].to(x.dtype)
+    D = h.shape[-1]
+    g = F.group_norm(h.transpose(1, 2).reshape(B * S, NH * D), NH, cell.outnorm.weight_proxy, cell.outnorm.bias, 1e-6)
+    y = g.view(B, S, NH * D) + layer.learnable_skip * x_act
+    out = layer.proj_down(y)
+    return out.flip(dims=[1]) if reverse else out
+
+
+class _Dir:
+    def __init__(self, name):
+        self.name = name
+
+
+@pytest.mark.parametrize("S", [256, 100])  # 100 -> padded to 128 like the model's smallest stage
+@pytest.mark.parametrize("reverse", [False, True])
+def test_flip_free_branch_matches_reference_composition(pkg, S, reverse):
+    torch.manual_seed(5)
+    dev = torch.device("cuda:0")
+    dim, NH, B = 128, 4, 2  # inner 256, D = 64
+    layer = _Layer(dim, NH, _Dir("ROWWISE_FROM_BOT_RIGHT" if reverse else "ROWWISE_FROM_TOP_LEFT")).to(dev)
+    x = torch.randn(B, S, dim, device=dev)
+    dout = torch.randn(B, S, dim, device=dev)
+
+    def run(fn):
+        layer.zero_grad()
+        xi = x.clone().requires_grad_(True)
+        out = fn(xi)
+        out.backward(dout)
+        grads = {n: p.grad.clone() for n, p in layer.named_parameters()}
+        return out.detach(), xi.grad.clone(), grads
+
+    o_ref, dx_ref, g_ref = run(lambda xi: _reference_branch(pkg, layer, xi, reverse))
+    o_new, dx_new, g_new = run(lambda xi: pkg.mlstm_branch_b200(layer, xi))
+    # both sides run the same fp16 kernel arithmetic; what differs is summation order and one 16-bit rounding
+    assert rel(o_new, o_ref) < 5e-3, rel(o_new, o_ref)
+    assert rel(dx_new, dx_ref) < 2e-2, rel(dx_new, dx_ref)
+    for n in g_ref:
+        assert rel(g_new[n], g_ref[n]) < 2e-2, (n, rel(g_new[n], g_ref[n]))

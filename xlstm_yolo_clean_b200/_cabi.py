@@ -25,6 +25,9 @@ EXPORTS = (
     "mlstm_b200_last_launch_count",
     "mlstm_b200_debug_set_clock_buffer",
     "mlstm_b200_debug_set_bw_variant",
+    "mlstm_b200_cellout_workspace_bytes",
+    "mlstm_b200_cellout_fw",
+    "mlstm_b200_cellout_bw",
 )
 
 
@@ -68,6 +71,25 @@ class BwArgs(C.Structure):
     ]
 
 
+class CellOutArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("NH", C.c_int32), ("S", C.c_int32), ("D", C.c_int32),
+        ("h_dtype", C.c_int32), ("x_dtype", C.c_int32), ("y_dtype", C.c_int32),
+        ("eps", C.c_float),
+        ("h", Tensor), ("x", Tensor), ("y", Tensor),
+        ("weight", C.c_void_p), ("bias", C.c_void_p), ("skip", C.c_void_p),
+    ]
+
+
+class CellOutBwArgs(C.Structure):
+    _fields_ = [
+        ("fw", CellOutArgs),
+        ("dy", Tensor), ("dh", Tensor), ("dx", Tensor),
+        ("dweight", C.c_void_p), ("dbias", C.c_void_p), ("dskip", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 _lib = None
 
 
@@ -103,6 +125,12 @@ def load_library(path: str | None = None):
     lib.mlstm_b200_debug_set_clock_buffer.argtypes = [C.c_void_p]
     lib.mlstm_b200_debug_set_bw_variant.restype = C.c_int
     lib.mlstm_b200_debug_set_bw_variant.argtypes = [C.c_int]
+    lib.mlstm_b200_cellout_workspace_bytes.restype = C.c_size_t
+    lib.mlstm_b200_cellout_workspace_bytes.argtypes = [C.POINTER(CellOutArgs)]
+    lib.mlstm_b200_cellout_fw.restype = C.c_int
+    lib.mlstm_b200_cellout_fw.argtypes = [C.POINTER(CellOutArgs), C.c_void_p]
+    lib.mlstm_b200_cellout_bw.restype = C.c_int
+    lib.mlstm_b200_cellout_bw.argtypes = [C.POINTER(CellOutBwArgs), C.c_void_p]
     v = lib.mlstm_b200_abi_version()
     if v != ABI_VERSION:
         raise RuntimeError(f"ABI mismatch: library {v}, binding {ABI_VERSION}")

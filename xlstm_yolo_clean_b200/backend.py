@@ -323,13 +323,17 @@ def register(name: str = KERNEL_NAME) -> str:
 
 
 def patch_model(model: torch.nn.Module, name: str = KERNEL_NAME, mode: str = "train_with_padding",
-                siging: bool = False) -> int:
+                siging: bool = False, fused: bool = False) -> int:
     """Point ``gpu_backend`` of every MatrixLSTMCell (vision_lstm2.py:685-697) at the B200 kernel.
 
     ``siging=True`` selects the sigmoid-input-gate variant, i.e. the same function the reference's
     CUDA default (``chunkwise--triton_xl_chunk_siging``) computes, so released weights keep their meaning;
     the default is the exp-gate / max-state path the reference runs on CPU (SURVEY.md finding 6).
-    Returns the number of cells patched.
+    ``fused=True`` additionally rebinds ``ViLLayer.mlstm_branch`` (vision_lstm2.py:292-312) to
+    ``vil.mlstm_branch_b200``: same parameters and function, but the cell's output stage (MultiHeadLayerNorm +
+    relayout + learnable skip) runs as one fused CUDA pass each way, the bottom-right direction uses the
+    kernel's anti-causal scan instead of two ``x.flip`` copies, and q/k/v are consumed as strided views
+    (SURVEY.md section 8(f) #2, #3).  Returns the number of cells patched.
     """
     from mlstm_kernels.torch.backend_module import mLSTMBackend, mLSTMBackendConfig
 
@@ -341,4 +345,16 @@ def patch_model(model: torch.nn.Module, name: str = KERNEL_NAME, mode: str = "tr
                 chunkwise_kernel=full, sequence_kernel="native_sequence__native", step_kernel="native", mode=mode,
                 return_last_states=False, chunk_size=64, eps=1e-6, autocast_kernel_dtype="bfloat16"))
             n += 1
+    if fused:
+        import types
+
+        from . import vil
+
+        for mod in model.modules():
+            cell = getattr(mod, "mlstm_cell", None)
+            if cell is None or not all(hasattr(mod, a) for a in ("proj_up", "qk_proj", "v_proj", "learnable_skip", "proj_down")):
+                continue
+            if not vil.cellout_supported(cell.num_heads, cell.dim // cell.num_heads):
+                continue
+            mod.mlstm_branch = types.MethodType(lambda self, x, _s=siging: vil.mlstm_branch_b200(self, x, siging=_s), mod)
     return n

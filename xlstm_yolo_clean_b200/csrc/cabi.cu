@@ -175,4 +175,32 @@ int mlstm_b200_chunkwise_bw(const mlstm_b200_bw_args* a, void* stream) {
   return tc ? tensor_bw(*a, (cudaStream_t)stream) : exact_bw(*a, (cudaStream_t)stream);
 }
 
+size_t mlstm_b200_cellout_workspace_bytes(const mlstm_b200_cellout_args* a) {
+  if (!a) return 0;
+  size_t n = cellout_workspace_bytes(*a);
+  return n < 256 ? 256 : n;
+}
+
+int mlstm_b200_cellout_fw(const mlstm_b200_cellout_args* a, void* stream) {
+  g_err[0] = 0;
+  g_launches = 0;
+  if (!a) {
+    set_error("args is NULL");
+    return MLSTM_B200_EINVAL;
+  }
+  if (int e = require_device()) return e;
+  return cellout_fw(*a, (cudaStream_t)stream);
+}
+
+int mlstm_b200_cellout_bw(const mlstm_b200_cellout_bw_args* a, void* stream) {
+  g_err[0] = 0;
+  g_launches = 0;
+  if (!a) {
+    set_error("args is NULL");
+    return MLSTM_B200_EINVAL;
+  }
+  if (int e = require_device()) return e;
+  return cellout_bw(*a, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -1,0 +1,369 @@
+// The mLSTM cell's output stage, fused: MultiHeadLayerNorm over every (token, head) group of h, the
+// (B,NH,S,D) -> (B,S,NH*D) relayout, and ViLLayer's learnable skip, in one pass over HBM each way.
+//
+//   y[b,s,c] = (h[b,hd,s,d] - mean) * rstd * weight[c] + bias[c] + skip[c] * x[b,s,c],   c = hd*D + d
+//
+// Reference (what this replaces, paths relative to the reference root):
+//   MultiHeadLayerNorm.forward        ultralytics/nn/modules/vision_lstm/vision_lstm2.py:928-944
+//       (transpose -> reshape copy -> F.group_norm(num_groups=NH) -> view -> transpose)
+//   MatrixLSTMCell.forward tail       vision_lstm2.py:749-751  (h.to(dtype), outnorm, transpose + reshape copy)
+//   ViLLayer.mlstm_branch skip add    vision_lstm2.py:306      (h + learnable_skip * x_qk_conv_act)
+// and their autograd backward (native_group_norm_backward + the copies), SURVEY.md section 8(f) #3.
+//
+// HBM-bound elementwise + small-group reduction work: no tensor cores.  One warp covers 128 consecutive
+// channels of one token row (4 channels per lane: 8-byte loads for 16-bit types), so x / y / dy / dx move
+// as fully coalesced 256-byte warp transactions and every h / dh access is one whole head row.  Group
+// statistics are xor-shuffle reductions over the D/4 lanes of a head; the per-channel parameter gradients
+// stay in registers across a persistent row loop and are reduced deterministically in two stages
+// (CTA partials in the caller's workspace, then one small kernel) -- no atomics.
+#include "common.cuh"
+
+namespace mlstm {
+namespace {
+
+constexpr int kRowsInFlight = 4;  // independent rows per warp per iteration (memory-level parallelism)
+constexpr int kMaxWarps = 16;
+
+struct CellP {
+  int B, NH, S, D, H, W, lpg;  // H = NH*D channels, W = H/128 warps per token row, lpg = D/4 lanes per head
+  float eps, inv_d;
+  const void *h, *x, *dy;
+  void *y, *dh, *dx;
+  int64_t hs[3], xs[2], ys[2], dys[2], dhs[3], dxs[2];
+  const float *weight, *bias, *skip;
+  float* partial;  // [gridDim.x][3][H]
+};
+
+template <typename T> __device__ __forceinline__ void load4(const T* p, float (&o)[4]);
+template <> __device__ __forceinline__ void load4<float>(const float* p, float (&o)[4]) {
+  const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+  o[0] = v.x, o[1] = v.y, o[2] = v.z, o[3] = v.w;
+}
+template <> __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float (&o)[4]) {
+  const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
+  o[0] = a.x, o[1] = a.y, o[2] = b.x, o[3] = b.y;
+}
+template <> __device__ __forceinline__ void load4<__half>(const __half* p, float (&o)[4]) {
+  const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+  o[0] = a.x, o[1] = a.y, o[2] = b.x, o[3] = b.y;
+}
+template <typename T> __device__ __forceinline__ void store4(T* p, const float (&o)[4]);
+template <> __device__ __forceinline__ void store4<float>(float* p, const float (&o)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+}
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, const float (&o)[4]) {
+  uint2 v;
+  *reinterpret_cast<__nv_bfloat162*>(&v.x) = __floats2bfloat162_rn(o[0], o[1]);
+  *reinterpret_cast<__nv_bfloat162*>(&v.y) = __floats2bfloat162_rn(o[2], o[3]);
+  *reinterpret_cast<uint2*>(p) = v;
+}
+template <> __device__ __forceinline__ void store4<__half>(__half* p, const float (&o)[4]) {
+  uint2 v;
+  *reinterpret_cast<__half2*>(&v.x) = __floats2half2_rn(o[0], o[1]);
+  *reinterpret_cast<__half2*>(&v.y) = __floats2half2_rn(o[2], o[3]);
+  *reinterpret_cast<uint2*>(p) = v;
+}
+
+// sum over the lpg lanes that share a head (lpg is a power of two <= 32, groups are lane-aligned)
+__device__ __forceinline__ float group_sum(float v, int lpg) {
+  for (int o = lpg >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// mean / rstd of one head row held 4 elements per lane (two-pass in registers, biased variance as
+// F.group_norm: vision_lstm2.py:935-941)
+__device__ __forceinline__ void group_stats(const float (&hv)[4], int lpg, float inv_d, float eps, float& mean, float& rstd) {
+  mean = group_sum(hv[0] + hv[1] + hv[2] + hv[3], lpg) * inv_d;
+  float q = 0.f;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) q += (hv[e] - mean) * (hv[e] - mean);
+  rstd = rsqrtf(group_sum(q, lpg) * inv_d + eps);
+}
+
+template <typename TH, typename TX>
+__global__ void __launch_bounds__(kMaxWarps * 32, 1) k_cellout_fw(const CellP p) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slot = warp % p.W, r = warp / p.W, R = (blockDim.x >> 5) / p.W;
+  const int c0 = slot * 128 + lane * 4, head = c0 / p.D, d0 = c0 % p.D;
+  float w[4], b[4], sk[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    w[e] = p.weight ? p.weight[c0 + e] : 1.f;
+    b[e] = p.bias ? p.bias[c0 + e] : 0.f;
+    sk[e] = p.skip ? p.skip[c0 + e] : 0.f;
+  }
+  const TH* hp = reinterpret_cast<const TH*>(p.h) + head * p.hs[1] + d0;
+  const TX* xp = reinterpret_cast<const TX*>(p.x);
+  TX* yp = reinterpret_cast<TX*>(p.y);
+  const int64_t rows = (int64_t)p.B * p.S, step = (int64_t)gridDim.x * R;
+  for (int64_t row0 = (int64_t)blockIdx.x * R + r; row0 < rows; row0 += step * kRowsInFlight) {
+    float hv[kRowsInFlight][4], xv[kRowsInFlight][4];
+    int64_t yoff[kRowsInFlight];
+#pragma unroll
+    for (int u = 0; u < kRowsInFlight; ++u) {
+      const int64_t row = row0 + u * step;
+      yoff[u] = -1;
+      if (row < rows) {
+        const int64_t bi = row / p.S, si = row - bi * p.S;
+        load4<TH>(hp + bi * p.hs[0] + si * p.hs[2], hv[u]);
+        if (xp) load4<TX>(xp + bi * p.xs[0] + si * p.xs[1] + c0, xv[u]);
+        yoff[u] = bi * p.ys[0] + si * p.ys[1] + c0;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) hv[u][e] = 0.f;
+      }
+      if (!xp || row >= rows) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) xv[u][e] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kRowsInFlight; ++u) {
+      float mean, rstd, o[4];
+      group_stats(hv[u], p.lpg, p.inv_d, p.eps, mean, rstd);  // all lanes shuffle, valid row or not
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = (hv[u][e] - mean) * rstd * w[e] + b[e] + sk[e] * xv[u][e];
+      if (yoff[u] >= 0) store4<TX>(yp + yoff[u], o);
+    }
+  }
+}
+
+template <typename TH, typename TX>
+__global__ void __launch_bounds__(kMaxWarps * 32, 1) k_cellout_bw(const CellP p) {
+  __shared__ float red[3][kMaxWarps][128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slot = warp % p.W, r = warp / p.W, R = (blockDim.x >> 5) / p.W;
+  const int c0 = slot * 128 + lane * 4, head = c0 / p.D, d0 = c0 % p.D;
+  float w[4], sk[4], aw[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f}, as[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    w[e] = p.weight ? p.weight[c0 + e] : 1.f;
+    sk[e] = p.skip ? p.skip[c0 + e] : 0.f;
+  }
+  const TH* hp = reinterpret_cast<const TH*>(p.h) + head * p.hs[1] + d0;
+  TH* dhp = reinterpret_cast<TH*>(p.dh) + head * p.dhs[1] + d0;
+  const TX* xp = reinterpret_cast<const TX*>(p.x);
+  const TX* dyp = reinterpret_cast<const TX*>(p.dy);
+  TX* dxp = reinterpret_cast<TX*>(p.dx);
+  const int64_t rows = (int64_t)p.B * p.S, step = (int64_t)gridDim.x * R;
+  for (int64_t row0 = (int64_t)blockIdx.x * R + r; row0 < rows; row0 += step * kRowsInFlight) {
+    float hv[kRowsInFlight][4], xv[kRowsInFlight][4], gv[kRowsInFlight][4];
+    int64_t bi_[kRowsInFlight], si_[kRowsInFlight];
+#pragma unroll
+    for (int u = 0; u < kRowsInFlight; ++u) {
+      const int64_t row = row0 + u * step;
+      bi_[u] = -1, si_[u] = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) hv[u][e] = xv[u][e] = gv[u][e] = 0.f;
+      if (row < rows) {
+        const int64_t bi = row / p.S, si = row - bi * p.S;
+        bi_[u] = bi, si_[u] = si;
+        load4<TH>(hp + bi * p.hs[0] + si * p.hs[2], hv[u]);
+        load4<TX>(dyp + bi * p.dys[0] + si * p.dys[1] + c0, gv[u]);
+        if (xp) load4<TX>(xp + bi * p.xs[0] + si * p.xs[1] + c0, xv[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kRowsInFlight; ++u) {
+      float mean, rstd, xh[4], g[4], o[4];
+      group_stats(hv[u], p.lpg, p.inv_d, p.eps, mean, rstd);
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        xh[e] = (hv[u][e] - mean) * rstd;
+        g[e] = gv[u][e] * w[e];
+        s1 += g[e];
+        s2 += g[e] * xh[e];
+        aw[e] += gv[u][e] * xh[e];  // zero rows contribute zero
+        ab[e] += gv[u][e];
+        as[e] += gv[u][e] * xv[u][e];
+      }
+      s1 = group_sum(s1, p.lpg) * p.inv_d;
+      s2 = group_sum(s2, p.lpg) * p.inv_d;
+      if (bi_[u] >= 0) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = rstd * (g[e] - s1 - xh[e] * s2);
+        store4<TH>(dhp + bi_[u] * p.dhs[0] + si_[u] * p.dhs[2], o);
+        if (dxp) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] = gv[u][e] * sk[e];
+          store4<TX>(dxp + bi_[u] * p.dxs[0] + si_[u] * p.dxs[1] + c0, o);
+        }
+      }
+    }
+  }
+  // stage 1 of the parameter-gradient reduction: over the R row-warps of this CTA
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    red[0][warp][lane * 4 + e] = aw[e];
+    red[1][warp][lane * 4 + e] = ab[e];
+    red[2][warp][lane * 4 + e] = as[e];
+  }
+  __syncthreads();
+  if (r == 0) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int rr = 0; rr < R; ++rr) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[e] += red[q][rr * p.W + slot][lane * 4 + e];
+      }
+      store4<float>(p.partial + ((int64_t)blockIdx.x * 3 + q) * p.H + c0, acc);
+    }
+  }
+}
+
+// stage 2: over CTAs, in a fixed order
+__global__ void k_cellout_reduce(const float* __restrict__ partial, int n_cta, int H, float* dweight, float* dbias, float* dskip) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 3 * H) return;
+  const int q = idx / H, c = idx - q * H;
+  float* out = q == 0 ? dweight : q == 1 ? dbias : dskip;
+  if (!out) return;
+  float acc = 0.f;
+  for (int i = 0; i < n_cta; ++i) acc += partial[((int64_t)i * 3 + q) * H + c];
+  out[c] = acc;
+}
+
+int grid_ctas() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return 2 * sms;  // two short CTAs per SM's worth of rows: evens out the tail without extra partials
+}
+
+bool aligned(const void* p, size_t a) { return ((uintptr_t)p % a) == 0; }
+
+int fill(const mlstm_b200_cellout_args& a, CellP& p) {
+  if (a.B <= 0 || a.NH <= 0 || a.S <= 0 || a.D <= 0) {
+    set_error("cellout: bad shape B=%d NH=%d S=%d D=%d", a.B, a.NH, a.S, a.D);
+    return MLSTM_B200_EINVAL;
+  }
+  const int H = a.NH * a.D;
+  if ((a.D != 32 && a.D != 64 && a.D != 128) || H % 128 != 0 || H / 128 > kMaxWarps) {
+    set_error("cellout: needs D in {32,64,128} and NH*D a multiple of 128 (got D=%d NH=%d)", a.D, a.NH);
+    return MLSTM_B200_EUNSUPPORTED;
+  }
+  if (!a.h.ptr || a.h.stride[3] != 1) {
+    set_error("cellout: h is NULL or its innermost stride is not 1");
+    return MLSTM_B200_EINVAL;
+  }
+  if (a.x.ptr && (!a.skip || a.x.stride[2] != 1)) {
+    set_error("cellout: x needs a skip vector and a unit innermost stride");
+    return MLSTM_B200_EINVAL;
+  }
+  p.B = a.B, p.NH = a.NH, p.S = a.S, p.D = a.D, p.H = H, p.W = H / 128, p.lpg = a.D / 4;
+  p.eps = a.eps, p.inv_d = 1.f / (float)a.D;
+  p.h = a.h.ptr, p.x = a.x.ptr;
+  for (int i = 0; i < 3; ++i) p.hs[i] = a.h.stride[i];
+  for (int i = 0; i < 2; ++i) p.xs[i] = a.x.stride[i];
+  p.weight = a.weight, p.bias = a.bias, p.skip = a.x.ptr ? a.skip : nullptr;
+  return 0;
+}
+
+bool vec_ok(const mlstm_b200_tensor& t, int nstride, int dtype) {
+  const size_t bytes = dtype == MLSTM_B200_F32 ? 16 : 8;
+  if (!aligned(t.ptr, bytes)) return false;
+  for (int i = 0; i < nstride; ++i)
+    if (t.stride[i] % 4) return false;
+  return true;
+}
+
+template <typename F> int dispatch2(int th, int tx, F&& f) {
+  // (h dtype, x/y dtype) pairs; 16-bit h is what the mLSTM kernels emit, fp32 h is the exact family's
+#define MLSTM_CELL_CASE(A, TA, Bv, TB) \
+  if (th == A && tx == Bv) return f(TA{}, TB{});
+  MLSTM_CELL_CASE(MLSTM_B200_BF16, __nv_bfloat16, MLSTM_B200_F16, __half)
+  MLSTM_CELL_CASE(MLSTM_B200_BF16, __nv_bfloat16, MLSTM_B200_BF16, __nv_bfloat16)
+  MLSTM_CELL_CASE(MLSTM_B200_BF16, __nv_bfloat16, MLSTM_B200_F32, float)
+  MLSTM_CELL_CASE(MLSTM_B200_F16, __half, MLSTM_B200_F16, __half)
+  MLSTM_CELL_CASE(MLSTM_B200_F16, __half, MLSTM_B200_BF16, __nv_bfloat16)
+  MLSTM_CELL_CASE(MLSTM_B200_F16, __half, MLSTM_B200_F32, float)
+  MLSTM_CELL_CASE(MLSTM_B200_F32, float, MLSTM_B200_F16, __half)
+  MLSTM_CELL_CASE(MLSTM_B200_F32, float, MLSTM_B200_BF16, __nv_bfloat16)
+  MLSTM_CELL_CASE(MLSTM_B200_F32, float, MLSTM_B200_F32, float)
+#undef MLSTM_CELL_CASE
+  set_error("cellout: unknown dtype pair (%d, %d)", th, tx);
+  return MLSTM_B200_EINVAL;
+}
+
+int block_threads(const CellP& p) { return (kMaxWarps / p.W) * p.W * 32; }
+
+}  // namespace
+
+size_t cellout_workspace_bytes(const mlstm_b200_cellout_args& a) {
+  return (size_t)grid_ctas() * 3 * (size_t)a.NH * a.D * sizeof(float);
+}
+
+int cellout_fw(const mlstm_b200_cellout_args& a, cudaStream_t st) {
+  CellP p{};
+  if (int e = fill(a, p)) return e;
+  if (!a.y.ptr || a.y.stride[2] != 1) {
+    set_error("cellout: y is NULL or its innermost stride is not 1");
+    return MLSTM_B200_EINVAL;
+  }
+  if (a.x.ptr && a.x_dtype != a.y_dtype) {
+    set_error("cellout: x and y must have the same dtype");
+    return MLSTM_B200_EUNSUPPORTED;
+  }
+  if (!vec_ok(a.h, 3, a.h_dtype) || !vec_ok(a.y, 2, a.y_dtype) || (a.x.ptr && !vec_ok(a.x, 2, a.x_dtype))) {
+    set_error("cellout: tensors must be 8-byte (16-bit) / 16-byte (fp32) aligned with strides that are multiples of 4");
+    return MLSTM_B200_EUNSUPPORTED;
+  }
+  p.y = a.y.ptr;
+  for (int i = 0; i < 2; ++i) p.ys[i] = a.y.stride[i];
+  const int grid = grid_ctas(), block = block_threads(p);
+  int rc = dispatch2(a.h_dtype, a.y_dtype, [&](auto th, auto tx) {
+    k_cellout_fw<decltype(th), decltype(tx)><<<grid, block, 0, st>>>(p);
+    return 0;
+  });
+  if (rc) return rc;
+  count_launch(1);
+  MLSTM_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int cellout_bw(const mlstm_b200_cellout_bw_args& b, cudaStream_t st) {
+  const mlstm_b200_cellout_args& a = b.fw;
+  CellP p{};
+  if (int e = fill(a, p)) return e;
+  if (!b.dy.ptr || b.dy.stride[2] != 1 || !b.dh.ptr || b.dh.stride[3] != 1 || (b.dx.ptr && b.dx.stride[2] != 1)) {
+    set_error("cellout_bw: dy / dh are NULL or an innermost stride is not 1");
+    return MLSTM_B200_EINVAL;
+  }
+  if (a.x.ptr && a.x_dtype != a.y_dtype) {
+    set_error("cellout: x and y must have the same dtype");
+    return MLSTM_B200_EUNSUPPORTED;
+  }
+  if (!vec_ok(a.h, 3, a.h_dtype) || !vec_ok(b.dh, 3, a.h_dtype) || !vec_ok(b.dy, 2, a.y_dtype) ||
+      (a.x.ptr && !vec_ok(a.x, 2, a.x_dtype)) || (b.dx.ptr && !vec_ok(b.dx, 2, a.y_dtype))) {
+    set_error("cellout_bw: tensors must be 8-byte (16-bit) / 16-byte (fp32) aligned with strides that are multiples of 4");
+    return MLSTM_B200_EUNSUPPORTED;
+  }
+  const size_t need = cellout_workspace_bytes(a);
+  if (!b.workspace || b.workspace_bytes < need) {
+    set_error("cellout_bw: workspace too small: need %zu bytes, got %zu", need, b.workspace_bytes);
+    return MLSTM_B200_EWORKSPACE;
+  }
+  p.dy = b.dy.ptr, p.dh = b.dh.ptr, p.dx = b.dx.ptr;
+  p.partial = reinterpret_cast<float*>(b.workspace);
+  for (int i = 0; i < 2; ++i) p.dys[i] = b.dy.stride[i], p.dxs[i] = b.dx.stride[i];
+  for (int i = 0; i < 3; ++i) p.dhs[i] = b.dh.stride[i];
+  const int grid = grid_ctas(), block = block_threads(p);
+  int rc = dispatch2(a.h_dtype, a.y_dtype, [&](auto th, auto tx) {
+    k_cellout_bw<decltype(th), decltype(tx)><<<grid, block, 0, st>>>(p);
+    return 0;
+  });
+  if (rc) return rc;
+  MLSTM_CUDA_CHECK(cudaGetLastError());
+  k_cellout_reduce<<<(3 * p.H + 255) / 256, 256, 0, st>>>(p.partial, grid, p.H, b.dweight, b.dbias, b.dskip);
+  count_launch(2);
+  MLSTM_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace mlstm

@@ -162,4 +162,10 @@ int tensor_set_bw_variant(int variant);
 int tensor_fw(const mlstm_b200_fw_args& a, cudaStream_t st);
 int tensor_bw(const mlstm_b200_bw_args& a, cudaStream_t st);
 
+
+// cell output stage (cell_kernels.cu)
+size_t cellout_workspace_bytes(const mlstm_b200_cellout_args& a);
+int cellout_fw(const mlstm_b200_cellout_args& a, cudaStream_t st);
+int cellout_bw(const mlstm_b200_cellout_bw_args& a, cudaStream_t st);
+
 }  // namespace mlstm

@@ -1,0 +1,178 @@
+"""Callers either side of the hot path: the mLSTM branch of a ViLLayer with
+
+  * the cell's output stage fused -- MultiHeadLayerNorm + (B,NH,S,D)->(B,S,H) relayout + learnable skip in one
+    CUDA pass each way (C-ABI ``mlstm_b200_cellout_fw`` / ``_bw``) instead of group_norm + transposes + copies
+    (ultralytics/nn/modules/vision_lstm/vision_lstm2.py:749-751, 928-944, 306);
+  * the bottom-right scan direction without the two ``x.flip`` copies (vision_lstm2.py:292-294, 309-310): the
+    kernel's anti-causal scan (``reverse=True``) plus the depthwise 3x3 conv evaluated with its weights rotated
+    by 180 degrees, which is the same function because a flip of the row-major token sequence is a 180-degree
+    rotation of the image and every other op on the branch acts per token;
+  * the q/k/v/i/f views handed to the kernel as they are (BSHD-strided, no ``contiguous``).
+
+``patch_model(model, fused=True)`` (backend.py) rebinds ``ViLLayer.mlstm_branch`` of the reference model to
+``mlstm_branch_b200``; parameters, state-dict keys and the function computed are unchanged.
+PyTorch is used for the dense layers (cuBLAS / cuDNN serve them), device memory and autograd plumbing.
+There is no CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn.functional as F
+
+from . import _cabi
+from .backend import _DTYPES, _tensor, mlstm_chunkwise__b200, mlstm_siging_chunkwise__b200
+
+
+def cellout_supported(NH: int, D: int) -> bool:
+    return D in (32, 64, 128) and (NH * D) % 128 == 0 and NH * D <= 2048
+
+
+def _f32c(t):
+    return None if t is None else t.detach().to(torch.float32).contiguous()
+
+
+def _vec_ok(t: torch.Tensor) -> bool:
+    return t.stride(-1) == 1 and all(s % 4 == 0 for s in t.stride()[:-1]) and t.data_ptr() % 16 == 0
+
+
+class _CellOut(torch.autograd.Function):
+    """y = MultiHeadLayerNorm(h) [+ skip * x], h (B,NH,S,D) -> y (B,S,NH*D)."""
+
+    @staticmethod
+    def forward(ctx, h, weight, bias, skip, x, eps, out_dtype):
+        lib = _cabi.load_library()
+        if not h.is_cuda:
+            raise RuntimeError("cell_out: h is on the CPU; this backend has no CPU path")
+        B, NH, S, D = h.shape
+        h = h if _vec_ok(h) else h.contiguous()
+        if x is not None:
+            x = x if (x.dtype == out_dtype and _vec_ok(x)) else x.to(out_dtype).contiguous()
+        w32, b32, s32 = _f32c(weight), _f32c(bias), _f32c(skip)
+        with torch.cuda.device(h.device):
+            y = torch.empty(B, S, NH * D, dtype=out_dtype, device=h.device)
+            a = _cabi.CellOutArgs()
+            a.B, a.NH, a.S, a.D = B, NH, S, D
+            a.h_dtype, a.x_dtype, a.y_dtype = _DTYPES[h.dtype], _DTYPES[out_dtype], _DTYPES[out_dtype]
+            a.eps = float(eps)
+            a.h, a.x, a.y = _tensor(h), _tensor(x), _tensor(y)
+            a.weight = None if w32 is None else w32.data_ptr()
+            a.bias = None if b32 is None else b32.data_ptr()
+            a.skip = None if s32 is None else s32.data_ptr()
+            st = lib.mlstm_b200_cellout_fw(C.byref(a), C.c_void_p(torch.cuda.current_stream(h.device).cuda_stream))
+            _cabi.check(st, "mlstm_b200_cellout_fw")
+        ctx.save_for_backward(h, x, weight, bias, skip)
+        ctx.eps, ctx.out_dtype = float(eps), out_dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _cabi.load_library()
+        h, x, weight, bias, skip = ctx.saved_tensors
+        B, NH, S, D = h.shape
+        dy = dy if (dy.dtype == ctx.out_dtype and _vec_ok(dy)) else dy.to(ctx.out_dtype).contiguous()
+        w32, s32 = _f32c(weight), _f32c(skip)
+        dev = h.device
+        with torch.cuda.device(dev):
+            dh = torch.empty(B, NH, S, D, dtype=h.dtype, device=dev)
+            dx = torch.empty_like(dy) if (x is not None and ctx.needs_input_grad[4]) else None
+            dpar = torch.empty(3, NH * D, dtype=torch.float32, device=dev)
+            b = _cabi.CellOutBwArgs()
+            a = b.fw
+            a.B, a.NH, a.S, a.D = B, NH, S, D
+            a.h_dtype, a.x_dtype, a.y_dtype = _DTYPES[h.dtype], _DTYPES[ctx.out_dtype], _DTYPES[ctx.out_dtype]
+            a.eps = ctx.eps
+            a.h, a.x = _tensor(h), _tensor(x)
+            a.weight = None if w32 is None else w32.data_ptr()
+            a.skip = None if s32 is None else s32.data_ptr()
+            b.dy, b.dh, b.dx = _tensor(dy), _tensor(dh), _tensor(dx)
+            b.dweight, b.dbias, b.dskip = dpar[0].data_ptr(), dpar[1].data_ptr(), dpar[2].data_ptr()
+            ws_bytes = lib.mlstm_b200_cellout_workspace_bytes(C.byref(a))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            b.workspace, b.workspace_bytes = ws.data_ptr(), ws_bytes
+            st = lib.mlstm_b200_cellout_bw(C.byref(b), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            _cabi.check(st, "mlstm_b200_cellout_bw")
+        return (dh,
+                None if weight is None else dpar[0].to(weight.dtype),
+                None if bias is None else dpar[1].to(bias.dtype),
+                None if skip is None else dpar[2].to(skip.dtype),
+                dx, None, None)
+
+
+def cell_out(h, weight=None, bias=None, skip=None, x=None, eps=1e-6, out_dtype=None):
+    """Fused MultiHeadLayerNorm (+ skip): see the module docstring.  ``weight`` is the effective scale
+    (the reference's ``weight_proxy`` = 1 + weight, vision_lstm2.py:900-907)."""
+    out_dtype = out_dtype or (x.dtype if x is not None else h.dtype)
+    return _CellOut.apply(h, weight, bias, skip, x, eps, out_dtype)
+
+
+def _is_reverse(layer) -> bool:
+    d = getattr(layer, "direction", None)
+    name = getattr(d, "name", None) or getattr(d, "value", None) or str(d)
+    return "BOT_RIGHT" in str(name).upper()
+
+
+def _seq_conv(conv, x, rotate: bool):
+    """SequenceConv2d (vision_lstm_util.py:96-114) on (B, S, C) tokens; ``rotate`` evaluates it with the
+    kernel rotated by 180 degrees = conv(flip(x)) flipped back."""
+    B, S, Cc = x.shape
+    seqlens = getattr(conv, "seqlens", None)
+    hh = int(seqlens[0]) if seqlens is not None else int(round(S ** 0.5))
+    w = conv.weight.flip(-1, -2) if rotate else conv.weight
+    img = x.view(B, hh, S // hh, Cc).permute(0, 3, 1, 2)
+    out = F.conv2d(img, w, conv.bias, conv.stride, conv.padding, conv.dilation, conv.groups)
+    return out.permute(0, 2, 3, 1).reshape(B, S, Cc)
+
+
+def mlstm_cell_b200(cell, q, k, v, reverse=False, skip=None, x_skip=None, siging=False, chunk_size=64, eps=1e-6):
+    """MatrixLSTMCell.forward (vision_lstm2.py:701-753) on the B200 kernels, output stage fused.
+
+    q, k, v (B, S, H) -> (B, S, H).  ``reverse`` runs the anti-causal scan; ``skip`` / ``x_skip`` add
+    ViLLayer's ``learnable_skip * x_qk_conv_act`` inside the same pass.  Kernel parameters are the ones the
+    reference's pad wrapper forces on every call: chunk 64, eps 1e-6, bf16 under CUDA autocast
+    (kernel_wrappers.py:214-217; SURVEY.md finding 3)."""
+    B, S, H = q.shape
+    if not q.is_cuda:
+        raise RuntimeError("mlstm_cell_b200: tensors are on the CPU; this backend has no CPU path")
+    NH = cell.num_heads
+    D = H // NH
+    if_preact = cell.ifgate(torch.cat([q, k, v], dim=-1))
+    capped = cell.gate_soft_cap * torch.tanh(if_preact / cell.gate_soft_cap)  # soft_cap, vision_lstm2.py:755-756
+    i_pre, f_pre = torch.chunk(capped, 2, dim=-1)
+    i, f = i_pre.transpose(-1, -2), f_pre.transpose(-1, -2)  # (B, NH, S) views
+    qh, kh, vh = (t.view(B, S, NH, D).transpose(1, 2) for t in (q, k, v))  # (B, NH, S, D) views, no copy
+    model_dtype = q.dtype
+    if cell.use_autocast:  # the reference casts on CUDA in train and eval alike (vision_lstm2.py:730-745)
+        qh, kh, vh, i, f = (t.to(cell.autocast_dtype) for t in (qh, kh, vh, i, f))
+    pad = (-S) % chunk_size
+    if pad:  # zero padding like wrap_chunkwise__pad_zeros (kernel_wrappers.py:227-247); the padded tokens must
+        # come LAST in scan order, i.e. at the front of memory for the anti-causal direction
+        pq = (0, 0, pad, 0) if reverse else (0, 0, 0, pad)
+        pg = (pad, 0) if reverse else (0, pad)
+        qh, kh, vh = (F.pad(t, pq) for t in (qh, kh, vh))
+        i, f = F.pad(i, pg), F.pad(f, pg)
+    fn = mlstm_siging_chunkwise__b200 if siging else mlstm_chunkwise__b200
+    h = fn(q=qh, k=kh, v=vh, i=i, f=f, chunk_size=chunk_size, eps=eps, autocast_kernel_dtype=torch.bfloat16,
+           reverse=reverse)
+    if pad:
+        h = h[:, :, pad:] if reverse else h[:, :, :S]
+    norm = cell.outnorm
+    out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else model_dtype
+    return cell_out(h, norm.weight_proxy, norm.bias, skip, x_skip, eps=norm.eps, out_dtype=out_dtype)
+
+
+def mlstm_branch_b200(layer, x, siging=False):
+    """ViLLayer.mlstm_branch (vision_lstm2.py:292-312) without flips and with the fused cell output."""
+    rev = _is_reverse(layer)
+    x_inner = layer.proj_up(x)
+    x_qk, x_v = torch.chunk(x_inner, 2, dim=-1)
+    if isinstance(layer.conv, torch.nn.Conv2d):
+        x_act = F.silu(_seq_conv(layer.conv, x_qk, rotate=rev))
+    else:
+        x_act = F.silu(layer.conv(x_qk))
+    qk = layer.qk_proj(x_act)
+    q, k = torch.chunk(qk, 2, dim=-1)
+    v = layer.v_proj(x_v)
+    y = mlstm_cell_b200(layer.mlstm_cell, q, k, v, reverse=rev, skip=layer.learnable_skip, x_skip=x_act, siging=siging)
+    return layer.proj_down(y)
