@@ -155,7 +155,8 @@ def _set_backend(model, name):
                 mode="train_with_padding", return_last_states=False, chunk_size=64, eps=1e-6,
                 autocast_kernel_dtype="bfloat16"))
         return len(cells)
-    return pkg.patch_model(model, siging="siging" in name, fused=name.endswith("_fused"))
+    return pkg.patch_model(model, siging="siging" in name, fused="_fused" in name,
+                           kernel_dtype="input" if name.endswith("_fp16") else "bfloat16")
 
 
 class _MlstmTimer:

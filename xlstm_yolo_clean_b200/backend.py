@@ -323,7 +323,7 @@ def register(name: str = KERNEL_NAME) -> str:
 
 
 def patch_model(model: torch.nn.Module, name: str = KERNEL_NAME, mode: str = "train_with_padding",
-                siging: bool = False, fused: bool = False) -> int:
+                siging: bool = False, fused: bool = False, kernel_dtype: str = "bfloat16") -> int:
     """Point ``gpu_backend`` of every MatrixLSTMCell (vision_lstm2.py:685-697) at the B200 kernel.
 
     ``siging=True`` selects the sigmoid-input-gate variant, i.e. the same function the reference's
@@ -356,5 +356,6 @@ def patch_model(model: torch.nn.Module, name: str = KERNEL_NAME, mode: str = "tr
                 continue
             if not vil.cellout_supported(cell.num_heads, cell.dim // cell.num_heads):
                 continue
-            mod.mlstm_branch = types.MethodType(lambda self, x, _s=siging: vil.mlstm_branch_b200(self, x, siging=_s), mod)
+            mod.mlstm_branch = types.MethodType(
+                lambda self, x, _s=siging, _k=kernel_dtype: vil.mlstm_branch_b200(self, x, siging=_s, kernel_dtype=_k), mod)
     return n

@@ -21,7 +21,13 @@
 namespace mlstm {
 namespace {
 
-constexpr int kRowsInFlight = 4;  // independent rows per warp per iteration (memory-level parallelism)
+#ifndef MLSTM_CELL_FW_ROWS
+#define MLSTM_CELL_FW_ROWS 4
+#endif
+#ifndef MLSTM_CELL_BW_ROWS
+#define MLSTM_CELL_BW_ROWS 4
+#endif
+constexpr int kFwRows = MLSTM_CELL_FW_ROWS, kBwRows = MLSTM_CELL_BW_ROWS;  // (halved for 32-bit operands)  // rows per warp per pipeline stage (two stages are in registers)
 constexpr int kMaxWarps = 16;
 
 struct CellP {
@@ -34,19 +40,27 @@ struct CellP {
   float* partial;  // [gridDim.x][3][H]
 };
 
-template <typename T> __device__ __forceinline__ void load4(const T* p, float (&o)[4]);
-template <> __device__ __forceinline__ void load4<float>(const float* p, float (&o)[4]) {
-  const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+// Four consecutive elements as they sit in memory; converted to fp32 only where they are consumed, so that the
+// software pipeline below really leaves the loads in flight (a conversion placed at the load would wait for it).
+template <typename T> struct Raw4 { using type = uint2; };
+template <> struct Raw4<float> { using type = float4; };
+template <typename T> __device__ __forceinline__ typename Raw4<T>::type ldraw(const T* p) {
+  return __ldg(reinterpret_cast<const typename Raw4<T>::type*>(p));
+}
+template <typename T> __device__ __forceinline__ typename Raw4<T>::type zraw();
+template <> __device__ __forceinline__ uint2 zraw<__nv_bfloat16>() { return make_uint2(0u, 0u); }
+template <> __device__ __forceinline__ uint2 zraw<__half>() { return make_uint2(0u, 0u); }
+template <> __device__ __forceinline__ float4 zraw<float>() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+template <typename T> __device__ __forceinline__ void cvt4(const typename Raw4<T>::type& v, float (&o)[4]);
+template <> __device__ __forceinline__ void cvt4<float>(const float4& v, float (&o)[4]) {
   o[0] = v.x, o[1] = v.y, o[2] = v.z, o[3] = v.w;
 }
-template <> __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float (&o)[4]) {
-  const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+template <> __device__ __forceinline__ void cvt4<__nv_bfloat16>(const uint2& v, float (&o)[4]) {
   const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x));
   const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
   o[0] = a.x, o[1] = a.y, o[2] = b.x, o[3] = b.y;
 }
-template <> __device__ __forceinline__ void load4<__half>(const __half* p, float (&o)[4]) {
-  const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+template <> __device__ __forceinline__ void cvt4<__half>(const uint2& v, float (&o)[4]) {
   const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
   const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
   o[0] = a.x, o[1] = a.y, o[2] = b.x, o[3] = b.y;
@@ -84,7 +98,31 @@ __device__ __forceinline__ void group_stats(const float (&hv)[4], int lpg, float
   rstd = rsqrtf(group_sum(q, lpg) * inv_d + eps);
 }
 
-template <typename TH, typename TX>
+// Walks the token rows row0, row0 + step, ... of one warp, keeping (batch, position) without a division per row.
+struct RowIt {
+  int64_t row, rows, step;
+  int bi, si, S, step_b, step_s;
+  __device__ __forceinline__ RowIt(int64_t row0, int64_t rows_, int64_t step_, int S_)
+      : row(row0), rows(rows_), step(step_), S(S_) {
+    bi = (int)(row0 / S_), si = (int)(row0 - (int64_t)bi * S_);
+    step_b = (int)(step_ / S_), step_s = (int)(step_ - (int64_t)step_b * S_);
+  }
+  __device__ __forceinline__ bool valid() const { return row < rows; }
+  __device__ __forceinline__ void next() {
+    row += step, bi += step_b, si += step_s;
+    if (si >= S) si -= S, ++bi;
+  }
+};
+
+template <typename TH, typename TX, int U> struct FwRegs {
+  typename Raw4<TH>::type hv[U];
+  typename Raw4<TX>::type xv[U];
+  int64_t yoff[U];  // < 0: no row
+};
+
+// Software-pipelined persistent loop: the loads of the next U rows are in flight while the current U rows are
+// normalised and stored (two register sets, ping-pong), so every warp keeps U*(h + x) loads outstanding.
+template <typename TH, typename TX, int U>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_cellout_fw(const CellP p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int slot = warp % p.W, r = warp / p.W, R = (blockDim.x >> 5) / p.W;
@@ -99,40 +137,52 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_cellout_fw(const CellP p)
   const TH* hp = reinterpret_cast<const TH*>(p.h) + head * p.hs[1] + d0;
   const TX* xp = reinterpret_cast<const TX*>(p.x);
   TX* yp = reinterpret_cast<TX*>(p.y);
-  const int64_t rows = (int64_t)p.B * p.S, step = (int64_t)gridDim.x * R;
-  for (int64_t row0 = (int64_t)blockIdx.x * R + r; row0 < rows; row0 += step * kRowsInFlight) {
-    float hv[kRowsInFlight][4], xv[kRowsInFlight][4];
-    int64_t yoff[kRowsInFlight];
+  RowIt it((int64_t)blockIdx.x * R + r, (int64_t)p.B * p.S, (int64_t)gridDim.x * R, p.S);
+
+  using Regs = FwRegs<TH, TX, U>;
+  auto load = [&](Regs& g) {
 #pragma unroll
-    for (int u = 0; u < kRowsInFlight; ++u) {
-      const int64_t row = row0 + u * step;
-      yoff[u] = -1;
-      if (row < rows) {
-        const int64_t bi = row / p.S, si = row - bi * p.S;
-        load4<TH>(hp + bi * p.hs[0] + si * p.hs[2], hv[u]);
-        if (xp) load4<TX>(xp + bi * p.xs[0] + si * p.xs[1] + c0, xv[u]);
-        yoff[u] = bi * p.ys[0] + si * p.ys[1] + c0;
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) hv[u][e] = 0.f;
+    for (int u = 0; u < U; ++u) {
+      g.yoff[u] = -1;
+      g.hv[u] = zraw<TH>(), g.xv[u] = zraw<TX>();
+      if (it.valid()) {
+        g.hv[u] = ldraw<TH>(hp + it.bi * p.hs[0] + it.si * p.hs[2]);
+        if (xp) g.xv[u] = ldraw<TX>(xp + it.bi * p.xs[0] + it.si * p.xs[1] + c0);
+        g.yoff[u] = it.bi * p.ys[0] + it.si * p.ys[1] + c0;
       }
-      if (!xp || row >= rows) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) xv[u][e] = 0.f;
-      }
+      it.next();
     }
+  };
+  auto process = [&](const Regs& g) {
 #pragma unroll
-    for (int u = 0; u < kRowsInFlight; ++u) {
-      float mean, rstd, o[4];
-      group_stats(hv[u], p.lpg, p.inv_d, p.eps, mean, rstd);  // all lanes shuffle, valid row or not
+    for (int u = 0; u < U; ++u) {
+      float mean, rstd, o[4], hv[4], xv[4];
+      cvt4<TH>(g.hv[u], hv);
+      cvt4<TX>(g.xv[u], xv);
+      group_stats(hv, p.lpg, p.inv_d, p.eps, mean, rstd);  // row validity is warp-uniform
 #pragma unroll
-      for (int e = 0; e < 4; ++e) o[e] = (hv[u][e] - mean) * rstd * w[e] + b[e] + sk[e] * xv[u][e];
-      if (yoff[u] >= 0) store4<TX>(yp + yoff[u], o);
+      for (int e = 0; e < 4; ++e) o[e] = (hv[e] - mean) * rstd * w[e] + b[e] + sk[e] * xv[e];
+      if (g.yoff[u] >= 0) store4<TX>(yp + g.yoff[u], o);
     }
+  };
+  Regs ga, gb;
+  load(ga);
+  while (ga.yoff[0] >= 0) {
+    load(gb);
+    process(ga);
+    if (gb.yoff[0] < 0) break;
+    load(ga);
+    process(gb);
   }
 }
 
-template <typename TH, typename TX>
+template <typename TH, typename TX, int U> struct BwRegs {
+  typename Raw4<TH>::type hv[U];
+  typename Raw4<TX>::type xv[U], gv[U];
+  int bi[U], si[U];  // bi < 0: no row
+};
+
+template <typename TH, typename TX, int U>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_cellout_bw(const CellP p) {
   __shared__ float red[3][kMaxWarps][128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -149,51 +199,65 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_cellout_bw(const CellP p)
   const TX* xp = reinterpret_cast<const TX*>(p.x);
   const TX* dyp = reinterpret_cast<const TX*>(p.dy);
   TX* dxp = reinterpret_cast<TX*>(p.dx);
-  const int64_t rows = (int64_t)p.B * p.S, step = (int64_t)gridDim.x * R;
-  for (int64_t row0 = (int64_t)blockIdx.x * R + r; row0 < rows; row0 += step * kRowsInFlight) {
-    float hv[kRowsInFlight][4], xv[kRowsInFlight][4], gv[kRowsInFlight][4];
-    int64_t bi_[kRowsInFlight], si_[kRowsInFlight];
+  RowIt it((int64_t)blockIdx.x * R + r, (int64_t)p.B * p.S, (int64_t)gridDim.x * R, p.S);
+
+  using Regs = BwRegs<TH, TX, U>;
+  auto load = [&](Regs& g) {
 #pragma unroll
-    for (int u = 0; u < kRowsInFlight; ++u) {
-      const int64_t row = row0 + u * step;
-      bi_[u] = -1, si_[u] = 0;
-#pragma unroll
-      for (int e = 0; e < 4; ++e) hv[u][e] = xv[u][e] = gv[u][e] = 0.f;
-      if (row < rows) {
-        const int64_t bi = row / p.S, si = row - bi * p.S;
-        bi_[u] = bi, si_[u] = si;
-        load4<TH>(hp + bi * p.hs[0] + si * p.hs[2], hv[u]);
-        load4<TX>(dyp + bi * p.dys[0] + si * p.dys[1] + c0, gv[u]);
-        if (xp) load4<TX>(xp + bi * p.xs[0] + si * p.xs[1] + c0, xv[u]);
+    for (int u = 0; u < U; ++u) {
+      g.bi[u] = -1, g.si[u] = 0;
+      g.hv[u] = zraw<TH>(), g.xv[u] = zraw<TX>(), g.gv[u] = zraw<TX>();
+      if (it.valid()) {
+        g.bi[u] = it.bi, g.si[u] = it.si;
+        g.hv[u] = ldraw<TH>(hp + it.bi * p.hs[0] + it.si * p.hs[2]);
+        g.gv[u] = ldraw<TX>(dyp + it.bi * p.dys[0] + it.si * p.dys[1] + c0);
+        if (xp) g.xv[u] = ldraw<TX>(xp + it.bi * p.xs[0] + it.si * p.xs[1] + c0);
       }
+      it.next();
     }
+  };
+  auto process = [&](const Regs& g) {
 #pragma unroll
-    for (int u = 0; u < kRowsInFlight; ++u) {
-      float mean, rstd, xh[4], g[4], o[4];
-      group_stats(hv[u], p.lpg, p.inv_d, p.eps, mean, rstd);
+    for (int u = 0; u < U; ++u) {
+      float mean, rstd, xh[4], gw[4], o[4], hv[4], xv[4], gv[4];
+      cvt4<TH>(g.hv[u], hv);
+      cvt4<TX>(g.xv[u], xv);
+      cvt4<TX>(g.gv[u], gv);
+      group_stats(hv, p.lpg, p.inv_d, p.eps, mean, rstd);
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        xh[e] = (hv[u][e] - mean) * rstd;
-        g[e] = gv[u][e] * w[e];
-        s1 += g[e];
-        s2 += g[e] * xh[e];
-        aw[e] += gv[u][e] * xh[e];  // zero rows contribute zero
-        ab[e] += gv[u][e];
-        as[e] += gv[u][e] * xv[u][e];
+        xh[e] = (hv[e] - mean) * rstd;
+        gw[e] = gv[e] * w[e];
+        s1 += gw[e];
+        s2 += gw[e] * xh[e];
+        aw[e] += gv[e] * xh[e];  // absent rows hold zeros
+        ab[e] += gv[e];
+        as[e] += gv[e] * xv[e];
       }
       s1 = group_sum(s1, p.lpg) * p.inv_d;
       s2 = group_sum(s2, p.lpg) * p.inv_d;
-      if (bi_[u] >= 0) {
+      if (g.bi[u] >= 0) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = rstd * (g[e] - s1 - xh[e] * s2);
-        store4<TH>(dhp + bi_[u] * p.dhs[0] + si_[u] * p.dhs[2], o);
+        for (int e = 0; e < 4; ++e) o[e] = rstd * (gw[e] - s1 - xh[e] * s2);
+        store4<TH>(dhp + g.bi[u] * p.dhs[0] + g.si[u] * p.dhs[2], o);
         if (dxp) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) o[e] = gv[u][e] * sk[e];
-          store4<TX>(dxp + bi_[u] * p.dxs[0] + si_[u] * p.dxs[1] + c0, o);
+          for (int e = 0; e < 4; ++e) o[e] = gv[e] * sk[e];
+          store4<TX>(dxp + g.bi[u] * p.dxs[0] + g.si[u] * p.dxs[1] + c0, o);
         }
       }
+    }
+  };
+  {
+    Regs ga, gb;
+    load(ga);
+    while (ga.bi[0] >= 0) {
+      load(gb);
+      process(ga);
+      if (gb.bi[0] < 0) break;
+      load(ga);
+      process(gb);
     }
   }
   // stage 1 of the parameter-gradient reduction: over the R row-warps of this CTA
@@ -318,7 +382,8 @@ int cellout_fw(const mlstm_b200_cellout_args& a, cudaStream_t st) {
   for (int i = 0; i < 2; ++i) p.ys[i] = a.y.stride[i];
   const int grid = grid_ctas(), block = block_threads(p);
   int rc = dispatch2(a.h_dtype, a.y_dtype, [&](auto th, auto tx) {
-    k_cellout_fw<decltype(th), decltype(tx)><<<grid, block, 0, st>>>(p);
+    constexpr int kRows = (sizeof(th) + sizeof(tx)) <= 4 ? kFwRows : kFwRows / 2;
+    k_cellout_fw<decltype(th), decltype(tx), kRows><<<grid, block, 0, st>>>(p);
     return 0;
   });
   if (rc) return rc;
@@ -355,7 +420,8 @@ int cellout_bw(const mlstm_b200_cellout_bw_args& b, cudaStream_t st) {
   for (int i = 0; i < 3; ++i) p.dhs[i] = b.dh.stride[i];
   const int grid = grid_ctas(), block = block_threads(p);
   int rc = dispatch2(a.h_dtype, a.y_dtype, [&](auto th, auto tx) {
-    k_cellout_bw<decltype(th), decltype(tx)><<<grid, block, 0, st>>>(p);
+    constexpr int kRows = (sizeof(th) + 2 * sizeof(tx)) <= 6 ? kBwRows : kBwRows / 2;  // register budget per pipeline stage
+    k_cellout_bw<decltype(th), decltype(tx), kRows><<<grid, block, 0, st>>>(p);
     return 0;
   });
   if (rc) return rc;

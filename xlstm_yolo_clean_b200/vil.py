@@ -125,19 +125,35 @@ def _seq_conv(conv, x, rotate: bool):
     return out.permute(0, 2, 3, 1).reshape(B, S, Cc)
 
 
-def mlstm_cell_b200(cell, q, k, v, reverse=False, skip=None, x_skip=None, siging=False, chunk_size=64, eps=1e-6):
+def _gate_preact(cell, q, k, v, qk=None):
+    """ifgate(cat[q, k, v]) (vision_lstm2.py:711-714).  When the caller still holds the fused qk_proj output
+    ``qk`` (B, S, 2H) whose halves q and k are, the (B, S, 3H) concatenation is never materialised: the product
+    splits into two GEMMs over tensors that already exist, accumulated inside the second one (addmm)."""
+    if qk is None:
+        return cell.ifgate(torch.cat([q, k, v], dim=-1))
+    B, S, H2 = qk.shape
+    W, b = cell.ifgate.weight, cell.ifgate.bias
+    pre_v = F.linear(v, W[:, H2:], b)
+    return torch.addmm(pre_v.reshape(B * S, -1), qk.reshape(B * S, H2), W[:, :H2].t()).view(B, S, -1)
+
+
+def mlstm_cell_b200(cell, q, k, v, reverse=False, skip=None, x_skip=None, siging=False, chunk_size=64, eps=1e-6,
+                    kernel_dtype="bfloat16", qk=None):
     """MatrixLSTMCell.forward (vision_lstm2.py:701-753) on the B200 kernels, output stage fused.
 
     q, k, v (B, S, H) -> (B, S, H).  ``reverse`` runs the anti-causal scan; ``skip`` / ``x_skip`` add
     ViLLayer's ``learnable_skip * x_qk_conv_act`` inside the same pass.  Kernel parameters are the ones the
     reference's pad wrapper forces on every call: chunk 64, eps 1e-6, bf16 under CUDA autocast
-    (kernel_wrappers.py:214-217; SURVEY.md finding 3)."""
+    (kernel_wrappers.py:214-217; SURVEY.md finding 3).  ``kernel_dtype="input"`` is an opt-in deviation: 16-bit
+    inputs go to the kernel as they are (fp16 under ultralytics' AMP) instead of being re-rounded to bf16, which
+    drops five cast passes forward and five backward; the result is closer to the fp32 function, not identical
+    to the reference's bf16 one."""
     B, S, H = q.shape
     if not q.is_cuda:
         raise RuntimeError("mlstm_cell_b200: tensors are on the CPU; this backend has no CPU path")
     NH = cell.num_heads
     D = H // NH
-    if_preact = cell.ifgate(torch.cat([q, k, v], dim=-1))
+    if_preact = _gate_preact(cell, q, k, v, qk)
     capped = cell.gate_soft_cap * torch.tanh(if_preact / cell.gate_soft_cap)  # soft_cap, vision_lstm2.py:755-756
     i_pre, f_pre = torch.chunk(capped, 2, dim=-1)
     i, f = i_pre.transpose(-1, -2), f_pre.transpose(-1, -2)  # (B, NH, S) views
@@ -153,8 +169,8 @@ def mlstm_cell_b200(cell, q, k, v, reverse=False, skip=None, x_skip=None, siging
         qh, kh, vh = (F.pad(t, pq) for t in (qh, kh, vh))
         i, f = F.pad(i, pg), F.pad(f, pg)
     fn = mlstm_siging_chunkwise__b200 if siging else mlstm_chunkwise__b200
-    h = fn(q=qh, k=kh, v=vh, i=i, f=f, chunk_size=chunk_size, eps=eps, autocast_kernel_dtype=torch.bfloat16,
-           reverse=reverse)
+    kdt = qh.dtype if (kernel_dtype == "input" and qh.dtype in (torch.float16, torch.bfloat16)) else torch.bfloat16
+    h = fn(q=qh, k=kh, v=vh, i=i, f=f, chunk_size=chunk_size, eps=eps, autocast_kernel_dtype=kdt, reverse=reverse)
     if pad:
         h = h[:, :, pad:] if reverse else h[:, :, :S]
     norm = cell.outnorm
@@ -162,7 +178,7 @@ def mlstm_cell_b200(cell, q, k, v, reverse=False, skip=None, x_skip=None, siging
     return cell_out(h, norm.weight_proxy, norm.bias, skip, x_skip, eps=norm.eps, out_dtype=out_dtype)
 
 
-def mlstm_branch_b200(layer, x, siging=False):
+def mlstm_branch_b200(layer, x, siging=False, kernel_dtype="bfloat16"):
     """ViLLayer.mlstm_branch (vision_lstm2.py:292-312) without flips and with the fused cell output."""
     rev = _is_reverse(layer)
     x_inner = layer.proj_up(x)
@@ -174,5 +190,6 @@ def mlstm_branch_b200(layer, x, siging=False):
     qk = layer.qk_proj(x_act)
     q, k = torch.chunk(qk, 2, dim=-1)
     v = layer.v_proj(x_v)
-    y = mlstm_cell_b200(layer.mlstm_cell, q, k, v, reverse=rev, skip=layer.learnable_skip, x_skip=x_act, siging=siging)
+    y = mlstm_cell_b200(layer.mlstm_cell, q, k, v, reverse=rev, skip=layer.learnable_skip, x_skip=x_act, siging=siging,
+                        kernel_dtype=kernel_dtype, qk=qk)
     return layer.proj_down(y)
