@@ -151,8 +151,11 @@ def mlstm_chunkwise_fw(q, k, v, i, f, c_initial=None, n_initial=None, m_initial=
 
 def mlstm_chunkwise_bw(q, k, v, i, f, n_out, m_out, dh, c_initial=None, n_initial=None, m_initial=None,
                        dc_last=None, qk_scale=None, chunk_size=64, eps=1e-6, impl=None, want_dc_initial=False,
-                       c_states=None, reverse=False, siging=False):
-    """C-ABI backward.  Returns dq, dk, dv, di, df, dc_initial-or-None (fp32)."""
+                       c_states=None, reverse=False, siging=False, out=None):
+    """C-ABI backward.  Returns dq, dk, dv, di, df, dc_initial-or-None (fp32).
+
+    ``out`` = (dq, dk, dv, di, df) lets the caller provide the gradient tensors (any batch/head/token strides,
+    unit innermost stride for dq/dk/dv), e.g. views into a fused (B, S, 2H) qk gradient."""
     lib = _cabi.load_library()
     _check_inputs(q, k, v, i, f)
     B, NH, S, DK = q.shape
@@ -169,11 +172,16 @@ def mlstm_chunkwise_bw(q, k, v, i, f, n_out, m_out, dh, c_initial=None, n_initia
         m0 = torch.zeros(B, NH, device=dev) if m0 is None else m0
     dcl = _state_f32(dc_last, (B, NH, DK, DV))
     with torch.cuda.device(dev):
-        dq = torch.empty(B, NH, S, DK, dtype=q.dtype, device=dev)
-        dk = torch.empty(B, NH, S, DK, dtype=q.dtype, device=dev)
-        dv = torch.empty(B, NH, S, DV, dtype=q.dtype, device=dev)
-        di = torch.empty(B, NH, S, dtype=q.dtype, device=dev)
-        df = torch.empty(B, NH, S, dtype=q.dtype, device=dev)
+        if out is not None:
+            dq, dk, dv, di, df = out
+            assert dq.shape == q.shape and dk.shape == k.shape and dv.shape == v.shape and di.shape == i.shape
+            assert all(t.dtype == q.dtype and t.device == dev for t in out)
+        else:
+            dq = torch.empty(B, NH, S, DK, dtype=q.dtype, device=dev)
+            dk = torch.empty(B, NH, S, DK, dtype=q.dtype, device=dev)
+            dv = torch.empty(B, NH, S, DV, dtype=q.dtype, device=dev)
+            di = torch.empty(B, NH, S, dtype=q.dtype, device=dev)
+            df = torch.empty(B, NH, S, dtype=q.dtype, device=dev)
         dc0 = torch.empty(B, NH, DK, DV, dtype=torch.float32, device=dev) if want_dc_initial else None
         a = _cabi.BwArgs()
         a.shape = _shape(q, v, chunk_size, eps, impl, qk_scale, reverse, siging)
@@ -323,7 +331,8 @@ def register(name: str = KERNEL_NAME) -> str:
 
 
 def patch_model(model: torch.nn.Module, name: str = KERNEL_NAME, mode: str = "train_with_padding",
-                siging: bool = False, fused: bool = False, kernel_dtype: str = "bfloat16") -> int:
+                siging: bool = False, fused: bool = False, kernel_dtype: str = "bfloat16",
+                keep_activations: bool = False) -> int:
     """Point ``gpu_backend`` of every MatrixLSTMCell (vision_lstm2.py:685-697) at the B200 kernel.
 
     ``siging=True`` selects the sigmoid-input-gate variant, i.e. the same function the reference's
@@ -333,7 +342,12 @@ def patch_model(model: torch.nn.Module, name: str = KERNEL_NAME, mode: str = "tr
     ``vil.mlstm_branch_b200``: same parameters and function, but the cell's output stage (MultiHeadLayerNorm +
     relayout + learnable skip) runs as one fused CUDA pass each way, the bottom-right direction uses the
     kernel's anti-causal scan instead of two ``x.flip`` copies, and q/k/v are consumed as strided views
-    (SURVEY.md section 8(f) #2, #3).  Returns the number of cells patched.
+    (SURVEY.md section 8(f) #2, #3).
+
+    ``keep_activations=True`` raises ``ViLBlockPair.ckpt_thresh`` (vision_lstm2.py:1030, 1071-1078) so that the
+    two S=6400 block pairs stop re-running their forward inside the backward: the reference checkpoints them to
+    fit 40-80 GB parts; a B=32 base256 step peaks at ~22 GB of the B200's 180 GB with checkpointing on.
+    Returns the number of cells patched.
     """
     from mlstm_kernels.torch.backend_module import mLSTMBackend, mLSTMBackendConfig
 
@@ -345,6 +359,10 @@ def patch_model(model: torch.nn.Module, name: str = KERNEL_NAME, mode: str = "tr
                 chunkwise_kernel=full, sequence_kernel="native_sequence__native", step_kernel="native", mode=mode,
                 return_last_states=False, chunk_size=64, eps=1e-6, autocast_kernel_dtype="bfloat16"))
             n += 1
+    if keep_activations:
+        for mod in model.modules():
+            if hasattr(mod, "ckpt_thresh"):
+                mod.ckpt_thresh = 1 << 62
     if fused:
         import types
 

@@ -22,7 +22,10 @@ import torch
 import torch.nn.functional as F
 
 from . import _cabi
-from .backend import _DTYPES, _tensor, mlstm_chunkwise__b200, mlstm_siging_chunkwise__b200
+from torch.amp import custom_bwd, custom_fwd
+
+from .backend import (_DTYPES, _tensor, mlstm_chunkwise__b200, mlstm_chunkwise_bw, mlstm_chunkwise_fw,
+                      mlstm_siging_chunkwise__b200)
 
 
 def cellout_supported(NH: int, D: int) -> bool:
@@ -107,6 +110,59 @@ def cell_out(h, weight=None, bias=None, skip=None, x=None, eps=1e-6, out_dtype=N
     return _CellOut.apply(h, weight, bias, skip, x, eps, out_dtype)
 
 
+def _heads(qk, v, gates, NH):
+    """(B, NH, S, D) / (B, NH, S) views of the layer-layout tensors: no data movement."""
+    B, S, H = v.shape
+    D = H // NH
+    q = qk[..., :H].view(B, S, NH, D).transpose(1, 2)
+    k = qk[..., H:].view(B, S, NH, D).transpose(1, 2)
+    vv = v.view(B, S, NH, D).transpose(1, 2)
+    return q, k, vv, gates[..., :NH].transpose(1, 2), gates[..., NH:].transpose(1, 2)
+
+
+class _MlstmLayerLayout(torch.autograd.Function):
+    """Chunkwise mLSTM on the tensors the layer already owns -- qk (B, S, 2H) = [q | k] from qk_proj, v (B, S, H),
+    gates (B, S, 2NH) = [i | f] -- with the gradients written by the kernel straight into tensors of those
+    layouts.  Same C-ABI calls as ``mlstm_chunkwise__b200``; what disappears is the autograd glue around
+    (B, NH, S, D) tensors: three transpose-copies and the q/k concatenation in every backward."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda")
+    def forward(ctx, qk, v, gates, NH, reverse, siging, chunk_size, eps, kernel_dtype):
+        B, S, H = v.shape
+        ctx.in_dtypes = (qk.dtype, v.dtype, gates.dtype)
+        qk_k, v_k, g_k = (t if t.dtype == kernel_dtype else t.to(kernel_dtype) for t in (qk, v, gates))
+        pad = (-S) % chunk_size
+        if pad:  # zero padding as wrap_chunkwise__pad_zeros (kernel_wrappers.py:227-247); padded tokens come last
+            pp = (0, 0, pad, 0) if reverse else (0, 0, 0, pad)  # in scan order = first in memory when reversed
+            qk_k, v_k, g_k = (F.pad(t, pp) for t in (qk_k, v_k, g_k))
+        q, k, vv, i, f = _heads(qk_k, v_k, g_k, NH)
+        need_bw = any(ctx.needs_input_grad[:3])
+        h, n_out, m_out, _, c_states = mlstm_chunkwise_fw(q, k, vv, i, f, chunk_size=chunk_size, eps=eps,
+                                                          save_states=need_bw, reverse=reverse, siging=siging)
+        ctx.save_for_backward(qk_k, v_k, g_k, n_out, m_out, c_states)
+        ctx.cfg = (NH, reverse, siging, chunk_size, eps, pad, S)
+        if pad:
+            h = h[:, :, pad:] if reverse else h[:, :, :S]
+        return h
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dh):
+        qk_k, v_k, g_k, n_out, m_out, c_states = ctx.saved_tensors
+        NH, reverse, siging, chunk_size, eps, pad, S = ctx.cfg
+        if pad:
+            dh = F.pad(dh, (0, 0, pad, 0) if reverse else (0, 0, 0, pad))
+        d_qk, d_v, d_g = torch.empty_like(qk_k), torch.empty_like(v_k), torch.empty_like(g_k)
+        q, k, vv, i, f = _heads(qk_k, v_k, g_k, NH)
+        mlstm_chunkwise_bw(q, k, vv, i, f, n_out, m_out, dh, chunk_size=chunk_size, eps=eps, c_states=c_states,
+                           reverse=reverse, siging=siging, out=_heads(d_qk, d_v, d_g, NH))
+        if pad:
+            d_qk, d_v, d_g = ((t[:, pad:] if reverse else t[:, :S]) for t in (d_qk, d_v, d_g))
+        d_qk, d_v, d_g = (t if t.dtype == dt else t.to(dt) for t, dt in zip((d_qk, d_v, d_g), ctx.in_dtypes))
+        return d_qk, d_v, d_g, None, None, None, None, None, None
+
+
 def _is_reverse(layer) -> bool:
     d = getattr(layer, "direction", None)
     name = getattr(d, "name", None) or getattr(d, "value", None) or str(d)
@@ -155,24 +211,33 @@ def mlstm_cell_b200(cell, q, k, v, reverse=False, skip=None, x_skip=None, siging
     D = H // NH
     if_preact = _gate_preact(cell, q, k, v, qk)
     capped = cell.gate_soft_cap * torch.tanh(if_preact / cell.gate_soft_cap)  # soft_cap, vision_lstm2.py:755-756
-    i_pre, f_pre = torch.chunk(capped, 2, dim=-1)
-    i, f = i_pre.transpose(-1, -2), f_pre.transpose(-1, -2)  # (B, NH, S) views
-    qh, kh, vh = (t.view(B, S, NH, D).transpose(1, 2) for t in (q, k, v))  # (B, NH, S, D) views, no copy
     model_dtype = q.dtype
-    if cell.use_autocast:  # the reference casts on CUDA in train and eval alike (vision_lstm2.py:730-745)
-        qh, kh, vh, i, f = (t.to(cell.autocast_dtype) for t in (qh, kh, vh, i, f))
-    pad = (-S) % chunk_size
-    if pad:  # zero padding like wrap_chunkwise__pad_zeros (kernel_wrappers.py:227-247); the padded tokens must
-        # come LAST in scan order, i.e. at the front of memory for the anti-causal direction
-        pq = (0, 0, pad, 0) if reverse else (0, 0, 0, pad)
-        pg = (pad, 0) if reverse else (0, pad)
-        qh, kh, vh = (F.pad(t, pq) for t in (qh, kh, vh))
-        i, f = F.pad(i, pg), F.pad(f, pg)
-    fn = mlstm_siging_chunkwise__b200 if siging else mlstm_chunkwise__b200
-    kdt = qh.dtype if (kernel_dtype == "input" and qh.dtype in (torch.float16, torch.bfloat16)) else torch.bfloat16
-    h = fn(q=qh, k=kh, v=vh, i=i, f=f, chunk_size=chunk_size, eps=eps, autocast_kernel_dtype=kdt, reverse=reverse)
-    if pad:
-        h = h[:, :, pad:] if reverse else h[:, :, :S]
+    if qk is not None:  # layer-layout path: the kernel reads / writes the layer's own tensors
+        qk_c, v_c, g_c = qk, v, capped
+        if cell.use_autocast:  # the reference casts on CUDA in train and eval alike (vision_lstm2.py:730-745)
+            qk_c, v_c, g_c = (t.to(cell.autocast_dtype) for t in (qk_c, v_c, g_c))
+        autocast_on = torch.is_autocast_enabled("cuda")
+        kdt = qk_c.dtype if (not autocast_on or (kernel_dtype == "input" and qk_c.dtype in (torch.float16, torch.bfloat16))) \
+            else torch.bfloat16  # custom_fwd(cast_inputs=bf16) rule of the registry kernels (native/fwbw.py:37)
+        h = _MlstmLayerLayout.apply(qk_c, v_c, g_c, NH, bool(reverse), bool(siging), int(chunk_size), float(eps), kdt)
+    else:
+        i_pre, f_pre = torch.chunk(capped, 2, dim=-1)
+        i, f = i_pre.transpose(-1, -2), f_pre.transpose(-1, -2)  # (B, NH, S) views
+        qh, kh, vh = (t.view(B, S, NH, D).transpose(1, 2) for t in (q, k, v))  # (B, NH, S, D) views, no copy
+        if cell.use_autocast:
+            qh, kh, vh, i, f = (t.to(cell.autocast_dtype) for t in (qh, kh, vh, i, f))
+        pad = (-S) % chunk_size
+        if pad:  # zero padding like wrap_chunkwise__pad_zeros (kernel_wrappers.py:227-247); the padded tokens must
+            # come LAST in scan order, i.e. at the front of memory for the anti-causal direction
+            pq = (0, 0, pad, 0) if reverse else (0, 0, 0, pad)
+            pg = (pad, 0) if reverse else (0, pad)
+            qh, kh, vh = (F.pad(t, pq) for t in (qh, kh, vh))
+            i, f = F.pad(i, pg), F.pad(f, pg)
+        fn = mlstm_siging_chunkwise__b200 if siging else mlstm_chunkwise__b200
+        kdt = qh.dtype if (kernel_dtype == "input" and qh.dtype in (torch.float16, torch.bfloat16)) else torch.bfloat16
+        h = fn(q=qh, k=kh, v=vh, i=i, f=f, chunk_size=chunk_size, eps=eps, autocast_kernel_dtype=kdt, reverse=reverse)
+        if pad:
+            h = h[:, :, pad:] if reverse else h[:, :, :S]
     norm = cell.outnorm
     out_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else model_dtype
     return cell_out(h, norm.weight_proxy, norm.bias, skip, x_skip, eps=norm.eps, out_dtype=out_dtype)
