@@ -174,7 +174,8 @@ int mlstm_b200_debug_set_bw_variant(int variant);
  *   weight (= 1 + MultiHeadLayerNorm.weight, the reference's weight_proxy, vision_lstm2.py:900-907),
  *   bias, skip: contiguous fp32 (NH*D); weight / bias may be NULL (1 / 0); x.ptr == NULL drops the skip term.
  * Supported: D in {32, 64, 128}, NH*D a multiple of 128 and <= 2048; pointers 8-byte (16-bit types) or
- * 16-byte (fp32) aligned, strides multiples of 4 elements.
+ * 16-byte (fp32) aligned, strides multiples of 4 elements; x has y's strides; in the backward dh has h's strides
+ * and x / dx have dy's (the kernels walk each family with one running offset).
  */
 typedef struct mlstm_b200_cellout_args {
   int32_t B, NH, S, D;

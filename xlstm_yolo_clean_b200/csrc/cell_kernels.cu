@@ -25,9 +25,9 @@ namespace {
 #define MLSTM_CELL_FW_ROWS 4
 #endif
 #ifndef MLSTM_CELL_BW_ROWS
-#define MLSTM_CELL_BW_ROWS 4
+#define MLSTM_CELL_BW_ROWS 3
 #endif
-constexpr int kFwRows = MLSTM_CELL_FW_ROWS, kBwRows = MLSTM_CELL_BW_ROWS;  // (halved for 32-bit operands)  // rows per warp per pipeline stage (two stages are in registers)
+constexpr int kFwRows = MLSTM_CELL_FW_ROWS, kBwRows = MLSTM_CELL_BW_ROWS;  // (fewer for 32-bit operands)  // rows per warp per pipeline stage (two stages are in registers)
 constexpr int kMaxWarps = 16;
 
 struct CellP {
@@ -82,35 +82,43 @@ template <> __device__ __forceinline__ void store4<__half>(__half* p, const floa
   *reinterpret_cast<uint2*>(p) = v;
 }
 
-// sum over the lpg lanes that share a head (lpg is a power of two <= 32, groups are lane-aligned)
-__device__ __forceinline__ float group_sum(float v, int lpg) {
-  for (int o = lpg >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+// sum over the LPG lanes that share a head (LPG = D/4 in {8, 16, 32}; groups are lane-aligned)
+template <int LPG> __device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPG >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
 // mean / rstd of one head row held 4 elements per lane (two-pass in registers, biased variance as
 // F.group_norm: vision_lstm2.py:935-941)
-__device__ __forceinline__ void group_stats(const float (&hv)[4], int lpg, float inv_d, float eps, float& mean, float& rstd) {
-  mean = group_sum(hv[0] + hv[1] + hv[2] + hv[3], lpg) * inv_d;
+template <int LPG>
+__device__ __forceinline__ void group_stats(const float (&hv)[4], float inv_d, float eps, float& mean, float& rstd) {
+  mean = group_sum<LPG>(hv[0] + hv[1] + hv[2] + hv[3]) * inv_d;
   float q = 0.f;
 #pragma unroll
   for (int e = 0; e < 4; ++e) q += (hv[e] - mean) * (hv[e] - mean);
-  rstd = rsqrtf(group_sum(q, lpg) * inv_d + eps);
+  rstd = rsqrtf(group_sum<LPG>(q) * inv_d + eps);
 }
 
 // Walks the token rows row0, row0 + step, ... of one warp, keeping (batch, position) without a division per row.
+// Also carries the running element offsets of the row in the (B, NH, S, D)-strided tensors ("a": stride sb_a per
+// batch, ss_a per token) and in the (B, S, H)-strided ones ("c"), advanced by additions only.
 struct RowIt {
-  int64_t row, rows, step;
-  int bi, si, S, step_b, step_s;
-  __device__ __forceinline__ RowIt(int64_t row0, int64_t rows_, int64_t step_, int S_)
+  int64_t row, rows, step, off_a, off_c, step_a, step_c, wrap_a, wrap_c;
+  int si, S, step_s;
+  __device__ __forceinline__ RowIt(int64_t row0, int64_t rows_, int64_t step_, int S_, int64_t sb_a, int64_t ss_a,
+                                   int64_t sb_c, int64_t ss_c)
       : row(row0), rows(rows_), step(step_), S(S_) {
-    bi = (int)(row0 / S_), si = (int)(row0 - (int64_t)bi * S_);
-    step_b = (int)(step_ / S_), step_s = (int)(step_ - (int64_t)step_b * S_);
+    const int64_t bi = row0 / S_, step_b = step_ / S_;
+    si = (int)(row0 - bi * S_), step_s = (int)(step_ - step_b * S_);
+    off_a = bi * sb_a + si * ss_a, off_c = bi * sb_c + si * ss_c;
+    step_a = step_b * sb_a + step_s * ss_a, step_c = step_b * sb_c + step_s * ss_c;
+    wrap_a = sb_a - S_ * ss_a, wrap_c = sb_c - S_ * ss_c;  // si -= S, ++bi
   }
   __device__ __forceinline__ bool valid() const { return row < rows; }
   __device__ __forceinline__ void next() {
-    row += step, bi += step_b, si += step_s;
-    if (si >= S) si -= S, ++bi;
+    row += step, si += step_s, off_a += step_a, off_c += step_c;
+    if (si >= S) si -= S, off_a += wrap_a, off_c += wrap_c;
   }
 };
 
@@ -122,7 +130,7 @@ template <typename TH, typename TX, int U> struct FwRegs {
 
 // Software-pipelined persistent loop: the loads of the next U rows are in flight while the current U rows are
 // normalised and stored (two register sets, ping-pong), so every warp keeps U*(h + x) loads outstanding.
-template <typename TH, typename TX, int U>
+template <typename TH, typename TX, int U, int LPG>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_cellout_fw(const CellP p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int slot = warp % p.W, r = warp / p.W, R = (blockDim.x >> 5) / p.W;
@@ -137,7 +145,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_cellout_fw(const CellP p)
   const TH* hp = reinterpret_cast<const TH*>(p.h) + head * p.hs[1] + d0;
   const TX* xp = reinterpret_cast<const TX*>(p.x);
   TX* yp = reinterpret_cast<TX*>(p.y);
-  RowIt it((int64_t)blockIdx.x * R + r, (int64_t)p.B * p.S, (int64_t)gridDim.x * R, p.S);
+  RowIt it((int64_t)blockIdx.x * R + r, (int64_t)p.B * p.S, (int64_t)gridDim.x * R, p.S, p.hs[0], p.hs[2], p.ys[0], p.ys[1]);
 
   using Regs = FwRegs<TH, TX, U>;
   auto load = [&](Regs& g) {
@@ -146,9 +154,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_cellout_fw(const CellP p)
       g.yoff[u] = -1;
       g.hv[u] = zraw<TH>(), g.xv[u] = zraw<TX>();
       if (it.valid()) {
-        g.hv[u] = ldraw<TH>(hp + it.bi * p.hs[0] + it.si * p.hs[2]);
-        if (xp) g.xv[u] = ldraw<TX>(xp + it.bi * p.xs[0] + it.si * p.xs[1] + c0);
-        g.yoff[u] = it.bi * p.ys[0] + it.si * p.ys[1] + c0;
+        g.hv[u] = ldraw<TH>(hp + it.off_a);
+        if (xp) g.xv[u] = ldraw<TX>(xp + it.off_c + c0);  // x shares y's strides (checked on the host)
+        g.yoff[u] = it.off_c + c0;
       }
       it.next();
     }
@@ -159,7 +167,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_cellout_fw(const CellP p)
       float mean, rstd, o[4], hv[4], xv[4];
       cvt4<TH>(g.hv[u], hv);
       cvt4<TX>(g.xv[u], xv);
-      group_stats(hv, p.lpg, p.inv_d, p.eps, mean, rstd);  // row validity is warp-uniform
+      group_stats<LPG>(hv, p.inv_d, p.eps, mean, rstd);  // row validity is warp-uniform
 #pragma unroll
       for (int e = 0; e < 4; ++e) o[e] = (hv[e] - mean) * rstd * w[e] + b[e] + sk[e] * xv[e];
       if (g.yoff[u] >= 0) store4<TX>(yp + g.yoff[u], o);
@@ -179,10 +187,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_cellout_fw(const CellP p)
 template <typename TH, typename TX, int U> struct BwRegs {
   typename Raw4<TH>::type hv[U];
   typename Raw4<TX>::type xv[U], gv[U];
-  int bi[U], si[U];  // bi < 0: no row
+  int64_t oa[U], oc[U];  // element offsets of the row in h / dh and in dy / x / dx; oa < 0: no row
 };
 
-template <typename TH, typename TX, int U>
+template <typename TH, typename TX, int U, int LPG>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_cellout_bw(const CellP p) {
   __shared__ float red[3][kMaxWarps][128];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -195,23 +203,23 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_cellout_bw(const CellP p)
     sk[e] = p.skip ? p.skip[c0 + e] : 0.f;
   }
   const TH* hp = reinterpret_cast<const TH*>(p.h) + head * p.hs[1] + d0;
-  TH* dhp = reinterpret_cast<TH*>(p.dh) + head * p.dhs[1] + d0;
+  TH* dhp = reinterpret_cast<TH*>(p.dh) + head * p.hs[1] + d0;
   const TX* xp = reinterpret_cast<const TX*>(p.x);
   const TX* dyp = reinterpret_cast<const TX*>(p.dy);
   TX* dxp = reinterpret_cast<TX*>(p.dx);
-  RowIt it((int64_t)blockIdx.x * R + r, (int64_t)p.B * p.S, (int64_t)gridDim.x * R, p.S);
+  RowIt it((int64_t)blockIdx.x * R + r, (int64_t)p.B * p.S, (int64_t)gridDim.x * R, p.S, p.hs[0], p.hs[2], p.dys[0], p.dys[1]);
 
   using Regs = BwRegs<TH, TX, U>;
   auto load = [&](Regs& g) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      g.bi[u] = -1, g.si[u] = 0;
+      g.oa[u] = -1, g.oc[u] = 0;
       g.hv[u] = zraw<TH>(), g.xv[u] = zraw<TX>(), g.gv[u] = zraw<TX>();
       if (it.valid()) {
-        g.bi[u] = it.bi, g.si[u] = it.si;
-        g.hv[u] = ldraw<TH>(hp + it.bi * p.hs[0] + it.si * p.hs[2]);
-        g.gv[u] = ldraw<TX>(dyp + it.bi * p.dys[0] + it.si * p.dys[1] + c0);
-        if (xp) g.xv[u] = ldraw<TX>(xp + it.bi * p.xs[0] + it.si * p.xs[1] + c0);
+        g.oa[u] = it.off_a, g.oc[u] = it.off_c + c0;  // dh shares h's strides, x / dx share dy's (host-checked)
+        g.hv[u] = ldraw<TH>(hp + it.off_a);
+        g.gv[u] = ldraw<TX>(dyp + g.oc[u]);
+        if (xp) g.xv[u] = ldraw<TX>(xp + g.oc[u]);
       }
       it.next();
     }
@@ -223,7 +231,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_cellout_bw(const CellP p)
       cvt4<TH>(g.hv[u], hv);
       cvt4<TX>(g.xv[u], xv);
       cvt4<TX>(g.gv[u], gv);
-      group_stats(hv, p.lpg, p.inv_d, p.eps, mean, rstd);
+      group_stats<LPG>(hv, p.inv_d, p.eps, mean, rstd);
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -235,16 +243,16 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_cellout_bw(const CellP p)
         ab[e] += gv[e];
         as[e] += gv[e] * xv[e];
       }
-      s1 = group_sum(s1, p.lpg) * p.inv_d;
-      s2 = group_sum(s2, p.lpg) * p.inv_d;
-      if (g.bi[u] >= 0) {
+      s1 = group_sum<LPG>(s1) * p.inv_d;
+      s2 = group_sum<LPG>(s2) * p.inv_d;
+      if (g.oa[u] >= 0) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) o[e] = rstd * (gw[e] - s1 - xh[e] * s2);
-        store4<TH>(dhp + g.bi[u] * p.dhs[0] + g.si[u] * p.dhs[2], o);
+        store4<TH>(dhp + g.oa[u], o);
         if (dxp) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) o[e] = gv[e] * sk[e];
-          store4<TX>(dxp + g.bi[u] * p.dxs[0] + g.si[u] * p.dxs[1] + c0, o);
+          store4<TX>(dxp + g.oc[u], o);
         }
       }
     }
@@ -252,10 +260,10 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_cellout_bw(const CellP p)
   {
     Regs ga, gb;
     load(ga);
-    while (ga.bi[0] >= 0) {
+    while (ga.oa[0] >= 0) {
       load(gb);
       process(ga);
-      if (gb.bi[0] < 0) break;
+      if (gb.oa[0] < 0) break;
       load(ga);
       process(gb);
     }
@@ -378,12 +386,20 @@ int cellout_fw(const mlstm_b200_cellout_args& a, cudaStream_t st) {
     set_error("cellout: tensors must be 8-byte (16-bit) / 16-byte (fp32) aligned with strides that are multiples of 4");
     return MLSTM_B200_EUNSUPPORTED;
   }
+  if (a.x.ptr && (a.x.stride[0] != a.y.stride[0] || a.x.stride[1] != a.y.stride[1])) {
+    set_error("cellout: x and y must have the same strides");
+    return MLSTM_B200_EUNSUPPORTED;
+  }
   p.y = a.y.ptr;
   for (int i = 0; i < 2; ++i) p.ys[i] = a.y.stride[i];
   const int grid = grid_ctas(), block = block_threads(p);
   int rc = dispatch2(a.h_dtype, a.y_dtype, [&](auto th, auto tx) {
     constexpr int kRows = (sizeof(th) + sizeof(tx)) <= 4 ? kFwRows : kFwRows / 2;
-    k_cellout_fw<decltype(th), decltype(tx), kRows><<<grid, block, 0, st>>>(p);
+    switch (p.lpg) {
+      case 8: k_cellout_fw<decltype(th), decltype(tx), kRows, 8><<<grid, block, 0, st>>>(p); break;
+      case 16: k_cellout_fw<decltype(th), decltype(tx), kRows, 16><<<grid, block, 0, st>>>(p); break;
+      default: k_cellout_fw<decltype(th), decltype(tx), kRows, 32><<<grid, block, 0, st>>>(p); break;
+    }
     return 0;
   });
   if (rc) return rc;
@@ -409,6 +425,18 @@ int cellout_bw(const mlstm_b200_cellout_bw_args& b, cudaStream_t st) {
     set_error("cellout_bw: tensors must be 8-byte (16-bit) / 16-byte (fp32) aligned with strides that are multiples of 4");
     return MLSTM_B200_EUNSUPPORTED;
   }
+  for (int i = 0; i < 3; ++i) {
+    if (b.dh.stride[i] != a.h.stride[i]) {
+      set_error("cellout_bw: dh must have the strides of h");
+      return MLSTM_B200_EUNSUPPORTED;
+    }
+  }
+  for (int i = 0; i < 2; ++i) {
+    if ((a.x.ptr && a.x.stride[i] != b.dy.stride[i]) || (b.dx.ptr && b.dx.stride[i] != b.dy.stride[i])) {
+      set_error("cellout_bw: x and dx must have the strides of dy");
+      return MLSTM_B200_EUNSUPPORTED;
+    }
+  }
   const size_t need = cellout_workspace_bytes(a);
   if (!b.workspace || b.workspace_bytes < need) {
     set_error("cellout_bw: workspace too small: need %zu bytes, got %zu", need, b.workspace_bytes);
@@ -420,8 +448,12 @@ int cellout_bw(const mlstm_b200_cellout_bw_args& b, cudaStream_t st) {
   for (int i = 0; i < 3; ++i) p.dhs[i] = b.dh.stride[i];
   const int grid = grid_ctas(), block = block_threads(p);
   int rc = dispatch2(a.h_dtype, a.y_dtype, [&](auto th, auto tx) {
-    constexpr int kRows = (sizeof(th) + 2 * sizeof(tx)) <= 6 ? kBwRows : kBwRows / 2;  // register budget per pipeline stage
-    k_cellout_bw<decltype(th), decltype(tx), kRows><<<grid, block, 0, st>>>(p);
+    constexpr int kRows = (sizeof(th) + 2 * sizeof(tx)) <= 6 ? kBwRows : 2;  // register budget per pipeline stage
+    switch (p.lpg) {
+      case 8: k_cellout_bw<decltype(th), decltype(tx), kRows, 8><<<grid, block, 0, st>>>(p); break;
+      case 16: k_cellout_bw<decltype(th), decltype(tx), kRows, 16><<<grid, block, 0, st>>>(p); break;
+      default: k_cellout_bw<decltype(th), decltype(tx), kRows, 32><<<grid, block, 0, st>>>(p); break;
+    }
     return 0;
   });
   if (rc) return rc;

@@ -50,8 +50,8 @@ class _CellOut(torch.autograd.Function):
             raise RuntimeError("cell_out: h is on the CPU; this backend has no CPU path")
         B, NH, S, D = h.shape
         h = h if _vec_ok(h) else h.contiguous()
-        if x is not None:
-            x = x if (x.dtype == out_dtype and _vec_ok(x)) else x.to(out_dtype).contiguous()
+        if x is not None:  # x, y, dy, dx all move as dense (B, S, H) rows
+            x = x if (x.dtype == out_dtype and x.is_contiguous() and x.data_ptr() % 16 == 0) else x.to(out_dtype).contiguous()
         w32, b32, s32 = _f32c(weight), _f32c(bias), _f32c(skip)
         with torch.cuda.device(h.device):
             y = torch.empty(B, S, NH * D, dtype=out_dtype, device=h.device)
@@ -74,11 +74,11 @@ class _CellOut(torch.autograd.Function):
         lib = _cabi.load_library()
         h, x, weight, bias, skip = ctx.saved_tensors
         B, NH, S, D = h.shape
-        dy = dy if (dy.dtype == ctx.out_dtype and _vec_ok(dy)) else dy.to(ctx.out_dtype).contiguous()
+        dy = dy if (dy.dtype == ctx.out_dtype and dy.is_contiguous() and dy.data_ptr() % 16 == 0) else dy.to(ctx.out_dtype).contiguous()
         w32, s32 = _f32c(weight), _f32c(skip)
         dev = h.device
         with torch.cuda.device(dev):
-            dh = torch.empty(B, NH, S, D, dtype=h.dtype, device=dev)
+            dh = torch.empty_strided(h.shape, h.stride(), dtype=h.dtype, device=dev)  # the kernel walks h and dh together
             dx = torch.empty_like(dy) if (x is not None and ctx.needs_input_grad[4]) else None
             dpar = torch.empty(3, NH * D, dtype=torch.float32, device=dev)
             b = _cabi.CellOutBwArgs()
