@@ -21,6 +21,17 @@ saved = pkg.mlstm_chunkwise_fw(t["q"], t["k"], t["v"], t["i"], t["f"])
 pkg.mlstm_chunkwise_bw(t["q"], t["k"], t["v"], t["i"], t["f"], saved[1], saved[2], t["dh"], c_states=saved[4])
 torch.cuda.synchronize()
 lib.mlstm_b200_debug_set_clock_buffer(None)
+flat = buf.cpu().view(2, 4096)
+for name, k in (("fw", 0), ("bw", 1)):
+    ct = flat[k, 3300:3300 + 3 * min(B * NH, 260)].view(-1, 3)
+    t0 = ct[:, 0].min().item()
+    st, en = (ct[:, 0] - t0).float() / 1e3, (ct[:, 1] - t0).float() / 1e3
+    dur = en - st
+    print(f"{name} CTA lifetimes (us, globaltimer): start min/max {st.min():.2f}/{st.max():.2f}  end min/max {en.min():.2f}/{en.max():.2f}  "
+          f"duration min/median/max {dur.min():.2f}/{dur.median():.2f}/{dur.max():.2f}  cta0 {dur[0]:.2f}  distinct SMs {len(set(ct[:, 2].tolist()))}")
+    order = dur.argsort()
+    print("   slowest CTAs (cta, sm, start, dur):", [(int(i), int(ct[i, 2]), round(float(st[i]), 2), round(float(dur[i]), 2)) for i in order[-6:]])
+    print("   fastest CTAs (cta, sm, start, dur):", [(int(i), int(ct[i, 2]), round(float(st[i]), 2), round(float(dur[i]), 2)) for i in order[:4]])
 v = buf.cpu().view(2, 256, 16)
 NT = (S + 127) // 128
 for name, k in (("fw", 0), ("bw", 1)):

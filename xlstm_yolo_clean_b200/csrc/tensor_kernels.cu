@@ -48,8 +48,21 @@ struct GateBuf {
 #ifdef MLSTM_TC_PROFILE  // phase clocks of CTA 0 (tools/phase_clocks.py builds with this flag)
 #define TC_PROF(tile, slot) \
   if (p.prof && blockIdx.x == 0 && (threadIdx.x == 0 || threadIdx.x == kWorkers)) p.prof[(tile) * 16 + (slot)] = clock64()
+// every CTA's lifetime on the global nanosecond timer: [3300 + 3*cta + {0 entry, 1 exit, 2 SM id}] (cta < 260)
+#define TC_PROF_CTA(which)                                                                  \
+  if (p.prof && threadIdx.x == 0 && blockIdx.x < 260) {                                    \
+    unsigned long long _t;                                                                  \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                                 \
+    p.prof[3300 + 3 * blockIdx.x + (which)] = (long long)_t;                               \
+    if ((which) == 0) {                                                                     \
+      unsigned _sm;                                                                         \
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(_sm));                                     \
+      p.prof[3300 + 3 * blockIdx.x + 2] = _sm;                                              \
+    }                                                                                       \
+  }
 #else
 #define TC_PROF(tile, slot)
+#define TC_PROF_CTA(which)
 #endif
 
 template <typename T>
@@ -318,8 +331,11 @@ struct FwSmem {
   static constexpr int oK = oQ + NSTAGE * kTile;
   static constexpr int oV = oK + NSTAGE * kTile;
   static constexpr int oKb = oV + NSTAGE * kTile;    // abar . K
-  static constexpr int oH = oKb + kTile;             // h staging
-  static constexpr int oC = oH + kTile;              // bf16 copy of C (D x D), MMA B operand of Q [C | n]
+  // h staging.  kHBuf = 2 would let the TMA store of tile c drain while tile c+1 runs (128 CTAs store in
+  // lock-step and a store takes up to ~3k cycles under that burst); the plumbing below supports it.
+  static constexpr int kHBuf = 1;  // measured: 2 buffers at D = 64 is 1-2 us SLOWER at config 2 (40.7-42.0 vs 39.5 us)
+  static constexpr int oH = oKb + kTile;
+  static constexpr int oC = oH + kHBuf * kTile;      // bf16 copy of C (D x D), MMA B operand of Q [C | n]
   static constexpr int oNt = oC + Lay<D>::kState;    // second N block of that operand: column 0 = bf16 copy of n
   static constexpr int oOnes = oNt + Lay<D>::kState; // [8][128] ones, K-major: B operand of dn = Kbar^T 1
   static constexpr int oSmall = oOnes + 2048;
@@ -348,6 +364,7 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
   using L = Lay<D>;
   constexpr int NSTAGE = SM::NSTAGE, CW = L::CW;
   TC_PROF(200, 0);  // kernel entry
+  TC_PROF_CTA(0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   float* fsm = (float*)(smem + SM::oSmall);
@@ -356,7 +373,7 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
   uint8_t* sC = smem + SM::oC;
   uint8_t* sNt = smem + SM::oNt;
   uint8_t* sOnes = smem + SM::oOnes;
-  __shared__ uint64_t bar_full[NSTAGE], bar_s, bar_dc, bar_h, bar_g[2];
+  __shared__ uint64_t bar_full[NSTAGE], bar_s, bar_dc, bar_h, bar_hx, bar_g[2];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -385,6 +402,7 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
     mbar_init(&bar_s, 1);
     mbar_init(&bar_dc, 1);
     mbar_init(&bar_h, 1);
+    mbar_init(&bar_hx, 1);
     mbar_init(&bar_g[0], 1);
     mbar_init(&bar_g[1], 1);
     fence_mbar_init();
@@ -481,20 +499,30 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       const int s = c % NSTAGE;
       const uint64_t dQ = umma_desc_advance(dQ0, s * SM::kTile), dV = umma_desc_advance(dV0, s * SM::kTile);
       TC_PROF(c, 9);
+      // Hinter = Q [C_{k-1} | n_{k-1}] (column D is q . n_{k-1}) depends on nothing this tile computes: the state
+      // copies were written before the previous tile's NB_C and its Q tile has landed (S(c) waited for it), so
+      // it runs under the workers' P phase instead of behind P V on the S -> P -> PV -> epilogue chain.
+      if (elect_one()) {  // elect.sync lets ptxas emit straight-line UTCHMMA (no per-instruction thread loop)
+        tc_fence_after_sync();
+#pragma unroll
+        for (int kk = 0; kk < D / 16; ++kk)
+          umma_f16(tHx, umma_desc_advance(dQ, kk * 32), umma_desc_advance(dC, kk * L::kAdvMN), id_hx, kk > 0);
+        umma_commit(&bar_hx);
+      }
+      __syncwarp();
       named_sync(NB_B, kNbAB);  // P(c) written
       if (lane == 0) {
-        tma_store_wait_read<0>();  // earlier h / c_states stores have read sH and sC (rewritten after bar_h)
+        // the stores that read the buffers rewritten after bar_h -- sC (c_states) and this tile's h staging buffer --
+        // are done; with two h buffers the newest group (h of the previous tile) may still be in flight
+        tma_store_wait_read<SM::kHBuf - 1>();
         TC_PROF(c, 10);
       }
       __syncwarp();
-      if (elect_one()) {  // elect.sync lets ptxas emit straight-line UTCHMMA (no per-instruction thread loop)
+      if (elect_one()) {
         tc_fence_after_sync();
 #pragma unroll
         for (int kk = 0; kk < LT / 16; ++kk)  // Hintra = P V, A = P from TMEM (packed inside the S columns)
           umma_f16_ts(tHi, (par ? tS1 : tS0) + 32 * (kk / 2) + 8 * (kk % 2), umma_desc_advance(dV, kk * L::kAdvMN), id_h, kk > 0);
-#pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk)  // Hinter = Q [C_{k-1} | n_{k-1}]: column D is q . n_{k-1}
-          umma_f16(tHx, umma_desc_advance(dQ, kk * 32), umma_desc_advance(dC, kk * L::kAdvMN), id_hx, kk > 0);
         umma_commit(&bar_h);
       }
       __syncwarp();
@@ -516,8 +544,11 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       named_sync(NB_C, kNbC);  // h staged, C_k written: every worker is done with this tile
       if (lane == 0) {
         TC_PROF(c, 14);
-        tma_store_4d(&mapH, sH, 0, mt(c) * LT, hh, b);
-        if (p.store_states && c + 1 < p.NT) tma_store_4d(&mapCs, sC, 0, mt(c + 1) * D, hh, b);  // state entering tile c+1
+        if (p.store_states && c + 1 < p.NT) {  // state entering tile c+1; its own, OLDER group than h(c): see the wait above
+          tma_store_4d(&mapCs, sC, 0, mt(c + 1) * D, hh, b);
+          tma_store_commit();
+        }
+        tma_store_4d(&mapH, sH + (SM::kHBuf == 2 ? (c & 1) * SM::kTile : 0), 0, mt(c) * LT, hh, b);
         tma_store_commit();
         if (c + NSTAGE < p.NT) load_stage(s, c + NSTAGE);
         TC_PROF(c, 15);
@@ -642,6 +673,7 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       }
       TC_PROF(c, 6);
       // ---- epilogue -----------------------------------------------------------------------------------
+      mbar_wait(&bar_hx, par, 9);
       mbar_wait(&bar_h, par, 7);
       tc_fence_after_sync();
       TC_PROF(c, 7);
@@ -659,7 +691,7 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
         float o[CW];
 #pragma unroll
         for (int j = 0; j < CW; ++j) o[j] = (__uint_as_float(hi[j]) + bq * __uint_as_float(hx[j])) * inv;  // fw.py:200-212
-        store_cols<T, D>(sH, row, ch * CW, o);
+        store_cols<T, D>(sH + (SM::kHBuf == 2 ? (c & 1) * SM::kTile : 0), row, ch * CW, o);
         if (ch == 0 && row < n_valid) {
           p.n_out[(int64_t)bh * p.S + t0 + row] = nmax;
           p.m_out[(int64_t)bh * p.S + t0 + row] = m_t;
@@ -676,7 +708,7 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
         if (owns_c) {
 #pragma unroll
           for (int j = 0; j < CW; ++j) Creg[j] = gbar * Creg[j] + __uint_as_float(v[j]);
-          store_cols<T, D>(sC, drow, ch * CW, Creg);  // Q [C | n]_{k-1} (bar_h) has finished reading the old copies
+          store_cols<T, D>(sC, drow, ch * CW, Creg);  // Q [C | n]_{k-1} (bar_hx) has finished reading the old copies
           if (ch == 0) {  // n_k = gbar n_{k-1} + column sums of Kbar (fw.py:116)
             n_reg = gbar * n_reg + __uint_as_float(dn_u);
             *reinterpret_cast<T*>(sNt + L::swz(drow, 0)) = from_f32<T>(n_reg);
@@ -704,6 +736,7 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
   tc_fence_before_sync();
   __syncthreads();
   TC_PROF(200, 2);
+  TC_PROF_CTA(1);
   if (warp == kCtlWarp) tmem_dealloc<SM::kTmemCols>(tmem);
 }
 
@@ -1125,6 +1158,7 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
   using L = Lay<D>;
   constexpr int CW = L::CW;
   TC_PROF(200, 0);  // kernel entry
+  TC_PROF_CTA(0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem + SM::oQ;  // stage 0; stage s is SM::kStage bytes further
@@ -1658,6 +1692,7 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
   tc_fence_before_sync();
   __syncthreads();
   TC_PROF(200, 2);
+  TC_PROF_CTA(1);
   if (warp == kCtlWarp) tmem_dealloc<512>(tmem);
 }
 
@@ -1704,6 +1739,7 @@ tc_bw2(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtenso
   using L = Lay<D>;
   constexpr int CW = L::CW;
   TC_PROF(200, 0);  // kernel entry
+  TC_PROF_CTA(0);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem + SM::oQ;  // buffer 0 of each input; processing step `it` uses buffer it % n
@@ -2288,6 +2324,7 @@ tc_bw2(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtenso
   tc_fence_before_sync();
   __syncthreads();
   TC_PROF(200, 2);
+  TC_PROF_CTA(1);
   if (warp == kCtlWarp) tmem_dealloc<512>(tmem);
 }
 
