@@ -65,6 +65,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   mbar_wait_slow(bar, parity, tag);
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// wait: blocks until the grid this one was made dependent on (launch attribute programmaticStreamSerialization)
+// has completed and its memory is visible; a no-op for a normal launch.  launch_dependents: lets the NEXT
+// dependent grid's CTAs take an SM as soon as resources free up; they must not touch global memory before their
+// own wait.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- named barriers (sub-CTA handoff)
 // arrive: non-blocking (producer side); sync: blocking.  `count` = total participating threads.
 __device__ __forceinline__ void named_arrive(int id, int count) {

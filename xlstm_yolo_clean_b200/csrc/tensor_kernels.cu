@@ -392,10 +392,13 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
     tma_load_4d(smem + SM::oK + s * SM::kTile, &mapK, &bar_full[s], 0, mt(c) * LT, hh, b);
     tma_load_4d(smem + SM::oV + s * SM::kTile, &mapV, &bar_full[s], 0, mt(c) * LT, hh, b);
   };
-  // cold start: the first Q / K / V tiles are requested before anything else happens in the CTA
+  // cold start: the first Q / K / V tiles are requested before anything else happens in the CTA.  Under
+  // programmatic dependent launch every thread passes griddepcontrol.wait before ITS first global access (a no-op
+  // for a normal launch), so the set-up below overlaps the tail of the previous kernel in the stream.
   if (tid == kCtlWarp * 32) {
     for (int s = 0; s < NSTAGE; ++s) mbar_init(&bar_full[s], 1);
     fence_mbar_init();
+    grid_dep_wait();
     for (int s = 0; s < NSTAGE && s < p.NT; ++s) load_stage(s, s);
   }
   if (tid == 0) {
@@ -413,6 +416,8 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       prefetch_tmap(&mapQ); prefetch_tmap(&mapK); prefetch_tmap(&mapV); prefetch_tmap(&mapH); prefetch_tmap(&mapCs);
     }
   }
+  grid_dep_wait();
+  grid_dep_launch();
   // worker-side state: fp32 master copy of C in the registers of lanes < 16 of the worker warps:
   // row d = 16*rb + lane (M=64 TMEM layout; D = 32 has 32 real rows, warps rb < 2), columns CW*ch .. CW*ch+CW-1;
   // the ch == 0 owner of a row also keeps n[d] (fp32) and its 16-bit operand copy in sNt(d, 0)
@@ -1192,10 +1197,12 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
     tma_load_4d(base + SM::odH, &mapdH, &bar_full[s], 0, mt(c) * LT, hh, b);
     tma_load_4d(base + SM::oCs, &mapCs, &bar_full[s], 0, mt(c) * D, hh, b);
   };
-  // cold start: the first input tiles are requested before anything else happens in the CTA
+  // cold start: the first input tiles are requested before anything else happens in the CTA (grid-dependency
+  // waits: see tc_fw)
   if (tid == kCtlWarp * 32) {
     for (int s = 0; s < SM::kNST; ++s) mbar_init(&bar_full[s], 1);
     fence_mbar_init();
+    grid_dep_wait();
     for (int s = 0; s < SM::kNST && s < p.NT; ++s) load_stage(s, p.NT - 1 - s);
   }
   if (tid == 0) {
@@ -1217,6 +1224,8 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       prefetch_tmap(&mapCs); prefetch_tmap(&mapdQ); prefetch_tmap(&mapdK); prefetch_tmap(&mapdV);
     }
   }
+  grid_dep_wait();
+  grid_dep_launch();
   const int rb = warp & 3, ch = (warp >> 2) & 1;
   const int row = rb * 32 + lane;
   const uint32_t lane_base = (uint32_t)(rb * 32) << 16;
@@ -2341,13 +2350,35 @@ int num_sms() {
   return n;
 }
 
+// Programmatic dependent launch for the two main kernels (tc_fw, tc_bw): the next kernel's CTAs may become resident
+// while this one drains; they block in griddepcontrol.wait before touching memory.  MLSTM_B200_PDL=0 disables it.
+int pdl_mode() {  // 0 off, 1 forward and backward, 2 forward only
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MLSTM_B200_PDL");
+    v = e ? (e[0] - '0') : 2;
+    if (v < 0 || v > 2) v = 2;
+  }
+  return v;
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(bool use_pdl, void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(block), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 template <typename T, int D>
 int launch_fw(const TcFwParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
               const CUtensorMap& mh, const CUtensorMap& mcs, cudaStream_t st) {
   using SM = FwSmem<D>;
   auto kern = p.rev ? tc_fw<T, D, true> : tc_fw<T, D, false>;
   MLSTM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
-  kern<<<p.B * p.NH, kTcThreads, SM::kBytes, st>>>(mq, mk, mv, mh, mcs, p);
+  MLSTM_CUDA_CHECK(launch_pdl(pdl_mode() != 0, kern, p.B * p.NH, kTcThreads, SM::kBytes, st, mq, mk, mv, mh, mcs, p));
   count_launch();
   MLSTM_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -2395,7 +2426,7 @@ int launch_bw(const TcBwParams& p, const CUtensorMap& mq, const CUtensorMap& mk,
   using SM = BwSmem<D>;
   auto kern = p.rev ? tc_bw<T, D, true> : tc_bw<T, D, false>;
   MLSTM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
-  kern<<<p.B * p.NH, kTcThreads, SM::kBytes, st>>>(mq, mk, mv, mdh, mcs, mdq, mdk, mdv, p);
+  MLSTM_CUDA_CHECK(launch_pdl(pdl_mode() == 1, kern, p.B * p.NH, kTcThreads, SM::kBytes, st, mq, mk, mv, mdh, mcs, mdq, mdk, mdv, p));
   MLSTM_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
