@@ -189,6 +189,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # NCCL writes its version banner to STDOUT at NCCL_DEBUG=VERSION; stdout carries the one JSON line only
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
         dist.barrier()
     import xlstm_yolo_clean_b200 as pkg
