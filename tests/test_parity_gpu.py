@@ -457,3 +457,50 @@ def test_transposed_backward_variant(pkg, shape, rev):
         for name, g in res[variant].items():
             w = want[name].flip(2) if (rev and name != "dc0") else want[name]
             assert O.rel_err(g.double().cpu(), w) < 2e-2, (variant, name)
+
+
+@pytest.mark.parametrize("S", [100, 400, 52, 1004])
+@pytest.mark.parametrize("D", [32, 64])
+@pytest.mark.parametrize("reverse", [False, True], ids=["causal", "anticausal"])
+def test_ragged_sequence_lengths_on_tensor_path(pkg, S, D, reverse):
+    """Any S % 4 == 0 runs on the tcgen05 kernels (ragged 128-token tail tiles are handled in-kernel: TMA
+    zero-fill, gates masked at scan time), so the model's S = 400 / 100 stages need no zero-padding copies
+    (kernel_wrappers.py:227-247).  chunk_size = 4 divides every case; the result does not depend on it."""
+    assert pkg.tensor_path_supported(2, 3, S, D, D, torch.bfloat16, chunk_size=4)
+    inp = O.make_inputs(2, 3, S, D, D, seed=70 + S, dtype=torch.float32)
+    dev = torch.device("cuda:0")
+    pkg.set_default_impl("tensor")
+    try:
+        t = {k: v.to(torch.bfloat16).to(dev) for k, v in inp.items()}
+        leaves = {k: t[k].detach().requires_grad_(True) for k in ("q", "k", "v", "i", "f")}
+        h = pkg.mlstm_chunkwise__b200(**leaves, chunk_size=4, reverse=reverse, autocast_kernel_dtype=torch.bfloat16)
+        h.backward(t["dh"])
+        torch.cuda.synchronize()
+    finally:
+        pkg.set_default_impl("auto")
+    seq = ("q", "k", "v", "i", "f", "dh")
+    src = {k: (v.flip(2) if (reverse and k in seq) else v) for k, v in inp.items()}
+    want = _oracle(src, torch.bfloat16, L=4)
+    got = dict(h=h, dq=leaves["q"].grad, dk=leaves["k"].grad, dv=leaves["v"].grad, di=leaves["i"].grad, df=leaves["f"].grad)
+    for name in got:
+        w = want[name].flip(2) if reverse else want[name]
+        assert O.rel_err(got[name].double().cpu(), w) < 2e-2, (name, O.rel_err(got[name].double().cpu(), w))
+
+
+def test_ragged_d128_forward_and_siging(pkg):
+    inp = O.make_inputs(1, 2, 100, 128, 128, seed=5, dtype=torch.float32)
+    dev = torch.device("cuda:0")
+    t = {k: v.to(torch.bfloat16).to(dev) for k, v in inp.items()}
+    with torch.no_grad():
+        h = pkg.mlstm_chunkwise__b200(q=t["q"], k=t["k"], v=t["v"], i=t["i"], f=t["f"], chunk_size=4)
+    assert O.rel_err(h.double().cpu(), _oracle(inp, torch.bfloat16, L=4)["h"]) < 2e-2
+    inp = O.make_inputs(2, 2, 400, 64, 64, seed=6, dtype=torch.float32)
+    t = {k: v.to(torch.bfloat16).to(dev) for k, v in inp.items()}
+    leaves = {k: t[k].detach().requires_grad_(True) for k in ("q", "k", "v", "i", "f")}
+    h = pkg.mlstm_siging_chunkwise__b200(**leaves, chunk_size=16)
+    h.backward(t["dh"])
+    r = {k: v.to(torch.bfloat16).double() for k, v in inp.items()}
+    hw, _, g = O.fwbw(r["q"], r["k"], r["v"], r["i"], r["f"], r["dh"], chunk_size=16, siging=True)
+    assert O.rel_err(h.double().cpu(), hw) < 2e-2
+    for got, want in zip((leaves["q"].grad, leaves["k"].grad, leaves["v"].grad, leaves["i"].grad, leaves["f"].grad), g[:5]):
+        assert O.rel_err(got.double().cpu(), want) < 2e-2

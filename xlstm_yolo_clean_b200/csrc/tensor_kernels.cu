@@ -1401,7 +1401,7 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       TileRaw r;
       const int t0 = mt(c) * LT, n_valid = min(LT, p.S - t0);
       r.g = load_gate_raw<T>(ip + (int64_t)t0 * p.ig_ss, p.ig_ss, fp + (int64_t)t0 * p.fg_ss, p.fg_ss, n_valid);
-      if (lane * 4 < n_valid) {  // n_valid is a multiple of 64
+      if (lane * 4 < n_valid) {  // n_valid is a multiple of 4 (tensor_supported)
         r.mt = *reinterpret_cast<const float4*>(mo + t0 + lane * 4);
         r.nt = *reinterpret_cast<const float4*>(no + t0 + lane * 4);
       } else {
@@ -1982,7 +1982,7 @@ tc_bw2(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtenso
       TileRaw r;
       const int t0 = mt(c) * LT, n_valid = min(LT, p.S - t0);
       r.g = load_gate_raw<T>(ip + (int64_t)t0 * p.ig_ss, p.ig_ss, fp + (int64_t)t0 * p.fg_ss, p.fg_ss, n_valid);
-      if (lane * 4 < n_valid) {  // n_valid is a multiple of 64
+      if (lane * 4 < n_valid) {  // n_valid is a multiple of 4 (tensor_supported)
         r.mt = *reinterpret_cast<const float4*>(mo + t0 + lane * 4);
         r.nt = *reinterpret_cast<const float4*>(no + t0 + lane * 4);
       } else {
@@ -2517,7 +2517,11 @@ bool tensor_supported(const mlstm_b200_shape& s, int backward) {
   if (s.dtype != MLSTM_B200_BF16 && s.dtype != MLSTM_B200_F16) return false;
   if (s.DHQK != s.DHHV) return false;
   if (s.DHQK != 64 && s.DHQK != 32 && !(s.DHQK == 128 && !backward)) return false;
-  if (s.chunk_size % 64 != 0 || s.S % 64 != 0) return false;
+  // Tiles are 128 tokens whatever chunk_size is (h and the states do not depend on it: the stabiliser equals the
+  // step-recurrent one), and ragged last tiles are handled in-kernel (TMA zero-fill, gates masked at scan time),
+  // so any S that keeps the fp32 n_out / m_out rows 16-byte aligned is covered; S % chunk_size == 0 is enforced
+  // at the C-ABI like the reference does (native/fw.py:252-254).
+  if (s.S % 4 != 0) return false;
   return true;
 }
 

@@ -17,6 +17,7 @@ There is no CPU path: CPU tensors raise.
 from __future__ import annotations
 
 import ctypes as C
+import math
 
 import torch
 import torch.nn.functional as F
@@ -25,7 +26,7 @@ from . import _cabi
 from torch.amp import custom_bwd, custom_fwd
 
 from .backend import (_DTYPES, _tensor, mlstm_chunkwise__b200, mlstm_chunkwise_bw, mlstm_chunkwise_fw,
-                      mlstm_siging_chunkwise__b200)
+                      mlstm_siging_chunkwise__b200, tensor_path_supported)
 
 
 def cellout_supported(NH: int, D: int) -> bool:
@@ -132,6 +133,13 @@ class _MlstmLayerLayout(torch.autograd.Function):
         B, S, H = v.shape
         ctx.in_dtypes = (qk.dtype, v.dtype, gates.dtype)
         qk_k, v_k, g_k = (t if t.dtype == kernel_dtype else t.to(kernel_dtype) for t in (qk, v, gates))
+        if S % chunk_size and kernel_dtype in (torch.float16, torch.bfloat16):
+            # The tcgen05 kernels walk 128-token tiles whatever the chunk size is and handle a ragged last tile
+            # themselves (the result does not depend on chunk_size: the stabiliser equals the step-recurrent one),
+            # so S = 400 / 100 run as they are with a chunk size that divides them -- no zero-padding copies.
+            g = math.gcd(S, chunk_size)
+            if tensor_path_supported(B, NH, S, H // NH, H // NH, kernel_dtype, chunk_size=g):
+                chunk_size = g
         pad = (-S) % chunk_size
         if pad:  # zero padding as wrap_chunkwise__pad_zeros (kernel_wrappers.py:227-247); padded tokens come last
             pp = (0, 0, pad, 0) if reverse else (0, 0, 0, pad)  # in scan order = first in memory when reversed
