@@ -289,16 +289,18 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) k_cellout_bw(const CellP p)
   }
 }
 
-// stage 2: over CTAs, in a fixed order
+// stage 2: over CTAs, in a fixed order: one warp per output element, lane l sums partials l, l + 32, ... and the
+// lanes are combined by a shuffle tree (same association every run: bit-identical results)
 __global__ void k_cellout_reduce(const float* __restrict__ partial, int n_cta, int H, float* dweight, float* dbias, float* dskip) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 3 * H) return;
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (idx >= 3 * H) return;  // warp-uniform
   const int q = idx / H, c = idx - q * H;
   float* out = q == 0 ? dweight : q == 1 ? dbias : dskip;
   if (!out) return;
   float acc = 0.f;
-  for (int i = 0; i < n_cta; ++i) acc += partial[((int64_t)i * 3 + q) * H + c];
-  out[c] = acc;
+  for (int i = lane; i < n_cta; i += 32) acc += partial[((int64_t)i * 3 + q) * H + c];
+  acc = warp_all_sum(acc);
+  if (lane == 0) out[c] = acc;
 }
 
 int grid_ctas() {
@@ -458,7 +460,7 @@ int cellout_bw(const mlstm_b200_cellout_bw_args& b, cudaStream_t st) {
   });
   if (rc) return rc;
   MLSTM_CUDA_CHECK(cudaGetLastError());
-  k_cellout_reduce<<<(3 * p.H + 255) / 256, 256, 0, st>>>(p.partial, grid, p.H, b.dweight, b.dbias, b.dskip);
+  k_cellout_reduce<<<(3 * p.H * 32 + 255) / 256, 256, 0, st>>>(p.partial, grid, p.H, b.dweight, b.dbias, b.dskip);
   count_launch(2);
   MLSTM_CUDA_CHECK(cudaGetLastError());
   return 0;
