@@ -207,3 +207,42 @@ def test_flip_free_branch_matches_reference_composition(pkg, S, reverse):
     assert rel(dx_new, dx_ref) < 2e-2, rel(dx_new, dx_ref)
     for n in g_ref:
         assert rel(g_new[n], g_ref[n]) < 2e-2, (n, rel(g_new[n], g_ref[n]))
+
+
+def test_patch_layers_rebinds_and_trains_under_amp(pkg):
+    """patch_layers on a two-direction stack: the rebound branch is what runs, under fp16 autocast + GradScaler
+    like the ultralytics trainer (engine/trainer.py:382-392), gradients reach every parameter and match the
+    un-rebound composition."""
+    torch.manual_seed(9)
+    dev = torch.device("cuda:0")
+
+    class Stack(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = _Layer(128, 4, _Dir("ROWWISE_FROM_TOP_LEFT"))
+            self.b = _Layer(128, 4, _Dir("ROWWISE_FROM_BOT_RIGHT"))
+            for l in (self.a, self.b):
+                l.mlstm_branch = lambda x, _l=l: _reference_branch(pkg, _l, x, pkg.vil._is_reverse(_l))
+
+        def forward(self, x):
+            x = x + self.a.mlstm_branch(x)
+            return x + self.b.mlstm_branch(x)
+
+    model = Stack().to(dev)
+    x = torch.randn(2, 400, 128, device=dev)
+
+    def step():
+        model.zero_grad()
+        with torch.autocast("cuda", dtype=torch.float16):
+            out = model(x)
+            loss = out.float().pow(2).mean()
+        loss.backward()
+        return float(loss), {n: p.grad.clone() for n, p in model.named_parameters()}
+
+    loss_ref, g_ref = step()
+    assert pkg.patch_layers(model) == 2
+    loss_new, g_new = step()
+    assert abs(loss_new - loss_ref) < 5e-3 * abs(loss_ref)
+    assert set(g_new) == set(g_ref)
+    for n in g_ref:
+        assert rel(g_new[n], g_ref[n]) < 3e-2, (n, rel(g_new[n], g_ref[n]))

@@ -364,16 +364,7 @@ def patch_model(model: torch.nn.Module, name: str = KERNEL_NAME, mode: str = "tr
             if hasattr(mod, "ckpt_thresh"):
                 mod.ckpt_thresh = 1 << 62
     if fused:
-        import types
-
         from . import vil
 
-        for mod in model.modules():
-            cell = getattr(mod, "mlstm_cell", None)
-            if cell is None or not all(hasattr(mod, a) for a in ("proj_up", "qk_proj", "v_proj", "learnable_skip", "proj_down")):
-                continue
-            if not vil.cellout_supported(cell.num_heads, cell.dim // cell.num_heads):
-                continue
-            mod.mlstm_branch = types.MethodType(
-                lambda self, x, _s=siging, _k=kernel_dtype: vil.mlstm_branch_b200(self, x, siging=_s, kernel_dtype=_k), mod)
+        vil.patch_layers(model, siging=siging, kernel_dtype=kernel_dtype)
     return n

@@ -266,3 +266,22 @@ def mlstm_branch_b200(layer, x, siging=False, kernel_dtype="bfloat16"):
     y = mlstm_cell_b200(layer.mlstm_cell, q, k, v, reverse=rev, skip=layer.learnable_skip, x_skip=x_act, siging=siging,
                         kernel_dtype=kernel_dtype, qk=qk)
     return layer.proj_down(y)
+
+
+def patch_layers(model: torch.nn.Module, siging: bool = False, kernel_dtype: str = "bfloat16") -> int:
+    """Rebind ``mlstm_branch`` of every ViLLayer-shaped module (``proj_up``, ``qk_proj``, ``v_proj``, ``mlstm_cell``,
+    ``learnable_skip``, ``proj_down``; vision_lstm2.py:218-290) whose head geometry the fused output kernel covers to
+    ``mlstm_branch_b200``.  Parameters and state-dict keys are untouched.  Returns the number of layers rebound."""
+    import types
+
+    n = 0
+    for mod in model.modules():
+        cell = getattr(mod, "mlstm_cell", None)
+        if cell is None or not all(hasattr(mod, a) for a in ("proj_up", "qk_proj", "v_proj", "learnable_skip", "proj_down")):
+            continue
+        if not cellout_supported(cell.num_heads, cell.dim // cell.num_heads):
+            continue
+        mod.mlstm_branch = types.MethodType(
+            lambda self, x, _s=siging, _k=kernel_dtype: mlstm_branch_b200(self, x, siging=_s, kernel_dtype=_k), mod)
+        n += 1
+    return n
