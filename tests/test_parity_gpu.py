@@ -504,3 +504,17 @@ def test_ragged_d128_forward_and_siging(pkg):
     assert O.rel_err(h.double().cpu(), hw) < 2e-2
     for got, want in zip((leaves["q"].grad, leaves["k"].grad, leaves["v"].grad, leaves["i"].grad, leaves["f"].grad), g[:5]):
         assert O.rel_err(got.double().cpu(), want) < 2e-2
+
+
+@pytest.mark.parametrize("B,NH,S,D", [(1, 1, 4, 64), (1, 3, 8, 32), (1, 1, 60, 64), (7, 1, 124, 32), (1, 2, 132, 64),
+                                     (3, 1, 260, 32), (1, 5, 388, 64)])
+def test_tiny_and_odd_shapes_on_tensor_path(pkg, B, NH, S, D):
+    """Edge shapes of the tcgen05 route: sequences shorter than one 128-token tile, tails of 4 tokens, odd
+    batch / head counts; forward, every gradient, fp16 this time."""
+    inp = O.make_inputs(B, NH, S, D, D, seed=S, dtype=torch.float32)
+    pkg.set_default_impl("tensor")
+    try:
+        got = _run(pkg, inp, torch.float16, L=4, impl="tensor")
+    finally:
+        pkg.set_default_impl("auto")
+    _assert_close(got, _oracle(inp, torch.float16, L=4), 2e-2, f"{(B, NH, S, D)}")
