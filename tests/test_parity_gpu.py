@@ -518,3 +518,47 @@ def test_tiny_and_odd_shapes_on_tensor_path(pkg, B, NH, S, D):
     finally:
         pkg.set_default_impl("auto")
     _assert_close(got, _oracle(inp, torch.float16, L=4), 2e-2, f"{(B, NH, S, D)}")
+
+
+@pytest.mark.parametrize("states", [False, True], ids=["plain", "states"])
+@pytest.mark.parametrize("reverse", [False, True], ids=["causal", "anticausal"])
+def test_d128_backward_by_blocks(pkg, states, reverse):
+    """Head dim 128 (base384): forward on tc_fw_d128, backward as four 64 x 64 block problems on tc_bw<64>
+    (backend._bw_d128_by_blocks).  Every gradient, incl. dC_initial with dC_last, both scan directions, a ragged S."""
+    S = 324
+    inp = O.make_inputs(2, 3, S, 128, 128, seed=128 + S, dtype=torch.float32, with_states=states)
+    dev = torch.device("cuda:0")
+    t = {k: v.to(torch.bfloat16).to(dev) for k, v in inp.items()}
+    leaves = {k: t[k].detach().requires_grad_(True) for k in ("q", "k", "v", "i", "f")}
+    kw = {}
+    if states:
+        c0 = t["c0"].detach().requires_grad_(True)
+        kw = dict(c_initial=c0, n_initial=t["n0"], m_initial=t["m0"], return_last_states=True)
+    out = pkg.mlstm_chunkwise__b200(**leaves, chunk_size=4, reverse=reverse, autocast_kernel_dtype=torch.bfloat16, **kw)
+    n_before = pkg.last_launch_count()
+    if states:
+        h, (c_last, n_last, m_last) = out
+        torch.autograd.backward([h, c_last], [t["dh"], t["dc_last"].to(c_last.dtype)])
+    else:
+        h = out
+        h.backward(t["dh"])
+    torch.cuda.synchronize()
+    seq = ("q", "k", "v", "i", "f", "dh")
+    src = {k: (v.flip(2) if (reverse and k in seq) else v) for k, v in inp.items()}
+    want = _oracle(src, torch.bfloat16, L=4, states=states)
+    got = dict(h=h, dq=leaves["q"].grad, dk=leaves["k"].grad, dv=leaves["v"].grad, di=leaves["i"].grad, df=leaves["f"].grad)
+    for name in got:
+        w = want[name].flip(2) if reverse else want[name]
+        assert O.rel_err(got[name].double().cpu(), w) < 2e-2, (name, O.rel_err(got[name].double().cpu(), w))
+    if states:
+        assert O.rel_err(c0.grad.double().cpu(), want["dc0"]) < 2e-2
+    del n_before
+
+
+def test_d128_backward_matches_exact_family(pkg):
+    """Same call through the exact fp32 FFMA kernels (the route d = 128 backward took before) and the block route."""
+    inp = O.make_inputs(1, 2, 256, 128, 128, seed=3, dtype=torch.float32)
+    a = _run(pkg, inp, torch.bfloat16, impl="exact")
+    b = _run(pkg, inp, torch.bfloat16, impl="auto")
+    for k in a:
+        assert O.rel_err(b[k], a[k]) < 2e-2, k

@@ -2512,7 +2512,8 @@ int tensor_set_bw_variant(int variant) {
   return prev;
 }
 
-// forward: d = 32, 64 and 128; backward: d = 32 and 64 (d = 128 backward does not fit shared memory with 128-token tiles)
+// forward: d = 32, 64 and 128; backward: d = 32 and 64 (a d = 128 backward tile set does not fit shared memory with
+// 128-token tiles: the host splits that call into four d = 64 block problems, backend._bw_d128_by_blocks)
 bool tensor_supported(const mlstm_b200_shape& s, int backward) {
   if (s.dtype != MLSTM_B200_BF16 && s.dtype != MLSTM_B200_F16) return false;
   if (s.DHQK != s.DHHV) return false;
