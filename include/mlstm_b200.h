@@ -133,7 +133,9 @@ size_t mlstm_b200_workspace_bytes(const mlstm_b200_shape* shape, int backward);
 /* Bytes of the optional c_states buffer (0 when the selected kernels recompute the states). */
 size_t mlstm_b200_states_bytes(const mlstm_b200_shape* shape);
 
-/* 1 if the tensor-core (tcgen05) kernels cover this shape/dtype, else 0. */
+/* 1 if the tensor-core (tcgen05) kernels cover this shape/dtype forward AND backward, else 0
+ * (16-bit dtypes, DHQK == DHHV in {32, 64, 128}, S % 4 == 0; the head-dim-128 backward runs as four
+ * head-dim-64 block problems inside the call). */
 int mlstm_b200_tensor_path_supported(const mlstm_b200_shape* shape);
 
 /* Forward: h, n_out, m_out and optionally the last (C, n, m) states. */

@@ -524,7 +524,7 @@ def test_tiny_and_odd_shapes_on_tensor_path(pkg, B, NH, S, D):
 @pytest.mark.parametrize("reverse", [False, True], ids=["causal", "anticausal"])
 def test_d128_backward_by_blocks(pkg, states, reverse):
     """Head dim 128 (base384): forward on tc_fw_d128, backward as four 64 x 64 block problems on tc_bw<64>
-    (backend._bw_d128_by_blocks).  Every gradient, incl. dC_initial with dC_last, both scan directions, a ragged S."""
+    (bw128_by_blocks in csrc/tensor_kernels.cu, inside the C-ABI call).  Every gradient, incl. dC_initial with dC_last, both scan directions, a ragged S."""
     S = 324
     inp = O.make_inputs(2, 3, S, 128, 128, seed=128 + S, dtype=torch.float32, with_states=states)
     dev = torch.device("cuda:0")

@@ -160,10 +160,6 @@ def mlstm_chunkwise_bw(q, k, v, i, f, n_out, m_out, dh, c_initial=None, n_initia
     _check_inputs(q, k, v, i, f)
     B, NH, S, DK = q.shape
     DV = v.shape[-1]
-    if (DK == 128 and DV == 128 and q.dtype in (torch.float16, torch.bfloat16) and S % 4 == 0
-            and (_default_impl if impl is None else impl) != _cabi.IMPL_EXACT):
-        return _bw_d128_by_blocks(q, k, v, i, f, n_out, m_out, dh, c_initial, n_initial, m_initial, dc_last, qk_scale,
-                                  chunk_size, eps, want_dc_initial, reverse, siging, out)
     q, k, v = (_rowmajor_last(t) for t in (q, k, v))
     dh = _rowmajor_last(dh if dh.dtype == q.dtype else dh.to(q.dtype))
     i = i if i.dtype == q.dtype else i.to(q.dtype)
@@ -201,59 +197,6 @@ def mlstm_chunkwise_bw(q, k, v, i, f, n_out, m_out, dh, c_initial=None, n_initia
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws_bytes
         st = lib.mlstm_b200_chunkwise_bw(C.byref(a), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
         _cabi.check(st, "mlstm_b200_chunkwise_bw")
-    return dq, dk, dv, di, df, dc0
-
-
-def _bw_d128_by_blocks(q, k, v, i, f, n_out, m_out, dh, c_initial, n_initial, m_initial, dc_last, qk_scale, chunk_size,
-                       eps, want_dc_initial, reverse, siging, out):
-    """Head dim 128 backward (base384) on the d = 64 tcgen05 kernel.
-
-    With n_out and every max state held constant (the definition of this backward, native/bw.py:44-47) every term
-    of bw.py:106-203 is bilinear in (a 64-wide block of q / k, a 64-wide block of v / dh): dS = (dH V^T) . D and
-    S = (Q K^T) . D are sums over column blocks, the state gradient dC (dqk x dv) splits into four independent
-    64 x 64 blocks with the same decay, and the stabilisers depend on the gates only.  So the 128 x 128 problem is
-    the sum of four 64 x 64 ones on strided views of the same tensors (no copies; the TMA tensor maps take the
-    views as they are), each recomputing its block of the states (bw.py:251-266), with qk_scale = 128^-0.5.
-    (A 128-wide tile set does not fit the backward's shared memory with
-    128-token tiles; this route is ~25x faster than the exact fp32 family it replaces.)"""
-    B, NH, S, _ = q.shape
-    scale = 128 ** -0.5 if qk_scale is None else qk_scale
-    dh = dh if dh.dtype == q.dtype else dh.to(q.dtype)
-    blk = lambda t, j: None if t is None else t[..., 64 * j:64 * (j + 1)]  # noqa: E731
-    dev = q.device
-    if out is not None:
-        dq, dk, dv, di, df = out
-    else:
-        dq, dk, dv = (torch.empty(B, NH, S, 128, dtype=q.dtype, device=dev) for _ in range(3))
-        di, df = (torch.empty(B, NH, S, dtype=q.dtype, device=dev) for _ in range(2))
-    dc0 = torch.empty(B, NH, 128, 128, dtype=torch.float32, device=dev) if want_dc_initial else None
-    # The first partial of every output block is written by the kernel straight into its place (strided views of
-    # the outputs); later partials go to scratch and are added in one pass.
-    tq, tk, tv = (torch.empty(B, NH, S, 64, dtype=q.dtype, device=dev) for _ in range(3))
-    ti, tf = (torch.empty(B, NH, S, dtype=q.dtype, device=dev) for _ in range(2))
-    first = True
-    for a in range(2):
-        for b in range(2):
-            c0 = None if c_initial is None else c_initial[:, :, 64 * a:64 * (a + 1), 64 * b:64 * (b + 1)]
-            dcl = None if dc_last is None else dc_last[:, :, 64 * a:64 * (a + 1), 64 * b:64 * (b + 1)]
-            oq = blk(dq, a) if b == 0 else tq  # dq_a, dk_a: sum over the v blocks
-            ok = blk(dk, a) if b == 0 else tk
-            ov = blk(dv, b) if a == 0 else tv  # dv_b: sum over the qk blocks
-            r = mlstm_chunkwise_bw(blk(q, a), blk(k, a), blk(v, b), i, f, n_out, m_out, blk(dh, b), c0, blk(n_initial, a),
-                                   m_initial, dc_last=dcl, qk_scale=scale, chunk_size=chunk_size, eps=eps,
-                                   impl=_cabi.IMPL_TENSOR, want_dc_initial=want_dc_initial, c_states=None,
-                                   reverse=reverse, siging=siging, out=(oq, ok, ov, di if first else ti, df if first else tf))
-            if b == 1:
-                blk(dq, a).add_(tq)
-                blk(dk, a).add_(tk)
-            if a == 1:
-                blk(dv, b).add_(tv)
-            if not first:
-                di.add_(ti)
-                df.add_(tf)
-            if dc0 is not None:
-                dc0[:, :, 64 * a:64 * (a + 1), 64 * b:64 * (b + 1)] = r[5]
-            first = False
     return dq, dk, dv, di, df, dc0
 
 

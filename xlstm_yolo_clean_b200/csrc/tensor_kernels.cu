@@ -2503,6 +2503,173 @@ BwWs bw_ws(const mlstm_b200_shape& s) {
   return w;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Head dim 128 backward (640-base384) as four d = 64 block problems.
+//
+// With n_out and every max state held constant (the definition of this backward, native/bw.py:44-47) every term
+// of bw.py:106-203 is bilinear in (a 64-wide block of q / k, a 64-wide block of v / dh): dS = (dH V^T) . D and
+// S = (Q K^T) . D are sums over column blocks, the state gradient dC (dqk x dv) splits into four independent
+// 64 x 64 blocks with the same decay, and the stabilisers depend on the gates only.  A 128-wide tile set does not
+// fit the backward's shared memory with 128-token tiles, so the 128 x 128 problem runs as the sum of four
+// tc_bw<64> problems on strided views of the same tensors (no copies of q/k/v/dh; qk_scale = 128^-1/2; each
+// recomputes its block of the states, bw.py:251-266).  The first partial of every output block is written in place,
+// the second goes to scratch and is added in one pass.
+template <typename T>
+__global__ void k_acc_block64(T* __restrict__ dst, int64_t sb, int64_t sh, int64_t ss, const T* __restrict__ src, int NH,
+                              int S, int64_t n_vec) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // one 8-element (16-byte) vector per thread
+  if (idx >= n_vec) return;
+  const int64_t tok = idx >> 3;
+  const int part = (int)(idx & 7);
+  const int64_t s_ = tok % S, bh = tok / S, h_ = bh % NH, b_ = bh / NH;
+  uint4* d = reinterpret_cast<uint4*>(dst + b_ * sb + h_ * sh + s_ * ss + part * 8);
+  const uint4 y = *reinterpret_cast<const uint4*>(src + tok * 64 + part * 8);
+  uint4 x = *d;
+  uint32_t* xp = reinterpret_cast<uint32_t*>(&x);
+  const uint32_t* yp = reinterpret_cast<const uint32_t*>(&y);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 a = unpack2<T>(xp[e]), b = unpack2<T>(yp[e]);
+    xp[e] = pack2<T>(a.x + b.x, a.y + b.y);
+  }
+  *d = x;
+}
+template <typename T>
+__global__ void k_acc_vec(T* __restrict__ dst, int64_t sb, int64_t sh, int64_t ss, const T* __restrict__ src, int NH, int S,
+                          int64_t n) {
+  const int64_t tok = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (tok >= n) return;
+  const int64_t s_ = tok % S, bh = tok / S, h_ = bh % NH, b_ = bh / NH;
+  T* d = dst + b_ * sb + h_ * sh + s_ * ss;
+  *d = from_f32<T>(to_f32<T>(*d) + to_f32<T>(src[tok]));
+}
+// 64 x 64 block (a, b) of a (BH, 128, 128) fp32 state <-> contiguous (BH, 64, 64); vec: (BH, 128) <-> (BH, 64)
+__global__ void k_state_block(float* __restrict__ blk, float* __restrict__ full, int a, int b, int64_t n, int scatter) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int64_t bh = idx >> 12;
+  const int r = (int)((idx >> 6) & 63), c = (int)(idx & 63);
+  float* f = full + (bh * 128 + a * 64 + r) * 128 + b * 64 + c;
+  if (scatter) *f = blk[idx]; else blk[idx] = *f;
+}
+__global__ void k_state_vec_block(float* __restrict__ blk, const float* __restrict__ full, int a, int64_t n) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  blk[idx] = full[(idx >> 6) * 128 + a * 64 + (idx & 63)];
+}
+
+mlstm_b200_shape block_shape(const mlstm_b200_shape& s) {
+  mlstm_b200_shape b = s;
+  b.DHQK = b.DHHV = 64;
+  b.qk_scale = s.qk_scale > 0.f ? s.qk_scale : 1.f / sqrtf(128.f);
+  return b;
+}
+struct Bw128Ws {
+  size_t off_sub, sub_bytes, off_tq, off_tk, off_tv, off_ti, off_tf, off_c0, off_n0, off_dcl, off_dc0, total;
+};
+Bw128Ws bw128_ws(const mlstm_b200_shape& s) {
+  Bw128Ws w{};
+  const size_t tok = (size_t)s.B * s.NH * s.S, bh = (size_t)s.B * s.NH;
+  size_t o = 0;
+  w.sub_bytes = bw_ws(block_shape(s)).total;
+  w.off_sub = o; o += align_up(w.sub_bytes, 256);
+  w.off_tq = o; o += align_up(tok * 64 * 2, 256);
+  w.off_tk = o; o += align_up(tok * 64 * 2, 256);
+  w.off_tv = o; o += align_up(tok * 64 * 2, 256);
+  w.off_ti = o; o += align_up(tok * 2, 256);
+  w.off_tf = o; o += align_up(tok * 2, 256);
+  w.off_c0 = o; o += align_up(bh * 64 * 64 * 4, 256);
+  w.off_n0 = o; o += align_up(bh * 64 * 4, 256);
+  w.off_dcl = o; o += align_up(bh * 64 * 64 * 4, 256);
+  w.off_dc0 = o; o += align_up(bh * 64 * 64 * 4, 256);
+  w.total = o;
+  return w;
+}
+
+template <typename T>
+int bw128_by_blocks(const mlstm_b200_bw_args& a, cudaStream_t st) {
+  const mlstm_b200_shape& s = a.shape;
+  const Bw128Ws w = bw128_ws(s);
+  if (!a.workspace || a.workspace_bytes < w.total) {
+    set_error("workspace too small: need %zu bytes, got %zu", w.total, a.workspace_bytes);
+    return MLSTM_B200_EWORKSPACE;
+  }
+  char* ws = (char*)a.workspace;
+  const int64_t tok = (int64_t)s.B * s.NH * s.S, bh = (int64_t)s.B * s.NH;
+  auto dense = [&](size_t off, int width) {  // contiguous (B, NH, S, width) scratch tensor
+    mlstm_b200_tensor t{};
+    t.ptr = ws + off;
+    t.stride[0] = (int64_t)s.NH * s.S * width, t.stride[1] = (int64_t)s.S * width, t.stride[2] = width, t.stride[3] = 1;
+    return t;
+  };
+  auto cols = [&](const mlstm_b200_tensor& t, int j) {  // columns 64 j .. 64 j + 63 of a 128-wide tensor: a view
+    mlstm_b200_tensor v = t;
+    v.ptr = (char*)t.ptr + (size_t)j * 64 * sizeof(T);
+    return v;
+  };
+  mlstm_b200_tensor ti = dense(w.off_ti, 1), tf = dense(w.off_tf, 1);
+  ti.stride[0] = tf.stride[0] = (int64_t)s.NH * s.S, ti.stride[1] = tf.stride[1] = s.S, ti.stride[2] = tf.stride[2] = 1;
+  ti.stride[3] = tf.stride[3] = 0;
+  const int thr = 256;
+  int launches = 0;
+  bool first = true;
+  for (int qa = 0; qa < 2; ++qa) {
+    for (int vb = 0; vb < 2; ++vb) {
+      mlstm_b200_bw_args sub = a;
+      sub.shape = block_shape(s);
+      sub.q = cols(a.q, qa); sub.k = cols(a.k, qa); sub.v = cols(a.v, vb); sub.dh = cols(a.dh, vb);
+      sub.c_states = nullptr;  // every block recomputes its own slice of the states
+      sub.workspace = ws + w.off_sub; sub.workspace_bytes = w.sub_bytes;
+      if (a.c_initial) {
+        k_state_block<<<(unsigned)((bh * 4096 + thr - 1) / thr), thr, 0, st>>>((float*)(ws + w.off_c0), (float*)a.c_initial, qa, vb, bh * 4096, 0);
+        k_state_vec_block<<<(unsigned)((bh * 64 + thr - 1) / thr), thr, 0, st>>>((float*)(ws + w.off_n0), a.n_initial, qa, bh * 64);
+        sub.c_initial = (const float*)(ws + w.off_c0);
+        sub.n_initial = (const float*)(ws + w.off_n0);
+        launches += 2;
+      }
+      if (a.dc_last) {
+        k_state_block<<<(unsigned)((bh * 4096 + thr - 1) / thr), thr, 0, st>>>((float*)(ws + w.off_dcl), (float*)a.dc_last, qa, vb, bh * 4096, 0);
+        sub.dc_last = (const float*)(ws + w.off_dcl);
+        ++launches;
+      }
+      if (a.dc_initial) sub.dc_initial = (float*)(ws + w.off_dc0);
+      sub.dq = vb == 0 ? cols(a.dq, qa) : dense(w.off_tq, 64);  // dq_a, dk_a: sums over the v blocks
+      sub.dk = vb == 0 ? cols(a.dk, qa) : dense(w.off_tk, 64);
+      sub.dv = qa == 0 ? cols(a.dv, vb) : dense(w.off_tv, 64);  // dv_b: sum over the qk blocks
+      sub.di = first ? a.di : ti;
+      sub.df = first ? a.df : tf;
+      if (int e = tensor_bw(sub, st)) return e;
+      launches += 2;
+      const unsigned gv = (unsigned)((tok * 8 + thr - 1) / thr), gs = (unsigned)((tok + thr - 1) / thr);
+      if (vb == 1) {
+        const mlstm_b200_tensor dq = cols(a.dq, qa), dk = cols(a.dk, qa);
+        k_acc_block64<T><<<gv, thr, 0, st>>>((T*)dq.ptr, dq.stride[0], dq.stride[1], dq.stride[2], (const T*)(ws + w.off_tq), s.NH, s.S, tok * 8);
+        k_acc_block64<T><<<gv, thr, 0, st>>>((T*)dk.ptr, dk.stride[0], dk.stride[1], dk.stride[2], (const T*)(ws + w.off_tk), s.NH, s.S, tok * 8);
+        launches += 2;
+      }
+      if (qa == 1) {
+        const mlstm_b200_tensor dv = cols(a.dv, vb);
+        k_acc_block64<T><<<gv, thr, 0, st>>>((T*)dv.ptr, dv.stride[0], dv.stride[1], dv.stride[2], (const T*)(ws + w.off_tv), s.NH, s.S, tok * 8);
+        ++launches;
+      }
+      if (!first) {
+        k_acc_vec<T><<<gs, thr, 0, st>>>((T*)a.di.ptr, a.di.stride[0], a.di.stride[1], a.di.stride[2], (const T*)(ws + w.off_ti), s.NH, s.S, tok);
+        k_acc_vec<T><<<gs, thr, 0, st>>>((T*)a.df.ptr, a.df.stride[0], a.df.stride[1], a.df.stride[2], (const T*)(ws + w.off_tf), s.NH, s.S, tok);
+        launches += 2;
+      }
+      if (a.dc_initial) {
+        k_state_block<<<(unsigned)((bh * 4096 + thr - 1) / thr), thr, 0, st>>>((float*)(ws + w.off_dc0), a.dc_initial, qa, vb, bh * 4096, 1);
+        ++launches;
+      }
+      first = false;
+    }
+  }
+  MLSTM_CUDA_CHECK(cudaGetLastError());
+  count_launch(launches - 4);  // the four tensor_bw calls counted their own backward launch
+  return 0;
+}
+
 }  // namespace
 
 void tensor_set_clock_buffer(void* dev_ptr) { g_prof = (long long*)dev_ptr; }
@@ -2512,12 +2679,11 @@ int tensor_set_bw_variant(int variant) {
   return prev;
 }
 
-// forward: d = 32, 64 and 128; backward: d = 32 and 64 (a d = 128 backward tile set does not fit shared memory with
-// 128-token tiles: the host splits that call into four d = 64 block problems, backend._bw_d128_by_blocks)
+// forward: d = 32, 64 and 128; backward: d = 32 and 64 natively, d = 128 as four d = 64 block problems (bw128_by_blocks)
 bool tensor_supported(const mlstm_b200_shape& s, int backward) {
   if (s.dtype != MLSTM_B200_BF16 && s.dtype != MLSTM_B200_F16) return false;
   if (s.DHQK != s.DHHV) return false;
-  if (s.DHQK != 64 && s.DHQK != 32 && !(s.DHQK == 128 && !backward)) return false;
+  if (s.DHQK != 64 && s.DHQK != 32 && s.DHQK != 128) return false;  // d = 128 backward: four d = 64 block problems
   // Tiles are 128 tokens whatever chunk_size is (h and the states do not depend on it: the stabiliser equals the
   // step-recurrent one), and ragged last tiles are handled in-kernel (TMA zero-fill, gates masked at scan time),
   // so any S that keeps the fp32 n_out / m_out rows 16-byte aligned is covered; S % chunk_size == 0 is enforced
@@ -2527,13 +2693,16 @@ bool tensor_supported(const mlstm_b200_shape& s, int backward) {
 }
 
 size_t tensor_states_bytes(const mlstm_b200_shape& s) {
-  if (!tensor_supported(s, 1)) return 0;
+  if (!tensor_supported(s, 1) || s.DHQK == 128) return 0;  // the d = 128 block backward recomputes its states
   const size_t NT = (s.S + LT - 1) / LT;
   return (size_t)s.B * s.NH * NT * s.DHQK * s.DHQK * 2;
 }
 
 // forward needs no scratch; backward needs room to recompute the states when c_states is absent
-size_t tensor_workspace_bytes(const mlstm_b200_shape& s, int backward) { return backward ? bw_ws(s).total : 256; }
+size_t tensor_workspace_bytes(const mlstm_b200_shape& s, int backward) {
+  if (!backward) return 256;
+  return s.DHQK == 128 ? bw128_ws(s).total : bw_ws(s).total;
+}
 
 int tensor_fw(const mlstm_b200_fw_args& a, cudaStream_t st) { return run_fw(a, a.c_states, st); }
 
@@ -2543,6 +2712,8 @@ int tensor_bw(const mlstm_b200_bw_args& a, cudaStream_t st) {
     set_error("tensor path needs 16-byte aligned q/k/v/dh/dq/dk/dv with strides that are multiples of 8 elements");
     return MLSTM_B200_EUNSUPPORTED;
   }
+  if (s.DHQK == 128)
+    return s.dtype == MLSTM_B200_BF16 ? bw128_by_blocks<__nv_bfloat16>(a, st) : bw128_by_blocks<__half>(a, st);
   const void* c_states = a.c_states;
   if (!c_states) {  // recompute the states with a forward pass into the workspace (bw.py:251-266)
     BwWs w = bw_ws(s);
