@@ -189,9 +189,11 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL writes its version banner to STDOUT at NCCL_DEBUG=VERSION; stdout carries the one JSON line only
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL writes its version banner / debug lines to STDOUT when NCCL_DEBUG is set in the environment (the GPU
+        # boxes export it); stdout carries the one JSON line only, so NCCL's output goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")
         dist.init_process_group("nccl", device_id=dev)
         dist.barrier()
     import xlstm_yolo_clean_b200 as pkg
