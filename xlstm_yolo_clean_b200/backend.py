@@ -47,9 +47,39 @@ def _tensor(t: Optional[torch.Tensor]) -> _cabi.Tensor:
         out.ptr = None
         return out
     out.ptr = t.data_ptr()
-    for d, s in enumerate(t.stride()):
-        out.stride[d] = s
+    st = t.stride()
+    out.stride[:len(st)] = st
     return out
+
+
+class _on_device:
+    """``torch.cuda.device(dev)`` only when ``dev`` is not already current (the common case costs nothing)."""
+
+    __slots__ = ("ctx",)
+
+    def __init__(self, dev):
+        self.ctx = None if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+
+
+_BYTES_CACHE: dict = {}
+
+
+def _scratch_bytes(lib, shape: "_cabi.Shape", backward: int, want_states: bool):
+    """(workspace bytes, states bytes) of a shape; the two C-ABI queries are cached per shape key."""
+    key = (shape.B, shape.NH, shape.S, shape.DHQK, shape.DHHV, shape.chunk_size, shape.dtype, shape.impl, backward)
+    r = _BYTES_CACHE.get(key)
+    if r is None:
+        r = (lib.mlstm_b200_workspace_bytes(C.byref(shape), backward), lib.mlstm_b200_states_bytes(C.byref(shape)))
+        _BYTES_CACHE[key] = r
+    return r[0], (r[1] if want_states else 0)
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -122,7 +152,7 @@ def mlstm_chunkwise_fw(q, k, v, i, f, c_initial=None, n_initial=None, m_initial=
         c0 = torch.zeros(B, NH, DK, DV, device=dev) if c0 is None else c0
         n0 = torch.zeros(B, NH, DK, device=dev) if n0 is None else n0
         m0 = torch.zeros(B, NH, device=dev) if m0 is None else m0
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         h = torch.empty(B, NH, S, DV, dtype=q.dtype, device=dev)
         n_out = torch.empty(B, NH, S, dtype=torch.float32, device=dev)
         m_out = torch.empty(B, NH, S, dtype=torch.float32, device=dev)
@@ -133,9 +163,8 @@ def mlstm_chunkwise_fw(q, k, v, i, f, c_initial=None, n_initial=None, m_initial=
                     torch.empty(B, NH, 1, dtype=torch.float32, device=dev))
         a = _cabi.FwArgs()
         a.shape = _shape(q, v, chunk_size, eps, impl, qk_scale, reverse, siging)
-        ws_bytes = lib.mlstm_b200_workspace_bytes(C.byref(a.shape), 0)
+        ws_bytes, st_bytes = _scratch_bytes(lib, a.shape, 0, save_states)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        st_bytes = lib.mlstm_b200_states_bytes(C.byref(a.shape)) if save_states else 0
         c_states = torch.empty(st_bytes, dtype=torch.uint8, device=dev) if st_bytes else None
         a.c_states = _ptr(c_states)
         a.q, a.k, a.v, a.i, a.f, a.h = (_tensor(t) for t in (q, k, v, i, f, h))
@@ -171,7 +200,7 @@ def mlstm_chunkwise_bw(q, k, v, i, f, n_out, m_out, dh, c_initial=None, n_initia
         n0 = torch.zeros(B, NH, DK, device=dev) if n0 is None else n0
         m0 = torch.zeros(B, NH, device=dev) if m0 is None else m0
     dcl = _state_f32(dc_last, (B, NH, DK, DV))
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         if out is not None:
             dq, dk, dv, di, df = out
             assert dq.shape == q.shape and dk.shape == k.shape and dv.shape == v.shape and di.shape == i.shape
@@ -185,7 +214,7 @@ def mlstm_chunkwise_bw(q, k, v, i, f, n_out, m_out, dh, c_initial=None, n_initia
         dc0 = torch.empty(B, NH, DK, DV, dtype=torch.float32, device=dev) if want_dc_initial else None
         a = _cabi.BwArgs()
         a.shape = _shape(q, v, chunk_size, eps, impl, qk_scale, reverse, siging)
-        ws_bytes = lib.mlstm_b200_workspace_bytes(C.byref(a.shape), 1)
+        ws_bytes, _ = _scratch_bytes(lib, a.shape, 1, False)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         a.q, a.k, a.v, a.i, a.f, a.dh = (_tensor(t) for t in (q, k, v, i, f, dh))
         a.c_initial, a.n_initial, a.m_initial = _ptr(c0), _ptr(n0), _ptr(m0)

@@ -19,7 +19,10 @@
 //   C_k    = gbar C_{k-1} + dC          fp32 registers (the only sequential dependency)
 // h and the final states do not depend on the tile length (m_t equals the step-recurrent
 // stabiliser), so a 128-token tile is used although the API chunk size is 64.
+#include <mutex>
+#include <set>
 #include <type_traits>
+#include <utility>
 
 #include "common.cuh"
 #include "sm100.cuh"
@@ -2350,6 +2353,27 @@ int num_sms() {
   return n;
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) instead of on every launch
+// (a runtime call of a few microseconds on the host path of a launch-bound training step)
+template <typename K>
+cudaError_t ensure_smem(K kern, int bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> done;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const std::pair<const void*, int> key(reinterpret_cast<const void*>(kern), dev);
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (done.count(key)) return cudaSuccess;
+  }
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) {
+    std::lock_guard<std::mutex> g(mu);
+    done.insert(key);
+  }
+  return e;
+}
+
 // Programmatic dependent launch for the two main kernels (tc_fw, tc_bw): the next kernel's CTAs may become resident
 // while this one drains; they block in griddepcontrol.wait before touching memory.  MLSTM_B200_PDL=0 disables it.
 int pdl_mode() {  // 0 off, 1 forward and backward, 2 forward only
@@ -2377,7 +2401,7 @@ int launch_fw(const TcFwParams& p, const CUtensorMap& mq, const CUtensorMap& mk,
               const CUtensorMap& mh, const CUtensorMap& mcs, cudaStream_t st) {
   using SM = FwSmem<D>;
   auto kern = p.rev ? tc_fw<T, D, true> : tc_fw<T, D, false>;
-  MLSTM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
+  MLSTM_CUDA_CHECK(ensure_smem(kern, SM::kBytes));
   MLSTM_CUDA_CHECK(launch_pdl(pdl_mode() != 0, kern, p.B * p.NH, kTcThreads, SM::kBytes, st, mq, mk, mv, mh, mcs, p));
   count_launch();
   MLSTM_CUDA_CHECK(cudaGetLastError());
@@ -2388,7 +2412,7 @@ template <typename T>
 int launch_fw_d128(const TcFwParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
                    const CUtensorMap& mh, cudaStream_t st) {
   auto kern = p.rev ? tc_fw_d128<T, true> : tc_fw_d128<T, false>;
-  MLSTM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FwSmem128::kBytes));
+  MLSTM_CUDA_CHECK(ensure_smem(kern, FwSmem128::kBytes));
   kern<<<p.B * p.NH, kTcThreads, FwSmem128::kBytes, st>>>(mq, mk, mv, mh, p);
   count_launch();
   MLSTM_CUDA_CHECK(cudaGetLastError());
@@ -2401,7 +2425,7 @@ int launch_bw2(const TcBwParams& p, const CUtensorMap& mq, const CUtensorMap& mk
                const CUtensorMap& mdv, cudaStream_t st) {
   using SM = Bw2Smem<D>;
   auto kern = p.rev ? tc_bw2<T, D, true> : tc_bw2<T, D, false>;
-  MLSTM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
+  MLSTM_CUDA_CHECK(ensure_smem(kern, SM::kBytes));
   kern<<<p.B * p.NH, kTcThreads, SM::kBytes, st>>>(mq, mk, mv, mdh, mcs, mdq, mdk, mdv, p);
   MLSTM_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -2425,7 +2449,7 @@ int launch_bw(const TcBwParams& p, const CUtensorMap& mq, const CUtensorMap& mk,
   if (bw_variant() == 2) return launch_bw2<T, D>(p, mq, mk, mv, mdh, mcs, mdq, mdk, mdv, st);
   using SM = BwSmem<D>;
   auto kern = p.rev ? tc_bw<T, D, true> : tc_bw<T, D, false>;
-  MLSTM_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kBytes));
+  MLSTM_CUDA_CHECK(ensure_smem(kern, SM::kBytes));
   MLSTM_CUDA_CHECK(launch_pdl(pdl_mode() == 1, kern, p.B * p.NH, kTcThreads, SM::kBytes, st, mq, mk, mv, mdh, mcs, mdq, mdk, mdv, p));
   MLSTM_CUDA_CHECK(cudaGetLastError());
   return 0;

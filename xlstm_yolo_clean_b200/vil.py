@@ -25,7 +25,7 @@ import torch.nn.functional as F
 from . import _cabi
 from torch.amp import custom_bwd, custom_fwd
 
-from .backend import (_DTYPES, _tensor, mlstm_chunkwise__b200, mlstm_chunkwise_bw, mlstm_chunkwise_fw,
+from .backend import (_DTYPES, _on_device, _tensor, mlstm_chunkwise__b200, mlstm_chunkwise_bw, mlstm_chunkwise_fw,
                       mlstm_siging_chunkwise__b200, tensor_path_supported)
 
 
@@ -54,7 +54,7 @@ class _CellOut(torch.autograd.Function):
         if x is not None:  # x, y, dy, dx all move as dense (B, S, H) rows
             x = x if (x.dtype == out_dtype and x.is_contiguous() and x.data_ptr() % 16 == 0) else x.to(out_dtype).contiguous()
         w32, b32, s32 = _f32c(weight), _f32c(bias), _f32c(skip)
-        with torch.cuda.device(h.device):
+        with _on_device(h.device):
             y = torch.empty(B, S, NH * D, dtype=out_dtype, device=h.device)
             a = _cabi.CellOutArgs()
             a.B, a.NH, a.S, a.D = B, NH, S, D
@@ -78,7 +78,7 @@ class _CellOut(torch.autograd.Function):
         dy = dy if (dy.dtype == ctx.out_dtype and dy.is_contiguous() and dy.data_ptr() % 16 == 0) else dy.to(ctx.out_dtype).contiguous()
         w32, s32 = _f32c(weight), _f32c(skip)
         dev = h.device
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             dh = torch.empty_strided(h.shape, h.stride(), dtype=h.dtype, device=dev)  # the kernel walks h and dh together
             dx = torch.empty_like(dy) if (x is not None and ctx.needs_input_grad[4]) else None
             dpar = torch.empty(3, NH * D, dtype=torch.float32, device=dev)
