@@ -562,3 +562,21 @@ def test_d128_backward_matches_exact_family(pkg):
     b = _run(pkg, inp, torch.bfloat16, impl="auto")
     for k in a:
         assert O.rel_err(b[k], a[k]) < 2e-2, k
+
+
+@pytest.mark.parametrize("reverse", [False, True], ids=["causal", "anticausal"])
+def test_d128_backward_recompute_equals_saved_states(pkg, reverse):
+    """The head-dim-128 backward with the forward's saved block states and without them (each block problem then
+    recomputes its slice, bw.py:251-266) must agree bit for bit: the saved states ARE what the recompute produces."""
+    dev = torch.device("cuda:0")
+    inp = O.make_inputs(2, 2, 388, 128, 128, seed=9, dtype=torch.float32, with_states=True)
+    t = {k: v.to(torch.bfloat16).to(dev) for k, v in inp.items()}
+    kw = dict(c_initial=t["c0"], n_initial=t["n0"], m_initial=t["m0"])
+    h, n_out, m_out, _, cst = pkg.mlstm_chunkwise_fw(t["q"], t["k"], t["v"], t["i"], t["f"], chunk_size=4, reverse=reverse, **kw)
+    assert cst is not None
+    a = pkg.mlstm_chunkwise_bw(t["q"], t["k"], t["v"], t["i"], t["f"], n_out, m_out, t["dh"], chunk_size=4, c_states=cst,
+                               reverse=reverse, want_dc_initial=True, dc_last=t["dc_last"], **kw)
+    b = pkg.mlstm_chunkwise_bw(t["q"], t["k"], t["v"], t["i"], t["f"], n_out, m_out, t["dh"], chunk_size=4, c_states=None,
+                               reverse=reverse, want_dc_initial=True, dc_last=t["dc_last"], **kw)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)

@@ -773,7 +773,8 @@ struct FwSmem128 {
 template <typename T, bool REV>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_fw_d128(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
-           const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapH, TcFwParams p) {
+           const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapH,
+           const __grid_constant__ CUtensorMap mapCs, TcFwParams p) {
   constexpr int D = 128;
   constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
   using SM = FwSmem128;
@@ -870,13 +871,30 @@ tc_fw_d128(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUt
                  umma_desc_advance(dK, (kk / 4) * SM::kTile + (kk % 4) * 32), id_kk, kk > 0);
       umma_commit(&bar_s);
     };
-    if (lane == 0) load_tile(0);
+    // State entering tile c, for the backward: the 16-bit operand copy of C is stored as its four 64 x 64 blocks
+    // (block = 2 * (dqk half) + (dv half)), 256 rows of 64 columns per tile, which is what the four head-dim-64
+    // block problems of the backward load (bw128_by_blocks).  sC holds two [128][64] column halves; a block is
+    // 64 consecutive rows (8 KB) of one half.
+    auto store_state = [&](int c) {
+#pragma unroll
+      for (int blk = 0; blk < 4; ++blk)
+        tma_store_4d(&mapCs, sC + (blk & 1) * SM::kTile + (blk >> 1) * 8192, 0, mt(c) * 256 + blk * 64, hh, b);
+    };
+    if (lane == 0) {
+      if (p.store_states) {
+        store_state(0);
+        tma_store_commit();
+      }
+      load_tile(0);
+    }
     __syncwarp();
     if (elect_one()) issue_s(0);
     __syncwarp();
     for (int c = 0; c < p.NT; ++c) {
       const uint32_t par = c & 1;
       named_sync(NB_B, kNbAB);  // P(c) written
+      if (c == 0 && lane == 0) tma_store_wait_read<0>();  // the initial-state store has read sC (rewritten after bar_h)
+      __syncwarp();
       if (elect_one()) {
         tc_fence_after_sync();
 #pragma unroll
@@ -905,6 +923,7 @@ tc_fw_d128(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUt
       if (lane == 0) {
         tma_store_4d(&mapH, sH, 0, mt(c) * LT, hh, b);
         tma_store_4d(&mapH, sH + SM::kTile, 64, mt(c) * LT, hh, b);
+        if (p.store_states && c + 1 < p.NT) store_state(c + 1);  // C_k = state entering tile c+1
         tma_store_commit();
         tma_store_wait_read<0>();  // the staging tile aliases P: it must be drained before bar_s(c+1) completes
       }
@@ -1121,6 +1140,9 @@ struct TcBwParams {
   float* dc0;
   int rev;  // 1: the forward ran anti-causally; this sweep then walks the memory tiles in ascending order
   int sig;  // 1: sigmoid input gate (m_out is all zeros, dI picks up sigmoid(-i))
+  // rows of the saved-states matrix per 128-token tile and row offset of this problem's D x D block inside a tile:
+  // (D, 0) normally; (256, 64 * block) when a head-dim-128 backward runs as four head-dim-64 block problems
+  int cs_rows, cs_off;
   long long* prof;
 };
 
@@ -1198,7 +1220,7 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
     tma_load_4d(base + SM::oK, &mapK, &bar_full[s], 0, mt(c) * LT, hh, b);
     tma_load_4d(base + SM::oV, &mapV, &bar_full[s], 0, mt(c) * LT, hh, b);
     tma_load_4d(base + SM::odH, &mapdH, &bar_full[s], 0, mt(c) * LT, hh, b);
-    tma_load_4d(base + SM::oCs, &mapCs, &bar_full[s], 0, mt(c) * D, hh, b);
+    tma_load_4d(base + SM::oCs, &mapCs, &bar_full[s], 0, mt(c) * p.cs_rows + p.cs_off, hh, b);
   };
   // cold start: the first input tiles are requested before anything else happens in the CTA (grid-dependency
   // waits: see tc_fw)
@@ -1310,7 +1332,7 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
         tma_prefetch_4d(&mapK, 0, r, hh, b);
         tma_prefetch_4d(&mapV, 0, r, hh, b);
         tma_prefetch_4d(&mapdH, 0, r, hh, b);
-        tma_prefetch_4d(&mapCs, 0, mt(c - 1) * D, hh, b);
+        tma_prefetch_4d(&mapCs, 0, mt(c - 1) * p.cs_rows + p.cs_off, hh, b);
       }
       named_sync(NB_B, kNbAB);  // Sb', dS written
       TC_PROF(it, 10);
@@ -1366,7 +1388,7 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
             tma_load_4d(sQ, &mapQ, &bar_full[0], 0, r, hh, b);
             tma_load_4d(sV, &mapV, &bar_full[0], 0, r, hh, b);
             mbar_wait(&bar_q, par, 24);
-            tma_load_4d(sCs, &mapCs, &bar_full[0], 0, mt(c - 1) * D, hh, b);
+            tma_load_4d(sCs, &mapCs, &bar_full[0], 0, mt(c - 1) * p.cs_rows + p.cs_off, hh, b);
             mbar_wait(&bar_b, par, 22);
             tma_load_4d(sK, &mapK, &bar_full[0], 0, r, hh, b);
             mbar_wait(&bar_v, par, 25);
@@ -2410,10 +2432,10 @@ int launch_fw(const TcFwParams& p, const CUtensorMap& mq, const CUtensorMap& mk,
 
 template <typename T>
 int launch_fw_d128(const TcFwParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
-                   const CUtensorMap& mh, cudaStream_t st) {
+                   const CUtensorMap& mh, const CUtensorMap& mcs, cudaStream_t st) {
   auto kern = p.rev ? tc_fw_d128<T, true> : tc_fw_d128<T, false>;
   MLSTM_CUDA_CHECK(ensure_smem(kern, FwSmem128::kBytes));
-  kern<<<p.B * p.NH, kTcThreads, FwSmem128::kBytes, st>>>(mq, mk, mv, mh, p);
+  kern<<<p.B * p.NH, kTcThreads, FwSmem128::kBytes, st>>>(mq, mk, mv, mh, mcs, p);
   count_launch();
   MLSTM_CUDA_CHECK(cudaGetLastError());
   return 0;
@@ -2472,6 +2494,13 @@ int make_states_map(CUtensorMap* m, const void* ptr, const mlstm_b200_shape& s) 
                                    (int64_t)NT * D * D, D, D, D);
 }
 
+// head dim 128: (B, NH, NT * 256, 64) -- four 64 x 64 blocks per tile (see tc_fw_d128::store_state)
+int make_states_map_blocks(CUtensorMap* m, const void* ptr, const mlstm_b200_shape& s) {
+  const int NT = (s.S + LT - 1) / LT;
+  return sm100_host::make_map_bhsd(m, ptr, s.dtype == MLSTM_B200_BF16, s.B, s.NH, NT * 256, 64, (int64_t)s.NH * NT * 256 * 64,
+                                   (int64_t)NT * 256 * 64, 64, 64, 64);
+}
+
 int run_fw(const mlstm_b200_fw_args& a, void* c_states, cudaStream_t st) {
   const mlstm_b200_shape& s = a.shape;
   if (!tma_ok(a.q) || !tma_ok(a.k) || !tma_ok(a.v) || !tma_ok(a.h)) {
@@ -2482,7 +2511,8 @@ int run_fw(const mlstm_b200_fw_args& a, void* c_states, cudaStream_t st) {
   int r = make_map(&mq, a.q, s, s.DHQK) | make_map(&mk, a.k, s, s.DHQK) | make_map(&mv, a.v, s, s.DHHV) |
           make_map(&mh, a.h, s, s.DHHV);
   // without a c_states buffer the map is never used by the kernel; point it at h to keep it valid
-  r |= (c_states && s.DHQK <= 64) ? make_states_map(&mcs, c_states, s) : make_map(&mcs, a.h, s, s.DHHV);
+  r |= !c_states ? make_map(&mcs, a.h, s, s.DHHV)
+                 : s.DHQK == 128 ? make_states_map_blocks(&mcs, c_states, s) : make_states_map(&mcs, c_states, s);
   if (r) {
     set_error("cuTensorMapEncodeTiled failed (%d)", r);
     return MLSTM_B200_ENODEVICE;
@@ -2501,9 +2531,8 @@ int run_fw(const mlstm_b200_fw_args& a, void* c_states, cudaStream_t st) {
   p.store_states = c_states != nullptr;
   p.prof = g_prof;
   if (s.DHQK == 128) {
-    p.store_states = 0;  // the d=128 backward runs on the exact family, which recomputes its states
-    if (s.dtype == MLSTM_B200_BF16) return launch_fw_d128<__nv_bfloat16>(p, mq, mk, mv, mh, st);
-    return launch_fw_d128<__half>(p, mq, mk, mv, mh, st);
+    if (s.dtype == MLSTM_B200_BF16) return launch_fw_d128<__nv_bfloat16>(p, mq, mk, mv, mh, mcs, st);
+    return launch_fw_d128<__half>(p, mq, mk, mv, mh, mcs, st);
   }
   if (s.DHQK == 32) {
     if (s.dtype == MLSTM_B200_BF16) return launch_fw<__nv_bfloat16, 32>(p, mq, mk, mv, mh, mcs, st);
@@ -2583,6 +2612,10 @@ __global__ void k_state_vec_block(float* __restrict__ blk, const float* __restri
   blk[idx] = full[(idx >> 6) * 128 + a * 64 + (idx & 63)];
 }
 
+}  // namespace
+int run_bw(const mlstm_b200_bw_args& a, const void* c_states, int block, cudaStream_t st);
+namespace {
+
 mlstm_b200_shape block_shape(const mlstm_b200_shape& s) {
   mlstm_b200_shape b = s;
   b.DHQK = b.DHHV = 64;
@@ -2643,9 +2676,12 @@ int bw128_by_blocks(const mlstm_b200_bw_args& a, cudaStream_t st) {
       mlstm_b200_bw_args sub = a;
       sub.shape = block_shape(s);
       sub.q = cols(a.q, qa); sub.k = cols(a.k, qa); sub.v = cols(a.v, vb); sub.dh = cols(a.dh, vb);
-      sub.c_states = nullptr;  // every block recomputes its own slice of the states
+      // With the forward's saved states (tc_fw_d128 stores them block-wise) every problem loads its block; without
+      // them -- or for the transposed variant, which keeps its own coordinates -- it recomputes its slice.
+      const bool saved = a.c_states != nullptr && bw_variant() == 1;
+      sub.c_states = nullptr;
       sub.workspace = ws + w.off_sub; sub.workspace_bytes = w.sub_bytes;
-      if (a.c_initial) {
+      if (a.c_initial && !saved) {
         k_state_block<<<(unsigned)((bh * 4096 + thr - 1) / thr), thr, 0, st>>>((float*)(ws + w.off_c0), (float*)a.c_initial, qa, vb, bh * 4096, 0);
         k_state_vec_block<<<(unsigned)((bh * 64 + thr - 1) / thr), thr, 0, st>>>((float*)(ws + w.off_n0), a.n_initial, qa, bh * 64);
         sub.c_initial = (const float*)(ws + w.off_c0);
@@ -2663,8 +2699,11 @@ int bw128_by_blocks(const mlstm_b200_bw_args& a, cudaStream_t st) {
       sub.dv = qa == 0 ? cols(a.dv, vb) : dense(w.off_tv, 64);  // dv_b: sum over the qk blocks
       sub.di = first ? a.di : ti;
       sub.df = first ? a.df : tf;
-      if (int e = tensor_bw(sub, st)) return e;
-      launches += 2;
+      if (saved) {
+        if (int e = run_bw(sub, a.c_states, 2 * qa + vb, st)) return e;
+      } else {
+        if (int e = tensor_bw(sub, st)) return e;
+      }
       const unsigned gv = (unsigned)((tok * 8 + thr - 1) / thr), gs = (unsigned)((tok + thr - 1) / thr);
       if (vb == 1) {
         const mlstm_b200_tensor dq = cols(a.dq, qa), dk = cols(a.dk, qa);
@@ -2690,7 +2729,7 @@ int bw128_by_blocks(const mlstm_b200_bw_args& a, cudaStream_t st) {
     }
   }
   MLSTM_CUDA_CHECK(cudaGetLastError());
-  count_launch(launches - 4);  // the four tensor_bw calls counted their own backward launch
+  count_launch(launches);  // the block problems counted their own launches
   return 0;
 }
 
@@ -2717,7 +2756,7 @@ bool tensor_supported(const mlstm_b200_shape& s, int backward) {
 }
 
 size_t tensor_states_bytes(const mlstm_b200_shape& s) {
-  if (!tensor_supported(s, 1) || s.DHQK == 128) return 0;  // the d = 128 block backward recomputes its states
+  if (!tensor_supported(s, 1)) return 0;
   const size_t NT = (s.S + LT - 1) / LT;
   return (size_t)s.B * s.NH * NT * s.DHQK * s.DHQK * 2;
 }
@@ -2757,11 +2796,18 @@ int tensor_bw(const mlstm_b200_bw_args& a, cudaStream_t st) {
     if (int e = run_fw(f, ws + w.off_states, st)) return e;
     c_states = ws + w.off_states;
   }
+  return run_bw(a, c_states, -1, st);
+}
+
+// block < 0: c_states holds this problem's own (B, NH, NT, D, D) states.  block = 0..3: c_states is the head-dim-128
+// forward's buffer (four 64 x 64 blocks per tile) and this head-dim-64 problem reads block `block` of every tile.
+int run_bw(const mlstm_b200_bw_args& a, const void* c_states, int block, cudaStream_t st) {
+  const mlstm_b200_shape& s = a.shape;
   CUtensorMap mq, mk, mv, mdh, mcs, mdq, mdk, mdv;
   const int D = s.DHQK;
   int r = make_map(&mq, a.q, s, D) | make_map(&mk, a.k, s, D) | make_map(&mv, a.v, s, D) | make_map(&mdh, a.dh, s, D) |
-          make_states_map(&mcs, c_states, s) | make_map(&mdq, a.dq, s, D) | make_map(&mdk, a.dk, s, D) |
-          make_map(&mdv, a.dv, s, D);
+          (block < 0 ? make_states_map(&mcs, c_states, s) : make_states_map_blocks(&mcs, c_states, s)) |
+          make_map(&mdq, a.dq, s, D) | make_map(&mdk, a.dk, s, D) | make_map(&mdv, a.dv, s, D);
   if (r) {
     set_error("cuTensorMapEncodeTiled failed (%d)", r);
     return MLSTM_B200_ENODEVICE;
@@ -2779,6 +2825,8 @@ int tensor_bw(const mlstm_b200_bw_args& a, cudaStream_t st) {
   p.dc0 = a.dc_initial;
   p.rev = s.reverse ? 1 : 0;
   p.sig = s.siging ? 1 : 0;
+  p.cs_rows = block < 0 ? D : 256;
+  p.cs_off = block < 0 ? 0 : 64 * block;
   p.prof = g_prof ? g_prof + 4096 : nullptr;
   int e;
   if (s.DHQK == 32)
