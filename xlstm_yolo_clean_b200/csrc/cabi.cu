@@ -50,12 +50,15 @@ int require_device() {
   // The tensor maps are encoded through the DRIVER API, which needs the device's primary context bound to the
   // calling thread.  A fresh thread -- e.g. PyTorch's autograd thread running the first backward of a process,
   // with its allocations served from the caching allocator -- may not have made a runtime call that binds it yet.
+  // (cudaFree(0) binds it; it is only issued when no context is current, so never inside a stream capture.)
   static thread_local int bound_dev = -1;
   if (bound_dev != dev) {
-    e = cudaFree(0);
-    if (e != cudaSuccess) {
-      set_error("cannot bind the CUDA context of device %d: %s", dev, cudaGetErrorString(e));
-      return MLSTM_B200_ENODEVICE;
+    if (!tensor_context_is_current()) {
+      e = cudaFree(0);
+      if (e != cudaSuccess) {
+        set_error("cannot bind the CUDA context of device %d: %s", dev, cudaGetErrorString(e));
+        return MLSTM_B200_ENODEVICE;
+      }
     }
     bound_dev = dev;
   }

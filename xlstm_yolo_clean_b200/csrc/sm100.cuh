@@ -307,6 +307,22 @@ inline EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// true if a CUDA context is current on the calling thread (driver-level query: the runtime never says)
+inline bool context_is_current() {
+  typedef CUresult (*CtxGetCurrentFn)(CUcontext*);
+  static CtxGetCurrentFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuCtxGetCurrent", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (CtxGetCurrentFn)p;
+  }
+  if (!fn) return false;
+  CUcontext ctx = nullptr;
+  return fn(&ctx) == CUDA_SUCCESS && ctx != nullptr;
+}
+
 // 4-D map over a (B, NH, S, D) 16-bit tensor with element strides (sb, sh, ss, 1);
 // box = (64 cols, box_rows, 1, 1), 128B swizzle, out-of-bounds rows read as zero / are not written.
 // box_cols = 64 -> 128B swizzle (default); box_cols = 32 -> 64B swizzle (head dim 32).

@@ -2736,6 +2736,7 @@ int bw128_by_blocks(const mlstm_b200_bw_args& a, cudaStream_t st) {
 }  // namespace
 
 void tensor_set_clock_buffer(void* dev_ptr) { g_prof = (long long*)dev_ptr; }
+bool tensor_context_is_current() { return sm100_host::context_is_current(); }
 int tensor_set_bw_variant(int variant) {
   const int prev = bw_variant();
   if (variant == 1 || variant == 2) g_bw_variant = variant;
