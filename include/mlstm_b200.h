@@ -207,6 +207,37 @@ size_t mlstm_b200_cellout_workspace_bytes(const mlstm_b200_cellout_args* args);
 int mlstm_b200_cellout_fw(const mlstm_b200_cellout_args* args, void* cuda_stream);
 int mlstm_b200_cellout_bw(const mlstm_b200_cellout_bw_args* args, void* cuda_stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * RMSNorm in front of the branch: ViLLayer.norm / .ffn_norm = nn.RMSNorm(dim, eps=1e-6, elementwise_affine)
+ * (vision_lstm2.py:277-278, applied at :318-327).  y = round_x(x * rsqrt(mean(x^2) + eps)) * weight over the last
+ * dimension of a dense (rows, C) matrix -- the rounding of the normalised row to the input dtype is what torch's
+ * composite rms_norm does when input and weight dtypes differ (fp16 autocast).  rstd (rows) fp32 is written by the
+ * forward and read by the backward.  C in {192, 256, 384, 512}; x / dx of x_dtype, y / dy of y_dtype.
+ */
+typedef struct mlstm_b200_rmsnorm_args {
+  int64_t rows;
+  int32_t C;
+  int32_t x_dtype, y_dtype;
+  float eps;
+  const void* x;
+  void* y;             /* out (forward) */
+  const float* weight; /* (C) fp32 or NULL (= 1) */
+  float* rstd;         /* (rows) fp32: out (forward), in (backward) */
+} mlstm_b200_rmsnorm_args;
+
+typedef struct mlstm_b200_rmsnorm_bw_args {
+  mlstm_b200_rmsnorm_args fw; /* x, weight, rstd as in the forward (y is ignored) */
+  const void* dy;
+  void* dx;                   /* out, x_dtype */
+  float* dweight;             /* out (C) fp32, optional */
+  void* workspace;            /* mlstm_b200_rmsnorm_workspace_bytes() bytes */
+  size_t workspace_bytes;
+} mlstm_b200_rmsnorm_bw_args;
+
+size_t mlstm_b200_rmsnorm_workspace_bytes(const mlstm_b200_rmsnorm_args* args);
+int mlstm_b200_rmsnorm_fw(const mlstm_b200_rmsnorm_args* args, void* cuda_stream);
+int mlstm_b200_rmsnorm_bw(const mlstm_b200_rmsnorm_bw_args* args, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -144,6 +144,9 @@ class _Layer(torch.nn.Module):
         self.mlstm_cell = _Cell(inner, NH)
         self.learnable_skip = torch.nn.Parameter(1.0 + 0.1 * torch.randn(inner))
         self.proj_down = torch.nn.Linear(inner, dim)
+        self.norm = torch.nn.RMSNorm(dim, eps=1e-6)
+        with torch.no_grad():
+            self.norm.weight.add_(0.1 * torch.randn(dim))
 
 
 def _reference_branch(pkg, layer, x, reverse):
@@ -197,7 +200,7 @@ def test_flip_free_branch_matches_reference_composition(pkg, S, reverse):
         xi = x.clone().requires_grad_(True)
         out = fn(xi)
         out.backward(dout)
-        grads = {n: p.grad.clone() for n, p in layer.named_parameters()}
+        grads = {n: p.grad.clone() for n, p in layer.named_parameters() if p.grad is not None}  # (norm is not on the branch)
         return out.detach(), xi.grad.clone(), grads
 
     o_ref, dx_ref, g_ref = run(lambda xi: _reference_branch(pkg, layer, xi, reverse))
@@ -225,8 +228,8 @@ def test_patch_layers_rebinds_and_trains_under_amp(pkg):
                 l.mlstm_branch = lambda x, _l=l: _reference_branch(pkg, _l, x, pkg.vil._is_reverse(_l))
 
         def forward(self, x):
-            x = x + self.a.mlstm_branch(x)
-            return x + self.b.mlstm_branch(x)
+            x = x + self.a.mlstm_branch(self.a.norm(x))
+            return x + self.b.mlstm_branch(self.b.norm(x))
 
     model = Stack().to(dev)
     x = torch.randn(2, 400, 128, device=dev)
@@ -246,3 +249,46 @@ def test_patch_layers_rebinds_and_trains_under_amp(pkg):
     assert set(g_new) == set(g_ref)
     for n in g_ref:
         assert rel(g_new[n], g_ref[n]) < 3e-2, (n, rel(g_new[n], g_ref[n]))
+
+
+@pytest.mark.parametrize("C", [192, 256, 384, 512])
+@pytest.mark.parametrize("x_dtype,y_dtype", [(torch.float16, torch.float16), (torch.float32, torch.float16),
+                                             (torch.float32, torch.float32), (torch.bfloat16, torch.float32)])
+def test_rms_norm_fw_bw(pkg, C, x_dtype, y_dtype):
+    """Fused RMSNorm (ViLLayer.norm / .ffn_norm, vision_lstm2.py:277-278) against torch.rms_norm itself -- the
+    composite path it replaces under autocast -- and against float64 autograd for the gradients."""
+    torch.manual_seed(C)
+    dev = torch.device("cuda:0")
+    x = (torch.randn(5, 77, C, device=dev) * 1.3 + 0.2).to(x_dtype).requires_grad_(True)
+    w = (1.0 + 0.2 * torch.randn(C, device=dev)).requires_grad_(True)
+    dy = torch.randn(5, 77, C, device=dev).to(y_dtype)
+    y = pkg.rms_norm_b200(x, w, 1e-6, out_dtype=y_dtype)
+    assert y.shape == x.shape and y.dtype == y_dtype
+    y.backward(dy)
+    want = torch.rms_norm(x.detach(), (C,), w.detach(), 1e-6)  # fp32 result of the composite / fused torch path
+    tol_y = {torch.float32: 2e-6, torch.float16: 1e-3, torch.bfloat16: 8e-3}
+    assert rel(y, want) < max(tol_y[y_dtype], tol_y[x_dtype]), rel(y, want)
+    x64, w64 = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
+    (x64 * torch.rsqrt(x64.pow(2).mean(-1, keepdim=True) + 1e-6) * w64).backward(dy.double())
+    assert rel(x.grad, x64.grad) < max(tol_y[x_dtype], 2e-3), rel(x.grad, x64.grad)
+    # dw sums dy * round_x(x rstd), the composite's own definition: bf16 rounding noise shows against float64
+    assert rel(w.grad, w64.grad) < max(tol_y[x_dtype], 2e-3), rel(w.grad, w64.grad)
+
+
+def test_rms_norm_autocast_output_feeds_linear_identically(pkg):
+    """Under fp16 autocast the consumers are Linear layers: what they read from the fused norm must equal what
+    they read from torch's (the fp32 composite output cast to fp16 by autocast) -- same rounding points, so the
+    only freedom is the summation order of mean(x^2): at most one fp16 ulp, on a small fraction of the elements."""
+    torch.manual_seed(3)
+    dev = torch.device("cuda:0")
+    norm = torch.nn.RMSNorm(256, eps=1e-6).to(dev)
+    with torch.no_grad():
+        norm.weight.add_(0.3 * torch.randn(256, device=dev))
+    x = torch.randn(4, 400, 256, device=dev).half()
+    with torch.autocast("cuda", dtype=torch.float16):
+        a = norm(x).to(torch.float16)
+        b = pkg.rms_norm_b200(x, norm.weight, norm.eps)
+    assert b.dtype == torch.float16
+    diff = (a.float() - b.float()).abs()
+    assert float((diff / a.float().abs().clamp_min(1e-3)).max()) <= 2.0 ** -9  # one ulp of fp16
+    assert float((diff > 0).float().mean()) < 0.02

@@ -28,6 +28,9 @@ EXPORTS = (
     "mlstm_b200_cellout_workspace_bytes",
     "mlstm_b200_cellout_fw",
     "mlstm_b200_cellout_bw",
+    "mlstm_b200_rmsnorm_workspace_bytes",
+    "mlstm_b200_rmsnorm_fw",
+    "mlstm_b200_rmsnorm_bw",
 )
 
 
@@ -90,6 +93,21 @@ class CellOutBwArgs(C.Structure):
     ]
 
 
+class RmsNormArgs(C.Structure):
+    _fields_ = [
+        ("rows", C.c_int64), ("C", C.c_int32), ("x_dtype", C.c_int32), ("y_dtype", C.c_int32), ("eps", C.c_float),
+        ("x", C.c_void_p), ("y", C.c_void_p), ("weight", C.c_void_p), ("rstd", C.c_void_p),
+    ]
+
+
+class RmsNormBwArgs(C.Structure):
+    _fields_ = [
+        ("fw", RmsNormArgs),
+        ("dy", C.c_void_p), ("dx", C.c_void_p), ("dweight", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
 _lib = None
 
 
@@ -131,6 +149,12 @@ def load_library(path: str | None = None):
     lib.mlstm_b200_cellout_fw.argtypes = [C.POINTER(CellOutArgs), C.c_void_p]
     lib.mlstm_b200_cellout_bw.restype = C.c_int
     lib.mlstm_b200_cellout_bw.argtypes = [C.POINTER(CellOutBwArgs), C.c_void_p]
+    lib.mlstm_b200_rmsnorm_workspace_bytes.restype = C.c_size_t
+    lib.mlstm_b200_rmsnorm_workspace_bytes.argtypes = [C.POINTER(RmsNormArgs)]
+    lib.mlstm_b200_rmsnorm_fw.restype = C.c_int
+    lib.mlstm_b200_rmsnorm_fw.argtypes = [C.POINTER(RmsNormArgs), C.c_void_p]
+    lib.mlstm_b200_rmsnorm_bw.restype = C.c_int
+    lib.mlstm_b200_rmsnorm_bw.argtypes = [C.POINTER(RmsNormBwArgs), C.c_void_p]
     v = lib.mlstm_b200_abi_version()
     if v != ABI_VERSION:
         raise RuntimeError(f"ABI mismatch: library {v}, binding {ABI_VERSION}")

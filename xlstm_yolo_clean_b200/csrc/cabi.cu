@@ -218,4 +218,32 @@ int mlstm_b200_cellout_bw(const mlstm_b200_cellout_bw_args* a, void* stream) {
   return cellout_bw(*a, (cudaStream_t)stream);
 }
 
+size_t mlstm_b200_rmsnorm_workspace_bytes(const mlstm_b200_rmsnorm_args* a) {
+  if (!a) return 0;
+  size_t n = rmsnorm_workspace_bytes(*a);
+  return n < 256 ? 256 : n;
+}
+
+int mlstm_b200_rmsnorm_fw(const mlstm_b200_rmsnorm_args* a, void* stream) {
+  g_err[0] = 0;
+  g_launches = 0;
+  if (!a) {
+    set_error("args is NULL");
+    return MLSTM_B200_EINVAL;
+  }
+  if (int e = require_device()) return e;
+  return rmsnorm_fw(*a, (cudaStream_t)stream);
+}
+
+int mlstm_b200_rmsnorm_bw(const mlstm_b200_rmsnorm_bw_args* a, void* stream) {
+  g_err[0] = 0;
+  g_launches = 0;
+  if (!a) {
+    set_error("args is NULL");
+    return MLSTM_B200_EINVAL;
+  }
+  if (int e = require_device()) return e;
+  return rmsnorm_bw(*a, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -303,6 +303,138 @@ __global__ void k_cellout_reduce(const float* __restrict__ partial, int n_cta, i
   if (lane == 0) out[c] = acc;
 }
 
+// ---------------------------------------------------------------------------------------------
+// RMSNorm in front of the branch (ViLLayer.norm / .ffn_norm = nn.RMSNorm(dim, eps=1e-6), vision_lstm2.py:277-278,
+// applied at :318-327).  Under fp16 autocast the input is 16-bit and the weight fp32, so torch.rms_norm falls off
+// its fused path ("Mismatch dtype between input and weight") onto a composite of ~15 elementwise / reduction
+// kernels per call, forward + backward -- 60 calls per step.  One warp per token row, J = dim/64 element pairs
+// per lane (coalesced 128-byte warp accesses), fp32 statistics; the forward reproduces the composite's rounding
+// ((x * rstd) rounded to the input dtype, then times the fp32 weight), the backward keeps the per-channel weight
+// gradient in registers and reduces it in two deterministic stages like the cell output stage.
+template <typename T> __device__ __forceinline__ float2 ld_pair(const T* p);
+template <> __device__ __forceinline__ float2 ld_pair<float>(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+template <> __device__ __forceinline__ float2 ld_pair<__half>(const __half* p) {
+  const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(p));
+  return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
+template <> __device__ __forceinline__ float2 ld_pair<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(p));
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u));
+}
+template <typename T> __device__ __forceinline__ void st_pair(T* p, float a, float b);
+template <> __device__ __forceinline__ void st_pair<float>(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+template <> __device__ __forceinline__ void st_pair<__half>(__half* p, float a, float b) { *reinterpret_cast<__half2*>(p) = __floats2half2_rn(a, b); }
+template <> __device__ __forceinline__ void st_pair<__nv_bfloat16>(__nv_bfloat16* p, float a, float b) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
+}
+template <typename T> __device__ __forceinline__ float round_to(float v) { return to_f32<T>(from_f32<T>(v)); }
+
+struct RmsP {
+  int64_t rows;
+  int C;
+  float eps;
+  const void *x, *dy;
+  void *y, *dx;
+  const float* w;
+  float* rstd;     // (rows) saved by the forward
+  float* partial;  // [gridDim.x][C]
+};
+
+template <typename TX, typename TY, int J>
+__global__ void __launch_bounds__(512, 1) k_rmsnorm_fw(const RmsP p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), nwarp = (int64_t)gridDim.x * (blockDim.x >> 5);
+  float2 w[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) w[j] = p.w ? *reinterpret_cast<const float2*>(p.w + 2 * (lane + 32 * j)) : make_float2(1.f, 1.f);
+  const float inv_c = 1.f / (float)p.C;
+  for (int64_t r0 = warp; r0 < p.rows; r0 += 2 * nwarp) {  // two rows per iteration: their loads overlap
+    float2 xa[J], xb[J];
+    const int64_t r1 = r0 + nwarp;
+    const bool has_b = r1 < p.rows;
+    const TX* pa = reinterpret_cast<const TX*>(p.x) + r0 * p.C;
+    const TX* pb = reinterpret_cast<const TX*>(p.x) + (has_b ? r1 : r0) * p.C;
+#pragma unroll
+    for (int j = 0; j < J; ++j) xa[j] = ld_pair<TX>(pa + 2 * (lane + 32 * j));
+#pragma unroll
+    for (int j = 0; j < J; ++j) xb[j] = ld_pair<TX>(pb + 2 * (lane + 32 * j));
+    float sa = 0.f, sb = 0.f;
+#pragma unroll
+    for (int j = 0; j < J; ++j) sa += xa[j].x * xa[j].x + xa[j].y * xa[j].y, sb += xb[j].x * xb[j].x + xb[j].y * xb[j].y;
+    sa = warp_all_sum(sa), sb = warp_all_sum(sb);
+    const float ra = rsqrtf(sa * inv_c + p.eps), rb = rsqrtf(sb * inv_c + p.eps);
+    TY* ya = reinterpret_cast<TY*>(p.y) + r0 * p.C;
+    TY* yb = reinterpret_cast<TY*>(p.y) + r1 * p.C;
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+      st_pair<TY>(ya + 2 * (lane + 32 * j), round_to<TX>(xa[j].x * ra) * w[j].x, round_to<TX>(xa[j].y * ra) * w[j].y);
+    if (has_b) {
+#pragma unroll
+      for (int j = 0; j < J; ++j)
+        st_pair<TY>(yb + 2 * (lane + 32 * j), round_to<TX>(xb[j].x * rb) * w[j].x, round_to<TX>(xb[j].y * rb) * w[j].y);
+    }
+    if (lane == 0) {
+      p.rstd[r0] = ra;
+      if (has_b) p.rstd[r1] = rb;
+    }
+  }
+}
+
+template <typename TX, typename TY, int J>
+__global__ void __launch_bounds__(512, 1) k_rmsnorm_bw(const RmsP p) {
+  extern __shared__ float red[];  // [warps][C]
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int64_t warp = (int64_t)blockIdx.x * nw + wib, nwarp = (int64_t)gridDim.x * nw;
+  float2 w[J], acc[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    w[j] = p.w ? *reinterpret_cast<const float2*>(p.w + 2 * (lane + 32 * j)) : make_float2(1.f, 1.f);
+    acc[j] = make_float2(0.f, 0.f);
+  }
+  const float inv_c = 1.f / (float)p.C;
+  for (int64_t r = warp; r < p.rows; r += nwarp) {
+    const TX* px = reinterpret_cast<const TX*>(p.x) + r * p.C;
+    const TY* pg = reinterpret_cast<const TY*>(p.dy) + r * p.C;
+    float2 x[J], g[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) x[j] = ld_pair<TX>(px + 2 * (lane + 32 * j));
+#pragma unroll
+    for (int j = 0; j < J; ++j) g[j] = ld_pair<TY>(pg + 2 * (lane + 32 * j));
+    const float rs = p.rstd[r];
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const float hx = x[j].x * rs, hy = x[j].y * rs;
+      acc[j].x += g[j].x * round_to<TX>(hx);  // d/dw of round(x rstd) * w
+      acc[j].y += g[j].y * round_to<TX>(hy);
+      g[j].x *= w[j].x, g[j].y *= w[j].y;     // gradient w.r.t. the normalised row
+      dot += g[j].x * hx + g[j].y * hy;
+      x[j].x = hx, x[j].y = hy;
+    }
+    dot = warp_all_sum(dot) * inv_c;
+    TX* pd = reinterpret_cast<TX*>(p.dx) + r * p.C;
+#pragma unroll
+    for (int j = 0; j < J; ++j) st_pair<TX>(pd + 2 * (lane + 32 * j), rs * (g[j].x - x[j].x * dot), rs * (g[j].y - x[j].y * dot));
+  }
+#pragma unroll
+  for (int j = 0; j < J; ++j) *reinterpret_cast<float2*>(red + wib * p.C + 2 * (lane + 32 * j)) = acc[j];
+  __syncthreads();
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    float a = 0.f;
+    for (int k = 0; k < nw; ++k) a += red[k * p.C + c];
+    p.partial[(int64_t)blockIdx.x * p.C + c] = a;
+  }
+}
+
+__global__ void k_rmsnorm_reduce(const float* __restrict__ partial, int n_cta, int C, float* dw) {
+  const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (idx >= C) return;
+  float acc = 0.f;
+  for (int i = lane; i < n_cta; i += 32) acc += partial[(int64_t)i * C + idx];
+  acc = warp_all_sum(acc);
+  if (lane == 0) dw[idx] = acc;
+}
+
 int grid_ctas() {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -461,6 +593,80 @@ int cellout_bw(const mlstm_b200_cellout_bw_args& b, cudaStream_t st) {
   if (rc) return rc;
   MLSTM_CUDA_CHECK(cudaGetLastError());
   k_cellout_reduce<<<(3 * p.H * 32 + 255) / 256, 256, 0, st>>>(p.partial, grid, p.H, b.dweight, b.dbias, b.dskip);
+  count_launch(2);
+  MLSTM_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+size_t rmsnorm_workspace_bytes(const mlstm_b200_rmsnorm_args& a) { return (size_t)grid_ctas() * a.C * sizeof(float); }
+
+namespace {
+int rms_check(const mlstm_b200_rmsnorm_args& a) {
+  if (a.rows <= 0 || !a.x || !a.rstd) {
+    set_error("rmsnorm: bad arguments");
+    return MLSTM_B200_EINVAL;
+  }
+  if (a.C != 192 && a.C != 256 && a.C != 384 && a.C != 512) {
+    set_error("rmsnorm: dim %d not covered (192, 256, 384, 512)", a.C);
+    return MLSTM_B200_EUNSUPPORTED;
+  }
+  return 0;
+}
+template <typename TX, typename TY, int J>
+void rms_launch(const RmsP& p, bool backward, cudaStream_t st) {
+  const int grid = grid_ctas();
+  if (backward)
+    k_rmsnorm_bw<TX, TY, J><<<grid, 512, 16 * p.C * sizeof(float), st>>>(p);
+  else
+    k_rmsnorm_fw<TX, TY, J><<<grid, 512, 0, st>>>(p);
+}
+template <typename TX, typename TY>
+int rms_dispatch_j(const RmsP& p, bool backward, cudaStream_t st) {
+  switch (p.C / 64) {
+    case 3: rms_launch<TX, TY, 3>(p, backward, st); return 0;
+    case 4: rms_launch<TX, TY, 4>(p, backward, st); return 0;
+    case 6: rms_launch<TX, TY, 6>(p, backward, st); return 0;
+    case 8: rms_launch<TX, TY, 8>(p, backward, st); return 0;
+  }
+  return MLSTM_B200_EUNSUPPORTED;
+}
+int rms_dispatch(int tx, int ty, const RmsP& p, bool backward, cudaStream_t st) {
+  return dispatch2(tx, ty, [&](auto a, auto b) { return rms_dispatch_j<decltype(a), decltype(b)>(p, backward, st); });
+}
+}  // namespace
+
+int rmsnorm_fw(const mlstm_b200_rmsnorm_args& a, cudaStream_t st) {
+  if (int e = rms_check(a)) return e;
+  if (!a.y) {
+    set_error("rmsnorm: y is NULL");
+    return MLSTM_B200_EINVAL;
+  }
+  RmsP p{};
+  p.rows = a.rows, p.C = a.C, p.eps = a.eps, p.x = a.x, p.y = a.y, p.w = a.weight, p.rstd = a.rstd;
+  if (int e = rms_dispatch(a.x_dtype, a.y_dtype, p, false, st)) return e;
+  count_launch(1);
+  MLSTM_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int rmsnorm_bw(const mlstm_b200_rmsnorm_bw_args& b, cudaStream_t st) {
+  const mlstm_b200_rmsnorm_args& a = b.fw;
+  if (int e = rms_check(a)) return e;
+  if (!b.dy || !b.dx) {
+    set_error("rmsnorm_bw: dy / dx are NULL");
+    return MLSTM_B200_EINVAL;
+  }
+  const size_t need = rmsnorm_workspace_bytes(a);
+  if (!b.workspace || b.workspace_bytes < need) {
+    set_error("rmsnorm_bw: workspace too small: need %zu bytes, got %zu", need, b.workspace_bytes);
+    return MLSTM_B200_EWORKSPACE;
+  }
+  RmsP p{};
+  p.rows = a.rows, p.C = a.C, p.eps = a.eps, p.x = a.x, p.dy = b.dy, p.dx = b.dx, p.w = a.weight, p.rstd = a.rstd;
+  p.partial = reinterpret_cast<float*>(b.workspace);
+  if (int e = rms_dispatch(a.x_dtype, a.y_dtype, p, true, st)) return e;
+  MLSTM_CUDA_CHECK(cudaGetLastError());
+  if (b.dweight) k_rmsnorm_reduce<<<(a.C * 32 + 255) / 256, 256, 0, st>>>(p.partial, grid_ctas(), a.C, b.dweight);
   count_launch(2);
   MLSTM_CUDA_CHECK(cudaGetLastError());
   return 0;

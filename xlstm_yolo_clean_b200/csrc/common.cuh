@@ -168,5 +168,8 @@ int tensor_bw(const mlstm_b200_bw_args& a, cudaStream_t st);
 size_t cellout_workspace_bytes(const mlstm_b200_cellout_args& a);
 int cellout_fw(const mlstm_b200_cellout_args& a, cudaStream_t st);
 int cellout_bw(const mlstm_b200_cellout_bw_args& a, cudaStream_t st);
+size_t rmsnorm_workspace_bytes(const mlstm_b200_rmsnorm_args& a);
+int rmsnorm_fw(const mlstm_b200_rmsnorm_args& a, cudaStream_t st);
+int rmsnorm_bw(const mlstm_b200_rmsnorm_bw_args& a, cudaStream_t st);
 
 }  // namespace mlstm

@@ -111,6 +111,73 @@ def cell_out(h, weight=None, bias=None, skip=None, x=None, eps=1e-6, out_dtype=N
     return _CellOut.apply(h, weight, bias, skip, x, eps, out_dtype)
 
 
+RMSNORM_DIMS = (192, 256, 384, 512)
+
+
+class _RmsNorm(torch.autograd.Function):
+    """nn.RMSNorm over the last dimension (ViLLayer.norm / .ffn_norm, vision_lstm2.py:277-278) as one CUDA pass each
+    way.  ``out_dtype``: what the consumer reads (a Linear under autocast reads the autocast dtype)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, eps, out_dtype):
+        lib = _cabi.load_library()
+        if not x.is_cuda:
+            raise RuntimeError("rms_norm_b200: x is on the CPU; this backend has no CPU path")
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1])
+        x2 = x2 if x2.is_contiguous() else x2.contiguous()
+        rows, Cdim = x2.shape
+        w32 = _f32c(weight)
+        with _on_device(x.device):
+            y = torch.empty(rows, Cdim, dtype=out_dtype, device=x.device)
+            rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+            a = _cabi.RmsNormArgs()
+            a.rows, a.C, a.x_dtype, a.y_dtype, a.eps = rows, Cdim, _DTYPES[x2.dtype], _DTYPES[out_dtype], float(eps)
+            a.x, a.y, a.rstd = x2.data_ptr(), y.data_ptr(), rstd.data_ptr()
+            a.weight = None if w32 is None else w32.data_ptr()
+            st = lib.mlstm_b200_rmsnorm_fw(C.byref(a), C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+            _cabi.check(st, "mlstm_b200_rmsnorm_fw")
+        ctx.save_for_backward(x2, weight, rstd)
+        ctx.eps, ctx.out_dtype, ctx.shp = float(eps), out_dtype, shp
+        return y.view(shp)
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _cabi.load_library()
+        x2, weight, rstd = ctx.saved_tensors
+        rows, Cdim = x2.shape
+        dy2 = dy.reshape(rows, Cdim)
+        dy2 = dy2 if (dy2.dtype == ctx.out_dtype and dy2.is_contiguous()) else dy2.to(ctx.out_dtype).contiguous()
+        w32 = _f32c(weight)
+        dev = x2.device
+        with _on_device(dev):
+            dx = torch.empty_like(x2)
+            dw = torch.empty(Cdim, dtype=torch.float32, device=dev)
+            b = _cabi.RmsNormBwArgs()
+            a = b.fw
+            a.rows, a.C, a.x_dtype, a.y_dtype, a.eps = rows, Cdim, _DTYPES[x2.dtype], _DTYPES[ctx.out_dtype], ctx.eps
+            a.x, a.rstd = x2.data_ptr(), rstd.data_ptr()
+            a.weight = None if w32 is None else w32.data_ptr()
+            b.dy, b.dx, b.dweight = dy2.data_ptr(), dx.data_ptr(), dw.data_ptr()
+            nws = lib.mlstm_b200_rmsnorm_workspace_bytes(C.byref(a))
+            ws = torch.empty(nws, dtype=torch.uint8, device=dev)
+            b.workspace, b.workspace_bytes = ws.data_ptr(), nws
+            st = lib.mlstm_b200_rmsnorm_bw(C.byref(b), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            _cabi.check(st, "mlstm_b200_rmsnorm_bw")
+        return dx.view(ctx.shp), (None if weight is None else dw.to(weight.dtype)), None, None
+
+
+def rms_norm_b200(x, weight=None, eps=1e-6, out_dtype=None):
+    """Fused RMSNorm.  Default ``out_dtype``: the CUDA autocast dtype if autocast is on (the consumers in ViLLayer
+    are Linear layers, which read exactly that), else what torch.rms_norm returns (promotion of x and weight)."""
+    if out_dtype is None:
+        if torch.is_autocast_enabled("cuda"):
+            out_dtype = torch.get_autocast_dtype("cuda")
+        else:
+            out_dtype = x.dtype if weight is None else torch.promote_types(x.dtype, weight.dtype)
+    return _RmsNorm.apply(x, weight, eps, out_dtype)
+
+
 def _heads(qk, v, gates, NH):
     """(B, NH, S, D) / (B, NH, S) views of the layer-layout tensors: no data movement."""
     B, S, H = v.shape
@@ -283,5 +350,11 @@ def patch_layers(model: torch.nn.Module, siging: bool = False, kernel_dtype: str
             continue
         mod.mlstm_branch = types.MethodType(
             lambda self, x, _s=siging, _k=kernel_dtype: mlstm_branch_b200(self, x, siging=_s, kernel_dtype=_k), mod)
+        for norm in (getattr(mod, "norm", None), getattr(mod, "ffn_norm", None)):  # the RMSNorms in front of the branches
+            if (isinstance(norm, torch.nn.RMSNorm) and len(norm.normalized_shape) == 1
+                    and norm.normalized_shape[0] in RMSNORM_DIMS):
+                norm.forward = types.MethodType(
+                    lambda self, x: rms_norm_b200(x, self.weight, 1e-6 if self.eps is None else self.eps)
+                    if x.is_cuda else torch.nn.RMSNorm.forward(self, x), norm)
         n += 1
     return n
