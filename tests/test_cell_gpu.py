@@ -271,14 +271,13 @@ def test_rms_norm_fw_bw(pkg, C, x_dtype, y_dtype):
     x64, w64 = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
     (x64 * torch.rsqrt(x64.pow(2).mean(-1, keepdim=True) + 1e-6) * w64).backward(dy.double())
     assert rel(x.grad, x64.grad) < max(tol_y[x_dtype], 2e-3), rel(x.grad, x64.grad)
-    # dw sums dy * round_x(x rstd), the composite's own definition: bf16 rounding noise shows against float64
     assert rel(w.grad, w64.grad) < max(tol_y[x_dtype], 2e-3), rel(w.grad, w64.grad)
 
 
 def test_rms_norm_autocast_output_feeds_linear_identically(pkg):
     """Under fp16 autocast the consumers are Linear layers: what they read from the fused norm must equal what
-    they read from torch's (the fp32 composite output cast to fp16 by autocast) -- same rounding points, so the
-    only freedom is the summation order of mean(x^2): at most one fp16 ulp, on a small fraction of the elements."""
+    they read from torch's composite (y = half((x rstd) w), one rounding) -- same arithmetic, so the only
+    freedom is the summation order of mean(x^2): at most one fp16 ulp, on a small fraction of the elements."""
     torch.manual_seed(3)
     dev = torch.device("cuda:0")
     norm = torch.nn.RMSNorm(256, eps=1e-6).to(dev)

@@ -308,9 +308,9 @@ __global__ void k_cellout_reduce(const float* __restrict__ partial, int n_cta, i
 // applied at :318-327).  Under fp16 autocast the input is 16-bit and the weight fp32, so torch.rms_norm falls off
 // its fused path ("Mismatch dtype between input and weight") onto a composite of ~15 elementwise / reduction
 // kernels per call, forward + backward -- 60 calls per step.  One warp per token row, J = dim/64 element pairs
-// per lane (coalesced 128-byte warp accesses), fp32 statistics; the forward reproduces the composite's rounding
-// ((x * rstd) rounded to the input dtype, then times the fp32 weight), the backward keeps the per-channel weight
-// gradient in registers and reduces it in two deterministic stages like the cell output stage.
+// per lane (coalesced 128-byte warp accesses), fp32 statistics and arithmetic with ONE rounding at the store, which
+// is what the composite does (y = cast((x * rstd) * weight)); the backward keeps the per-channel weight gradient
+// in registers and reduces it in two deterministic stages like the cell output stage.
 template <typename T> __device__ __forceinline__ float2 ld_pair(const T* p);
 template <> __device__ __forceinline__ float2 ld_pair<float>(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 template <> __device__ __forceinline__ float2 ld_pair<__half>(const __half* p) {
@@ -327,7 +327,6 @@ template <> __device__ __forceinline__ void st_pair<__half>(__half* p, float a, 
 template <> __device__ __forceinline__ void st_pair<__nv_bfloat16>(__nv_bfloat16* p, float a, float b) {
   *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
 }
-template <typename T> __device__ __forceinline__ float round_to(float v) { return to_f32<T>(from_f32<T>(v)); }
 
 struct RmsP {
   int64_t rows;
@@ -367,11 +366,11 @@ __global__ void __launch_bounds__(512, 1) k_rmsnorm_fw(const RmsP p) {
     TY* yb = reinterpret_cast<TY*>(p.y) + r1 * p.C;
 #pragma unroll
     for (int j = 0; j < J; ++j)
-      st_pair<TY>(ya + 2 * (lane + 32 * j), round_to<TX>(xa[j].x * ra) * w[j].x, round_to<TX>(xa[j].y * ra) * w[j].y);
+      st_pair<TY>(ya + 2 * (lane + 32 * j), xa[j].x * ra * w[j].x, xa[j].y * ra * w[j].y);
     if (has_b) {
 #pragma unroll
       for (int j = 0; j < J; ++j)
-        st_pair<TY>(yb + 2 * (lane + 32 * j), round_to<TX>(xb[j].x * rb) * w[j].x, round_to<TX>(xb[j].y * rb) * w[j].y);
+        st_pair<TY>(yb + 2 * (lane + 32 * j), xb[j].x * rb * w[j].x, xb[j].y * rb * w[j].y);
     }
     if (lane == 0) {
       p.rstd[r0] = ra;
@@ -405,8 +404,8 @@ __global__ void __launch_bounds__(512, 1) k_rmsnorm_bw(const RmsP p) {
 #pragma unroll
     for (int j = 0; j < J; ++j) {
       const float hx = x[j].x * rs, hy = x[j].y * rs;
-      acc[j].x += g[j].x * round_to<TX>(hx);  // d/dw of round(x rstd) * w
-      acc[j].y += g[j].y * round_to<TX>(hy);
+      acc[j].x += g[j].x * hx;  // d/dw of (x rstd) * w
+      acc[j].y += g[j].y * hy;
       g[j].x *= w[j].x, g[j].y *= w[j].y;     // gradient w.r.t. the normalised row
       dot += g[j].x * hx + g[j].y * hy;
       x[j].x = hx, x[j].y = hy;

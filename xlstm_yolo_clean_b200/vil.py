@@ -169,12 +169,12 @@ class _RmsNorm(torch.autograd.Function):
 
 def rms_norm_b200(x, weight=None, eps=1e-6, out_dtype=None):
     """Fused RMSNorm.  Default ``out_dtype``: the CUDA autocast dtype if autocast is on (the consumers in ViLLayer
-    are Linear layers, which read exactly that), else what torch.rms_norm returns (promotion of x and weight)."""
+    are Linear layers, which read exactly that), else the input dtype like torch.rms_norm."""
     if out_dtype is None:
         if torch.is_autocast_enabled("cuda"):
             out_dtype = torch.get_autocast_dtype("cuda")
         else:
-            out_dtype = x.dtype if weight is None else torch.promote_types(x.dtype, weight.dtype)
+            out_dtype = x.dtype  # torch.rms_norm returns the input dtype
     return _RmsNorm.apply(x, weight, eps, out_dtype)
 
 
