@@ -7,10 +7,15 @@
     kernel's anti-causal scan (``reverse=True``) plus the depthwise 3x3 conv evaluated with its weights rotated
     by 180 degrees, which is the same function because a flip of the row-major token sequence is a 180-degree
     rotation of the image and every other op on the branch acts per token;
-  * the q/k/v/i/f views handed to the kernel as they are (BSHD-strided, no ``contiguous``).
+  * the q/k/v/i/f views handed to the kernel as they are (BSHD-strided, no ``contiguous``), gradients written by
+    the kernel straight into tensors of the layer's own layouts, no zero-padding copies for S = 400 / 100;
+  * the two ``nn.RMSNorm`` modules in front of the branches (``ViLLayer.norm`` / ``.ffn_norm``, vision_lstm2.py:277-278,
+    318-327) as one CUDA pass each way (``mlstm_b200_rmsnorm_fw`` / ``_bw``): under fp16 autocast torch's own falls off
+    its fused path onto a composite of ~15 kernels per call.
 
-``patch_model(model, fused=True)`` (backend.py) rebinds ``ViLLayer.mlstm_branch`` of the reference model to
-``mlstm_branch_b200``; parameters, state-dict keys and the function computed are unchanged.
+``patch_model(model, fused=True)`` (backend.py) / ``patch_layers(model)`` rebind ``ViLLayer.mlstm_branch`` of the
+reference model to ``mlstm_branch_b200`` and the two norms' ``forward`` to ``rms_norm_b200``; parameters, state-dict
+keys and the function computed are unchanged.
 PyTorch is used for the dense layers (cuBLAS / cuDNN serve them), device memory and autograd plumbing.
 There is no CPU path: CPU tensors raise.
 """
