@@ -163,3 +163,41 @@ def test_cellout_without_device_returns_error(lib):
     a.B, a.NH, a.S, a.D = 1, 2, 8, 64
     st = lib.mlstm_b200_cellout_fw(ctypes.byref(a), None)
     assert st != 0 and lib.mlstm_b200_last_error() != b""
+
+
+def test_patch_layers_rebinds_without_a_gpu():
+    """Host logic of the fused-layer rebinding (vil.patch_layers): ViLLayer-shaped modules get the new branch and
+    norm forwards; the norm keeps working for CPU tensors (torch's own forward), the branch refuses them."""
+    import xlstm_yolo_clean_b200 as pkg
+
+    class Cell(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.dim, self.num_heads, self.gate_soft_cap = 256, 4, 15.0
+            self.use_autocast, self.autocast_dtype = True, torch.float16
+            self.ifgate = torch.nn.Linear(768, 8)
+
+    class Layer(torch.nn.Module):
+        def __init__(self, heads_ok=True):
+            super().__init__()
+            self.direction = "ROWWISE_FROM_BOT_RIGHT"
+            self.proj_up = torch.nn.Linear(128, 512)
+            self.conv = torch.nn.Conv2d(256, 256, 3, padding=1, groups=256)
+            self.qk_proj, self.v_proj = torch.nn.Linear(256, 512), torch.nn.Linear(256, 256)
+            self.mlstm_cell = Cell()
+            if not heads_ok:
+                self.mlstm_cell.num_heads = 5  # 256 / 5: geometry the fused output kernel does not cover
+            self.learnable_skip = torch.nn.Parameter(torch.ones(256))
+            self.proj_down = torch.nn.Linear(256, 128)
+            self.norm, self.ffn_norm = torch.nn.RMSNorm(256, eps=1e-6), torch.nn.RMSNorm(100, eps=1e-6)
+
+    model = torch.nn.Sequential(Layer(), Layer(heads_ok=False), torch.nn.Linear(4, 4))
+    assert pkg.patch_layers(model) == 1
+    a, b = model[0], model[1]
+    assert "mlstm_branch" in a.__dict__ and "mlstm_branch" not in b.__dict__
+    assert "forward" in a.norm.__dict__ and "forward" not in a.ffn_norm.__dict__  # dim 100 is not covered
+    x = torch.randn(2, 9, 256)
+    assert torch.allclose(a.norm(x), torch.nn.functional.rms_norm(x, (256,), a.norm.weight, 1e-6))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        a.mlstm_branch(torch.randn(1, 16, 128))
+    assert pkg.vil._is_reverse(a)
