@@ -149,16 +149,11 @@ int mlstm_b200_chunkwise_bw(const mlstm_b200_bw_args* args, void* cuda_stream);
  * gpu_launches claim). */
 int mlstm_b200_last_launch_count(void);
 
-/* Debug / profiling hook (not thread-safe): when set to a device buffer of at least 8192
- * int64, CTA 0 of the tensor-core kernels records clock64() at its phase boundaries
- * (forward at [tile*16 + slot], backward at [4096 + tile*16 + slot]).  NULL disables it. */
+/* Profiling hook of the PROFILE build (lib/libmlstm_b200_prof.so, compiled with -DMLSTM_TC_PROFILE): when set to
+ * a device buffer of at least 8192 int64, CTA 0 of the tensor-core kernels records clock64() at its phase
+ * boundaries (forward at [tile*16 + slot], backward at [4096 + tile*16 + slot]).  NULL disables it.
+ * In the product library this is a no-op: the product build holds no process-global mutable state. */
 void mlstm_b200_debug_set_clock_buffer(void* dev_ptr);
-
-/* Backward formulation of the tensor-core path: 1 = tc_bw (query index on the TMEM lanes; default),
- * 2 = tc_bw2 (transposed: key / value index on the lanes, TS-mode operands, one accumulator per output).
- * Both compute the same function (bw.py:206-348); returns the previous value.  Also settable through
- * the environment variable MLSTM_B200_BW before the first call. */
-int mlstm_b200_debug_set_bw_variant(int variant);
 
 /* ---------------------------------------------------------------------------------------------
  * The cell's output stage (the callers either side of the path).

@@ -424,42 +424,6 @@ def test_d32_base192_call_exact_vs_tensor(pkg):
         assert O.rel_err(a[name], b[name]) < 2e-2, name
 
 
-# ---------------------------------------------------------------------------------------------------
-# The transposed backward (tc_bw2: key/value index on the TMEM lanes, TS-mode operands) computes the
-# same function as the default backward; it is selected with mlstm_b200_debug_set_bw_variant(2).
-# ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("shape", [(2, 4, 448, 64, 64), (2, 3, 320, 32, 32)], ids=["d64", "d32"])
-@pytest.mark.parametrize("rev", [False, True], ids=["causal", "anticausal"])
-def test_transposed_backward_variant(pkg, shape, rev):
-    from xlstm_yolo_clean_b200 import _cabi
-    lib = _cabi.load_library()
-    inp = O.make_inputs(*shape, seed=90, dtype=torch.float32, with_states=True)
-    t = {k: v.to(torch.bfloat16).cuda() for k, v in inp.items()}
-    res = {}
-    prev = lib.mlstm_b200_debug_set_bw_variant(1)
-    try:
-        for variant in (1, 2):
-            lib.mlstm_b200_debug_set_bw_variant(variant)
-            leaves = {k: t[k].detach().requires_grad_(True) for k in ("q", "k", "v", "i", "f")}
-            c0 = t["c0"].detach().requires_grad_(True)
-            h, (c_last, n_last, m_last) = pkg.mlstm_chunkwise__b200(
-                **leaves, c_initial=c0, n_initial=t["n0"], m_initial=t["m0"], return_last_states=True, reverse=rev,
-                autocast_kernel_dtype=torch.float32)
-            torch.autograd.backward([h, c_last], [t["dh"], t["dc_last"].to(c_last.dtype)])
-            torch.cuda.synchronize()
-            res[variant] = dict(dq=leaves["q"].grad, dk=leaves["k"].grad, dv=leaves["v"].grad, di=leaves["i"].grad,
-                                df=leaves["f"].grad, dc0=c0.grad)
-    finally:
-        lib.mlstm_b200_debug_set_bw_variant(prev)
-    seq = ("q", "k", "v", "i", "f", "dh")
-    ref_in = {k: (v.flip(2) if (rev and k in seq) else v) for k, v in inp.items()}
-    want = _oracle(ref_in, torch.bfloat16, states=True)
-    for variant in (1, 2):
-        for name, g in res[variant].items():
-            w = want[name].flip(2) if (rev and name != "dc0") else want[name]
-            assert O.rel_err(g.double().cpu(), w) < 2e-2, (variant, name)
-
-
 @pytest.mark.parametrize("S", [100, 400, 52, 1004])
 @pytest.mark.parametrize("D", [32, 64])
 @pytest.mark.parametrize("reverse", [False, True], ids=["causal", "anticausal"])

@@ -24,7 +24,6 @@ EXPORTS = (
     "mlstm_b200_chunkwise_bw",
     "mlstm_b200_last_launch_count",
     "mlstm_b200_debug_set_clock_buffer",
-    "mlstm_b200_debug_set_bw_variant",
     "mlstm_b200_cellout_workspace_bytes",
     "mlstm_b200_cellout_fw",
     "mlstm_b200_cellout_bw",
@@ -141,8 +140,6 @@ def load_library(path: str | None = None):
     lib.mlstm_b200_last_launch_count.restype = C.c_int
     lib.mlstm_b200_debug_set_clock_buffer.restype = None
     lib.mlstm_b200_debug_set_clock_buffer.argtypes = [C.c_void_p]
-    lib.mlstm_b200_debug_set_bw_variant.restype = C.c_int
-    lib.mlstm_b200_debug_set_bw_variant.argtypes = [C.c_int]
     lib.mlstm_b200_cellout_workspace_bytes.restype = C.c_size_t
     lib.mlstm_b200_cellout_workspace_bytes.argtypes = [C.POINTER(CellOutArgs)]
     lib.mlstm_b200_cellout_fw.restype = C.c_int

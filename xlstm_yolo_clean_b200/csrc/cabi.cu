@@ -97,7 +97,6 @@ const char* mlstm_b200_last_error(void) { return g_err; }
 int mlstm_b200_last_launch_count(void) { return g_launches; }
 
 void mlstm_b200_debug_set_clock_buffer(void* dev_ptr) { tensor_set_clock_buffer(dev_ptr); }
-int mlstm_b200_debug_set_bw_variant(int variant) { return tensor_set_bw_variant(variant); }
 
 int mlstm_b200_tensor_path_supported(const mlstm_b200_shape* shape) {
   if (!shape) return 0;

@@ -159,7 +159,6 @@ size_t tensor_workspace_bytes(const mlstm_b200_shape& s, int backward);
 size_t tensor_states_bytes(const mlstm_b200_shape& s);
 void tensor_set_clock_buffer(void* dev_ptr);
 bool tensor_context_is_current();  // a CUDA context is current on the calling thread (driver-level query)
-int tensor_set_bw_variant(int variant);
 int tensor_fw(const mlstm_b200_fw_args& a, cudaStream_t st);
 int tensor_bw(const mlstm_b200_bw_args& a, cudaStream_t st);
 

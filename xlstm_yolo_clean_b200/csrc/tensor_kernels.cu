@@ -19,6 +19,7 @@
 //   C_k    = gbar C_{k-1} + dC          fp32 registers (the only sequential dependency)
 // h and the final states do not depend on the tile length (m_t equals the step-recurrent
 // stabiliser), so a 128-token tile is used although the API chunk size is 64.
+#include <atomic>
 #include <mutex>
 #include <set>
 #include <type_traits>
@@ -322,7 +323,9 @@ struct TcFwParams {
   int rev;           // 1: anti-causal direction (tiles walked from the end, mirrored in-tile mask)
   int sig;           // 1: sigmoid input gate, all max states are 0 (siging variant)
   int store_states;  // 1: TMA-store the bf16 copy of C entering every tile (consumed by the backward)
-  long long* prof;   // debug: per-tile phase clocks of CTA 0 (mlstm_b200_debug_set_clock_buffer)
+#ifdef MLSTM_TC_PROFILE
+  long long* prof;   // per-tile phase clocks of CTA 0 (profile build only)
+#endif
 };
 
 template <int D_>
@@ -1143,7 +1146,9 @@ struct TcBwParams {
   // rows of the saved-states matrix per 128-token tile and row offset of this problem's D x D block inside a tile:
   // (D, 0) normally; (256, 64 * block) when a head-dim-128 backward runs as four head-dim-64 block problems
   int cs_rows, cs_off;
+#ifdef MLSTM_TC_PROFILE
   long long* prof;
+#endif
 };
 
 template <int D_>
@@ -1730,640 +1735,14 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
   if (warp == kCtlWarp) tmem_dealloc<512>(tmem);
 }
 
-// >>> BW2 BEGIN
-// =============================================================================================
-// Backward, transposed formulation (tc_bw2): S^T = K Q^T and dSb^T = V dH^T put the key / value index on the
-// TMEM lanes, so the weighted tiles Sb'^T and dS^T are packed IN PLACE by the thread that owns the row and feed
-// dv = Sb'^T dH and dk = dS^T Q as TMEM A operands (TS mode, no shared-memory read for A, no Sb' buffer); the
-// inter-chunk terms ride in the same accumulators through row-scaled operand copies (abar k, abar v,
-// scale bbar/(n+eps) dh) kept in the unused TMEM columns.  Same warp roles, barriers and scan warp as tc_bw.
-// =============================================================================================
-template <int D_>
-struct Bw2Smem {
-  static constexpr int D = D_;
-  static constexpr int kTile = Lay<D>::kTile;   // one [128][D] tile
-  static constexpr int kPTile = LT * 128;       // one [128][64] half of dS^T
-  static constexpr int kState = Lay<D>::kState;
-  // Input buffers.  D = 32: two of each (a whole tile prefetched ahead).  D = 64: two K and two dH tiles (loaded a
-  // tile ahead), one Q, V, C_{k-1}, re-filled behind the MMA batch as soon as their last reader has completed.
-  static constexpr int nQ = D == 64 ? 1 : 2, nK = 2, nV = nQ, nH = 2, nCs = nQ;
-  static constexpr int oQ = 0, oK = oQ + nQ * kTile, oV = oK + nK * kTile, odH = oV + nV * kTile, oCs = odH + nH * kTile;
-  static constexpr int oQt = oCs + nCs * kState;  // wq . Q
-  static constexpr int odS = oQt + kTile;       // dS^T rows, two halves (query columns 0-63 / 64-127)
-  static constexpr int odQ = odS + 2 * kPTile;  // dq / dv / dk staging
-  static constexpr int odV = odQ + kTile;
-  static constexpr int odK = odV + kTile;
-  static constexpr int odC = odK + kTile;       // dC_k 16-bit operand copy
-  static constexpr int oSmall = odC + kState;
-  static constexpr int fGates = 0, fPart = 2 * GateBuf::kFloats, kSmallFloats = fPart + 12 * LT;
-  static constexpr int kBytes = oSmall + kSmallFloats * 4 + 1024;
-  static constexpr bool kAlias = false;
-  // TMEM: S^T and dSb^T (128 columns each; later the packed operands), one accumulator per output
-  static constexpr uint32_t cST = 0, cdST = 128, cdV = 256, cdK = cdV + D, cdQ = cdK + D, cddC = cdQ + D;
-};
-
-template <typename T, int D, bool REV>
-__global__ void __launch_bounds__(kTcThreads, 1)
-tc_bw2(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
-          const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdH,
-          const __grid_constant__ CUtensorMap mapCs, const __grid_constant__ CUtensorMap mapdQ,
-          const __grid_constant__ CUtensorMap mapdK, const __grid_constant__ CUtensorMap mapdV, TcBwParams p) {
-  constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
-  using SM = Bw2Smem<D>;
-  using L = Lay<D>;
-  constexpr int CW = L::CW;
-  TC_PROF(200, 0);  // kernel entry
-  TC_PROF_CTA(0);
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sQ = smem + SM::oQ;  // buffer 0 of each input; processing step `it` uses buffer it % n
-  uint8_t* sK = smem + SM::oK;
-  uint8_t* sV = smem + SM::oV;
-  uint8_t* sdH = smem + SM::odH;
-  uint8_t* sQt = smem + SM::oQt;
-  uint8_t* sdS = smem + SM::odS;
-  uint8_t* sdQ = smem + SM::odQ;
-  uint8_t* sdV = smem + SM::odV;
-  uint8_t* sdK = smem + SM::odK;
-  uint8_t* sCs = smem + SM::oCs;
-  uint8_t* sdC = smem + SM::odC;
-  float* fsm = (float*)(smem + SM::oSmall);
-  __shared__ uint64_t bar_fa[2], bar_fb[2], bar_fc[2], bar_s, bar_q, bar_v, bar_k, bar_d, bar_st, bar_g[2];
-  __shared__ uint32_t tmem_base_s;
-
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform: role branches stay uniform
-  const int bh = blockIdx.x, b = bh / p.NH, hh = bh % p.NH;
-
-  // memory tile of processing tile c (see the forward kernel); the sweep visits c = NT-1 .. 0
-  auto mt = [&](int c) { return REV ? p.NT - 1 - c : c; };
-  // loads of processing step `it` (memory tile mt(NT-1-it)): Q, K complete on bar_fa[it & 1] (operands of S^T),
-  // V, dH on bar_fb (operands of dSb^T), C_{k-1} on bar_fc
-  auto expect_step = [&](int it) {
-    mbar_expect_tx(&bar_fa[it & 1], 2 * SM::kTile);
-    mbar_expect_tx(&bar_fb[it & 1], 2 * SM::kTile);
-    mbar_expect_tx(&bar_fc[it & 1], SM::kState);
-  };
-  auto load_Q = [&](int it) { tma_load_4d(sQ + (it % SM::nQ) * SM::kTile, &mapQ, &bar_fa[it & 1], 0, mt(p.NT - 1 - it) * LT, hh, b); };
-  auto load_K = [&](int it) { tma_load_4d(sK + (it % SM::nK) * SM::kTile, &mapK, &bar_fa[it & 1], 0, mt(p.NT - 1 - it) * LT, hh, b); };
-  auto load_V = [&](int it) { tma_load_4d(sV + (it % SM::nV) * SM::kTile, &mapV, &bar_fb[it & 1], 0, mt(p.NT - 1 - it) * LT, hh, b); };
-  auto load_H = [&](int it) { tma_load_4d(sdH + (it % SM::nH) * SM::kTile, &mapdH, &bar_fb[it & 1], 0, mt(p.NT - 1 - it) * LT, hh, b); };
-  auto load_C = [&](int it) { tma_load_4d(sCs + (it % SM::nCs) * SM::kState, &mapCs, &bar_fc[it & 1], 0, mt(p.NT - 1 - it) * D, hh, b); };
-  // cold start: the first input tiles are requested before anything else happens in the CTA
-  if (tid == kCtlWarp * 32) {
-    for (int s = 0; s < 2; ++s) { mbar_init(&bar_fa[s], 1); mbar_init(&bar_fb[s], 1); mbar_init(&bar_fc[s], 1); }
-    fence_mbar_init();
-    expect_step(0);
-    load_Q(0); load_K(0); load_V(0); load_H(0); load_C(0);
-  }
-  if (tid == 0) {
-    mbar_init(&bar_s, 1);
-    mbar_init(&bar_st, 1);
-    mbar_init(&bar_q, 1);
-    mbar_init(&bar_v, 1);
-    mbar_init(&bar_k, 1);
-    mbar_init(&bar_d, 1);
-    mbar_init(&bar_g[0], 1);
-    mbar_init(&bar_g[1], 1);
-    fence_mbar_init();
-  }
-  if (warp == kCtlWarp) {
-    tmem_alloc<512>(&tmem_base_s);
-    if (lane == 0) {
-      prefetch_tmap(&mapQ); prefetch_tmap(&mapK); prefetch_tmap(&mapV); prefetch_tmap(&mapdH);
-      prefetch_tmap(&mapCs); prefetch_tmap(&mapdQ); prefetch_tmap(&mapdK); prefetch_tmap(&mapdV);
-    }
-  }
-  const int rb = warp & 3, ch = (warp >> 2) & 1;
-  const int row = rb * 32 + lane;
-  const uint32_t lane_base = (uint32_t)(rb * 32) << 16;
-  const int drow = rb * 16 + (lane & 15);
-  const bool owns_c = warp < kCtlWarp && lane < 16 && rb * 16 < D;
-  float dCreg[CW];
-#pragma unroll
-  for (int j = 0; j < CW; ++j) dCreg[j] = 0.f;
-  if (warp < kCtlWarp) {
-    if (p.dc_last && owns_c) {
-      const float* src = p.dc_last + ((int64_t)bh * D + drow) * D + ch * CW;
-#pragma unroll
-      for (int j = 0; j < CW; ++j) dCreg[j] = src[j];
-    }
-    if (owns_c) store_cols<T, D>(sdC, drow, ch * CW, dCreg);
-    fence_proxy_async_smem();
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem = tmem_base_s;
-  const uint32_t tST = tmem + SM::cST, tdST = tmem + SM::cdST;
-  const uint32_t tdV = tmem + SM::cdV, tdK = tmem + SM::cdK, tdQ = tmem + SM::cdQ, tddC = tmem + SM::cddC;
-  // packed 16-bit A operands written by the workers: Sb'^T / dS^T in the first 16 columns of every 32-column
-  // unit of tST / tdST; Kbar, Vbar, dHbar in the second 16 columns ("slots") of units ch (K, V) and ch + 2 (dH)
-  auto slot = [](uint32_t base, int u) { return base + 32u * (uint32_t)u + 16u; };
-  // A address of k-chunk kk (16 elements = 8 columns) of an operand whose rows are split in CW-element halves
-  auto half_op = [&](uint32_t base, int u0, int kk) { return slot(base, u0 + kk / (CW / 16)) + 8u * (uint32_t)(kk % (CW / 16)); };
-
-  const T* ip = (const T*)p.ig + b * p.ig_sb + hh * p.ig_sh;
-  const T* fp = (const T*)p.fg + b * p.fg_sb + hh * p.fg_sh;
-  const float* mo = p.m_out + (int64_t)bh * p.S;
-  const float* no = p.n_out + (int64_t)bh * p.S;
-  if (warp == kCtlWarp) {
-    // =========================== control warp ===================================================
-    constexpr uint32_t id_s = umma_idesc(128, 128, false, false, kBf16);
-    constexpr uint32_t id_c = umma_idesc(64, D, true, true, kBf16);
-    constexpr uint32_t id_ts_mn = umma_idesc(128, D, false, true, kBf16);  // A from TMEM, B MN-major
-    constexpr uint32_t id_mn_mn = umma_idesc(128, D, true, true, kBf16);   // A MN-major, B MN-major
-    constexpr uint32_t id_ts_k = umma_idesc(128, D, false, false, kBf16);  // A from TMEM, B K-major
-    // stage-0 descriptors; stage s adds s * kStage (warp-uniform)
-    const uint64_t kQ0 = L::desc(smem_u32(sQ), 0), mQ0 = L::desc(smem_u32(sQ), SM::kTile);
-    const uint64_t kK0 = L::desc(smem_u32(sK), 0), mK0 = L::desc(smem_u32(sK), SM::kTile);
-    const uint64_t kV0 = L::desc(smem_u32(sV), 0);
-    const uint64_t kH0 = L::desc(smem_u32(sdH), 0), mH0 = L::desc(smem_u32(sdH), SM::kTile);
-    const uint64_t kCs0 = L::desc(smem_u32(sCs), 0);
-    const uint64_t mQt = L::desc(smem_u32(sQt), D == 64 ? SM::kTile : 0);  // D = 32: rows 32-63 of the M = 64 MMA re-read the block
-    const uint64_t kdS = umma_smem_desc(smem_u32(sdS), 0, 1024), mdS = umma_smem_desc(smem_u32(sdS), SM::kPTile, 1024);
-    const uint64_t kdC = L::desc(smem_u32(sdC), 0), mdC = L::desc(smem_u32(sdC), SM::kState);
-    auto issue_s = [&](int it) {  // S^T = K Q^T, dSb^T = V dH^T of processing step `it` (its loads are in flight)
-      const uint64_t kQ = umma_desc_advance(kQ0, (it % SM::nQ) * SM::kTile), kK = umma_desc_advance(kK0, (it % SM::nK) * SM::kTile);
-      const uint64_t kH = umma_desc_advance(kH0, (it % SM::nH) * SM::kTile), kV = umma_desc_advance(kV0, (it % SM::nV) * SM::kTile);
-      mbar_wait(&bar_fa[it & 1], (it >> 1) & 1, 11);
-      tc_fence_after_sync();
-#pragma unroll
-      for (int kk = 0; kk < D / 16; ++kk)
-        umma_f16(tST, umma_desc_advance(kK, kk * 32), umma_desc_advance(kQ, kk * 32), id_s, kk > 0);
-      mbar_wait(&bar_fb[it & 1], (it >> 1) & 1, 11);
-      tc_fence_after_sync();
-#pragma unroll
-      for (int kk = 0; kk < D / 16; ++kk)
-        umma_f16(tdST, umma_desc_advance(kV, kk * 32), umma_desc_advance(kH, kk * 32), id_s, kk > 0);
-      umma_commit(&bar_s);
-    };
-
-    if (elect_one()) issue_s(0);
-    __syncwarp();
-
-    for (int it = 0; it < p.NT; ++it) {
-      const int c = p.NT - 1 - it, pb = it & 1;
-      const uint32_t par = it & 1;
-      const int t0 = mt(c) * LT, n_valid = min(LT, p.S - t0);
-      const uint64_t mQ = umma_desc_advance(mQ0, (it % SM::nQ) * SM::kTile), mK = umma_desc_advance(mK0, (it % SM::nK) * SM::kTile);
-      const uint64_t mH = umma_desc_advance(mH0, (it % SM::nH) * SM::kTile), kCs = umma_desc_advance(kCs0, (it % SM::nCs) * SM::kState);
-      TC_PROF(it, 9);
-      if (c > 0 && lane == 0) {  // inputs of the next tile
-        expect_step(it + 1);
-        if (SM::nK == 2) load_K(it + 1);  // double-buffered: the other buffer was released by the previous tile's batch
-        load_H(it + 1);
-        if (SM::nQ == 2) { load_Q(it + 1); load_V(it + 1); load_C(it + 1); }
-        else {  // single buffers: pull the rows into L2 now, so that the re-fills behind the MMA batch are L2 hits
-          const int r = mt(c - 1) * LT;
-          tma_prefetch_4d(&mapQ, 0, r, hh, b);
-          tma_prefetch_4d(&mapV, 0, r, hh, b);
-          tma_prefetch_4d(&mapCs, 0, mt(c - 1) * D, hh, b);
-          if (SM::nK == 1) tma_prefetch_4d(&mapK, 0, r, hh, b);
-        }
-      }
-      named_sync(NB_B, kNbAB);  // operands written, input rows read
-      TC_PROF(it, 10);
-      if (lane == 0) {
-        tma_store_wait_read<0>();  // the previous tile's dq / dk / dv stores (issued a W phase ago) have left their
-        mbar_arrive(&bar_st);      // staging buffers
-        mbar_wait(&bar_fc[it & 1], (it >> 1) & 1, 26);  // C_{k-1} has landed
-      }
-      __syncwarp();
-      // MMA batch.  Every 128 x 128 A operand that has the tile row on its M axis comes from TMEM (TS mode: no
-      // shared-memory read for A), the inter-chunk terms are accumulated into the same TMEM columns through
-      // row-scaled operand copies, so each output has ONE accumulator and needs no scaling in its epilogue.
-      if (elect_one()) {
-        tc_fence_after_sync();
-#pragma unroll
-        for (int kk = 0; kk < LT / 16; ++kk)  // dk  = dS^T Q            (A = packed dS^T in tdST)
-          umma_f16_ts(tdK, tdST + 32 * (kk / 2) + 8 * (kk % 2), umma_desc_advance(mQ, kk * L::kAdvMN), id_ts_mn, kk > 0);
-#pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk)   //     + (abar V) dC_k^T   (A = Vbar slots of tdST)
-          umma_f16_ts(tdK, half_op(tdST, 0, kk), umma_desc_advance(kdC, kk * 32), id_ts_k, true);
-        umma_commit(&bar_k);  // Q consumed; dk complete
-#pragma unroll
-        for (int kk = 0; kk < LT / 16; ++kk)  // dq  = dS K              (A = dS^T rows in shared memory, MN-major)
-          umma_f16(tdQ, umma_desc_advance(mdS, kk * 2048), umma_desc_advance(mK, kk * L::kAdvMN), id_mn_mn, kk > 0);
-      }
-      __syncwarp();
-      named_sync(NB_A, kNbAB);  // Kbar / dHbar copies written
-      if (elect_one()) {
-        tc_fence_after_sync();
-#pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk)   //     + (wb dH) C_{k-1}^T (A = dHbar slots of tST)
-          umma_f16_ts(tdQ, half_op(tST, 2, kk), umma_desc_advance(kCs, kk * 32), id_ts_k, true);
-        umma_commit(&bar_q);  // K, C_{k-1} consumed; dq complete
-#pragma unroll
-        for (int kk = 0; kk < LT / 16; ++kk)  // dv  = Sb'^T dH          (A = packed Sb'^T in tST)
-          umma_f16_ts(tdV, tST + 32 * (kk / 2) + 8 * (kk % 2), umma_desc_advance(mH, kk * L::kAdvMN), id_ts_mn, kk > 0);
-#pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk)   //     + (abar K) dC_k     (A = Kbar slots of tST)
-          umma_f16_ts(tdV, half_op(tST, 0, kk), umma_desc_advance(mdC, kk * L::kAdvMN), id_ts_mn, true);
-        umma_commit(&bar_v);  // dv complete (dC_k consumed)
-#pragma unroll
-        for (int kk = 0; kk < LT / 16; ++kk)  // ddC = Qt^T dH
-          umma_f16(tddC, umma_desc_advance(mQt, kk * L::kAdvMN), umma_desc_advance(mH, kk * L::kAdvMN), id_c, kk > 0);
-        umma_commit(&bar_d);  // dH consumed; last group of the batch
-      }
-      __syncwarp();
-      TC_PROF(it, 11);
-      if (c > 0 && elect_one()) {
-        if (SM::nQ == 1) {  // single-buffered inputs: re-fill each as soon as its last reader has completed
-          load_V(it + 1);   // V: only dSb^T (complete) and the workers (before NB_B) read it
-          mbar_wait(&bar_k, par, 21);
-          load_Q(it + 1);
-        }
-        mbar_wait(&bar_v, par, 25);  // the TS groups have read their packed TMEM operands (ddC, still queued, has none) (measured: an MMA that writes
-        issue_s(it + 1);             // TMEM columns may overtake the A-operand reads of the instruction before it)
-        if (SM::nQ == 1) {
-          mbar_wait(&bar_q, par, 24);
-          if (SM::nK == 1) load_K(it + 1);
-          load_C(it + 1);
-        }
-      }
-      __syncwarp();
-      TC_PROF(it, 13);
-      named_sync(NB_C, kNbC);  // dq / dk / dv staged, dC_{k-1} written
-      TC_PROF(it, 14);
-      if (lane == 0) {
-        tma_store_4d(&mapdQ, sdQ, 0, t0, hh, b);
-        tma_store_4d(&mapdV, sdV, 0, t0, hh, b);
-        tma_store_4d(&mapdK, sdK, 0, t0, hh, b);
-        tma_store_commit();
-      }
-      __syncwarp();
-    }
-    if (lane == 0) tma_store_wait_all<0>();
-  } else if (warp == kScanWarp) {
-    // =========================== scan warp: tile vectors two tiles ahead + dI / dF ==================
-    // raw per-tile vectors (gate inputs, saved m / n) are loaded one tile before they are scanned
-    struct TileRaw {
-      GateRaw<T> g;
-      float4 mt, nt;
-      float m_prev, m_next;
-    };
-    auto raw_of = [&](int c) {
-      TileRaw r;
-      const int t0 = mt(c) * LT, n_valid = min(LT, p.S - t0);
-      r.g = load_gate_raw<T>(ip + (int64_t)t0 * p.ig_ss, p.ig_ss, fp + (int64_t)t0 * p.fg_ss, p.fg_ss, n_valid);
-      if (lane * 4 < n_valid) {  // n_valid is a multiple of 4 (tensor_supported)
-        r.mt = *reinterpret_cast<const float4*>(mo + t0 + lane * 4);
-        r.nt = *reinterpret_cast<const float4*>(no + t0 + lane * 4);
-      } else {
-        r.mt = make_float4(0.f, 0.f, 0.f, 0.f);
-        r.nt = make_float4(1.f, 1.f, 1.f, 1.f);
-      }
-      // m of the state entering the tile = m_out of the previously processed token; m of the state leaving it
-      // = m_out of the tile's last processed token (its first memory row in the anti-causal direction)
-      if (!REV) {
-        r.m_prev = c > 0 ? mo[t0 - 1] : (p.m0 ? p.m0[bh] : 0.f);
-        r.m_next = mo[t0 + n_valid - 1];
-      } else {
-        r.m_prev = c > 0 ? mo[t0 + LT] : (p.m0 ? p.m0[bh] : 0.f);
-        r.m_next = mo[t0];
-      }
-      return r;
-    };
-    auto publish = [&](float* gb, const TileRaw& r) {
-      gate_scan_regs(gb, r.g, REV, p.sig != 0);
-      reinterpret_cast<float4*>(gb + GateBuf::oMt)[lane] = r.mt;
-      reinterpret_cast<float4*>(gb + GateBuf::oNt)[lane] = r.nt;
-      {  // column factors of W^T: X_t = (b_t - m_t) log2e + log2(scale / (n_t + eps)), -inf for tail tokens;
-         // per 32-column unit: XM_u = max X, cx_t = exp2(X_t - XM_u) <= 1 (rank-1 form of the blocks off the diagonal)
-        __syncwarp();
-        const float4 bb = reinterpret_cast<const float4*>(gb + GateBuf::oB)[lane];
-        const float bv[4] = {bb.x, bb.y, bb.z, bb.w}, mv[4] = {r.mt.x, r.mt.y, r.mt.z, r.mt.w},
-                    nv[4] = {r.nt.x, r.nt.y, r.nt.z, r.nt.w};
-        float X[4], xm = -INFINITY;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          X[e] = lane * 4 + e < r.g.n_valid ? (bv[e] - mv[e]) * kLog2e + log2f(p.scale / (nv[e] + p.eps)) : -INFINITY;
-          xm = fmaxf(xm, X[e]);
-        }
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) xm = fmaxf(xm, __shfl_xor_sync(0xffffffffu, xm, o));
-        xm = fmaxf(xm, -1e30f);
-        reinterpret_cast<float4*>(gb + GateBuf::oPm)[lane] = make_float4(X[0], X[1], X[2], X[3]);
-        reinterpret_cast<float4*>(gb + GateBuf::oCf)[lane] =
-            make_float4(ex2_approx(X[0] - xm), ex2_approx(X[1] - xm), ex2_approx(X[2] - xm), ex2_approx(X[3] - xm));
-        if ((lane & 7) == 0) gb[GateBuf::oScal + 4 + (lane >> 3)] = xm;
-      }
-      if (lane == 0) {
-        gb[GateBuf::oScal + 2] = r.m_prev;
-        gb[GateBuf::oScal + 3] = r.m_next;
-      }
-    };
-
-    TileRaw raw = raw_of(p.NT - 1);
-    float carry = 0.f;  // running suffix sum of (q.dq - k.dk)
-    // n = processing index of the tile whose vectors are published; the dI / dF scan lags two tiles
-    for (int n = 0; n < p.NT + 2; ++n) {
-      if (n >= 2) {
-      const int it = n - 2;
-      const int c = p.NT - 1 - it, pb = it & 1;
-      const int t0 = mt(c) * LT, n_valid = min(LT, p.S - t0);
-      named_sync(NB_C, kNbC);  // row dots of tile `it` are in shared memory; its buffers can be reused afterwards
-      // ---- gate gradients: reverse (suffix) scan over the tile, carried across tiles -------------
-      {
-        const float* sp = fsm + SM::fPart + pb * 6 * LT;
-        const float* gb = fsm + SM::fGates + pb * GateBuf::kFloats;
-        float acc[4], di[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int t = lane * 4 + e;
-          acc[e] = (sp[0 * LT + t] + sp[1 * LT + t]) - (sp[2 * LT + t] + sp[3 * LT + t]);  // bw.py:321
-          di[e] = sp[4 * LT + t] + sp[5 * LT + t];                                         // bw.py:326
-        }
-        // sum over all tokens processed AFTER t: a suffix sum over memory rows, or a prefix sum when the
-        // forward ran anti-causally (this sweep then visits the memory tiles in ascending order)
-        float incl, own;
-        if (!REV) {
-          acc[2] += acc[3];
-          acc[1] += acc[2];
-          acc[0] += acc[1];
-          incl = own = acc[0];
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            float u = __shfl_down_sync(0xffffffffu, incl, o);
-            if (lane + o < 32) incl += u;
-          }
-        } else {
-          acc[1] += acc[0];
-          acc[2] += acc[1];
-          acc[3] += acc[2];
-          incl = own = acc[3];
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            float u = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += u;
-          }
-        }
-        const float excl = incl - own + carry;
-        T* dip = (T*)p.di + b * p.di_sb + hh * p.di_sh;
-        T* dfp = (T*)p.df + b * p.df_sb + hh * p.df_sh;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int t = lane * 4 + e;
-          if (t < n_valid) {
-            const float dsig = p.sig ? 1.f - __expf(gb[GateBuf::oI + t]) : 1.f;  // sigmoid(-i) = 1 - exp(logsigmoid(i))
-            dip[(int64_t)(t0 + t) * p.di_ss] = from_f32<T>(di[e] * dsig);
-            dfp[(int64_t)(t0 + t) * p.df_ss] =
-                from_f32<T>((acc[e] + excl) * sigmoid_neg_f32(gb[GateBuf::oF + t]));  // bw.py:322-323
-          }
-        }
-        carry += __shfl_sync(0xffffffffu, incl, REV ? 31 : 0);
-      }
-      __syncwarp();
-      }
-      if (n < p.NT) {
-        publish(fsm + SM::fGates + (n & 1) * GateBuf::kFloats, raw);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&bar_g[n & 1]);
-        if (n + 1 < p.NT) raw = raw_of(p.NT - 2 - n);
-      }
-    }
-  } else {
-    // =========================== worker warps ===================================================
-    for (int it = 0; it < p.NT; ++it) {
-      const int pb = it & 1;
-      const uint32_t par = it & 1;
-      const float* gb = fsm + SM::fGates + pb * GateBuf::kFloats;
-      float* spart = fsm + SM::fPart + pb * 6 * LT;
-      const int n_valid = min(LT, p.S - mt(p.NT - 1 - it) * LT);
-      const bool valid = row < n_valid;
-
-      TC_PROF(it, 0);
-      mbar_wait(&bar_g[pb], (it >> 1) & 1, 12);
-      const float g = gb[GateBuf::oScal], m_prev = gb[GateBuf::oScal + 2], m_next = gb[GateBuf::oScal + 3];
-      const float b_t = gb[GateBuf::oB + row], i_t = gb[GateBuf::oI + row];
-      const float m_t = gb[GateBuf::oMt + row], n_t = gb[GateBuf::oNt + row];
-      const float rinv = valid ? 1.f / (n_t + p.eps) : 0.f;         // bw.py:135
-      const float bbar = valid ? __expf(b_t + m_prev - m_t) : 0.f;  // bw.py:186
-      const float abar = __expf(g - b_t + i_t - m_next);            // bw.py:187 (0 for tail tokens)
-      const float gbar = __expf(g + m_prev - m_next);               // bw.py:76
-      TC_PROF(it, 1);
-      // ---- Qt = wq . Q, written while the S / dSb MMAs of this tile run (ddC of the previous tile, the last
-      // reader of sQt, completed before the previous dC update); q row slice kept for the gate gradients
-      mbar_wait(&bar_fa[it & 1], (it >> 1) & 1, 13);
-      uint32_t qs[CW / 2];
-      {
-        const float wq = p.scale * bbar * rinv;  // bw.py:83-90
-#pragma unroll
-        for (int j = 0; j < CW / 8; ++j) {
-          const uint32_t off = L::swz(row, ch * CW + 8 * j);
-          uint4 u = *reinterpret_cast<const uint4*>(sQ + (it % SM::nQ) * SM::kTile + off);
-          qs[4 * j] = u.x; qs[4 * j + 1] = u.y; qs[4 * j + 2] = u.z; qs[4 * j + 3] = u.w;
-          float2 a0 = unpack2<T>(u.x), a1 = unpack2<T>(u.y), a2 = unpack2<T>(u.z), a3 = unpack2<T>(u.w);
-          u.x = pack2<T>(a0.x * wq, a0.y * wq);
-          u.y = pack2<T>(a1.x * wq, a1.y * wq);
-          u.z = pack2<T>(a2.x * wq, a2.y * wq);
-          u.w = pack2<T>(a3.x * wq, a3.y * wq);
-          *reinterpret_cast<uint4*>(sQt + off) = u;
-        }
-      }
-      // ---- W^T (this thread: key / value row s = row, its two 32-column units of query columns t) ------------
-      //   W_ts = exp2(X_t + Y_s) for t >= s (mirrored in the anti-causal direction), Y_s = (i_s - b_s) log2e;
-      //   Sb'^T = scale S^T W^T and dS^T = scale dSb^T W^T are packed in place (TMEM A operands of dv / dk),
-      //   dS^T rows also go to shared memory (MN-major A operand of dq = dS K)
-      mbar_wait(&bar_s, par, 14);
-      tc_fence_after_sync();
-      TC_PROF(it, 2);
-      {
-        const float y_s = gb[GateBuf::oY + row];
-        const float* sx = gb + GateBuf::oPm;
-        const float* scx = gb + GateBuf::oCf;
-#pragma unroll 1
-        for (int u = ch; u < 4; u += 2) {  // warp-uniform branches
-          float v[32], w[32];
-          const bool nonzero = REV ? u <= rb : u >= rb;
-          if (nonzero) {
-            uint32_t rv[32], rw[32];
-            tmem_ld32_nowait(tST + lane_base + u * 32, rv);
-            tmem_ld32_nowait(tdST + lane_base + u * 32, rw);
-            tmem_ld_wait();
-            if (u != rb) {  // fully unmasked 32x32 block: rank-1 weights, one exp per row
-              const float r_s = ex2_approx(y_s + gb[GateBuf::oScal + 4 + u]);
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 cf = *reinterpret_cast<const float4*>(scx + u * 32 + 4 * j4);
-                const float cc[4] = {cf.x, cf.y, cf.z, cf.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int j = 4 * j4 + e;
-                  const float wg = cc[e] * r_s;
-                  v[j] = __uint_as_float(rv[j]) * wg;
-                  w[j] = __uint_as_float(rw[j]) * wg;
-                }
-              }
-            } else {  // diagonal block: mask, one exp per entry
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 x = *reinterpret_cast<const float4*>(sx + u * 32 + 4 * j4);
-                const float xx[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int j = 4 * j4 + e;
-                  float wg = ex2_approx(xx[e] + y_s);
-                  wg = (REV ? j <= lane : j >= lane) ? wg : 0.f;
-                  v[j] = __uint_as_float(rv[j]) * wg;
-                  w[j] = __uint_as_float(rw[j]) * wg;
-                }
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { v[j] = 0.f; w[j] = 0.f; }
-          }
-          uint32_t pv[16], pw[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            pv[j] = pack2<T>(v[2 * j], v[2 * j + 1]);
-            pw[j] = pack2<T>(w[2 * j], w[2 * j + 1]);
-          }
-          tmem_st16(tST + lane_base + u * 32, pv);
-          tmem_st16(tdST + lane_base + u * 32, pw);
-          if (nonzero || it == 0) {  // the zero blocks of the shared-memory copy are written once
-            uint8_t* tile = sdS + (u >> 1) * SM::kPTile;
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<uint4*>(tile + swz128(row, (u & 1) * 32 + 8 * j)) =
-                  make_uint4(pw[4 * j], pw[4 * j + 1], pw[4 * j + 2], pw[4 * j + 3]);
-          }
-        }
-      }
-      // ---- row-scaled operand copies into the free TMEM slots; k / v row slices kept for the gate gradients ----
-      mbar_wait(&bar_fb[it & 1], (it >> 1) & 1, 13);
-      uint32_t ks[CW / 2], vs[CW / 2];
-      {
-        uint32_t ob[CW / 2];
-        const T ab = from_f32<T>(abar);
-        const T wbs = from_f32<T>(p.scale * bbar * rinv);
-#pragma unroll
-        for (int j = 0; j < CW / 8; ++j) {
-          const uint32_t off = L::swz(row, ch * CW + 8 * j);
-          const uint4 uk = *reinterpret_cast<const uint4*>(sK + (it % SM::nK) * SM::kTile + off);
-          ks[4 * j] = uk.x; ks[4 * j + 1] = uk.y; ks[4 * j + 2] = uk.z; ks[4 * j + 3] = uk.w;
-          const uint4 uv = *reinterpret_cast<const uint4*>(sV + (it % SM::nV) * SM::kTile + off);
-          vs[4 * j] = uv.x; vs[4 * j + 1] = uv.y; vs[4 * j + 2] = uv.z; vs[4 * j + 3] = uv.w;
-        }
-#pragma unroll
-        for (int j = 0; j < CW / 2; ++j) ob[j] = mul2<T>(vs[j], ab);   // Vbar = abar v  (bw.py:192)
-        tmem_st(slot(tdST, ch) + lane_base, ob);
-        // first hand-off: everything the dk group and the shared-memory half of the dq group need
-        tmem_st_wait();
-        fence_proxy_async_smem();
-        tc_fence_before_sync();
-        named_arrive(NB_B, kNbAB);
-        TC_PROF(it, 3);
-#pragma unroll
-        for (int j = 0; j < CW / 2; ++j) ob[j] = mul2<T>(ks[j], ab);   // Kbar = abar k  (bw.py:190)
-        tmem_st(slot(tST, ch) + lane_base, ob);
-#pragma unroll
-        for (int j = 0; j < CW / 8; ++j) {
-          const uint4 uh = *reinterpret_cast<const uint4*>(sdH + (it % SM::nH) * SM::kTile + L::swz(row, ch * CW + 8 * j));
-          ob[4 * j] = mul2<T>(uh.x, wbs); ob[4 * j + 1] = mul2<T>(uh.y, wbs);
-          ob[4 * j + 2] = mul2<T>(uh.z, wbs); ob[4 * j + 3] = mul2<T>(uh.w, wbs);  // dHbar = scale bbar/(n+eps) dh (bw.py:193)
-        }
-        tmem_st(slot(tST, ch + 2) + lane_base, ob);
-      }
-      // second hand-off: the row-scaled copies the remaining TS instructions read (written while the dk group runs)
-      tmem_st_wait();
-      tc_fence_before_sync();
-      named_arrive(NB_A, kNbAB);
-      TC_PROF(it, 4);
-      // ---- epilogues (one accumulator per output, no scaling), pipelined with the MMA batch ------------------
-      {
-        uint32_t ra[CW];
-        float o[CW];
-        float dot;
-        // dk
-        mbar_wait(&bar_k, par, 18);
-        tc_fence_after_sync();
-        TC_PROF(it, 5);
-        tmem_ld_nowait(tdK + lane_base + ch * CW, ra);
-        tmem_ld_wait();
-        dot = 0.f;
-#pragma unroll
-        for (int j = 0; j < CW / 2; ++j) {
-          o[2 * j] = __uint_as_float(ra[2 * j]);  // bw.py:170,192
-          o[2 * j + 1] = __uint_as_float(ra[2 * j + 1]);
-          float2 kv = unpack2<T>(ks[j]);
-          dot += kv.x * o[2 * j] + kv.y * o[2 * j + 1];
-        }
-        mbar_wait(&bar_st, par, 19);  // staging buffers free (the previous tile's stores have read them)
-        store_cols<T, D>(sdK, row, ch * CW, o);
-        spart[(1 * 2 + ch) * LT + row] = dot;
-        // dq
-        mbar_wait(&bar_q, par, 16);
-        tc_fence_after_sync();
-        TC_PROF(it, 6);
-        tmem_ld_nowait(tdQ + lane_base + ch * CW, ra);
-        tmem_ld_wait();
-        dot = 0.f;
-#pragma unroll
-        for (int j = 0; j < CW / 2; ++j) {
-          o[2 * j] = __uint_as_float(ra[2 * j]);  // bw.py:169,193
-          o[2 * j + 1] = __uint_as_float(ra[2 * j + 1]);
-          float2 qv = unpack2<T>(qs[j]);
-          dot += qv.x * o[2 * j] + qv.y * o[2 * j + 1];
-        }
-        store_cols<T, D>(sdQ, row, ch * CW, o);
-        spart[(0 * 2 + ch) * LT + row] = dot;
-      }
-      // ---- dv ---------------------------------------------------------------------------------------
-      {
-        uint32_t ra[CW];
-        float o[CW];
-        float dot = 0.f;
-        mbar_wait(&bar_v, par, 17);
-        tc_fence_after_sync();
-        tmem_ld_nowait(tdV + lane_base + ch * CW, ra);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < CW / 2; ++j) {
-          o[2 * j] = __uint_as_float(ra[2 * j]);  // bw.py:164,190
-          o[2 * j + 1] = __uint_as_float(ra[2 * j + 1]);
-          float2 vv = unpack2<T>(vs[j]);
-          dot += vv.x * o[2 * j] + vv.y * o[2 * j + 1];
-        }
-        store_cols<T, D>(sdV, row, ch * CW, o);
-        spart[(2 * 2 + ch) * LT + row] = dot;
-      }
-      // ---- dC_{k-1} = gbar dC_k + ddC ----------------------------------------------------------------
-      mbar_wait(&bar_d, par, 15);
-      tc_fence_after_sync();
-      TC_PROF(it, 7);
-      {
-        float v[CW];
-        tmem_ld(tddC + lane_base + ch * CW, v);
-        if (owns_c) {
-#pragma unroll
-          for (int j = 0; j < CW; ++j) dCreg[j] = gbar * dCreg[j] + v[j];  // bw.py:93-95
-          store_cols<T, D>(sdC, drow, ch * CW, dCreg);                     // its readers (dk, dv groups) have completed
-        }
-      }
-      fence_proxy_async_smem();
-      tc_fence_before_sync();
-      named_arrive(NB_C, kNbC);
-      TC_PROF(it, 8);
-    }
-    if (p.dc0 && owns_c) {  // dC_initial = dC_0 (bw.py:329-331)
-      float* dst = p.dc0 + ((int64_t)bh * D + drow) * D + ch * CW;
-#pragma unroll
-      for (int j = 0; j < CW; ++j) dst[j] = dCreg[j];
-    }
-  }
-  TC_PROF(200, 1);  // this role is done
-  tc_fence_before_sync();
-  __syncthreads();
-  TC_PROF(200, 2);
-  TC_PROF_CTA(1);
-  if (warp == kCtlWarp) tmem_dealloc<512>(tmem);
-}
-
-// <<< BW2 END
-long long* g_prof = nullptr;  // debug hook, see tensor_set_clock_buffer
+#ifdef MLSTM_TC_PROFILE
+// Phase-clock buffer of the PROFILE build only (lib/libmlstm_b200_prof.so, tools/phase_clocks.py); the product
+// library carries no process-global mutable state: tensor_set_clock_buffer is a no-op there.
+std::atomic<long long*> g_prof{nullptr};
+#define TC_SET_PROF(p, off) (p).prof = g_prof.load() ? g_prof.load() + (off) : nullptr
+#else
+#define TC_SET_PROF(p, off)
+#endif
 
 int num_sms() {
   static int n = 0;
@@ -2442,33 +1821,9 @@ int launch_fw_d128(const TcFwParams& p, const CUtensorMap& mq, const CUtensorMap
 }
 
 template <typename T, int D>
-int launch_bw2(const TcBwParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
-               const CUtensorMap& mdh, const CUtensorMap& mcs, const CUtensorMap& mdq, const CUtensorMap& mdk,
-               const CUtensorMap& mdv, cudaStream_t st) {
-  using SM = Bw2Smem<D>;
-  auto kern = p.rev ? tc_bw2<T, D, true> : tc_bw2<T, D, false>;
-  MLSTM_CUDA_CHECK(ensure_smem(kern, SM::kBytes));
-  kern<<<p.B * p.NH, kTcThreads, SM::kBytes, st>>>(mq, mk, mv, mdh, mcs, mdq, mdk, mdv, p);
-  MLSTM_CUDA_CHECK(cudaGetLastError());
-  return 0;
-}
-
-// which backward formulation: 1 = tc_bw (default), 2 = transposed tc_bw2 (MLSTM_B200_BW=2 in the environment or
-// mlstm_b200_debug_set_bw_variant)
-int g_bw_variant = 0;
-int bw_variant() {
-  if (!g_bw_variant) {
-    const char* e = getenv("MLSTM_B200_BW");
-    g_bw_variant = (e && e[0] == '2') ? 2 : 1;
-  }
-  return g_bw_variant;
-}
-
-template <typename T, int D>
 int launch_bw(const TcBwParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
               const CUtensorMap& mdh, const CUtensorMap& mcs, const CUtensorMap& mdq, const CUtensorMap& mdk,
               const CUtensorMap& mdv, cudaStream_t st) {
-  if (bw_variant() == 2) return launch_bw2<T, D>(p, mq, mk, mv, mdh, mcs, mdq, mdk, mdv, st);
   using SM = BwSmem<D>;
   auto kern = p.rev ? tc_bw<T, D, true> : tc_bw<T, D, false>;
   MLSTM_CUDA_CHECK(ensure_smem(kern, SM::kBytes));
@@ -2529,7 +1884,7 @@ int run_fw(const mlstm_b200_fw_args& a, void* c_states, cudaStream_t st) {
   p.rev = s.reverse ? 1 : 0;
   p.sig = s.siging ? 1 : 0;
   p.store_states = c_states != nullptr;
-  p.prof = g_prof;
+  TC_SET_PROF(p, 0);
   if (s.DHQK == 128) {
     if (s.dtype == MLSTM_B200_BF16) return launch_fw_d128<__nv_bfloat16>(p, mq, mk, mv, mh, mcs, st);
     return launch_fw_d128<__half>(p, mq, mk, mv, mh, mcs, st);
@@ -2677,8 +2032,8 @@ int bw128_by_blocks(const mlstm_b200_bw_args& a, cudaStream_t st) {
       sub.shape = block_shape(s);
       sub.q = cols(a.q, qa); sub.k = cols(a.k, qa); sub.v = cols(a.v, vb); sub.dh = cols(a.dh, vb);
       // With the forward's saved states (tc_fw_d128 stores them block-wise) every problem loads its block; without
-      // them -- or for the transposed variant, which keeps its own coordinates -- it recomputes its slice.
-      const bool saved = a.c_states != nullptr && bw_variant() == 1;
+      // them it recomputes its slice.
+      const bool saved = a.c_states != nullptr;
       sub.c_states = nullptr;
       sub.workspace = ws + w.off_sub; sub.workspace_bytes = w.sub_bytes;
       if (a.c_initial && !saved) {
@@ -2735,13 +2090,14 @@ int bw128_by_blocks(const mlstm_b200_bw_args& a, cudaStream_t st) {
 
 }  // namespace
 
-void tensor_set_clock_buffer(void* dev_ptr) { g_prof = (long long*)dev_ptr; }
-bool tensor_context_is_current() { return sm100_host::context_is_current(); }
-int tensor_set_bw_variant(int variant) {
-  const int prev = bw_variant();
-  if (variant == 1 || variant == 2) g_bw_variant = variant;
-  return prev;
+void tensor_set_clock_buffer(void* dev_ptr) {
+#ifdef MLSTM_TC_PROFILE
+  g_prof.store((long long*)dev_ptr);
+#else
+  (void)dev_ptr;
+#endif
 }
+bool tensor_context_is_current() { return sm100_host::context_is_current(); }
 
 // forward: d = 32, 64 and 128; backward: d = 32 and 64 natively, d = 128 as four d = 64 block problems (bw128_by_blocks)
 bool tensor_supported(const mlstm_b200_shape& s, int backward) {
@@ -2828,7 +2184,7 @@ int run_bw(const mlstm_b200_bw_args& a, const void* c_states, int block, cudaStr
   p.sig = s.siging ? 1 : 0;
   p.cs_rows = block < 0 ? D : 256;
   p.cs_off = block < 0 ? 0 : 64 * block;
-  p.prof = g_prof ? g_prof + 4096 : nullptr;
+  TC_SET_PROF(p, 4096);
   int e;
   if (s.DHQK == 32)
     e = s.dtype == MLSTM_B200_BF16 ? launch_bw<__nv_bfloat16, 32>(p, mq, mk, mv, mdh, mcs, mdq, mdk, mdv, st)
