@@ -165,33 +165,34 @@ def test_cellout_without_device_returns_error(lib):
     assert st != 0 and lib.mlstm_b200_last_error() != b""
 
 
+class _PCell(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.dim, self.num_heads, self.gate_soft_cap = 256, 4, 15.0
+        self.use_autocast, self.autocast_dtype = True, torch.float16
+        self.ifgate = torch.nn.Linear(768, 8)
+
+class _PLayer(torch.nn.Module):
+    def __init__(self, heads_ok=True):
+        super().__init__()
+        self.direction = "ROWWISE_FROM_BOT_RIGHT"
+        self.proj_up = torch.nn.Linear(128, 512)
+        self.conv = torch.nn.Conv2d(256, 256, 3, padding=1, groups=256)
+        self.qk_proj, self.v_proj = torch.nn.Linear(256, 512), torch.nn.Linear(256, 256)
+        self.mlstm_cell = _PCell()
+        if not heads_ok:
+            self.mlstm_cell.num_heads = 5  # 256 / 5: geometry the fused output kernel does not cover
+        self.learnable_skip = torch.nn.Parameter(torch.ones(256))
+        self.proj_down = torch.nn.Linear(256, 128)
+        self.norm, self.ffn_norm = torch.nn.RMSNorm(256, eps=1e-6), torch.nn.RMSNorm(100, eps=1e-6)
+
+
 def test_patch_layers_rebinds_without_a_gpu():
     """Host logic of the fused-layer rebinding (vil.patch_layers): ViLLayer-shaped modules get the new branch and
     norm forwards; the norm keeps working for CPU tensors (torch's own forward), the branch refuses them."""
     import xlstm_yolo_clean_b200 as pkg
 
-    class Cell(torch.nn.Module):
-        def __init__(self):
-            super().__init__()
-            self.dim, self.num_heads, self.gate_soft_cap = 256, 4, 15.0
-            self.use_autocast, self.autocast_dtype = True, torch.float16
-            self.ifgate = torch.nn.Linear(768, 8)
-
-    class Layer(torch.nn.Module):
-        def __init__(self, heads_ok=True):
-            super().__init__()
-            self.direction = "ROWWISE_FROM_BOT_RIGHT"
-            self.proj_up = torch.nn.Linear(128, 512)
-            self.conv = torch.nn.Conv2d(256, 256, 3, padding=1, groups=256)
-            self.qk_proj, self.v_proj = torch.nn.Linear(256, 512), torch.nn.Linear(256, 256)
-            self.mlstm_cell = Cell()
-            if not heads_ok:
-                self.mlstm_cell.num_heads = 5  # 256 / 5: geometry the fused output kernel does not cover
-            self.learnable_skip = torch.nn.Parameter(torch.ones(256))
-            self.proj_down = torch.nn.Linear(256, 128)
-            self.norm, self.ffn_norm = torch.nn.RMSNorm(256, eps=1e-6), torch.nn.RMSNorm(100, eps=1e-6)
-
-    model = torch.nn.Sequential(Layer(), Layer(heads_ok=False), torch.nn.Linear(4, 4))
+    model = torch.nn.Sequential(_PLayer(), _PLayer(heads_ok=False), torch.nn.Linear(4, 4))
     assert pkg.patch_layers(model) == 1
     a, b = model[0], model[1]
     assert "mlstm_branch" in a.__dict__ and "mlstm_branch" not in b.__dict__
@@ -201,3 +202,27 @@ def test_patch_layers_rebinds_without_a_gpu():
     with pytest.raises(RuntimeError, match="no CPU path"):
         a.mlstm_branch(torch.randn(1, 16, 128))
     assert pkg.vil._is_reverse(a)
+
+
+def test_patched_model_survives_deepcopy_and_torch_save(tmp_path):
+    """The reference trainer checkpoints whole modules -- torch.save({'ema': deepcopy(ema).half(), ...}),
+    ultralytics/engine/trainer.py:517-540 -- so a patched model must pickle, load back, and stay bound to ITSELF
+    (not to the module it was copied from)."""
+    import copy
+
+    import xlstm_yolo_clean_b200 as pkg
+
+    model = torch.nn.Sequential(_PLayer(), torch.nn.Linear(4, 4))
+    assert pkg.patch_layers(model, siging=True) == 1
+    path = tmp_path / "last.pt"
+    torch.save({"model": copy.deepcopy(model).half(), "epoch": 3}, path)
+    loaded = torch.load(path, weights_only=False)["model"]
+    for m in (copy.deepcopy(model), loaded):
+        layer = m[0]
+        assert "mlstm_branch" in layer.__dict__ and "forward" in layer.norm.__dict__
+        assert layer.mlstm_branch.args[0] is layer and layer.norm.forward.args[0] is layer.norm  # re-bound to the copy
+        assert layer.mlstm_branch.keywords == {"siging": True, "kernel_dtype": "bfloat16"}
+        x = torch.randn(2, 9, 256, dtype=layer.norm.weight.dtype)
+        assert torch.allclose(layer.norm(x), torch.nn.functional.rms_norm(x, (256,), layer.norm.weight, 1e-6))
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            layer.mlstm_branch(torch.randn(1, 16, 128, dtype=layer.norm.weight.dtype))

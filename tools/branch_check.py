@@ -28,7 +28,7 @@ def rel(a, b):
 
 for yaml_name in sys.argv[1:] or ["640-base192.yaml", "640-base256.yaml", "640-base384.yaml"]:
     model = MB._build_model(yaml_name, dev)
-    pkg.patch_model(model)  # unfused: reference modules + chunkwise--b200
+    pkg.patch_model(model, siging=False)  # unfused: reference modules + chunkwise--b200 (exp gate, the oracle function)
     stats = []
     for mod in model.modules():
         if hasattr(mod, "mlstm_cell") and hasattr(mod, "proj_up"):

@@ -359,14 +359,23 @@ def register(name: str = KERNEL_NAME) -> str:
     return f"chunkwise--{name}"
 
 
+def _cell_uses_siging(cell) -> bool:
+    """True if the cell's current CUDA backend is a sigmoid-input-gate kernel (its ``chunkwise_kernel`` name
+    carries ``siging``: ``chunkwise--triton_xl_chunk_siging`` in the reference, vision_lstm2.py:685-697)."""
+    cfg = getattr(getattr(cell, "gpu_backend", None), "config", None)
+    return "siging" in str(getattr(cfg, "chunkwise_kernel", ""))
+
+
 def patch_model(model: torch.nn.Module, name: str = KERNEL_NAME, mode: str = "train_with_padding",
-                siging: bool = False, fused: bool = False, kernel_dtype: str = "bfloat16",
+                siging: Optional[bool] = None, fused: bool = False, kernel_dtype: str = "bfloat16",
                 keep_activations: bool = False) -> int:
     """Point ``gpu_backend`` of every MatrixLSTMCell (vision_lstm2.py:685-697) at the B200 kernel.
 
-    ``siging=True`` selects the sigmoid-input-gate variant, i.e. the same function the reference's
-    CUDA default (``chunkwise--triton_xl_chunk_siging``) computes, so released weights keep their meaning;
-    the default is the exp-gate / max-state path the reference runs on CPU (SURVEY.md finding 6).
+    ``siging=None`` (default) keeps the FUNCTION each cell computes on CUDA: a cell whose ``gpu_backend`` is a
+    sigmoid-input-gate kernel -- the reference's CUDA default ``chunkwise--triton_xl_chunk_siging`` (sigmoid
+    input gate, denominator max(|n|, 1)) -- gets ``chunkwise--b200_siging``, so released weights keep their
+    meaning; any other cell gets the exp-gate / max-state kernel.  ``siging=True`` / ``False`` force one variant
+    for every cell (``False`` = the function the reference runs on CPU, SURVEY.md finding 6; the parity oracle).
     ``fused=True`` additionally rebinds ``ViLLayer.mlstm_branch`` (vision_lstm2.py:292-312) to
     ``vil.mlstm_branch_b200``: same parameters and function, but the cell's output stage (MultiHeadLayerNorm +
     relayout + learnable skip) runs as one fused CUDA pass each way, the bottom-right direction uses the
@@ -380,14 +389,17 @@ def patch_model(model: torch.nn.Module, name: str = KERNEL_NAME, mode: str = "tr
     """
     from mlstm_kernels.torch.backend_module import mLSTMBackend, mLSTMBackendConfig
 
-    full = register(name) + ("_siging" if siging else "")
-    n = 0
+    base = register(name)
+    n = n_sig = 0
     for mod in model.modules():
         if hasattr(mod, "gpu_backend") and hasattr(mod, "cpu_backend"):
+            sig = _cell_uses_siging(mod) if siging is None else bool(siging)
             mod.gpu_backend = mLSTMBackend(mLSTMBackendConfig(
-                chunkwise_kernel=full, sequence_kernel="native_sequence__native", step_kernel="native", mode=mode,
-                return_last_states=False, chunk_size=64, eps=1e-6, autocast_kernel_dtype="bfloat16"))
+                chunkwise_kernel=base + ("_siging" if sig else ""), sequence_kernel="native_sequence__native",
+                step_kernel="native", mode=mode, return_last_states=False, chunk_size=64, eps=1e-6,
+                autocast_kernel_dtype="bfloat16"))
             n += 1
+            n_sig += int(sig)
     if keep_activations:
         for mod in model.modules():
             if hasattr(mod, "ckpt_thresh"):

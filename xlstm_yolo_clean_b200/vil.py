@@ -30,7 +30,7 @@ import torch.nn.functional as F
 from . import _cabi
 from torch.amp import custom_bwd, custom_fwd
 
-from .backend import (_DTYPES, _on_device, _tensor, mlstm_chunkwise__b200, mlstm_chunkwise_bw, mlstm_chunkwise_fw,
+from .backend import (_DTYPES, _cell_uses_siging, _on_device, _tensor, mlstm_chunkwise__b200, mlstm_chunkwise_bw, mlstm_chunkwise_fw,
                       mlstm_siging_chunkwise__b200, tensor_path_supported)
 
 
@@ -340,11 +340,30 @@ def mlstm_branch_b200(layer, x, siging=False, kernel_dtype="bfloat16"):
     return layer.proj_down(y)
 
 
-def patch_layers(model: torch.nn.Module, siging: bool = False, kernel_dtype: str = "bfloat16") -> int:
+def _branch_entry(layer, x, siging=False, kernel_dtype="bfloat16"):
+    """What ``patch_layers`` binds as ``layer.mlstm_branch`` (module-level, so that a patched model pickles)."""
+    return mlstm_branch_b200(layer, x, siging=siging, kernel_dtype=kernel_dtype)
+
+
+def _norm_entry(norm, x):
+    """What ``patch_layers`` binds as ``norm.forward``: the fused RMSNorm for CUDA tensors, torch's own otherwise."""
+    if x.is_cuda:
+        return rms_norm_b200(x, norm.weight, 1e-6 if norm.eps is None else norm.eps)
+    return torch.nn.RMSNorm.forward(norm, x)
+
+
+def patch_layers(model: torch.nn.Module, siging=None, kernel_dtype: str = "bfloat16") -> int:
     """Rebind ``mlstm_branch`` of every ViLLayer-shaped module (``proj_up``, ``qk_proj``, ``v_proj``, ``mlstm_cell``,
     ``learnable_skip``, ``proj_down``; vision_lstm2.py:218-290) whose head geometry the fused output kernel covers to
-    ``mlstm_branch_b200``.  Parameters and state-dict keys are untouched.  Returns the number of layers rebound."""
-    import types
+    ``mlstm_branch_b200``.  Parameters and state-dict keys are untouched.  Returns the number of layers rebound.
+    ``siging=None`` keeps the gate function of each layer's cell (sigmoid input gate iff the cell's CUDA backend is
+    a ``*siging*`` kernel, as in the reference model); True / False force it.
+
+    The overrides are ``functools.partial`` objects over module-level functions, so a patched model (or its EMA
+    copy) survives ``copy.deepcopy`` and the whole-module ``torch.save`` / ``torch.load`` the reference trainer
+    uses for last.pt / best.pt (ultralytics/engine/trainer.py:517-540): the partial's bound module is pickled as
+    part of the same object graph and re-bound to the loaded / copied module."""
+    import functools
 
     n = 0
     for mod in model.modules():
@@ -353,13 +372,11 @@ def patch_layers(model: torch.nn.Module, siging: bool = False, kernel_dtype: str
             continue
         if not cellout_supported(cell.num_heads, cell.dim // cell.num_heads):
             continue
-        mod.mlstm_branch = types.MethodType(
-            lambda self, x, _s=siging, _k=kernel_dtype: mlstm_branch_b200(self, x, siging=_s, kernel_dtype=_k), mod)
+        sig = _cell_uses_siging(cell) if siging is None else bool(siging)
+        mod.mlstm_branch = functools.partial(_branch_entry, mod, siging=sig, kernel_dtype=kernel_dtype)
         for norm in (getattr(mod, "norm", None), getattr(mod, "ffn_norm", None)):  # the RMSNorms in front of the branches
             if (isinstance(norm, torch.nn.RMSNorm) and len(norm.normalized_shape) == 1
                     and norm.normalized_shape[0] in RMSNORM_DIMS):
-                norm.forward = types.MethodType(
-                    lambda self, x: rms_norm_b200(x, self.weight, 1e-6 if self.eps is None else self.eps)
-                    if x.is_cuda else torch.nn.RMSNorm.forward(self, x), norm)
+                norm.forward = functools.partial(_norm_entry, norm)
         n += 1
     return n
