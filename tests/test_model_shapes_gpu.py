@@ -1,0 +1,124 @@
+"""Parity at the REAL per-GPU call shapes of BASELINE configs 3, 4 and 5:
+
+    640-base256 (config 4, 32 img / GPU)   (32,  8, 6400,  64)   256 CTAs  = 1.73 waves on 148 SMs
+    640-base192 (config 3, 64 img)         (64, 12, 6400,  32)   768 CTAs, two head-dim-32 CTAs per SM
+                                           (64, 12, 1600,  32)
+    640-base384 (config 5, 16 img / GPU)   (16,  6, 6400, 128)    96 CTAs
+
+i.e. grids larger than the machine, co-resident CTAs sharing TMEM and shared memory, and the head-dim-128 path --
+what the small-shape parity tests never launch.  Every case runs forward + backward on the tensor-core path in bf16
+and fp16, causal and anti-causal, and checks h, n_out, m_out, dq, dk, dv, di, df
+
+  * against the float64 oracle on three (batch, head) slices spread over the grid (first, middle, last CTA), at the
+    north_star tolerance (2e-2 relative for 16-bit inputs), and
+  * against the exact fp32-FFMA kernel family (itself pinned to the oracle at 1e-5 in test_parity_gpu.py) on EVERY
+    (batch, head) of the call, so that a wrong CTA anywhere in the grid is caught.
+
+The reference path these shapes come from: MatrixLSTMCell.forward, ultralytics/nn/modules/vision_lstm/
+vision_lstm2.py:701-753, called from ViLBlockPair at the four stage resolutions (:1066-1079)."""
+import pytest
+import torch
+
+from oracle import mlstm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = {
+    "base256_S6400": (32, 8, 6400, 64),
+    "base192_S6400": (64, 12, 6400, 32),
+    "base192_S1600": (64, 12, 1600, 32),
+    "base384_S6400": (16, 6, 6400, 128),
+}
+TOL = 2e-2
+
+
+@pytest.fixture(scope="module")
+def pkg():
+    import __graft_entry__ as G
+
+    G.build()
+    import xlstm_yolo_clean_b200 as p
+
+    return p
+
+
+def _inputs(B, NH, S, D, dtype, seed):
+    """Model-like statistics (random-init cell: i = 15 tanh(-10/15), f in 15 tanh(linspace(3, 6)/15) per head,
+    vision_lstm2.py:755-769) with per-token jitter so that every gate gradient is exercised; generated on the GPU."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    dev = torch.device("cuda:0")
+    t = {k: (0.5 * torch.randn(B, NH, S, D, generator=g, device=dev)).to(dtype) for k in ("q", "k", "v", "dh")}
+    f_head = 15.0 * torch.tanh(torch.linspace(3.0, 6.0, NH, device=dev) / 15.0)
+    t["f"] = (f_head.view(1, NH, 1) + 0.5 * torch.randn(B, NH, S, generator=g, device=dev)).to(dtype)
+    t["i"] = (-8.73 + 6.0 * torch.rand(B, NH, S, generator=g, device=dev)).to(dtype)
+    return t
+
+
+def _run(pkg, t, impl, reverse):
+    pkg.set_default_impl(impl)
+    try:
+        h, n_out, m_out, _, cst = pkg.mlstm_chunkwise_fw(t["q"], t["k"], t["v"], t["i"], t["f"], chunk_size=64, eps=1e-6,
+                                                         reverse=reverse)
+        dq, dk, dv, di, df, _ = pkg.mlstm_chunkwise_bw(t["q"], t["k"], t["v"], t["i"], t["f"], n_out, m_out, t["dh"],
+                                                      chunk_size=64, eps=1e-6, c_states=cst, reverse=reverse)
+        torch.cuda.synchronize()
+    finally:
+        pkg.set_default_impl("auto")
+    return dict(h=h, n_out=n_out, m_out=m_out, dq=dq, dk=dk, dv=dv, di=di, df=df)
+
+
+def _oracle_slice(t, b, hd, reverse):
+    """float64 oracle on one (batch, head); the anti-causal direction is flip -> causal -> flip."""
+    r = {k: v[b:b + 1, hd:hd + 1].double().cpu() for k, v in t.items()}
+    if reverse:
+        r = {k: v.flip(2) for k, v in r.items()}
+    h, n_tok, m_tok, _, _ = O.chunkwise_fw(r["q"], r["k"], r["v"], r["i"], r["f"], chunk_size=64)
+    dq, dk, dv, di, df, _ = O.chunkwise_bw(r["q"], r["k"], r["v"], r["i"], r["f"], r["dh"], n_tok, m_tok, chunk_size=64)
+    out = dict(h=h, n_out=n_tok, m_out=m_tok, dq=dq, dk=dk, dv=dv, di=di, df=df)
+    return {k: (v.flip(2) if reverse else v) for k, v in out.items()}
+
+
+@pytest.mark.parametrize("reverse", [False, True], ids=["causal", "anticausal"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+@pytest.mark.parametrize("name", list(SHAPES))
+def test_real_call_shape(pkg, name, dtype, reverse):
+    B, NH, S, D = SHAPES[name]
+    assert pkg.tensor_path_supported(B, NH, S, D, D, dtype)
+    t = _inputs(B, NH, S, D, dtype, seed=1000 * list(SHAPES).index(name) + 10 * (dtype == torch.float16) + int(reverse))
+    got = _run(pkg, t, "tensor", reverse)
+    for v in got.values():
+        assert torch.isfinite(v).all()
+    # (1) float64 oracle on the first, a middle and the last (batch, head) of the grid
+    bad = {}
+    for (b, hd) in ((0, 0), (B // 2, NH // 2), (B - 1, NH - 1)):
+        want = _oracle_slice(t, b, hd, reverse)
+        for k, w in want.items():
+            e = O.rel_err(got[k][b:b + 1, hd:hd + 1].double().cpu().reshape(w.shape), w)
+            # m_out is a function of the gates alone (running max of fp32 cumulative sums): tighter than the outputs
+            if not e < (1e-3 if k == "m_out" else TOL):
+                bad[(b, hd, k)] = e
+    assert not bad, f"{name} {dtype} reverse={reverse}: vs float64 oracle: {bad}"
+    # (2) the exact fp32-FFMA family on the whole call
+    ref = _run(pkg, t, "exact", reverse)
+    bad = {}
+    for k in got:
+        # per-(batch, head) relative error, so that one wrong CTA cannot hide behind the global maximum
+        a, r = got[k].float().flatten(2), ref[k].float().flatten(2)
+        err = (a - r).abs().amax(dim=2) / r.abs().amax(dim=2).clamp_min(1e-20)
+        tol = 1e-3 if k == "m_out" else 2 * TOL  # both sides carry 16-bit rounding of the outputs
+        if not bool((err < tol).all()):
+            idx = int(err.argmax())
+            bad[k] = (float(err.max()), divmod(idx, NH))
+    assert not bad, f"{name} {dtype} reverse={reverse}: tensor path vs exact family per (b, h): {bad}"
+
+
+def test_two_resident_d32_ctas_do_not_interfere(pkg):
+    """Head dim 32 runs two CTAs per SM (TMEM 2 x 256 columns, 2 x 105 KB shared memory): the same (b, h) problem must
+    give bit-identical results whether its CTA shares the SM or not."""
+    B, NH, S, D = 64, 12, 1600, 32
+    t = _inputs(B, NH, S, D, torch.bfloat16, seed=5)
+    full = _run(pkg, t, "tensor", False)
+    small = {k: v[:2, :3].contiguous() for k, v in t.items()}  # 6 CTAs: every one alone on its SM
+    alone = _run(pkg, small, "tensor", False)
+    for k in full:
+        assert torch.equal(full[k][:2, :3], alone[k]), k

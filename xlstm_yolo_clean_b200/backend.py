@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import threading
 from typing import Optional
 
 import torch
@@ -69,23 +70,6 @@ class _on_device:
             self.ctx.__exit__(*a)
 
 
-_BYTES_CACHE: dict = {}
-
-
-def _scratch_bytes(lib, shape: "_cabi.Shape", backward: int, want_states: bool):
-    """(workspace bytes, states bytes) of a shape; the two C-ABI queries are cached per shape key."""
-    key = (shape.B, shape.NH, shape.S, shape.DHQK, shape.DHHV, shape.chunk_size, shape.dtype, shape.impl, backward)
-    r = _BYTES_CACHE.get(key)
-    if r is None:
-        r = (lib.mlstm_b200_workspace_bytes(C.byref(shape), backward), lib.mlstm_b200_states_bytes(C.byref(shape)))
-        _BYTES_CACHE[key] = r
-    return r[0], (r[1] if want_states else 0)
-
-
-def _ptr(t: Optional[torch.Tensor]):
-    return None if t is None else t.data_ptr()
-
-
 def _shape(q, v, chunk_size, eps, impl, qk_scale=None, reverse=False, siging=False) -> _cabi.Shape:
     B, NH, S, DK = q.shape
     s = _cabi.Shape()
@@ -106,11 +90,6 @@ def tensor_path_supported(B, NH, S, DK, DV, dtype=torch.bfloat16, chunk_size=64)
     return bool(_cabi.load_library().mlstm_b200_tensor_path_supported(C.byref(s)))
 
 
-def _rowmajor_last(t: torch.Tensor) -> torch.Tensor:
-    """The kernels take any batch/head/token strides but need a unit innermost stride."""
-    return t if t.stride(-1) == 1 else t.contiguous()
-
-
 def _check_inputs(q, k, v, i, f):
     for name, t in (("q", q), ("k", k), ("v", v), ("i", i), ("f", f)):
         if not t.is_cuda:
@@ -129,53 +108,257 @@ def _state_f32(t, shape):
     return t.detach().to(torch.float32).reshape(shape).contiguous()
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# Call plans.  A YOLO-ViL training step makes ~90 forward / backward calls of a handful of distinct (shape, strides)
+# signatures and is launch-bound on the host, so everything that does not change between two calls of one signature --
+# validation, the C-ABI shape / stride structs, scratch sizes, the choice between handing the views to the kernels
+# as they are or copying them -- is done once and kept in a per-thread plan (forward runs on the caller's thread,
+# backward on an autograd thread, checkpoint recompute re-enters: SURVEY.md section 8b "Threading"; the structs are
+# mutated per call, hence thread-local).  Per call: output allocation, ~10 pointer stores, one ctypes call.
+# ------------------------------------------------------------------------------------------------------------------
+_tls = threading.local()
+_raw_stream = torch._C._cuda_getCurrentRawStream
+
+
+def _plans() -> dict:
+    d = getattr(_tls, "plans", None)
+    if d is None:
+        d = _tls.plans = {}
+    return d
+
+
+def _tma_strides_ok(t: torch.Tensor) -> bool:
+    """What a TMA tensor map needs from a (B, NH, S, D) 16-bit view: unit innermost stride, the other strides
+    multiples of 8 elements (16 bytes).  Broadcast (stride 0) dimensions would pass the test but make overlapping
+    output rows, so they are copied too."""
+    st = t.stride()
+    return st[3] == 1 and all(x % 8 == 0 and x > 0 for x in st[:3])
+
+
+def _tensor_route(lib, shape) -> bool:
+    return shape.impl != _cabi.IMPL_EXACT and bool(lib.mlstm_b200_tensor_path_supported(C.byref(shape)))
+
+
+def _fix_views(tensor_route: bool, ts):
+    """The kernels take any batch / head / token strides; what they cannot take is copied here, like the reference's
+    @contiguous decorator does for every argument (mlstm_kernels/torch/utils.py:30-42): a non-unit innermost stride
+    always, and on the tensor-core route strides that are not multiples of 16 bytes or a base pointer that is not
+    16-byte aligned (sliced / offset views)."""
+    out = []
+    for t in ts:
+        if t.stride(-1) != 1 or (tensor_route and t.dim() == 4 and (not _tma_strides_ok(t) or t.data_ptr() & 15)):
+            t = t.contiguous()
+            if t.data_ptr() & 15:  # a contiguous view at an odd offset of its storage
+                t = t.clone()
+        out.append(t)
+    return out
+
+
+class _FwPlan:
+    __slots__ = ("args", "ref", "ws_bytes", "st_bytes", "tensor_route", "h_shape", "nm_shape", "states")
+
+
+class _BwPlan:
+    __slots__ = ("args", "ref", "ws_bytes", "tensor_route", "gshape_qk", "gshape_v", "gshape_g")
+
+
+def _ws_tensor(nbytes: int, dev):
+    """Scratch for a call.  The tensor-core forward needs none and its backward only when it has to recompute the
+    states; those calls share one tiny per-device buffer instead of allocating 256 bytes each."""
+    if nbytes <= 256:
+        cache = getattr(_tls, "tiny_ws", None)
+        if cache is None:
+            cache = _tls.tiny_ws = {}
+        t = cache.get(dev.index)
+        if t is None:
+            t = cache[dev.index] = torch.empty(256, dtype=torch.uint8, device=dev)
+        return t
+    return torch.empty(nbytes, dtype=torch.uint8, device=dev)
+
+
+def _fw_launch(q, k, v, i, f, c0, n0, m0, qk_scale, return_last_states, chunk_size, eps, impl, save_states, reverse, siging):
+    """Returns h, nm (2, B, NH, S) fp32 = [n_out, m_out], last-or-None, c_states-or-None."""
+    impl = _default_impl if impl is None else impl
+    dt = q.dtype
+    if i.dtype is not dt:
+        i = i.to(dt)
+    if f.dtype is not dt:
+        f = f.to(dt)
+    if k.dtype is not dt:
+        k = k.to(dt)
+    if v.dtype is not dt:
+        v = v.to(dt)
+    dev = q.device
+    key = (0, q.shape, v.shape[3], dt, q.stride(), k.stride(), v.stride(), i.stride(), f.stride(), chunk_size, eps, impl,
+           qk_scale, reverse, siging, c0 is not None, return_last_states, save_states, dev.index)
+    plans = _plans()
+    plan = plans.get(key)
+    lib = _cabi.load_library()
+    if plan is None:
+        _check_inputs(q, k, v, i, f)
+        B, NH, S, DK = q.shape
+        assert S % chunk_size == 0, f"Sequence length {S} is not divisible by chunk size {chunk_size}."
+        a = _cabi.FwArgs()
+        a.shape = _shape(q, v, chunk_size, eps, impl, qk_scale, reverse, siging)
+        plan = _FwPlan()
+        plan.tensor_route = _tensor_route(lib, a.shape)
+        fixed = _fix_views(plan.tensor_route, (q, k, v))
+        if any(x is not y for x, y in zip(fixed, (q, k, v))):  # a signature that needs copies: plan on the copies
+            return _fw_launch(*fixed, i, f, c0, n0, m0, qk_scale, return_last_states, chunk_size, eps, impl, save_states,
+                              reverse, siging)
+        plan.ws_bytes = lib.mlstm_b200_workspace_bytes(C.byref(a.shape), 0)
+        plan.st_bytes = lib.mlstm_b200_states_bytes(C.byref(a.shape)) if save_states else 0
+        plan.h_shape, plan.nm_shape = (B, NH, S, v.shape[3]), (2, B, NH, S)
+        plan.states = ((B, NH, DK, v.shape[3]), (B, NH, DK), (B, NH))
+        for name, t in (("q", q), ("k", k), ("v", v), ("i", i), ("f", f)):
+            getattr(a, name).stride[:t.dim()] = t.stride()
+        a.h.stride[:4] = (NH * S * v.shape[3], S * v.shape[3], v.shape[3], 1)
+        a.workspace_bytes = max(plan.ws_bytes, 256)
+        plan.args, plan.ref = a, C.byref(a)
+        plans[key] = plan
+    elif plan.tensor_route and (q.data_ptr() | k.data_ptr() | v.data_ptr()) & 15:  # offset views of this signature
+        q, k, v = _fix_views(True, (q, k, v))
+    a = plan.args
+    if torch._C._cuda_getDevice() != dev.index:
+        with torch.cuda.device(dev):
+            return _fw_launch(q, k, v, i, f, c0, n0, m0, qk_scale, return_last_states, chunk_size, eps, impl, save_states,
+                              reverse, siging)
+    h = torch.empty(plan.h_shape, dtype=dt, device=dev)
+    nm = torch.empty(plan.nm_shape, dtype=torch.float32, device=dev)
+    c_states = torch.empty(plan.st_bytes, dtype=torch.uint8, device=dev) if plan.st_bytes else None
+    ws = _ws_tensor(plan.ws_bytes, dev)
+    last = None
+    if c0 is not None:
+        sc, sn, sm = plan.states
+        c0, n0, m0 = _state_f32(c0, sc), _state_f32(n0, sn), _state_f32(m0, sm)
+        n0 = torch.zeros(sn, device=dev) if n0 is None else n0
+        m0 = torch.zeros(sm, device=dev) if m0 is None else m0
+        a.c_initial, a.n_initial, a.m_initial = c0.data_ptr(), n0.data_ptr(), m0.data_ptr()
+    if return_last_states:
+        sc, sn, sm = plan.states
+        last = (torch.empty(sc, dtype=torch.float32, device=dev), torch.empty(sn, dtype=torch.float32, device=dev),
+                torch.empty(sm + (1,), dtype=torch.float32, device=dev))
+        a.c_last, a.n_last, a.m_last = last[0].data_ptr(), last[1].data_ptr(), last[2].data_ptr()
+    a.q.ptr, a.k.ptr, a.v.ptr, a.i.ptr, a.f.ptr, a.h.ptr = (q.data_ptr(), k.data_ptr(), v.data_ptr(), i.data_ptr(),
+                                                            f.data_ptr(), h.data_ptr())
+    nmp = nm.data_ptr()
+    a.n_out, a.m_out = nmp, nmp + nm.stride(0) * 4
+    a.c_states = c_states.data_ptr() if c_states is not None else None
+    a.workspace = ws.data_ptr()
+    st = lib.mlstm_b200_chunkwise_fw(plan.ref, _raw_stream(dev.index))
+    if st:
+        _cabi.check(st, "mlstm_b200_chunkwise_fw")
+    return h, nm, last, c_states
+
+
 def mlstm_chunkwise_fw(q, k, v, i, f, c_initial=None, n_initial=None, m_initial=None, qk_scale=None,
                        return_last_states=False, chunk_size=64, eps=1e-6, impl=None, save_states=True, reverse=False, siging=False):
     """C-ABI forward.  Returns h, n_out, m_out, last_states-or-None (fp32), c_states-or-None.
 
     ``c_states`` is the opaque per-tile state buffer the tensor-core backward consumes (the
     reference's return_all_states mode, native/fwbw.py:73-101); None when the kernels recompute."""
-    global _last_launches
-    lib = _cabi.load_library()
-    _check_inputs(q, k, v, i, f)
-    B, NH, S, DK = q.shape
-    DV = v.shape[-1]
-    assert S % chunk_size == 0, f"Sequence length {S} is not divisible by chunk size {chunk_size}."
-    q, k, v = (_rowmajor_last(t) for t in (q, k, v))
-    i = i if i.dtype == q.dtype else i.to(q.dtype)
-    f = f if f.dtype == q.dtype else f.to(q.dtype)
-    k = k if k.dtype == q.dtype else k.to(q.dtype)
-    v = v if v.dtype == q.dtype else v.to(q.dtype)
+    if c_initial is None and (n_initial is not None or m_initial is not None):
+        B, NH, S, DK = q.shape
+        c_initial = torch.zeros(B, NH, DK, v.shape[-1], device=q.device)
+    h, nm, last, c_states = _fw_launch(q, k, v, i, f, c_initial, n_initial, m_initial, qk_scale, bool(return_last_states),
+                                       int(chunk_size), float(eps), impl, bool(save_states), bool(reverse), bool(siging))
+    return h, nm[0], nm[1], last, c_states
+
+
+def _bw_launch(q, k, v, i, f, n_ptr, m_ptr, dh, c0, n0, m0, dcl, qk_scale, chunk_size, eps, impl, want_dc_initial, c_states,
+               reverse, siging, out):
+    impl = _default_impl if impl is None else impl
+    dt = q.dtype
+    if dh.dtype is not dt:
+        dh = dh.to(dt)
+    if i.dtype is not dt:
+        i = i.to(dt)
+    if f.dtype is not dt:
+        f = f.to(dt)
     dev = q.device
-    c0, n0, m0 = _state_f32(c_initial, (B, NH, DK, DV)), _state_f32(n_initial, (B, NH, DK)), _state_f32(m_initial, (B, NH))
-    if c0 is not None or n0 is not None or m0 is not None:
-        c0 = torch.zeros(B, NH, DK, DV, device=dev) if c0 is None else c0
+    key = (1, q.shape, v.shape[3], dt, q.stride(), k.stride(), v.stride(), i.stride(), f.stride(), dh.stride(), chunk_size, eps,
+           impl, qk_scale, reverse, siging, c0 is not None, want_dc_initial, c_states is not None, dev.index,
+           None if out is None else tuple(t.stride() for t in out))
+    plans = _plans()
+    plan = plans.get(key)
+    lib = _cabi.load_library()
+    if plan is None:
+        _check_inputs(q, k, v, i, f)
+        B, NH, S, DK = q.shape
+        DV = v.shape[3]
+        a = _cabi.BwArgs()
+        a.shape = _shape(q, v, chunk_size, eps, impl, qk_scale, reverse, siging)
+        plan = _BwPlan()
+        plan.tensor_route = _tensor_route(lib, a.shape)
+        fixed = _fix_views(plan.tensor_route, (q, k, v, dh))
+        if any(x is not y for x, y in zip(fixed, (q, k, v, dh))):
+            return _bw_launch(*fixed[:3], i, f, n_ptr, m_ptr, fixed[3], c0, n0, m0, dcl, qk_scale, chunk_size, eps, impl,
+                              want_dc_initial, c_states, reverse, siging, out)
+        if out is not None:
+            dq, dk, dv, di, df = out
+            assert dq.shape == q.shape and dk.shape == k.shape and dv.shape == v.shape and di.shape == i.shape
+            assert all(t.dtype == dt and t.device == dev for t in out)
+            if plan.tensor_route and not all(_tma_strides_ok(t) for t in (dq, dk, dv)):
+                raise RuntimeError("caller-provided dq / dk / dv need a unit innermost stride and 16-byte-multiple strides")
+            for name, t in zip(("dq", "dk", "dv", "di", "df"), out):
+                getattr(a, name).stride[:t.dim()] = t.stride()
+        else:
+            a.dq.stride[:4] = a.dk.stride[:4] = (NH * S * DK, S * DK, DK, 1)
+            a.dv.stride[:4] = (NH * S * DV, S * DV, DV, 1)
+            a.di.stride[:3] = a.df.stride[:3] = (NH * S, S, 1)
+        # the tensor-core route only needs scratch to recompute the states (or for the head-dim-128 block problems)
+        plan.ws_bytes = lib.mlstm_b200_workspace_bytes(C.byref(a.shape), 1)
+        if plan.tensor_route and c_states is not None and DK != 128:
+            plan.ws_bytes = 0
+        plan.gshape_qk, plan.gshape_v, plan.gshape_g = (B, NH, S, DK), (B, NH, S, DV), (B, NH, S)
+        for name, t in (("q", q), ("k", k), ("v", v), ("i", i), ("f", f), ("dh", dh)):
+            getattr(a, name).stride[:t.dim()] = t.stride()
+        a.workspace_bytes = max(plan.ws_bytes, 256)
+        plan.args, plan.ref = a, C.byref(a)
+        plans[key] = plan
+    elif plan.tensor_route and (q.data_ptr() | k.data_ptr() | v.data_ptr() | dh.data_ptr()) & 15:
+        q, k, v, dh = _fix_views(True, (q, k, v, dh))
+    a = plan.args
+    if torch._C._cuda_getDevice() != dev.index:
+        with torch.cuda.device(dev):
+            return _bw_launch(q, k, v, i, f, n_ptr, m_ptr, dh, c0, n0, m0, dcl, qk_scale, chunk_size, eps, impl,
+                              want_dc_initial, c_states, reverse, siging, out)
+    if out is not None:
+        dq, dk, dv, di, df = out
+        if plan.tensor_route and (dq.data_ptr() | dk.data_ptr() | dv.data_ptr()) & 15:
+            raise RuntimeError("caller-provided dq / dk / dv must be 16-byte aligned")
+    else:
+        dq = torch.empty(plan.gshape_qk, dtype=dt, device=dev)
+        dk = torch.empty(plan.gshape_qk, dtype=dt, device=dev)
+        dv = torch.empty(plan.gshape_v, dtype=dt, device=dev)
+        di = torch.empty(plan.gshape_g, dtype=dt, device=dev)
+        df = torch.empty(plan.gshape_g, dtype=dt, device=dev)
+    ws = _ws_tensor(plan.ws_bytes, dev)
+    dc0 = None
+    if c0 is not None:
+        B, NH, S, DK = q.shape
+        DV = v.shape[3]
+        c0, n0, m0 = _state_f32(c0, (B, NH, DK, DV)), _state_f32(n0, (B, NH, DK)), _state_f32(m0, (B, NH))
         n0 = torch.zeros(B, NH, DK, device=dev) if n0 is None else n0
         m0 = torch.zeros(B, NH, device=dev) if m0 is None else m0
-    with _on_device(dev):
-        h = torch.empty(B, NH, S, DV, dtype=q.dtype, device=dev)
-        n_out = torch.empty(B, NH, S, dtype=torch.float32, device=dev)
-        m_out = torch.empty(B, NH, S, dtype=torch.float32, device=dev)
-        last = None
-        if return_last_states:
-            last = (torch.empty(B, NH, DK, DV, dtype=torch.float32, device=dev),
-                    torch.empty(B, NH, DK, dtype=torch.float32, device=dev),
-                    torch.empty(B, NH, 1, dtype=torch.float32, device=dev))
-        a = _cabi.FwArgs()
-        a.shape = _shape(q, v, chunk_size, eps, impl, qk_scale, reverse, siging)
-        ws_bytes, st_bytes = _scratch_bytes(lib, a.shape, 0, save_states)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        c_states = torch.empty(st_bytes, dtype=torch.uint8, device=dev) if st_bytes else None
-        a.c_states = _ptr(c_states)
-        a.q, a.k, a.v, a.i, a.f, a.h = (_tensor(t) for t in (q, k, v, i, f, h))
-        a.c_initial, a.n_initial, a.m_initial = _ptr(c0), _ptr(n0), _ptr(m0)
-        a.n_out, a.m_out = n_out.data_ptr(), m_out.data_ptr()
-        if last is not None:
-            a.c_last, a.n_last, a.m_last = (t.data_ptr() for t in last)
-        a.workspace, a.workspace_bytes = ws.data_ptr(), ws_bytes
-        st = lib.mlstm_b200_chunkwise_fw(C.byref(a), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
-        _cabi.check(st, "mlstm_b200_chunkwise_fw")
-    return h, n_out, m_out, last, c_states
+        a.c_initial, a.n_initial, a.m_initial = c0.data_ptr(), n0.data_ptr(), m0.data_ptr()
+    if want_dc_initial:
+        dc0 = torch.empty(q.shape[0], q.shape[1], q.shape[3], v.shape[3], dtype=torch.float32, device=dev)
+        a.dc_initial = dc0.data_ptr()
+    if dcl is not None:
+        dcl = _state_f32(dcl, (q.shape[0], q.shape[1], q.shape[3], v.shape[3]))
+    a.dc_last = None if dcl is None else dcl.data_ptr()
+    a.q.ptr, a.k.ptr, a.v.ptr, a.i.ptr, a.f.ptr, a.dh.ptr = (q.data_ptr(), k.data_ptr(), v.data_ptr(), i.data_ptr(),
+                                                             f.data_ptr(), dh.data_ptr())
+    a.dq.ptr, a.dk.ptr, a.dv.ptr, a.di.ptr, a.df.ptr = (dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), di.data_ptr(),
+                                                        df.data_ptr())
+    a.n_out, a.m_out = n_ptr, m_ptr
+    a.c_states = c_states.data_ptr() if c_states is not None else None
+    a.workspace = ws.data_ptr()
+    st = lib.mlstm_b200_chunkwise_bw(plan.ref, _raw_stream(dev.index))
+    if st:
+        _cabi.check(st, "mlstm_b200_chunkwise_bw")
+    return dq, dk, dv, di, df, dc0
 
 
 def mlstm_chunkwise_bw(q, k, v, i, f, n_out, m_out, dh, c_initial=None, n_initial=None, m_initial=None,
@@ -185,48 +368,13 @@ def mlstm_chunkwise_bw(q, k, v, i, f, n_out, m_out, dh, c_initial=None, n_initia
 
     ``out`` = (dq, dk, dv, di, df) lets the caller provide the gradient tensors (any batch/head/token strides,
     unit innermost stride for dq/dk/dv), e.g. views into a fused (B, S, 2H) qk gradient."""
-    lib = _cabi.load_library()
-    _check_inputs(q, k, v, i, f)
-    B, NH, S, DK = q.shape
-    DV = v.shape[-1]
-    q, k, v = (_rowmajor_last(t) for t in (q, k, v))
-    dh = _rowmajor_last(dh if dh.dtype == q.dtype else dh.to(q.dtype))
-    i = i if i.dtype == q.dtype else i.to(q.dtype)
-    f = f if f.dtype == q.dtype else f.to(q.dtype)
-    dev = q.device
-    c0, n0, m0 = _state_f32(c_initial, (B, NH, DK, DV)), _state_f32(n_initial, (B, NH, DK)), _state_f32(m_initial, (B, NH))
-    if c0 is not None or n0 is not None or m0 is not None:
-        c0 = torch.zeros(B, NH, DK, DV, device=dev) if c0 is None else c0
-        n0 = torch.zeros(B, NH, DK, device=dev) if n0 is None else n0
-        m0 = torch.zeros(B, NH, device=dev) if m0 is None else m0
-    dcl = _state_f32(dc_last, (B, NH, DK, DV))
-    with _on_device(dev):
-        if out is not None:
-            dq, dk, dv, di, df = out
-            assert dq.shape == q.shape and dk.shape == k.shape and dv.shape == v.shape and di.shape == i.shape
-            assert all(t.dtype == q.dtype and t.device == dev for t in out)
-        else:
-            dq = torch.empty(B, NH, S, DK, dtype=q.dtype, device=dev)
-            dk = torch.empty(B, NH, S, DK, dtype=q.dtype, device=dev)
-            dv = torch.empty(B, NH, S, DV, dtype=q.dtype, device=dev)
-            di = torch.empty(B, NH, S, dtype=q.dtype, device=dev)
-            df = torch.empty(B, NH, S, dtype=q.dtype, device=dev)
-        dc0 = torch.empty(B, NH, DK, DV, dtype=torch.float32, device=dev) if want_dc_initial else None
-        a = _cabi.BwArgs()
-        a.shape = _shape(q, v, chunk_size, eps, impl, qk_scale, reverse, siging)
-        ws_bytes, _ = _scratch_bytes(lib, a.shape, 1, False)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        a.q, a.k, a.v, a.i, a.f, a.dh = (_tensor(t) for t in (q, k, v, i, f, dh))
-        a.c_initial, a.n_initial, a.m_initial = _ptr(c0), _ptr(n0), _ptr(m0)
-        a.n_out, a.m_out = n_out.data_ptr(), m_out.data_ptr()
-        a.c_states = _ptr(c_states)
-        a.dc_last = _ptr(dcl)
-        a.dq, a.dk, a.dv, a.di, a.df = (_tensor(t) for t in (dq, dk, dv, di, df))
-        a.dc_initial = _ptr(dc0)
-        a.workspace, a.workspace_bytes = ws.data_ptr(), ws_bytes
-        st = lib.mlstm_b200_chunkwise_bw(C.byref(a), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
-        _cabi.check(st, "mlstm_b200_chunkwise_bw")
-    return dq, dk, dv, di, df, dc0
+    if c_initial is None and (n_initial is not None or m_initial is not None):
+        B, NH, S, DK = q.shape
+        c_initial = torch.zeros(B, NH, DK, v.shape[-1], device=q.device)
+    n_out = n_out if n_out.is_contiguous() else n_out.contiguous()
+    m_out = m_out if m_out.is_contiguous() else m_out.contiguous()
+    return _bw_launch(q, k, v, i, f, n_out.data_ptr(), m_out.data_ptr(), dh, c_initial, n_initial, m_initial, dc_last, qk_scale,
+                      int(chunk_size), float(eps), impl, bool(want_dc_initial), c_states, bool(reverse), bool(siging), out)
 
 
 def _make_function(autocast_kernel_dtype: torch.dtype):
@@ -238,10 +386,11 @@ def _make_function(autocast_kernel_dtype: torch.dtype):
         def forward(ctx, q, k, v, i, f, c_initial, n_initial, m_initial, return_last_states, chunk_size, eps, reverse,
                     siging):
             need_bw = any(ctx.needs_input_grad[:6])
-            h, n_out, m_out, last, c_states = mlstm_chunkwise_fw(
-                q, k, v, i, f, c_initial, n_initial, m_initial, return_last_states=return_last_states,
-                chunk_size=chunk_size, eps=eps, save_states=need_bw, reverse=reverse, siging=siging)
-            ctx.save_for_backward(q, k, v, i, f, c_initial, n_initial, m_initial, n_out, m_out, c_states)
+            if c_initial is None and (n_initial is not None or m_initial is not None):
+                c_initial = torch.zeros(q.shape[0], q.shape[1], q.shape[3], v.shape[3], dtype=q.dtype, device=q.device)
+            h, nm, last, c_states = _fw_launch(q, k, v, i, f, c_initial, n_initial, m_initial, None, return_last_states,
+                                               chunk_size, eps, None, need_bw, reverse, siging)
+            ctx.save_for_backward(q, k, v, i, f, c_initial, n_initial, m_initial, nm, c_states)
             ctx.chunk_size, ctx.eps, ctx.reverse, ctx.siging = chunk_size, eps, reverse, siging
             if last is None:
                 return h, None, None, None
@@ -251,10 +400,11 @@ def _make_function(autocast_kernel_dtype: torch.dtype):
         @staticmethod
         @custom_bwd(device_type="cuda")
         def backward(ctx, dh, dc_last, dn_last, dm_last):
-            q, k, v, i, f, c0, n0, m0, n_out, m_out, c_states = ctx.saved_tensors
-            dq, dk, dv, di, df, dc0 = mlstm_chunkwise_bw(
-                q, k, v, i, f, n_out, m_out, dh, c0, n0, m0, dc_last=dc_last, chunk_size=ctx.chunk_size, eps=ctx.eps,
-                want_dc_initial=c0 is not None, c_states=c_states, reverse=ctx.reverse, siging=ctx.siging)
+            q, k, v, i, f, c0, n0, m0, nm, c_states = ctx.saved_tensors
+            nmp = nm.data_ptr()
+            dq, dk, dv, di, df, dc0 = _bw_launch(q, k, v, i, f, nmp, nmp + nm.stride(0) * 4, dh, c0, n0, m0, dc_last, None,
+                                                 ctx.chunk_size, ctx.eps, None, c0 is not None, c_states, ctx.reverse,
+                                                 ctx.siging, None)
             # dn_last / dm_last are ignored and dN/dM_initial are zeros, as in native/bw.py:329-337
             return (dq, dk, dv, di, df,
                     None if c0 is None else dc0.to(c0.dtype),

@@ -39,16 +39,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Non-blocking test (mbarrier.try_wait may suspend the thread for a system-dependent time when the phase is incomplete)
-__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\tmbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
 // Bounded wait: a lost arrival traps (the error surfaces to the host) instead of hanging the GPU.
 // The bound is ~2^31 SM cycles (about one second); `tag` is stored to *g_dbg (if set) first.
 #ifndef SM100_WAIT_CYCLES

@@ -752,953 +752,6 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
 }
 
 // =============================================================================================
-// Forward, role-split variant (tc_fw2).  Same math, tiles, TMEM / shared-memory operands and state handling as
-// tc_fw; what changes is WHO does the per-tile work.  In tc_fw each of the 8 worker warps runs the whole chain
-// S -> P -> Kbar -> epilogue -> state update of its rows, one tile after the other: a latency-bound dependent chain
-// (issue slots 40 % busy, ncu) in which the causal P phase of the bottom row block (TMEM lane quadrant 3 is only
-// reachable from warps with warp % 4 == 3) sets the pace.  Here two groups of 8 warps work on ADJACENT tiles:
-//   P-warps (0-7):  wait S(c) -> P(c) = S . decay, packed in place into TMEM       (the causal, exp-heavy part)
-//   E-warps (8-15): Kbar(c) = abar . K -> epilogue h(c) -> state update C_c, n_c   (the uniform part)
-// so that P(c+1) overlaps the epilogue and state update of tile c.  The only thing the groups exchange directly is
-// the fp32 row sums of P (the denominator; summing the 16-bit-rounded P on the tensor pipe instead costs a factor 2
-// in accuracy when the row nearly cancels, measured on the extreme-gate test).  The scan warp runs up to four tiles
-// ahead (four gate buffers), so neither group ever waits for gate vectors.  Control warp per tile c:  S(c+1) | wait E(c-1): stores, stage refill, Hx(c) = Q [C | n] |
-// wait P(c): P V | wait Kbar(c): dC, dn.  Every mbarrier is completed at most once between two waits of each
-// waiter (bar_s is split by TMEM buffer parity for that reason).
-// =============================================================================================
-constexpr int kFw2Threads = 576;  // 8 P-warps + 8 E-warps + control + scan
-constexpr int kFw2Ctl = 16, kFw2Scan = 17;
-enum { NB2_KB = 9, NB2_EPI = 10, NB2_ST = 12, NB2_INIT = 11 };
-constexpr int kNb2PC = 256 + 32;   // a worker group + control
-constexpr int kNb2E = 256 + 64;    // E-warps + control + scan
-
-#ifdef MLSTM_TC_PROFILE  // tc_fw2: P-warp 3 (thread 96: bottom row block), E-warp 11 (thread 352), control (thread 512)
-#define TC_PROF2(tile, slot, who) \
-  if (p.prof && blockIdx.x == 0 && threadIdx.x == (who)) p.prof[(tile) * 16 + (slot)] = clock64()
-#else
-#define TC_PROF2(tile, slot, who)
-#endif
-
-template <int D_>
-struct Fw2Smem {
-  static constexpr int D = D_;
-  static constexpr int NSTAGE = 3;
-  static constexpr int kTile = Lay<D>::kTile;
-  static constexpr int oQ = 0;
-  static constexpr int oK = oQ + NSTAGE * kTile;
-  static constexpr int oV = oK + NSTAGE * kTile;
-  static constexpr int oKb = oV + NSTAGE * kTile;    // abar . K
-  static constexpr int oH = oKb + kTile;             // h staging
-  static constexpr int oC = oH + kTile;              // bf16 copy of C (D x D), MMA B operand of Q [C | n]
-  static constexpr int oNt = oC + Lay<D>::kState;    // second N block of that operand: column 0 = bf16 copy of n
-  static constexpr int oOnes = oNt + Lay<D>::kState; // [8][128] ones, K-major: B operand of dn = Kbar^T 1
-  static constexpr int oSmall = oOnes + 2048;
-  static constexpr int kGateBufs = 4;                // the scan warp runs up to 4 tiles ahead of the E-warps
-  // floats: gates[4], srs[4][2][LT] (row sums of P: written by the P-warps of tile c, read by its E-warps)
-  static constexpr int fGates = 0, fRs = kGateBufs * GateBuf::kFloats, kSmallFloats = fRs + kGateBufs * 2 * LT;
-  static constexpr int kBytes = oSmall + kSmallFloats * 4 + 1024 /*alignment slack*/;
-  // TMEM (512 columns, one CTA per SM): S double-buffered by tile parity, P packed in place
-  static constexpr uint32_t cS0 = 0, cS1 = 128, cHi = 256, cHx = cHi + D, cDC = cHx + D + 16, cDN = cDC + D;
-  static_assert(cDN + 8 <= 512, "TMEM budget");
-};
-
-template <typename T, int D, bool REV>
-__global__ void __launch_bounds__(kFw2Threads, 1)
-tc_fw2(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
-       const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapH,
-       const __grid_constant__ CUtensorMap mapCs, TcFwParams p) {
-  constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
-  using SM = Fw2Smem<D>;
-  using L = Lay<D>;
-  constexpr int NSTAGE = SM::NSTAGE, CW = L::CW;
-  TC_PROF_CTA(0);
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  float* fsm = (float*)(smem + SM::oSmall);
-  uint8_t* sKb = smem + SM::oKb;
-  uint8_t* sH = smem + SM::oH;
-  uint8_t* sC = smem + SM::oC;
-  uint8_t* sNt = smem + SM::oNt;
-  uint8_t* sOnes = smem + SM::oOnes;
-  __shared__ uint64_t bar_full[NSTAGE], bar_s[2], bar_p[2], bar_dc, bar_h, bar_hx, bar_g[SM::kGateBufs];
-  __shared__ uint32_t tmem_base_s;
-
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const int bh = blockIdx.x, b = bh / p.NH, hh = bh % p.NH;
-
-  const T* ip = (const T*)p.ig + b * p.ig_sb + hh * p.ig_sh;
-  const T* fp = (const T*)p.fg + b * p.fg_sb + hh * p.fg_sh;
-  constexpr uint32_t kStageBytes = 3 * SM::kTile;
-  auto mt = [&](int c) { return REV ? p.NT - 1 - c : c; };
-  auto load_stage = [&](int s, int c) {
-    mbar_expect_tx(&bar_full[s], kStageBytes);
-    tma_load_4d(smem + SM::oQ + s * SM::kTile, &mapQ, &bar_full[s], 0, mt(c) * LT, hh, b);
-    tma_load_4d(smem + SM::oK + s * SM::kTile, &mapK, &bar_full[s], 0, mt(c) * LT, hh, b);
-    tma_load_4d(smem + SM::oV + s * SM::kTile, &mapV, &bar_full[s], 0, mt(c) * LT, hh, b);
-  };
-  // Two tiles beyond the shared-memory ring are pulled into L2 (no shared memory needed): with the P-warps a tile ahead
-  // of the E-warps two of the three stages are in use, and one stage in flight does not cover the DRAM latency at the
-  // per-SM bandwidth share; an L2 hit does not need more.
-  constexpr int kL2Ahead = 2;
-  auto prefetch_l2 = [&](int c) {
-    tma_prefetch_4d(&mapQ, 0, mt(c) * LT, hh, b);
-    tma_prefetch_4d(&mapK, 0, mt(c) * LT, hh, b);
-    tma_prefetch_4d(&mapV, 0, mt(c) * LT, hh, b);
-  };
-  if (tid == kFw2Ctl * 32) {  // cold start: first loads before anything else (grid-dependency waits: see tc_fw)
-    for (int s = 0; s < NSTAGE; ++s) mbar_init(&bar_full[s], 1);
-    fence_mbar_init();
-    grid_dep_wait();
-    for (int s = 0; s < NSTAGE && s < p.NT; ++s) load_stage(s, s);
-    for (int c = NSTAGE; c < NSTAGE + kL2Ahead && c < p.NT; ++c) prefetch_l2(c);
-  }
-  if (tid == 0) {
-    mbar_init(&bar_s[0], 1);
-    mbar_init(&bar_s[1], 1);
-    mbar_init(&bar_p[0], 8);  // one arrival per P-warp
-    mbar_init(&bar_p[1], 8);
-    mbar_init(&bar_dc, 1);
-    mbar_init(&bar_h, 1);
-    mbar_init(&bar_hx, 1);
-    for (int j = 0; j < SM::kGateBufs; ++j) mbar_init(&bar_g[j], 1);
-    fence_mbar_init();
-  }
-  if (warp == kFw2Ctl) {
-    tmem_alloc<512>(&tmem_base_s);
-    if (lane == 0) {
-      prefetch_tmap(&mapQ); prefetch_tmap(&mapK); prefetch_tmap(&mapV); prefetch_tmap(&mapH); prefetch_tmap(&mapCs);
-    }
-  }
-  grid_dep_wait();
-  grid_dep_launch();
-  // both worker groups use the tc_fw thread -> (row block, column half) map inside their group
-  const int rb = warp & 3, ch = (warp >> 2) & 1;
-  const int row = rb * 32 + lane;  // tile row == TMEM lane of this thread
-  const uint32_t lane_base = (uint32_t)(rb * 32) << 16;
-  const int drow = rb * 16 + (lane & 15);
-  const bool is_e = warp >= 8 && warp < 16;
-  const bool owns_c = is_e && lane < 16 && rb * 16 < D;  // fp32 master copy of C (M = 64 TMEM layout), E-warps
-  float Creg[CW];
-  float n_reg = 0.f;
-#pragma unroll
-  for (int j = 0; j < CW; ++j) Creg[j] = 0.f;
-  if (is_e) {
-    const int etid = tid - 256;
-    if (p.c0 && owns_c) {
-      const float* src = p.c0 + ((int64_t)bh * D + drow) * D + ch * CW;
-#pragma unroll
-      for (int j = 0; j < CW; ++j) Creg[j] = src[j];
-    }
-    if (owns_c) store_cols<T, D>(sC, drow, ch * CW, Creg);
-    for (int e = etid; e < L::kState / 16; e += 256) reinterpret_cast<uint4*>(sNt)[e] = make_uint4(0, 0, 0, 0);
-    {
-      const uint32_t one2 = pack2<T>(1.f, 1.f);
-      for (int e = etid; e < 2048 / 16; e += 256) reinterpret_cast<uint4*>(sOnes)[e] = make_uint4(one2, one2, one2, one2);
-    }
-    named_sync(NB2_INIT, 256);  // sNt zeroed before the owners write column 0
-    if (owns_c && ch == 0) {
-      n_reg = p.n0 ? p.n0[(int64_t)bh * D + drow] : 0.f;
-      *reinterpret_cast<T*>(sNt + L::swz(drow, 0)) = from_f32<T>(n_reg);
-    }
-    fence_proxy_async_smem();
-  }
-  if (warp == kFw2Scan) {
-    const int t1 = mt(0) * LT, nv = min(LT, p.S - t1);
-    for (int e = lane; e < nv; e += 32) {
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(ip + (int64_t)(t1 + e) * p.ig_ss));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(fp + (int64_t)(t1 + e) * p.fg_ss));
-    }
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem = tmem_base_s;
-  const uint32_t tS0 = tmem + SM::cS0, tS1 = tmem + SM::cS1, tHi = tmem + SM::cHi, tHx = tmem + SM::cHx, tDC = tmem + SM::cDC,
-                 tDN = tmem + SM::cDN;
-
-  if (warp == kFw2Ctl) {
-    // =========================== control warp ===================================================
-    constexpr uint32_t id_s = umma_idesc(128, 128, false, false, kBf16);
-    constexpr uint32_t id_dc = umma_idesc(64, D, true, true, kBf16);
-    constexpr uint32_t id_h = umma_idesc(128, D, false, true, kBf16);
-    constexpr uint32_t id_hx = umma_idesc(128, D + 16, false, true, kBf16);  // Q [C | n]
-    constexpr uint32_t id_dn = umma_idesc(64, 8, true, false, kBf16);        // Kbar^T 1
-    const uint64_t dOnes = umma_smem_desc(smem_u32(sOnes), 0, 1024);
-    const uint64_t dKb = L::desc(smem_u32(sKb), D == 64 ? SM::kTile : 0);
-    const uint64_t dC = L::desc(smem_u32(sC), L::kState);
-    const uint64_t dQ0 = L::desc(smem_u32(smem + SM::oQ), 0);
-    const uint64_t dK0 = L::desc(smem_u32(smem + SM::oK), 0);
-    const uint64_t dV0 = L::desc(smem_u32(smem + SM::oV), SM::kTile);
-    // S(c) = Q K^T into the TMEM buffer of the tile's parity.  `block` = false: only if the tile has landed (one
-    // non-spinning test); returns whether the MMAs were issued.
-    auto issue_s = [&](int c, auto PAR, bool block) -> bool {
-      constexpr int par = decltype(PAR)::value;
-      const int s = c % NSTAGE;
-      if (block) mbar_wait(&bar_full[s], (c / NSTAGE) & 1, 1);
-      else if (!mbar_test_wait(&bar_full[s], (c / NSTAGE) & 1)) return false;
-      tc_fence_after_sync();
-      const uint64_t dQ = umma_desc_advance(dQ0, s * SM::kTile), dK = umma_desc_advance(dK0, s * SM::kTile);
-      const uint32_t tS = par ? tS1 : tS0;
-#pragma unroll
-      for (int kk = 0; kk < D / 16; ++kk)
-        umma_f16(tS, umma_desc_advance(dQ, kk * 32), umma_desc_advance(dK, kk * 32), id_s, kk > 0);
-      umma_commit(&bar_s[par]);
-      return true;
-    };
-    auto issue_hx = [&](int c) {  // Hinter = Q [C_{c-1} | n_{c-1}] (column D is q . n_{c-1})
-      const uint64_t dQ = umma_desc_advance(dQ0, (c % NSTAGE) * SM::kTile);
-      tc_fence_after_sync();
-#pragma unroll
-      for (int kk = 0; kk < D / 16; ++kk)
-        umma_f16(tHx, umma_desc_advance(dQ, kk * 32), umma_desc_advance(dC, kk * L::kAdvMN), id_hx, kk > 0);
-      umma_commit(&bar_hx);
-    };
-    auto issue_pv = [&](int c, auto PAR) {  // Hintra = P V, A = P from TMEM (packed inside the S columns)
-      constexpr int par = decltype(PAR)::value;
-      const uint64_t dV = umma_desc_advance(dV0, (c % NSTAGE) * SM::kTile);
-      // an mbarrier per TMEM buffer, not a named barrier: the P-warps run ahead of this warp, and a named barrier cannot
-      // queue a second generation of arrivals
-      mbar_wait(&bar_p[par], (c >> 1) & 1, 4);
-      tc_fence_after_sync();
-#pragma unroll
-      for (int kk = 0; kk < LT / 16; ++kk)
-        umma_f16_ts(tHi, (par ? tS1 : tS0) + 32 * (kk / 2) + 8 * (kk % 2), umma_desc_advance(dV, kk * L::kAdvMN), id_h, kk > 0);
-      umma_commit(&bar_h);
-    };
-    auto issue_dc = [&](int c) {  // dC = Kbar^T V, dn = Kbar^T 1
-      const uint64_t dV = umma_desc_advance(dV0, (c % NSTAGE) * SM::kTile);
-      tc_fence_after_sync();
-#pragma unroll
-      for (int kk = 0; kk < LT / 16; ++kk)
-        umma_f16(tDC, umma_desc_advance(dKb, kk * L::kAdvMN), umma_desc_advance(dV, kk * L::kAdvMN), id_dc, kk > 0);
-#pragma unroll
-      for (int kk = 0; kk < LT / 16; ++kk)
-        umma_f16(tDN, umma_desc_advance(dKb, kk * L::kAdvMN), umma_desc_advance(dOnes, (kk / 4) * 1024 + (kk % 4) * 32), id_dn,
-                 kk > 0);
-      umma_commit(&bar_dc);
-    };
-    if (lane == 0 && p.store_states) {  // state entering tile 0 -> c_states[b, h, 0]
-      tma_store_4d(&mapCs, sC, 0, mt(0) * D, hh, b);
-      tma_store_commit();
-    }
-    __syncwarp();
-    // prologue: S(0), S(1), Hx(0), P V (0), dC(0)
-    if (elect_one()) {
-      issue_s(0, std::integral_constant<int, 0>{}, true);
-      if (p.NT > 1) issue_s(1, std::integral_constant<int, 1>{}, true);
-      issue_hx(0);
-      issue_pv(0, std::integral_constant<int, 0>{});
-    }
-    __syncwarp();
-    named_sync(NB2_KB, kNb2PC);  // Kbar(0)
-    if (lane == 0) tma_store_wait_read<0>();  // the initial-state store has read sC before bar_dc lets the E-warps rewrite it
-    __syncwarp();
-    if (elect_one()) issue_dc(0);
-    __syncwarp();
-
-    // iteration c follows the E-warps through tile c: epilogue(c) | state(c) | Kbar(c+1)
-    int s_issued = min(p.NT, 2);  // S(0 .. s_issued-1) have been issued (lane-uniform)
-    for (int c = 0; c < p.NT; c += 2) {
-      tile_body(c, std::integral_constant<int, 0>{});
-      if (c + 1 < p.NT) tile_body(c + 1, std::integral_constant<int, 1>{});
-    }
-    if (lane == 0) tma_store_wait_all<0>();
-  } else if (warp == kScanWarp) {
-    // =========================== scan warp: gate vectors two tiles ahead ===========================
-    auto raw_of = [&](int c) {
-      const int t1 = mt(c) * LT;
-      return load_gate_raw<T>(ip + (int64_t)t1 * p.ig_ss, p.ig_ss, fp + (int64_t)t1 * p.fg_ss, p.fg_ss, min(LT, p.S - t1));
-    };
-    GateRaw<T> raw = raw_of(0);
-    for (int n = 0; n < p.NT; ++n) {  // vectors of tile n; tiles 0 and 1 need no buffer hand-back
-      if (n >= 2) named_sync(NB_C, kNbC);  // every worker is done with tile n-2: its gate buffer can be reused
-      gate_scan_regs(fsm + SM::fGates + (n & 1) * GateBuf::kFloats, raw, REV, p.sig != 0);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_g[n & 1]);
-      if (n + 1 < p.NT) raw = raw_of(n + 1);  // stays in flight until the next hand-back
-    }
-    for (int n = max(p.NT - 2, 0); n < p.NT; ++n) named_sync(NB_C, kNbC);  // match the workers' remaining arrivals
-  } else {
-    // =========================== worker warps ===================================================
-    float m_run = p.m0 ? p.m0[bh] : 0.f;
-    for (int c = 0; c < p.NT; ++c) {
-      const int s = c % NSTAGE, pb = c & 1;
-      const uint32_t par_full = (c / NSTAGE) & 1, par = c & 1;
-      const uint8_t* sQ = smem + SM::oQ + s * SM::kTile;
-      const uint8_t* sK = smem + SM::oK + s * SM::kTile;
-      const float* gb = fsm + SM::fGates + pb * GateBuf::kFloats;
-      float* srs = fsm + SM::fRs + pb * 2 * LT;
-      const int t0 = mt(c) * LT;
-      const int n_valid = min(LT, p.S - t0);
-      const uint32_t tS = (c & 1) ? tS1 : tS0;
-
-      TC_PROF(c, 0);
-      mbar_wait(&bar_g[pb], (c >> 1) & 1, 2);
-      const float g = gb[GateBuf::oScal], amax = gb[GateBuf::oScal + 1];
-      const float m_next = p.sig ? 0.f : fmaxf(g + m_run, g + amax);    // fw.py:96-98
-      const float gbar = __expf(g + m_run - m_next);                    // fw.py:106
-      const float b_t = gb[GateBuf::oB + row], i_t = gb[GateBuf::oI + row];
-      const float m_t = p.sig ? 0.f : b_t + fmaxf(m_run, gb[GateBuf::oPm + row]);  // fw.py:178-184
-      TC_PROF(c, 1);
-      // ---- P = S . D (causal), row sums ----------------------------------------------------------
-      mbar_wait(&bar_s, par, 5);
-      tc_fence_after_sync();
-      TC_PROF(c, 2);
-      {
-        const float x_t = (b_t - m_t) * kLog2e + log2f(p.scale);
-        const float* sy = gb + GateBuf::oY;
-        const float* scf = gb + GateBuf::oCf;
-        float rs = 0.f;
-#pragma unroll 1
-        for (int u = ch; u < 4; u += 2) {  // this thread's two 32-column units (warp-uniform branches)
-          float v[32];
-          const bool off_diag = REV ? u > rb : u < rb;  // fully unmasked 32x32 block
-          if (off_diag) {  // rank-1 decay, one exp per row
-            tmem_ld32(tS + lane_base + u * 32, v);
-            const float r_t = ex2_approx(x_t + gb[GateBuf::oScal + 4 + u]);
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 cf = *reinterpret_cast<const float4*>(scf + u * 32 + 4 * j4);
-              v[4 * j4 + 0] *= cf.x * r_t;
-              v[4 * j4 + 1] *= cf.y * r_t;
-              v[4 * j4 + 2] *= cf.z * r_t;
-              v[4 * j4 + 3] *= cf.w * r_t;
-              rs += (v[4 * j4 + 0] + v[4 * j4 + 1]) + (v[4 * j4 + 2] + v[4 * j4 + 3]);
-            }
-          } else if (u == rb) {  // diagonal block: causal mask, one exp per entry
-            tmem_ld32(tS + lane_base + u * 32, v);
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 y = *reinterpret_cast<const float4*>(sy + u * 32 + 4 * j4);
-              const float yy[4] = {y.x, y.y, y.z, y.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int j = 4 * j4 + e;
-                float pv = v[j] * ex2_approx(x_t + yy[e]);
-                pv = (REV ? j >= lane : j <= lane) ? pv : 0.f;
-                rs += pv;
-                v[j] = pv;
-              }
-            }
-          } else {  // above the diagonal: zeros (the S MMA of every tile overwrites these columns)
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
-          }
-          uint32_t pk[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = pack2<T>(v[2 * j], v[2 * j + 1]);
-          tmem_st16(tS + lane_base + u * 32, pk);
-        }
-        srs[ch * LT + row] = rs;
-      }
-      TC_PROF(c, 3);
-      tmem_st_wait();
-      TC_PROF(c, 4);
-      tc_fence_before_sync();
-      named_arrive(NB_B, kNbAB);
-      TC_PROF(c, 5);
-      // (the loads and n_{k-1} are only needed from here on: their waits stay off the S -> P -> PV chain)
-      mbar_wait(&bar_full[s], par_full, 3);
-      // ---- Kbar = abar . K (this thread: row, CW columns); overlaps the H MMAs ---------------------------
-      {
-        const float ab = __expf(g - b_t + i_t - m_next);  // fw.py:102 (exp(-inf) = 0 for tail tokens)
-        float kb[CW];
-#pragma unroll
-        for (int j = 0; j < CW / 8; ++j) {
-          uint4 u = *reinterpret_cast<const uint4*>(sK + L::swz(row, ch * CW + 8 * j));
-          float2 a0 = unpack2<T>(u.x), a1 = unpack2<T>(u.y), a2 = unpack2<T>(u.z), a3 = unpack2<T>(u.w);
-          kb[8 * j + 0] = a0.x * ab; kb[8 * j + 1] = a0.y * ab; kb[8 * j + 2] = a1.x * ab; kb[8 * j + 3] = a1.y * ab;
-          kb[8 * j + 4] = a2.x * ab; kb[8 * j + 5] = a2.y * ab; kb[8 * j + 6] = a3.x * ab; kb[8 * j + 7] = a3.y * ab;
-        }
-        store_cols<T, D>(sKb, row, ch * CW, kb);
-        fence_proxy_async_smem();
-        named_arrive(NB_A, kNbAB);
-      }
-      TC_PROF(c, 6);
-      // ---- epilogue -----------------------------------------------------------------------------------
-      mbar_wait(&bar_hx, par, 9);
-      mbar_wait(&bar_h, par, 7);
-      tc_fence_after_sync();
-      TC_PROF(c, 7);
-      {
-        uint32_t hi[CW], hx[CW], qn_u;
-        tmem_ld_nowait(tHi + lane_base + ch * CW, hi);
-        tmem_ld_nowait(tHx + lane_base + ch * CW, hx);
-        tmem_ld1_nowait(tHx + lane_base + D, qn_u);  // q . n_{k-1}
-        const float bq = __expf(b_t + m_run - m_t) * p.scale;  // fw.py:197-198
-        const float rs = srs[row] + srs[LT + row];
-        tmem_ld_wait();
-        const float den = bq * __uint_as_float(qn_u) + rs;       // fw.py:204-206
-        const float nmax = fmaxf(fabsf(den), __expf(-m_t));    // fw.py:208-210
-        const float inv = 1.f / (nmax + p.eps);
-        float o[CW];
-#pragma unroll
-        for (int j = 0; j < CW; ++j) o[j] = (__uint_as_float(hi[j]) + bq * __uint_as_float(hx[j])) * inv;  // fw.py:200-212
-        store_cols<T, D>(sH + (SM::kHBuf == 2 ? (c & 1) * SM::kTile : 0), row, ch * CW, o);
-        if (ch == 0 && row < n_valid) {
-          p.n_out[(int64_t)bh * p.S + t0 + row] = nmax;
-          p.m_out[(int64_t)bh * p.S + t0 + row] = m_t;
-        }
-      }
-      // ---- state update C_k = gbar C_{k-1} + dC; n_k ---------------------------------------------------
-      mbar_wait(&bar_dc, par, 6);
-      tc_fence_after_sync();
-      {
-        uint32_t v[CW], dn_u;
-        tmem_ld_nowait(tDC + lane_base + ch * CW, v);  // M=64 layout: lanes 0-15 of each quadrant hold rows
-        tmem_ld1_nowait(tDN + lane_base, dn_u);
-        tmem_ld_wait();
-        if (owns_c) {
-#pragma unroll
-          for (int j = 0; j < CW; ++j) Creg[j] = gbar * Creg[j] + __uint_as_float(v[j]);
-          store_cols<T, D>(sC, drow, ch * CW, Creg);  // Q [C | n]_{k-1} (bar_hx) has finished reading the old copies
-          if (ch == 0) {  // n_k = gbar n_{k-1} + column sums of Kbar (fw.py:116)
-            n_reg = gbar * n_reg + __uint_as_float(dn_u);
-            *reinterpret_cast<T*>(sNt + L::swz(drow, 0)) = from_f32<T>(n_reg);
-          }
-        }
-      }
-      fence_proxy_async_smem();
-      tc_fence_before_sync();
-      named_arrive(NB_C, kNbC);
-      TC_PROF(c, 8);
-      m_run = m_next;
-    }
-    // final states (fw.py:302-309)
-    if (p.c_last) {
-      if (owns_c) {
-        float* dst = p.c_last + ((int64_t)bh * D + drow) * D + ch * CW;
-#pragma unroll
-        for (int j = 0; j < CW; ++j) dst[j] = Creg[j];
-      }
-      if (owns_c && ch == 0) p.n_last[(int64_t)bh * D + drow] = n_reg;
-      if (tid == 0) p.m_last[bh] = m_run;
-    }
-  }
-  TC_PROF(200, 1);  // this role is done
-  tc_fence_before_sync();
-  __syncthreads();
-  TC_PROF(200, 2);
-  TC_PROF_CTA(1);
-  if (warp == kCtlWarp) tmem_dealloc<SM::kTmemCols>(tmem);
-}
-
-// =============================================================================================
-// Forward, role-split variant (tc_fw2).  Same math, tiles, TMEM / shared-memory operands and state handling as
-// tc_fw; what changes is WHO does the per-tile work.  In tc_fw each of the 8 worker warps runs the whole chain
-// S -> P -> Kbar -> epilogue -> state update of its rows, one tile after the other: a latency-bound dependent chain
-// (issue slots 40 % busy, ncu) in which the causal P phase of the bottom row block (TMEM lane quadrant 3 is only
-// reachable from warps with warp % 4 == 3) sets the pace.  Here two groups of 8 warps work on ADJACENT tiles:
-//   P-warps (0-7):  wait S(c) -> P(c) = S . decay, packed in place into TMEM       (the causal, exp-heavy part)
-//   E-warps (8-15): Kbar(c) = abar . K -> epilogue h(c) -> state update C_c, n_c   (the uniform part)
-// so that P(c+1) overlaps the epilogue and state update of tile c.  The only thing the groups exchange directly is
-// the fp32 row sums of P (the denominator; summing the 16-bit-rounded P on the tensor pipe instead costs a factor 2
-// in accuracy when the row nearly cancels, measured on the extreme-gate test).  The scan warp runs up to four tiles
-// ahead (four gate buffers), so neither group ever waits for gate vectors.  Control warp per tile c:  S(c+1) | wait E(c-1): stores, stage refill, Hx(c) = Q [C | n] |
-// wait P(c): P V | wait Kbar(c): dC, dn.  Every mbarrier is completed at most once between two waits of each
-// waiter (bar_s is split by TMEM buffer parity for that reason).
-// =============================================================================================
-constexpr int kFw2Threads = 576;  // 8 P-warps + 8 E-warps + control + scan
-constexpr int kFw2Ctl = 16, kFw2Scan = 17;
-enum { NB2_KB = 9, NB2_EPI = 10, NB2_ST = 12, NB2_INIT = 11 };
-constexpr int kNb2PC = 256 + 32;   // a worker group + control
-constexpr int kNb2E = 256 + 64;    // E-warps + control + scan
-
-#ifdef MLSTM_TC_PROFILE  // tc_fw2: P-warp 3 (thread 96: bottom row block), E-warp 11 (thread 352), control (thread 512)
-#define TC_PROF2(tile, slot, who) \
-  if (p.prof && blockIdx.x == 0 && threadIdx.x == (who)) p.prof[(tile) * 16 + (slot)] = clock64()
-#else
-#define TC_PROF2(tile, slot, who)
-#endif
-
-template <int D_>
-struct Fw2Smem {
-  static constexpr int D = D_;
-  static constexpr int NSTAGE = 3;
-  static constexpr int kTile = Lay<D>::kTile;
-  static constexpr int oQ = 0;
-  static constexpr int oK = oQ + NSTAGE * kTile;
-  static constexpr int oV = oK + NSTAGE * kTile;
-  static constexpr int oKb = oV + NSTAGE * kTile;    // abar . K
-  static constexpr int oH = oKb + kTile;             // h staging
-  static constexpr int oC = oH + kTile;              // bf16 copy of C (D x D), MMA B operand of Q [C | n]
-  static constexpr int oNt = oC + Lay<D>::kState;    // second N block of that operand: column 0 = bf16 copy of n
-  static constexpr int oOnes = oNt + Lay<D>::kState; // [8][128] ones, K-major: B operand of dn = Kbar^T 1
-  static constexpr int oSmall = oOnes + 2048;
-  static constexpr int kGateBufs = 4;                // the scan warp runs up to 4 tiles ahead of the E-warps
-  // floats: gates[4], srs[4][2][LT] (row sums of P: written by the P-warps of tile c, read by its E-warps)
-  static constexpr int fGates = 0, fRs = kGateBufs * GateBuf::kFloats, kSmallFloats = fRs + kGateBufs * 2 * LT;
-  static constexpr int kBytes = oSmall + kSmallFloats * 4 + 1024 /*alignment slack*/;
-  // TMEM (512 columns, one CTA per SM): S double-buffered by tile parity, P packed in place
-  static constexpr uint32_t cS0 = 0, cS1 = 128, cHi = 256, cHx = cHi + D, cDC = cHx + D + 16, cDN = cDC + D;
-  static_assert(cDN + 8 <= 512, "TMEM budget");
-};
-
-template <typename T, int D, bool REV>
-__global__ void __launch_bounds__(kFw2Threads, 1)
-tc_fw2(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
-       const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapH,
-       const __grid_constant__ CUtensorMap mapCs, TcFwParams p) {
-  constexpr bool kBf16 = std::is_same<T, __nv_bfloat16>::value;
-  using SM = Fw2Smem<D>;
-  using L = Lay<D>;
-  constexpr int NSTAGE = SM::NSTAGE, CW = L::CW;
-  TC_PROF_CTA(0);
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  float* fsm = (float*)(smem + SM::oSmall);
-  uint8_t* sKb = smem + SM::oKb;
-  uint8_t* sH = smem + SM::oH;
-  uint8_t* sC = smem + SM::oC;
-  uint8_t* sNt = smem + SM::oNt;
-  uint8_t* sOnes = smem + SM::oOnes;
-  __shared__ uint64_t bar_full[NSTAGE], bar_s[2], bar_p[2], bar_dc, bar_h, bar_hx, bar_g[SM::kGateBufs];
-  __shared__ uint32_t tmem_base_s;
-
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const int bh = blockIdx.x, b = bh / p.NH, hh = bh % p.NH;
-
-  const T* ip = (const T*)p.ig + b * p.ig_sb + hh * p.ig_sh;
-  const T* fp = (const T*)p.fg + b * p.fg_sb + hh * p.fg_sh;
-  constexpr uint32_t kStageBytes = 3 * SM::kTile;
-  auto mt = [&](int c) { return REV ? p.NT - 1 - c : c; };
-  auto load_stage = [&](int s, int c) {
-    mbar_expect_tx(&bar_full[s], kStageBytes);
-    tma_load_4d(smem + SM::oQ + s * SM::kTile, &mapQ, &bar_full[s], 0, mt(c) * LT, hh, b);
-    tma_load_4d(smem + SM::oK + s * SM::kTile, &mapK, &bar_full[s], 0, mt(c) * LT, hh, b);
-    tma_load_4d(smem + SM::oV + s * SM::kTile, &mapV, &bar_full[s], 0, mt(c) * LT, hh, b);
-  };
-  // Two tiles beyond the shared-memory ring are pulled into L2 (no shared memory needed): with the P-warps a tile ahead
-  // of the E-warps two of the three stages are in use, and one stage in flight does not cover the DRAM latency at the
-  // per-SM bandwidth share; an L2 hit does not need more.
-  constexpr int kL2Ahead = 2;
-  auto prefetch_l2 = [&](int c) {
-    tma_prefetch_4d(&mapQ, 0, mt(c) * LT, hh, b);
-    tma_prefetch_4d(&mapK, 0, mt(c) * LT, hh, b);
-    tma_prefetch_4d(&mapV, 0, mt(c) * LT, hh, b);
-  };
-  if (tid == kFw2Ctl * 32) {  // cold start: first loads before anything else (grid-dependency waits: see tc_fw)
-    for (int s = 0; s < NSTAGE; ++s) mbar_init(&bar_full[s], 1);
-    fence_mbar_init();
-    grid_dep_wait();
-    for (int s = 0; s < NSTAGE && s < p.NT; ++s) load_stage(s, s);
-    for (int c = NSTAGE; c < NSTAGE + kL2Ahead && c < p.NT; ++c) prefetch_l2(c);
-  }
-  if (tid == 0) {
-    mbar_init(&bar_s[0], 1);
-    mbar_init(&bar_s[1], 1);
-    mbar_init(&bar_p[0], 8);  // one arrival per P-warp
-    mbar_init(&bar_p[1], 8);
-    mbar_init(&bar_dc, 1);
-    mbar_init(&bar_h, 1);
-    mbar_init(&bar_hx, 1);
-    for (int j = 0; j < SM::kGateBufs; ++j) mbar_init(&bar_g[j], 1);
-    fence_mbar_init();
-  }
-  if (warp == kFw2Ctl) {
-    tmem_alloc<512>(&tmem_base_s);
-    if (lane == 0) {
-      prefetch_tmap(&mapQ); prefetch_tmap(&mapK); prefetch_tmap(&mapV); prefetch_tmap(&mapH); prefetch_tmap(&mapCs);
-    }
-  }
-  grid_dep_wait();
-  grid_dep_launch();
-  // both worker groups use the tc_fw thread -> (row block, column half) map inside their group
-  const int rb = warp & 3, ch = (warp >> 2) & 1;
-  const int row = rb * 32 + lane;  // tile row == TMEM lane of this thread
-  const uint32_t lane_base = (uint32_t)(rb * 32) << 16;
-  const int drow = rb * 16 + (lane & 15);
-  const bool is_e = warp >= 8 && warp < 16;
-  const bool owns_c = is_e && lane < 16 && rb * 16 < D;  // fp32 master copy of C (M = 64 TMEM layout), E-warps
-  float Creg[CW];
-  float n_reg = 0.f;
-#pragma unroll
-  for (int j = 0; j < CW; ++j) Creg[j] = 0.f;
-  if (is_e) {
-    const int etid = tid - 256;
-    if (p.c0 && owns_c) {
-      const float* src = p.c0 + ((int64_t)bh * D + drow) * D + ch * CW;
-#pragma unroll
-      for (int j = 0; j < CW; ++j) Creg[j] = src[j];
-    }
-    if (owns_c) store_cols<T, D>(sC, drow, ch * CW, Creg);
-    for (int e = etid; e < L::kState / 16; e += 256) reinterpret_cast<uint4*>(sNt)[e] = make_uint4(0, 0, 0, 0);
-    {
-      const uint32_t one2 = pack2<T>(1.f, 1.f);
-      for (int e = etid; e < 2048 / 16; e += 256) reinterpret_cast<uint4*>(sOnes)[e] = make_uint4(one2, one2, one2, one2);
-    }
-    named_sync(NB2_INIT, 256);  // sNt zeroed before the owners write column 0
-    if (owns_c && ch == 0) {
-      n_reg = p.n0 ? p.n0[(int64_t)bh * D + drow] : 0.f;
-      *reinterpret_cast<T*>(sNt + L::swz(drow, 0)) = from_f32<T>(n_reg);
-    }
-    fence_proxy_async_smem();
-  }
-  if (warp == kFw2Scan) {
-    const int t1 = mt(0) * LT, nv = min(LT, p.S - t1);
-    for (int e = lane; e < nv; e += 32) {
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(ip + (int64_t)(t1 + e) * p.ig_ss));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(fp + (int64_t)(t1 + e) * p.fg_ss));
-    }
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem = tmem_base_s;
-  const uint32_t tS0 = tmem + SM::cS0, tS1 = tmem + SM::cS1, tHi = tmem + SM::cHi, tHx = tmem + SM::cHx, tDC = tmem + SM::cDC,
-                 tDN = tmem + SM::cDN;
-
-  if (warp == kFw2Ctl) {
-    // =========================== control warp ===================================================
-    constexpr uint32_t id_s = umma_idesc(128, 128, false, false, kBf16);
-    constexpr uint32_t id_dc = umma_idesc(64, D, true, true, kBf16);
-    constexpr uint32_t id_h = umma_idesc(128, D, false, true, kBf16);
-    constexpr uint32_t id_hx = umma_idesc(128, D + 16, false, true, kBf16);  // Q [C | n]
-    constexpr uint32_t id_dn = umma_idesc(64, 8, true, false, kBf16);        // Kbar^T 1
-    const uint64_t dOnes = umma_smem_desc(smem_u32(sOnes), 0, 1024);
-    const uint64_t dKb = L::desc(smem_u32(sKb), D == 64 ? SM::kTile : 0);
-    const uint64_t dC = L::desc(smem_u32(sC), L::kState);
-    const uint64_t dQ0 = L::desc(smem_u32(smem + SM::oQ), 0);
-    const uint64_t dK0 = L::desc(smem_u32(smem + SM::oK), 0);
-    const uint64_t dV0 = L::desc(smem_u32(smem + SM::oV), SM::kTile);
-    // S(c) = Q K^T into the TMEM buffer of the tile's parity.  `block` = false: only if the tile has landed (one
-    // non-spinning test); returns whether the MMAs were issued.
-    auto issue_s = [&](int c, auto PAR, bool block) -> bool {
-      constexpr int par = decltype(PAR)::value;
-      const int s = c % NSTAGE;
-      if (block) mbar_wait(&bar_full[s], (c / NSTAGE) & 1, 1);
-      else if (!mbar_test_wait(&bar_full[s], (c / NSTAGE) & 1)) return false;
-      tc_fence_after_sync();
-      const uint64_t dQ = umma_desc_advance(dQ0, s * SM::kTile), dK = umma_desc_advance(dK0, s * SM::kTile);
-      const uint32_t tS = par ? tS1 : tS0;
-#pragma unroll
-      for (int kk = 0; kk < D / 16; ++kk)
-        umma_f16(tS, umma_desc_advance(dQ, kk * 32), umma_desc_advance(dK, kk * 32), id_s, kk > 0);
-      umma_commit(&bar_s[par]);
-      return true;
-    };
-    auto issue_hx = [&](int c) {  // Hinter = Q [C_{c-1} | n_{c-1}] (column D is q . n_{c-1})
-      const uint64_t dQ = umma_desc_advance(dQ0, (c % NSTAGE) * SM::kTile);
-      tc_fence_after_sync();
-#pragma unroll
-      for (int kk = 0; kk < D / 16; ++kk)
-        umma_f16(tHx, umma_desc_advance(dQ, kk * 32), umma_desc_advance(dC, kk * L::kAdvMN), id_hx, kk > 0);
-      umma_commit(&bar_hx);
-    };
-    auto issue_pv = [&](int c, auto PAR) {  // Hintra = P V, A = P from TMEM (packed inside the S columns)
-      constexpr int par = decltype(PAR)::value;
-      const uint64_t dV = umma_desc_advance(dV0, (c % NSTAGE) * SM::kTile);
-      // an mbarrier per TMEM buffer, not a named barrier: the P-warps run ahead of this warp, and a named barrier cannot
-      // queue a second generation of arrivals
-      mbar_wait(&bar_p[par], (c >> 1) & 1, 4);
-      tc_fence_after_sync();
-#pragma unroll
-      for (int kk = 0; kk < LT / 16; ++kk)
-        umma_f16_ts(tHi, (par ? tS1 : tS0) + 32 * (kk / 2) + 8 * (kk % 2), umma_desc_advance(dV, kk * L::kAdvMN), id_h, kk > 0);
-      umma_commit(&bar_h);
-    };
-    auto issue_dc = [&](int c) {  // dC = Kbar^T V, dn = Kbar^T 1
-      const uint64_t dV = umma_desc_advance(dV0, (c % NSTAGE) * SM::kTile);
-      tc_fence_after_sync();
-#pragma unroll
-      for (int kk = 0; kk < LT / 16; ++kk)
-        umma_f16(tDC, umma_desc_advance(dKb, kk * L::kAdvMN), umma_desc_advance(dV, kk * L::kAdvMN), id_dc, kk > 0);
-#pragma unroll
-      for (int kk = 0; kk < LT / 16; ++kk)
-        umma_f16(tDN, umma_desc_advance(dKb, kk * L::kAdvMN), umma_desc_advance(dOnes, (kk / 4) * 1024 + (kk % 4) * 32), id_dn,
-                 kk > 0);
-      umma_commit(&bar_dc);
-    };
-    if (lane == 0 && p.store_states) {  // state entering tile 0 -> c_states[b, h, 0]
-      tma_store_4d(&mapCs, sC, 0, mt(0) * D, hh, b);
-      tma_store_commit();
-    }
-    __syncwarp();
-    // prologue: S(0), S(1), Hx(0), P V (0), dC(0)
-    if (elect_one()) {
-      issue_s(0, std::integral_constant<int, 0>{}, true);
-      if (p.NT > 1) issue_s(1, std::integral_constant<int, 1>{}, true);
-      issue_hx(0);
-      issue_pv(0, std::integral_constant<int, 0>{});
-    }
-    __syncwarp();
-    named_sync(NB2_KB, kNb2PC);  // Kbar(0)
-    if (lane == 0) tma_store_wait_read<0>();  // the initial-state store has read sC before bar_dc lets the E-warps rewrite it
-    __syncwarp();
-    if (elect_one()) issue_dc(0);
-    __syncwarp();
-
-    // iteration c follows the E-warps through tile c: epilogue(c) | state(c) | Kbar(c+1)
-    int s_issued = min(p.NT, 2);  // S(0 .. s_issued-1) have been issued (lane-uniform)
-    auto tile_body = [&](int c, auto PAR) {
-      constexpr int par = decltype(PAR)::value;  // parity of tile c
-      // S(c+2) goes into the TMEM buffer P V (c) consumed (issued in the previous iteration: the tensor pipe executes in
-      // issue order); it is issued as soon as its tile has landed, at the first of several points of this iteration
-      auto try_s = [&](bool block) {
-        if (s_issued == c + 2 && c + 2 < p.NT) {
-          int ok = 0;
-          if (elect_one()) ok = issue_s(c + 2, std::integral_constant<int, par>{}, block) ? 1 : 0;
-          ok = __shfl_sync(0xffffffffu, __ballot_sync(0xffffffffu, ok) != 0, 0);
-          s_issued += ok;
-        }
-      };
-      TC_PROF2(c, 9, 512);
-      try_s(false);
-      // 1: h(c) staged, Hi / Hx read -> store h(c), the next P V
-      named_sync(NB2_EPI, kNb2PC);
-      TC_PROF2(c, 10, 512);
-      if (lane == 0) {
-        tma_store_4d(&mapH, sH, 0, mt(c) * LT, hh, b);
-        tma_store_commit();
-      }
-      __syncwarp();
-      if (c + 1 < p.NT && elect_one()) issue_pv(c + 1, std::integral_constant<int, par ^ 1>{});
-      __syncwarp();
-      try_s(false);
-      TC_PROF2(c, 11, 512);
-      // 2: C_c / n_c operand copies written, dC read -> the next Hinter, saved state, stage refill (every reader of
-      //    tile c's Q / K / V is done)
-      named_sync(NB2_ST, kNb2E);
-      TC_PROF2(c, 12, 512);
-      if (lane == 0) tma_store_wait_read<0>();  // h(c) has left sH before bar_hx lets the E-warps into the next epilogue
-      __syncwarp();
-      if (c + 1 < p.NT && elect_one()) issue_hx(c + 1);
-      __syncwarp();
-      if (lane == 0) {
-        if (p.store_states && c + 1 < p.NT) {  // state entering tile c+1
-          tma_store_4d(&mapCs, sC, 0, mt(c + 1) * D, hh, b);
-          tma_store_commit();
-        }
-        if (c + NSTAGE < p.NT) load_stage(c % NSTAGE, c + NSTAGE);
-        if (c + NSTAGE + kL2Ahead < p.NT) prefetch_l2(c + NSTAGE + kL2Ahead);
-      }
-      __syncwarp();
-      try_s(false);
-      TC_PROF2(c, 13, 512);
-      if (c + 1 < p.NT) {
-        // 3: Kbar(c+1) written
-        named_sync(NB2_KB, kNb2PC);
-        if (lane == 0) tma_store_wait_read<0>();  // the saved-state store has read sC before bar_dc lets the E-warps rewrite it
-        __syncwarp();
-        if (elect_one()) issue_dc(c + 1);
-        __syncwarp();
-      }
-      try_s(true);  // the P-warps need it next
-      TC_PROF2(c, 14, 512);
-    };
-    for (int c = 0; c < p.NT; c += 2) {
-      tile_body(c, std::integral_constant<int, 0>{});
-      if (c + 1 < p.NT) tile_body(c + 1, std::integral_constant<int, 1>{});
-    }
-    if (lane == 0) tma_store_wait_all<0>();
-  } else if (warp == kFw2Scan) {
-    // =========================== scan warp: gate vectors two tiles ahead ===========================
-    auto raw_of = [&](int c) {
-      const int t1 = mt(c) * LT;
-      return load_gate_raw<T>(ip + (int64_t)t1 * p.ig_ss, p.ig_ss, fp + (int64_t)t1 * p.fg_ss, p.fg_ss, min(LT, p.S - t1));
-    };
-    GateRaw<T> raw = raw_of(0);
-    for (int n = 0; n < p.NT; ++n) {
-      if (n >= SM::kGateBufs) named_sync(NB2_ST, kNb2E);  // the E-warps (hence the P-warps) are done with the gates of tile n-4
-      gate_scan_regs(fsm + SM::fGates + (n % SM::kGateBufs) * GateBuf::kFloats, raw, REV, p.sig != 0);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_g[n % SM::kGateBufs]);
-      if (n + 1 < p.NT) raw = raw_of(n + 1);
-    }
-    for (int n = max(p.NT - SM::kGateBufs, 0); n < p.NT; ++n) named_sync(NB2_ST, kNb2E);  // match the E-warps' remaining arrivals
-  } else if (warp < 8) {
-    // =========================== P-warps: P(c) = S(c) . decay, packed in place ===========================
-    float m_run = p.m0 ? p.m0[bh] : 0.f;
-    const float lscale = log2f(p.scale);
-    for (int c = 0; c < p.NT; ++c) {
-      const int pb = c & 1, gi = c % SM::kGateBufs;
-      const float* gb = fsm + SM::fGates + gi * GateBuf::kFloats;
-      float* srs = fsm + SM::fRs + gi * 2 * LT;
-      const uint32_t tS = pb ? tS1 : tS0;
-      TC_PROF2(c, 0, 96);
-      mbar_wait(&bar_g[gi], (c / SM::kGateBufs) & 1, 2);
-      const float g = gb[GateBuf::oScal], amax = gb[GateBuf::oScal + 1];
-      const float m_next = p.sig ? 0.f : fmaxf(g + m_run, g + amax);                     // fw.py:96-98
-      const float b_t = gb[GateBuf::oB + row];
-      const float m_t = p.sig ? 0.f : b_t + fmaxf(m_run, gb[GateBuf::oPm + row]);        // fw.py:178-184
-      const float x_t = (b_t - m_t) * kLog2e + lscale;
-      const float* sy = gb + GateBuf::oY;
-      const float* scf = gb + GateBuf::oCf;
-      TC_PROF2(c, 1, 96);
-      mbar_wait(&bar_s[pb], (c >> 1) & 1, 5);
-      tc_fence_after_sync();
-      TC_PROF2(c, 2, 96);
-      float rs = 0.f;
-#pragma unroll 1
-      for (int u = ch; u < 4; u += 2) {  // this thread's two 32-column units (warp-uniform branches)
-        uint32_t pk[16];
-        const bool off_diag = REV ? u > rb : u < rb;  // fully unmasked 32x32 block
-        if (off_diag) {  // rank-1 decay, one exp per row
-          float v[32];
-          tmem_ld32(tS + lane_base + u * 32, v);
-          const float r_t = ex2_approx(x_t + gb[GateBuf::oScal + 4 + u]);
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 cf = *reinterpret_cast<const float4*>(scf + u * 32 + 4 * j4);
-            const float p0 = v[4 * j4 + 0] * (cf.x * r_t), p1 = v[4 * j4 + 1] * (cf.y * r_t);
-            const float p2 = v[4 * j4 + 2] * (cf.z * r_t), p3 = v[4 * j4 + 3] * (cf.w * r_t);
-            rs += (p0 + p1) + (p2 + p3);
-            pk[2 * j4] = pack2<T>(p0, p1);
-            pk[2 * j4 + 1] = pack2<T>(p2, p3);
-          }
-        } else if (u == rb) {  // diagonal block: causal mask, one exp per entry
-          float v[32];
-          tmem_ld32(tS + lane_base + u * 32, v);
-#pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 y = *reinterpret_cast<const float4*>(sy + u * 32 + 4 * j4);
-            const float yy[4] = {y.x, y.y, y.z, y.w};
-            float pv[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = 4 * j4 + e;
-              pv[e] = v[j] * ex2_approx(x_t + yy[e]);
-              pv[e] = (REV ? j >= lane : j <= lane) ? pv[e] : 0.f;
-            }
-            rs += (pv[0] + pv[1]) + (pv[2] + pv[3]);
-            pk[2 * j4] = pack2<T>(pv[0], pv[1]);
-            pk[2 * j4 + 1] = pack2<T>(pv[2], pv[3]);
-          }
-        } else {  // above the diagonal: zeros (the S MMA of every tile overwrites these columns)
-#pragma unroll
-          for (int j = 0; j < 16; ++j) pk[j] = 0u;
-        }
-        tmem_st16(tS + lane_base + u * 32, pk);
-      }
-      srs[ch * LT + row] = rs;  // read by this tile's E-warps after bar_h, i.e. after this arrival
-      tmem_st_wait();
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bar_p[pb]);
-      TC_PROF2(c, 3, 96);
-      m_run = m_next;
-    }
-  } else {
-    // =========================== E-warps: epilogue(c), state update(c), Kbar(c+1) ===========================
-    // Kbar = abar . K of tile c (this thread: row, CW columns) into sKb; sKb is free: dC(c-1) completed before the state
-    // update of tile c-1.  m_in = max state entering the tile; returns the one leaving it.
-    auto kbar_of = [&](int c, float m_in) {
-      const int s = c % NSTAGE, gi = c % SM::kGateBufs;
-      const uint8_t* sK = smem + SM::oK + s * SM::kTile;
-      const float* gb = fsm + SM::fGates + gi * GateBuf::kFloats;
-      mbar_wait(&bar_g[gi], (c / SM::kGateBufs) & 1, 2);
-      const float g = gb[GateBuf::oScal], amax = gb[GateBuf::oScal + 1];
-      const float m_next = p.sig ? 0.f : fmaxf(g + m_in, g + amax);    // fw.py:96-98
-      const float ab = __expf(g - gb[GateBuf::oB + row] + gb[GateBuf::oI + row] - m_next);  // fw.py:102 (0 for tail tokens)
-      mbar_wait(&bar_full[s], (c / NSTAGE) & 1, 3);
-      float kb[CW];
-#pragma unroll
-      for (int j = 0; j < CW / 8; ++j) {
-        uint4 u = *reinterpret_cast<const uint4*>(sK + L::swz(row, ch * CW + 8 * j));
-        float2 a0 = unpack2<T>(u.x), a1 = unpack2<T>(u.y), a2 = unpack2<T>(u.z), a3 = unpack2<T>(u.w);
-        kb[8 * j + 0] = a0.x * ab; kb[8 * j + 1] = a0.y * ab; kb[8 * j + 2] = a1.x * ab; kb[8 * j + 3] = a1.y * ab;
-        kb[8 * j + 4] = a2.x * ab; kb[8 * j + 5] = a2.y * ab; kb[8 * j + 6] = a3.x * ab; kb[8 * j + 7] = a3.y * ab;
-      }
-      store_cols<T, D>(sKb, row, ch * CW, kb);
-      fence_proxy_async_smem();
-      named_arrive(NB2_KB, kNb2PC);
-      return m_next;
-    };
-    float m_run = p.m0 ? p.m0[bh] : 0.f;   // max state entering tile c
-    float m_next = kbar_of(0, m_run);      // ... and leaving it
-    for (int c = 0; c < p.NT; ++c) {
-      const uint32_t par = c & 1;
-      const int gi = c % SM::kGateBufs;
-      const float* gb = fsm + SM::fGates + gi * GateBuf::kFloats;
-      const float* srs = fsm + SM::fRs + gi * 2 * LT;
-      const int t0 = mt(c) * LT;
-      const int n_valid = min(LT, p.S - t0);
-      TC_PROF2(c, 4, 352);
-      const float g = gb[GateBuf::oScal];
-      const float gbar = __expf(g + m_run - m_next);                    // fw.py:106
-      const float b_t = gb[GateBuf::oB + row];
-      const float m_t = p.sig ? 0.f : b_t + fmaxf(m_run, gb[GateBuf::oPm + row]);  // fw.py:178-184
-      // ---- epilogue -----------------------------------------------------------------------------------
-      mbar_wait(&bar_hx, par, 9);
-      mbar_wait(&bar_h, par, 7);
-      tc_fence_after_sync();
-      TC_PROF2(c, 5, 352);
-      {
-        uint32_t qn_u;
-        tmem_ld1_nowait(tHx + lane_base + D, qn_u);  // q . n_{k-1}
-        const float bq = __expf(b_t + m_run - m_t) * p.scale;  // fw.py:197-198
-        const float rs = srs[row] + srs[LT + row];
-        tmem_ld_wait();
-        const float den = bq * __uint_as_float(qn_u) + rs;       // fw.py:204-206
-        const float nmax = fmaxf(fabsf(den), __expf(-m_t));    // fw.py:208-210
-        const float inv = 1.f / (nmax + p.eps);
-        const float bqi = bq * inv;
-#pragma unroll
-        for (int hf = 0; hf < CW / 16; ++hf) {  // 16 columns at a time keeps the live registers under the 112 cap
-          uint32_t hi[16], hx[16];
-          tmem_ld16_nowait(tHi + lane_base + ch * CW + hf * 16, hi);
-          tmem_ld16_nowait(tHx + lane_base + ch * CW + hf * 16, hx);
-          tmem_ld_wait();
-          float o[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) o[j] = __uint_as_float(hi[j]) * inv + bqi * __uint_as_float(hx[j]);  // fw.py:200-212
-          store_cols<T, D>(sH, row, ch * CW + hf * 16, o);
-        }
-        fence_proxy_async_smem();
-        tc_fence_before_sync();
-        named_arrive(NB2_EPI, kNb2PC);
-        if (ch == 0 && row < n_valid) {
-          p.n_out[(int64_t)bh * p.S + t0 + row] = nmax;
-          p.m_out[(int64_t)bh * p.S + t0 + row] = m_t;
-        }
-      }
-      TC_PROF2(c, 6, 352);
-      // ---- state update C_k = gbar C_{k-1} + dC; n_k ---------------------------------------------------
-      mbar_wait(&bar_dc, par, 6);
-      tc_fence_after_sync();
-      TC_PROF2(c, 7, 352);
-      {
-        uint32_t v[CW], dn_u;
-        tmem_ld_nowait(tDC + lane_base + ch * CW, v);  // M=64 layout: lanes 0-15 of each quadrant hold rows
-        tmem_ld1_nowait(tDN + lane_base, dn_u);
-        tmem_ld_wait();
-        if (owns_c) {
-#pragma unroll
-          for (int j = 0; j < CW; ++j) Creg[j] = gbar * Creg[j] + __uint_as_float(v[j]);
-          store_cols<T, D>(sC, drow, ch * CW, Creg);  // Q [C | n]_{k-1} (bar_hx) has finished reading the old copies
-          if (ch == 0) {  // n_k = gbar n_{k-1} + column sums of Kbar (fw.py:116)
-            n_reg = gbar * n_reg + __uint_as_float(dn_u);
-            *reinterpret_cast<T*>(sNt + L::swz(drow, 0)) = from_f32<T>(n_reg);
-          }
-        }
-      }
-      fence_proxy_async_smem();
-      tc_fence_before_sync();
-      named_arrive(NB2_ST, kNb2E);
-      TC_PROF2(c, 8, 352);
-      m_run = m_next;
-      if (c + 1 < p.NT) m_next = kbar_of(c + 1, m_run);
-    }
-    // final states (fw.py:302-309)
-    if (p.c_last) {
-      if (owns_c) {
-        float* dst = p.c_last + ((int64_t)bh * D + drow) * D + ch * CW;
-#pragma unroll
-        for (int j = 0; j < CW; ++j) dst[j] = Creg[j];
-      }
-      if (owns_c && ch == 0) p.n_last[(int64_t)bh * D + drow] = n_reg;
-      if (tid == 256) p.m_last[bh] = m_run;
-    }
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  TC_PROF_CTA(1);
-  if (warp == kFw2Ctl) tmem_dealloc<512>(tmem);
-}
-
-// =============================================================================================
 // Forward, head dim 128 (640-base384.yaml: NH=6, DH=128; the inference config of BASELINE.json).
 // Same algorithm and warp roles as tc_fw_d64; differences: every Q/K/V/H/C tile is two [128][64]
 // swizzled sub-tiles (column halves), dC = Kbar^T V is M128 N128 so C lives in the plain TMEM
@@ -2744,27 +1797,9 @@ cudaError_t launch_pdl(bool use_pdl, void (*kern)(KArgs...), int grid, int block
   return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
-int fw_variant() {  // development A/B switch: MLSTM_B200_FW=1 selects the single-group forward
-  static const int v = [] { const char* e = getenv("MLSTM_B200_FW"); return e ? atoi(e) : 2; }();
-  return v;
-}
-
-template <typename T, int D>
-int launch_fw2(const TcFwParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
-               const CUtensorMap& mh, const CUtensorMap& mcs, cudaStream_t st) {
-  using SM = Fw2Smem<D>;
-  auto kern = p.rev ? tc_fw2<T, D, true> : tc_fw2<T, D, false>;
-  MLSTM_CUDA_CHECK(ensure_smem(kern, SM::kBytes));
-  MLSTM_CUDA_CHECK(launch_pdl(pdl_mode() != 0, kern, p.B * p.NH, kFw2Threads, SM::kBytes, st, mq, mk, mv, mh, mcs, p));
-  count_launch();
-  MLSTM_CUDA_CHECK(cudaGetLastError());
-  return 0;
-}
-
 template <typename T, int D>
 int launch_fw(const TcFwParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
               const CUtensorMap& mh, const CUtensorMap& mcs, cudaStream_t st) {
-  if (D == 64 && fw_variant() == 2) return launch_fw2<T, 64>(p, mq, mk, mv, mh, mcs, st);
   using SM = FwSmem<D>;
   auto kern = p.rev ? tc_fw<T, D, true> : tc_fw<T, D, false>;
   MLSTM_CUDA_CHECK(ensure_smem(kern, SM::kBytes));
