@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define MLSTM_B200_ABI_VERSION 1
+#define MLSTM_B200_ABI_VERSION 2
 
 /* element types of q/k/v/i/f/h and of the gradients */
 enum { MLSTM_B200_F32 = 0, MLSTM_B200_BF16 = 1, MLSTM_B200_F16 = 2 };
@@ -78,6 +78,12 @@ typedef struct mlstm_b200_shape {
                          parallel/native_siging/fw.py:15-74); m_initial / m_last are then ignored / zero */
   float eps;
   float qk_scale;     /* <= 0 selects DHQK^-0.5 (native/fw.py:263-264) */
+  float gate_soft_cap;/* > 0: i and f are gate PRE-activations and the kernels apply the cell's soft cap
+                         cap * tanh(x / cap) themselves (MatrixLSTMCell.soft_cap, vision_lstm2.py:714-715, 755-756)
+                         while scanning; di / df are then gradients w.r.t. the pre-activations (the factor
+                         1 - tanh^2(x / cap) is applied at the store).  Tensor-core route only: the exact route
+                         returns MLSTM_B200_EUNSUPPORTED for gate_soft_cap > 0.  <= 0: i / f are used as given. */
+  int32_t reserved;   /* must be 0 */
 } mlstm_b200_shape;
 
 typedef struct mlstm_b200_fw_args {
@@ -154,6 +160,37 @@ int mlstm_b200_last_launch_count(void);
  * boundaries (forward at [tile*16 + slot], backward at [4096 + tile*16 + slot]).  NULL disables it.
  * In the product library this is a no-op: the product build holds no process-global mutable state. */
 void mlstm_b200_debug_set_clock_buffer(void* dev_ptr);
+
+/* ---------------------------------------------------------------------------------------------
+ * Recurrent form: S token-by-token steps of the mLSTM with the (C, n, m) state kept on
+ * chip for the whole call.  S = 1 is the step kernel
+ *   mlstm_recurrent_step__native_fw      mlstm_kernels/torch/recurrent/native_step.py:8-101
+ * and S > 1 the sequence loop around it
+ *   _mlstm_recurrent_sequence_loop_fw    mlstm_kernels/torch/recurrent/native_sequence.py:14-130
+ * which the reference's inference wrapper runs for the tokens that do not fill a chunk
+ * (wrap_chunkwise__arbitrary_sequence_length, mlstm_kernels/torch/kernel_wrappers.py:12-201).
+ *   q, k (B, NH, S, DHQK), v, h (B, NH, S, DHHV), i, f (B, NH, S): element strides [b, head, s, 1] / [b, head, s];
+ *   DHQK == DHHV in {32, 64, 128}; dtype of q / k / v / i / f / h; states contiguous fp32 as in the chunkwise calls
+ *   (m is (B, NH)).  Initial states: all three or none (none = zeros); last states: all three or none; the last
+ *   states may alias the initial ones (in-place update).  siging = 1: sigmoid input gate, m stays 0.
+ *   Forward only (the reference's recurrent kernels have no backward).
+ */
+typedef struct mlstm_b200_recurrent_args {
+  int32_t B, NH, S, DHQK, DHHV;
+  int32_t dtype;  /* MLSTM_B200_F32 / BF16 / F16 */
+  int32_t siging;
+  float eps;
+  mlstm_b200_tensor q, k, v, i, f;
+  const float* c_initial;
+  const float* n_initial;
+  const float* m_initial;
+  mlstm_b200_tensor h; /* out */
+  float* c_last;
+  float* n_last;
+  float* m_last;
+} mlstm_b200_recurrent_args;
+
+int mlstm_b200_recurrent_sequence(const mlstm_b200_recurrent_args* args, void* cuda_stream);
 
 /* ---------------------------------------------------------------------------------------------
  * The cell's output stage (the callers either side of the path).

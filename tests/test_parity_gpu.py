@@ -545,3 +545,54 @@ def test_d128_backward_recompute_equals_saved_states(pkg, reverse):
                                reverse=reverse, want_dc_initial=True, dc_last=t["dc_last"], **kw)
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+def test_views_the_tma_cannot_describe_are_accepted(pkg):
+    """The reference takes any strides (its @contiguous decorator copies every argument, mlstm_kernels/torch/utils.py:30-42).
+    Views a TMA tensor map cannot describe -- a base pointer at an odd offset, a token stride that is not a multiple of
+    16 bytes, a broadcast batch -- are copied by the host side (AUTO route) instead of raising, and give bit-identical
+    results to the contiguous call; at the C-ABI the same views fall through to the any-stride exact kernels."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(3)
+    B, NH, S, D = 2, 3, 256, 64
+    big = torch.randn(B, NH, S, D + 16, generator=g).to(torch.bfloat16).to(dev)
+    q = big[..., 3:3 + D]                                     # base pointer 6 bytes off
+    k = torch.randn(1, NH, S, D, generator=g).to(torch.bfloat16).to(dev).expand(B, NH, S, D)  # stride-0 batch
+    odd = torch.randn(B, NH, S, D + 4, generator=g).to(torch.bfloat16).to(dev)
+    v = odd[..., :D]                                          # token stride 68 elements = 136 bytes
+    i = torch.randn(B, NH, S, generator=g).to(torch.bfloat16).to(dev)
+    f = (3.0 + torch.randn(B, NH, S, generator=g)).to(torch.bfloat16).to(dev)
+    dh = torch.randn(B, NH, S, D + 4, generator=g).to(torch.bfloat16).to(dev)[..., 2:2 + D]
+    assert q.data_ptr() % 16 and v.stride(2) % 8 and k.stride(0) == 0
+
+    def run(q, k, v, dh):
+        leaves = [t.detach().requires_grad_(True) for t in (q, k, v, i, f)]
+        h = pkg.mlstm_chunkwise__b200(*leaves, chunk_size=64)
+        grads = torch.autograd.grad(h, leaves, dh)
+        torch.cuda.synchronize()
+        return [h] + list(grads)
+
+    got = run(q, k, v, dh)
+    want = run(q.contiguous(), k.contiguous(), v.contiguous(), dh.contiguous())
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and torch.equal(a, b)
+    # C-ABI level: AUTO + misaligned q -> exact kernels (needs the exact family's workspace)
+    import ctypes as C
+
+    from xlstm_yolo_clean_b200 import _cabi, backend
+    lib = _cabi.load_library()
+    a = _cabi.FwArgs()
+    a.shape = backend._shape(q, v, 64, 1e-6, _cabi.IMPL_AUTO)
+    ex = backend._shape(q, v, 64, 1e-6, _cabi.IMPL_EXACT)
+    ws = torch.empty(lib.mlstm_b200_workspace_bytes(C.byref(ex), 0), dtype=torch.uint8, device=dev)
+    h = torch.empty(B, NH, S, D, dtype=torch.bfloat16, device=dev)
+    nm = torch.empty(2, B, NH, S, dtype=torch.float32, device=dev)
+    kc, vc = k.contiguous(), v.contiguous()
+    a.q, a.k, a.v, a.i, a.f, a.h = (backend._tensor(t) for t in (q, kc, vc, i, f, h))
+    a.n_out, a.m_out = nm[0].data_ptr(), nm[1].data_ptr()
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+    st = lib.mlstm_b200_chunkwise_fw(C.byref(a), None)
+    torch.cuda.synchronize()
+    assert st == 0, lib.mlstm_b200_last_error()
+    assert lib.mlstm_b200_last_launch_count() == 2  # the exact family's two forward kernels, not the tensor path's one
+    assert O.rel_err(h.double().cpu(), want[0].double().cpu()) < 2e-2

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmlstm_b200.so")
 
 F32, BF16, F16 = 0, 1, 2
 IMPL_AUTO, IMPL_EXACT, IMPL_TENSOR = 0, 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTS = (
     "mlstm_b200_abi_version",
@@ -24,6 +24,7 @@ EXPORTS = (
     "mlstm_b200_chunkwise_bw",
     "mlstm_b200_last_launch_count",
     "mlstm_b200_debug_set_clock_buffer",
+    "mlstm_b200_recurrent_sequence",
     "mlstm_b200_cellout_workspace_bytes",
     "mlstm_b200_cellout_fw",
     "mlstm_b200_cellout_bw",
@@ -41,7 +42,7 @@ class Shape(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("NH", C.c_int32), ("S", C.c_int32), ("DHQK", C.c_int32), ("DHHV", C.c_int32),
         ("chunk_size", C.c_int32), ("dtype", C.c_int32), ("impl", C.c_int32), ("reverse", C.c_int32), ("siging", C.c_int32),
-        ("eps", C.c_float), ("qk_scale", C.c_float),
+        ("eps", C.c_float), ("qk_scale", C.c_float), ("gate_soft_cap", C.c_float), ("reserved", C.c_int32),
     ]
 
 
@@ -70,6 +71,17 @@ class BwArgs(C.Structure):
         ("dq", Tensor), ("dk", Tensor), ("dv", Tensor), ("di", Tensor), ("df", Tensor),
         ("dc_initial", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+class RecurrentArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("NH", C.c_int32), ("S", C.c_int32), ("DHQK", C.c_int32), ("DHHV", C.c_int32),
+        ("dtype", C.c_int32), ("siging", C.c_int32), ("eps", C.c_float),
+        ("q", Tensor), ("k", Tensor), ("v", Tensor), ("i", Tensor), ("f", Tensor),
+        ("c_initial", C.c_void_p), ("n_initial", C.c_void_p), ("m_initial", C.c_void_p),
+        ("h", Tensor),
+        ("c_last", C.c_void_p), ("n_last", C.c_void_p), ("m_last", C.c_void_p),
     ]
 
 
@@ -140,6 +152,8 @@ def load_library(path: str | None = None):
     lib.mlstm_b200_last_launch_count.restype = C.c_int
     lib.mlstm_b200_debug_set_clock_buffer.restype = None
     lib.mlstm_b200_debug_set_clock_buffer.argtypes = [C.c_void_p]
+    lib.mlstm_b200_recurrent_sequence.restype = C.c_int
+    lib.mlstm_b200_recurrent_sequence.argtypes = [C.POINTER(RecurrentArgs), C.c_void_p]
     lib.mlstm_b200_cellout_workspace_bytes.restype = C.c_size_t
     lib.mlstm_b200_cellout_workspace_bytes.argtypes = [C.POINTER(CellOutArgs)]
     lib.mlstm_b200_cellout_fw.restype = C.c_int

@@ -70,7 +70,7 @@ class _on_device:
             self.ctx.__exit__(*a)
 
 
-def _shape(q, v, chunk_size, eps, impl, qk_scale=None, reverse=False, siging=False) -> _cabi.Shape:
+def _shape(q, v, chunk_size, eps, impl, qk_scale=None, reverse=False, siging=False, gate_soft_cap=0.0) -> _cabi.Shape:
     B, NH, S, DK = q.shape
     s = _cabi.Shape()
     s.B, s.NH, s.S, s.DHQK, s.DHHV = B, NH, S, DK, v.shape[-1]
@@ -81,6 +81,7 @@ def _shape(q, v, chunk_size, eps, impl, qk_scale=None, reverse=False, siging=Fal
     s.siging = 1 if siging else 0
     s.eps = float(eps)
     s.qk_scale = -1.0 if qk_scale is None else float(qk_scale)
+    s.gate_soft_cap = float(gate_soft_cap or 0.0)
     return s
 
 
@@ -176,7 +177,8 @@ def _ws_tensor(nbytes: int, dev):
     return torch.empty(nbytes, dtype=torch.uint8, device=dev)
 
 
-def _fw_launch(q, k, v, i, f, c0, n0, m0, qk_scale, return_last_states, chunk_size, eps, impl, save_states, reverse, siging):
+def _fw_launch(q, k, v, i, f, c0, n0, m0, qk_scale, return_last_states, chunk_size, eps, impl, save_states, reverse, siging,
+               soft_cap=0.0):
     """Returns h, nm (2, B, NH, S) fp32 = [n_out, m_out], last-or-None, c_states-or-None."""
     impl = _default_impl if impl is None else impl
     dt = q.dtype
@@ -190,7 +192,7 @@ def _fw_launch(q, k, v, i, f, c0, n0, m0, qk_scale, return_last_states, chunk_si
         v = v.to(dt)
     dev = q.device
     key = (0, q.shape, v.shape[3], dt, q.stride(), k.stride(), v.stride(), i.stride(), f.stride(), chunk_size, eps, impl,
-           qk_scale, reverse, siging, c0 is not None, return_last_states, save_states, dev.index)
+           qk_scale, reverse, siging, c0 is not None, return_last_states, save_states, dev.index, soft_cap)
     plans = _plans()
     plan = plans.get(key)
     lib = _cabi.load_library()
@@ -199,13 +201,15 @@ def _fw_launch(q, k, v, i, f, c0, n0, m0, qk_scale, return_last_states, chunk_si
         B, NH, S, DK = q.shape
         assert S % chunk_size == 0, f"Sequence length {S} is not divisible by chunk size {chunk_size}."
         a = _cabi.FwArgs()
-        a.shape = _shape(q, v, chunk_size, eps, impl, qk_scale, reverse, siging)
+        a.shape = _shape(q, v, chunk_size, eps, impl, qk_scale, reverse, siging, soft_cap)
         plan = _FwPlan()
         plan.tensor_route = _tensor_route(lib, a.shape)
+        if soft_cap and not plan.tensor_route:
+            raise RuntimeError("gate_soft_cap is applied in-kernel on the tensor-core route only; cap the gates first")
         fixed = _fix_views(plan.tensor_route, (q, k, v))
         if any(x is not y for x, y in zip(fixed, (q, k, v))):  # a signature that needs copies: plan on the copies
             return _fw_launch(*fixed, i, f, c0, n0, m0, qk_scale, return_last_states, chunk_size, eps, impl, save_states,
-                              reverse, siging)
+                              reverse, siging, soft_cap)
         plan.ws_bytes = lib.mlstm_b200_workspace_bytes(C.byref(a.shape), 0)
         plan.st_bytes = lib.mlstm_b200_states_bytes(C.byref(a.shape)) if save_states else 0
         plan.h_shape, plan.nm_shape = (B, NH, S, v.shape[3]), (2, B, NH, S)
@@ -222,7 +226,7 @@ def _fw_launch(q, k, v, i, f, c0, n0, m0, qk_scale, return_last_states, chunk_si
     if torch._C._cuda_getDevice() != dev.index:
         with torch.cuda.device(dev):
             return _fw_launch(q, k, v, i, f, c0, n0, m0, qk_scale, return_last_states, chunk_size, eps, impl, save_states,
-                              reverse, siging)
+                              reverse, siging, soft_cap)
     h = torch.empty(plan.h_shape, dtype=dt, device=dev)
     nm = torch.empty(plan.nm_shape, dtype=torch.float32, device=dev)
     c_states = torch.empty(plan.st_bytes, dtype=torch.uint8, device=dev) if plan.st_bytes else None
@@ -252,8 +256,12 @@ def _fw_launch(q, k, v, i, f, c0, n0, m0, qk_scale, return_last_states, chunk_si
 
 
 def mlstm_chunkwise_fw(q, k, v, i, f, c_initial=None, n_initial=None, m_initial=None, qk_scale=None,
-                       return_last_states=False, chunk_size=64, eps=1e-6, impl=None, save_states=True, reverse=False, siging=False):
+                       return_last_states=False, chunk_size=64, eps=1e-6, impl=None, save_states=True, reverse=False, siging=False,
+                       gate_soft_cap=0.0):
     """C-ABI forward.  Returns h, n_out, m_out, last_states-or-None (fp32), c_states-or-None.
+
+    ``gate_soft_cap`` > 0: ``i`` / ``f`` are gate pre-activations and the kernel applies ``cap * tanh(x / cap)``
+    (MatrixLSTMCell.soft_cap, vision_lstm2.py:714-715) while it scans them (tensor-core route only).
 
     ``c_states`` is the opaque per-tile state buffer the tensor-core backward consumes (the
     reference's return_all_states mode, native/fwbw.py:73-101); None when the kernels recompute."""
@@ -261,12 +269,13 @@ def mlstm_chunkwise_fw(q, k, v, i, f, c_initial=None, n_initial=None, m_initial=
         B, NH, S, DK = q.shape
         c_initial = torch.zeros(B, NH, DK, v.shape[-1], device=q.device)
     h, nm, last, c_states = _fw_launch(q, k, v, i, f, c_initial, n_initial, m_initial, qk_scale, bool(return_last_states),
-                                       int(chunk_size), float(eps), impl, bool(save_states), bool(reverse), bool(siging))
+                                       int(chunk_size), float(eps), impl, bool(save_states), bool(reverse), bool(siging),
+                                       float(gate_soft_cap or 0.0))
     return h, nm[0], nm[1], last, c_states
 
 
 def _bw_launch(q, k, v, i, f, n_ptr, m_ptr, dh, c0, n0, m0, dcl, qk_scale, chunk_size, eps, impl, want_dc_initial, c_states,
-               reverse, siging, out):
+               reverse, siging, out, soft_cap=0.0):
     impl = _default_impl if impl is None else impl
     dt = q.dtype
     if dh.dtype is not dt:
@@ -278,7 +287,7 @@ def _bw_launch(q, k, v, i, f, n_ptr, m_ptr, dh, c0, n0, m0, dcl, qk_scale, chunk
     dev = q.device
     key = (1, q.shape, v.shape[3], dt, q.stride(), k.stride(), v.stride(), i.stride(), f.stride(), dh.stride(), chunk_size, eps,
            impl, qk_scale, reverse, siging, c0 is not None, want_dc_initial, c_states is not None, dev.index,
-           None if out is None else tuple(t.stride() for t in out))
+           None if out is None else tuple(t.stride() for t in out), soft_cap)
     plans = _plans()
     plan = plans.get(key)
     lib = _cabi.load_library()
@@ -287,13 +296,13 @@ def _bw_launch(q, k, v, i, f, n_ptr, m_ptr, dh, c0, n0, m0, dcl, qk_scale, chunk
         B, NH, S, DK = q.shape
         DV = v.shape[3]
         a = _cabi.BwArgs()
-        a.shape = _shape(q, v, chunk_size, eps, impl, qk_scale, reverse, siging)
+        a.shape = _shape(q, v, chunk_size, eps, impl, qk_scale, reverse, siging, soft_cap)
         plan = _BwPlan()
         plan.tensor_route = _tensor_route(lib, a.shape)
         fixed = _fix_views(plan.tensor_route, (q, k, v, dh))
         if any(x is not y for x, y in zip(fixed, (q, k, v, dh))):
             return _bw_launch(*fixed[:3], i, f, n_ptr, m_ptr, fixed[3], c0, n0, m0, dcl, qk_scale, chunk_size, eps, impl,
-                              want_dc_initial, c_states, reverse, siging, out)
+                              want_dc_initial, c_states, reverse, siging, out, soft_cap)
         if out is not None:
             dq, dk, dv, di, df = out
             assert dq.shape == q.shape and dk.shape == k.shape and dv.shape == v.shape and di.shape == i.shape
@@ -322,7 +331,7 @@ def _bw_launch(q, k, v, i, f, n_ptr, m_ptr, dh, c0, n0, m0, dcl, qk_scale, chunk
     if torch._C._cuda_getDevice() != dev.index:
         with torch.cuda.device(dev):
             return _bw_launch(q, k, v, i, f, n_ptr, m_ptr, dh, c0, n0, m0, dcl, qk_scale, chunk_size, eps, impl,
-                              want_dc_initial, c_states, reverse, siging, out)
+                              want_dc_initial, c_states, reverse, siging, out, soft_cap)
     if out is not None:
         dq, dk, dv, di, df = out
         if plan.tensor_route and (dq.data_ptr() | dk.data_ptr() | dv.data_ptr()) & 15:
@@ -363,8 +372,10 @@ def _bw_launch(q, k, v, i, f, n_ptr, m_ptr, dh, c0, n0, m0, dcl, qk_scale, chunk
 
 def mlstm_chunkwise_bw(q, k, v, i, f, n_out, m_out, dh, c_initial=None, n_initial=None, m_initial=None,
                        dc_last=None, qk_scale=None, chunk_size=64, eps=1e-6, impl=None, want_dc_initial=False,
-                       c_states=None, reverse=False, siging=False, out=None):
+                       c_states=None, reverse=False, siging=False, out=None, gate_soft_cap=0.0):
     """C-ABI backward.  Returns dq, dk, dv, di, df, dc_initial-or-None (fp32).
+
+    With ``gate_soft_cap`` > 0 (see the forward) di / df are gradients w.r.t. the gate pre-activations.
 
     ``out`` = (dq, dk, dv, di, df) lets the caller provide the gradient tensors (any batch/head/token strides,
     unit innermost stride for dq/dk/dv), e.g. views into a fused (B, S, 2H) qk gradient."""
@@ -374,7 +385,8 @@ def mlstm_chunkwise_bw(q, k, v, i, f, n_out, m_out, dh, c_initial=None, n_initia
     n_out = n_out if n_out.is_contiguous() else n_out.contiguous()
     m_out = m_out if m_out.is_contiguous() else m_out.contiguous()
     return _bw_launch(q, k, v, i, f, n_out.data_ptr(), m_out.data_ptr(), dh, c_initial, n_initial, m_initial, dc_last, qk_scale,
-                      int(chunk_size), float(eps), impl, bool(want_dc_initial), c_states, bool(reverse), bool(siging), out)
+                      int(chunk_size), float(eps), impl, bool(want_dc_initial), c_states, bool(reverse), bool(siging), out,
+                      float(gate_soft_cap or 0.0))
 
 
 def _make_function(autocast_kernel_dtype: torch.dtype):
@@ -495,6 +507,61 @@ def mlstm_siging_chunkwise__b200(
     return h
 
 
+def mlstm_recurrent_sequence__b200(q, k, v, i, f, c_initial=None, n_initial=None, m_initial=None,
+                                   return_last_states: bool = False, eps: float = 1e-6,
+                                   dtype_state: torch.dtype = torch.float32, siging: bool = False, **kwargs):
+    """Token-by-token mLSTM over a whole sequence in ONE launch, state on chip: drop-in for
+    ``mlstm_recurrent_sequence__native_fw`` (mlstm_kernels/torch/recurrent/native_sequence.py:133-175; registry name
+    ``native_sequence__native``).  q, k (B, NH, S, DHQK), v (B, NH, S, DHHV), i, f (B, NH, S).
+    Returns h, or (h, (C, n, m)) with ``return_last_states`` -- the reference's convention; forward only."""
+    lib = _cabi.load_library()
+    for name, t in (("q", q), ("k", k), ("v", v), ("i", i), ("f", f)):
+        if not t.is_cuda:
+            raise RuntimeError(f"mlstm_recurrent_sequence__b200: {name} is on {t.device}; this backend has no CPU path")
+    B, NH, S, DK = q.shape
+    DV = v.shape[-1]
+    dt = q.dtype
+    if dt not in _DTYPES:
+        raise RuntimeError(f"unsupported dtype {dt}")
+    q, k, v = (t if t.stride(-1) == 1 else t.contiguous() for t in (q, k.to(dt), v.to(dt)))
+    i, f = i.reshape(B, NH, S).to(dt), f.reshape(B, NH, S).to(dt)
+    dev = q.device
+    with _on_device(dev):
+        a = _cabi.RecurrentArgs()
+        a.B, a.NH, a.S, a.DHQK, a.DHHV, a.dtype, a.siging, a.eps = B, NH, S, DK, DV, _DTYPES[dt], int(bool(siging)), float(eps)
+        h = torch.empty(B, NH, S, DV, dtype=dt, device=dev)
+        a.q, a.k, a.v, a.i, a.f, a.h = (_tensor(t) for t in (q, k, v, i, f, h))
+        keep = []
+        if c_initial is not None:
+            c0 = _state_f32(c_initial, (B, NH, DK, DV))
+            n0 = _state_f32(n_initial, (B, NH, DK)) if n_initial is not None else torch.zeros(B, NH, DK, device=dev)
+            m0 = _state_f32(m_initial, (B, NH)) if m_initial is not None else torch.zeros(B, NH, device=dev)
+            keep = [c0, n0, m0]
+            a.c_initial, a.n_initial, a.m_initial = c0.data_ptr(), n0.data_ptr(), m0.data_ptr()
+        last = None
+        if return_last_states:
+            last = (torch.empty(B, NH, DK, DV, dtype=torch.float32, device=dev),
+                    torch.empty(B, NH, DK, dtype=torch.float32, device=dev),
+                    torch.empty(B, NH, 1, dtype=torch.float32, device=dev))
+            a.c_last, a.n_last, a.m_last = (t.data_ptr() for t in last)
+        st = lib.mlstm_b200_recurrent_sequence(C.byref(a), _raw_stream(dev.index))
+        _cabi.check(st, "mlstm_b200_recurrent_sequence")
+    if last is None:
+        return h
+    return h, tuple(t.to(dtype_state) for t in last)
+
+
+def mlstm_recurrent_step__b200(q, k, v, i, f, c, n, m, eps: float = 1e-6, dtype_state: torch.dtype = torch.float32,
+                               siging: bool = False, **kwargs):
+    """One recurrent step: drop-in for ``mlstm_recurrent_step__native`` (recurrent/native_step.py:104-132; registry name
+    ``native``).  q, k (B, NH, DHQK), v (B, NH, DHHV), i, f (B, NH, 1); states c (B, NH, DHQK, DHHV), n (B, NH, DHQK),
+    m (B, NH, 1).  Returns h (B, NH, DHHV), (c_new, n_new, m_new)."""
+    h, last = mlstm_recurrent_sequence__b200(q.unsqueeze(2), k.unsqueeze(2), v.unsqueeze(2), i.reshape(*i.shape[:2], 1),
+                                             f.reshape(*f.shape[:2], 1), c, n, m, return_last_states=True, eps=eps,
+                                             dtype_state=dtype_state, siging=siging)
+    return h.squeeze(2), last
+
+
 def register(name: str = KERNEL_NAME) -> str:
     """Insert the kernels into the reference registry (mlstm_kernels/torch/chunkwise/__init__.py:9-15):
     ``<name>`` (exp input gate, max-state stabilised) and ``<name>_siging`` (sigmoid input gate).
@@ -506,6 +573,13 @@ def register(name: str = KERNEL_NAME) -> str:
 
     registry[name] = mlstm_chunkwise__b200
     registry[name + "_siging"] = mlstm_siging_chunkwise__b200
+    try:  # the recurrent registries (mlstm_kernels/torch/recurrent/__init__.py:14-25): step_kernel="b200",
+        from mlstm_kernels.torch.recurrent import registry_sequence, registry_step  # sequence_kernel="native_sequence__b200"
+
+        registry_step[name] = mlstm_recurrent_step__b200
+        registry_sequence["native_sequence__" + name] = mlstm_recurrent_sequence__b200
+    except ImportError:  # pragma: no cover
+        pass
     return f"chunkwise--{name}"
 
 

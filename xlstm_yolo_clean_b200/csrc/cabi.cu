@@ -148,6 +148,14 @@ int mlstm_b200_chunkwise_fw(const mlstm_b200_fw_args* a, void* stream) {
   int err = 0;
   bool tc = use_tensor(a->shape, 0, &err);
   if (err) return err;
+  // AUTO accepts any strides like the reference does (torch/utils.py:30-42): views a TMA tensor map cannot describe
+  // (odd offsets, strides that are not multiples of 16 bytes) go to the exact kernels, which take any stride.  The
+  // exact family needs its own (larger) workspace: mlstm_b200_workspace_bytes with impl = EXACT.
+  if (tc && a->shape.impl == MLSTM_B200_IMPL_AUTO && !tensor_fw_views_ok(*a)) tc = false;
+  if (!tc && a->shape.gate_soft_cap > 0.f) {
+    set_error("gate_soft_cap is applied by the tensor-core kernels only; cap the gates before an exact-route call");
+    return MLSTM_B200_EUNSUPPORTED;
+  }
   return tc ? tensor_fw(*a, (cudaStream_t)stream) : exact_fw(*a, (cudaStream_t)stream);
 }
 
@@ -186,7 +194,23 @@ int mlstm_b200_chunkwise_bw(const mlstm_b200_bw_args* a, void* stream) {
   int err = 0;
   bool tc = use_tensor(a->shape, 1, &err);
   if (err) return err;
+  if (tc && a->shape.impl == MLSTM_B200_IMPL_AUTO && !tensor_bw_views_ok(*a)) tc = false;  // see the forward
+  if (!tc && a->shape.gate_soft_cap > 0.f) {
+    set_error("gate_soft_cap is applied by the tensor-core kernels only; cap the gates before an exact-route call");
+    return MLSTM_B200_EUNSUPPORTED;
+  }
   return tc ? tensor_bw(*a, (cudaStream_t)stream) : exact_bw(*a, (cudaStream_t)stream);
+}
+
+int mlstm_b200_recurrent_sequence(const mlstm_b200_recurrent_args* a, void* stream) {
+  g_err[0] = 0;
+  g_launches = 0;
+  if (!a) {
+    set_error("args is NULL");
+    return MLSTM_B200_EINVAL;
+  }
+  if (int e = require_device()) return e;
+  return recurrent_sequence(*a, (cudaStream_t)stream);
 }
 
 size_t mlstm_b200_cellout_workspace_bytes(const mlstm_b200_cellout_args* a) {

@@ -159,9 +159,14 @@ size_t tensor_workspace_bytes(const mlstm_b200_shape& s, int backward);
 size_t tensor_states_bytes(const mlstm_b200_shape& s);
 void tensor_set_clock_buffer(void* dev_ptr);
 bool tensor_context_is_current();  // a CUDA context is current on the calling thread (driver-level query)
+bool tensor_fw_views_ok(const mlstm_b200_fw_args& a);
+bool tensor_bw_views_ok(const mlstm_b200_bw_args& a);
 int tensor_fw(const mlstm_b200_fw_args& a, cudaStream_t st);
 int tensor_bw(const mlstm_b200_bw_args& a, cudaStream_t st);
 
+
+// recurrent step / sequence (step_kernels.cu)
+int recurrent_sequence(const mlstm_b200_recurrent_args& a, cudaStream_t st);
 
 // cell output stage (cell_kernels.cu)
 size_t cellout_workspace_bytes(const mlstm_b200_cellout_args& a);

@@ -6,6 +6,7 @@
 #include <cuda.h>  // CUtensorMap
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace sm100 {
 
@@ -326,8 +327,33 @@ inline bool context_is_current() {
 // 4-D map over a (B, NH, S, D) 16-bit tensor with element strides (sb, sh, ss, 1);
 // box = (64 cols, box_rows, 1, 1), 128B swizzle, out-of-bounds rows read as zero / are not written.
 // box_cols = 64 -> 128B swizzle (default); box_cols = 32 -> 64B swizzle (head dim 32).
+//
+// cuTensorMapEncodeTiled costs about a microsecond and a forward + backward call pair needs 13 maps; a training step
+// re-issues the same (pointer, shape, strides) signatures step after step (the caching allocator hands the same blocks
+// back), so encoded maps are kept in a small per-thread direct-mapped cache: no lock, re-entrant, nothing shared
+// between the caller's thread and the autograd threads (SURVEY.md section 8b "Threading").
+struct MapKey {
+  const void* ptr;
+  int64_t sb, sh, ss;
+  int32_t B, NH, S, D, box_rows, box_cols, bf16, pad;
+};
 inline int make_map_bhsd(CUtensorMap* map, const void* ptr, bool bf16, int B, int NH, int S, int D, int64_t sb,
                          int64_t sh, int64_t ss, int box_rows, int box_cols = 64) {
+  constexpr int kSlots = 128;
+  struct Slot {
+    MapKey key;
+    CUtensorMap map;
+    bool valid;
+  };
+  static thread_local Slot cache[kSlots];
+  MapKey key{ptr, sb, sh, ss, B, NH, S, D, box_rows, box_cols, bf16 ? 1 : 0, 0};
+  uint64_t h = (uint64_t)(uintptr_t)ptr * 0x9E3779B97F4A7C15ull;
+  h ^= ((uint64_t)(uint32_t)S << 32 | (uint32_t)D) * 0xC2B2AE3D27D4EB4Full + (uint64_t)ss * 31 + (uint64_t)box_rows;
+  Slot& slot = cache[(h >> 32) % kSlots];
+  if (slot.valid && memcmp(&slot.key, &key, sizeof(MapKey)) == 0) {
+    *map = slot.map;
+    return 0;
+  }
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return -1;
   cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)S, (cuuint64_t)NH, (cuuint64_t)B};
@@ -339,7 +365,11 @@ inline int make_map_bhsd(CUtensorMap* map, const void* ptr, bool bf16, int B, in
                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS ? 0 : (int)r;
+  if (r != CUDA_SUCCESS) return (int)r;
+  slot.key = key;
+  slot.map = *map;
+  slot.valid = true;
+  return 0;
 }
 
 }  // namespace sm100_host

@@ -45,8 +45,9 @@ enum { NB_A = 1, NB_B = 2, NB_C = 3, NB_PAIR0 = 4 };  // named barriers: operand
 // per-tile gate vectors produced by the control warp (floats)
 struct GateBuf {
   static constexpr int oB = 0, oI = LT, oPm = 2 * LT, oY = 3 * LT, oF = 4 * LT, oMt = 5 * LT, oNt = 6 * LT,
-                       oCf = 7 * LT, oScal = 8 * LT, kFloats = 8 * LT + 8;
+                       oCf = 7 * LT, oDi = 8 * LT, oDf = 9 * LT, oScal = 10 * LT, kFloats = 10 * LT + 8;
   // oScal: 0 g, 1 amax, 2 m_prev, 3 m_next (backward), 4..7 max of y over each 32-column unit
+  // oDi / oDf: derivative of the soft cap at the raw gate pre-activations (1 when the cap is off); backward only
 };
 
 #ifdef MLSTM_TC_PROFILE  // phase clocks of CTA 0 (tools/phase_clocks.py builds with this flag)
@@ -254,17 +255,41 @@ __device__ __forceinline__ float warp_incl_max_dir(float v, int lane, bool rev) 
 
 // `rev`: anti-causal direction -- the cumulative sums / maxima run from the END of the tile
 // (suffix scans over the memory rows), everything else is unchanged.
+// `cap` > 0: the inputs are gate PRE-activations and the cell's soft cap cap * tanh(x / cap) (MatrixLSTMCell.soft_cap,
+// vision_lstm2.py:714-715, 755-756) is applied here; its derivative 1 - tanh^2 goes to oDi / oDf for the backward.
 template <typename T>
-__device__ __noinline__ void gate_scan_regs(float* gb, const GateRaw<T>& r, bool rev, bool siging) {
+__device__ __noinline__ void gate_scan_regs(float* gb, const GateRaw<T>& r, bool rev, bool siging, float cap = 0.f) {
   const int lane = threadIdx.x & 31;
   float lf[4], iv[4], fv[4];
   float run = 0.f;
+  if (cap > 0.f) {
+    const float rc = 1.f / cap;
+    float di[4], df[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float ti = tanhf(to_f32<T>(r.i[e]) * rc), tf = tanhf(to_f32<T>(r.f[e]) * rc);
+      iv[e] = cap * ti;
+      fv[e] = cap * tf;
+      di[e] = 1.f - ti * ti;
+      df[e] = 1.f - tf * tf;
+    }
+    reinterpret_cast<float4*>(gb + GateBuf::oDi)[lane] = make_float4(di[0], di[1], di[2], di[3]);
+    reinterpret_cast<float4*>(gb + GateBuf::oDf)[lane] = make_float4(df[0], df[1], df[2], df[3]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      iv[e] = to_f32<T>(r.i[e]);
+      fv[e] = to_f32<T>(r.f[e]);
+    }
+    reinterpret_cast<float4*>(gb + GateBuf::oDi)[lane] = make_float4(1.f, 1.f, 1.f, 1.f);
+    reinterpret_cast<float4*>(gb + GateBuf::oDf)[lane] = make_float4(1.f, 1.f, 1.f, 1.f);
+  }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int e = rev ? 3 - k : k;  // scan order inside the lane
     const bool ok = lane * 4 + e < r.n_valid;
-    fv[e] = ok ? to_f32<T>(r.f[e]) : INFINITY;
-    iv[e] = ok ? to_f32<T>(r.i[e]) : -INFINITY;
+    fv[e] = ok ? fv[e] : INFINITY;
+    iv[e] = ok ? iv[e] : -INFINITY;
     if (siging) iv[e] = ok ? logsigmoid_fast(iv[e]) : -INFINITY;  // sigmoid input gate
     run += logsigmoid_fast(fv[e]);
     lf[e] = run;
@@ -323,6 +348,7 @@ struct TcFwParams {
   int rev;           // 1: anti-causal direction (tiles walked from the end, mirrored in-tile mask)
   int sig;           // 1: sigmoid input gate, all max states are 0 (siging variant)
   int store_states;  // 1: TMA-store the bf16 copy of C entering every tile (consumed by the backward)
+  float cap;         // > 0: gate soft cap applied in the scan warp (mlstm_b200_shape::gate_soft_cap)
 #ifdef MLSTM_TC_PROFILE
   long long* prof;   // per-tile phase clocks of CTA 0 (profile build only)
 #endif
@@ -580,7 +606,7 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
     GateRaw<T> raw = raw_of(0);
     for (int n = 0; n < p.NT; ++n) {  // vectors of tile n; tiles 0 and 1 need no buffer hand-back
       if (n >= 2) named_sync(NB_C, kNbC);  // every worker is done with tile n-2: its gate buffer can be reused
-      gate_scan_regs(fsm + SM::fGates + (n & 1) * GateBuf::kFloats, raw, REV, p.sig != 0);
+      gate_scan_regs(fsm + SM::fGates + (n & 1) * GateBuf::kFloats, raw, REV, p.sig != 0, p.cap);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_g[n & 1]);
       if (n + 1 < p.NT) raw = raw_of(n + 1);  // stays in flight until the next hand-back
@@ -944,7 +970,7 @@ tc_fw_d128(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUt
     GateRaw<T> raw = raw_of(0);
     for (int n = 0; n < p.NT; ++n) {
       if (n >= 2) named_sync(NB_C, kNbC);
-      gate_scan_regs(fsm + SM::fGates + (n & 1) * GateBuf::kFloats, raw, REV, p.sig != 0);
+      gate_scan_regs(fsm + SM::fGates + (n & 1) * GateBuf::kFloats, raw, REV, p.sig != 0, p.cap);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_g[n & 1]);
       if (n + 1 < p.NT) raw = raw_of(n + 1);
@@ -1143,6 +1169,7 @@ struct TcBwParams {
   float* dc0;
   int rev;  // 1: the forward ran anti-causally; this sweep then walks the memory tiles in ascending order
   int sig;  // 1: sigmoid input gate (m_out is all zeros, dI picks up sigmoid(-i))
+  float cap;  // > 0: gate soft cap (see TcFwParams); dI / dF are written w.r.t. the pre-activations
   // rows of the saved-states matrix per 128-token tile and row offset of this problem's D x D block inside a tile:
   // (D, 0) normally; (256, 64 * block) when a head-dim-128 backward runs as four head-dim-64 block problems
   int cs_rows, cs_off;
@@ -1450,7 +1477,7 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       return r;
     };
     auto publish = [&](float* gb, const TileRaw& r) {
-      gate_scan_regs(gb, r.g, REV, p.sig != 0);
+      gate_scan_regs(gb, r.g, REV, p.sig != 0, p.cap);
       reinterpret_cast<float4*>(gb + GateBuf::oMt)[lane] = r.mt;
       reinterpret_cast<float4*>(gb + GateBuf::oNt)[lane] = r.nt;
       if (lane == 0) {
@@ -1511,9 +1538,9 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
           const int t = lane * 4 + e;
           if (t < n_valid) {
             const float dsig = p.sig ? 1.f - __expf(gb[GateBuf::oI + t]) : 1.f;  // sigmoid(-i) = 1 - exp(logsigmoid(i))
-            dip[(int64_t)(t0 + t) * p.di_ss] = from_f32<T>(di[e] * dsig);
+            dip[(int64_t)(t0 + t) * p.di_ss] = from_f32<T>(di[e] * dsig * gb[GateBuf::oDi + t]);
             dfp[(int64_t)(t0 + t) * p.df_ss] =
-                from_f32<T>((acc[e] + excl) * sigmoid_neg_f32(gb[GateBuf::oF + t]));  // bw.py:322-323
+                from_f32<T>((acc[e] + excl) * sigmoid_neg_f32(gb[GateBuf::oF + t]) * gb[GateBuf::oDf + t]);  // bw.py:322-323
           }
         }
         carry += __shfl_sync(0xffffffffu, incl, REV ? 31 : 0);
@@ -1884,6 +1911,7 @@ int run_fw(const mlstm_b200_fw_args& a, void* c_states, cudaStream_t st) {
   p.rev = s.reverse ? 1 : 0;
   p.sig = s.siging ? 1 : 0;
   p.store_states = c_states != nullptr;
+  p.cap = s.gate_soft_cap;
   TC_SET_PROF(p, 0);
   if (s.DHQK == 128) {
     if (s.dtype == MLSTM_B200_BF16) return launch_fw_d128<__nv_bfloat16>(p, mq, mk, mv, mh, mcs, st);
@@ -2090,6 +2118,12 @@ int bw128_by_blocks(const mlstm_b200_bw_args& a, cudaStream_t st) {
 
 }  // namespace
 
+// the views a call hands in can be described by TMA tensor maps (16-byte aligned base, 16-byte-multiple strides)
+bool tensor_fw_views_ok(const mlstm_b200_fw_args& a) { return tma_ok(a.q) && tma_ok(a.k) && tma_ok(a.v) && tma_ok(a.h); }
+bool tensor_bw_views_ok(const mlstm_b200_bw_args& a) {
+  return tma_ok(a.q) && tma_ok(a.k) && tma_ok(a.v) && tma_ok(a.dh) && tma_ok(a.dq) && tma_ok(a.dk) && tma_ok(a.dv);
+}
+
 void tensor_set_clock_buffer(void* dev_ptr) {
 #ifdef MLSTM_TC_PROFILE
   g_prof.store((long long*)dev_ptr);
@@ -2182,6 +2216,7 @@ int run_bw(const mlstm_b200_bw_args& a, const void* c_states, int block, cudaStr
   p.dc0 = a.dc_initial;
   p.rev = s.reverse ? 1 : 0;
   p.sig = s.siging ? 1 : 0;
+  p.cap = s.gate_soft_cap;
   p.cs_rows = block < 0 ? D : 256;
   p.cs_off = block < 0 ? 0 : 64 * block;
   TC_SET_PROF(p, 4096);

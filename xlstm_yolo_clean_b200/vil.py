@@ -28,6 +28,7 @@ import torch
 import torch.nn.functional as F
 
 from . import _cabi
+from . import backend as _backend
 from torch.amp import custom_bwd, custom_fwd
 
 from .backend import (_DTYPES, _cell_uses_siging, _on_device, _tensor, mlstm_chunkwise__b200, mlstm_chunkwise_bw, mlstm_chunkwise_fw,
@@ -201,7 +202,7 @@ class _MlstmLayerLayout(torch.autograd.Function):
 
     @staticmethod
     @custom_fwd(device_type="cuda")
-    def forward(ctx, qk, v, gates, NH, reverse, siging, chunk_size, eps, kernel_dtype):
+    def forward(ctx, qk, v, gates, NH, reverse, siging, chunk_size, eps, kernel_dtype, soft_cap=0.0):
         B, S, H = v.shape
         ctx.in_dtypes = (qk.dtype, v.dtype, gates.dtype)
         qk_k, v_k, g_k = (t if t.dtype == kernel_dtype else t.to(kernel_dtype) for t in (qk, v, gates))
@@ -219,9 +220,10 @@ class _MlstmLayerLayout(torch.autograd.Function):
         q, k, vv, i, f = _heads(qk_k, v_k, g_k, NH)
         need_bw = any(ctx.needs_input_grad[:3])
         h, n_out, m_out, _, c_states = mlstm_chunkwise_fw(q, k, vv, i, f, chunk_size=chunk_size, eps=eps,
-                                                          save_states=need_bw, reverse=reverse, siging=siging)
+                                                          save_states=need_bw, reverse=reverse, siging=siging,
+                                                          gate_soft_cap=soft_cap)
         ctx.save_for_backward(qk_k, v_k, g_k, n_out, m_out, c_states)
-        ctx.cfg = (NH, reverse, siging, chunk_size, eps, pad, S)
+        ctx.cfg = (NH, reverse, siging, chunk_size, eps, pad, S, soft_cap)
         if pad:
             h = h[:, :, pad:] if reverse else h[:, :, :S]
         return h
@@ -230,17 +232,17 @@ class _MlstmLayerLayout(torch.autograd.Function):
     @custom_bwd(device_type="cuda")
     def backward(ctx, dh):
         qk_k, v_k, g_k, n_out, m_out, c_states = ctx.saved_tensors
-        NH, reverse, siging, chunk_size, eps, pad, S = ctx.cfg
+        NH, reverse, siging, chunk_size, eps, pad, S, soft_cap = ctx.cfg
         if pad:
             dh = F.pad(dh, (0, 0, pad, 0) if reverse else (0, 0, 0, pad))
         d_qk, d_v, d_g = torch.empty_like(qk_k), torch.empty_like(v_k), torch.empty_like(g_k)
         q, k, vv, i, f = _heads(qk_k, v_k, g_k, NH)
         mlstm_chunkwise_bw(q, k, vv, i, f, n_out, m_out, dh, chunk_size=chunk_size, eps=eps, c_states=c_states,
-                           reverse=reverse, siging=siging, out=_heads(d_qk, d_v, d_g, NH))
+                           reverse=reverse, siging=siging, out=_heads(d_qk, d_v, d_g, NH), gate_soft_cap=soft_cap)
         if pad:
             d_qk, d_v, d_g = ((t[:, pad:] if reverse else t[:, :S]) for t in (d_qk, d_v, d_g))
         d_qk, d_v, d_g = (t if t.dtype == dt else t.to(dt) for t, dt in zip((d_qk, d_v, d_g), ctx.in_dtypes))
-        return d_qk, d_v, d_g, None, None, None, None, None, None
+        return d_qk, d_v, d_g, None, None, None, None, None, None, None
 
 
 def _is_reverse(layer) -> bool:
@@ -290,17 +292,24 @@ def mlstm_cell_b200(cell, q, k, v, reverse=False, skip=None, x_skip=None, siging
     NH = cell.num_heads
     D = H // NH
     if_preact = _gate_preact(cell, q, k, v, qk)
-    capped = cell.gate_soft_cap * torch.tanh(if_preact / cell.gate_soft_cap)  # soft_cap, vision_lstm2.py:755-756
     model_dtype = q.dtype
     if qk is not None:  # layer-layout path: the kernel reads / writes the layer's own tensors
-        qk_c, v_c, g_c = qk, v, capped
-        if cell.use_autocast:  # the reference casts on CUDA in train and eval alike (vision_lstm2.py:730-745)
-            qk_c, v_c, g_c = (t.to(cell.autocast_dtype) for t in (qk_c, v_c, g_c))
         autocast_on = torch.is_autocast_enabled("cuda")
-        kdt = qk_c.dtype if (not autocast_on or (kernel_dtype == "input" and qk_c.dtype in (torch.float16, torch.bfloat16))) \
+        in_dt = cell.autocast_dtype if cell.use_autocast else qk.dtype  # the reference casts on CUDA in train and eval
+        kdt = in_dt if (not autocast_on or (kernel_dtype == "input" and in_dt in (torch.float16, torch.bfloat16))) \
             else torch.bfloat16  # custom_fwd(cast_inputs=bf16) rule of the registry kernels (native/fwbw.py:37)
-        h = _MlstmLayerLayout.apply(qk_c, v_c, g_c, NH, bool(reverse), bool(siging), int(chunk_size), float(eps), kdt)
+        # soft_cap (vision_lstm2.py:714-715, 755-756): on the tensor-core route the scan warp of the kernels applies
+        # cap * tanh(x / cap) to the pre-activations it reads anyway, and the backward applies its derivative where it
+        # stores dI / dF -- no elementwise passes over the gates in either direction (zero padding stays zero: tanh 0 = 0)
+        in_kernel_cap = (kdt in (torch.float16, torch.bfloat16) and D in (32, 64, 128) and _backend._default_impl != _cabi.IMPL_EXACT)
+        gates = if_preact if in_kernel_cap else cell.gate_soft_cap * torch.tanh(if_preact / cell.gate_soft_cap)
+        qk_c, v_c, g_c = qk, v, gates
+        if cell.use_autocast:
+            qk_c, v_c, g_c = (t.to(cell.autocast_dtype) for t in (qk_c, v_c, g_c))
+        h = _MlstmLayerLayout.apply(qk_c, v_c, g_c, NH, bool(reverse), bool(siging), int(chunk_size), float(eps), kdt,
+                                    float(cell.gate_soft_cap) if in_kernel_cap else 0.0)
     else:
+        capped = cell.gate_soft_cap * torch.tanh(if_preact / cell.gate_soft_cap)  # soft_cap, vision_lstm2.py:755-756
         i_pre, f_pre = torch.chunk(capped, 2, dim=-1)
         i, f = i_pre.transpose(-1, -2), f_pre.transpose(-1, -2)  # (B, NH, S) views
         qh, kh, vh = (t.view(B, S, NH, D).transpose(1, 2) for t in (q, k, v))  # (B, NH, S, D) views, no copy
