@@ -104,22 +104,33 @@ class ClockSampler:
                 "samples": len(self.sm)}
 
 
-def cpu_baseline(sample_b=4, reps=3):
-    """Oracle port (native-torch formulation) in fp32 on the host cores, on a bounded sample."""
+def _oracle_step(c, seed=0):
+    """Inputs + one fp32 fwd+bwd step of the reference's native-torch formulation (oracle port) on the host cores."""
     from oracle import mlstm_oracle as O
 
+    inp = O.make_inputs(c["B"], c["NH"], c["S"], c["DK"], c["DV"], seed=seed, dtype=torch.float32)
+
+    def step():
+        # the reference's custbw path: forward, then the hand-written backward with the saved n / m vectors
+        # (native/fwbw.py:34-171); no autograd graph is involved in either, grad mode is left on as in training
+        return O.fwbw(inp["q"], inp["k"], inp["v"], inp["i"], inp["f"], inp["dh"], chunk_size=c["L"])
+
+    return step
+
+
+def cpu_baseline(sample_b=8, reps=2):
+    """Oracle port (native-torch formulation) in fp32 on the host cores, on a bounded sample (rank 0, N = 1 only)."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     c = dict(CFG, B=sample_b)
-    inp = O.make_inputs(c["B"], c["NH"], c["S"], c["DK"], c["DV"], seed=0, dtype=torch.float32)
+    step = _oracle_step(c)
     best = float("inf")
-    with torch.no_grad():
-        for r in range(reps + 1):
-            t0 = time.perf_counter()
-            O.fwbw(inp["q"], inp["k"], inp["v"], inp["i"], inp["f"], inp["dh"], chunk_size=c["L"])
-            dt = time.perf_counter() - t0
-            if r:
-                best = min(best, dt)
+    for r in range(reps + 1):
+        t0 = time.perf_counter()
+        step()
+        dt = time.perf_counter() - t0
+        if r:
+            best = min(best, dt)
     ff, fb, _, _ = flops_and_bytes(c, 4)
     return {"value": (ff + fb) / best / 1e12, "unit": "TFLOP/s", "cores": cores, "kind": "port",
             "sample": f"fp32 fwd+bwd of B={sample_b} (of 32) NH=4 S=1600 DH=64 chunk=64, best of {reps}, {best * 1e3:.1f} ms",
@@ -127,36 +138,256 @@ def cpu_baseline(sample_b=4, reps=3):
 
 
 def run_reference(args, rank):
-    """--impl reference: the reference's CPU formulation (oracle port; the Python reference cannot
-    travel to the GPU box) on the host cores, same config / metric."""
+    """--impl reference: the reference's CPU formulation (oracle port; the Python reference cannot travel to the GPU
+    box) on all host cores, on the SAME configuration as the B200 arm: every step is the full B=32 fwd+bwd."""
     if rank != 0:
         return
-    from oracle import mlstm_oracle as O
-
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample_b = 4
-    c = dict(CFG, B=sample_b)
-    inp = O.make_inputs(c["B"], c["NH"], c["S"], c["DK"], c["DV"], seed=0, dtype=torch.float32)
+    c = dict(CFG)
+    step = _oracle_step(c)
     times = []
-    with torch.no_grad():
-        for s in range(args.warmup + args.steps):
-            t0 = time.perf_counter()
-            O.fwbw(inp["q"], inp["k"], inp["v"], inp["i"], inp["f"], inp["dh"], chunk_size=c["L"])
-            if s >= args.warmup:
-                times.append(time.perf_counter() - t0)
+    for s in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        step()
+        if s >= args.warmup:
+            times.append(time.perf_counter() - t0)
     ff, fb, _, _ = flops_and_bytes(c, 4)
     dt = sum(times) / len(times)
     val = (ff + fb) / dt / 1e12
-    sample = f"each step = fp32 fwd+bwd of B={sample_b} (of 32) NH=4 S=1600 DH=64 chunk=64 on host cores"
+    sample = "each step = the full configuration: fp32 fwd+bwd of B=32 NH=4 S=1600 DH=64 chunk=64 on the host cores"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "TFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
+        "config": {"workload": WORKLOAD, "per_gpu": True, "sample": sample, "same_config": True},
         "cpu_baseline": {"value": val, "unit": "TFLOP/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+# --------------------------------------------------------------------------------------------------------------
+# The calls a YOLO-ViL step makes (SURVEY.md section 3.1): 10 block pairs x 2 directions per forward pass, at four stage
+# resolutions; in training the two S = 6400 pairs are activation-checkpointed, so a step runs 24 forwards + 20
+# backwards.  S = 400 / 100 are what the fused layer path hands to the kernels (ragged last 128-token tile handled
+# in-kernel); the reference's pad wrapper would make them 448 / 128.
+MODEL_CALLS = {
+    "config3 640-base192 train, 64 img": dict(B=64, NH=12, D=32, train=True),
+    "config4 640-base256 train, 32 img per GPU": dict(B=32, NH=8, D=64, train=True),
+    "config5 640-base384 inference, 16 img per GPU": dict(B=16, NH=6, D=128, train=False),
+}
+STAGE_CALLS = ((6400, 4), (1600, 6), (400, 6), (100, 4))  # (S, calls per forward pass)
+
+
+def call_bytes(B, NH, S, D, itemsize=2):
+    tok = B * NH * S
+    fw = tok * (4 * D * itemsize + 2 * itemsize + 8)
+    bw = tok * (7 * D * itemsize + 4 * itemsize + 8)
+    return fw, bw
+
+
+def _graph_period(fn, reps, dev):
+    """Device time per call: `reps` back-to-back calls captured in one CUDA graph (launch latency amortised)."""
+    keep = []
+    side = torch.cuda.Stream(dev)
+    with torch.cuda.stream(side):
+        fn()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(reps):
+                keep.append(fn())
+    torch.cuda.synchronize()
+    g.replay()
+    ts = []
+    for _ in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        g.replay()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b) / reps)
+    del g, keep
+    return min(ts)
+
+
+def model_calls_block(pkg, dev, hbm_peak, flush):
+    """Every mLSTM call shape of BASELINE configs 3 / 4 / 5, timed on its own: device time of the kernels (graph of
+    back-to-back launches; the working set of the S >= 1600 calls exceeds the 126 MB L2) with the fraction of the measured
+    HBM peak their algorithmic bytes reach, and the wall time of one eager call through the registered drop-in
+    (autograd fwd+bwd, or the forward under no_grad for the inference config) with the L2 flushed between calls."""
+    out = {}
+    for name, c in MODEL_CALLS.items():
+        B, NH, D, train = c["B"], c["NH"], c["D"], c["train"]
+        rows, step_dev, step_eager = [], 0.0, 0.0
+        for S, n_fw in STAGE_CALLS:
+            g = torch.Generator(device=dev).manual_seed(S + D)
+            t = {k: (0.3 * torch.randn(B, NH, S, D, generator=g, device=dev)).to(torch.bfloat16) for k in ("q", "k", "v", "dh")}
+            t["i"] = torch.full((B, NH, S), -8.73, device=dev).to(torch.bfloat16)
+            t["f"] = (3.0 + 3.0 * torch.rand(B, NH, S, generator=g, device=dev)).to(torch.bfloat16)
+            L = 64 if S % 64 == 0 else 4
+            reps = 4 if S >= 1600 else 16
+            saved = pkg.mlstm_chunkwise_fw(t["q"], t["k"], t["v"], t["i"], t["f"], chunk_size=L, save_states=train)
+            fw_ms = _graph_period(lambda: pkg.mlstm_chunkwise_fw(t["q"], t["k"], t["v"], t["i"], t["f"], chunk_size=L,
+                                                                save_states=train), reps, dev)
+            fwb, bwb = call_bytes(B, NH, S, D)
+            row = {"S": S, "heads": B * NH, "d": D, "calls_fw": n_fw + (4 if (train and S == 6400) else 0), "fw_us": fw_ms * 1e3,
+                   "fw_gbs": fwb / fw_ms / 1e6, "fw_frac": fwb / fw_ms / 1e6 / hbm_peak}
+            if train:
+                bw_ms = _graph_period(lambda: pkg.mlstm_chunkwise_bw(t["q"], t["k"], t["v"], t["i"], t["f"], saved[1], saved[2],
+                                                                    t["dh"], chunk_size=L, c_states=saved[4]), reps, dev)
+                row.update(calls_bw=n_fw, bw_us=bw_ms * 1e3, bw_gbs=bwb / bw_ms / 1e6, bw_frac=bwb / bw_ms / 1e6 / hbm_peak)
+            # eager drop-in call (what the model pays per call when it is not launch-bound elsewhere)
+            leaves = {k: t[k].detach().requires_grad_(train) for k in ("q", "k", "v", "i", "f")}
+
+            def eager():
+                if train:
+                    h = pkg.mlstm_chunkwise__b200(**leaves, chunk_size=L)
+                    h.backward(t["dh"])
+                    for x in leaves.values():
+                        x.grad = None
+                else:
+                    with torch.no_grad():
+                        pkg.mlstm_chunkwise__b200(**leaves, chunk_size=L)
+
+            for _ in range(3):
+                eager()
+            ts = []
+            for _ in range(5):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                eager()
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            row["eager_dropin_us"] = statistics.median(ts) * 1e3
+            rows.append(row)
+            step_dev += row["calls_fw"] * row["fw_us"] + row.get("calls_bw", 0) * row.get("bw_us", 0.0)
+            del t, saved, leaves
+            torch.cuda.empty_cache()
+        out[name] = {"calls": rows, "mlstm_device_ms_per_step": step_dev / 1e3}
+    return out
+
+
+def bind_numa_near_gpu(local_rank):
+    """Pin this rank's threads and future host allocations (the pinned e2e buffers) to the NUMA node its GPU hangs off:
+    with all ranks on node 0 the 8-GPU e2e run was bound by one socket's memory / PCIe root (round-1 VERDICT).  Best
+    effort (sysfs + the raw set_mempolicy syscall; no libnuma in the image); returns what it did."""
+    try:
+        import ctypes
+
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local_rank]) if vis and vis.split(",")[local_rank].isdigit() else local_rank
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        bus = bus[-12:] if len(bus) > 12 else bus  # sysfs uses a 4-digit PCI domain
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return {"numa_node": None, "note": "single NUMA node / not reported"}
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.extend(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        mask = ctypes.c_ulong(1 << node)
+        rc = ctypes.CDLL(None, use_errno=True).syscall(238, 1, ctypes.byref(mask), 64)  # set_mempolicy(MPOL_PREFERRED)
+        return {"numa_node": node, "cpus": len(allowed), "mempolicy_rc": int(rc)}
+    except Exception as e:  # pragma: no cover
+        return {"numa_node": None, "note": repr(e)[:120]}
+
+
+def ddp_proxy_block(pkg, dist, dev, world, flush):
+    """N > 1: the data-parallel pattern of BASELINE config 4 around the hot path -- per rank the mLSTM call sequence of
+    one 640-base256 training step at 32 img per GPU (24 forwards + 20 backwards), and the gradient all-reduce DDP issues
+    for that model (187 MB fp32, 25 MB buckets: engine/trainer.py:277, torch DDP defaults) over NCCL, launched bucket by
+    bucket while the backward calls run.  Reports the three times (calls alone, all-reduce alone, overlapped) and which
+    one bounds the step: the op itself has no collective, this is the one around it."""
+    c = MODEL_CALLS["config4 640-base256 train, 32 img per GPU"]
+    B, NH, D = c["B"], c["NH"], c["D"]
+    ts = {}
+    for S, _ in STAGE_CALLS:
+        g = torch.Generator(device=dev).manual_seed(S)
+        t = {k: (0.3 * torch.randn(B, NH, S, D, generator=g, device=dev)).to(torch.bfloat16) for k in ("q", "k", "v", "dh")}
+        t["i"] = torch.full((B, NH, S), -8.73, device=dev).to(torch.bfloat16)
+        t["f"] = (3.0 + 3.0 * torch.rand(B, NH, S, generator=g, device=dev)).to(torch.bfloat16)
+        t["L"] = 64 if S % 64 == 0 else 4
+        ts[S] = t
+    n_bucket, bucket_elems = 8, (187 << 20) // 4 // 8
+    buckets = [torch.ones(bucket_elems, device=dev) for _ in range(n_bucket)]
+    comm = torch.cuda.Stream(dev)
+
+    def forward_calls():
+        saved = {}
+        for S, n in STAGE_CALLS:
+            t = ts[S]
+            for _ in range(n):
+                saved[S] = pkg.mlstm_chunkwise_fw(t["q"], t["k"], t["v"], t["i"], t["f"], chunk_size=t["L"])
+        return saved
+
+    def backward_calls(saved, with_comm):
+        k = 0
+        for S, n in reversed(STAGE_CALLS):
+            t = ts[S]
+            for j in range(n):
+                if S == 6400:  # checkpointed block pairs: the forward is recomputed inside the backward
+                    saved[S] = pkg.mlstm_chunkwise_fw(t["q"], t["k"], t["v"], t["i"], t["f"], chunk_size=t["L"])
+                pkg.mlstm_chunkwise_bw(t["q"], t["k"], t["v"], t["i"], t["f"], saved[S][1], saved[S][2], t["dh"],
+                                       chunk_size=t["L"], c_states=saved[S][4])
+                if with_comm and (j % 3 == 2 or j == n - 1) and k < n_bucket:  # a bucket fills every few layers
+                    comm.wait_stream(torch.cuda.current_stream(dev))
+                    with torch.cuda.stream(comm):
+                        dist.all_reduce(buckets[k])
+                    k += 1
+        if with_comm:
+            with torch.cuda.stream(comm):
+                for kk in range(k, n_bucket):
+                    dist.all_reduce(buckets[kk])
+            torch.cuda.current_stream(dev).wait_stream(comm)
+
+    def timed(fn, reps=3):
+        best = float("inf")
+        for _ in range(reps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+        return best
+
+    def calls_only():
+        backward_calls(forward_calls(), False)
+
+    def comm_only():
+        for x in buckets:
+            dist.all_reduce(x)
+
+    def overlapped():
+        backward_calls(forward_calls(), True)
+
+    for fn in (calls_only, comm_only, overlapped):
+        fn()
+    torch.cuda.synchronize()
+    from xlstm_yolo_clean_b200 import replicas
+
+    t_calls = replicas.max_over_ranks(timed(calls_only), dev)
+    t_comm = replicas.max_over_ranks(timed(comm_only), dev)
+    t_both = replicas.max_over_ranks(timed(overlapped), dev)
+    bus_gbs = 2 * (world - 1) / world * (187 << 20) / (t_comm * 1e-3) / 1e9
+    limiter = "mLSTM calls (the all-reduce hides behind them)" if t_both < 1.1 * t_calls else (
+        "gradient all-reduce" if t_comm > t_calls else "launch / stream serialisation of calls and all-reduce")
+    return {"workload": "640-base256 step per rank: 24 fw + 20 bw mLSTM calls (32 img per GPU) + all-reduce of 187 MB fp32 in 8 buckets",
+            "mlstm_calls_ms": t_calls, "allreduce_ms": t_comm, "overlapped_ms": t_both,
+            "allreduce_bus_gbs": bus_gbs, "overlap_efficiency": max(t_calls, t_comm) / t_both, "limiter": limiter,
+            "images_per_s_bound_by_this_path": world * B / (t_both * 1e-3)}
 
 
 def main():
@@ -167,6 +398,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--kernel-impl", default="auto", choices=["auto", "exact", "tensor"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-model-calls", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -333,9 +565,12 @@ def main():
     roof = {"bound": "hbm", "kernel": f"{dom[3]} (mlstm_b200_chunkwise_{dom[0]}, one launch per call)",
             "achieved": dom[1] / (dom[2] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": dom[1] / (dom[2] * 1e-3) / 1e9 / hbm_peak, "traffic": traffic,
-            "traffic_source": "profiles/r01_traffic.json (ncu --set full, same command)" if traffic else None,
+            "traffic_source": "static: committed ncu --set full capture of the same command (profiles/r01_traffic.json), not measured in this run" if traffic else None,
             "peak_kind": peak_kind,
             "algorithmic_bytes": dom[1], "fw_ms": fw_t, "bw_ms": bw_t,
+            # the saved per-tile states are extra traffic the kernels really move (written by fw, read by bw); they are NOT
+            # counted in the algorithmic bytes above ("no state materialisation")
+            "c_states_bytes_each_way": c["B"] * c["NH"] * ((c["S"] + 127) // 128) * c["DK"] * c["DV"] * 2,
             "timing": f"CUDA events around a graph of {REP * N_SETS} back-to-back launches of the one kernel over the rotating input sets, / {REP * N_SETS}",
             "fw_ms_single_launch_graph": fw_single, "bw_ms_single_launch_graph": bw_single,
             "fw_gbs": fw_bytes / (fw_t * 1e-3) / 1e9, "bw_gbs": bw_bytes / (bw_t * 1e-3) / 1e9,
@@ -344,6 +579,7 @@ def main():
 
     # ---- end to end through the public host-buffer API: pinned host tensors in, pinned host tensors out,
     #      H2D / kernels / D2H pipelined over batch slices (xlstm_yolo_clean_b200.HostFwBw) -----------
+    numa = bind_numa_near_gpu(local_rank)
     host = {k: v.cpu().pin_memory() for k, v in sets[0].items()}
     pipe = pkg.HostFwBw(c["B"], c["NH"], c["S"], c["DK"], c["DV"], dtype=dt, device=dev, n_slices=5, chunk_size=c["L"])
     host_out = pkg.HostFwBw.alloc_host(c["B"], c["NH"], c["S"], c["DK"], c["DV"], dtype=dt)
@@ -361,6 +597,66 @@ def main():
     e2e_val = replicas.sum_over_ranks(ff + fb, dev) / (e2e_ms * 1e-3) / 1e12
     e2e_check = float((host_out["h"].float() - keep[0][0][0].float().cpu()).abs().max())  # same inputs as set 0
 
+    # ---- the same step through the registered drop-in (autograd.Function, eager launches): what a model pays --------
+    leaves = [{k: st[k].detach().requires_grad_(True) for k in ("q", "k", "v", "i", "f")} for st in sets]
+
+    def dropin_step(r):
+        lv = leaves[r]
+        h = pkg.mlstm_chunkwise__b200(**lv, chunk_size=c["L"])
+        h.backward(sets[r]["dh"])
+        for x in lv.values():
+            x.grad = None
+
+    for w in range(8):
+        dropin_step(w % N_SETS)
+    torch.cuda.synchronize()
+    d_steps = max(8, min(args.steps, 100))
+    e0.record()
+    for k in range(d_steps):
+        dropin_step(k % N_SETS)
+    e1.record()
+    sync_all()
+    dropin_ms = replicas.max_over_ranks(e0.elapsed_time(e1), dev) / d_steps
+    t0 = time.perf_counter()
+    for k in range(200):
+        dropin_step(k % N_SETS)
+    host_us = (time.perf_counter() - t0) / 200 * 1e6  # (the GPU queue may throttle this when the host is faster)
+    torch.cuda.synchronize()
+    dropin = {"api": "mlstm_chunkwise__b200 (registered drop-in) + autograd backward, eager launches, rotating input sets",
+              "ms_per_step": dropin_ms, "value": replicas.sum_over_ranks(ff + fb, dev) / (dropin_ms * 1e-3) / 1e12,
+              "unit": "TFLOP/s", "host_us_per_step": host_us}
+    # the same autograd step captured in a CUDA graph (forward AND backward through the autograd.Function): the
+    # launch-bound part of the eager number is PyTorch's autograd engine, not the C-ABI call
+    try:
+        gd = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            for r in range(N_SETS):
+                dropin_step(r)
+            with torch.cuda.graph(gd, stream=side):
+                for r in range(N_SETS):
+                    dropin_step(r)
+        torch.cuda.synchronize()
+        gd.replay()
+        sync_all()
+        e0.record()
+        for _ in range(max(2, d_steps // N_SETS)):
+            gd.replay()
+        e1.record()
+        sync_all()
+        g_ms = replicas.max_over_ranks(e0.elapsed_time(e1), dev) / (max(2, d_steps // N_SETS) * N_SETS)
+        dropin["graph_captured_ms_per_step"] = g_ms
+        dropin["graph_captured_value"] = replicas.sum_over_ranks(ff + fb, dev) / (g_ms * 1e-3) / 1e12
+    except Exception as e:  # pragma: no cover
+        dropin["graph_capture_error"] = repr(e)[:200]
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    calls = None
+    if world == 1 and not args.no_model_calls:
+        calls = model_calls_block(pkg, dev, hbm_peak, flush)
+    proxy = None
+    if world > 1:
+        proxy = ddp_proxy_block(pkg, dist, dev, world, flush)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,
@@ -375,8 +671,16 @@ def main():
                     "steps": e_steps, "ms_per_step": e2e_ms, "api": "HostFwBw.run (pinned host in/out, 5 tapered batch slices on 3 streams, replayed as one CUDA graph)",
                     "max_abs_diff_vs_device_path": e2e_check},
             "roofline": roof,
+            "dropin": dropin,
         }
-        if not args.no_cpu_baseline:
+        line["e2e"]["numa"] = numa
+        line["e2e"]["note"] = ("PCIe-bound: %.0f MB in + %.0f MB out per step; every rank's pinned buffers sit on its GPU's NUMA node "
+                               "when the platform reports one" % (h2d / 1e6, d2h / 1e6))
+        if calls is not None:
+            line["model_calls"] = calls
+        if proxy is not None:
+            line["ddp_proxy"] = proxy
+        if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only (at N > 1 the other ranks would spin in a barrier)
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line))
     if world > 1:

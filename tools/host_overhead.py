@@ -59,4 +59,4 @@ for _ in range(1000):
     fwbw()
 pr.disable()
 torch.cuda.synchronize()
-pstats.Stats(pr).sort_stats("tottime").print_stats(14)
+pstats.Stats(pr).sort_stats("tottime").print_stats(30)
