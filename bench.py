@@ -390,6 +390,46 @@ def ddp_proxy_block(pkg, dist, dev, world, flush):
             "images_per_s_bound_by_this_path": world * B / (t_both * 1e-3)}
 
 
+def model_train_block(pkg, dist, dev, rank, world, steps=3, warmup=2):
+    """The second half of BASELINE.json's metric -- 640-base256 training img/s -- through the reference's OWN model:
+    the unmodified YOLO-ViL DetectionModel staged under baseline/_ref (git-ignored; it travels to the GPU box with the
+    snapshot), patched with patch_model(fused=True), 32 synthetic 640x640 images per GPU, fp16 AMP, SGD step, DDP with
+    NCCL gradient all-reduce when N > 1 (engine/trainer.py:221-232, 277, 382-392).  At N = 1 the same model with the
+    reference's native-torch kernels on the GPU is timed beside it.  Absent reference -> {"unavailable": ...}."""
+    import contextlib
+    import types
+
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        import model_bench as MB
+
+        if not os.path.isdir(os.path.join(MB.REF, "mlstm_kernels")):
+            return {"unavailable": "baseline/_ref is not staged (tools/stage_reference.sh)"}
+        out = {"model": "640-base256.yaml (DetectionModel, 80 classes)", "img_per_gpu": 32, "amp": "fp16", "n_gpus": world,
+               "step": "autocast fwd + loss, GradScaler backward (DDP all-reduce at N > 1), clip 10, SGD step; synthetic batch"}
+        args = types.SimpleNamespace(yaml="640-base256.yaml", batch=32, steps=steps, warmup=warmup, check_finite=False, profile=False)
+        with contextlib.redirect_stdout(sys.stderr):
+            MB._import_reference()
+            for name in (["b200_fused"] + (["reference_native_custbw_on_gpu"] if world == 1 else [])):
+                model = MB._build_model(args.yaml, dev)
+                if name == "b200_fused":
+                    pkg.patch_model(model, fused=True)  # siging derived from the model's own CUDA backend
+                else:
+                    MB._set_backend(model, "native_custbw")
+                res = MB._train_loop(model, MB._batch(32, dev, seed=rank), args, world, dev)
+                ms = res["ms_per_step"]
+                if world > 1:
+                    t = torch.tensor([ms], device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    ms = float(t)
+                out[name] = {"ms_per_step": ms, "img_per_s": world * 32 / (ms * 1e-3), "peak_mem_gb": res["peak_mem_gb"]}
+                del model
+                torch.cuda.empty_cache()
+        return out
+    except Exception as e:  # the block must never break the JSON line
+        return {"error": repr(e)[:300]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -399,6 +439,7 @@ def main():
     ap.add_argument("--kernel-impl", default="auto", choices=["auto", "exact", "tensor"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-model-calls", action="store_true")
+    ap.add_argument("--no-model-train", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -656,6 +697,10 @@ def main():
     proxy = None
     if world > 1:
         proxy = ddp_proxy_block(pkg, dist, dev, world, flush)
+    del flush
+    mtrain = None
+    if not args.no_model_train:
+        mtrain = model_train_block(pkg, dist, dev, rank, world)
 
     if rank == 0:
         line = {
@@ -680,6 +725,8 @@ def main():
             line["model_calls"] = calls
         if proxy is not None:
             line["ddp_proxy"] = proxy
+        if mtrain is not None:
+            line["model_train"] = mtrain
         if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only (at N > 1 the other ranks would spin in a barrier)
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line))

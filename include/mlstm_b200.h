@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define MLSTM_B200_ABI_VERSION 2
+#define MLSTM_B200_ABI_VERSION 3
 
 /* element types of q/k/v/i/f/h and of the gradients */
 enum { MLSTM_B200_F32 = 0, MLSTM_B200_BF16 = 1, MLSTM_B200_F16 = 2 };
@@ -86,6 +86,28 @@ typedef struct mlstm_b200_shape {
   int32_t reserved;   /* must be 0 */
 } mlstm_b200_shape;
 
+/* Optional fused cell-output epilogue of the forward: instead of (or in addition to) h the
+ * kernel writes
+ *     y[b,hd,s,d] = (h - mean) * rstd * weight[c] + bias[c] + skip[c] * x[b,hd,s,d],   c = hd * DHHV + d
+ * with mean / rstd over the DHHV elements of one (token, head) row of h rounded to the kernel dtype (biased variance,
+ * rstd = (var + eps)^-1/2) -- MultiHeadLayerNorm (vision_lstm2.py:928-944) on the cell's output, ViLLayer's learnable
+ * skip (vision_lstm2.py:306) and, through y's strides, the (B, NH, S, D) -> (B, S, NH*D) relayout (vision_lstm2.py:749-751)
+ * -- from the registers that hold the row in the epilogue anyway: in inference h never reaches HBM un-normalised; in
+ * training h is still written (fw_args.h) because the LayerNorm backward needs it (mlstm_b200_cellout_bw).
+ * y and x are (B, NH, S, DHHV) views given by element strides, innermost stride 1, 16-byte aligned with strides that are
+ * multiples of 8 elements (y goes out through a TMA tensor map); both are 16-bit, of dtype xy_dtype (BF16 or F16), which
+ * may differ from shape.dtype (bf16 kernel under fp16 autocast).  weight / bias / skip: contiguous fp32 (NH*DHHV), each
+ * may be NULL (1 / 0 / 0); x.ptr may be NULL.  Tensor-core route only. */
+typedef struct mlstm_b200_fw_epilogue {
+  mlstm_b200_tensor y; /* out */
+  mlstm_b200_tensor x; /* optional skip input */
+  const float* weight;
+  const float* bias;
+  const float* skip;
+  float eps;
+  int32_t xy_dtype;
+} mlstm_b200_fw_epilogue;
+
 typedef struct mlstm_b200_fw_args {
   mlstm_b200_shape shape;
   /* inputs */
@@ -104,6 +126,7 @@ typedef struct mlstm_b200_fw_args {
                              bytes (the reference's return_all_states mode, native/fwbw.py:73-101) */
   void* workspace;
   size_t workspace_bytes;
+  const mlstm_b200_fw_epilogue* epilogue; /* optional; with it h.ptr may be NULL (no un-normalised h is written) */
 } mlstm_b200_fw_args;
 
 typedef struct mlstm_b200_bw_args {

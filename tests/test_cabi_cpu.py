@@ -36,7 +36,7 @@ def test_exports_match_header(lib):
 
 
 def test_abi_version_and_error_string(lib):
-    assert lib.mlstm_b200_abi_version() == 2
+    assert lib.mlstm_b200_abi_version() == 3
     assert isinstance(lib.mlstm_b200_last_error(), bytes)
 
 
@@ -47,10 +47,10 @@ def test_struct_sizes_match_header(lib):
 
     from xlstm_yolo_clean_b200 import _cabi
 
-    code = '#include <stdio.h>\n#include "mlstm_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
+    code = '#include <stdio.h>\n#include "mlstm_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
            "sizeof(mlstm_b200_tensor),sizeof(mlstm_b200_shape),sizeof(mlstm_b200_fw_args),sizeof(mlstm_b200_bw_args)," \
            "sizeof(mlstm_b200_cellout_args),sizeof(mlstm_b200_cellout_bw_args)," \
-           "sizeof(mlstm_b200_rmsnorm_args),sizeof(mlstm_b200_rmsnorm_bw_args),sizeof(mlstm_b200_recurrent_args));}"
+           "sizeof(mlstm_b200_rmsnorm_args),sizeof(mlstm_b200_rmsnorm_bw_args),sizeof(mlstm_b200_recurrent_args),sizeof(mlstm_b200_fw_epilogue));}"
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
         open(c, "w").write(code)
@@ -59,7 +59,7 @@ def test_struct_sizes_match_header(lib):
     sizes = [int(x) for x in out]
     assert sizes == [ctypes.sizeof(_cabi.Tensor), ctypes.sizeof(_cabi.Shape), ctypes.sizeof(_cabi.FwArgs),
                      ctypes.sizeof(_cabi.BwArgs), ctypes.sizeof(_cabi.CellOutArgs), ctypes.sizeof(_cabi.CellOutBwArgs),
-                     ctypes.sizeof(_cabi.RmsNormArgs), ctypes.sizeof(_cabi.RmsNormBwArgs), ctypes.sizeof(_cabi.RecurrentArgs)]
+                     ctypes.sizeof(_cabi.RmsNormArgs), ctypes.sizeof(_cabi.RmsNormBwArgs), ctypes.sizeof(_cabi.RecurrentArgs), ctypes.sizeof(_cabi.FwEpilogue)]
 
 
 def test_workspace_query_needs_no_gpu(lib):

@@ -1,8 +1,9 @@
 #!/bin/sh
 # Stage the UNMODIFIED reference (its two Python packages and the three model YAMLs) under the git-ignored
-# baseline/_ref/ so that tools/model_bench.py can run the reference's own model and its own CUDA (Triton)
-# kernels on the GPU box next to the B200 backend.  gpurun ships baseline/_ref with the snapshot; git never
-# sees it (.gitignore).  Nothing in tests/, bench.py or smoke() reads it.
+# baseline/_ref/ so that the reference's own model and wrappers can run on the GPU box next to the B200 backend
+# (tools/model_bench.py, the wrapper / model tests in tests/test_recurrent_and_wrappers_gpu.py, bench.py's
+# model_train block).  gpurun ships baseline/_ref with the snapshot; git never sees it (.gitignore).  Everything that
+# reads it skips or reports "unavailable" when it is absent; the product never imports it.
 set -e
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
 SRC="${1:-/root/reference}"

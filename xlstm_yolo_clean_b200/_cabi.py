@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmlstm_b200.so")
 
 F32, BF16, F16 = 0, 1, 2
 IMPL_AUTO, IMPL_EXACT, IMPL_TENSOR = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EXPORTS = (
     "mlstm_b200_abi_version",
@@ -46,6 +46,14 @@ class Shape(C.Structure):
     ]
 
 
+class FwEpilogue(C.Structure):
+    _fields_ = [
+        ("y", Tensor), ("x", Tensor),
+        ("weight", C.c_void_p), ("bias", C.c_void_p), ("skip", C.c_void_p),
+        ("eps", C.c_float), ("xy_dtype", C.c_int32),
+    ]
+
+
 class FwArgs(C.Structure):
     _fields_ = [
         ("shape", Shape),
@@ -56,6 +64,7 @@ class FwArgs(C.Structure):
         ("c_last", C.c_void_p), ("n_last", C.c_void_p), ("m_last", C.c_void_p),
         ("c_states", C.c_void_p),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("epilogue", C.POINTER(FwEpilogue)),
     ]
 
 

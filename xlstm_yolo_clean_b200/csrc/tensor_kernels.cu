@@ -334,6 +334,75 @@ __device__ __noinline__ void gate_scan_regs(float* gb, const GateRaw<T>& r, bool
   if ((lane & 7) == 0) gb[GateBuf::oScal + 4 + (lane >> 3)] = umax;
 }
 
+// 16-bit <-> fp32 with the element type chosen at run time (the fused epilogue's x / y may be fp16 under a bf16 kernel)
+__device__ __forceinline__ float2 unpack2_rt(uint32_t u, bool f16) {
+  return f16 ? __half22float2(*reinterpret_cast<__half2*>(&u)) : __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+}
+__device__ __forceinline__ uint32_t pack2_rt(float a, float b, bool f16) {
+  return f16 ? pack2<__half>(a, b) : pack2<__nv_bfloat16>(a, b);
+}
+
+// Fused cell-output epilogue for one thread's slice of a staged h tile: row `row`, NC columns from `col0` of a
+// [128][64]-subtiled (D = 128) or plain (D = 64 / 32) swizzled tile that already holds h rounded to the kernel dtype T.
+// The two threads that share a row (column halves, warps w and w + 4) exchange partial sums through `sstat` and a
+// 64-thread named barrier: mean first, then the centred sum of squares (two-pass variance like the stand-alone
+// kernel).  The slice is then overwritten in place with y = (h - mean) rstd w + b + skip x in the y dtype.
+template <typename T, int D, int NC, typename SwzFn>
+__device__ __forceinline__ void ln_epilogue_slice(uint8_t* tile_slice_base, SwzFn swz, int row, int col0, int ch, int pair_bar,
+                                                  float* sstat, const float* spar, const void* xrow, bool xy_f16, float ln_eps,
+                                                  bool row_valid) {
+  // spar: [3][D] = weight, bias, skip of this head; sstat: [2][LT] partial sums by column half
+  float s1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < NC / 8; ++j) {
+    const uint4 u = *reinterpret_cast<const uint4*>(tile_slice_base + swz(row, col0 + 8 * j));
+    const float2 a0 = unpack2<T>(u.x), a1 = unpack2<T>(u.y), a2 = unpack2<T>(u.z), a3 = unpack2<T>(u.w);
+    s1 += ((a0.x + a0.y) + (a1.x + a1.y)) + ((a2.x + a2.y) + (a3.x + a3.y));
+  }
+  sstat[ch * LT + row] = s1;
+  named_sync(pair_bar, 64);
+  const float mean = (sstat[row] + sstat[LT + row]) * (1.f / D);
+  float s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < NC / 8; ++j) {
+    const uint4 u = *reinterpret_cast<const uint4*>(tile_slice_base + swz(row, col0 + 8 * j));
+    const float2 a0 = unpack2<T>(u.x), a1 = unpack2<T>(u.y), a2 = unpack2<T>(u.z), a3 = unpack2<T>(u.w);
+    const float d0 = a0.x - mean, d1 = a0.y - mean, d2 = a1.x - mean, d3 = a1.y - mean, d4 = a2.x - mean, d5 = a2.y - mean,
+                d6 = a3.x - mean, d7 = a3.y - mean;
+    s2 += ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3)) + ((d4 * d4 + d5 * d5) + (d6 * d6 + d7 * d7));
+  }
+  named_sync(pair_bar, 64);  // both threads have read the means' partial sums
+  sstat[2 * LT + ch * LT + row] = s2;
+  named_sync(pair_bar, 64);
+  const float rstd = rsqrtf((sstat[2 * LT + row] + sstat[3 * LT + row]) * (1.f / D) + ln_eps);
+  const uint4* xp = reinterpret_cast<const uint4*>(xrow);
+#pragma unroll
+  for (int j = 0; j < NC / 8; ++j) {
+    uint4* slot = reinterpret_cast<uint4*>(tile_slice_base + swz(row, col0 + 8 * j));
+    const uint4 u = *slot;
+    const float2 a[4] = {unpack2<T>(u.x), unpack2<T>(u.y), unpack2<T>(u.z), unpack2<T>(u.w)};
+    float xv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (xp && row_valid) {
+      const uint4 xu = xp[j];
+      const float2 x0 = unpack2_rt(xu.x, xy_f16), x1 = unpack2_rt(xu.y, xy_f16), x2 = unpack2_rt(xu.z, xy_f16), x3 = unpack2_rt(xu.w, xy_f16);
+      xv[0] = x0.x; xv[1] = x0.y; xv[2] = x1.x; xv[3] = x1.y; xv[4] = x2.x; xv[5] = x2.y; xv[6] = x3.x; xv[7] = x3.y;
+    }
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int c = col0 + 8 * j + e;
+      const float hv = (e & 1) ? a[e >> 1].y : a[e >> 1].x;
+      o[e] = (hv - mean) * rstd * spar[c] + spar[D + c] + spar[2 * D + c] * xv[e];
+    }
+    uint4 w;
+    w.x = pack2_rt(o[0], o[1], xy_f16);
+    w.y = pack2_rt(o[2], o[3], xy_f16);
+    w.z = pack2_rt(o[4], o[5], xy_f16);
+    w.w = pack2_rt(o[6], o[7], xy_f16);
+    *slot = w;
+  }
+}
+
 // =============================================================================================
 // Forward
 // =============================================================================================
@@ -349,6 +418,16 @@ struct TcFwParams {
   int sig;           // 1: sigmoid input gate, all max states are 0 (siging variant)
   int store_states;  // 1: TMA-store the bf16 copy of C entering every tile (consumed by the backward)
   float cap;         // > 0: gate soft cap applied in the scan warp (mlstm_b200_shape::gate_soft_cap)
+  // fused cell-output epilogue (mlstm_b200_fw_epilogue): the tensor map "mapH" then describes y; the plain h (if wanted)
+  // is written straight from the registers
+  int epi;           // 1: fused epilogue on
+  int xy_f16;        // y / x element type: 1 fp16, 0 bf16
+  float ln_eps;
+  const float *ln_w, *ln_b, *ln_skip;  // (NH * D) fp32, each may be NULL
+  const void* x;     // skip input, (B, NH, S, D) view, or NULL
+  int64_t x_sb, x_sh, x_ss;
+  void* h_plain;     // un-normalised h (kernel dtype), (B, NH, S, D) view, or NULL
+  int64_t h_sb, h_sh, h_ss;
 #ifdef MLSTM_TC_PROFILE
   long long* prof;   // per-tile phase clocks of CTA 0 (profile build only)
 #endif
@@ -371,8 +450,9 @@ struct FwSmem {
   static constexpr int oNt = oC + Lay<D>::kState;    // second N block of that operand: column 0 = bf16 copy of n
   static constexpr int oOnes = oNt + Lay<D>::kState; // [8][128] ones, K-major: B operand of dn = Kbar^T 1
   static constexpr int oSmall = oOnes + 2048;
-  // floats: gates[2], srs[2][2][LT]
-  static constexpr int fGates = 0, fRs = 2 * GateBuf::kFloats, kSmallFloats = fRs + 4 * LT;
+  // floats: gates[2], srs[2][2][LT], fused epilogue: stat[4][LT] (row partial sums), par[3][D] (weight, bias, skip)
+  static constexpr int fGates = 0, fRs = 2 * GateBuf::kFloats, fStat = fRs + 4 * LT, fPar = fStat + 4 * LT,
+                       kSmallFloats = fPar + 3 * D;
   static constexpr int kBytes = oSmall + kSmallFloats * 4 + 1024 /*alignment slack*/;
   // TMEM columns.  D = 64: S double-buffered by tile parity (512 columns, one CTA per SM).  D = 32: one S
   // buffer, 256 columns, so that two CTAs share an SM (S(k+1) is issued behind the MMAs that read P(k)).
@@ -473,6 +553,14 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
     {
       const uint32_t one2 = pack2<T>(1.f, 1.f);
       for (int e = tid; e < 2048 / 16; e += kWorkers) reinterpret_cast<uint4*>(sOnes)[e] = make_uint4(one2, one2, one2, one2);
+    }
+    if (p.epi) {  // per-channel parameters of the fused cell-output epilogue for this head
+      float* spar = fsm + SM::fPar;
+      for (int e = tid; e < D; e += kWorkers) {
+        spar[e] = p.ln_w ? p.ln_w[hh * D + e] : 1.f;
+        spar[D + e] = p.ln_b ? p.ln_b[hh * D + e] : 0.f;
+        spar[2 * D + e] = p.ln_skip ? p.ln_skip[hh * D + e] : 0.f;
+      }
     }
     named_sync(NB_PAIR0, kWorkers);  // sNt zeroed before the owners write column 0
     if (owns_c && ch == 0) {
@@ -728,10 +816,24 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
         float o[CW];
 #pragma unroll
         for (int j = 0; j < CW; ++j) o[j] = (__uint_as_float(hi[j]) + bq * __uint_as_float(hx[j])) * inv;  // fw.py:200-212
-        store_cols<T, D>(sH + (SM::kHBuf == 2 ? (c & 1) * SM::kTile : 0), row, ch * CW, o);
+        uint8_t* sHc = sH + (SM::kHBuf == 2 ? (c & 1) * SM::kTile : 0);
+        store_cols<T, D>(sHc, row, ch * CW, o);
         if (ch == 0 && row < n_valid) {
           p.n_out[(int64_t)bh * p.S + t0 + row] = nmax;
           p.m_out[(int64_t)bh * p.S + t0 + row] = m_t;
+        }
+        if (p.epi) {
+          // fused cell output (mlstm_b200_fw_epilogue): the un-normalised row goes out from the staged copy (training:
+          // the LayerNorm backward needs it), then the staged slice becomes y = LN(h) w + b + skip x
+          const int64_t tok = (int64_t)(t0 + row);
+          if (p.h_plain && row < n_valid) {
+            uint4* dst = reinterpret_cast<uint4*>((T*)p.h_plain + b * p.h_sb + hh * p.h_sh + tok * p.h_ss + ch * CW);
+#pragma unroll
+            for (int j = 0; j < CW / 8; ++j) dst[j] = *reinterpret_cast<const uint4*>(sHc + L::swz(row, ch * CW + 8 * j));
+          }
+          const void* xrow = p.x ? (const void*)((const uint16_t*)p.x + b * p.x_sb + hh * p.x_sh + tok * p.x_ss + ch * CW) : nullptr;
+          ln_epilogue_slice<T, D, CW>(sHc, [](int r, int cc) { return L::swz(r, cc); }, row, ch * CW, ch, NB_PAIR0 + rb,
+                                      fsm + SM::fStat, fsm + SM::fPar, xrow, p.xy_f16 != 0, p.ln_eps, row < n_valid);
         }
       }
       // ---- state update C_k = gbar C_{k-1} + dC; n_k ---------------------------------------------------
