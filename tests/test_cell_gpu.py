@@ -332,3 +332,44 @@ def test_branch_matches_reference_vil_layer_golden(pkg, tag):
     assert ey < 1e-4 and ex < 1e-3, (ey, ex)
     ey16, _ = run(True)
     assert ey16 < 2e-2, ey16
+
+
+@pytest.mark.parametrize("kdt,odt", [(torch.bfloat16, torch.float16), (torch.float16, torch.float16), (torch.bfloat16, torch.bfloat16)],
+                         ids=["bf16_kernel_fp16_out", "fp16", "bf16"])
+@pytest.mark.parametrize("NH,D,S", [(4, 64, 384), (12, 32, 200), (3, 128, 256), (8, 64, 100)])
+@pytest.mark.parametrize("reverse", [False, True], ids=["causal", "anticausal"])
+def test_fused_forward_epilogue_equals_kernel_plus_cell_out(pkg, NH, D, S, reverse, kdt, odt):
+    """mlstm_b200_fw_epilogue: MultiHeadLayerNorm + relayout + learnable skip inside the
+    forward kernel's epilogue.  The un-normalised h it can still write is bit-identical to the plain forward's, and y equals
+    the stand-alone cell-output kernel applied to that h (itself pinned to a float64 group_norm above) up to one rounding
+    of the output dtype; without want_h no h is written at all."""
+    from xlstm_yolo_clean_b200 import backend
+
+    B, H = 2, NH * D
+    g = torch.Generator().manual_seed(S + D)
+    dev = torch.device("cuda:0")
+    qk = torch.randn(B, S, 2 * H, generator=g).to(kdt).to(dev)
+    v = torch.randn(B, S, H, generator=g).to(kdt).to(dev)
+    gates = torch.cat([torch.randn(B, S, NH, generator=g), 3 + torch.randn(B, S, NH, generator=g)], -1).to(kdt).to(dev)
+    x = torch.randn(B, S, H, generator=g).to(odt).to(dev)
+    w = (1 + 0.1 * torch.randn(H, generator=g)).to(dev)
+    b = (0.1 * torch.randn(H, generator=g)).to(dev)
+    sk = torch.randn(H, generator=g).to(dev)
+    q, k, vv, i, f = pkg.vil._heads(qk, v, gates, NH)
+    L = 4
+    h0 = pkg.mlstm_chunkwise_fw(q, k, vv, i, f, chunk_size=L, reverse=reverse)[0]
+    heads = lambda t: t.view(B, S, NH, D).transpose(1, 2)  # noqa: E731
+    y = torch.empty(B, S, H, dtype=odt, device=dev)
+    epi = backend.FwEpilogue(heads(y), heads(x), w, b, sk, 1e-5, True)
+    h1 = backend._fw_launch(q, k, vv, i, f, None, None, None, None, False, L, 1e-6, None, True, reverse, False, 0.0, epi)[0]
+    torch.cuda.synchronize()
+    assert torch.equal(h1, h0)
+    want = pkg.cell_out(h0, w, b, sk, x, eps=1e-5, out_dtype=odt)
+    assert rel(y, want) < (2e-3 if odt == torch.float16 else 1.2e-2)
+    # inference flavour: no skip input, no bias, h not written
+    y2 = torch.empty(B, S, H, dtype=odt, device=dev)
+    epi2 = backend.FwEpilogue(heads(y2), None, w, None, None, 1e-5, False)
+    h2 = backend._fw_launch(q, k, vv, i, f, None, None, None, None, False, L, 1e-6, None, False, reverse, False, 0.0, epi2)[0]
+    torch.cuda.synchronize()
+    assert h2 is None
+    assert rel(y2, pkg.cell_out(h0, w, None, None, None, eps=1e-5, out_dtype=odt)) < (2e-3 if odt == torch.float16 else 1.2e-2)

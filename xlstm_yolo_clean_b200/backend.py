@@ -156,7 +156,18 @@ def _fix_views(tensor_route: bool, ts):
 
 
 class _FwPlan:
-    __slots__ = ("args", "ref", "ws_bytes", "st_bytes", "tensor_route", "h_shape", "nm_shape", "states")
+    __slots__ = ("args", "ref", "ws_bytes", "st_bytes", "tensor_route", "h_shape", "nm_shape", "states", "epi")
+
+
+class FwEpilogue:
+    """Arguments of the fused cell-output epilogue (include/mlstm_b200.h, mlstm_b200_fw_epilogue): ``y`` (out) and ``x``
+    (optional skip input) are (B, NH, S, D) VIEWS of 16-bit tensors (e.g. of a (B, S, NH*D) buffer), ``weight`` / ``bias`` /
+    ``skip`` contiguous fp32 (NH*D) or None; ``want_h``: also write the un-normalised h (training)."""
+
+    __slots__ = ("y", "x", "weight", "bias", "skip", "eps", "want_h")
+
+    def __init__(self, y, x, weight, bias, skip, eps, want_h):
+        self.y, self.x, self.weight, self.bias, self.skip, self.eps, self.want_h = y, x, weight, bias, skip, float(eps), bool(want_h)
 
 
 class _BwPlan:
@@ -178,8 +189,9 @@ def _ws_tensor(nbytes: int, dev):
 
 
 def _fw_launch(q, k, v, i, f, c0, n0, m0, qk_scale, return_last_states, chunk_size, eps, impl, save_states, reverse, siging,
-               soft_cap=0.0):
-    """Returns h, nm (2, B, NH, S) fp32 = [n_out, m_out], last-or-None, c_states-or-None."""
+               soft_cap=0.0, epi: Optional[FwEpilogue] = None):
+    """Returns h, nm (2, B, NH, S) fp32 = [n_out, m_out], last-or-None, c_states-or-None.  With ``epi`` the kernel writes
+    epi.y (fused LayerNorm + skip epilogue) and h is None unless epi.want_h."""
     impl = _default_impl if impl is None else impl
     dt = q.dtype
     if i.dtype is not dt:
@@ -192,7 +204,9 @@ def _fw_launch(q, k, v, i, f, c0, n0, m0, qk_scale, return_last_states, chunk_si
         v = v.to(dt)
     dev = q.device
     key = (0, q.shape, v.shape[3], dt, q.stride(), k.stride(), v.stride(), i.stride(), f.stride(), chunk_size, eps, impl,
-           qk_scale, reverse, siging, c0 is not None, return_last_states, save_states, dev.index, soft_cap)
+           qk_scale, reverse, siging, c0 is not None, return_last_states, save_states, dev.index, soft_cap,
+           None if epi is None else (epi.y.stride(), epi.y.dtype, None if epi.x is None else epi.x.stride(), epi.want_h,
+                                     epi.weight is None, epi.bias is None, epi.skip is None, epi.eps))
     plans = _plans()
     plan = plans.get(key)
     lib = _cabi.load_library()
@@ -209,7 +223,7 @@ def _fw_launch(q, k, v, i, f, c0, n0, m0, qk_scale, return_last_states, chunk_si
         fixed = _fix_views(plan.tensor_route, (q, k, v))
         if any(x is not y for x, y in zip(fixed, (q, k, v))):  # a signature that needs copies: plan on the copies
             return _fw_launch(*fixed, i, f, c0, n0, m0, qk_scale, return_last_states, chunk_size, eps, impl, save_states,
-                              reverse, siging, soft_cap)
+                              reverse, siging, soft_cap, epi)
         plan.ws_bytes = lib.mlstm_b200_workspace_bytes(C.byref(a.shape), 0)
         plan.st_bytes = lib.mlstm_b200_states_bytes(C.byref(a.shape)) if save_states else 0
         plan.h_shape, plan.nm_shape = (B, NH, S, v.shape[3]), (2, B, NH, S)
@@ -218,6 +232,21 @@ def _fw_launch(q, k, v, i, f, c0, n0, m0, qk_scale, return_last_states, chunk_si
             getattr(a, name).stride[:t.dim()] = t.stride()
         a.h.stride[:4] = (NH * S * v.shape[3], S * v.shape[3], v.shape[3], 1)
         a.workspace_bytes = max(plan.ws_bytes, 256)
+        plan.epi = None
+        if epi is not None:
+            if not plan.tensor_route:
+                raise RuntimeError("the fused cell-output epilogue exists on the tensor-core route only")
+            assert epi.y.shape == plan.h_shape and epi.y.dtype in (torch.float16, torch.bfloat16)
+            assert epi.x is None or (epi.x.shape == plan.h_shape and epi.x.dtype == epi.y.dtype)
+            if not _tma_strides_ok(epi.y) or (epi.x is not None and not _tma_strides_ok(epi.x)):
+                raise RuntimeError("fused epilogue: y / x need a unit innermost stride and 16-byte-multiple strides")
+            e = _cabi.FwEpilogue()
+            e.y.stride[:4] = epi.y.stride()
+            if epi.x is not None:
+                e.x.stride[:4] = epi.x.stride()
+            e.eps, e.xy_dtype = epi.eps, _DTYPES[epi.y.dtype]
+            plan.epi = e
+            a.epilogue = C.pointer(e)
         plan.args, plan.ref = a, C.byref(a)
         plans[key] = plan
     elif plan.tensor_route and (q.data_ptr() | k.data_ptr() | v.data_ptr()) & 15:  # offset views of this signature
@@ -226,8 +255,8 @@ def _fw_launch(q, k, v, i, f, c0, n0, m0, qk_scale, return_last_states, chunk_si
     if torch._C._cuda_getDevice() != dev.index:
         with torch.cuda.device(dev):
             return _fw_launch(q, k, v, i, f, c0, n0, m0, qk_scale, return_last_states, chunk_size, eps, impl, save_states,
-                              reverse, siging, soft_cap)
-    h = torch.empty(plan.h_shape, dtype=dt, device=dev)
+                              reverse, siging, soft_cap, epi)
+    h = torch.empty(plan.h_shape, dtype=dt, device=dev) if (epi is None or epi.want_h) else None
     nm = torch.empty(plan.nm_shape, dtype=torch.float32, device=dev)
     c_states = torch.empty(plan.st_bytes, dtype=torch.uint8, device=dev) if plan.st_bytes else None
     ws = _ws_tensor(plan.ws_bytes, dev)
@@ -243,8 +272,17 @@ def _fw_launch(q, k, v, i, f, c0, n0, m0, qk_scale, return_last_states, chunk_si
         last = (torch.empty(sc, dtype=torch.float32, device=dev), torch.empty(sn, dtype=torch.float32, device=dev),
                 torch.empty(sm + (1,), dtype=torch.float32, device=dev))
         a.c_last, a.n_last, a.m_last = last[0].data_ptr(), last[1].data_ptr(), last[2].data_ptr()
-    a.q.ptr, a.k.ptr, a.v.ptr, a.i.ptr, a.f.ptr, a.h.ptr = (q.data_ptr(), k.data_ptr(), v.data_ptr(), i.data_ptr(),
-                                                            f.data_ptr(), h.data_ptr())
+    a.q.ptr, a.k.ptr, a.v.ptr, a.i.ptr, a.f.ptr = q.data_ptr(), k.data_ptr(), v.data_ptr(), i.data_ptr(), f.data_ptr()
+    a.h.ptr = h.data_ptr() if h is not None else None
+    if epi is not None:
+        e = plan.epi
+        if (epi.y.data_ptr() | (0 if epi.x is None else epi.x.data_ptr())) & 15:
+            raise RuntimeError("fused epilogue: y / x must be 16-byte aligned")
+        e.y.ptr = epi.y.data_ptr()
+        e.x.ptr = None if epi.x is None else epi.x.data_ptr()
+        e.weight = None if epi.weight is None else epi.weight.data_ptr()
+        e.bias = None if epi.bias is None else epi.bias.data_ptr()
+        e.skip = None if epi.skip is None else epi.skip.data_ptr()
     nmp = nm.data_ptr()
     a.n_out, a.m_out = nmp, nmp + nm.stride(0) * 4
     a.c_states = c_states.data_ptr() if c_states is not None else None

@@ -127,7 +127,13 @@ int mlstm_b200_chunkwise_fw(const mlstm_b200_fw_args* a, void* stream) {
   if (int e = check_qkv(a->q, "q")) return e;
   if (int e = check_qkv(a->k, "k")) return e;
   if (int e = check_qkv(a->v, "v")) return e;
-  if (int e = check_qkv(a->h, "h")) return e;
+  if (a->epilogue) {  // fused cell-output epilogue: y is mandatory, the un-normalised h optional
+    if (int e = check_qkv(a->epilogue->y, "epilogue.y")) return e;
+    if (a->h.ptr)
+      if (int e = check_qkv(a->h, "h")) return e;
+  } else if (int e = check_qkv(a->h, "h")) {
+    return e;
+  }
   if (int e = check_vec(a->i, "i")) return e;
   if (int e = check_vec(a->f, "f")) return e;
   if (!a->n_out || !a->m_out) {
@@ -154,6 +160,10 @@ int mlstm_b200_chunkwise_fw(const mlstm_b200_fw_args* a, void* stream) {
   if (tc && a->shape.impl == MLSTM_B200_IMPL_AUTO && !tensor_fw_views_ok(*a)) tc = false;
   if (!tc && a->shape.gate_soft_cap > 0.f) {
     set_error("gate_soft_cap is applied by the tensor-core kernels only; cap the gates before an exact-route call");
+    return MLSTM_B200_EUNSUPPORTED;
+  }
+  if (!tc && a->epilogue) {
+    set_error("the fused cell-output epilogue exists on the tensor-core route only (use mlstm_b200_cellout_fw)");
     return MLSTM_B200_EUNSUPPORTED;
   }
   return tc ? tensor_fw(*a, (cudaStream_t)stream) : exact_fw(*a, (cudaStream_t)stream);

@@ -894,9 +894,9 @@ struct FwSmem128 {
   static constexpr int oP = 8 * kTile;        // P (two K-halves); the h staging tile aliases it
   static constexpr int oC = 10 * kTile;       // bf16 copy of C: [128 dqk rows][128 dv cols]
   static constexpr int oSmall = 12 * kTile;
-  // floats: gates[2], srs[2][2][LT], sqn[2][2][LT], npart[2][4][D], sN[2][D]
+  // floats: gates[2], srs[2][2][LT], sqn[2][2][LT], npart[2][4][D], sN[2][D], fused epilogue: stat[4][LT], par[3][D]
   static constexpr int fGates = 0, fRs = 2 * GateBuf::kFloats, fQn = fRs + 4 * LT, fNp = fQn + 4 * LT,
-                       fN = fNp + 8 * D, kSmallFloats = fN + 2 * D;
+                       fN = fNp + 8 * D, fStat = fN + 2 * D, fPar = fStat + 4 * LT, kSmallFloats = fPar + 3 * D;
   static constexpr int kBytes = oSmall + kSmallFloats * 4 + 1024;
   static constexpr uint32_t kLoadBytes = 6 * kTile;
 };
@@ -962,6 +962,12 @@ tc_fw_d128(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUt
       store_row32<T>(sC, row, ch * 64 + hf * 32, t32);
     }
     if (tid < D) fsm[SM::fN + tid] = p.n0 ? p.n0[(int64_t)bh * D + tid] : 0.f;
+    if (p.epi && tid < D) {  // per-channel parameters of the fused cell-output epilogue for this head
+      float* spar = fsm + SM::fPar;
+      spar[tid] = p.ln_w ? p.ln_w[hh * D + tid] : 1.f;
+      spar[D + tid] = p.ln_b ? p.ln_b[hh * D + tid] : 0.f;
+      spar[2 * D + tid] = p.ln_skip ? p.ln_skip[hh * D + tid] : 0.f;
+    }
     fence_proxy_async_smem();
   }
   tc_fence_before_sync();
@@ -1205,6 +1211,19 @@ tc_fw_d128(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUt
         if (ch == 0 && row < n_valid) {
           p.n_out[(int64_t)bh * p.S + t0 + row] = nmax;
           p.m_out[(int64_t)bh * p.S + t0 + row] = m_t;
+        }
+        if (p.epi) {  // fused cell output: see tc_fw (this thread: row, columns 64 ch .. 64 ch + 63 = one [128][64] sub-tile)
+          uint8_t* sub = sH + ch * SM::kTile;
+          const int64_t tok = (int64_t)(t0 + row);
+          if (p.h_plain && row < n_valid) {
+            uint4* dst = reinterpret_cast<uint4*>((T*)p.h_plain + b * p.h_sb + hh * p.h_sh + tok * p.h_ss + ch * 64);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = *reinterpret_cast<const uint4*>(sub + swz128(row, 8 * j));
+          }
+          const void* xrow = p.x ? (const void*)((const uint16_t*)p.x + b * p.x_sb + hh * p.x_sh + tok * p.x_ss + ch * 64) : nullptr;
+          // (parameters are indexed by the column inside the head: offset the table instead of the column)
+          ln_epilogue_slice<T, 128, 64>(sub, [](int r, int cc) { return swz128(r, cc & 63); }, row, ch * 64, ch, NB_PAIR0 + rb,
+                                        fsm + SM::fStat, fsm + SM::fPar, xrow, p.xy_f16 != 0, p.ln_eps, row < n_valid);
         }
       }
       // ---- state update C_k = gbar C_{k-1} + dC (M128 layout: lane == dqk row); n_k -----------------------
@@ -1987,15 +2006,30 @@ int make_states_map_blocks(CUtensorMap* m, const void* ptr, const mlstm_b200_sha
 
 int run_fw(const mlstm_b200_fw_args& a, void* c_states, cudaStream_t st) {
   const mlstm_b200_shape& s = a.shape;
-  if (!tma_ok(a.q) || !tma_ok(a.k) || !tma_ok(a.v) || !tma_ok(a.h)) {
+  const mlstm_b200_fw_epilogue* ep = a.epilogue;
+  // with the fused epilogue the tensor map describes y (the un-normalised h, if wanted, is stored from registers)
+  const mlstm_b200_tensor& out = ep ? ep->y : a.h;
+  if (!tma_ok(a.q) || !tma_ok(a.k) || !tma_ok(a.v) || !tma_ok(out)) {
     set_error("tensor path needs 16-byte aligned q/k/v/h with strides that are multiples of 8 elements");
     return MLSTM_B200_EUNSUPPORTED;
   }
+  if (ep) {
+    if (ep->xy_dtype != MLSTM_B200_BF16 && ep->xy_dtype != MLSTM_B200_F16) {
+      set_error("fused epilogue: y / x must be bf16 or fp16");
+      return MLSTM_B200_EUNSUPPORTED;
+    }
+    if ((ep->x.ptr && !tma_ok(ep->x)) || (a.h.ptr && !tma_ok(a.h))) {
+      set_error("fused epilogue: x and h need 16-byte aligned rows (unit innermost stride, strides multiples of 8 elements)");
+      return MLSTM_B200_EUNSUPPORTED;
+    }
+  }
   CUtensorMap mq, mk, mv, mh, mcs;
+  mlstm_b200_shape so = s;  // the y map carries y's element type
+  if (ep) so.dtype = ep->xy_dtype;
   int r = make_map(&mq, a.q, s, s.DHQK) | make_map(&mk, a.k, s, s.DHQK) | make_map(&mv, a.v, s, s.DHHV) |
-          make_map(&mh, a.h, s, s.DHHV);
-  // without a c_states buffer the map is never used by the kernel; point it at h to keep it valid
-  r |= !c_states ? make_map(&mcs, a.h, s, s.DHHV)
+          make_map(&mh, out, so, s.DHHV);
+  // without a c_states buffer the map is never used by the kernel; point it at the output to keep it valid
+  r |= !c_states ? make_map(&mcs, out, so, s.DHHV)
                  : s.DHQK == 128 ? make_states_map_blocks(&mcs, c_states, s) : make_states_map(&mcs, c_states, s);
   if (r) {
     set_error("cuTensorMapEncodeTiled failed (%d)", r);
@@ -2014,6 +2048,14 @@ int run_fw(const mlstm_b200_fw_args& a, void* c_states, cudaStream_t st) {
   p.sig = s.siging ? 1 : 0;
   p.store_states = c_states != nullptr;
   p.cap = s.gate_soft_cap;
+  if (ep) {
+    p.epi = 1;
+    p.xy_f16 = ep->xy_dtype == MLSTM_B200_F16;
+    p.ln_eps = ep->eps;
+    p.ln_w = ep->weight; p.ln_b = ep->bias; p.ln_skip = ep->skip;
+    p.x = ep->x.ptr; p.x_sb = ep->x.stride[0]; p.x_sh = ep->x.stride[1]; p.x_ss = ep->x.stride[2];
+    p.h_plain = a.h.ptr; p.h_sb = a.h.stride[0]; p.h_sh = a.h.stride[1]; p.h_ss = a.h.stride[2];
+  }
   TC_SET_PROF(p, 0);
   if (s.DHQK == 128) {
     if (s.dtype == MLSTM_B200_BF16) return launch_fw_d128<__nv_bfloat16>(p, mq, mk, mv, mh, mcs, st);
@@ -2221,7 +2263,9 @@ int bw128_by_blocks(const mlstm_b200_bw_args& a, cudaStream_t st) {
 }  // namespace
 
 // the views a call hands in can be described by TMA tensor maps (16-byte aligned base, 16-byte-multiple strides)
-bool tensor_fw_views_ok(const mlstm_b200_fw_args& a) { return tma_ok(a.q) && tma_ok(a.k) && tma_ok(a.v) && tma_ok(a.h); }
+bool tensor_fw_views_ok(const mlstm_b200_fw_args& a) {
+  return tma_ok(a.q) && tma_ok(a.k) && tma_ok(a.v) && tma_ok(a.epilogue ? a.epilogue->y : a.h);
+}
 bool tensor_bw_views_ok(const mlstm_b200_bw_args& a) {
   return tma_ok(a.q) && tma_ok(a.k) && tma_ok(a.v) && tma_ok(a.dh) && tma_ok(a.dq) && tma_ok(a.dk) && tma_ok(a.dv);
 }

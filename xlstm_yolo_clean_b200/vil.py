@@ -245,6 +245,87 @@ class _MlstmLayerLayout(torch.autograd.Function):
         return d_qk, d_v, d_g, None, None, None, None, None, None, None
 
 
+def _cellout_bw_call(h, x, weight, skip, dy, eps, out_dtype, want_dx):
+    """mlstm_b200_cellout_bw on saved tensors: returns dh (h's strides), dpar (3, H) fp32 = [dweight, dbias, dskip], dx."""
+    lib = _cabi.load_library()
+    B, NH, S, D = h.shape
+    dy = dy if (dy.dtype == out_dtype and dy.is_contiguous() and dy.data_ptr() % 16 == 0) else dy.to(out_dtype).contiguous()
+    w32, s32 = _f32c(weight), _f32c(skip)
+    dev = h.device
+    with _on_device(dev):
+        dh = torch.empty_strided(h.shape, h.stride(), dtype=h.dtype, device=dev)  # the kernel walks h and dh together
+        dx = torch.empty_like(dy) if (x is not None and want_dx) else None
+        dpar = torch.empty(3, NH * D, dtype=torch.float32, device=dev)
+        b = _cabi.CellOutBwArgs()
+        a = b.fw
+        a.B, a.NH, a.S, a.D = B, NH, S, D
+        a.h_dtype, a.x_dtype, a.y_dtype = _DTYPES[h.dtype], _DTYPES[out_dtype], _DTYPES[out_dtype]
+        a.eps = eps
+        a.h, a.x = _tensor(h), _tensor(x)
+        a.weight = None if w32 is None else w32.data_ptr()
+        a.skip = None if s32 is None else s32.data_ptr()
+        b.dy, b.dh, b.dx = _tensor(dy), _tensor(dh), _tensor(dx)
+        b.dweight, b.dbias, b.dskip = dpar[0].data_ptr(), dpar[1].data_ptr(), dpar[2].data_ptr()
+        ws_bytes = lib.mlstm_b200_cellout_workspace_bytes(C.byref(a))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        b.workspace, b.workspace_bytes = ws.data_ptr(), ws_bytes
+        st = lib.mlstm_b200_cellout_bw(C.byref(b), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _cabi.check(st, "mlstm_b200_cellout_bw")
+    return dh, dpar, dx
+
+
+class _MlstmCellFused(torch.autograd.Function):
+    """The whole cell in ONE forward launch: chunkwise mLSTM on the layer's own tensors (like
+    ``_MlstmLayerLayout``) with MultiHeadLayerNorm, the (B, NH, S, D) -> (B, S, H) relayout and the learnable skip done in
+    the kernel's epilogue (C-ABI ``mlstm_b200_fw_epilogue``): no separate cell-output pass, and under no_grad h never
+    reaches HBM un-normalised.  In training h is also written (the LayerNorm backward needs it); the backward is the
+    stand-alone cell-output backward followed by the mLSTM backward."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda")
+    def forward(ctx, qk, v, gates, x_skip, weight, bias, skip, NH, reverse, siging, chunk_size, eps, kernel_dtype, soft_cap,
+                ln_eps, out_dtype):
+        B, S, H = v.shape
+        D = H // NH
+        ctx.in_dtypes = (qk.dtype, v.dtype, gates.dtype)
+        qk_k, v_k, g_k = (t if t.dtype == kernel_dtype else t.to(kernel_dtype) for t in (qk, v, gates))
+        if S % chunk_size:
+            chunk_size = math.gcd(S, chunk_size)  # any S % 4 == 0 runs unpadded (see _MlstmLayerLayout)
+        q, k, vv, i, f = _heads(qk_k, v_k, g_k, NH)
+        need_bw = any(ctx.needs_input_grad[:7])
+        y = torch.empty(B, S, H, dtype=out_dtype, device=v.device)
+        xs = None
+        if x_skip is not None and skip is not None:
+            xs = x_skip if (x_skip.dtype == out_dtype and x_skip.is_contiguous()) else x_skip.to(out_dtype).contiguous()
+        as_heads = lambda t: t.view(B, S, NH, D).transpose(1, 2)  # noqa: E731  (B, NH, S, D) view of a (B, S, H) tensor
+        epi = _backend.FwEpilogue(as_heads(y), None if xs is None else as_heads(xs), _f32c(weight), _f32c(bias),
+                                  None if xs is None else _f32c(skip), ln_eps, need_bw)
+        h, nm, _, c_states = _backend._fw_launch(q, k, vv, i, f, None, None, None, None, False, chunk_size, eps, None, need_bw,
+                                                 reverse, siging, soft_cap, epi)
+        ctx.save_for_backward(qk_k, v_k, g_k, nm, c_states, h, xs, weight, bias, skip)
+        ctx.cfg = (NH, reverse, siging, chunk_size, eps, soft_cap, ln_eps, out_dtype)
+        return y
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        qk_k, v_k, g_k, nm, c_states, h, xs, weight, bias, skip = ctx.saved_tensors
+        NH, reverse, siging, chunk_size, eps, soft_cap, ln_eps, out_dtype = ctx.cfg
+        dh, dpar, dx = _cellout_bw_call(h, xs, weight, skip if xs is not None else None, dy, ln_eps, out_dtype,
+                                        ctx.needs_input_grad[3])
+        d_qk, d_v, d_g = torch.empty_like(qk_k), torch.empty_like(v_k), torch.empty_like(g_k)
+        q, k, vv, i, f = _heads(qk_k, v_k, g_k, NH)
+        nmp = nm.data_ptr()
+        _backend._bw_launch(q, k, vv, i, f, nmp, nmp + nm.stride(0) * 4, dh, None, None, None, None, None, chunk_size, eps, None,
+                            False, c_states, reverse, siging, _heads(d_qk, d_v, d_g, NH), soft_cap)
+        d_qk, d_v, d_g = (t if t.dtype == dt else t.to(dt) for t, dt in zip((d_qk, d_v, d_g), ctx.in_dtypes))
+        return (d_qk, d_v, d_g, dx,
+                None if weight is None else dpar[0].to(weight.dtype),
+                None if bias is None else dpar[1].to(bias.dtype),
+                None if (skip is None or xs is None) else dpar[2].to(skip.dtype),
+                None, None, None, None, None, None, None, None, None)
+
+
 def _is_reverse(layer) -> bool:
     d = getattr(layer, "direction", None)
     name = getattr(d, "name", None) or getattr(d, "value", None) or str(d)
@@ -306,6 +387,14 @@ def mlstm_cell_b200(cell, q, k, v, reverse=False, skip=None, x_skip=None, siging
         qk_c, v_c, g_c = qk, v, gates
         if cell.use_autocast:
             qk_c, v_c, g_c = (t.to(cell.autocast_dtype) for t in (qk_c, v_c, g_c))
+        norm = cell.outnorm
+        out_dtype = torch.get_autocast_dtype("cuda") if autocast_on else model_dtype
+        if (in_kernel_cap and S % 4 == 0 and out_dtype in (torch.float16, torch.bfloat16) and cellout_supported(NH, D)
+                and (x_skip is None or x_skip.shape == (B, S, H))):
+            # everything in one launch: the kernel's epilogue normalises, relayouts and adds the skip (_MlstmCellFused)
+            return _MlstmCellFused.apply(qk_c, v_c, g_c, x_skip if skip is not None else None, norm.weight_proxy, norm.bias,
+                                         skip, NH, bool(reverse), bool(siging), int(chunk_size), float(eps), kdt,
+                                         float(cell.gate_soft_cap), float(norm.eps), out_dtype)
         h = _MlstmLayerLayout.apply(qk_c, v_c, g_c, NH, bool(reverse), bool(siging), int(chunk_size), float(eps), kdt,
                                     float(cell.gate_soft_cap) if in_kernel_cap else 0.0)
     else:
