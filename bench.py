@@ -599,14 +599,14 @@ def main():
     dom = ("bw", bw_bytes, bw_t, "tc_bw") if bw_t >= fw_t else ("fw", fw_bytes, fw_t, "tc_fw")
     traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu capture (same workload)
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[dom[3]]
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))[dom[3]]
         traffic = tj["dram_read_bytes"] + tj["dram_write_bytes"] if args.kernel_impl == "auto" else None
     except Exception:
         pass
     roof = {"bound": "hbm", "kernel": f"{dom[3]} (mlstm_b200_chunkwise_{dom[0]}, one launch per call)",
             "achieved": dom[1] / (dom[2] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
             "frac": dom[1] / (dom[2] * 1e-3) / 1e9 / hbm_peak, "traffic": traffic,
-            "traffic_source": "static: committed ncu --set full capture of the same command (profiles/r01_traffic.json), not measured in this run" if traffic else None,
+            "traffic_source": "static: committed ncu --set full capture of the same command (profiles/r02_traffic.json), not measured in this run" if traffic else None,
             "peak_kind": peak_kind,
             "algorithmic_bytes": dom[1], "fw_ms": fw_t, "bw_ms": bw_t,
             # the saved per-tile states are extra traffic the kernels really move (written by fw, read by bw); they are NOT
