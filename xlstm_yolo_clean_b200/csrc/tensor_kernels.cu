@@ -991,6 +991,17 @@ tc_fw_d128(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUt
         tma_load_4d(sV + hf * SM::kTile, &mapV, &bar_full, hf * 64, mt(c) * LT, hh, b);
       }
     };
+    // One shared-memory stage only (192 KB of tiles): the refill of tile c+1 can start when every MMA of tile c has
+    // read Q / K / V, so its latency is exposed.  The tiles are therefore pulled into L2 two tiles ahead (no shared
+    // memory needed), which turns the refill into an L2 hit.
+    auto prefetch_tile = [&](int c) {
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        tma_prefetch_4d(&mapQ, hf * 64, mt(c) * LT, hh, b);
+        tma_prefetch_4d(&mapK, hf * 64, mt(c) * LT, hh, b);
+        tma_prefetch_4d(&mapV, hf * 64, mt(c) * LT, hh, b);
+      }
+    };
     constexpr uint32_t id_kk = umma_idesc(128, 128, false, false, kBf16);  // A K-major, B K-major
     constexpr uint32_t id_mm = umma_idesc(128, 128, true, true, kBf16);    // A MN-major, B MN-major
     constexpr uint32_t id_km = umma_idesc(128, 128, false, true, kBf16);   // A K-major, B MN-major
@@ -1023,12 +1034,14 @@ tc_fw_d128(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUt
         tma_store_commit();
       }
       load_tile(0);
+      if (p.NT > 1) prefetch_tile(1);
     }
     __syncwarp();
     if (elect_one()) issue_s(0);
     __syncwarp();
     for (int c = 0; c < p.NT; ++c) {
       const uint32_t par = c & 1;
+      if (lane == 0 && c + 2 < p.NT) prefetch_tile(c + 2);
       named_sync(NB_B, kNbAB);  // P(c) written
       if (c == 0 && lane == 0) tma_store_wait_read<0>();  // the initial-state store has read sC (rewritten after bar_h)
       __syncwarp();
