@@ -1304,6 +1304,9 @@ struct TcBwParams {
   int rev;  // 1: the forward ran anti-causally; this sweep then walks the memory tiles in ascending order
   int sig;  // 1: sigmoid input gate (m_out is all zeros, dI picks up sigmoid(-i))
   float cap;  // > 0: gate soft cap (see TcFwParams); dI / dF are written w.r.t. the pre-activations
+  // head-dim-128 block problems: add into outputs another block problem of the same call has already written
+  // (dq / dk / dv through TMA reduce-add, di / df read-modify-write by their one owner thread)
+  int acc_qk, acc_v, acc_g;
   // rows of the saved-states matrix per 128-token tile and row offset of this problem's D x D block inside a tile:
   // (D, 0) normally; (256, 64 * block) when a head-dim-128 backward runs as four head-dim-64 block problems
   int cs_rows, cs_off;
@@ -1570,9 +1573,15 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       named_sync(NB_C, kNbC);  // dq / dk / dv staged, dC_{k-1} written
       TC_PROF(it, 14);
       if (lane == 0) {
-        tma_store_4d(&mapdQ, sdQ, 0, t0, hh, b);
-        tma_store_4d(&mapdV, sdV, 0, t0, hh, b);
-        tma_store_4d(&mapdK, sdK, 0, t0, hh, b);
+        if (p.acc_qk) {
+          tma_reduce_add_4d(&mapdQ, sdQ, 0, t0, hh, b);
+          tma_reduce_add_4d(&mapdK, sdK, 0, t0, hh, b);
+        } else {
+          tma_store_4d(&mapdQ, sdQ, 0, t0, hh, b);
+          tma_store_4d(&mapdK, sdK, 0, t0, hh, b);
+        }
+        if (p.acc_v) tma_reduce_add_4d(&mapdV, sdV, 0, t0, hh, b);
+        else tma_store_4d(&mapdV, sdV, 0, t0, hh, b);
         tma_store_commit();
       }
       __syncwarp();
@@ -1672,9 +1681,16 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
           const int t = lane * 4 + e;
           if (t < n_valid) {
             const float dsig = p.sig ? 1.f - __expf(gb[GateBuf::oI + t]) : 1.f;  // sigmoid(-i) = 1 - exp(logsigmoid(i))
-            dip[(int64_t)(t0 + t) * p.di_ss] = from_f32<T>(di[e] * dsig * gb[GateBuf::oDi + t]);
-            dfp[(int64_t)(t0 + t) * p.df_ss] =
-                from_f32<T>((acc[e] + excl) * sigmoid_neg_f32(gb[GateBuf::oF + t]) * gb[GateBuf::oDf + t]);  // bw.py:322-323
+            float gi = di[e] * dsig * gb[GateBuf::oDi + t];
+            float gf = (acc[e] + excl) * sigmoid_neg_f32(gb[GateBuf::oF + t]) * gb[GateBuf::oDf + t];  // bw.py:322-323
+            T* pi = dip + (int64_t)(t0 + t) * p.di_ss;
+            T* pf = dfp + (int64_t)(t0 + t) * p.df_ss;
+            if (p.acc_g) {  // (the block problems of one call run one after the other on the stream)
+              gi += to_f32<T>(*pi);
+              gf += to_f32<T>(*pf);
+            }
+            *pi = from_f32<T>(gi);
+            *pf = from_f32<T>(gf);
           }
         }
         carry += __shfl_sync(0xffffffffu, incl, REV ? 31 : 0);
@@ -2105,38 +2121,9 @@ BwWs bw_ws(const mlstm_b200_shape& s) {
 // S = (Q K^T) . D are sums over column blocks, the state gradient dC (dqk x dv) splits into four independent
 // 64 x 64 blocks with the same decay, and the stabilisers depend on the gates only.  A 128-wide tile set does not
 // fit the backward's shared memory with 128-token tiles, so the 128 x 128 problem runs as the sum of four
-// tc_bw<64> problems on strided views of the same tensors (no copies of q/k/v/dh; qk_scale = 128^-1/2; each
-// recomputes its block of the states, bw.py:251-266).  The first partial of every output block is written in place,
-// the second goes to scratch and is added in one pass.
-template <typename T>
-__global__ void k_acc_block64(T* __restrict__ dst, int64_t sb, int64_t sh, int64_t ss, const T* __restrict__ src, int NH,
-                              int S, int64_t n_vec) {
-  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // one 8-element (16-byte) vector per thread
-  if (idx >= n_vec) return;
-  const int64_t tok = idx >> 3;
-  const int part = (int)(idx & 7);
-  const int64_t s_ = tok % S, bh = tok / S, h_ = bh % NH, b_ = bh / NH;
-  uint4* d = reinterpret_cast<uint4*>(dst + b_ * sb + h_ * sh + s_ * ss + part * 8);
-  const uint4 y = *reinterpret_cast<const uint4*>(src + tok * 64 + part * 8);
-  uint4 x = *d;
-  uint32_t* xp = reinterpret_cast<uint32_t*>(&x);
-  const uint32_t* yp = reinterpret_cast<const uint32_t*>(&y);
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const float2 a = unpack2<T>(xp[e]), b = unpack2<T>(yp[e]);
-    xp[e] = pack2<T>(a.x + b.x, a.y + b.y);
-  }
-  *d = x;
-}
-template <typename T>
-__global__ void k_acc_vec(T* __restrict__ dst, int64_t sb, int64_t sh, int64_t ss, const T* __restrict__ src, int NH, int S,
-                          int64_t n) {
-  const int64_t tok = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (tok >= n) return;
-  const int64_t s_ = tok % S, bh = tok / S, h_ = bh % NH, b_ = bh / NH;
-  T* d = dst + b_ * sb + h_ * sh + s_ * ss;
-  *d = from_f32<T>(to_f32<T>(*d) + to_f32<T>(src[tok]));
-}
+// tc_bw<64> problems on strided views of the same tensors (no copies of q/k/v/dh; qk_scale = 128^-1/2; each loads its
+// block of the forward's saved states or recomputes it, bw.py:251-266).  The first partial of every output block is
+// written in place, the second is added by the kernel that produces it (TMA reduce-add stores).
 // 64 x 64 block (a, b) of a (BH, 128, 128) fp32 state <-> contiguous (BH, 64, 64); vec: (BH, 128) <-> (BH, 64)
 __global__ void k_state_block(float* __restrict__ blk, float* __restrict__ full, int a, int b, int64_t n, int scatter) {
   const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -2153,7 +2140,10 @@ __global__ void k_state_vec_block(float* __restrict__ blk, const float* __restri
 }
 
 }  // namespace
-int run_bw(const mlstm_b200_bw_args& a, const void* c_states, int block, cudaStream_t st);
+int run_bw(const mlstm_b200_bw_args& a, const void* c_states, int block, cudaStream_t st, int acc_qk = 0, int acc_v = 0,
+           int acc_g = 0);
+int tensor_bw_blocks(const mlstm_b200_bw_args& a, const void* c_states_in, int block, cudaStream_t st, int acc_qk, int acc_v,
+                     int acc_g);
 namespace {
 
 mlstm_b200_shape block_shape(const mlstm_b200_shape& s) {
@@ -2171,11 +2161,7 @@ Bw128Ws bw128_ws(const mlstm_b200_shape& s) {
   size_t o = 0;
   w.sub_bytes = bw_ws(block_shape(s)).total;
   w.off_sub = o; o += align_up(w.sub_bytes, 256);
-  w.off_tq = o; o += align_up(tok * 64 * 2, 256);
-  w.off_tk = o; o += align_up(tok * 64 * 2, 256);
-  w.off_tv = o; o += align_up(tok * 64 * 2, 256);
-  w.off_ti = o; o += align_up(tok * 2, 256);
-  w.off_tf = o; o += align_up(tok * 2, 256);
+  w.off_tq = w.off_tk = w.off_tv = w.off_ti = w.off_tf = o;  // (partial sums are accumulated in-kernel: no scratch)
   w.off_c0 = o; o += align_up(bh * 64 * 64 * 4, 256);
   w.off_n0 = o; o += align_up(bh * 64 * 4, 256);
   w.off_dcl = o; o += align_up(bh * 64 * 64 * 4, 256);
@@ -2205,9 +2191,6 @@ int bw128_by_blocks(const mlstm_b200_bw_args& a, cudaStream_t st) {
     v.ptr = (char*)t.ptr + (size_t)j * 64 * sizeof(T);
     return v;
   };
-  mlstm_b200_tensor ti = dense(w.off_ti, 1), tf = dense(w.off_tf, 1);
-  ti.stride[0] = tf.stride[0] = (int64_t)s.NH * s.S, ti.stride[1] = tf.stride[1] = s.S, ti.stride[2] = tf.stride[2] = 1;
-  ti.stride[3] = tf.stride[3] = 0;
   const int thr = 256;
   int launches = 0;
   bool first = true;
@@ -2234,33 +2217,17 @@ int bw128_by_blocks(const mlstm_b200_bw_args& a, cudaStream_t st) {
         ++launches;
       }
       if (a.dc_initial) sub.dc_initial = (float*)(ws + w.off_dc0);
-      sub.dq = vb == 0 ? cols(a.dq, qa) : dense(w.off_tq, 64);  // dq_a, dk_a: sums over the v blocks
-      sub.dk = vb == 0 ? cols(a.dk, qa) : dense(w.off_tk, 64);
-      sub.dv = qa == 0 ? cols(a.dv, vb) : dense(w.off_tv, 64);  // dv_b: sum over the qk blocks
-      sub.di = first ? a.di : ti;
-      sub.df = first ? a.df : tf;
-      if (saved) {
-        if (int e = run_bw(sub, a.c_states, 2 * qa + vb, st)) return e;
-      } else {
-        if (int e = tensor_bw(sub, st)) return e;
-      }
-      const unsigned gv = (unsigned)((tok * 8 + thr - 1) / thr), gs = (unsigned)((tok + thr - 1) / thr);
-      if (vb == 1) {
-        const mlstm_b200_tensor dq = cols(a.dq, qa), dk = cols(a.dk, qa);
-        k_acc_block64<T><<<gv, thr, 0, st>>>((T*)dq.ptr, dq.stride[0], dq.stride[1], dq.stride[2], (const T*)(ws + w.off_tq), s.NH, s.S, tok * 8);
-        k_acc_block64<T><<<gv, thr, 0, st>>>((T*)dk.ptr, dk.stride[0], dk.stride[1], dk.stride[2], (const T*)(ws + w.off_tk), s.NH, s.S, tok * 8);
-        launches += 2;
-      }
-      if (qa == 1) {
-        const mlstm_b200_tensor dv = cols(a.dv, vb);
-        k_acc_block64<T><<<gv, thr, 0, st>>>((T*)dv.ptr, dv.stride[0], dv.stride[1], dv.stride[2], (const T*)(ws + w.off_tv), s.NH, s.S, tok * 8);
-        ++launches;
-      }
-      if (!first) {
-        k_acc_vec<T><<<gs, thr, 0, st>>>((T*)a.di.ptr, a.di.stride[0], a.di.stride[1], a.di.stride[2], (const T*)(ws + w.off_ti), s.NH, s.S, tok);
-        k_acc_vec<T><<<gs, thr, 0, st>>>((T*)a.df.ptr, a.df.stride[0], a.df.stride[1], a.df.stride[2], (const T*)(ws + w.off_tf), s.NH, s.S, tok);
-        launches += 2;
-      }
+      // The partial sums of an output block are added IN the kernel that produces the second one: dq_a, dk_a (sums over
+      // the v blocks) and dv_b (sum over the qk blocks) through TMA reduce-add stores, di / df by their owner threads --
+      // the block problems run one after the other on the stream, so the result is deterministic (one 16-bit rounding
+      // per addition, as a separate accumulate pass would do) and no scratch copies or accumulate launches are needed.
+      sub.dq = cols(a.dq, qa);
+      sub.dk = cols(a.dk, qa);
+      sub.dv = cols(a.dv, vb);
+      sub.di = a.di;
+      sub.df = a.df;
+      if (int e = tensor_bw_blocks(sub, saved ? a.c_states : nullptr, saved ? 2 * qa + vb : -1, st, vb == 1, qa == 1, !first))
+        return e;
       if (a.dc_initial) {
         k_state_block<<<(unsigned)((bh * 4096 + thr - 1) / thr), thr, 0, st>>>((float*)(ws + w.off_dc0), a.dc_initial, qa, vb, bh * 4096, 1);
         ++launches;
@@ -2319,7 +2286,12 @@ size_t tensor_workspace_bytes(const mlstm_b200_shape& s, int backward) {
 
 int tensor_fw(const mlstm_b200_fw_args& a, cudaStream_t st) { return run_fw(a, a.c_states, st); }
 
-int tensor_bw(const mlstm_b200_bw_args& a, cudaStream_t st) {
+int tensor_bw(const mlstm_b200_bw_args& a, cudaStream_t st) { return tensor_bw_blocks(a, a.c_states, -1, st, 0, 0, 0); }
+
+// c_states: the forward's saved states (block < 0: this problem's own; block = 0..3: block `block` of a head-dim-128
+// forward's buffer) or NULL = recompute; acc_*: add into dq / dk, dv, di / df instead of overwriting them
+int tensor_bw_blocks(const mlstm_b200_bw_args& a, const void* c_states_in, int block, cudaStream_t st, int acc_qk, int acc_v,
+                     int acc_g) {
   const mlstm_b200_shape& s = a.shape;
   if (!tma_ok(a.q) || !tma_ok(a.k) || !tma_ok(a.v) || !tma_ok(a.dh) || !tma_ok(a.dq) || !tma_ok(a.dk) || !tma_ok(a.dv)) {
     set_error("tensor path needs 16-byte aligned q/k/v/dh/dq/dk/dv with strides that are multiples of 8 elements");
@@ -2327,8 +2299,9 @@ int tensor_bw(const mlstm_b200_bw_args& a, cudaStream_t st) {
   }
   if (s.DHQK == 128)
     return s.dtype == MLSTM_B200_BF16 ? bw128_by_blocks<__nv_bfloat16>(a, st) : bw128_by_blocks<__half>(a, st);
-  const void* c_states = a.c_states;
+  const void* c_states = c_states_in;
   if (!c_states) {  // recompute the states with a forward pass into the workspace (bw.py:251-266)
+    block = -1;
     BwWs w = bw_ws(s);
     if (!a.workspace || a.workspace_bytes < w.total) {
       set_error("workspace too small: need %zu bytes, got %zu", w.total, a.workspace_bytes);
@@ -2346,12 +2319,12 @@ int tensor_bw(const mlstm_b200_bw_args& a, cudaStream_t st) {
     if (int e = run_fw(f, ws + w.off_states, st)) return e;
     c_states = ws + w.off_states;
   }
-  return run_bw(a, c_states, -1, st);
+  return run_bw(a, c_states, block, st, acc_qk, acc_v, acc_g);
 }
 
 // block < 0: c_states holds this problem's own (B, NH, NT, D, D) states.  block = 0..3: c_states is the head-dim-128
 // forward's buffer (four 64 x 64 blocks per tile) and this head-dim-64 problem reads block `block` of every tile.
-int run_bw(const mlstm_b200_bw_args& a, const void* c_states, int block, cudaStream_t st) {
+int run_bw(const mlstm_b200_bw_args& a, const void* c_states, int block, cudaStream_t st, int acc_qk, int acc_v, int acc_g) {
   const mlstm_b200_shape& s = a.shape;
   CUtensorMap mq, mk, mv, mdh, mcs, mdq, mdk, mdv;
   const int D = s.DHQK;
@@ -2376,6 +2349,7 @@ int run_bw(const mlstm_b200_bw_args& a, const void* c_states, int block, cudaStr
   p.rev = s.reverse ? 1 : 0;
   p.sig = s.siging ? 1 : 0;
   p.cap = s.gate_soft_cap;
+  p.acc_qk = acc_qk; p.acc_v = acc_v; p.acc_g = acc_g;
   p.cs_rows = block < 0 ? D : 256;
   p.cs_off = block < 0 ? 0 : 64 * block;
   TC_SET_PROF(p, 4096);
