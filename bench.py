@@ -618,28 +618,6 @@ def main():
             "fw_frac": fw_bytes / (fw_t * 1e-3) / 1e9 / hbm_peak, "bw_frac": bw_bytes / (bw_t * 1e-3) / 1e9 / hbm_peak,
             "tflops_frac_of_bf16_peak": (ff + fb) / ((fw_t + bw_t) * 1e-3) / 1e12 / tf_peak}
 
-    # ---- end to end through the public host-buffer API: pinned host tensors in, pinned host tensors out,
-    #      H2D / kernels / D2H pipelined over batch slices (xlstm_yolo_clean_b200.HostFwBw) -----------
-    numa = bind_numa_near_gpu(local_rank)
-    host = {k: v.cpu().pin_memory() for k, v in sets[0].items()}
-    pipe = pkg.HostFwBw(c["B"], c["NH"], c["S"], c["DK"], c["DV"], dtype=dt, device=dev, n_slices=1, lanes=2, chunk_size=c["L"])
-    host_out = pkg.HostFwBw.alloc_host(c["B"], c["NH"], c["S"], c["DK"], c["DV"], dtype=dt)
-    h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
-    for _ in range(4):
-        pipe.run(host, host_out)
-    pipe.flush()
-    sync_all()
-    e_steps = max(4, min(args.steps, 20))
-    e0.record()
-    for _ in range(e_steps):
-        pipe.run(host, host_out)  # every step: H2D of its inputs, fw + bw kernels, D2H of its results
-    pipe.flush()                  # (consecutive steps overlap on two device buffer sets; all of them end before e1)
-    e1.record()
-    sync_all()
-    e2e_ms = replicas.max_over_ranks(e0.elapsed_time(e1), dev) / e_steps
-    e2e_val = replicas.sum_over_ranks(ff + fb, dev) / (e2e_ms * 1e-3) / 1e12
-    e2e_check = float((host_out["h"].float() - keep[0][0][0].float().cpu()).abs().max())  # same inputs as set 0
-
     # ---- the same step through the registered drop-in (autograd.Function, eager launches): what a model pays --------
     leaves = [{k: st[k].detach().requires_grad_(True) for k in ("q", "k", "v", "i", "f")} for st in sets]
 
@@ -692,6 +670,29 @@ def main():
     except Exception as e:  # pragma: no cover
         dropin["graph_capture_error"] = repr(e)[:200]
 
+    # ---- end to end through the public host-buffer API: pinned host tensors in, pinned host tensors out,
+    #      H2D / kernels / D2H pipelined over batch slices (xlstm_yolo_clean_b200.HostFwBw) -----------
+    numa = bind_numa_near_gpu(local_rank)
+    host = {k: v.cpu().pin_memory() for k, v in sets[0].items()}
+    pipe = pkg.HostFwBw(c["B"], c["NH"], c["S"], c["DK"], c["DV"], dtype=dt, device=dev, n_slices=1, lanes=2, chunk_size=c["L"])
+    host_out = pkg.HostFwBw.alloc_host(c["B"], c["NH"], c["S"], c["DK"], c["DV"], dtype=dt)
+    h2d, d2h = pipe.h2d_bytes, pipe.d2h_bytes
+    for _ in range(4):
+        pipe.run(host, host_out)
+    pipe.flush()
+    sync_all()
+    e_steps = max(4, min(args.steps, 20))
+    e0.record()
+    for _ in range(e_steps):
+        pipe.run(host, host_out)  # every step: H2D of its inputs, fw + bw kernels, D2H of its results
+    pipe.flush()                  # (consecutive steps overlap on two device buffer sets; all of them end before e1)
+    e1.record()
+    sync_all()
+    e2e_ms = replicas.max_over_ranks(e0.elapsed_time(e1), dev) / e_steps
+    e2e_val = replicas.sum_over_ranks(ff + fb, dev) / (e2e_ms * 1e-3) / 1e12
+    e2e_check = float((host_out["h"].float() - keep[0][0][0].float().cpu()).abs().max())  # same inputs as set 0
+
+    del pipe
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     calls = None
     if world == 1 and not args.no_model_calls:
