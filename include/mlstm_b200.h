@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define MLSTM_B200_ABI_VERSION 3
+#define MLSTM_B200_ABI_VERSION 4
 
 /* element types of q/k/v/i/f/h and of the gradients */
 enum { MLSTM_B200_F32 = 0, MLSTM_B200_BF16 = 1, MLSTM_B200_F16 = 2 };
@@ -83,7 +83,10 @@ typedef struct mlstm_b200_shape {
                          while scanning; di / df are then gradients w.r.t. the pre-activations (the factor
                          1 - tanh^2(x / cap) is applied at the store).  Tensor-core route only: the exact route
                          returns MLSTM_B200_EUNSUPPORTED for gate_soft_cap > 0.  <= 0: i / f are used as given. */
-  int32_t reserved;   /* must be 0 */
+  int32_t grad_dtype; /* backward only: dtype of dq / dk / dv / di / df.  0 = shape.dtype.  MLSTM_B200_F16 with a BF16 kernel
+                         (or the reverse) writes the gradients in the CALLER's 16-bit dtype straight from the fp32
+                         accumulators -- a bf16 kernel under fp16 autocast (native/fwbw.py:37 casts the inputs, autograd casts
+                         the gradients back) then needs no cast pass over dq / dk / dv.  Tensor-core route only. */
 } mlstm_b200_shape;
 
 /* Optional fused cell-output epilogue of the forward: instead of (or in addition to) h the
@@ -292,6 +295,12 @@ typedef struct mlstm_b200_rmsnorm_bw_args {
 size_t mlstm_b200_rmsnorm_workspace_bytes(const mlstm_b200_rmsnorm_args* args);
 int mlstm_b200_rmsnorm_fw(const mlstm_b200_rmsnorm_args* args, void* cuda_stream);
 int mlstm_b200_rmsnorm_bw(const mlstm_b200_rmsnorm_bw_args* args, void* cuda_stream);
+
+/* Re-round a contiguous buffer of n 16-bit elements fp16 -> bf16 or bf16 -> fp16 (one RN rounding through fp32,
+ * bit-identical to Tensor.to()): the cast the reference's kernels apply to q / k / v under CUDA autocast
+ * (custom_fwd(cast_inputs=autocast_kernel_dtype), native/fwbw.py:37) as one streaming pass at HBM rate.  src and dst
+ * may not overlap unless identical (in place). */
+int mlstm_b200_convert16(const void* src, void* dst, int64_t n, int32_t src_dtype, int32_t dst_dtype, void* cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -3,7 +3,9 @@
 // swizzled operand writes and a TMA store.  Prints one PASS/FAIL line per variant.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -o umma_probe umma_probe.cu
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdio.h>
+#include <string.h>
 #include <stdlib.h>
 #include <math.h>
 #include <vector>
@@ -16,7 +18,7 @@ typedef __nv_bfloat16 bf16;
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); return 1; } } while (0)
 
 // A: K-major -> global [M][K]; MN-major -> global [K][M].  Same for B with N.
-template <int M, int N, int K, bool A_MN, bool B_MN, bool MANUAL_A, bool TMA_OUT>
+template <int M, int N, int K, bool A_MN, bool B_MN, bool MANUAL_A, bool TMA_OUT, bool A_F16 = false, bool B_F16 = false>
 __global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap mapA,
                                              const __grid_constant__ CUtensorMap mapB,
                                              const __grid_constant__ CUtensorMap mapO, const bf16* __restrict__ gA,
@@ -63,7 +65,7 @@ __global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap
   tc_fence_after_sync();
 
   if (warp == 0 && elect_one()) {
-    constexpr uint32_t idesc = umma_idesc(M, N, A_MN, B_MN, true);
+    constexpr uint32_t idesc = umma_idesc(M, N, A_MN, B_MN, !A_F16, !B_F16);
     for (int kk = 0; kk < K / 16; ++kk) {
       uint64_t ad, bd;
       if (A_MN) ad = umma_smem_desc(smem_u32(sA) + kk * 2048, K * 128, 1024);
@@ -106,12 +108,27 @@ __global__ void __launch_bounds__(128) probe(const __grid_constant__ CUtensorMap
 
 static float frand() { return (float)(rand() % 2001 - 1000) / 1000.f; }
 
-template <int M, int N, int K, bool A_MN, bool B_MN, bool MANUAL_A, bool TMA_OUT>
+// 16-bit pattern of x in the operand's format, and the value that pattern stands for
+template <bool F16>
+static bf16 enc16(float x, float* back) {
+  if (F16) {
+    __half h = __float2half(x);
+    *back = __half2float(h);
+    bf16 r;
+    memcpy(&r, &h, 2);
+    return r;
+  }
+  bf16 r = __float2bfloat16(x);
+  *back = __bfloat162float(r);
+  return r;
+}
+
+template <int M, int N, int K, bool A_MN, bool B_MN, bool MANUAL_A, bool TMA_OUT, bool A_F16 = false, bool B_F16 = false>
 int run(const char* name) {
   std::vector<bf16> hA(M * K), hB(N * K);
   std::vector<float> fA(M * K), fB(N * K);  // logical A[m][k], B[n][k]
-  for (int m = 0; m < M; ++m) for (int k = 0; k < K; ++k) { bf16 x = __float2bfloat16(frand()); fA[m * K + k] = __bfloat162float(x); hA[A_MN ? k * M + m : m * K + k] = x; }
-  for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) { bf16 x = __float2bfloat16(frand()); fB[n * K + k] = __bfloat162float(x); hB[B_MN ? k * N + n : n * K + k] = x; }
+  for (int m = 0; m < M; ++m) for (int k = 0; k < K; ++k) { bf16 x = enc16<A_F16>(frand(), &fA[m * K + k]); hA[A_MN ? k * M + m : m * K + k] = x; }
+  for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) { bf16 x = enc16<B_F16>(frand(), &fB[n * K + k]); hB[B_MN ? k * N + n : n * K + k] = x; }
   bf16 *dA, *dB, *dO16; float* dO;
   CK(cudaMalloc(&dA, M * K * 2)); CK(cudaMalloc(&dB, N * K * 2)); CK(cudaMalloc(&dO, M * N * 4)); CK(cudaMalloc(&dO16, 128 * 64 * 2));
   CK(cudaMemcpy(dA, hA.data(), M * K * 2, cudaMemcpyHostToDevice));
@@ -125,7 +142,7 @@ int run(const char* name) {
   int rO = sm100_host::make_map_bhsd(&mO, dO16, true, 1, 1, 128, 64, 128 * 64, 128 * 64, 64, 128);
   if (rA || rB || rO) { printf("%s: tensor map encode failed %d %d %d\n", name, rA, rB, rO); return 1; }
   size_t smem = (size_t)M * K * 2 + (size_t)N * K * 2 + 128 * 128 + 2048;
-  auto kern = probe<M, N, K, A_MN, B_MN, MANUAL_A, TMA_OUT>;
+  auto kern = probe<M, N, K, A_MN, B_MN, MANUAL_A, TMA_OUT, A_F16, B_F16>;
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int* hdbg = nullptr; int* ddbg = nullptr;
   CK(cudaHostAlloc(&hdbg, 64, cudaHostAllocMapped)); hdbg[0] = 0; hdbg[1] = 0;
@@ -156,6 +173,16 @@ int main(int argc, char** argv) {
   if (argc > 1 && argv[1][0] == 't') return time_main();
   if (argc > 1 && argv[1][0] == 's') return sw64_main();
   int bad = 0;
+  if (argc > 1 && argv[1][0] == 'm') {  // `umma_probe mixed`: one operand fp16, the other bf16, in one kind::f16 instruction
+    bad += run<128, 128, 64, false, false, false, false, true, false>("mixed  A:f16 (K)  B:bf16 (K)   M128 N128 K64 ") != 0;
+    bad += run<128, 128, 64, false, false, false, false, false, true>("mixed  A:bf16 (K) B:f16 (K)    M128 N128 K64 ") != 0;
+    bad += run<128, 64, 128, false, true, false, false, false, true>("mixed  A:bf16 (K) B:f16 (MN)   M128 N64  K128") != 0;
+    bad += run<64, 64, 128, true, true, false, false, false, true>("mixed  A:bf16 (MN) B:f16 (MN)  M64  N64  K128") != 0;
+    bad += run<128, 64, 128, true, true, false, false, true, false>("mixed  A:f16 (MN) B:bf16 (MN)  M128 N64  K128") != 0;
+    bad += run<128, 128, 64, false, false, false, false, true, true>("plain  A:f16 (K)  B:f16 (K)    M128 N128 K64 ") != 0;
+    printf("%d variant(s) failed\n", bad);
+    return bad ? 1 : 0;
+  }
   bad += run<128, 128, 64, false, false, false, false>("S=QK^T      M128 N128 K64  A:K  B:K ") != 0;
   bad += run<128, 64, 128, false, true, false, true>("PV          M128 N64  K128 A:K  B:MN +tma_store") != 0;
   bad += run<128, 64, 128, false, true, true, false>("PV manualA  M128 N64  K128 A:K* B:MN") != 0;

@@ -36,7 +36,7 @@ def test_exports_match_header(lib):
 
 
 def test_abi_version_and_error_string(lib):
-    assert lib.mlstm_b200_abi_version() == 3
+    assert lib.mlstm_b200_abi_version() == 4
     assert isinstance(lib.mlstm_b200_last_error(), bytes)
 
 

@@ -393,3 +393,29 @@ def test_fused_forward_epilogue_equals_kernel_plus_cell_out(pkg, NH, D, S, rever
     torch.cuda.synchronize()
     assert h2 is None
     assert rel(y2, pkg.cell_out(h0, w, None, None, None, eps=1e-5, out_dtype=odt)) < (2e-3 if odt == torch.float16 else 1.2e-2)
+
+
+@pytest.mark.parametrize("src,dst", [(torch.float16, torch.bfloat16), (torch.bfloat16, torch.float16)], ids=["fp16_to_bf16", "bf16_to_fp16"])
+def test_convert16_is_bit_identical_to_torch(pkg, src, dst):
+    """mlstm_b200_convert16 = Tensor.to() for the autocast re-rounding of q / k / v (native/fwbw.py:37): every size
+    class of the vector loop, a misaligned view, a dense permuted tensor, non-finite and subnormal values."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(5)
+    for n in (1, 7, 8, 9, 8 * 256 * 4 - 1, 1_000_003, 32 * 1600 * 512 + 24):
+        x = (torch.randn(n, generator=g) * 50).to(src).to(dev)
+        y = pkg.convert16(x, dst)
+        assert y.dtype == dst and torch.equal(y.view(torch.int16), x.to(dst).view(torch.int16)), n
+    special = torch.tensor([0.0, -0.0, float("inf"), -float("inf"), float("nan"), 65504.0, -65504.0, 6e-8, 1e-7, 3e38, -3e38,
+                            1.0009765625, 0.99951171875, 5.9e-8, 1e-40] * 3, dtype=torch.float32).to(src).to(dev)
+    a, b = pkg.convert16(special, dst), special.to(dst)
+    assert torch.equal(torch.isnan(a), torch.isnan(b))
+    assert torch.equal(a.nan_to_num(7.0).view(torch.int16), b.nan_to_num(7.0).view(torch.int16))
+    base = (torch.randn(4099, generator=g)).to(src).to(dev)
+    off = base[3:]  # starts 6 bytes into a vector
+    assert torch.equal(pkg.convert16(off, dst), off.to(dst))
+    perm = (torch.randn(6, 40, 24, generator=g)).to(src).to(dev).permute(1, 0, 2)  # dense, not contiguous: strides are kept
+    yp = pkg.convert16(perm, dst)
+    assert yp.stride() == perm.stride() and torch.equal(yp, perm.to(dst))
+    sliced = perm[:, :, :8]  # not dense: torch's path
+    assert torch.equal(pkg.convert16(sliced, dst), sliced.to(dst))
+    assert pkg.convert16(base, src) is base

@@ -3,6 +3,7 @@ golden vectors.  Tolerances are north_star's: 1e-5 relative in fp32, 2e-2 in bf1
 as max|a-b| / max|b| per tensor against the float64 oracle on inputs pre-rounded to the test dtype
 (SURVEY.md §8c)."""
 import glob
+import math
 import os
 
 import numpy as np
@@ -596,3 +597,53 @@ def test_views_the_tma_cannot_describe_are_accepted(pkg):
     assert st == 0, lib.mlstm_b200_last_error()
     assert lib.mlstm_b200_last_launch_count() == 2  # the exact family's two forward kernels, not the tensor path's one
     assert O.rel_err(h.double().cpu(), want[0].double().cpu()) < 2e-2
+
+
+@pytest.mark.parametrize("reverse", [False, True], ids=["causal", "anticausal"])
+@pytest.mark.parametrize("B,NH,S,D", [(2, 3, 384, 64), (2, 4, 200, 32), (1, 2, 256, 128)], ids=["d64", "d32_ragged", "d128_blocks"])
+@pytest.mark.parametrize("kdt,gdt", [(torch.bfloat16, torch.float16), (torch.float16, torch.bfloat16)], ids=["bf16_kernel_fp16_grads", "fp16_kernel_bf16_grads"])
+def test_backward_writes_gradients_in_the_callers_dtype(pkg, kdt, gdt, B, NH, S, D, reverse):
+    """shape.grad_dtype: a kernel that computes in one 16-bit dtype rounds its fp32 accumulators straight to the other
+    (what autograd's cast of the gradients does under fp16 autocast with the bf16 kernels, native/fwbw.py:37, minus the
+    pass over dq / dk / dv): same values as the kernel-dtype gradients up to one rounding, and within the 16-bit bar of
+    the fp64 oracle -- for freshly allocated gradients and for caller-owned strided ones."""
+    inp = O.make_inputs(B, NH, S, D, D, seed=71, dtype=torch.float32)
+    t = {k: v.to(kdt).cuda() for k, v in inp.items()}
+    L = math.gcd(S, 64)
+    _, n_out, m_out, _, cs = pkg.mlstm_chunkwise_fw(t["q"], t["k"], t["v"], t["i"], t["f"], chunk_size=L, reverse=reverse)
+    args = (t["q"], t["k"], t["v"], t["i"], t["f"], n_out, m_out, t["dh"])
+    base = pkg.mlstm_chunkwise_bw(*args, chunk_size=L, c_states=cs, reverse=reverse)[:5]
+    got = pkg.mlstm_chunkwise_bw(*args, chunk_size=L, c_states=cs, reverse=reverse, grad_dtype=gdt)[:5]
+    # caller-owned gradients in the layer layout (B, S, NH, 2D | D | 2), other dtype
+    d_qk = torch.empty(B, S, NH, 2 * D, dtype=gdt, device="cuda")
+    d_v = torch.empty(B, S, NH, D, dtype=gdt, device="cuda")
+    d_g = torch.empty(B, S, NH, 2, dtype=gdt, device="cuda")
+    out = (d_qk[..., :D].transpose(1, 2), d_qk[..., D:].transpose(1, 2), d_v.transpose(1, 2), d_g[..., 0].transpose(1, 2),
+           d_g[..., 1].transpose(1, 2))
+    pkg.mlstm_chunkwise_bw(*args, chunk_size=L, c_states=cs, reverse=reverse, out=out)
+    torch.cuda.synchronize()
+    r = {k: v.to(kdt).double() for k, v in inp.items()}
+    flip = (lambda x: x.flip(2)) if reverse else (lambda x: x)
+    _, _, grads = O.fwbw(*(flip(r[n]) for n in ("q", "k", "v", "i", "f", "dh")), None, None, None, chunk_size=L)
+    for name, b, g, o, w in zip(("dq", "dk", "dv", "di", "df"), base, got, out, grads):
+        assert g.dtype == gdt and o.dtype == gdt and b.dtype == kdt
+        assert torch.equal(g, o.contiguous()), name
+        assert O.rel_err(g.double().cpu(), b.double().cpu()) < 6e-3, name  # one bf16 rounding apart
+        # (dF is a suffix sum: its bf16 bar at long S is documented in test_model_shapes_gpu; S <= 384 here)
+        assert O.rel_err(g.double().cpu(), flip(w)) < 2e-2, name
+
+
+def test_registry_function_under_fp16_autocast_returns_fp16_gradients_without_casts(pkg):
+    """fp16 leaves under CUDA autocast with the bf16 kernels (the reference trainer's situation): gradients arrive in
+    fp16, written by the backward kernel itself, equal to what the kernel-dtype gradients round to."""
+    inp = O.make_inputs(2, 4, 256, 64, 64, seed=72, dtype=torch.float32)
+    leaves = {k: inp[k].to(torch.float16).cuda().requires_grad_(True) for k in ("q", "k", "v", "i", "f")}
+    dh = inp["dh"].cuda()
+    with torch.autocast("cuda", dtype=torch.float16):
+        h = pkg.mlstm_chunkwise__b200(**leaves, autocast_kernel_dtype=torch.bfloat16)
+    assert h.dtype == torch.bfloat16
+    h.backward(dh.to(h.dtype))
+    ref = _oracle({k: (v.to(torch.float16) if k in leaves else v) for k, v in inp.items()}, torch.bfloat16)
+    for n, key in (("q", "dq"), ("k", "dk"), ("v", "dv"), ("i", "di"), ("f", "df")):
+        assert leaves[n].grad.dtype == torch.float16
+        assert O.rel_err(leaves[n].grad.double().cpu(), ref[key]) < 2e-2, key

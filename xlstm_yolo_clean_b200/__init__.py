@@ -22,6 +22,7 @@ from .backend import (  # noqa: F401
     mlstm_chunkwise_fw,
     mlstm_recurrent_sequence__b200,
     mlstm_recurrent_step__b200,
+    convert16,
     mlstm_siging_chunkwise__b200,
     patch_model,
     register,

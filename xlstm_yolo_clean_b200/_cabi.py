@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmlstm_b200.so")
 
 F32, BF16, F16 = 0, 1, 2
 IMPL_AUTO, IMPL_EXACT, IMPL_TENSOR = 0, 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 EXPORTS = (
     "mlstm_b200_abi_version",
@@ -31,6 +31,7 @@ EXPORTS = (
     "mlstm_b200_rmsnorm_workspace_bytes",
     "mlstm_b200_rmsnorm_fw",
     "mlstm_b200_rmsnorm_bw",
+    "mlstm_b200_convert16",
 )
 
 
@@ -42,7 +43,7 @@ class Shape(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("NH", C.c_int32), ("S", C.c_int32), ("DHQK", C.c_int32), ("DHHV", C.c_int32),
         ("chunk_size", C.c_int32), ("dtype", C.c_int32), ("impl", C.c_int32), ("reverse", C.c_int32), ("siging", C.c_int32),
-        ("eps", C.c_float), ("qk_scale", C.c_float), ("gate_soft_cap", C.c_float), ("reserved", C.c_int32),
+        ("eps", C.c_float), ("qk_scale", C.c_float), ("gate_soft_cap", C.c_float), ("grad_dtype", C.c_int32),
     ]
 
 
@@ -175,6 +176,8 @@ def load_library(path: str | None = None):
     lib.mlstm_b200_rmsnorm_fw.argtypes = [C.POINTER(RmsNormArgs), C.c_void_p]
     lib.mlstm_b200_rmsnorm_bw.restype = C.c_int
     lib.mlstm_b200_rmsnorm_bw.argtypes = [C.POINTER(RmsNormBwArgs), C.c_void_p]
+    lib.mlstm_b200_convert16.restype = C.c_int
+    lib.mlstm_b200_convert16.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
     v = lib.mlstm_b200_abi_version()
     if v != ABI_VERSION:
         raise RuntimeError(f"ABI mismatch: library {v}, binding {ABI_VERSION}")

@@ -293,6 +293,44 @@ def _fw_launch(q, k, v, i, f, c0, n0, m0, qk_scale, return_last_states, chunk_si
     return h, nm, last, c_states
 
 
+def _is_dense(x) -> bool:
+    """A permutation of a contiguous buffer: every element of the storage range is addressed exactly once."""
+    if x.is_contiguous():
+        return True
+    expected = 1
+    for st, sz in sorted(zip(x.stride(), x.shape)):
+        if sz == 1:
+            continue
+        if st != expected:
+            return False
+        expected *= sz
+    return True
+
+
+def convert16(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """``x.to(dtype)`` for fp16 <-> bf16 CUDA tensors as one streaming pass (C-ABI ``mlstm_b200_convert16``): the
+    re-rounding the reference kernels apply to their inputs under autocast (native/fwbw.py:37), bit-identical to torch's,
+    at twice its rate.  Dense tensors only (any permutation of a contiguous buffer keeps its strides); everything else
+    goes through torch."""
+    if x.dtype is dtype:
+        return x
+    if (not x.is_cuda or {x.dtype, dtype} != {torch.float16, torch.bfloat16} or x.numel() == 0
+            or not _is_dense(x)):
+        return x.to(dtype)
+    y = torch.empty_like(x, dtype=dtype)  # preserve_format: same strides for a dense tensor
+    if y.stride() != x.stride():
+        return x.to(dtype)
+    dev = x.device
+    if torch._C._cuda_getDevice() != dev.index:
+        with torch.cuda.device(dev):
+            return convert16(x, dtype)
+    st = _cabi.load_library().mlstm_b200_convert16(x.data_ptr(), y.data_ptr(), x.numel(), _DTYPES[x.dtype], _DTYPES[dtype],
+                                                  _raw_stream(dev.index))
+    if st:
+        _cabi.check(st, "mlstm_b200_convert16")
+    return y
+
+
 def mlstm_chunkwise_fw(q, k, v, i, f, c_initial=None, n_initial=None, m_initial=None, qk_scale=None,
                        return_last_states=False, chunk_size=64, eps=1e-6, impl=None, save_states=True, reverse=False, siging=False,
                        gate_soft_cap=0.0):
@@ -313,9 +351,13 @@ def mlstm_chunkwise_fw(q, k, v, i, f, c_initial=None, n_initial=None, m_initial=
 
 
 def _bw_launch(q, k, v, i, f, n_ptr, m_ptr, dh, c0, n0, m0, dcl, qk_scale, chunk_size, eps, impl, want_dc_initial, c_states,
-               reverse, siging, out, soft_cap=0.0):
+               reverse, siging, out, soft_cap=0.0, grad_dtype=None):
+    """``out``: caller-owned (dq, dk, dv, di, df).  Their dtype (or ``grad_dtype`` when the gradients are allocated here)
+    may be the OTHER 16-bit dtype than the kernel's: the tensor-core backward then rounds its fp32 accumulators straight
+    to it (``shape.grad_dtype``) -- a bf16 kernel under fp16 autocast needs no cast pass over the gradients."""
     impl = _default_impl if impl is None else impl
     dt = q.dtype
+    gdt = out[0].dtype if out is not None else (grad_dtype or dt)
     if dh.dtype is not dt:
         dh = dh.to(dt)
     if i.dtype is not dt:
@@ -325,7 +367,7 @@ def _bw_launch(q, k, v, i, f, n_ptr, m_ptr, dh, c0, n0, m0, dcl, qk_scale, chunk
     dev = q.device
     key = (1, q.shape, v.shape[3], dt, q.stride(), k.stride(), v.stride(), i.stride(), f.stride(), dh.stride(), chunk_size, eps,
            impl, qk_scale, reverse, siging, c0 is not None, want_dc_initial, c_states is not None, dev.index,
-           None if out is None else tuple(t.stride() for t in out), soft_cap)
+           None if out is None else tuple(t.stride() for t in out), soft_cap, gdt)
     plans = _plans()
     plan = plans.get(key)
     lib = _cabi.load_library()
@@ -337,14 +379,22 @@ def _bw_launch(q, k, v, i, f, n_ptr, m_ptr, dh, c0, n0, m0, dcl, qk_scale, chunk
         a.shape = _shape(q, v, chunk_size, eps, impl, qk_scale, reverse, siging, soft_cap)
         plan = _BwPlan()
         plan.tensor_route = _tensor_route(lib, a.shape)
+        if gdt is not dt:
+            if out is None and (not plan.tensor_route or gdt not in (torch.float16, torch.bfloat16)):
+                # gradients allocated here: the kernel dtype it is (autograd casts them where it has to)
+                return _bw_launch(q, k, v, i, f, n_ptr, m_ptr, dh, c0, n0, m0, dcl, qk_scale, chunk_size, eps, impl,
+                                  want_dc_initial, c_states, reverse, siging, None, soft_cap, None)
+            if not plan.tensor_route or gdt not in (torch.float16, torch.bfloat16):
+                raise RuntimeError(f"gradients in {gdt} from a {dt} kernel: tensor-core route and 16-bit dtypes only")
+            a.shape.grad_dtype = _DTYPES[gdt]
         fixed = _fix_views(plan.tensor_route, (q, k, v, dh))
         if any(x is not y for x, y in zip(fixed, (q, k, v, dh))):
             return _bw_launch(*fixed[:3], i, f, n_ptr, m_ptr, fixed[3], c0, n0, m0, dcl, qk_scale, chunk_size, eps, impl,
-                              want_dc_initial, c_states, reverse, siging, out, soft_cap)
+                              want_dc_initial, c_states, reverse, siging, out, soft_cap, grad_dtype)
         if out is not None:
             dq, dk, dv, di, df = out
             assert dq.shape == q.shape and dk.shape == k.shape and dv.shape == v.shape and di.shape == i.shape
-            assert all(t.dtype == dt and t.device == dev for t in out)
+            assert all(t.dtype == gdt and t.device == dev for t in out)
             if plan.tensor_route and not all(_tma_strides_ok(t) for t in (dq, dk, dv)):
                 raise RuntimeError("caller-provided dq / dk / dv need a unit innermost stride and 16-byte-multiple strides")
             for name, t in zip(("dq", "dk", "dv", "di", "df"), out):
@@ -369,17 +419,17 @@ def _bw_launch(q, k, v, i, f, n_ptr, m_ptr, dh, c0, n0, m0, dcl, qk_scale, chunk
     if torch._C._cuda_getDevice() != dev.index:
         with torch.cuda.device(dev):
             return _bw_launch(q, k, v, i, f, n_ptr, m_ptr, dh, c0, n0, m0, dcl, qk_scale, chunk_size, eps, impl,
-                              want_dc_initial, c_states, reverse, siging, out, soft_cap)
+                              want_dc_initial, c_states, reverse, siging, out, soft_cap, grad_dtype)
     if out is not None:
         dq, dk, dv, di, df = out
         if plan.tensor_route and (dq.data_ptr() | dk.data_ptr() | dv.data_ptr()) & 15:
             raise RuntimeError("caller-provided dq / dk / dv must be 16-byte aligned")
     else:
-        dq = torch.empty(plan.gshape_qk, dtype=dt, device=dev)
-        dk = torch.empty(plan.gshape_qk, dtype=dt, device=dev)
-        dv = torch.empty(plan.gshape_v, dtype=dt, device=dev)
-        di = torch.empty(plan.gshape_g, dtype=dt, device=dev)
-        df = torch.empty(plan.gshape_g, dtype=dt, device=dev)
+        dq = torch.empty(plan.gshape_qk, dtype=gdt, device=dev)
+        dk = torch.empty(plan.gshape_qk, dtype=gdt, device=dev)
+        dv = torch.empty(plan.gshape_v, dtype=gdt, device=dev)
+        di = torch.empty(plan.gshape_g, dtype=gdt, device=dev)
+        df = torch.empty(plan.gshape_g, dtype=gdt, device=dev)
     ws = _ws_tensor(plan.ws_bytes, dev)
     dc0 = None
     if c0 is not None:
@@ -410,13 +460,14 @@ def _bw_launch(q, k, v, i, f, n_ptr, m_ptr, dh, c0, n0, m0, dcl, qk_scale, chunk
 
 def mlstm_chunkwise_bw(q, k, v, i, f, n_out, m_out, dh, c_initial=None, n_initial=None, m_initial=None,
                        dc_last=None, qk_scale=None, chunk_size=64, eps=1e-6, impl=None, want_dc_initial=False,
-                       c_states=None, reverse=False, siging=False, out=None, gate_soft_cap=0.0):
+                       c_states=None, reverse=False, siging=False, out=None, gate_soft_cap=0.0, grad_dtype=None):
     """C-ABI backward.  Returns dq, dk, dv, di, df, dc_initial-or-None (fp32).
 
     With ``gate_soft_cap`` > 0 (see the forward) di / df are gradients w.r.t. the gate pre-activations.
 
     ``out`` = (dq, dk, dv, di, df) lets the caller provide the gradient tensors (any batch/head/token strides,
-    unit innermost stride for dq/dk/dv), e.g. views into a fused (B, S, 2H) qk gradient."""
+    unit innermost stride for dq/dk/dv), e.g. views into a fused (B, S, 2H) qk gradient.  Their dtype -- or
+    ``grad_dtype`` when the gradients are allocated here -- may be the other 16-bit dtype than the kernel's."""
     if c_initial is None and (n_initial is not None or m_initial is not None):
         B, NH, S, DK = q.shape
         c_initial = torch.zeros(B, NH, DK, v.shape[-1], device=q.device)
@@ -424,7 +475,7 @@ def mlstm_chunkwise_bw(q, k, v, i, f, n_out, m_out, dh, c_initial=None, n_initia
     m_out = m_out if m_out.is_contiguous() else m_out.contiguous()
     return _bw_launch(q, k, v, i, f, n_out.data_ptr(), m_out.data_ptr(), dh, c_initial, n_initial, m_initial, dc_last, qk_scale,
                       int(chunk_size), float(eps), impl, bool(want_dc_initial), c_states, bool(reverse), bool(siging), out,
-                      float(gate_soft_cap or 0.0))
+                      float(gate_soft_cap or 0.0), grad_dtype)
 
 
 def _make_function(autocast_kernel_dtype: torch.dtype):
@@ -434,8 +485,9 @@ def _make_function(autocast_kernel_dtype: torch.dtype):
         @staticmethod
         @custom_fwd(device_type="cuda", cast_inputs=autocast_kernel_dtype)
         def forward(ctx, q, k, v, i, f, c_initial, n_initial, m_initial, return_last_states, chunk_size, eps, reverse,
-                    siging):
+                    siging, grad_dtype=None):
             need_bw = any(ctx.needs_input_grad[:6])
+            ctx.grad_dtype = grad_dtype
             if c_initial is None and (n_initial is not None or m_initial is not None):
                 c_initial = torch.zeros(q.shape[0], q.shape[1], q.shape[3], v.shape[3], dtype=q.dtype, device=q.device)
             h, nm, last, c_states = _fw_launch(q, k, v, i, f, c_initial, n_initial, m_initial, None, return_last_states,
@@ -454,15 +506,26 @@ def _make_function(autocast_kernel_dtype: torch.dtype):
             nmp = nm.data_ptr()
             dq, dk, dv, di, df, dc0 = _bw_launch(q, k, v, i, f, nmp, nmp + nm.stride(0) * 4, dh, c0, n0, m0, dc_last, None,
                                                  ctx.chunk_size, ctx.eps, None, c0 is not None, c_states, ctx.reverse,
-                                                 ctx.siging, None)
+                                                 ctx.siging, None, 0.0, ctx.grad_dtype)
             # dn_last / dm_last are ignored and dN/dM_initial are zeros, as in native/bw.py:329-337
             return (dq, dk, dv, di, df,
                     None if c0 is None else dc0.to(c0.dtype),
                     None if n0 is None else torch.zeros_like(n0),
                     None if m0 is None else torch.zeros_like(m0),
-                    None, None, None, None, None)
+                    None, None, None, None, None, None)
 
     return _MlstmChunkwiseB200
+
+
+def _caller_grad_dtype(kernel_dtype, *tensors):
+    """Under CUDA autocast custom_fwd re-rounds 16-bit inputs to the kernel dtype and autograd casts the gradients back:
+    when every differentiable input has the same OTHER 16-bit dtype the backward kernel writes that dtype itself."""
+    if not torch.is_autocast_enabled("cuda"):
+        return None
+    dt = tensors[0].dtype
+    if dt is kernel_dtype or dt not in (torch.float16, torch.bfloat16) or kernel_dtype not in (torch.float16, torch.bfloat16):
+        return None
+    return dt if all(t.dtype is dt for t in tensors) else None
 
 
 _FUNCTIONS = {dt: _make_function(dt) for dt in (torch.float32, torch.float16, torch.bfloat16)}
@@ -497,7 +560,8 @@ def mlstm_chunkwise__b200(
         raise ValueError(f"Unsupported kernel dtype {autocast_kernel_dtype}.")
     fn = _FUNCTIONS[autocast_kernel_dtype]
     h, c_last, n_last, m_last = fn.apply(q, k, v, i, f, c_initial, n_initial, m_initial, bool(return_last_states),
-                                         int(chunk_size), float(eps), bool(reverse), False)
+                                         int(chunk_size), float(eps), bool(reverse), False,
+                                         _caller_grad_dtype(autocast_kernel_dtype, q, k, v, i, f))
     if return_last_states:
         return h, (c_last, n_last, m_last)
     return h
@@ -539,7 +603,8 @@ def mlstm_siging_chunkwise__b200(
         if n_initial is None:
             n_initial = torch.zeros(B, NH, q.shape[-1], dtype=q.dtype, device=q.device)
     h, c_last, n_last, _ = fn.apply(q, k, v, i, f, c_initial, n_initial, m_initial, bool(return_last_states),
-                                    int(chunk_size), float(eps), bool(reverse), True)
+                                    int(chunk_size), float(eps), bool(reverse), True,
+                                    _caller_grad_dtype(autocast_kernel_dtype, q, k, v, i, f))
     if return_last_states:
         return h, (c_last, n_last)
     return h

@@ -209,6 +209,17 @@ int mlstm_b200_chunkwise_bw(const mlstm_b200_bw_args* a, void* stream) {
     set_error("gate_soft_cap is applied by the tensor-core kernels only; cap the gates before an exact-route call");
     return MLSTM_B200_EUNSUPPORTED;
   }
+  const int gd = a->shape.grad_dtype;
+  if (gd != 0 && gd != a->shape.dtype) {
+    if (gd != MLSTM_B200_BF16 && gd != MLSTM_B200_F16) {
+      set_error("grad_dtype must be 0, MLSTM_B200_BF16 or MLSTM_B200_F16 (got %d)", gd);
+      return MLSTM_B200_EINVAL;
+    }
+    if (!tc) {
+      set_error("gradients in a dtype other than shape.dtype are written by the tensor-core kernels only");
+      return MLSTM_B200_EUNSUPPORTED;
+    }
+  }
   return tc ? tensor_bw(*a, (cudaStream_t)stream) : exact_bw(*a, (cudaStream_t)stream);
 }
 
@@ -277,6 +288,13 @@ int mlstm_b200_rmsnorm_bw(const mlstm_b200_rmsnorm_bw_args* a, void* stream) {
   }
   if (int e = require_device()) return e;
   return rmsnorm_bw(*a, (cudaStream_t)stream);
+}
+
+int mlstm_b200_convert16(const void* src, void* dst, int64_t n, int32_t src_dtype, int32_t dst_dtype, void* stream) {
+  g_err[0] = 0;
+  g_launches = 0;
+  if (int e = require_device()) return e;
+  return convert16(src, dst, n, src_dtype, dst_dtype, (cudaStream_t)stream);
 }
 
 }  // extern "C"

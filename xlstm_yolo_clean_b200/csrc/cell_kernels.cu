@@ -634,6 +634,81 @@ int rms_dispatch(int tx, int ty, const RmsP& p, bool backward, cudaStream_t st) 
 }
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------
+// 16-bit re-rounding pass: fp16 <-> bf16 over a contiguous buffer.  The reference kernels re-round their inputs to
+// autocast_kernel_dtype under CUDA autocast (custom_fwd(cast_inputs=bf16), native/fwbw.py:37); under ultralytics' fp16
+// AMP that is one pass over q / k / v per cell.  torch's copy_ does it with its generic unrolled elementwise kernel
+// (~3 TB/s here); this one is a plain streaming kernel: 16-byte vectors, four in flight per thread, evict-first loads
+// and stores, 4 bytes of HBM traffic per element.  Values go through fp32 (exact for both source formats), one RN
+// rounding -- bit-identical to Tensor.to().
+template <typename TS, typename TD>
+__device__ __forceinline__ uint4 convert8(uint4 v) {
+  const uint32_t in[4] = {v.x, v.y, v.z, v.w};
+  uint32_t out[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = unpack2<TS>(in[j]);
+    out[j] = pack2<TD>(f.x, f.y);
+  }
+  return make_uint4(out[0], out[1], out[2], out[3]);
+}
+
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) k_convert16(const TS* __restrict__ src, TD* __restrict__ dst, int64_t n) {
+  const int64_t nvec = n >> 3;
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < nvec; i += 4 * stride) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldcs(s4 + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) __stcs(d4 + i + u * stride, convert8<TS, TD>(v[u]));
+  }
+  for (; i < nvec; i += stride) __stcs(d4 + i, convert8<TS, TD>(__ldcs(s4 + i)));
+  // tail of fewer than 8 elements
+  const int64_t t = (nvec << 3) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) dst[t] = from_f32<TD>(to_f32<TS>(src[t]));
+}
+
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) k_convert16_scalar(const TS* __restrict__ src, TD* __restrict__ dst, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = from_f32<TD>(to_f32<TS>(src[i]));
+}
+
+template <typename TS, typename TD>
+void launch_convert16(const void* src, void* dst, int64_t n, cudaStream_t st) {
+  const int64_t per_cta = 256 * 8 * 4;
+  const int64_t want = (n + per_cta - 1) / per_cta;
+  const int grid = (int)(want < 1 ? 1 : (want > 8 * (grid_ctas() / 2) ? 8 * (grid_ctas() / 2) : want));
+  if (aligned(src, 16) && aligned(dst, 16))
+    k_convert16<TS, TD><<<grid, 256, 0, st>>>((const TS*)src, (TD*)dst, n);
+  else  // views that start inside a vector: element-wise (same values)
+    k_convert16_scalar<TS, TD><<<grid, 256, 0, st>>>((const TS*)src, (TD*)dst, n);
+}
+
+int convert16(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, cudaStream_t st) {
+  const bool ok = (src_dtype == MLSTM_B200_F16 && dst_dtype == MLSTM_B200_BF16) ||
+                  (src_dtype == MLSTM_B200_BF16 && dst_dtype == MLSTM_B200_F16);
+  if (!ok) {
+    set_error("convert16: fp16 -> bf16 or bf16 -> fp16 (got dtypes %d -> %d)", src_dtype, dst_dtype);
+    return MLSTM_B200_EUNSUPPORTED;
+  }
+  if (n < 0 || (n > 0 && (!src || !dst))) {
+    set_error("convert16: NULL buffer or negative length");
+    return MLSTM_B200_EINVAL;
+  }
+  if (n == 0) return 0;
+  if (src_dtype == MLSTM_B200_F16) launch_convert16<__half, __nv_bfloat16>(src, dst, n, st);
+  else launch_convert16<__nv_bfloat16, __half>(src, dst, n, st);
+  count_launch(1);
+  MLSTM_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 int rmsnorm_fw(const mlstm_b200_rmsnorm_args& a, cudaStream_t st) {
   if (int e = rms_check(a)) return e;
   if (!a.y) {

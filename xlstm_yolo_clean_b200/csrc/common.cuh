@@ -42,6 +42,30 @@ template <> __device__ __forceinline__ float from_f32<float>(float x) { return x
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
 template <> __device__ __forceinline__ __half from_f32<__half>(float x) { return __float2half_rn(x); }
 
+// two fp32 values <-> one 32-bit word holding two 16-bit elements (element 0 in the low half)
+template <typename T>
+__device__ __forceinline__ uint32_t pack2(float a, float b);
+template <>
+__device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+template <>
+__device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+template <typename T>
+__device__ __forceinline__ float2 unpack2(uint32_t u);
+template <>
+__device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t u) {
+  return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+}
+template <>
+__device__ __forceinline__ float2 unpack2<__half>(uint32_t u) {
+  return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
+
 // logsigmoid(x) = min(x, 0) - log1p(exp(-|x|))   (reference: F.logsigmoid, native/fw.py:261)
 __device__ __forceinline__ float logsigmoid_f32(float x) { return fminf(x, 0.f) - log1pf(expf(-fabsf(x))); }
 // sigmoid(-x)  (native/bw.py:323)
@@ -175,5 +199,6 @@ int cellout_bw(const mlstm_b200_cellout_bw_args& a, cudaStream_t st);
 size_t rmsnorm_workspace_bytes(const mlstm_b200_rmsnorm_args& a);
 int rmsnorm_fw(const mlstm_b200_rmsnorm_args& a, cudaStream_t st);
 int rmsnorm_bw(const mlstm_b200_rmsnorm_bw_args& a, cudaStream_t st);
+int convert16(const void* src, void* dst, int64_t n, int src_dtype, int dst_dtype, cudaStream_t st);
 
 }  // namespace mlstm

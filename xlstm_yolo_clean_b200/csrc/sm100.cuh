@@ -254,9 +254,13 @@ __device__ __forceinline__ uint64_t umma_desc_advance(uint64_t desc, uint32_t by
 // Instruction descriptor for kind::f16 (bf16 or fp16 inputs, fp32 accumulate).
 //   bits 4-5 D format (1 = f32), 7-9 A format, 10-12 B format (0 = f16, 1 = bf16),
 //   bit 15 A major, bit 16 B major (0 = K, 1 = MN), bits 17-22 N>>3, bits 24-28 M>>4.
-__host__ __device__ constexpr uint32_t umma_idesc(int M, int N, bool a_mn, bool b_mn, bool bf16) {
-  return (1u << 4) | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) | ((a_mn ? 1u : 0u) << 15) |
+//   A and B formats are independent: one operand may be fp16 and the other bf16 (tests/cuda/umma_probe.cu `mixed`).
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N, bool a_mn, bool b_mn, bool a_bf16, bool b_bf16) {
+  return (1u << 4) | ((a_bf16 ? 1u : 0u) << 7) | ((b_bf16 ? 1u : 0u) << 10) | ((a_mn ? 1u : 0u) << 15) |
          ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N, bool a_mn, bool b_mn, bool bf16) {
+  return umma_idesc(M, N, a_mn, b_mn, bf16, bf16);
 }
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool accum) {

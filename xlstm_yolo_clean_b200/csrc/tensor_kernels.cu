@@ -70,29 +70,6 @@ struct GateBuf {
 #define TC_PROF_CTA(which)
 #endif
 
-template <typename T>
-__device__ __forceinline__ uint32_t pack2(float a, float b);
-template <>
-__device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-template <>
-__device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
-  __half2 v = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-template <typename T>
-__device__ __forceinline__ float2 unpack2(uint32_t u);
-template <>
-__device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t u) {
-  return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
-}
-template <>
-__device__ __forceinline__ float2 unpack2<__half>(uint32_t u) {
-  return __half22float2(*reinterpret_cast<__half2*>(&u));
-}
-
 // store 32 consecutive columns (col0 multiple of 32) of row `row` of a [128][64]-subtiled,
 // 128B-swizzled 16-bit matrix; `base` points at the first subtile, subtiles are LT*128 B apart.
 template <typename T>
@@ -1346,7 +1323,7 @@ struct BwSmem {
                             cdQa = D == 64 ? 256 : 384, cdQb = cdQa + D, cddC = D == 64 ? 384 : 448;
 };
 
-template <typename T, int D, bool REV>
+template <typename T, int D, bool REV, typename TO>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
           const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdH,
@@ -1674,8 +1651,8 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
           }
         }
         const float excl = incl - own + carry;
-        T* dip = (T*)p.di + b * p.di_sb + hh * p.di_sh;
-        T* dfp = (T*)p.df + b * p.df_sb + hh * p.df_sh;
+        TO* dip = (TO*)p.di + b * p.di_sb + hh * p.di_sh;
+        TO* dfp = (TO*)p.df + b * p.df_sb + hh * p.df_sh;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int t = lane * 4 + e;
@@ -1683,14 +1660,14 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
             const float dsig = p.sig ? 1.f - __expf(gb[GateBuf::oI + t]) : 1.f;  // sigmoid(-i) = 1 - exp(logsigmoid(i))
             float gi = di[e] * dsig * gb[GateBuf::oDi + t];
             float gf = (acc[e] + excl) * sigmoid_neg_f32(gb[GateBuf::oF + t]) * gb[GateBuf::oDf + t];  // bw.py:322-323
-            T* pi = dip + (int64_t)(t0 + t) * p.di_ss;
-            T* pf = dfp + (int64_t)(t0 + t) * p.df_ss;
+            TO* pi = dip + (int64_t)(t0 + t) * p.di_ss;
+            TO* pf = dfp + (int64_t)(t0 + t) * p.df_ss;
             if (p.acc_g) {  // (the block problems of one call run one after the other on the stream)
-              gi += to_f32<T>(*pi);
-              gf += to_f32<T>(*pf);
+              gi += to_f32<TO>(*pi);
+              gf += to_f32<TO>(*pf);
             }
-            *pi = from_f32<T>(gi);
-            *pf = from_f32<T>(gf);
+            *pi = from_f32<TO>(gi);
+            *pf = from_f32<TO>(gf);
           }
         }
         carry += __shfl_sync(0xffffffffu, incl, REV ? 31 : 0);
@@ -1837,7 +1814,7 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
           dot += kv.x * o[2 * j] + kv.y * o[2 * j + 1];
         }
         mbar_wait(&bar_st, par, 19);  // staging buffers free (the previous tile's stores have read them)
-        store_cols<T, D>(sdK, row, ch * CW, o);
+        store_cols<TO, D>(sdK, row, ch * CW, o);
         spart[(1 * 2 + ch) * LT + row] = dot;
         // dq
         mbar_wait(&bar_q, par, 16);
@@ -1855,7 +1832,7 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
           float2 qv = unpack2<T>(qs[j]);
           dot += qv.x * o[2 * j] + qv.y * o[2 * j + 1];
         }
-        store_cols<T, D>(sdQ, row, ch * CW, o);
+        store_cols<TO, D>(sdQ, row, ch * CW, o);
         spart[(0 * 2 + ch) * LT + row] = dot;
       }
       // ---- dC_{k-1} = gbar dC_k + ddC ----------------------------------------------------------------
@@ -1890,7 +1867,7 @@ tc_bw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
           float2 vv = unpack2<T>(vs[j]);
           dot += vv.x * o[2 * j] + vv.y * o[2 * j + 1];
         }
-        store_cols<T, D>(sdV, row, ch * CW, o);
+        store_cols<TO, D>(sdV, row, ch * CW, o);
         spart[(2 * 2 + ch) * LT + row] = dot;
       }
       fence_proxy_async_smem();
@@ -1997,12 +1974,12 @@ int launch_fw_d128(const TcFwParams& p, const CUtensorMap& mq, const CUtensorMap
   return 0;
 }
 
-template <typename T, int D>
+template <typename T, int D, typename TO = T>
 int launch_bw(const TcBwParams& p, const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv,
               const CUtensorMap& mdh, const CUtensorMap& mcs, const CUtensorMap& mdq, const CUtensorMap& mdk,
               const CUtensorMap& mdv, cudaStream_t st) {
   using SM = BwSmem<D>;
-  auto kern = p.rev ? tc_bw<T, D, true> : tc_bw<T, D, false>;
+  auto kern = p.rev ? tc_bw<T, D, true, TO> : tc_bw<T, D, false, TO>;
   MLSTM_CUDA_CHECK(ensure_smem(kern, SM::kBytes));
   MLSTM_CUDA_CHECK(launch_pdl(pdl_mode() == 1, kern, p.B * p.NH, kTcThreads, SM::kBytes, st, mq, mk, mv, mdh, mcs, mdq, mdk, mdv, p));
   MLSTM_CUDA_CHECK(cudaGetLastError());
@@ -2328,9 +2305,12 @@ int run_bw(const mlstm_b200_bw_args& a, const void* c_states, int block, cudaStr
   const mlstm_b200_shape& s = a.shape;
   CUtensorMap mq, mk, mv, mdh, mcs, mdq, mdk, mdv;
   const int D = s.DHQK;
+  mlstm_b200_shape sg = s;  // the gradients' tensor maps carry THEIR dtype (it matters for the reduce-add stores)
+  if (s.grad_dtype) sg.dtype = s.grad_dtype;
+  const bool mixed = sg.dtype != s.dtype;
   int r = make_map(&mq, a.q, s, D) | make_map(&mk, a.k, s, D) | make_map(&mv, a.v, s, D) | make_map(&mdh, a.dh, s, D) |
           (block < 0 ? make_states_map(&mcs, c_states, s) : make_states_map_blocks(&mcs, c_states, s)) |
-          make_map(&mdq, a.dq, s, D) | make_map(&mdk, a.dk, s, D) | make_map(&mdv, a.dv, s, D);
+          make_map(&mdq, a.dq, sg, D) | make_map(&mdk, a.dk, sg, D) | make_map(&mdv, a.dv, sg, D);
   if (r) {
     set_error("cuTensorMapEncodeTiled failed (%d)", r);
     return MLSTM_B200_ENODEVICE;
@@ -2354,7 +2334,14 @@ int run_bw(const mlstm_b200_bw_args& a, const void* c_states, int block, cudaStr
   p.cs_off = block < 0 ? 0 : 64 * block;
   TC_SET_PROF(p, 4096);
   int e;
-  if (s.DHQK == 32)
+  if (mixed) {  // kernel operands in one 16-bit dtype, gradients rounded once from fp32 to the other
+    if (s.DHQK == 32)
+      e = s.dtype == MLSTM_B200_BF16 ? launch_bw<__nv_bfloat16, 32, __half>(p, mq, mk, mv, mdh, mcs, mdq, mdk, mdv, st)
+                                     : launch_bw<__half, 32, __nv_bfloat16>(p, mq, mk, mv, mdh, mcs, mdq, mdk, mdv, st);
+    else
+      e = s.dtype == MLSTM_B200_BF16 ? launch_bw<__nv_bfloat16, 64, __half>(p, mq, mk, mv, mdh, mcs, mdq, mdk, mdv, st)
+                                     : launch_bw<__half, 64, __nv_bfloat16>(p, mq, mk, mv, mdh, mcs, mdq, mdk, mdv, st);
+  } else if (s.DHQK == 32)
     e = s.dtype == MLSTM_B200_BF16 ? launch_bw<__nv_bfloat16, 32>(p, mq, mk, mv, mdh, mcs, mdq, mdk, mdv, st)
                                    : launch_bw<__half, 32>(p, mq, mk, mv, mdh, mcs, mdq, mdk, mdv, st);
   else

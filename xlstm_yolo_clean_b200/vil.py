@@ -184,6 +184,19 @@ def rms_norm_b200(x, weight=None, eps=1e-6, out_dtype=None):
     return _RmsNorm.apply(x, weight, eps, out_dtype)
 
 
+def _grad_dtype(in_dtypes, v_k, NH):
+    """dtype the backward kernel writes d_qk / d_v / d_gates in: the dtype the layer's tensors had before they were
+    re-rounded to the kernel dtype (fp16 under ultralytics' AMP with the bf16 kernels) when the tensor-core route runs
+    and the three agree -- ``shape.grad_dtype`` of the C-ABI -- else the kernel dtype (and a cast afterwards)."""
+    kdt, dt = v_k.dtype, in_dtypes[0]
+    S, D = v_k.shape[1], v_k.shape[2] // NH
+    if (dt is not kdt and dt in (torch.float16, torch.bfloat16) and kdt in (torch.float16, torch.bfloat16)
+            and all(t is dt for t in in_dtypes) and D in (32, 64, 128) and S % 4 == 0
+            and _backend._default_impl != _cabi.IMPL_EXACT):
+        return dt
+    return kdt
+
+
 def _heads(qk, v, gates, NH):
     """(B, NH, S, D) / (B, NH, S) views of the layer-layout tensors: no data movement."""
     B, S, H = v.shape
@@ -205,7 +218,7 @@ class _MlstmLayerLayout(torch.autograd.Function):
     def forward(ctx, qk, v, gates, NH, reverse, siging, chunk_size, eps, kernel_dtype, soft_cap=0.0):
         B, S, H = v.shape
         ctx.in_dtypes = (qk.dtype, v.dtype, gates.dtype)
-        qk_k, v_k, g_k = (t if t.dtype == kernel_dtype else t.to(kernel_dtype) for t in (qk, v, gates))
+        qk_k, v_k, g_k = (_backend.convert16(t, kernel_dtype) for t in (qk, v, gates))  # (fp32 inputs: torch's cast)
         if S % chunk_size and kernel_dtype in (torch.float16, torch.bfloat16):
             # The tcgen05 kernels walk 128-token tiles whatever the chunk size is and handle a ragged last tile
             # themselves (the result does not depend on chunk_size: the stabiliser equals the step-recurrent one),
@@ -235,7 +248,8 @@ class _MlstmLayerLayout(torch.autograd.Function):
         NH, reverse, siging, chunk_size, eps, pad, S, soft_cap = ctx.cfg
         if pad:
             dh = F.pad(dh, (0, 0, pad, 0) if reverse else (0, 0, 0, pad))
-        d_qk, d_v, d_g = torch.empty_like(qk_k), torch.empty_like(v_k), torch.empty_like(g_k)
+        gdt = _grad_dtype(ctx.in_dtypes, v_k, NH)  # the caller's 16-bit dtype: no cast pass over the gradients
+        d_qk, d_v, d_g = (torch.empty_like(t, dtype=gdt) for t in (qk_k, v_k, g_k))
         q, k, vv, i, f = _heads(qk_k, v_k, g_k, NH)
         mlstm_chunkwise_bw(q, k, vv, i, f, n_out, m_out, dh, chunk_size=chunk_size, eps=eps, c_states=c_states,
                            reverse=reverse, siging=siging, out=_heads(d_qk, d_v, d_g, NH), gate_soft_cap=soft_cap)
@@ -288,7 +302,7 @@ class _MlstmCellFused(torch.autograd.Function):
         B, S, H = v.shape
         D = H // NH
         ctx.in_dtypes = (qk.dtype, v.dtype, gates.dtype)
-        qk_k, v_k, g_k = (t if t.dtype == kernel_dtype else t.to(kernel_dtype) for t in (qk, v, gates))
+        qk_k, v_k, g_k = (_backend.convert16(t, kernel_dtype) for t in (qk, v, gates))  # (fp32 inputs: torch's cast)
         if S % chunk_size:
             chunk_size = math.gcd(S, chunk_size)  # any S % 4 == 0 runs unpadded (see _MlstmLayerLayout)
         q, k, vv, i, f = _heads(qk_k, v_k, g_k, NH)
@@ -313,7 +327,8 @@ class _MlstmCellFused(torch.autograd.Function):
         NH, reverse, siging, chunk_size, eps, soft_cap, ln_eps, out_dtype = ctx.cfg
         dh, dpar, dx = _cellout_bw_call(h, xs, weight, skip if xs is not None else None, dy, ln_eps, out_dtype,
                                         ctx.needs_input_grad[3])
-        d_qk, d_v, d_g = torch.empty_like(qk_k), torch.empty_like(v_k), torch.empty_like(g_k)
+        gdt = _grad_dtype(ctx.in_dtypes, v_k, NH)  # the caller's 16-bit dtype: no cast pass over the gradients
+        d_qk, d_v, d_g = (torch.empty_like(t, dtype=gdt) for t in (qk_k, v_k, g_k))
         q, k, vv, i, f = _heads(qk_k, v_k, g_k, NH)
         nmp = nm.data_ptr()
         _backend._bw_launch(q, k, vv, i, f, nmp, nmp + nm.stride(0) * 4, dh, None, None, None, None, None, chunk_size, eps, None,
