@@ -319,51 +319,72 @@ __device__ __forceinline__ uint32_t pack2_rt(float a, float b, bool f16) {
   return f16 ? pack2<__half>(a, b) : pack2<__nv_bfloat16>(a, b);
 }
 
+// L2 prefetch of `n_rows` rows of ROW_BYTES bytes (16-bit elements, `stride` elements apart) by one warp
+template <int ROW_BYTES>
+__device__ __forceinline__ void prefetch_rows_l2(const uint16_t* base, int64_t stride, int row0, int n_rows, int lane) {
+  constexpr int LINES = (ROW_BYTES + 127) / 128;
+  for (int r = lane; r < n_rows; r += 32) {
+    const char* ptr = reinterpret_cast<const char*>(base + (int64_t)(row0 + r) * stride);
+#pragma unroll
+    for (int l = 0; l < LINES; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr + l * 128));
+  }
+}
+
 // Fused cell-output epilogue for one thread's slice of a staged h tile: row `row`, NC columns from `col0` of a
 // [128][64]-subtiled (D = 128) or plain (D = 64 / 32) swizzled tile that already holds h rounded to the kernel dtype T.
-// The two threads that share a row (column halves, warps w and w + 4) exchange partial sums through `sstat` and a
-// 64-thread named barrier: mean first, then the centred sum of squares (two-pass variance like the stand-alone
-// kernel).  The slice is then overwritten in place with y = (h - mean) rstd w + b + skip x in the y dtype.
+// Each thread takes mean and centred sum of squares of ITS NC values (two passes over its own slice, no
+// synchronisation); the two threads that share a row (column halves, warps w and w + 4) then exchange (mean, M2) once
+// through `sstat` and a 64-thread named barrier and combine them exactly (Chan et al.: M2 = M2_a + M2_b +
+// (mean_a - mean_b)^2 NC / 2) -- the same two-pass variance as the stand-alone kernel with one hand-off instead of
+// three.  The skip input's row is requested from global memory before any of that (the scan warp pulled it into L2 a
+// tile earlier), so its latency hides under the statistics.  The slice is then overwritten in place with
+// y = (h - mean) rstd w + b + skip x in the y dtype.  (sstat is reused by the next tile only after every worker has
+// passed that tile's control-warp barriers, so one barrier per tile is enough.)
 template <typename T, int D, int NC, typename SwzFn>
 __device__ __forceinline__ void ln_epilogue_slice(uint8_t* tile_slice_base, SwzFn swz, int row, int col0, int ch, int pair_bar,
                                                   float* sstat, const float* spar, const void* xrow, bool xy_f16, float ln_eps,
                                                   bool row_valid) {
-  // spar: [3][D] = weight, bias, skip of this head; sstat: [2][LT] partial sums by column half
+  // spar: [3][D] = weight, bias, skip of this head; sstat: [2][LT] means, [2][LT] centred sums of squares, by column half
+  constexpr int NV = NC / 8;        // 16-byte vectors in the slice
+  constexpr int XE = NV < 4 ? NV : 4;  // skip-input vectors requested up front (the rest while the first are consumed)
+  const uint4* xp = (xrow && row_valid) ? reinterpret_cast<const uint4*>(xrow) : nullptr;
+  uint4 xe[XE];
+#pragma unroll
+  for (int j = 0; j < XE; ++j) xe[j] = xp ? __ldg(xp + j) : make_uint4(0u, 0u, 0u, 0u);
   float s1 = 0.f;
 #pragma unroll
-  for (int j = 0; j < NC / 8; ++j) {
+  for (int j = 0; j < NV; ++j) {
     const uint4 u = *reinterpret_cast<const uint4*>(tile_slice_base + swz(row, col0 + 8 * j));
     const float2 a0 = unpack2<T>(u.x), a1 = unpack2<T>(u.y), a2 = unpack2<T>(u.z), a3 = unpack2<T>(u.w);
     s1 += ((a0.x + a0.y) + (a1.x + a1.y)) + ((a2.x + a2.y) + (a3.x + a3.y));
   }
-  sstat[ch * LT + row] = s1;
-  named_sync(pair_bar, 64);
-  const float mean = (sstat[row] + sstat[LT + row]) * (1.f / D);
+  const float mean_a = s1 * (1.f / NC);
   float s2 = 0.f;
 #pragma unroll
-  for (int j = 0; j < NC / 8; ++j) {
+  for (int j = 0; j < NV; ++j) {
     const uint4 u = *reinterpret_cast<const uint4*>(tile_slice_base + swz(row, col0 + 8 * j));
     const float2 a0 = unpack2<T>(u.x), a1 = unpack2<T>(u.y), a2 = unpack2<T>(u.z), a3 = unpack2<T>(u.w);
-    const float d0 = a0.x - mean, d1 = a0.y - mean, d2 = a1.x - mean, d3 = a1.y - mean, d4 = a2.x - mean, d5 = a2.y - mean,
-                d6 = a3.x - mean, d7 = a3.y - mean;
+    const float d0 = a0.x - mean_a, d1 = a0.y - mean_a, d2 = a1.x - mean_a, d3 = a1.y - mean_a, d4 = a2.x - mean_a,
+                d5 = a2.y - mean_a, d6 = a3.x - mean_a, d7 = a3.y - mean_a;
     s2 += ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3)) + ((d4 * d4 + d5 * d5) + (d6 * d6 + d7 * d7));
   }
-  named_sync(pair_bar, 64);  // both threads have read the means' partial sums
+  sstat[ch * LT + row] = mean_a;
   sstat[2 * LT + ch * LT + row] = s2;
   named_sync(pair_bar, 64);
-  const float rstd = rsqrtf((sstat[2 * LT + row] + sstat[3 * LT + row]) * (1.f / D) + ln_eps);
-  const uint4* xp = reinterpret_cast<const uint4*>(xrow);
+  const float mean_b = sstat[(ch ^ 1) * LT + row], s2_b = sstat[2 * LT + (ch ^ 1) * LT + row];
+  const float mean = 0.5f * (mean_a + mean_b), dm = mean_a - mean_b;
+  // (symmetric in a / b: both threads of the row get bit-identical statistics)
+  const float rstd = rsqrtf(((s2 + s2_b) + dm * dm * (0.5f * NC)) * (1.f / D) + ln_eps);
 #pragma unroll
-  for (int j = 0; j < NC / 8; ++j) {
+  for (int j = 0; j < NV; ++j) {
     uint4* slot = reinterpret_cast<uint4*>(tile_slice_base + swz(row, col0 + 8 * j));
     const uint4 u = *slot;
     const float2 a[4] = {unpack2<T>(u.x), unpack2<T>(u.y), unpack2<T>(u.z), unpack2<T>(u.w)};
-    float xv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (xp && row_valid) {
-      const uint4 xu = xp[j];
-      const float2 x0 = unpack2_rt(xu.x, xy_f16), x1 = unpack2_rt(xu.y, xy_f16), x2 = unpack2_rt(xu.z, xy_f16), x3 = unpack2_rt(xu.w, xy_f16);
-      xv[0] = x0.x; xv[1] = x0.y; xv[2] = x1.x; xv[3] = x1.y; xv[4] = x2.x; xv[5] = x2.y; xv[6] = x3.x; xv[7] = x3.y;
-    }
+    uint4 xu;
+    if (j < XE) xu = xe[j];
+    else xu = xp ? __ldg(xp + j) : make_uint4(0u, 0u, 0u, 0u);
+    const float2 x0 = unpack2_rt(xu.x, xy_f16), x1 = unpack2_rt(xu.y, xy_f16), x2 = unpack2_rt(xu.z, xy_f16), x3 = unpack2_rt(xu.w, xy_f16);
+    const float xv[8] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y, x3.x, x3.y};
     float o[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -668,8 +689,11 @@ tc_fw(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensor
       const int t1 = mt(c) * LT;
       return load_gate_raw<T>(ip + (int64_t)t1 * p.ig_ss, p.ig_ss, fp + (int64_t)t1 * p.fg_ss, p.fg_ss, min(LT, p.S - t1));
     };
+    // skip-input rows of this head (fused epilogue): pulled into L2 two tiles before the workers read them
+    const uint16_t* xbase = p.x ? (const uint16_t*)p.x + b * p.x_sb + hh * p.x_sh : nullptr;
     GateRaw<T> raw = raw_of(0);
     for (int n = 0; n < p.NT; ++n) {  // vectors of tile n; tiles 0 and 1 need no buffer hand-back
+      if (p.epi && p.x) prefetch_rows_l2<D * 2>(xbase, p.x_ss, mt(n) * LT, min(LT, p.S - mt(n) * LT), lane);
       if (n >= 2) named_sync(NB_C, kNbC);  // every worker is done with tile n-2: its gate buffer can be reused
       gate_scan_regs(fsm + SM::fGates + (n & 1) * GateBuf::kFloats, raw, REV, p.sig != 0, p.cap);
       __syncwarp();
@@ -1065,8 +1089,11 @@ tc_fw_d128(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUt
       const int t1 = mt(c) * LT;
       return load_gate_raw<T>(ip + (int64_t)t1 * p.ig_ss, p.ig_ss, fp + (int64_t)t1 * p.fg_ss, p.fg_ss, min(LT, p.S - t1));
     };
+    // skip-input rows of this head (fused epilogue): pulled into L2 two tiles before the workers read them
+    const uint16_t* xbase = p.x ? (const uint16_t*)p.x + b * p.x_sb + hh * p.x_sh : nullptr;
     GateRaw<T> raw = raw_of(0);
     for (int n = 0; n < p.NT; ++n) {
+      if (p.epi && p.x) prefetch_rows_l2<D * 2>(xbase, p.x_ss, mt(n) * LT, min(LT, p.S - mt(n) * LT), lane);
       if (n >= 2) named_sync(NB_C, kNbC);
       gate_scan_regs(fsm + SM::fGates + (n & 1) * GateBuf::kFloats, raw, REV, p.sig != 0, p.cap);
       __syncwarp();

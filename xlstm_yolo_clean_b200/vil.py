@@ -372,7 +372,7 @@ def _gate_preact(cell, q, k, v, qk=None):
 
 
 def mlstm_cell_b200(cell, q, k, v, reverse=False, skip=None, x_skip=None, siging=False, chunk_size=64, eps=1e-6,
-                    kernel_dtype="bfloat16", qk=None):
+                    kernel_dtype="bfloat16", qk=None, one_launch="auto"):
     """MatrixLSTMCell.forward (vision_lstm2.py:701-753) on the B200 kernels, output stage fused.
 
     q, k, v (B, S, H) -> (B, S, H).  ``reverse`` runs the anti-causal scan; ``skip`` / ``x_skip`` add
@@ -381,7 +381,10 @@ def mlstm_cell_b200(cell, q, k, v, reverse=False, skip=None, x_skip=None, siging
     (kernel_wrappers.py:214-217; SURVEY.md finding 3).  ``kernel_dtype="input"`` is an opt-in deviation: 16-bit
     inputs go to the kernel as they are (fp16 under ultralytics' AMP) instead of being re-rounded to bf16, which
     drops five cast passes forward and five backward; the result is closer to the fp32 function, not identical
-    to the reference's bf16 one."""
+    to the reference's bf16 one.  ``one_launch``: "auto" | "always" | "never" -- when the cell runs as ONE forward launch
+    (fused LayerNorm / skip epilogue); see below."""
+    if one_launch not in ("auto", "always", "never"):
+        raise ValueError(f"one_launch must be 'auto', 'always' or 'never' (got {one_launch!r})")
     B, S, H = q.shape
     if not q.is_cuda:
         raise RuntimeError("mlstm_cell_b200: tensors are on the CPU; this backend has no CPU path")
@@ -404,9 +407,16 @@ def mlstm_cell_b200(cell, q, k, v, reverse=False, skip=None, x_skip=None, siging
             qk_c, v_c, g_c = (t.to(cell.autocast_dtype) for t in (qk_c, v_c, g_c))
         norm = cell.outnorm
         out_dtype = torch.get_autocast_dtype("cuda") if autocast_on else model_dtype
-        if (in_kernel_cap and S % 4 == 0 and out_dtype in (torch.float16, torch.bfloat16) and cellout_supported(NH, D)
-                and (x_skip is None or x_skip.shape == (B, S, H))):
-            # everything in one launch: the kernel's epilogue normalises, relayouts and adds the skip (_MlstmCellFused)
+        # One launch for the whole cell (_MlstmCellFused: the kernel's epilogue normalises, relayouts and adds the skip)
+        # where that is the faster composition -- measured on B200: without gradients at head
+        # dims 32 / 64 (h never reaches HBM: 334 vs 397 us at 256 heads x 6400 x 64).  In training h has to be written
+        # as well (the LayerNorm backward reads it) and at head dim 128 the epilogue holds 64 columns per thread; there
+        # the mLSTM kernel followed by the stand-alone cell-output pass is faster (408 vs 428 us; 327 vs 352 us).
+        needs_grad = torch.is_grad_enabled() and any(
+            t is not None and t.requires_grad for t in (qk_c, v_c, g_c, x_skip, norm.weight_proxy, norm.bias, skip))
+        fuse = one_launch == "always" or (one_launch == "auto" and not needs_grad and D in (32, 64))
+        if (fuse and in_kernel_cap and S % 4 == 0 and out_dtype in (torch.float16, torch.bfloat16)
+                and cellout_supported(NH, D) and (x_skip is None or x_skip.shape == (B, S, H))):
             return _MlstmCellFused.apply(qk_c, v_c, g_c, x_skip if skip is not None else None, norm.weight_proxy, norm.bias,
                                          skip, NH, bool(reverse), bool(siging), int(chunk_size), float(eps), kdt,
                                          float(cell.gate_soft_cap), float(norm.eps), out_dtype)
@@ -436,7 +446,7 @@ def mlstm_cell_b200(cell, q, k, v, reverse=False, skip=None, x_skip=None, siging
     return cell_out(h, norm.weight_proxy, norm.bias, skip, x_skip, eps=norm.eps, out_dtype=out_dtype)
 
 
-def mlstm_branch_b200(layer, x, siging=False, kernel_dtype="bfloat16"):
+def mlstm_branch_b200(layer, x, siging=False, kernel_dtype="bfloat16", one_launch="auto"):
     """ViLLayer.mlstm_branch (vision_lstm2.py:292-312) without flips and with the fused cell output."""
     rev = _is_reverse(layer)
     x_inner = layer.proj_up(x)
@@ -449,13 +459,13 @@ def mlstm_branch_b200(layer, x, siging=False, kernel_dtype="bfloat16"):
     q, k = torch.chunk(qk, 2, dim=-1)
     v = layer.v_proj(x_v)
     y = mlstm_cell_b200(layer.mlstm_cell, q, k, v, reverse=rev, skip=layer.learnable_skip, x_skip=x_act, siging=siging,
-                        kernel_dtype=kernel_dtype, qk=qk)
+                        kernel_dtype=kernel_dtype, qk=qk, one_launch=one_launch)
     return layer.proj_down(y)
 
 
-def _branch_entry(layer, x, siging=False, kernel_dtype="bfloat16"):
+def _branch_entry(layer, x, siging=False, kernel_dtype="bfloat16", one_launch="auto"):
     """What ``patch_layers`` binds as ``layer.mlstm_branch`` (module-level, so that a patched model pickles)."""
-    return mlstm_branch_b200(layer, x, siging=siging, kernel_dtype=kernel_dtype)
+    return mlstm_branch_b200(layer, x, siging=siging, kernel_dtype=kernel_dtype, one_launch=one_launch)
 
 
 def _norm_entry(norm, x):
@@ -465,7 +475,7 @@ def _norm_entry(norm, x):
     return torch.nn.RMSNorm.forward(norm, x)
 
 
-def patch_layers(model: torch.nn.Module, siging=None, kernel_dtype: str = "bfloat16") -> int:
+def patch_layers(model: torch.nn.Module, siging=None, kernel_dtype: str = "bfloat16", one_launch: str = "auto") -> int:
     """Rebind ``mlstm_branch`` of every ViLLayer-shaped module (``proj_up``, ``qk_proj``, ``v_proj``, ``mlstm_cell``,
     ``learnable_skip``, ``proj_down``; vision_lstm2.py:218-290) whose head geometry the fused output kernel covers to
     ``mlstm_branch_b200``.  Parameters and state-dict keys are untouched.  Returns the number of layers rebound.
@@ -486,7 +496,7 @@ def patch_layers(model: torch.nn.Module, siging=None, kernel_dtype: str = "bfloa
         if not cellout_supported(cell.num_heads, cell.dim // cell.num_heads):
             continue
         sig = _cell_uses_siging(cell) if siging is None else bool(siging)
-        mod.mlstm_branch = functools.partial(_branch_entry, mod, siging=sig, kernel_dtype=kernel_dtype)
+        mod.mlstm_branch = functools.partial(_branch_entry, mod, siging=sig, kernel_dtype=kernel_dtype, one_launch=one_launch)
         for norm in (getattr(mod, "norm", None), getattr(mod, "ffn_norm", None)):  # the RMSNorms in front of the branches
             if (isinstance(norm, torch.nn.RMSNorm) and len(norm.normalized_shape) == 1
                     and norm.normalized_shape[0] in RMSNORM_DIMS):
