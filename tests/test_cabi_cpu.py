@@ -221,8 +221,28 @@ def test_patched_model_survives_deepcopy_and_torch_save(tmp_path):
         layer = m[0]
         assert "mlstm_branch" in layer.__dict__ and "forward" in layer.norm.__dict__
         assert layer.mlstm_branch.args[0] is layer and layer.norm.forward.args[0] is layer.norm  # re-bound to the copy
-        assert layer.mlstm_branch.keywords == {"siging": True, "kernel_dtype": "bfloat16"}
+        assert layer.mlstm_branch.keywords == {"siging": True, "kernel_dtype": "bfloat16", "one_launch": "auto"}
         x = torch.randn(2, 9, 256, dtype=layer.norm.weight.dtype)
         assert torch.allclose(layer.norm(x), torch.nn.functional.rms_norm(x, (256,), layer.norm.weight, 1e-6))
         with pytest.raises(RuntimeError, match="no CPU path"):
             layer.mlstm_branch(torch.randn(1, 16, 128, dtype=layer.norm.weight.dtype))
+
+
+def test_graphed_patch_survives_deepcopy_and_torch_save(tmp_path):
+    """patch_layers(graphs=True) binds a vil._GraphedBranch: it pickles without its CUDA graphs and stays bound to the
+    copy it travels with."""
+    import copy
+
+    import xlstm_yolo_clean_b200 as pkg
+
+    model = torch.nn.Sequential(_PLayer(), torch.nn.Linear(4, 4))
+    assert pkg.patch_layers(model, graphs=True) == 1
+    model[0].mlstm_branch._graphs["sentinel"] = object()  # stands for a built graph
+    path = tmp_path / "last.pt"
+    torch.save({"model": copy.deepcopy(model).half()}, path)
+    loaded = torch.load(path, weights_only=False)["model"]
+    for m in (copy.deepcopy(model), loaded):
+        br = m[0].mlstm_branch
+        assert br.layer is m[0] and br._graphs == {} and br.cfg[1:] == ("bfloat16", "auto")
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            br(torch.randn(1, 16, 128, dtype=m[0].norm.weight.dtype))

@@ -423,3 +423,98 @@ def test_convert16_is_bit_identical_to_torch(pkg, src, dst):
     sliced = perm[:, :, :8]  # not dense: torch's path
     assert torch.equal(pkg.convert16(sliced, dst), sliced.to(dst))
     assert pkg.convert16(base, src) is base
+
+
+@pytest.mark.parametrize("S,reverse", [(400, False), (100, True)])
+def test_graphed_branch_is_bit_identical_to_eager_over_optimizer_steps(pkg, S, reverse):
+    """patch_layers(graphs=True): the branch's forward / backward replay as CUDA graphs (vil._GraphedBranch).  Same
+    kernels on the live parameters: losses, input gradients and the parameters after every SGD step equal the eager
+    branch's bit for bit -- in particular the fp16 weight copies of the autocast rule are re-made on every replay."""
+    import copy
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    side = int(S ** 0.5)
+    eager = _Layer(128, 4, _Dir("ROWWISE_FROM_BOT_RIGHT" if reverse else "ROWWISE_FROM_TOP_LEFT")).to(dev)
+    eager.conv.seqlens = [side, side]
+    graphed = copy.deepcopy(eager)
+    graphed.conv.seqlens = [side, side]
+    assert pkg.patch_layers(eager) == 1 and pkg.patch_layers(graphed, graphs=True) == 1
+    opts = [torch.optim.SGD(m.parameters(), lr=0.05) for m in (eager, graphed)]
+    for it in range(4):
+        x = torch.randn(8, S, 128, device=dev).half()
+        res = []
+        for m, opt in zip((eager, graphed), opts):
+            xi = x.clone().requires_grad_(True)
+            opt.zero_grad()
+            with torch.autocast("cuda", dtype=torch.float16):
+                y = m.mlstm_branch(xi)
+            loss = (y.float() ** 2).mean()
+            loss.backward()
+            opt.step()
+            res.append((loss.detach(), xi.grad))
+        assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]), it
+        for a, b in zip(eager.parameters(), graphed.parameters()):
+            assert torch.equal(a, b), it
+    assert len(graphed.mlstm_branch._graphs) == 1
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):  # no gradients: eager path, same function
+        assert torch.equal(graphed.mlstm_branch(x), eager.mlstm_branch(x))
+    clone = copy.deepcopy(graphed)  # graphs do not travel with copies; the copy builds its own
+    assert clone.mlstm_branch._graphs == {} and clone.mlstm_branch.layer is clone
+
+
+class _NoDrop(torch.nn.Module):
+    drop_prob = 0.0
+
+
+class _FullLayer(_Layer):
+    """_Layer plus what ViLLayer.forward wraps around the branch (vision_lstm2.py:331-341)."""
+
+    def __init__(self, dim, NH, direction):
+        super().__init__(dim, NH, direction)
+        self.ffn_norm = torch.nn.RMSNorm(dim, eps=1e-6)
+        self.ffn = torch.nn.Sequential(torch.nn.Linear(dim, 2 * dim), torch.nn.GELU(), torch.nn.Linear(2 * dim, dim))
+        self.drop_path = _NoDrop()
+
+    def mlstm_branch(self, x):  # replaced by patch_layers
+        raise AssertionError("unpatched")
+
+    def forward(self, x):
+        x = x + self.mlstm_branch(self.norm(x))
+        return x + self.ffn(self.ffn_norm(x))
+
+
+def test_graphed_whole_layer_is_bit_identical_to_eager_over_optimizer_steps(pkg):
+    """patch_layers(graphs=True) on a full ViLLayer-shaped module: norm -> fused branch -> residual -> ffn_norm -> ffn ->
+    residual replay as one forward and one backward CUDA graph (vil._GraphedLayer); bit-identical training."""
+    import copy
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(4)
+    eager = _FullLayer(256, 8, _Dir("ROWWISE_FROM_BOT_RIGHT")).to(dev)
+    eager.conv.seqlens = [20, 20]
+    graphed = copy.deepcopy(eager)
+    graphed.conv.seqlens = [20, 20]
+    assert pkg.patch_layers(eager) == 1 and pkg.patch_layers(graphed, graphs=True) == 1
+    assert "forward" in graphed.__dict__ and "forward" not in eager.__dict__
+    opts = [torch.optim.SGD(m.parameters(), lr=0.05) for m in (eager, graphed)]
+    for it in range(3):
+        x = torch.randn(4, 400, 256, device=dev)
+        res = []
+        for m, opt in zip((eager, graphed), opts):
+            xi = x.clone().requires_grad_(True)
+            opt.zero_grad()
+            with torch.autocast("cuda", dtype=torch.float16):
+                y = m(xi)
+            loss = (y.float() ** 2).mean()
+            loss.backward()
+            opt.step()
+            res.append((loss.detach(), xi.grad))
+        assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]), it
+        for a, b in zip(eager.parameters(), graphed.parameters()):
+            assert torch.equal(a, b), it
+    assert len(graphed.forward._graphs) == 1
+    graphed.drop_path.drop_prob = 0.1  # stochastic depth selects samples by value: eager
+    with torch.autocast("cuda", dtype=torch.float16):
+        graphed(x.clone().requires_grad_(True))
+    assert len(graphed.forward._graphs) == 1

@@ -157,7 +157,7 @@ def _set_backend(model, name):
         return len(cells)
     return pkg.patch_model(model, siging="siging" in name, fused="_fused" in name,
                            kernel_dtype="input" if "_fp16" in name else "bfloat16",
-                           keep_activations=name.endswith("_keep"))
+                           keep_activations="_keep" in name, graphs="_graphs" in name)
 
 
 class _MlstmTimer:

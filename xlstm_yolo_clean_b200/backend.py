@@ -695,7 +695,7 @@ def _cell_uses_siging(cell) -> bool:
 
 def patch_model(model: torch.nn.Module, name: str = KERNEL_NAME, mode: str = "train_with_padding",
                 siging: Optional[bool] = None, fused: bool = False, kernel_dtype: str = "bfloat16",
-                keep_activations: bool = False) -> int:
+                keep_activations: bool = False, graphs: bool = False) -> int:
     """Point ``gpu_backend`` of every MatrixLSTMCell (vision_lstm2.py:685-697) at the B200 kernel.
 
     ``siging=None`` (default) keeps the FUNCTION each cell computes on CUDA: a cell whose ``gpu_backend`` is a
@@ -712,6 +712,8 @@ def patch_model(model: torch.nn.Module, name: str = KERNEL_NAME, mode: str = "tr
     ``keep_activations=True`` raises ``ViLBlockPair.ckpt_thresh`` (vision_lstm2.py:1030, 1071-1078) so that the
     two S=6400 block pairs stop re-running their forward inside the backward: the reference checkpoints them to
     fit 40-80 GB parts; a B=32 base256 step peaks at ~22 GB of the B200's 180 GB with checkpointing on.
+    ``graphs=True`` (with ``fused=True``): the fused branches replay as CUDA graphs in training
+    (``vil._GraphedBranch``: a step of the patched model is otherwise bound by the host's launch rate).
     Returns the number of cells patched.
     """
     from mlstm_kernels.torch.backend_module import mLSTMBackend, mLSTMBackendConfig
@@ -734,5 +736,5 @@ def patch_model(model: torch.nn.Module, name: str = KERNEL_NAME, mode: str = "tr
     if fused:
         from . import vil
 
-        vil.patch_layers(model, siging=siging, kernel_dtype=kernel_dtype)
+        vil.patch_layers(model, siging=siging, kernel_dtype=kernel_dtype, graphs=graphs)
     return n

@@ -475,7 +475,137 @@ def _norm_entry(norm, x):
     return torch.nn.RMSNorm.forward(norm, x)
 
 
-def patch_layers(model: torch.nn.Module, siging=None, kernel_dtype: str = "bfloat16", one_launch: str = "auto") -> int:
+class _BranchModule(torch.nn.Module):
+    """The sub-modules and the parameter ``mlstm_branch_b200`` reads, re-registered (shared, not copied) under one
+    parent so that ``torch.cuda.make_graphed_callables`` sees exactly the parameters of the branch."""
+
+    def __init__(self, layer, siging, kernel_dtype, one_launch, amp_dtype):
+        super().__init__()
+        for name in ("proj_up", "conv", "qk_proj", "v_proj", "mlstm_cell", "proj_down"):
+            self.add_module(name, getattr(layer, name))
+        self.learnable_skip = layer.learnable_skip
+        self.direction = getattr(layer, "direction", None)
+        self._cfg = (siging, kernel_dtype, one_launch, amp_dtype)
+
+    def forward(self, x):
+        import contextlib
+
+        siging, kernel_dtype, one_launch, amp_dtype = self._cfg
+        # the caller's autocast state, re-entered WITHOUT the weight-cast cache: inside a graph every replay must
+        # re-round the current fp32 weights (a cached fp16 copy would freeze them at their capture-time values)
+        ctx = (torch.autocast("cuda", dtype=amp_dtype, cache_enabled=False) if amp_dtype is not None
+               else contextlib.nullcontext())
+        with ctx:
+            return mlstm_branch_b200(self, x, siging=siging, kernel_dtype=kernel_dtype, one_launch=one_launch)
+
+
+class _LayerModule(torch.nn.Module):
+    """A whole ViLLayer (vision_lstm2.py:331-341: x + mlstm_branch(norm(x)), then + ffn(ffn_norm(.))) under one parent for
+    ``torch.cuda.make_graphed_callables``; runs the layer's OWN class forward, so whatever is bound on the instance
+    (the fused branch, the fused RMSNorms) is what gets captured."""
+
+    def __init__(self, layer, amp_dtype):
+        super().__init__()
+        self.add_module("layer", layer)
+        self._amp = amp_dtype
+
+    def forward(self, x):
+        import contextlib
+
+        ctx = (torch.autocast("cuda", dtype=self._amp, cache_enabled=False) if self._amp is not None
+               else contextlib.nullcontext())
+        with ctx:
+            return type(self.layer).forward(self.layer, x)
+
+
+class _Graphed:
+    """Training-time CUDA graphs of a callable of one (B, S, C) tensor: one forward and one backward graph per
+    (input shape, dtype, autocast dtype), built lazily by ``torch.cuda.make_graphed_callables`` at the first training
+    call.  A ViLLayer is ~70 kernel launches forward + backward and ~3 ms of host time in eager PyTorch whatever its
+    size; at the models' S = 100 / 400 stages that is several times its GPU time (0.5 / 0.9 ms for the mLSTM branch at 32
+    images), and with 20 layers per step the host, not the GPU, bounds a training step.  The graphs run the same
+    kernels on the same (live) parameters and are bit-identical to the eager code, step after optimizer step
+    (tests/test_cell_gpu.py) -- the module is rebuilt with the autocast weight-cast cache off, so every replay
+    re-rounds the current fp32 weights.  Calls without gradients, on the CPU, in a multi-process (DDP) job, during
+    someone else's capture, with stochastic depth active (its batch selection is data dependent) or with more than ``max_tokens`` tokens (GPU-bound
+    anyway, and their activations would stay resident in the graph's private pool) run eagerly."""
+
+    def __init__(self, layer, max_tokens=65536, max_graphs=4):
+        self.layer = layer
+        self.max_tokens, self.max_graphs = max_tokens, max_graphs
+        self._graphs = {}
+
+    def __getstate__(self):  # graphs are not picklable / copyable: a copied or loaded model rebuilds them lazily
+        d = self.__dict__.copy()
+        d["_graphs"] = {}
+        return d
+
+    def _eager(self, x):
+        raise NotImplementedError
+
+    def _module(self, amp):
+        raise NotImplementedError
+
+    def _graphable(self, x) -> bool:
+        if (torch.distributed.is_available() and torch.distributed.is_initialized()
+                and torch.distributed.get_world_size() > 1):
+            # single-process training only: a capture started lazily inside DDP's forward is invalidated by the
+            # process group's watchdog thread (global capture mode), and make_graphed_callables wants to run
+            # before the DDP wrapper exists (measured: cudaErrorStreamCaptureInvalidated at world size 2)
+            return False
+        return (x.is_cuda and torch.is_grad_enabled() and x.requires_grad and x.dim() == 3
+                and x.shape[0] * x.shape[1] <= self.max_tokens and not torch.cuda.is_current_stream_capturing())
+
+    def __call__(self, x):
+        if not self._graphable(x):
+            return self._eager(x)
+        amp = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else None
+        key = (tuple(x.shape), x.dtype, amp, x.device.index, self.layer.training)
+        g = self._graphs.get(key)
+        if g is None:
+            if len(self._graphs) >= self.max_graphs:
+                return self._eager(x)
+            mod = self._module(amp)
+            mod.train(self.layer.training)
+            sample = x.detach().clone().requires_grad_(True)
+            with torch.autocast("cuda", enabled=False):  # (make_graphed_callables refuses to run under a caching autocast)
+                g = torch.cuda.make_graphed_callables(mod, (sample,), allow_unused_input=True)
+            self._graphs[key] = g
+        return g(x)
+
+
+class _GraphedBranch(_Graphed):
+    """``layer.mlstm_branch`` as CUDA graphs (layers without the ViLLayer forward around the branch)."""
+
+    def __init__(self, layer, siging, kernel_dtype, one_launch, **kw):
+        super().__init__(layer, **kw)
+        self.cfg = (siging, kernel_dtype, one_launch)
+
+    def _eager(self, x):
+        siging, kernel_dtype, one_launch = self.cfg
+        return mlstm_branch_b200(self.layer, x, siging=siging, kernel_dtype=kernel_dtype, one_launch=one_launch)
+
+    def _module(self, amp):
+        return _BranchModule(self.layer, *self.cfg, amp)
+
+
+class _GraphedLayer(_Graphed):
+    """``layer.forward`` of a whole ViLLayer as CUDA graphs: both residual branches, their RMSNorms and the adds."""
+
+    def _eager(self, x):
+        return type(self.layer).forward(self.layer, x)
+
+    def _module(self, amp):
+        return _LayerModule(self.layer, amp)
+
+    def _graphable(self, x) -> bool:
+        dp = getattr(self.layer, "drop_path", None)
+        stochastic = dp is not None and self.layer.training and float(getattr(dp, "drop_prob", 0.0)) > 0.0
+        return not stochastic and super()._graphable(x)
+
+
+def patch_layers(model: torch.nn.Module, siging=None, kernel_dtype: str = "bfloat16", one_launch: str = "auto",
+                 graphs: bool = False) -> int:
     """Rebind ``mlstm_branch`` of every ViLLayer-shaped module (``proj_up``, ``qk_proj``, ``v_proj``, ``mlstm_cell``,
     ``learnable_skip``, ``proj_down``; vision_lstm2.py:218-290) whose head geometry the fused output kernel covers to
     ``mlstm_branch_b200``.  Parameters and state-dict keys are untouched.  Returns the number of layers rebound.
@@ -485,7 +615,9 @@ def patch_layers(model: torch.nn.Module, siging=None, kernel_dtype: str = "bfloa
     The overrides are ``functools.partial`` objects over module-level functions, so a patched model (or its EMA
     copy) survives ``copy.deepcopy`` and the whole-module ``torch.save`` / ``torch.load`` the reference trainer
     uses for last.pt / best.pt (ultralytics/engine/trainer.py:517-540): the partial's bound module is pickled as
-    part of the same object graph and re-bound to the loaded / copied module."""
+    part of the same object graph and re-bound to the loaded / copied module.  ``graphs=True`` additionally makes the
+    training forward / backward of every such layer replay as CUDA graphs (``_GraphedLayer`` bound as ``layer.forward``
+    for a full ViLLayer, ``_GraphedBranch`` as ``layer.mlstm_branch`` otherwise; see ``_Graphed``)."""
     import functools
 
     n = 0
@@ -496,7 +628,13 @@ def patch_layers(model: torch.nn.Module, siging=None, kernel_dtype: str = "bfloa
         if not cellout_supported(cell.num_heads, cell.dim // cell.num_heads):
             continue
         sig = _cell_uses_siging(cell) if siging is None else bool(siging)
-        mod.mlstm_branch = functools.partial(_branch_entry, mod, siging=sig, kernel_dtype=kernel_dtype, one_launch=one_launch)
+        whole_layer = graphs and all(hasattr(mod, a) for a in ("norm", "ffn_norm", "ffn", "drop_path"))
+        if graphs and not whole_layer:
+            mod.mlstm_branch = _GraphedBranch(mod, sig, kernel_dtype, one_launch)
+        else:
+            mod.mlstm_branch = functools.partial(_branch_entry, mod, siging=sig, kernel_dtype=kernel_dtype, one_launch=one_launch)
+        if whole_layer:
+            mod.forward = _GraphedLayer(mod)
         for norm in (getattr(mod, "norm", None), getattr(mod, "ffn_norm", None)):  # the RMSNorms in front of the branches
             if (isinstance(norm, torch.nn.RMSNorm) and len(norm.normalized_shape) == 1
                     and norm.normalized_shape[0] in RMSNORM_DIMS):
