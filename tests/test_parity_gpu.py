@@ -103,6 +103,13 @@ def test_golden_fp32(pkg, path):
         got = {k: v[:, :, :S] for k, v in got.items()}
     else:
         got = _run(pkg, inp, torch.float32, L=L, states=bool(st))
+        # the vectors the forward saves for the backward are the reference's own (vecN_out = max(|q.n|, exp(-m)),
+        # fw.py:208-210, and vecM_out, fw.py:178-184)
+        t = {k: v.float().cuda() for k, v in inp.items()}
+        kw = dict(c_initial=t["c0"], n_initial=t["n0"], m_initial=t["m0"]) if st else {}
+        _, n_out, m_out, _, _ = pkg.mlstm_chunkwise_fw(t["q"], t["k"], t["v"], t["i"], t["f"], chunk_size=L, **kw)
+        got.update(n_out=n_out.double().cpu(), m_out=m_out.double().cpu())
+        want.update(n_out=torch.from_numpy(z["n_out"]), m_out=torch.from_numpy(z["m_out"]))
     _assert_close(got, want, TOL[torch.float32], os.path.basename(path))
 
 
