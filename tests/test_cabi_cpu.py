@@ -246,3 +246,14 @@ def test_graphed_patch_survives_deepcopy_and_torch_save(tmp_path):
         assert br.layer is m[0] and br._graphs == {} and br.cfg[1:] == ("bfloat16", "auto")
         with pytest.raises(RuntimeError, match="no CPU path"):
             br(torch.randn(1, 16, 128, dtype=m[0].norm.weight.dtype))
+
+
+def test_call_plan_table_is_bounded():
+    """Callers with ever-changing shapes must not grow the per-thread plan table without bound."""
+    import xlstm_yolo_clean_b200.backend as be
+
+    d = be._plans()
+    d.clear()
+    for i in range(be._MAX_PLANS):
+        d[("dummy", i)] = None
+    assert len(be._plans()) == 0

@@ -121,10 +121,18 @@ _tls = threading.local()
 _raw_stream = torch._C._cuda_getCurrentRawStream
 
 
+_MAX_PLANS = 1024
+
+
 def _plans() -> dict:
+    """Per-thread call plans (argument structs with everything but the pointers filled in), keyed by the call's
+    signature.  A training loop cycles through a few dozen signatures; a caller with ever-changing shapes (variable
+    sequence lengths at inference) would otherwise grow the table without bound, so it is simply dropped when full."""
     d = getattr(_tls, "plans", None)
     if d is None:
         d = _tls.plans = {}
+    elif len(d) >= _MAX_PLANS:
+        d.clear()
     return d
 
 
