@@ -410,12 +410,15 @@ def model_train_block(pkg, dist, dev, rank, world, steps=3, warmup=2):
         args = types.SimpleNamespace(yaml="640-base256.yaml", batch=32, steps=steps, warmup=warmup, check_finite=False, profile=False)
         with contextlib.redirect_stdout(sys.stderr):
             MB._import_reference()
-            for name in (["b200_fused"] + (["b200_fused_graphs", "reference_native_custbw_on_gpu"] if world == 1 else [])):
+            for name in (["b200_fused"] + (["b200_fused_graphs", "b200_fused_graphs_keep_activations",
+                                              "reference_native_custbw_on_gpu"] if world == 1 else [])):
                 model = MB._build_model(args.yaml, dev)
                 if name.startswith("b200_fused"):
                     # siging derived from the model's own CUDA backend; "_graphs": the layers' training forward /
-                    # backward replay as CUDA graphs (single-process only, vil._Graphed)
-                    pkg.patch_model(model, fused=True, graphs=name.endswith("_graphs"))
+                    # backward replay as CUDA graphs (single-process only, vil._Graphed); "_keep_activations": the
+                    # S = 6400 block pairs are not re-run inside the backward (the reference checkpoints them to fit
+                    # 40-80 GB parts; the step peaks at ~40 of the B200's 180 GB without)
+                    pkg.patch_model(model, fused=True, graphs="_graphs" in name, keep_activations="_keep_activations" in name)
                 else:
                     MB._set_backend(model, "native_custbw")
                 res = MB._train_loop(model, MB._batch(32, dev, seed=rank), args, world, dev)
