@@ -457,8 +457,18 @@ def test_graphed_branch_is_bit_identical_to_eager_over_optimizer_steps(pkg, S, r
         for a, b in zip(eager.parameters(), graphed.parameters()):
             assert torch.equal(a, b), it
     assert len(graphed.mlstm_branch._graphs) == 1
-    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):  # no gradients: eager path, same function
-        assert torch.equal(graphed.mlstm_branch(x), eager.mlstm_branch(x))
+    for it in range(3):  # no gradients: a forward-only graph, same function, live parameters
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+            x = torch.randn(8, S, 128, device=dev).half()
+            a, b = graphed.mlstm_branch(x), eager.mlstm_branch(x)
+            assert torch.equal(a, b), it
+            assert a.data_ptr() != graphed.mlstm_branch(x).data_ptr()  # results are copies, not the static buffer
+        with torch.no_grad():
+            for pa, pb in zip(eager.parameters(), graphed.parameters()):
+                d = 0.01 * torch.randn_like(pa)
+                pa.add_(d)
+                pb.add_(d)
+    assert len(graphed.mlstm_branch._graphs) == 2
     clone = copy.deepcopy(graphed)  # graphs do not travel with copies; the copy builds its own
     assert clone.mlstm_branch._graphs == {} and clone.mlstm_branch.layer is clone
 
@@ -514,7 +524,13 @@ def test_graphed_whole_layer_is_bit_identical_to_eager_over_optimizer_steps(pkg)
         for a, b in zip(eager.parameters(), graphed.parameters()):
             assert torch.equal(a, b), it
     assert len(graphed.forward._graphs) == 1
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):  # inference: forward-only graph of the whole layer
+        graphed.eval(), eager.eval()
+        xe = torch.randn(1, 400, 256, device=dev)
+        assert torch.equal(graphed(xe), eager(xe)) and torch.equal(graphed(xe), eager(xe))
+        graphed.train(), eager.train()
+    assert len(graphed.forward._graphs) == 2
     graphed.drop_path.drop_prob = 0.1  # stochastic depth selects samples by value: eager
     with torch.autocast("cuda", dtype=torch.float16):
         graphed(x.clone().requires_grad_(True))
-    assert len(graphed.forward._graphs) == 1
+    assert len(graphed.forward._graphs) == 2

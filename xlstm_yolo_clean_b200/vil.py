@@ -526,11 +526,14 @@ class _Graphed:
     images), and with 20 layers per step the host, not the GPU, bounds a training step.  The graphs run the same
     kernels on the same (live) parameters and are bit-identical to the eager code, step after optimizer step
     (tests/test_cell_gpu.py) -- the module is rebuilt with the autocast weight-cast cache off, so every replay
-    re-rounds the current fp32 weights.  Calls without gradients, on the CPU, in a multi-process (DDP) job, during
-    someone else's capture, with stochastic depth active (its batch selection is data dependent) or with more than ``max_tokens`` tokens (GPU-bound
-    anyway, and their activations would stay resident in the graph's private pool) run eagerly."""
+    re-rounds the current fp32 weights.  Calls WITHOUT gradients (inference, the first pass of a checkpointed block)
+    replay a forward-only graph captured the same way: static input copy in, clone of the static output out (a
+    batch-1 forward of base192 is 20 layers x ~0.6 ms of host time around ~0.1 ms of GPU work).  Calls on the CPU, in a
+    multi-process job, during someone else's capture, with stochastic depth active (its batch selection is data
+    dependent) or with more than ``max_tokens`` tokens (GPU-bound anyway, and their activations would stay resident
+    in the graph's private pool) run eagerly."""
 
-    def __init__(self, layer, max_tokens=65536, max_graphs=4):
+    def __init__(self, layer, max_tokens=65536, max_graphs=6):
         self.layer = layer
         self.max_tokens, self.max_graphs = max_tokens, max_graphs
         self._graphs = {}
@@ -553,25 +556,50 @@ class _Graphed:
             # process group's watchdog thread (global capture mode), and make_graphed_callables wants to run
             # before the DDP wrapper exists (measured: cudaErrorStreamCaptureInvalidated at world size 2)
             return False
-        return (x.is_cuda and torch.is_grad_enabled() and x.requires_grad and x.dim() == 3
-                and x.shape[0] * x.shape[1] <= self.max_tokens and not torch.cuda.is_current_stream_capturing())
+        return (x.is_cuda and x.dim() == 3 and x.shape[0] * x.shape[1] <= self.max_tokens
+                and not torch.cuda.is_current_stream_capturing())
+
+    def _capture_forward(self, mod, x):
+        """Forward-only graph: (graph, static input, static output)."""
+        static_in = x.detach().clone()
+        side = torch.cuda.Stream(device=x.device)
+        side.wait_stream(torch.cuda.current_stream(x.device))
+        with torch.no_grad(), torch.autocast("cuda", enabled=False), torch.cuda.stream(side):
+            for _ in range(2):  # warm-up outside the capture: plans, tensor maps, cuDNN / cuBLAS workspaces
+                mod(static_in)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                static_out = mod(static_in)
+        torch.cuda.current_stream(x.device).wait_stream(side)
+        return g, static_in, static_out
 
     def __call__(self, x):
         if not self._graphable(x):
             return self._eager(x)
+        train = torch.is_grad_enabled() and x.requires_grad
+        if not train and torch.is_grad_enabled() and any(p.requires_grad for p in self.layer.parameters()):
+            return self._eager(x)  # gradients w.r.t. the parameters only: rare, not worth a third kind of graph
         amp = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else None
-        key = (tuple(x.shape), x.dtype, amp, x.device.index, self.layer.training)
+        key = (tuple(x.shape), x.dtype, amp, x.device.index, self.layer.training, train)
         g = self._graphs.get(key)
         if g is None:
             if len(self._graphs) >= self.max_graphs:
                 return self._eager(x)
             mod = self._module(amp)
             mod.train(self.layer.training)
-            sample = x.detach().clone().requires_grad_(True)
-            with torch.autocast("cuda", enabled=False):  # (make_graphed_callables refuses to run under a caching autocast)
-                g = torch.cuda.make_graphed_callables(mod, (sample,), allow_unused_input=True)
+            if train:
+                sample = x.detach().clone().requires_grad_(True)
+                with torch.autocast("cuda", enabled=False):  # (make_graphed_callables refuses a caching autocast)
+                    g = torch.cuda.make_graphed_callables(mod, (sample,), allow_unused_input=True)
+            else:
+                g = self._capture_forward(mod, x)
             self._graphs[key] = g
-        return g(x)
+        if train:
+            return g(x)
+        graph, static_in, static_out = g
+        static_in.copy_(x)
+        graph.replay()
+        return static_out.clone()
 
 
 class _GraphedBranch(_Graphed):
