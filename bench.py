@@ -435,6 +435,38 @@ def model_train_block(pkg, dist, dev, rank, world, steps=3, warmup=2):
         return {"error": repr(e)[:300]}
 
 
+def model_infer_block(pkg, dev):
+    """BASELINE configs 1 and 5 through the reference's own model (N = 1 only): 640-base192 single-image forward latency
+    and 640-base384 forward throughput at 16 images per GPU, fp16 autocast, no_grad, with patch_model(fused=True) and with
+    the layers' forward additionally replayed as CUDA graphs (graphs=True)."""
+    import contextlib
+    import types
+
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        import model_bench as MB
+
+        if not os.path.isdir(os.path.join(MB.REF, "mlstm_kernels")):
+            return {"unavailable": "baseline/_ref is not staged (tools/stage_reference.sh)"}
+        out = {"amp": "fp16", "step": "model(x) under no_grad + autocast, synthetic images resident on the device"}
+        with contextlib.redirect_stdout(sys.stderr):
+            MB._import_reference()
+            for cfg, yaml_name, batch, steps in (("config1_base192_b1", "640-base192.yaml", 1, 20), ("config5_base384_b16", "640-base384.yaml", 16, 8)):
+                args = types.SimpleNamespace(yaml=yaml_name, batch=batch, steps=steps, warmup=4)
+                out[cfg] = {}
+                for name, graphs in (("b200_fused", False), ("b200_fused_graphs", True)):
+                    model = MB._build_model(yaml_name, dev)
+                    pkg.patch_model(model, fused=True, graphs=graphs)
+                    res = MB._infer_loop(model, MB._batch(batch, dev, seed=0), args, dev)
+                    out[cfg][name] = {"ms_per_step": res["ms_per_step"], "img_per_s": batch / (res["ms_per_step"] * 1e-3),
+                                      "out_checksum": res["out_checksum"]}
+                    del model
+                    torch.cuda.empty_cache()
+        return out
+    except Exception as e:  # the block must never break the JSON line
+        return {"error": repr(e)[:300]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -709,6 +741,7 @@ def main():
     mtrain = None
     if not args.no_model_train:
         mtrain = model_train_block(pkg, dist, dev, rank, world)
+    minfer = model_infer_block(pkg, dev) if (world == 1 and not args.no_model_train) else None
 
     if rank == 0:
         line = {
@@ -735,6 +768,8 @@ def main():
             line["ddp_proxy"] = proxy
         if mtrain is not None:
             line["model_train"] = mtrain
+        if minfer is not None:
+            line["model_infer"] = minfer
         if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only (at N > 1 the other ranks would spin in a barrier)
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line))
