@@ -531,7 +531,8 @@ class _Graphed:
     batch-1 forward of base192 is 20 layers x ~0.6 ms of host time around ~0.1 ms of GPU work).  Calls on the CPU, in a
     multi-process job, during someone else's capture, with stochastic depth active (its batch selection is data
     dependent) or with more than ``max_tokens`` tokens (GPU-bound anyway, and their activations would stay resident
-    in the graph's private pool) run eagerly."""
+    in the graph's private pool) run eagerly.  One caller at a time per model: a graph owns its static buffers, so two
+    threads driving the SAME patched model concurrently must not both use graphs (separate model copies are fine)."""
 
     def __init__(self, layer, max_tokens=65536, max_graphs=6):
         self.layer = layer
