@@ -726,6 +726,8 @@ def patch_model(model: torch.nn.Module, name: str = KERNEL_NAME, mode: str = "tr
     """
     from mlstm_kernels.torch.backend_module import mLSTMBackend, mLSTMBackendConfig
 
+    if graphs and not fused:
+        raise ValueError("graphs=True replays the FUSED layers as CUDA graphs: pass fused=True as well")
     base = register(name)
     n = n_sig = 0
     for mod in model.modules():
