@@ -534,3 +534,37 @@ def test_graphed_whole_layer_is_bit_identical_to_eager_over_optimizer_steps(pkg)
     with torch.autocast("cuda", dtype=torch.float16):
         graphed(x.clone().requires_grad_(True))
     assert len(graphed.forward._graphs) == 2
+
+
+@pytest.mark.parametrize("reentrant", [True, False])
+def test_graphed_layer_inside_a_checkpointed_block(pkg, reentrant):
+    """The reference checkpoints its S = 6400 block pairs (vision_lstm2.py:1071-1078): the first pass runs without
+    gradients (forward-only graph), the re-computation runs inside the backward pass (never builds a graph there).
+    Same losses, gradients and parameters as the eager layer."""
+    import copy
+
+    from torch.utils.checkpoint import checkpoint
+
+    dev = torch.device("cuda:0")
+    torch.manual_seed(6)
+    eager = _FullLayer(256, 8, _Dir("ROWWISE_FROM_TOP_LEFT")).to(dev)
+    eager.conv.seqlens = [10, 10]
+    graphed = copy.deepcopy(eager)
+    graphed.conv.seqlens = [10, 10]
+    assert pkg.patch_layers(eager) == 1 and pkg.patch_layers(graphed, graphs=True) == 1
+    opts = [torch.optim.SGD(m.parameters(), lr=0.05) for m in (eager, graphed)]
+    for it in range(3):
+        x = torch.randn(4, 100, 256, device=dev)
+        res = []
+        for m, opt in zip((eager, graphed), opts):
+            xi = x.clone().requires_grad_(True)
+            opt.zero_grad()
+            with torch.autocast("cuda", dtype=torch.float16):
+                y = checkpoint(m, xi, use_reentrant=reentrant)
+            loss = (y.float() ** 2).mean()
+            loss.backward()
+            opt.step()
+            res.append((loss.detach(), xi.grad))
+        assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]), it
+        for a, b in zip(eager.parameters(), graphed.parameters()):
+            assert torch.equal(a, b), it

@@ -574,17 +574,31 @@ class _Graphed:
         torch.cuda.current_stream(x.device).wait_stream(side)
         return g, static_in, static_out
 
+    @staticmethod
+    def _saved_tensor_hooks_active() -> bool:
+        """Someone (non-reentrant activation checkpointing, CPU offload) is intercepting what autograd saves: the
+        activations of a graph live in its private pool and must not be routed through such hooks."""
+        top = getattr(torch._C._autograd, "_top_saved_tensors_default_hooks", None)
+        try:
+            return top is not None and top(True) is not None
+        except Exception:  # noqa: BLE001 -- private API: when in doubt, stay eager
+            return True
+
     def __call__(self, x):
         if not self._graphable(x):
             return self._eager(x)
         train = torch.is_grad_enabled() and x.requires_grad
+        if train and self._saved_tensor_hooks_active():
+            return self._eager(x)
         if not train and torch.is_grad_enabled() and any(p.requires_grad for p in self.layer.parameters()):
             return self._eager(x)  # gradients w.r.t. the parameters only: rare, not worth a third kind of graph
         amp = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else None
         key = (tuple(x.shape), x.dtype, amp, x.device.index, self.layer.training, train)
         g = self._graphs.get(key)
         if g is None:
-            if len(self._graphs) >= self.max_graphs:
+            # never build from inside a running backward pass (the re-computation of a checkpointed block,
+            # vision_lstm2.py:1071-1078, calls the layer there): that call stays eager
+            if len(self._graphs) >= self.max_graphs or torch._C._current_graph_task_id() != -1:
                 return self._eager(x)
             mod = self._module(amp)
             mod.train(self.layer.training)
